@@ -1,0 +1,36 @@
+"""Golden-fixture case table shared by make_golden.py (reference side) and the tests (oracle / CUDA side)."""
+from contextflow_b200.synth import CONFIGS, variant
+
+CASES = {
+    # the four BASELINE.json configurations, full architecture, small batch
+    'cfg1': dict(conf=CONFIGS['cfg1'], B=4),
+    'cfg2': dict(conf=CONFIGS['cfg2'], B=4),
+    'cfg3': dict(conf=CONFIGS['cfg3'], B=3),
+    'cfg4': dict(conf=CONFIGS['cfg4'], B=5),
+    # ActNorm data-dependent initialisation from the first batch (actnorm.py:28-35,46,53)
+    'cfg1_init': dict(conf=CONFIGS['cfg1'], B=6, fresh_actnorm=True),
+    'cfg4_init': dict(conf=CONFIGS['cfg4'], B=7, fresh_actnorm=True),
+    'cfg2_init': dict(conf=variant('cfg2', num_blocks=2, block_size=1), B=5, fresh_actnorm=True),
+    # encoder / embedding variants, reduced depth
+    'mnist_onehot_uniform': dict(conf=variant('cfg1', generalist=False, contextflow=True, enc_emb='onehot', enc_type='uniform',
+                                              num_blocks=2, block_size=1, contexts=[8, 3]), B=3),
+    'mnist_eye_uniform': dict(conf=variant('cfg1', generalist=False, contextflow=True, enc_emb='eye', enc_type='uniform',
+                                           num_blocks=1, block_size=2, contexts=[64]), B=3),
+    'mnist_eye_vardeq2': dict(conf=variant('cfg1', generalist=False, contextflow=True, enc_emb='eye', enc_type='vardeq',
+                                           num_blocks=1, block_size=1, contexts=[7, 5]), B=3),
+    'mnist_embed_probsample': dict(conf=variant('cfg1', generalist=False, contextflow=True, enc_emb='embed', enc_type='probsample',
+                                                num_blocks=1, block_size=1, contexts=[6, 4]), B=3),
+    'mnist_embed_eyesample': dict(conf=variant('cfg1', generalist=False, contextflow=True, enc_emb='embed', enc_type='eyesample',
+                                               num_blocks=1, block_size=1, contexts=[6]), B=3),
+    # (onehot|eye) x eyesample raise inside the reference itself (int64 context into nn.Linear), so they are not cases
+    'atm_argmax2': dict(conf=variant('cfg3', num_blocks=1, block_size=2, contexts=[9, 5], data_size=(6, 16, 1)), B=4),
+    # conventional (concatenated) context conditioning: contextflow=False specialists (coupling.py:47, conv1x1.py:46-49)
+    'cifar_conventional': dict(conf=variant('cfg2', contextflow=False, num_blocks=2, block_size=1), B=3),
+    'smap_conventional': dict(conf=variant('cfg4', generalist=False, contextflow=False, enc_emb='onehot', enc_type='vardeq',
+                                           num_blocks=1, block_size=2, contexts=[4, 2]), B=3),
+    # time-series conv coupling (3,1) reflect kernels; MSL-shaped windows
+    'msl_conv': dict(conf=variant('cfg4', dataset='msl', coupling='conv', data_size=(55, 8, 1), contexts=[27],
+                                  num_blocks=1, block_size=2), B=3),
+    # MNIST at the literal 28x28 shape (BASELINE configs[0])
+    'mnist28': dict(conf=variant('cfg1', data_size=(1, 28, 28)), B=2),
+}
