@@ -1,0 +1,89 @@
+"""ctypes binding of libcfpp.so (include/cfpp.h).  There is no CPU fallback: a missing library is a hard error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libcfpp.so')
+
+MAX_CTX = 8
+ENC_MAXC = 64
+EMB = dict(onehot=0, eye=1, embed=2, dense=3)
+ENC = dict(eyesample=0, uniform=1, vardeq=2, argmax=3, probsample=4)
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+
+class VitDesc(C.Structure):
+    _fields_ = [('Cin', i32), ('H', i32), ('W', i32), ('p1', i32), ('p2', i32),
+                ('T', i32), ('depth', i32), ('n_tok', i32), ('patch_dim', i32),
+                ('ln0_w', vp), ('ln0_b', vp), ('pe_wt', vp), ('pe_b', vp), ('ln1_w', vp), ('ln1_b', vp),
+                ('pos', vp), ('lnf_w', vp), ('lnf_b', vp), ('layers', vp)]
+
+
+class EncDesc(C.Structure):
+    _fields_ = [('emb', i32), ('type', i32), ('n_ctx', i32), ('C', i32),
+                ('card', i32 * MAX_CTX), ('bits', i32 * MAX_CTX), ('emb_dim', i32),
+                ('emb_w', vp * MAX_CTX), ('dense', vp), ('qbins', vp), ('ldj_per_dim', vp), ('temperature', vp),
+                ('inner_dim', i32), ('inner_w', vp * MAX_CTX),
+                ('fc', vp * 2), ('fc_logabsdet', vp * 2), ('an_t', vp * 2), ('an_logs', vp * 2),
+                ('cw1t', vp * 2), ('cb1', vp * 2), ('cw2t', vp * 2), ('cb2', vp * 2), ('cw3t', vp * 2), ('cb3', vp * 2)]
+
+
+_SIGNATURES = {
+    'cfpp_version': (i32, []),
+    'cfpp_last_error': (C.c_char_p, []),
+    'cfpp_launch_count': (i64, []),
+    'cfpp_squeeze_fwd': (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    'cfpp_squeeze_inv': (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    'cfpp_permute_fwd': (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    'cfpp_slice_channels': (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
+    'cfpp_add_fwd': (i32, [vp, vp, vp, i64, vp]),
+    'cfpp_normalize_fwd': (i32, [vp, vp, i64, f32, f32, vp]),
+    'cfpp_logit_fwd': (i32, [vp, vp, vp, i32, i32, vp]),
+    'cfpp_augment_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    'cfpp_prologue_fwd': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32, f32, vp]),
+    'cfpp_slogdet': (i32, [vp, i32, vp, vp]),
+    'cfpp_conv1x1_fwd': (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, f32, i32, i32, i32, vp]),
+    'cfpp_actnorm_fwd': (i32, [vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp]),
+    'cfpp_actnorm_stats': (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    'cfpp_coupling_fwd': (i32, [vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, vp]),
+    'cfpp_conv_cond_fwd': (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    'cfpp_vit_layer_floats': (i64, [i32]),
+    'cfpp_vit_cond_fwd': (i32, [vp, i64, vp, i32, vp, C.POINTER(VitDesc), i32, vp]),
+    'cfpp_gmm_logprob': (i32, [vp, i64, vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, vp]),
+    'cfpp_gmm_workspace_floats': (i64, [i32, i32, i32, i32]),
+    'cfpp_ctx_encode': (i32, [vp, vp, vp, vp, C.POINTER(EncDesc), i32, i32, vp]),
+    'cfpp_embed_lookup': (i32, [vp, C.POINTER(vp), i32, i32, vp, i32, vp]),
+    'cfpp_linear_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    'cfpp_ldj_accumulate': (i32, [vp, vp, i32, i32, i32, vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded CUDA library; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                '(nvcc, sm_100a).  contextflow_b200 has no CPU or PyTorch fallback for its kernels.')
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = ''):
+    if rc != 0:
+        msg = lib().cfpp_last_error().decode(errors='replace')
+        raise RuntimeError(f'libcfpp {what} failed (status {rc}): {msg}')
+
+
+def launch_count() -> int:
+    return int(lib().cfpp_launch_count())

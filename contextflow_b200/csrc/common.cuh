@@ -1,0 +1,66 @@
+// Shared device/host helpers for libcfpp (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/cfpp.h"
+
+namespace cfpp {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return CFPP_ERR_CUDA; }
+  return CFPP_OK;
+}
+
+#define CFPP_REQUIRE(cond, ...) do { if (!(cond)) { ::cfpp::set_error(__VA_ARGS__); return CFPP_ERR_ARG; } } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over a group of G consecutive threads (G multiple of 32, G <= blockDim). `red` needs blockDim/32 floats.
+// Every thread of the group receives the total.  All threads of the block must call (uses __syncthreads).
+template <int MAXW = 32>
+__device__ __forceinline__ float group_sum(float v, int G, float* red) {
+  v = warp_sum(v);
+  if (G == 32) return v;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  const int wpg = G >> 5, g0 = (w / wpg) * wpg;
+  float s = 0.f;
+  for (int i = 0; i < wpg; ++i) s += red[g0 + i];
+  __syncthreads();
+  return s;
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {   // streaming 128-bit load, no L1 allocation
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float softplus_f(float x) {   // F.softplus(beta=1, threshold=20)
+  return x > 20.f ? x : log1pf(expf(x));
+}
+
+constexpr float kHalfLog2Pi = 0.91893853320467274178f;
+
+}  // namespace cfpp

@@ -1,0 +1,85 @@
+// The fused memory-bound affine-coupling transform (layers/coupling.py:50-66, :131-148).
+// One HBM pass: read x and h once (128-bit streaming loads), write z once, reduce log_s into ldj[b] with warp
+// shuffles + one shared-memory hop.  Algorithmic traffic: 12*C*HW bytes per sample.
+#include "common.cuh"
+
+namespace cfpp {
+
+__device__ __forceinline__ void couple1(float x1, float t, float r, float& z1, float& acc) {
+  const float ls = 2.0f * tanhf(r * 0.5f);      // log_s = logs_range * tanh(h / logs_range), logs_range = 2
+  z1 = fmaf(x1, expf(ls), t);
+  acc += ls;
+}
+
+// G threads cooperate on one sample; blockDim/G samples per CTA.
+template <bool VEC>
+__global__ void __launch_bounds__(256) coupling_kernel(const float* __restrict__ x, const float* __restrict__ h,
+                                                       const float* __restrict__ add, const float* __restrict__ logp_c,
+                                                       float logp_scale, float* __restrict__ z, float* __restrict__ ldj,
+                                                       int B, int C, int HW, int G) {
+  __shared__ float red[32];
+  const int spc = blockDim.x / G;
+  const int s = threadIdx.x / G, g = threadIdx.x % G;
+  const int64_t b = (int64_t)blockIdx.x * spc + s;
+  const bool valid = b < B;
+  const int Ch = C / 2;
+  const int64_t n = (int64_t)Ch * HW;           // elements per half
+  float acc = 0.f;
+  if (valid) {
+    const float* xb = x + b * 2 * n; const float* hb = h + b * 2 * n; float* zb = z + b * 2 * n;
+    const float* ab = add ? add + b * C : nullptr;
+    if (VEC) {
+      const int n4 = (int)(n / 4), hw4 = HW / 4;
+      const float4* x0 = reinterpret_cast<const float4*>(xb); const float4* x1 = x0 + n4;
+      const float4* ht = reinterpret_cast<const float4*>(hb); const float4* hr = ht + n4;
+      float4* z0 = reinterpret_cast<float4*>(zb); float4* z1 = z0 + n4;
+#pragma unroll 2
+      for (int i = g; i < n4; i += G) {
+        const float4 a0 = ldg_stream(x0 + i), a1 = ldg_stream(x1 + i);
+        float4 t = ldg_stream(ht + i), r = ldg_stream(hr + i);
+        if (ab) {
+          const int ch = i / hw4;
+          const float at = ab[ch], ar = ab[Ch + ch];
+          t.x += at; t.y += at; t.z += at; t.w += at;
+          r.x += ar; r.y += ar; r.z += ar; r.w += ar;
+        }
+        float4 o;
+        couple1(a1.x, t.x, r.x, o.x, acc); couple1(a1.y, t.y, r.y, o.y, acc);
+        couple1(a1.z, t.z, r.z, o.z, acc); couple1(a1.w, t.w, r.w, o.w, acc);
+        stg_stream(z0 + i, a0);
+        stg_stream(z1 + i, o);
+      }
+    } else {
+      for (int64_t i = g; i < n; i += G) {
+        float t = hb[i], r = hb[n + i];
+        if (ab) { const int ch = (int)(i / HW); t += ab[ch]; r += ab[Ch + ch]; }
+        float o;
+        couple1(xb[n + i], t, r, o, acc);
+        zb[i] = xb[i];
+        zb[n + i] = o;
+      }
+    }
+  }
+  acc = group_sum(acc, G, red);
+  if (valid && g == 0) ldj[b] = acc + (logp_c ? logp_scale * logp_c[b] : 0.f);
+}
+
+}  // namespace cfpp
+using namespace cfpp;
+
+extern "C" int cfpp_coupling_fwd(const float* x, const float* h, const float* add, const float* logp_c, float logp_scale,
+                                 float* z, float* ldj, int B, int C, int HW, void* stream) {
+  CFPP_REQUIRE(C >= 2 && C % 2 == 0 && HW >= 1, "coupling: C=%d must be even, HW=%d", C, HW);
+  if (B <= 0) return CFPP_OK;
+  const int64_t n = (int64_t)(C / 2) * HW;
+  const bool vec = (HW % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(z)) % 16 == 0);
+  const int64_t work = vec ? n / 4 : n;
+  int G = 32;
+  while (G < 256 && G * 4 < work) G <<= 1;
+  const int spc = 256 / G;
+  const int blocks = (int)((B + spc - 1) / spc);
+  if (vec) coupling_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, h, add, logp_c, logp_scale, z, ldj, B, C, HW, G);
+  else coupling_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, h, add, logp_c, logp_scale, z, ldj, B, C, HW, G);
+  return check_launch("coupling_fwd");
+}

@@ -1,0 +1,164 @@
+// Gaussian-mixture log-prob (base density and SplitPrior), layers/distributions/gaussian.py:142-161.
+//
+// out[b,m] = logsumexp_k( logmix[m,k] + sum_e [ -(x_be - mu)^2 / (2 sigma^2) - log sigma - 0.5 log 2pi ] )
+// mu = mG[m,k,e] (+ cm[b,m,k,d]),  sigma = softplus(sG[m,k,e] (+ cs[b,m,k,d])),  e = (d,h,w).
+//
+// A CTA keeps a tile of S samples in shared memory and walks all M*K components over it, so each component's
+// parameters are fetched from L2 once per S samples and x is read from HBM exactly once.  Without context the
+// sigma-dependent terms are hoisted into a per-parameter table by gmm_prepare_kernel (1/(2 sigma^2), sum_e log sigma),
+// leaving 3 FP32 ops per Gaussian evaluation; with per-sample context offsets sigma is a function of (b,m,k,e) and
+// is evaluated in place (SFU-bound).
+#include "common.cuh"
+
+namespace cfpp {
+
+// logmix[m,k] = log_softmax(log(clamp(softmax(wG[m])/sum, eps, 1-eps)))  (torch Categorical(probs) + MixtureSameFamily)
+__device__ float log_mix(const float* __restrict__ wrow, int K, int k) {
+  float mx = -INFINITY;
+  for (int i = 0; i < K; ++i) mx = fmaxf(mx, wrow[i]);
+  float den = 0.f;
+  for (int i = 0; i < K; ++i) den += expf(wrow[i] - mx);
+  float psum = 0.f;
+  for (int i = 0; i < K; ++i) psum += expf(wrow[i] - mx) / den;
+  const float eps = 1.1920928955078125e-07f;
+  float lmx = -INFINITY;
+  for (int i = 0; i < K; ++i) lmx = fmaxf(lmx, logf(fminf(fmaxf(expf(wrow[i] - mx) / den / psum, eps), 1.f - eps)));
+  float lse = 0.f, lk = 0.f;
+  for (int i = 0; i < K; ++i) {
+    const float l = logf(fminf(fmaxf(expf(wrow[i] - mx) / den / psum, eps), 1.f - eps));
+    lse += expf(l - lmx);
+    if (i == k) lk = l;
+  }
+  return lk - (lmx + logf(lse));
+}
+
+// ws layout: [A: MK*E] [LB: MK]   A = 1/(2 sigma^2), LB = logmix - sum_e log sigma - E*0.5*log(2 pi)
+__global__ void gmm_prepare_kernel(const float* __restrict__ sG, const float* __restrict__ wG, float* __restrict__ ws,
+                                   int MK, int K, int E, bool with_table) {
+  __shared__ float red[32];
+  const int mk = blockIdx.x;
+  float acc = 0.f;
+  if (with_table) {
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      const float sc = softplus_f(sG[(int64_t)mk * E + e]);
+      ws[(int64_t)mk * E + e] = 1.f / (2.f * sc * sc);
+      acc += logf(sc);
+    }
+    acc = group_sum(acc, blockDim.x, red);
+  }
+  if (threadIdx.x == 0)
+    ws[(int64_t)MK * E + mk] = log_mix(wG + (mk / K) * K, K, mk % K) - acc - (float)E * kHalfLog2Pi;
+}
+
+template <bool CTX, int S, int PK>
+__global__ void __launch_bounds__(256) gmm_kernel(const float* __restrict__ x, int64_t x_bstride, const float* __restrict__ mG,
+                                                  const float* __restrict__ sG, const float* __restrict__ ws,
+                                                  const float* __restrict__ ctx_off, const float* __restrict__ logp_c,
+                                                  float logp_scale, float* __restrict__ out, int B, int M, int K, int D, int HW) {
+  extern __shared__ float4 sm4[];
+  float* xs = reinterpret_cast<float*>(sm4);          // [S][E]
+  const int E = D * HW, MK = M * K;
+  float* comp = xs + (int64_t)S * E;                  // [S][MK]
+  const int b0 = blockIdx.x * S;
+  for (int idx = threadIdx.x; idx < S * E; idx += blockDim.x) {
+    const int s = idx / E, e = idx % E;
+    xs[idx] = (b0 + s < B) ? x[(int64_t)(b0 + s) * x_bstride + e] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const float* A = ws;
+  const float* LB = ws + (int64_t)MK * E;
+  const int ngroups = (MK + PK - 1) / PK;
+  for (int g = warp; g < ngroups; g += nwarps) {
+    float acc[PK][S];
+#pragma unroll
+    for (int j = 0; j < PK; ++j)
+#pragma unroll
+      for (int s = 0; s < S; ++s) acc[j][s] = 0.f;
+    const int mk0 = g * PK;
+    for (int e = lane; e < E; e += 32) {
+      float xv[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) xv[s] = xs[s * E + e];
+      const int d = CTX ? e / HW : 0;
+#pragma unroll
+      for (int j = 0; j < PK; ++j) {
+        const int mk = mk0 + j < MK ? mk0 + j : MK - 1;
+        const float mu = mG[(int64_t)mk * E + e];
+        if (!CTX) {
+          const float a = A[(int64_t)mk * E + e];
+#pragma unroll
+          for (int s = 0; s < S; ++s) { const float df = xv[s] - mu; acc[j][s] = fmaf(-a * df, df, acc[j][s]); }
+        } else {
+          const float sg = sG[(int64_t)mk * E + e];
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            const int bb = b0 + s < B ? b0 + s : B - 1;
+            const float* co = ctx_off + (int64_t)bb * 2 * MK * D + (int64_t)mk * D + d;     // 'b (p m k d)'
+            const float sc = softplus_f(sg + co[(int64_t)MK * D]);
+            const float df = xv[s] - (mu + co[0]);
+            acc[j][s] += -(df * df) / (2.f * sc * sc) - logf(sc);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PK; ++j)
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const float v = warp_sum(acc[j][s]);
+        if (lane == 0 && mk0 + j < MK) comp[s * MK + mk0 + j] = v + LB[mk0 + j];
+      }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < S * M; idx += blockDim.x) {
+    const int s = idx / M, m = idx % M;
+    if (b0 + s >= B) continue;
+    const float* c = comp + s * MK + m * K;
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, c[k]);
+    float se = 0.f;
+    for (int k = 0; k < K; ++k) se += expf(c[k] - mx);
+    out[(int64_t)(b0 + s) * M + m] = mx + logf(se) + (logp_c ? logp_scale * logp_c[b0 + s] : 0.f);
+  }
+}
+
+template <bool CTX, int S, int PK>
+static int launch_gmm(const float* x, int64_t bs, const float* mG, const float* sG, const float* ws, const float* co, const float* lp,
+                      float lps, float* out, int B, int M, int K, int D, int HW, cudaStream_t st) {
+  const int E = D * HW, MK = M * K;
+  const size_t smem = ((size_t)S * E + (size_t)S * MK) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(gmm_kernel<CTX, S, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  const int ngroups = (MK + PK - 1) / PK;
+  const int nwarps = ngroups < 8 ? ngroups : 8;
+  gmm_kernel<CTX, S, PK><<<(B + S - 1) / S, nwarps * 32, smem, st>>>(x, bs, mG, sG, ws, co, lp, lps, out, B, M, K, D, HW);
+  return check_launch("gmm_logprob");
+}
+
+}  // namespace cfpp
+using namespace cfpp;
+
+extern "C" int64_t cfpp_gmm_workspace_floats(int M, int K, int D, int HW) { return (int64_t)M * K * D * HW + (int64_t)M * K; }
+
+extern "C" int cfpp_gmm_logprob(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* wG,
+                                const float* ctx_off, const float* logp_c, float logp_scale, float* out, float* workspace,
+                                int B, int M, int K, int D, int HW, void* stream) {
+  CFPP_REQUIRE(M >= 1 && K >= 1 && K <= 64 && D >= 1 && HW >= 1, "gmm: bad dims M=%d K=%d D=%d HW=%d", M, K, D, HW);
+  CFPP_REQUIRE(workspace != nullptr, "gmm: workspace of cfpp_gmm_workspace_floats() floats required");
+  if (B <= 0) return CFPP_OK;
+  const int E = D * HW, MK = M * K;
+  cudaStream_t st = (cudaStream_t)stream;
+  gmm_prepare_kernel<<<MK, 256, 0, st>>>(sG, wG, workspace, MK, K, E, ctx_off == nullptr);
+  int rc = check_launch("gmm_prepare");
+  if (rc) return rc;
+  const size_t budget = 200 * 1024;
+  const bool fit8 = ((size_t)8 * (E + MK)) * 4 <= budget, fit2 = ((size_t)2 * (E + MK)) * 4 <= budget;
+  CFPP_REQUIRE(fit2, "gmm: event size %d too large for the shared-memory tile", E);
+  if (ctx_off) {
+    return fit8 ? launch_gmm<true, 8, 2>(x, x_bstride, mG, sG, workspace, ctx_off, logp_c, logp_scale, out, B, M, K, D, HW, st)
+                : launch_gmm<true, 2, 4>(x, x_bstride, mG, sG, workspace, ctx_off, logp_c, logp_scale, out, B, M, K, D, HW, st);
+  }
+  return fit8 ? launch_gmm<false, 8, 4>(x, x_bstride, mG, sG, workspace, nullptr, logp_c, logp_scale, out, B, M, K, D, HW, st)
+              : launch_gmm<false, 2, 8>(x, x_bstride, mG, sG, workspace, nullptr, logp_c, logp_scale, out, B, M, K, D, HW, st);
+}

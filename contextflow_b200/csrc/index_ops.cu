@@ -1,0 +1,195 @@
+// Index-only layers (Squeeze, PermuteAxes, channel slice) and the image prologue (Dequantization, Normalization x2,
+// LogitTransform, Augment).  All HBM-bound; values are moved bit-exactly by the index kernels.
+#include "common.cuh"
+
+namespace cfpp {
+
+// ---- Squeeze: y[b, (c*p1+i)*p2+j, h, w] = x[b, c, h*p1+i, w*p2+j] -------------------------------------------
+// One thread per INPUT float2/float pair row segment would complicate generic p; the input row (W floats) is read
+// coalesced by consecutive threads and scattered to p2 output planes; the p2 planes' writes are each W/p2-contiguous.
+// Grid-stride over input elements keeps reads perfectly coalesced; writes hit p2 distinct 32B-sector streams per warp.
+__global__ void squeeze_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total, int C, int H, int W,
+                               int p1, int p2, bool inverse) {
+  const int Ho = H / p1, Wo = W / p2;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    // idx enumerates the OUTPUT-of-squeeze layout so that the wide tensor side is always written/read contiguously
+    int w = idx % Wo; int64_t r = idx / Wo;
+    int h = r % Ho; r /= Ho;
+    int j = r % p2; r /= p2;
+    int i = r % p1; r /= p1;
+    int c = r % C; int64_t b = r / C;
+    int64_t in = ((b * C + c) * H + (h * p1 + i)) * (int64_t)W + (w * p2 + j);
+    if (!inverse) y[idx] = x[in]; else y[in] = x[idx];
+  }
+}
+
+// ---- PermuteAxes (0,2,1,3): y[b,h,c,w] = x[b,c,h,w];  32x32 smem tile transpose over (c,h) per (b,w) ---------
+__global__ void permute_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int H, int W) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z / W, w = blockIdx.z % W;
+  const int c0 = blockIdx.y * 32, h0 = blockIdx.x * 32;
+  const float* xb = x + (int64_t)b * C * H * W;
+  float* yb = y + (int64_t)b * C * H * W;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int c = c0 + r, h = h0 + threadIdx.x;
+    if (c < C && h < H) tile[r][threadIdx.x] = xb[((int64_t)c * H + h) * W + w];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int h = h0 + r, c = c0 + threadIdx.x;
+    if (c < C && h < H) yb[((int64_t)h * C + c) * W + w] = tile[threadIdx.x][r];
+  }
+}
+
+__global__ void slice_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total, int C, int HW, int c0, int Cn) {
+  const int64_t per = (int64_t)Cn * HW;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = idx / per, r = idx % per;
+    y[idx] = x[(b * C + c0) * HW + r];
+  }
+}
+
+__global__ void add_kernel(const float* __restrict__ x, const float* __restrict__ u, float* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = x[i] + u[i];
+}
+__global__ void normalize_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float s, float t) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = x[i] / s + t;
+}
+
+// ---- per-sample kernels with an ldj reduction: one CTA per sample ---------------------------------------------
+__global__ void logit_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ ldj, int n) {
+  __shared__ float red[32];
+  const int64_t b = blockIdx.x;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = x[b * n + i];
+    float l0 = logf(v), l1 = logf(1.f - v);
+    y[b * n + i] = l0 - l1;
+    acc += -l0 - l1;
+  }
+  acc = group_sum(acc, blockDim.x, red);
+  if (threadIdx.x == 0) ldj[b] = acc;
+}
+
+__global__ void augment_kernel(const float* __restrict__ x, const float* __restrict__ eps, float* __restrict__ y,
+                               float* __restrict__ ldj, int C, int A, int HW) {
+  __shared__ float red[32];
+  const int64_t b = blockIdx.x;
+  const int nx = C * HW, ne = A * HW;
+  float* yb = y + b * (int64_t)(nx + ne);
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) yb[i] = x[b * nx + i];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+    float e = eps[b * ne + i];
+    yb[nx + i] = e;
+    acc += kHalfLog2Pi + 0.5f * e * e;
+  }
+  acc = group_sum(acc, blockDim.x, red);
+  if (threadIdx.x == 0) ldj[b] = acc;
+}
+
+__global__ void prologue_kernel(const float* __restrict__ x, const float* __restrict__ u, const float* __restrict__ eps,
+                                float* __restrict__ y, float* __restrict__ ldj, int C, int A, int HW,
+                                float s0, float t0, float s1, float t1, float ldj_const) {
+  __shared__ float red[32];
+  const int64_t b = blockIdx.x;
+  const int nx = C * HW, ne = A * HW;
+  float* yb = y + b * (int64_t)(nx + ne);
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+    float v = x[b * nx + i] + u[b * nx + i];
+    v = v / s0 + t0;
+    v = v / s1 + t1;
+    float l0 = logf(v), l1 = logf(1.f - v);
+    yb[i] = l0 - l1;
+    acc += -l0 - l1;
+  }
+  for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+    float e = eps[b * ne + i];
+    yb[nx + i] = e;
+    acc += kHalfLog2Pi + 0.5f * e * e;
+  }
+  acc = group_sum(acc, blockDim.x, red);
+  if (threadIdx.x == 0) ldj[b] = acc + ldj_const;
+}
+
+static inline int grid_for(int64_t n, int threads) {
+  int64_t g = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)num_sms() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace cfpp
+using namespace cfpp;
+
+extern "C" int cfpp_squeeze_fwd(const float* x, float* y, int B, int C, int H, int W, int p1, int p2, void* stream) {
+  CFPP_REQUIRE(B >= 0 && C > 0 && p1 > 0 && p2 > 0 && H % p1 == 0 && W % p2 == 0, "squeeze: bad dims C=%d H=%d W=%d p=(%d,%d)", C, H, W, p1, p2);
+  int64_t total = (int64_t)B * C * H * W;
+  if (!total) return CFPP_OK;
+  squeeze_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, total, C, H, W, p1, p2, false);
+  return check_launch("squeeze_fwd");
+}
+extern "C" int cfpp_squeeze_inv(const float* y, float* x, int B, int C, int H, int W, int p1, int p2, void* stream) {
+  CFPP_REQUIRE(B >= 0 && C > 0 && p1 > 0 && p2 > 0 && H % p1 == 0 && W % p2 == 0, "squeeze_inv: bad dims");
+  int64_t total = (int64_t)B * C * H * W;
+  if (!total) return CFPP_OK;
+  squeeze_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(y, x, total, C, H, W, p1, p2, true);
+  return check_launch("squeeze_inv");
+}
+extern "C" int cfpp_permute_fwd(const float* x, float* y, int B, int C, int H, int W, void* stream) {
+  CFPP_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0, "permute: bad dims");
+  if (!B) return CFPP_OK;
+  CFPP_REQUIRE((int64_t)B * W <= 65535, "permute: B*W=%lld exceeds grid.z", (long long)B * W);
+  dim3 grid((H + 31) / 32, (C + 31) / 32, B * W), block(32, 8);
+  permute_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, C, H, W);
+  return check_launch("permute_fwd");
+}
+extern "C" int cfpp_slice_channels(const float* x, float* y, int B, int C, int HW, int c0, int Cn, void* stream) {
+  CFPP_REQUIRE(c0 >= 0 && Cn > 0 && c0 + Cn <= C, "slice: bad channel range");
+  int64_t total = (int64_t)B * Cn * HW;
+  if (!total) return CFPP_OK;
+  slice_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, total, C, HW, c0, Cn);
+  return check_launch("slice_channels");
+}
+extern "C" int cfpp_add_fwd(const float* x, const float* u, float* y, int64_t n, void* stream) {
+  if (n <= 0) return CFPP_OK;
+  add_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, u, y, n);
+  return check_launch("add_fwd");
+}
+extern "C" int cfpp_normalize_fwd(const float* x, float* y, int64_t n, float scale, float translation, void* stream) {
+  if (n <= 0) return CFPP_OK;
+  normalize_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, scale, translation);
+  return check_launch("normalize_fwd");
+}
+extern "C" int cfpp_logit_fwd(const float* x, float* y, float* ldj, int B, int n, void* stream) {
+  if (B <= 0) return CFPP_OK;
+  logit_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, y, ldj, n);
+  return check_launch("logit_fwd");
+}
+extern "C" int cfpp_augment_fwd(const float* x, const float* eps, float* y, float* ldj, int B, int C, int A, int HW, void* stream) {
+  if (B <= 0) return CFPP_OK;
+  augment_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, eps, y, ldj, C, A, HW);
+  return check_launch("augment_fwd");
+}
+extern "C" int cfpp_prologue_fwd(const float* x, const float* u, const float* eps, float* y, float* ldj, int B, int C, int A, int HW,
+                                 float s0, float t0, float s1, float t1, float ldj_const, void* stream) {
+  if (B <= 0) return CFPP_OK;
+  CFPP_REQUIRE(A == 0 || eps != nullptr, "prologue: eps required when A>0");
+  prologue_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, u, eps, y, ldj, C, A, HW, s0, t0, s1, t1, ldj_const);
+  return check_launch("prologue_fwd");
+}
+
+// FlowSequential.forward's `logdet += ldj` (layers/flowsequential.py:23): logdet (B,M) += ldj (B,cols), cols in {1, M}.
+namespace cfpp {
+__global__ void ldj_accumulate_kernel(float* __restrict__ logdet, const float* __restrict__ ldj, int64_t total, int M, int cols) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    logdet[i] += ldj[(i / M) * cols + (cols == 1 ? 0 : i % M)];
+}
+}  // namespace cfpp
+extern "C" int cfpp_ldj_accumulate(float* logdet, const float* ldj, int B, int M, int cols, void* stream) {
+  CFPP_REQUIRE(cols == 1 || cols == M, "ldj_accumulate: ldj has %d columns, expected 1 or %d", cols, M);
+  const int64_t total = (int64_t)B * M;
+  if (total <= 0) return CFPP_OK;
+  cfpp::ldj_accumulate_kernel<<<cfpp::grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(logdet, ldj, total, M, cols);
+  return cfpp::check_launch("ldj_accumulate");
+}

@@ -1,0 +1,214 @@
+"""Building cfpp_enc_desc descriptors from the encoder module tree and launching the fused encoder kernel.
+
+ContextEncoder (reference model.py:30-90) = Sequential(embedding, surjection); the variational / argmax / prob surjections
+own `encoder` = FlowInvSequential(ConditionalGaussianDistribution(CatEmbeddings), FC, ActNormFC, CouplingFC, FC, ActNormFC,
+CouplingFC).  One kernel launch evaluates all of it per sample (cfpp_ctx_encode)."""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from .. import _cabi, ops, rng
+from .flowlayer import PackCache
+
+
+def _vp(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _inner_flow_parts(flow):
+    """(dist embeddings, [(FC, ActNormFC, CouplingFC)] * 2) if `flow` has the create_model encoder structure, else None."""
+    from .actnorm import ActNormFC
+    from .conv1x1 import FC
+    from .coupling import CouplingFC
+    from .distributions import ConditionalGaussianDistribution
+    from .flowsequential import FlowInvSequential
+    from .rtdl.nn._embeddings import CatEmbeddings
+    if not isinstance(flow, FlowInvSequential) or not isinstance(flow.dist, ConditionalGaussianDistribution):
+        return None
+    if not isinstance(flow.dist.context_net, CatEmbeddings) or flow.dist.context_net.uniform_width() is None:
+        return None
+    mods = list(flow.sequence_modules)
+    if len(mods) != 6:
+        return None
+    triples = [mods[0:3], mods[3:6]]
+    for fc, an, cp in triples:
+        if not (isinstance(fc, FC) and isinstance(an, ActNormFC) and isinstance(cp, CouplingFC)):
+            return None
+    return flow.dist.context_net, triples
+
+
+class FusedEncoder:
+    """Descriptor + launch for one (embedding, surjection) pair.  `embedding` may be None: the surjection then receives an
+    already-embedded dense (B, C) matrix (standalone module call)."""
+
+    def __init__(self, emb, surj):
+        self.emb, self.surj = emb, surj
+        self._packs = PackCache()
+
+    # ------------------------------------------------------------------------------------------ recognition
+    @staticmethod
+    def recognise(context_net):
+        from .dequantize import _CatSurjection
+        from .rtdl.nn._embeddings import CatEmbeddings, EyeEncoder, OneHotEncoder
+        if not (isinstance(context_net, nn.Sequential) and len(context_net) == 2):
+            return None
+        emb, surj = context_net[0], context_net[1]
+        if not isinstance(emb, (OneHotEncoder, EyeEncoder, CatEmbeddings)) or not isinstance(surj, _CatSurjection):
+            return None
+        if isinstance(emb, CatEmbeddings) and emb.uniform_width() is None:
+            return None
+        if surj.kind in ('vardeq', 'argmax', 'probsample') and _inner_flow_parts(surj.encoder) is None:
+            return None
+        if surj.kind in ('uniform', 'vardeq', 'argmax') and isinstance(emb, CatEmbeddings):
+            return None        # num_cats is undefined for this pair in the reference (model.py:76-84)
+        return FusedEncoder(emb, surj)
+
+    # ------------------------------------------------------------------------------------------ descriptor
+    def _sources(self):
+        from .rtdl.nn._embeddings import CatEmbeddings
+        src = []
+        if isinstance(self.emb, CatEmbeddings):
+            src += self.emb.tables()
+        for name in ('qbins', 'ldj_per_dim'):
+            if hasattr(self.surj, name):
+                src.append(getattr(self.surj, name))
+        if hasattr(self.surj, 'sigmoid'):
+            src.append(self.surj.sigmoid.temperature)
+        if self.surj.kind in ('vardeq', 'argmax', 'probsample'):
+            inner, triples = _inner_flow_parts(self.surj.encoder)
+            src += inner.tables()
+            for fc, an, cp in triples:
+                src += [fc.NN, an.NN_t, an.NN_logs] + [p for p in cp.NN.parameters()]
+        return src
+
+    def _build(self, n_ctx, width, dense):
+        from .rtdl.nn._embeddings import CatEmbeddings, EyeEncoder, OneHotEncoder
+        d = _cabi.EncDesc()
+        keep = []
+        kind = self.surj.kind
+        d.type = _cabi.ENC[kind]
+        d.n_ctx = n_ctx
+        if dense:
+            d.emb = _cabi.EMB['dense']
+        elif isinstance(self.emb, OneHotEncoder):
+            d.emb = _cabi.EMB['onehot']
+            for i, c in enumerate(self.emb._cards):
+                d.card[i] = c
+        elif isinstance(self.emb, EyeEncoder):
+            d.emb = _cabi.EMB['eye']
+        else:
+            d.emb = _cabi.EMB['embed']
+            d.emb_dim = self.emb.uniform_width()
+            for i, t in enumerate(self.emb.tables()):
+                tt = t.detach().float().contiguous(); keep.append(tt); d.emb_w[i] = _vp(tt)
+        d.C = width
+        if kind in ('uniform', 'vardeq'):
+            if self.surj.qbins.numel() != width:
+                raise ValueError(f'{type(self.surj).__name__}: {self.surj.qbins.numel()} category bins for a width-{width} embedding')
+            d.qbins, d.ldj_per_dim = _vp(self.surj.qbins), _vp(self.surj.ldj_per_dim)
+        if kind == 'argmax':
+            bits = self.surj.num_bits if isinstance(self.surj.num_bits, (list, tuple)) else [self.surj.num_bits]
+            if len(bits) != n_ctx or sum(bits) + sum(bits) % 2 != width:
+                raise ValueError('ArgmaxCatDequantization: bit widths do not match the context / encoder width')
+            for i, b in enumerate(bits):
+                d.bits[i] = b
+        if kind in ('vardeq', 'argmax', 'probsample'):
+            inner, triples = _inner_flow_parts(self.surj.encoder)
+            d.temperature = _vp(self.surj.sigmoid.temperature)
+            d.inner_dim = inner.uniform_width()
+            if d.inner_dim * n_ctx != 2 * width:
+                raise ValueError('encoder base distribution width does not match the flow width')
+            for i, t in enumerate(inner.tables()):
+                tt = t.detach().float().contiguous(); keep.append(tt); d.inner_w[i] = _vp(tt)
+            for L, (fc, an, cp) in enumerate(triples):
+                if fc.D != width or an.D != width or cp.D != width:
+                    raise ValueError('encoder flow layers do not match the embedding width')
+                lad = fc.logabsdet(); keep.append(lad)
+                d.fc[L], d.fc_logabsdet[L] = _vp(fc.NN), _vp(lad)
+                d.an_t[L], d.an_logs[L] = _vp(an.NN_t), _vp(an.NN_logs)
+                c1, c2, c3 = cp.NN[0], cp.NN[2], cp.NN[4]
+                packs = [ops.pack_kmajor(c.weight.reshape(c.weight.shape[0], -1), 1) for c in (c1, c2, c3)]
+                keep += packs
+                d.cw1t[L], d.cw2t[L], d.cw3t[L] = (_vp(p) for p in packs)
+                d.cb1[L], d.cb2[L], d.cb3[L] = _vp(c1.bias), _vp(c2.bias), _vp(c3.bias)
+        return d, keep
+
+    def _descriptor(self, n_ctx, width, dense=False):
+        if width > _cabi.ENC_MAXC:
+            raise NotImplementedError(f'encoder width {width} exceeds the fused kernel limit {_cabi.ENC_MAXC}')
+        d, _ = self._packs.get(('desc', n_ctx, width, dense), self._sources(), lambda: self._build(n_ctx, width, dense))
+        return d
+
+    def _width(self, n_ctx):
+        from .rtdl.nn._embeddings import CatEmbeddings, EyeEncoder, OneHotEncoder
+        if isinstance(self.emb, OneHotEncoder):
+            return sum(self.emb._cards)
+        if isinstance(self.emb, CatEmbeddings):
+            return self.emb.uniform_width() * n_ctx
+        if self.surj.kind == 'argmax':
+            bits = self.surj.num_bits if isinstance(self.surj.num_bits, (list, tuple)) else [self.surj.num_bits]
+            return sum(bits) + sum(bits) % 2
+        return n_ctx
+
+    # ------------------------------------------------------------------------------------------ launch
+    def _draw(self, B, width, device):
+        kind = self.surj.kind
+        if kind == 'eyesample':
+            return None
+        if kind == 'uniform':
+            return rng.rand((B, width), device)                       # dequantize.py:57
+        return rng.randn((B, width), device)                          # gaussian.py:265
+
+    def _ensure_actnorm(self, ctx, noise, d):
+        """ActNormFC data-dependent initialisation on the first batch (actnorm.py:53), stage by stage."""
+        if self.surj.kind not in ('vardeq', 'argmax', 'probsample'):
+            return
+        _, triples = _inner_flow_parts(self.surj.encoder)
+        for L, (_, an, _) in enumerate(triples):
+            if not an.is_initialized():
+                pre, _ = ops.ctx_encode(ctx, noise, d, emit_stage=L)
+                an.initialize(pre.reshape(-1, an.D, 1, 1))
+
+    def __call__(self, context, dense=None):
+        if context.dim() != 2:
+            raise ValueError('The input must have two dimensions')
+        B, n_ctx = context.shape
+        if dense is None and self.surj.kind == 'eyesample' and hasattr(self.emb, 'tables'):
+            # embed + eyesample (the split / base prior contexts, model.py:157,162): a plain table lookup, any width
+            return ops.embed_lookup(context, self.emb.tables()), torch.zeros(B, device=context.device, dtype=torch.float32)
+        width = self._width(n_ctx) if dense is None else dense.shape[1]
+        d = self._descriptor(n_ctx, width, dense is not None)
+        if dense is not None:
+            d.dense = _vp(dense)
+        noise = self._draw(B, width, context.device)
+        self._ensure_actnorm(context, noise, d)
+        return ops.ctx_encode(context, noise, d)
+
+
+def run_surjection(surj, x, context):
+    """Standalone surjection.forward((x, context)) with an already-embedded x."""
+    if not hasattr(surj, '_fused_dense'):
+        if surj.kind in ('vardeq', 'argmax', 'probsample') and _inner_flow_parts(surj.encoder) is None:
+            raise NotImplementedError('only the create_model encoder flow (FC, ActNormFC, CouplingFC) x 2 has a fused kernel')
+        object.__setattr__(surj, '_fused_dense', FusedEncoder(None, surj))
+    dense = x.to(torch.float32).contiguous()
+    return surj._fused_dense(context, dense=dense)
+
+
+def cond_gauss_sample(dist, n_samples, context):
+    """ConditionalGaussianDistribution.sample (gaussian.py:263-270) alone: emit_stage 2 of the encoder kernel."""
+    from .rtdl.nn._embeddings import CatEmbeddings
+    emb = dist.context_net
+    if not isinstance(emb, CatEmbeddings) or emb.uniform_width() is None:
+        raise NotImplementedError('ConditionalGaussianDistribution needs a CatEmbeddings context_net')
+    width = dist.D
+    n_ctx = context.shape[1]
+    d = _cabi.EncDesc()
+    d.emb, d.type, d.n_ctx, d.C = _cabi.EMB['eye'], _cabi.ENC['vardeq'], n_ctx, width
+    d.inner_dim = emb.uniform_width()
+    keep = [t.detach().float().contiguous() for t in emb.tables()]
+    for i, t in enumerate(keep):
+        d.inner_w[i] = _vp(t)
+    noise = rng.randn((n_samples, width), context.device)
+    return ops.ctx_encode(context, noise, d, emit_stage=2)

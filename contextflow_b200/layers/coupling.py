@@ -1,0 +1,142 @@
+"""Affine coupling layers (reference layers/coupling.py): Coupling (3-conv conditioner, :14-77), CouplingFC (:80-97),
+TransCoupling (SimpleViT conditioner, :100-159).  Conditioner -> h in HBM -> fused coupling kernel (x,h -> z, ldj)."""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .context import ContextPlan
+from .flowlayer import FlowLayer, PackCache, inference_only
+from .simple_vit import SimpleViT
+
+__all__ = ['Coupling', 'CouplingFC', 'TransCoupling', 'MaskedCoupling']
+
+
+def _freeze(module):
+    for p in module.parameters():
+        p.requires_grad = False
+    return module
+
+
+def _context_mlp(C, H, O):
+    return nn.Sequential(nn.Linear(C, H), nn.ReLU(), nn.Linear(H, H), nn.ReLU(), nn.Linear(H, O))
+
+
+class _CouplingBase(FlowLayer):
+    """Shared context plumbing: CN is Linear-ReLU-Linear-ReLU-Linear on the encoded context (coupling.py:37,121)."""
+
+    def _context_terms(self, context):
+        c, logp_c = self._plan.run(self.context_net, context)
+        lin = [self.CN[0], self.CN[2], self.CN[4]]
+        packs = self._packs.get('cn', [l.weight for l in lin], lambda: [ops.pack_kmajor(l.weight, 1) for l in lin])
+        h = ops.linear(c, packs[0], lin[0].bias.detach(), relu=True)
+        h = ops.linear(h, packs[1], lin[1].bias.detach(), relu=True)
+        return ops.linear(h, packs[2], lin[2].bias.detach()), logp_c
+
+    def reverse(self, z, context=None):
+        raise NotImplementedError('inverse path is outside this round (SURVEY §8f-3)')
+
+    def logdet(self, input, context=None):
+        return self.forward(input, context)[1]
+
+
+class Coupling(_CouplingBase):
+    def __init__(self, data_channels, kernel_size=(1, 1), padding=(0, 0), context_net=None, contextflow=False):
+        super().__init__()
+        D, H, O = data_channels // 2, data_channels * 2, data_channels
+        self.krn, self.pad = tuple(kernel_size), tuple(padding)
+        self.context_net, self.contextflow = context_net, contextflow
+        first_in = D + O if (context_net and not contextflow) else D          # conventional: concatenated context
+        self.NN = nn.Sequential(nn.Conv2d(first_in, H, 1), nn.ReLU(),
+                                nn.Conv2d(H, H, self.krn, padding=self.pad, padding_mode='reflect'), nn.ReLU(),
+                                nn.Conv2d(H, O, 1))
+        if self.context_net:
+            if self.contextflow:
+                _freeze(self.NN)
+            self.C = self.context_net.C
+            self.CN = _context_mlp(self.C, H, O)
+        self._dims = (D, H, O)
+        self._plan, self._packs = ContextPlan(), PackCache()
+        if self.pad != (self.krn[0] // 2, self.krn[1] // 2):
+            raise NotImplementedError('the fused conditioner assumes "same" reflect padding (model.py:114)')
+
+    def _packed_nn(self):
+        D, H, O = self._dims
+        c1, c2, c3 = self.NN[0], self.NN[2], self.NN[4]
+
+        def build():
+            w1 = c1.weight.reshape(H, -1)
+            return dict(main=(ops.pack_kmajor(w1[:, :D]), ops.pad_vec(c1.bias), ops.pack_kmajor(c2.weight.reshape(H, -1)),
+                              ops.pad_vec(c2.bias), ops.pack_kmajor(c3.weight.reshape(O, -1)), ops.pad_vec(c3.bias)),
+                        ctx_w=ops.pack_kmajor(w1[:, D:], 1) if w1.shape[1] > D else None)
+        return self._packs.get('nn', [c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias], build)
+
+    def forward(self, x, context=None):
+        inference_only(x)
+        D, H, O = self._dims
+        Hh, Ww = x.shape[2], x.shape[3]
+        pk = self._packed_nn()
+        if not self.context_net:
+            h = ops.conv_cond(x, D, pk['main'], Hh, Ww, self.krn[0], self.krn[1], O)
+            return ops.coupling(x, h)
+        cn, logp_c = self._context_terms(context)
+        if self.contextflow:                                      # additive: h = NN(x0) + CN(c)   (coupling.py:45)
+            h = ops.conv_cond(x, D, pk['main'], Hh, Ww, self.krn[0], self.krn[1], O)
+            return ops.coupling(x, h, add=cn, logp_c=logp_c, logp_scale=float(Hh * Ww))
+        # conventional: NN(cat(x0, CN(c) broadcast)) == first conv with the per-sample bias b1 + W1[:, D:] CN(c)  (coupling.py:47)
+        bias1 = ops.linear(cn, pk['ctx_w'], self.NN[0].bias.detach())
+        h = ops.conv_cond(x, D, pk['main'], Hh, Ww, self.krn[0], self.krn[1], O, bias1_b=bias1)
+        return ops.coupling(x, h, logp_c=logp_c, logp_scale=float(Hh * Ww))
+
+
+class CouplingFC(Coupling):
+    def __init__(self, data_channels, kernel_size=(1, 1), padding=(0, 0), context_net=None, contextflow=False):
+        super().__init__(data_channels, kernel_size=(1, 1), padding=(0, 0), context_net=None, contextflow=False)
+        self.D = data_channels
+
+    def forward(self, x, context=None):
+        out, ldj = super().forward(x.reshape(-1, self.D, 1, 1), context)
+        return out.view(-1, self.D), ldj
+
+    def logdet(self, x, context=None):
+        return self.forward(x, context)[1]
+
+
+class TransCoupling(_CouplingBase):
+    def __init__(self, in_sz, p_sz, context_net=None, contextflow=False):
+        super().__init__()
+        D, H, O = in_sz[0] // 2, in_sz[0] * 2, in_sz[0]
+        T = O * p_sz[0] * p_sz[1]
+        self.context_net, self.contextflow = context_net, contextflow
+        vit = dict(image_size=(in_sz[1], in_sz[2]), patch_size=tuple(p_sz), dim=T, depth=6, heads=1, mlp_dim=T)
+        if self.context_net and not self.contextflow:
+            self.NN = SimpleViT(channels=D + O, **vit)              # bare module: keys NN.* (App. C-6)
+        else:
+            self.NN = nn.Sequential(SimpleViT(channels=D, **vit))   # keys NN.0.*
+            if self.context_net:
+                _freeze(self.NN)
+        if self.context_net:
+            self.C = self.context_net.C
+            self.CN = _context_mlp(self.C, H, O)
+        self._dims = (D, H, O)
+        self._plan, self._packs = ContextPlan(), PackCache()
+
+    def forward(self, x, context=None):
+        inference_only(x)
+        vit = self.NN if isinstance(self.NN, SimpleViT) else self.NN[0]
+        if not self.context_net:
+            return ops.coupling(x, vit(x))
+        cn, logp_c = self._context_terms(context)                   # note: logp_c is NOT scaled by H*W here (coupling.py:126)
+        if self.contextflow:
+            return ops.coupling(x, vit(x), add=cn, logp_c=logp_c, logp_scale=1.0)
+        return ops.coupling(x, vit(x, extra=cn), logp_c=logp_c, logp_scale=1.0)
+
+
+class MaskedCoupling(FlowLayer):
+    """--coupling maf: outside the accelerated path."""
+
+    def __init__(self, *a, **kw):
+        raise NotImplementedError('MaskedCoupling (--coupling maf) is outside the accelerated path')
+
+    def forward(self, input, context=None): ...
+    def reverse(self, input, context=None): ...
+    def logdet(self, input, context=None): ...

@@ -1,0 +1,94 @@
+"""Gaussian densities of the path (reference layers/distributions/gaussian.py):
+StandardNormal (Augment noise, :10-72), GaussianMixtureDistribution (base + split priors, :118-169),
+ConditionalGaussianDistribution (encoder base, :234-270)."""
+import torch
+import torch.nn as nn
+
+from ... import ops, rng
+from ..context import ContextPlan
+from ..flowlayer import inference_only
+
+
+__all__ = ['StandardNormal', 'GaussianMixtureDistribution', 'ConditionalGaussianDistribution']
+
+class StandardNormal(nn.Module):
+    """N(0, I) over `size`; only the context-free form is on the path (model.py:122, :62)."""
+
+    def __init__(self, size, mixtures=1, context_net=None, contextflow=False):
+        super().__init__()
+        assert mixtures == 1, 'mixtures should be 1 in GaussianDistribution'
+        if context_net:
+            raise NotImplementedError('the class-conditional StandardNormal variant is not instantiated by create_model')
+        self.size = torch.Size(size)
+        self.M, self.K = mixtures, 8
+        self.register_buffer('buffer', torch.zeros(1))
+        self.context_net, self.contextflow = context_net, contextflow
+
+    def forward(self, input, context=None):
+        return self.log_prob(input, context)
+
+    def log_prob(self, input, context=None):
+        flat = input.reshape(input.shape[0], -1, 1, 1)
+        return -ops.augment(None, flat)[1].unsqueeze(-1)
+
+    def draw(self, n_samples, device=None):
+        return rng.randn((n_samples, *self.size), self.buffer.device if device is None else device, self.buffer.dtype)
+
+    def sample(self, n_samples, context=None):
+        x = self.draw(n_samples)
+        return x, self.log_prob(x, context)
+
+
+class GaussianMixtureDistribution(nn.Module):
+    """K-component, M-mixture diagonal GMM; context adds per-sample mean / pre-softplus scale offsets."""
+
+    def __init__(self, size, mixtures=2, components=8, context_net=None, contextflow=False):
+        super().__init__()
+        self.size = size
+        D, H, W = size
+        self.D, self.M, self.K = D, mixtures, components
+        self.mG = nn.Parameter(torch.randn(self.M, self.K, D, H, W))
+        self.sG = nn.Parameter(torch.ones(self.M, self.K, D, H, W))
+        self.wG = nn.Parameter(torch.randn(self.M, self.K))
+        self.context_net, self.contextflow = context_net, contextflow
+        if self.context_net:
+            self.C = self.context_net.C
+            if self.contextflow:
+                for p in (self.mG, self.sG, self.wG):
+                    p.requires_grad_(False)
+        self._plan = ContextPlan()
+
+    def log_prob(self, input, context=None):
+        inference_only(self.mG); inference_only(input)
+        H, W = input.shape[2], input.shape[3]
+        if isinstance(context, list):
+            context = context[0]
+        if self.context_net:
+            c, logp_c = self._plan.run(self.context_net, context)       # c: 'b (p m k d)'
+            return ops.gmm_logprob(input, self.mG, self.sG, self.wG, c, logp_c, float(H * W))
+        return ops.gmm_logprob(input, self.mG, self.sG, self.wG)
+
+    def sample(self, n_samples, context=None):
+        raise NotImplementedError('sampling / inverse path is outside this round (SURVEY §8f-3)')
+
+
+class ConditionalGaussianDistribution(nn.Module):
+    """q(u | context) = N(mean(context), exp(log_scale(context))): base of the encoder flows."""
+
+    def __init__(self, size, mixtures=1, context_net=None, contextflow=False):
+        super().__init__()
+        self.size = size
+        self.D = size[0]
+        assert mixtures == 1, 'mixtures should be 1 in GaussianDistribution'
+        self.M = mixtures
+        self.context_net, self.contextflow = context_net, contextflow
+
+    def forward(self, x, context=None):
+        return self.log_prob(x, context)
+
+    def log_prob(self, x, context=None):
+        raise NotImplementedError('only ConditionalGaussianDistribution.sample is on the path (flowsequential.py:61)')
+
+    def sample(self, n_samples, context=None):
+        from .._encoder_desc import cond_gauss_sample
+        return cond_gauss_sample(self, n_samples, context)

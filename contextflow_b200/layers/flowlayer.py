@@ -1,0 +1,55 @@
+"""The plugin boundary: FlowLayer.forward(x, context) -> (z, ldj) (reference layers/flowlayer.py:7-24)."""
+from abc import ABCMeta, abstractmethod
+
+import torch
+import torch.nn as nn
+
+
+class FlowLayer(nn.Module, metaclass=ABCMeta):
+    @abstractmethod
+    def forward(self, input, context=None):
+        """-> (output, ldj)"""
+
+    @abstractmethod
+    def reverse(self, input, context=None):
+        """-> input of forward"""
+
+    @abstractmethod
+    def logdet(self, input, context=None):
+        """-> ldj"""
+
+
+class ModifiedGradFlowLayer(FlowLayer):
+    pass
+
+
+class PreprocessingFlowLayer(FlowLayer):
+    pass
+
+
+def mark_expensive(func):
+    func._expensive_computation = True
+    return func
+
+
+def inference_only(t: torch.Tensor):
+    """The CUDA path is the log-density *forward*; autograd through it is the next scope row."""
+    if torch.is_grad_enabled() and t.requires_grad:
+        raise NotImplementedError('contextflow_b200 implements the forward log-density path; wrap the call in torch.no_grad() '
+                                  '(backward kernels are out of scope for this round, see DESIGN.md)')
+
+
+class PackCache:
+    """One-time weight repacking (K-major, padded) keyed on the source tensors' version counters and storage."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, name, tensors, build):
+        key = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+        hit = self._store.get(name)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, build())
+            self._store[name] = hit
+        return hit[1]

@@ -1,0 +1,63 @@
+"""Flow containers (reference layers/flowsequential.py): FlowSequential.forward/log_prob (:18-30) accumulates the per-layer
+ldj into a (B, M) log-det and adds the base log-prob; FlowInvSequential.sample (:60-69) drives the encoder flows."""
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+__all__ = ['FlowSequential', 'FlowInvSequential']
+
+
+class FlowSequential(nn.Module):
+    def __init__(self, dist, *modules):
+        super().__init__()
+        self.dist = dist
+        self.mixtures = dist.M
+        for i, module in enumerate(modules):
+            self.add_module(str(i), module)
+        self.sequence_modules = modules
+
+    def __iter__(self):
+        yield from self.sequence_modules
+
+    def forward(self, input, context=None):
+        B = input.shape[0]
+        logdet = torch.zeros((B, self.mixtures), device=input.device, dtype=torch.float32)
+        out = input
+        for module in self.sequence_modules:
+            out, ldj = module(out, context)
+            ops.ldj_accumulate(logdet, ldj)                     # (B,), (B,1) broadcast or (B,M)   (flowsequential.py:23)
+        logprob = self.dist.log_prob(out, context)              # fresh (B, M) tensor: accumulate into it and return it
+        ops.ldj_accumulate(logprob, logdet)
+        return out, logprob
+
+    def log_prob(self, input, context=None):
+        return self.forward(input, context)[1]
+
+    def sample(self, n_samples, context=None):
+        raise NotImplementedError('sampling / inverse path is outside this round (SURVEY §8f-3)')
+
+
+class FlowInvSequential(nn.Module):
+    def __init__(self, dist, *modules):
+        super().__init__()
+        self.dist = dist
+        for i, module in enumerate(modules):
+            self.add_module(str(i), module)
+        self.sequence_modules = modules
+
+    def __iter__(self):
+        yield from self.sequence_modules
+
+    def forward(self, input, context=None):
+        return self.sample(input, context)
+
+    def log_prob(self, input, context=None):
+        raise RuntimeError('InverseFlow does not support log_prob, see Flow instead.')
+
+    def sample(self, input, context=None):
+        out, logprob = self.dist.sample(input.size(0), context)
+        for module in self.sequence_modules:
+            out, ldj = module(out, context)
+            logprob = logprob - (ldj if ldj.dim() == logprob.dim() else ldj.squeeze(-1))
+        return out, logprob

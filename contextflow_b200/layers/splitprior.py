@@ -1,0 +1,21 @@
+"""SplitPrior: factor out the second half of the channels under a (context-conditioned) mixture prior
+(reference layers/splitprior.py:7-15)."""
+from .. import ops
+from .flowlayer import FlowLayer
+
+
+class SplitPrior(FlowLayer):
+    def __init__(self, dist):
+        super().__init__()
+        self.dist = dist
+
+    def forward(self, x, context=None):
+        half = x.shape[1] // 2
+        ldj = self.dist.log_prob(x[:, half:], context)         # read in place through the batch stride, (B, M)
+        return ops.slice_channels(x, 0, half), ldj
+
+    def reverse(self, z, context=None):
+        raise NotImplementedError('inverse path is outside this round (SURVEY §8f-3)')
+
+    def logdet(self, input, context=None):
+        return self.forward(input, context)[1]

@@ -1,0 +1,14 @@
+"""LogitTransform (reference layers/transforms.py:6-18)."""
+from .. import ops
+from .flowlayer import PreprocessingFlowLayer
+
+
+class LogitTransform(PreprocessingFlowLayer):
+    def forward(self, input, context=None):
+        return ops.logit(input)
+
+    def reverse(self, input, context=None):
+        raise NotImplementedError('inverse path is outside this round (SURVEY §8f-3)')
+
+    def logdet(self, input, context=None):
+        return ops.logit(input)[1]

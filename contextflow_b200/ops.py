@@ -1,0 +1,273 @@
+"""Tensor-level wrappers over the C ABI (include/cfpp.h).  torch supplies device memory and the stream; every
+computation below is a libcfpp kernel.  CPU tensors are rejected: there is no fallback path."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _cabi
+from ._cabi import check, lib, vp
+
+
+def _stream():
+    return vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('contextflow_b200 kernels run on CUDA tensors only (no CPU fallback); got a CPU tensor')
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f'float32 expected, got {t.dtype}')
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else vp(t.data_ptr())
+
+
+def _half_view(x: torch.Tensor):
+    """Accept (B,C,H,W) tensors that are contiguous or a channel-slice view of a contiguous tensor: returns batch stride."""
+    if x.dtype != torch.float32:
+        raise TypeError(f'float32 expected, got {x.dtype}')
+    B, Cc, H, W = x.shape
+    st = x.stride()
+    if B == 0 or (st[1] == H * W and st[2] == W and st[3] == 1) or (Cc == 1 and st[2] == W and st[3] == 1):
+        return x, (st[0] if B > 1 else Cc * H * W)
+    x = x.contiguous()
+    return x, Cc * H * W
+
+
+# ---------------------------------------------------------------------------------------------- index ops
+def squeeze(x, p1, p2):
+    _need_cuda(x); x = _f32(x)
+    B, Cc, H, W = x.shape
+    y = torch.empty((B, Cc * p1 * p2, H // p1, W // p2), device=x.device, dtype=x.dtype)
+    check(lib().cfpp_squeeze_fwd(_p(x), _p(y), B, Cc, H, W, p1, p2, _stream()), 'squeeze_fwd')
+    return y
+
+
+def unsqueeze(y, p1, p2):
+    _need_cuda(y); y = _f32(y)
+    B, Cs, Hs, Ws = y.shape
+    Cc, H, W = Cs // (p1 * p2), Hs * p1, Ws * p2
+    x = torch.empty((B, Cc, H, W), device=y.device, dtype=y.dtype)
+    check(lib().cfpp_squeeze_inv(_p(y), _p(x), B, Cc, H, W, p1, p2, _stream()), 'squeeze_inv')
+    return x
+
+
+def permute_chw(x):
+    _need_cuda(x); x = _f32(x)
+    B, Cc, H, W = x.shape
+    y = torch.empty((B, H, Cc, W), device=x.device, dtype=x.dtype)
+    step = max(1, 65535 // max(W, 1))
+    for b0 in range(0, B, step):
+        nb = min(step, B - b0)
+        check(lib().cfpp_permute_fwd(_p(x[b0:]), _p(y[b0:]), nb, Cc, H, W, _stream()), 'permute_fwd')
+    return y
+
+
+def slice_channels(x, c0, cn):
+    _need_cuda(x); x = _f32(x)
+    B, Cc, H, W = x.shape
+    y = torch.empty((B, cn, H, W), device=x.device, dtype=x.dtype)
+    check(lib().cfpp_slice_channels(_p(x), _p(y), B, Cc, H * W, c0, cn, _stream()), 'slice_channels')
+    return y
+
+
+# ---------------------------------------------------------------------------------------------- prologue
+def add(x, u):
+    _need_cuda(x, u); x = _f32(x); u = _f32(u)
+    y = torch.empty_like(x)
+    check(lib().cfpp_add_fwd(_p(x), _p(u), _p(y), x.numel(), _stream()), 'add_fwd')
+    return y
+
+
+def normalize(x, scale: float, translation: float):
+    _need_cuda(x); x = _f32(x)
+    y = torch.empty_like(x)
+    check(lib().cfpp_normalize_fwd(_p(x), _p(y), x.numel(), scale, translation, _stream()), 'normalize_fwd')
+    return y
+
+
+def logit(x):
+    _need_cuda(x); x = _f32(x)
+    B = x.shape[0]
+    y = torch.empty_like(x); ldj = torch.empty(B, device=x.device, dtype=x.dtype)
+    check(lib().cfpp_logit_fwd(_p(x), _p(y), _p(ldj), B, x[0].numel() if B else 0, _stream()), 'logit_fwd')
+    return y, ldj
+
+
+def augment(x, eps):
+    """cat([x, eps], 1) and ldj = sum(0.5 log 2pi + 0.5 eps^2) (B,).  x may be None (pure noise log-density)."""
+    _need_cuda(eps); eps = _f32(eps)
+    B, A = eps.shape[0], eps.shape[1]
+    HW = eps[0, 0].numel() if B else 1
+    Cc = 0 if x is None else x.shape[1]
+    if x is not None:
+        _need_cuda(x); x = _f32(x)
+    y = torch.empty((B, Cc + A) + tuple(eps.shape[2:]), device=eps.device, dtype=eps.dtype)
+    ldj = torch.empty(B, device=eps.device, dtype=eps.dtype)
+    check(lib().cfpp_augment_fwd(_p(x), _p(eps), _p(y), _p(ldj), B, Cc, A, HW, _stream()), 'augment_fwd')
+    return y, ldj
+
+
+def prologue(x, u, eps, s0, t0, s1, t1, ldj_const):
+    _need_cuda(x, u, eps); x = _f32(x); u = _f32(u)
+    B, Cc, H, W = x.shape
+    A = 0 if eps is None else eps.shape[1]
+    if eps is not None:
+        eps = _f32(eps)
+    y = torch.empty((B, Cc + A, H, W), device=x.device, dtype=x.dtype)
+    ldj = torch.empty(B, device=x.device, dtype=x.dtype)
+    check(lib().cfpp_prologue_fwd(_p(x), _p(u), _p(eps), _p(y), _p(ldj), B, Cc, A, H * W, s0, t0, s1, t1, ldj_const, _stream()), 'prologue_fwd')
+    return y, ldj
+
+
+# ---------------------------------------------------------------------------------------------- 1x1 conv / actnorm
+def slogdet(A):
+    _need_cuda(A); A = _f32(A)
+    out = torch.empty(1, device=A.device, dtype=A.dtype)
+    check(lib().cfpp_slogdet(_p(A), A.shape[0], _p(out), _stream()), 'slogdet')
+    return out
+
+
+def conv1x1(x, NN, logabsdet, c=None, logp_c=None, contextflow=False, an_t=None, an_logs=None, an_logp_c=None, an_logp_scale=0.0):
+    _need_cuda(x, NN); x = _f32(x)
+    B, D = x.shape[0], x.shape[1]
+    HW = x[0, 0].numel() if B else 1
+    z = torch.empty_like(x); ldj = torch.empty(B, device=x.device, dtype=x.dtype)
+    per_sample = int(an_t is not None and an_t.dim() == 2)
+    check(lib().cfpp_conv1x1_fwd(_p(x), _p(z), _p(ldj), _p(_f32(NN)), _p(logabsdet), _p(None if c is None else _f32(c)),
+                                 _p(logp_c), int(bool(contextflow)), _p(an_t), _p(an_logs), per_sample, _p(an_logp_c),
+                                 float(an_logp_scale), B, D, HW, _stream()), 'conv1x1_fwd')
+    return z, ldj
+
+
+def actnorm(x, base_t, base_logs, c=None, logp_c=None, logp_scale=0.0, mode=0):
+    _need_cuda(x); x = _f32(x)
+    B, D = x.shape[0], x.shape[1]
+    HW = x[0, 0].numel() if B else 1
+    z = torch.empty_like(x); ldj = torch.empty(B, device=x.device, dtype=x.dtype)
+    check(lib().cfpp_actnorm_fwd(_p(x), _p(z), _p(ldj), _p(base_t), _p(base_logs), _p(None if c is None else _f32(c)), _p(logp_c),
+                                 float(logp_scale), mode, B, D, HW, _stream()), 'actnorm_fwd')
+    return z, ldj
+
+
+def actnorm_stats(x):
+    _need_cuda(x); x = _f32(x)
+    B, D = x.shape[0], x.shape[1]
+    HW = x[0, 0].numel()
+    mean = torch.empty(D, device=x.device, dtype=x.dtype); logstd = torch.empty_like(mean)
+    check(lib().cfpp_actnorm_stats(_p(x), _p(mean), _p(logstd), B, D, HW, _stream()), 'actnorm_stats')
+    return mean, logstd
+
+
+# ---------------------------------------------------------------------------------------------- coupling
+def coupling(x, h, add=None, logp_c=None, logp_scale=0.0):
+    _need_cuda(x, h); x = _f32(x); h = _f32(h)
+    B, Cc = x.shape[0], x.shape[1]
+    HW = x[0, 0].numel() if B else 1
+    z = torch.empty_like(x); ldj = torch.empty(B, device=x.device, dtype=x.dtype)
+    check(lib().cfpp_coupling_fwd(_p(x), _p(h), _p(None if add is None else _f32(add)), _p(logp_c), float(logp_scale),
+                                  _p(z), _p(ldj), B, Cc, HW, _stream()), 'coupling_fwd')
+    return z, ldj
+
+
+def pack_kmajor(w2d: torch.Tensor, pad_to: int = 16) -> torch.Tensor:
+    """(N, K) weight -> K-major (K, NP) with the output dim zero-padded to a multiple of `pad_to` (one-time weight prep)."""
+    N, K = w2d.shape
+    NP = (N + pad_to - 1) // pad_to * pad_to
+    out = torch.zeros((K, NP), device=w2d.device, dtype=torch.float32)
+    out[:, :N] = w2d.detach().t().to(torch.float32)
+    return out
+
+
+def pad_vec(v: torch.Tensor, pad_to: int = 16) -> torch.Tensor:
+    N = v.shape[0]
+    NP = (N + pad_to - 1) // pad_to * pad_to
+    out = torch.zeros(NP, device=v.device, dtype=torch.float32)
+    out[:N] = v.detach().to(torch.float32)
+    return out
+
+
+def conv_cond(x, cin, packed, H, W, KH, KW, cout, bias1_b=None):
+    """packed = (w1t, b1, w2t, b2, w3t, b3) from pack_kmajor/pad_vec; reads the first `cin` channels of x in place."""
+    _need_cuda(x)
+    xv, bstride = _half_view(x)
+    B = x.shape[0]
+    w1t, b1, w2t, b2, w3t, b3 = packed
+    ch = w2t.shape[0] // (KH * KW)
+    h = torch.empty((B, cout, H, W), device=x.device, dtype=torch.float32)
+    check(lib().cfpp_conv_cond_fwd(_p(xv), bstride, _p(h), _p(w1t), _p(b1), _p(None if bias1_b is None else _f32(bias1_b)),
+                                   _p(w2t), _p(b2), _p(w3t), _p(b3), B, cin, ch, cout, H, W, KH, KW, _stream()), 'conv_cond_fwd')
+    return h
+
+
+def vit_cond(x, desc: _cabi.VitDesc, cout, extra=None):
+    _need_cuda(x)
+    xv, bstride = _half_view(x)
+    B = x.shape[0]
+    h = torch.empty((B, cout, desc.H, desc.W), device=x.device, dtype=torch.float32)
+    cextra = 0 if extra is None else extra.shape[1]
+    check(lib().cfpp_vit_cond_fwd(_p(xv), bstride, _p(None if extra is None else _f32(extra)), cextra, _p(h), C.byref(desc), B, _stream()),
+          'vit_cond_fwd')
+    return h
+
+
+# ---------------------------------------------------------------------------------------------- GMM
+def gmm_logprob(x, mG, sG, wG, ctx_off=None, logp_c=None, logp_scale=0.0):
+    _need_cuda(x, mG)
+    M, K, D = mG.shape[0], mG.shape[1], mG.shape[2]
+    xv, bstride = _half_view(x)
+    B = x.shape[0]
+    HW = x.shape[2] * x.shape[3]
+    out = torch.empty((B, M), device=x.device, dtype=torch.float32)
+    ws = torch.empty(int(lib().cfpp_gmm_workspace_floats(M, K, D, HW)), device=x.device, dtype=torch.float32)
+    check(lib().cfpp_gmm_logprob(_p(xv), bstride, _p(_f32(mG)), _p(_f32(sG)), _p(_f32(wG)), _p(None if ctx_off is None else _f32(ctx_off)),
+                                 _p(logp_c), float(logp_scale), _p(out), _p(ws), B, M, K, D, HW, _stream()), 'gmm_logprob')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- context
+def embed_lookup(ctx, tables: Sequence[torch.Tensor]):
+    _need_cuda(ctx, *tables)
+    B, n = ctx.shape
+    width = tables[0].shape[1]
+    out = torch.empty((B, n * width), device=ctx.device, dtype=torch.float32)
+    arr = (vp * n)(*[vp(_f32(t).data_ptr()) for t in tables])
+    check(lib().cfpp_embed_lookup(_p(ctx.contiguous()), arr, n, width, _p(out), B, _stream()), 'embed_lookup')
+    return out
+
+
+def ctx_encode(ctx, noise, desc: _cabi.EncDesc, emit_stage=-1):
+    _need_cuda(ctx, noise)
+    B = ctx.shape[0]
+    c = torch.empty((B, desc.C), device=ctx.device, dtype=torch.float32)
+    logp = torch.empty(B, device=ctx.device, dtype=torch.float32)
+    check(lib().cfpp_ctx_encode(_p(ctx.contiguous()), _p(None if noise is None else _f32(noise)), _p(c), _p(logp), C.byref(desc),
+                                emit_stage, B, _stream()), 'ctx_encode')
+    return c, logp
+
+
+def linear(x, wt, b=None, relu=False, n_out=None):
+    """y = act(x @ wt + b); wt is K-major (K, N) (possibly column-padded: pass n_out to trim)."""
+    _need_cuda(x, wt); x = _f32(x)
+    B, K = x.shape
+    N = wt.shape[1]
+    y = torch.empty((B, N), device=x.device, dtype=torch.float32)
+    check(lib().cfpp_linear_fwd(_p(x), _p(wt), _p(b), _p(y), B, K, N, int(relu), _stream()), 'linear_fwd')
+    return y if n_out is None or n_out == N else y[:, :n_out]
+
+
+def ldj_accumulate(logdet, ldj):
+    _need_cuda(logdet, ldj)
+    B, M = logdet.shape
+    cols = 1 if ldj.dim() == 1 else ldj.shape[1]
+    check(lib().cfpp_ldj_accumulate(_p(logdet), _p(_f32(ldj)), B, M, cols, _stream()), 'ldj_accumulate')
+    return logdet

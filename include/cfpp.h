@@ -1,0 +1,176 @@
+/* cfpp.h -- C ABI of libcfpp.so: B200 (sm_100a) kernels for the ContextFlow++ flow log-density path.
+ *
+ * The reference (gudovskiy/contextflow) has no FFI: its hot path is the Python class API
+ * FlowLayer.forward(x, context) -> (z, ldj) (contextflow/layers/flowlayer.py:7-24) evaluated by PyTorch eager ops.
+ * This header is the boundary a binding replaces that path with; each entry point cites the reference
+ * code it computes.  Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (torch allocates); fp32 NCHW contiguous unless a
+ *     batch stride argument says otherwise; contexts are int64 (B, n_ctx);
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous on it;
+ *   - return value: 0 = ok, non-zero = error (message via cfpp_last_error(), thread-local); nothing is thrown
+ *     across the ABI and the library never exits the process; no global mutable state.
+ * File paths below are relative to /root/reference/contextflow.
+ */
+#ifndef CFPP_H_
+#define CFPP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFPP_OK 0
+#define CFPP_ERR_ARG 1
+#define CFPP_ERR_CUDA 2
+#define CFPP_ERR_UNSUPPORTED 3
+
+int cfpp_version(void);
+const char* cfpp_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches claim) */
+int64_t cfpp_launch_count(void);
+
+/* ---- index-only layers (bit exact) ------------------------------------------------------------------ */
+/* Squeeze.forward, layers/squeeze.py:10-11: y[b,(c p1 p2),h,w] = x[b,c,h*p1+i,w*p2+j]; (H,W) are INPUT dims. */
+int cfpp_squeeze_fwd(const float* x, float* y, int B, int C, int H, int W, int p1, int p2, void* stream);
+/* Squeeze.reverse, layers/squeeze.py:13-14; (H,W) are the dims of the un-squeezed OUTPUT. */
+int cfpp_squeeze_inv(const float* y, float* x, int B, int C, int H, int W, int p1, int p2, void* stream);
+/* PermuteAxes((0,2,1,3)).forward, layers/permute_axes.py:13-14: y[b,h,c,w] = x[b,c,h,w]. */
+int cfpp_permute_fwd(const float* x, float* y, int B, int C, int H, int W, void* stream);
+/* channel slice copy: y[b, 0:Cn, :] = x[b, c0:c0+Cn, :]  (SplitPrior's x[0], layers/splitprior.py:13-15). */
+int cfpp_slice_channels(const float* x, float* y, int B, int C, int HW, int c0, int Cn, void* stream);
+
+/* ---- image prologue ----------------------------------------------------------------------------------- */
+/* Dequantization.forward, layers/dequantize.py:14-17: y = x + u. */
+int cfpp_add_fwd(const float* x, const float* u, float* y, int64_t n, void* stream);
+/* Normalization.forward (scalar scale), layers/normalize.py:27-34: y = x / scale + translation. */
+int cfpp_normalize_fwd(const float* x, float* y, int64_t n, float scale, float translation, void* stream);
+/* LogitTransform.forward/logdet, layers/transforms.py:11-18: y = log x - log(1-x); ldj[b] = sum(-log x - log(1-x)). */
+int cfpp_logit_fwd(const float* x, float* y, float* ldj, int B, int n_per_sample, void* stream);
+/* Augment.forward + StandardNormal.log_prob, layers/augment.py:14-18, distributions/gaussian.py:50-72:
+ * y = cat([x, eps], 1) with eps (B,A,HW); ldj[b] = sum(0.5 log 2pi + 0.5 eps^2). */
+int cfpp_augment_fwd(const float* x, const float* eps, float* y, float* ldj, int B, int C, int A, int HW, void* stream);
+/* The four prologue layers of create_model (model.py:97-100) + optional Augment, in one pass:
+ * v = ((x+u)/s0 + t0)/s1 + t1; y = logit(v) (C channels) ++ eps (A channels, may be 0);
+ * ldj[b] = ldj_const + sum(-log v - log(1-v)) + sum(0.5 log 2pi + 0.5 eps^2). */
+int cfpp_prologue_fwd(const float* x, const float* u, const float* eps, float* y, float* ldj, int B, int C, int A, int HW,
+                      float s0, float t0, float s1, float t1, float ldj_const, void* stream);
+
+/* ---- invertible 1x1 conv and ActNorm ------------------------------------------------------------------- */
+/* torch.slogdet(NN)[1], layers/conv1x1.py:43,53: log|det A| of a DxD matrix (fp64 LU inside), D <= 128. */
+int cfpp_slogdet(const float* A, int D, float* logabsdet, void* stream);
+/* Conv1x1.forward, layers/conv1x1.py:28-57.
+ *   c == NULL : z = NN x per pixel; ldj[b] = HW * logabsdet.
+ *   c != NULL : c is the raw CN output (B,D,D); W_b = tril(c,-1) + diag(exp(diag c)) [- I + NN if contextflow];
+ *               ldj[b] = HW * ((contextflow ? logabsdet : 0) + sum diag c_b) + HW * logp_c[b].
+ * Optional fused ActNorm epilogue (t, logs non-NULL, per-sample (B,D) when an_per_sample else (D)):
+ *   z = (z - t) * exp(-logs); ldj[b] += sum_d logs (+ an_logp_scale * an_logp_c[b]).   (layers/actnorm.py:37-60) */
+int cfpp_conv1x1_fwd(const float* x, float* z, float* ldj, const float* NN, const float* logabsdet,
+                     const float* c, const float* logp_c, int contextflow,
+                     const float* an_t, const float* an_logs, int an_per_sample, const float* an_logp_c, float an_logp_scale,
+                     int B, int D, int HW, void* stream);
+/* ActNorm.forward, layers/actnorm.py:37-60: t,logs = base (D) [+ c (B,2D) 'b (p d)'] per mode:
+ *   mode 0: base only; mode 1: base + c (contextflow); mode 2: c only (conventional).
+ * z = (x - t) * exp(-logs); ldj[b] = sum_d logs[b,d] + logp_scale * logp_c[b]   (note: no H*W factor, App. C-1). */
+int cfpp_actnorm_fwd(const float* x, float* z, float* ldj, const float* base_t, const float* base_logs, const float* c,
+                     const float* logp_c, float logp_scale, int mode, int B, int D, int HW, void* stream);
+/* ActNorm.initialize, layers/actnorm.py:28-35: mean[d], logstd[d] = log(unbiased std + 1e-8) over (B,HW). */
+int cfpp_actnorm_stats(const float* x, float* mean, float* logstd, int B, int D, int HW, void* stream);
+
+/* ---- coupling -------------------------------------------------------------------------------------------- */
+/* The fused memory-bound coupling transform, layers/coupling.py:50-66 (also :131-148):
+ *   t = h[:, :C/2] (+ add[:, :C/2]); r = h[:, C/2:] (+ add[:, C/2:]); log_s = 2 tanh(r/2);
+ *   z = cat(x[:, :C/2], x[:, C/2:] * exp(log_s) + t); ldj[b] = sum log_s + logp_scale * logp_c[b].
+ * add (B,C) and logp_c (B) may be NULL.  One HBM pass: reads x,h once, writes z once (12*C*HW bytes/sample). */
+int cfpp_coupling_fwd(const float* x, const float* h, const float* add, const float* logp_c, float logp_scale,
+                      float* z, float* ldj, int B, int C, int HW, void* stream);
+/* Coupling.NN, layers/coupling.py:26-29: Conv(Cin->Ch,1x1) ReLU Conv(Ch->Ch, KHxKW, reflect pad (KH/2,KW/2)) ReLU
+ * Conv(Ch->Cout,1x1).  x is (B, >=Cin, H, W) with batch stride x_bstride (the coupling's x0 half is read in place).
+ * Weights are PACKED K-major: w1t (Cin,Ch), w2t (Ch*KH*KW, Ch) with k = (cin*KH+ky)*KW+kx, w3t (Ch,Cout).
+ * bias1_b (B,Ch) optional per-sample first-layer bias replacing b1 (conventional context concat, coupling.py:47). */
+int cfpp_conv_cond_fwd(const float* x, int64_t x_bstride, float* h,
+                       const float* w1t, const float* b1, const float* bias1_b,
+                       const float* w2t, const float* b2, const float* w3t, const float* b3,
+                       int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, void* stream);
+
+/* SimpleViT conditioner of TransCoupling, layers/simple_vit.py:91-127 (heads=1, dim_head=64, dim=mlp_dim=T, GELU-erf,
+ * LayerNorm eps 1e-5).  All weight matrices PACKED K-major (in_features, out_features). */
+typedef struct {
+  int Cin, H, W, p1, p2;     /* input channels (x0 half, or + concat), image size, patch size */
+  int T, depth, n_tok, patch_dim;
+  const float *ln0_w, *ln0_b;              /* LayerNorm(patch_dim) */
+  const float *pe_wt, *pe_b;               /* Linear(patch_dim -> T) */
+  const float *ln1_w, *ln1_b;              /* LayerNorm(T) */
+  const float *pos;                        /* (n_tok, T) sincos table (simple_vit.py:18-27) */
+  const float *lnf_w, *lnf_b;              /* transformer.norm */
+  const float* layers;                     /* depth x per-layer block, see cfpp_vit_layer_floats() */
+} cfpp_vit_desc;
+/* Packed matrices have their output dimension zero-padded to NP = 16*ceil(T/16) columns (pe_wt, Wo, W1, W2; biases too).
+ * floats per packed layer block: [ln_a w,b (2T)] [Wqkv^T (T*192)] [Wo^T (64*NP)] [ln_f w,b (2T)] [W1^T (T*NP)] [b1 (NP)] [W2^T (T*NP)] [b2 (NP)] */
+int64_t cfpp_vit_layer_floats(int T);
+/* h (B, T/(p1 p2), H, W).  extra (B, Cextra) optional per-sample constant channels appended to x0 (conventional concat). */
+int cfpp_vit_cond_fwd(const float* x, int64_t x_bstride, const float* extra, int Cextra, float* h,
+                      const cfpp_vit_desc* desc, int B, void* stream);
+
+/* ---- Gaussian-mixture log-prob ----------------------------------------------------------------------------- */
+/* GaussianMixtureDistribution.log_prob, layers/distributions/gaussian.py:142-161 (torch.distributions semantics):
+ * out[b,m] = logsumexp_k( logmix[m,k] + sum_e N(x[b,e]; mG[m,k,e] (+cm), softplus(sG[m,k,e] (+cs))) ) + logp_scale*logp_c[b]
+ * with e over (d,h,w), logmix = log_softmax(log(clamp(softmax(wG)/sum, eps, 1-eps))).
+ * ctx_off (B, 2*M*K*D) optional: 'b (p m k d)' mean / pre-softplus-scale offsets per sample. x has batch stride. */
+int cfpp_gmm_logprob(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* wG,
+                     const float* ctx_off, const float* logp_c, float logp_scale, float* out, float* workspace,
+                     int B, int M, int K, int D, int HW, void* stream);
+/* floats of caller-provided scratch cfpp_gmm_logprob needs (hoisted 1/(2 sigma^2) table + per-component constants) */
+int64_t cfpp_gmm_workspace_floats(int M, int K, int D, int HW);
+
+/* ---- context encoders -------------------------------------------------------------------------------------- */
+#define CFPP_MAX_CTX 8
+#define CFPP_ENC_MAXC 64
+enum { CFPP_EMB_ONEHOT = 0, CFPP_EMB_EYE = 1, CFPP_EMB_EMBED = 2, CFPP_EMB_DENSE = 3 /* embedding given as a (B,C) float matrix */ };
+enum { CFPP_ENC_EYESAMPLE = 0, CFPP_ENC_UNIFORM = 1, CFPP_ENC_VARDEQ = 2, CFPP_ENC_ARGMAX = 3, CFPP_ENC_PROBSAMPLE = 4 };
+/* ContextEncoder = Sequential(embedding, surjection) (model.py:30-90): context (B,n) int64 -> c (B,C), logp_c (B).
+ * Embeddings: layers/rtdl/nn/_embeddings.py:103-109,140-150,265-283.  Surjections: layers/dequantize.py:55-63 (uniform),
+ * :107-116 (variational), :239-268 (argmax bits, MSB first), :133-136 (eye), :152-161 (prob).  Inner flow:
+ * FlowInvSequential.sample (layers/flowsequential.py:60-69) over ConditionalGaussianDistribution.sample
+ * (distributions/gaussian.py:263-270) and 2 x [FC, ActNormFC, CouplingFC]. */
+typedef struct {
+  int emb, type, n_ctx, C;
+  int card[CFPP_MAX_CTX];
+  int bits[CFPP_MAX_CTX];
+  int emb_dim;                              /* embed: columns per feature */
+  const float* emb_w[CFPP_MAX_CTX];         /* embed: (card_i, emb_dim) */
+  const float* dense;                       /* CFPP_EMB_DENSE: (B,C) already-embedded input */
+  const float* qbins;                       /* (n_in) uniform/vardeq */
+  const float* ldj_per_dim;                 /* (n_in) */
+  const float* temperature;                 /* (1) sigmoid flow */
+  int inner_dim;                            /* columns per feature of the inner (mean, log-scale) embedding = 2C/n_ctx */
+  const float* inner_w[CFPP_MAX_CTX];       /* (card_i, inner_dim) */
+  const float* fc[2];                       /* FC.NN (C,C) */
+  const float* fc_logabsdet[2];             /* device scalars */
+  const float* an_t[2];
+  const float* an_logs[2];
+  const float* cw1t[2]; const float* cb1[2];   /* CouplingFC: (C/2 -> 2C) packed K-major */
+  const float* cw2t[2]; const float* cb2[2];   /* (2C -> 2C) */
+  const float* cw3t[2]; const float* cb3[2];   /* (2C -> C) */
+} cfpp_enc_desc;
+/* noise: randn (B,C) for vardeq/argmax/probsample, rand (B,n_in) for uniform, NULL for eyesample.
+ * emit_stage: -1 = full encoder; 0 / 1 = stop before ActNormFC #0 / #1 and write that (B,C) activation to c
+ * (used once for the data-dependent ActNorm initialisation, layers/actnorm.py:53); 2 = stop after the conditional
+ * Gaussian draw and write (x, log q) -- ConditionalGaussianDistribution.sample alone (gaussian.py:263-270). */
+int cfpp_ctx_encode(const int64_t* ctx, const float* noise, float* c, float* logp_c, const cfpp_enc_desc* desc,
+                    int emit_stage, int B, void* stream);
+/* CatEmbeddings.forward (stack=False), layers/rtdl/nn/_embeddings.py:265-283: out[b] = cat_i tables[i][ctx[b,i]], each `width` wide.
+ * `tables` is a HOST array of n_ctx device pointers. */
+int cfpp_embed_lookup(const int64_t* ctx, const float* const* tables, int n_ctx, int width, float* out, int B, void* stream);
+/* y (B,N) = act(x (B,K) @ wt (K,N) + b): the CN context networks (nn.Linear; coupling.py:37, actnorm.py:21, conv1x1.py:22). */
+int cfpp_linear_fwd(const float* x, const float* wt, const float* b, float* y, int B, int K, int N, int relu, void* stream);
+
+
+/* ---- container ------------------------------------------------------------------------------------------------ */
+/* FlowSequential.forward, layers/flowsequential.py:23: logdet (B,M) += ldj (B,cols) with cols = 1 (broadcast) or M. */
+int cfpp_ldj_accumulate(float* logdet, const float* ldj, int B, int M, int cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFPP_H_ */

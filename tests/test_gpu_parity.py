@@ -1,0 +1,107 @@
+"""GPU parity: the CUDA path (through the C ABI) against the committed reference goldens and against the CPU oracle.
+Gates: z rtol 1e-4 / atol 1e-5; ldj, log-prob rtol 1e-4 / atol 1e-3; bits-per-dim 1e-3; index work bit exact."""
+import numpy as np
+import pytest
+import torch
+
+from contextflow_b200 import builder, rng, synth
+from oracle import flow_oracle as O
+from tests.golden.cases import CASES
+from tests.helpers import (BPD_ATOL, L_ATOL, L_RTOL, Z_ATOL, Z_RTOL, assert_close, case_inputs, golden_state, load_golden)
+
+pytestmark = pytest.mark.gpu
+
+
+def build_cuda_model(case):
+    conf = case['conf']
+    model = builder.build_named(conf)
+    sd = model.state_dict()
+    synth.fill_state(sd, case.get('wseed', 'w0'))
+    if case.get('fresh_actnorm'):
+        for k in sd:
+            if k.endswith('.initialized'):
+                sd[k].fill_(0)
+    model.load_state_dict(sd)
+    return model.cuda().eval()
+
+
+def run_traced(model, x, ctx, tape):
+    rec = {}
+    hooks = []
+    for i, m in enumerate(model.sequence_modules):
+        hooks.append(m.register_forward_hook(lambda mod, inp, out, i=i: rec.__setitem__(i, (out[0].detach().cpu(), out[1].detach().cpu()))))
+    with torch.no_grad(), rng.use_source(tape):
+        z, logp = model(x.cuda(), ctx.cuda())
+    for h in hooks:
+        h.remove()
+    torch.cuda.synchronize()
+    return z.cpu(), logp.cpu(), rec
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_cuda_matches_reference_golden(name):
+    case = CASES[name]
+    g = load_golden(name)
+    model = build_cuda_model(case)
+    assert {k: list(v.shape) for k, v in model.state_dict().items()} == g['keys']
+    x, ctx = case_inputs(case)
+    tape = synth.NoiseTape(case.get('nseed', 'noise0'))
+    z, logp, rec = run_traced(model, x, ctx, tape)
+    assert [tuple(d) for d in tape.log] == [(k, tuple(s)) for k, s in g['draws']], 'RNG contract: draw order / shapes'
+    for i in range(int(g['n_layers'])):
+        zi, ldj = rec[i]
+        assert_close(ldj.numpy(), g[f'ldj_{i}'], L_RTOL, L_ATOL, f'{name} layer {i} {g["layer_types"][i]} ldj')
+        zd = zi.double()
+        ref = g[f'zsum_{i}']
+        assert_close(np.array([zd.sum().item(), zd.abs().sum().item()]), ref, 0.0, Z_RTOL * float(ref[1]) + 1e-5,
+                     f'{name} layer {i} {g["layer_types"][i]} z-sum')
+    assert_close(z.numpy(), g['z'], Z_RTOL, Z_ATOL * max(1.0, float(np.abs(g['z']).max())), f'{name} z')
+    assert_close(logp.numpy(), g['logp'], L_RTOL, L_ATOL, f'{name} logp')
+    ds = case['conf']['data_size']
+    assert_close(O.bits_per_dim(logp, ds).numpy(), O.bits_per_dim(torch.from_numpy(g['logp']), ds).numpy(), 0.0, BPD_ATOL, f'{name} bpd')
+    if case.get('fresh_actnorm'):
+        sd = model.state_dict()
+        for k, v in g.items():
+            if k.startswith('post:'):
+                assert_close(sd[k[5:]].cpu().numpy(), v, 1e-4, 1e-5, f'{name} {k}')
+
+
+@pytest.mark.parametrize('name,B', [('cfg1', 9), ('cfg2', 11), ('cfg3', 5), ('cfg4', 67), ('cifar_conventional', 6), ('msl_conv', 19)])
+def test_cuda_matches_oracle_per_layer(name, B):
+    """Fresh seeded inputs (not in the goldens), ragged batch sizes; every layer's full z and ldj against the oracle."""
+    case = dict(CASES[name], B=B, iseed='in1', nseed='noise1')
+    g = load_golden(name)
+    stack, state = golden_state(g, case)
+    model = build_cuda_model(case)
+    x, ctx = case_inputs(case)
+    ora = {}
+    O.forward(stack, state, x, ctx, synth.NoiseTape('noise1'), torch.float32, lambda lay, z, ldj: ora.__setitem__(int(lay['key']), (z.clone(), ldj.clone())))
+    _, logp_o = O.forward(stack, state, x, ctx, synth.NoiseTape('noise1'), torch.float32)
+    z, logp, rec = run_traced(model, x, ctx, synth.NoiseTape('noise1'))
+    for i in sorted(ora):
+        zo, lo = ora[i]
+        scale = max(1.0, float(zo.abs().max()))
+        if stack['layers'][i]['op'] in ('squeeze', 'permute'):
+            assert torch.equal(rec[i][0], zo.float()), f'{name} layer {i}: index op must be bit exact'
+        else:
+            assert_close(rec[i][0].numpy(), zo.numpy(), Z_RTOL, Z_ATOL * scale, f'{name} layer {i} {stack["layers"][i]["op"]} z')
+        assert_close(rec[i][1].numpy(), lo.numpy(), L_RTOL, L_ATOL, f'{name} layer {i} {stack["layers"][i]["op"]} ldj')
+    assert_close(logp.numpy(), logp_o.numpy(), L_RTOL, L_ATOL, f'{name} logp')
+
+
+def test_empty_batch_and_single_sample():
+    case = CASES['cfg4']
+    model = build_cuda_model(case)
+    x, ctx = synth.make_inputs(case['conf'], 1, 'in2')
+    with torch.no_grad(), rng.use_source(synth.NoiseTape('n2')):
+        z, lp = model(x.cuda(), ctx.cuda())
+    assert lp.shape == (1, 1) and torch.isfinite(lp).all()
+    with torch.no_grad(), rng.use_source(synth.NoiseTape('n2')):
+        z0, lp0 = model(x[:0].cuda(), ctx[:0].cuda())
+    assert lp0.shape == (0, 1)
+
+
+def test_cpu_tensor_is_rejected_loudly():
+    from contextflow_b200 import ops
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ops.squeeze(torch.zeros(1, 1, 2, 2), 2, 2)
