@@ -13,7 +13,7 @@ class PermuteAxes(FlowLayer):
         self.permutation = tuple(permutation)
         self.inverse_permutation = sorted(range(len(self.permutation)), key=self.permutation.__getitem__)
 
-    def _apply(self, x, perm):
+    def _permute(self, x, perm):
         if tuple(perm) == tuple(range(len(perm))):
             return x.clone()
         if tuple(perm) != (0, 2, 1, 3):
@@ -21,10 +21,10 @@ class PermuteAxes(FlowLayer):
         return ops.permute_chw(x)
 
     def forward(self, input, context=None):
-        return self._apply(input, self.permutation), self.logdet(input, context)
+        return self._permute(input, self.permutation), self.logdet(input, context)
 
     def reverse(self, input, context=None):
-        return self._apply(input, self.inverse_permutation)
+        return self._permute(input, self.inverse_permutation)
 
     def logdet(self, input, context=None):
         return input.new_zeros(len(input))

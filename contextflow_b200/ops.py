@@ -11,6 +11,50 @@ from . import _cabi
 from ._cabi import check, lib, vp
 
 
+class OpTimer:
+    """Collects (op, cuda start event, cuda end event, work dict) per libcfpp launch on the launching stream (bench.py)."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        out = {}
+        for name, s, e, work in self.records:
+            d = out.setdefault(name, dict(ms=0.0, n=0, bytes=0.0, flops=0.0))
+            d['ms'] += s.elapsed_time(e); d['n'] += 1
+            d['bytes'] += work.get('bytes', 0.0); d['flops'] += work.get('flops', 0.0)
+        return out
+
+
+_timer = None          # set to an OpTimer to time every launch with CUDA events
+_work = {}             # algorithmic work of the next launch (bytes / flops), set by the wrapper that knows the shapes
+
+
+def set_timer(t):
+    global _timer
+    _timer = t
+
+
+def _call(name, args, label=None):
+    global _work
+    fn = getattr(lib(), 'cfpp_' + name)
+    if _timer is None:
+        _work = {}
+        check(fn(*args), name)
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = fn(*args)
+    e.record()
+    _timer.records.append((name, s, e, _work)); _work = {}
+    check(rc, name)
+
+
+def _set_work(**kw):
+    global _work
+    _work = kw
+
+
 def _stream():
     return vp(torch.cuda.current_stream().cuda_stream)
 
@@ -48,7 +92,8 @@ def squeeze(x, p1, p2):
     _need_cuda(x); x = _f32(x)
     B, Cc, H, W = x.shape
     y = torch.empty((B, Cc * p1 * p2, H // p1, W // p2), device=x.device, dtype=x.dtype)
-    check(lib().cfpp_squeeze_fwd(_p(x), _p(y), B, Cc, H, W, p1, p2, _stream()), 'squeeze_fwd')
+    _set_work(bytes=8.0 * x.numel())
+    _call('squeeze_fwd', (_p(x), _p(y), B, Cc, H, W, p1, p2, _stream()), 'squeeze_fwd')
     return y
 
 
@@ -57,7 +102,7 @@ def unsqueeze(y, p1, p2):
     B, Cs, Hs, Ws = y.shape
     Cc, H, W = Cs // (p1 * p2), Hs * p1, Ws * p2
     x = torch.empty((B, Cc, H, W), device=y.device, dtype=y.dtype)
-    check(lib().cfpp_squeeze_inv(_p(y), _p(x), B, Cc, H, W, p1, p2, _stream()), 'squeeze_inv')
+    _call('squeeze_inv', (_p(y), _p(x), B, Cc, H, W, p1, p2, _stream()), 'squeeze_inv')
     return x
 
 
@@ -68,7 +113,8 @@ def permute_chw(x):
     step = max(1, 65535 // max(W, 1))
     for b0 in range(0, B, step):
         nb = min(step, B - b0)
-        check(lib().cfpp_permute_fwd(_p(x[b0:]), _p(y[b0:]), nb, Cc, H, W, _stream()), 'permute_fwd')
+        _set_work(bytes=8.0 * nb * Cc * H * W)
+        _call('permute_fwd', (_p(x[b0:]), _p(y[b0:]), nb, Cc, H, W, _stream()), 'permute_fwd')
     return y
 
 
@@ -76,7 +122,8 @@ def slice_channels(x, c0, cn):
     _need_cuda(x); x = _f32(x)
     B, Cc, H, W = x.shape
     y = torch.empty((B, cn, H, W), device=x.device, dtype=x.dtype)
-    check(lib().cfpp_slice_channels(_p(x), _p(y), B, Cc, H * W, c0, cn, _stream()), 'slice_channels')
+    _set_work(bytes=8.0 * y.numel())
+    _call('slice_channels', (_p(x), _p(y), B, Cc, H * W, c0, cn, _stream()), 'slice_channels')
     return y
 
 
@@ -84,14 +131,14 @@ def slice_channels(x, c0, cn):
 def add(x, u):
     _need_cuda(x, u); x = _f32(x); u = _f32(u)
     y = torch.empty_like(x)
-    check(lib().cfpp_add_fwd(_p(x), _p(u), _p(y), x.numel(), _stream()), 'add_fwd')
+    _call('add_fwd', (_p(x), _p(u), _p(y), x.numel(), _stream()), 'add_fwd')
     return y
 
 
 def normalize(x, scale: float, translation: float):
     _need_cuda(x); x = _f32(x)
     y = torch.empty_like(x)
-    check(lib().cfpp_normalize_fwd(_p(x), _p(y), x.numel(), scale, translation, _stream()), 'normalize_fwd')
+    _call('normalize_fwd', (_p(x), _p(y), x.numel(), scale, translation, _stream()), 'normalize_fwd')
     return y
 
 
@@ -99,7 +146,7 @@ def logit(x):
     _need_cuda(x); x = _f32(x)
     B = x.shape[0]
     y = torch.empty_like(x); ldj = torch.empty(B, device=x.device, dtype=x.dtype)
-    check(lib().cfpp_logit_fwd(_p(x), _p(y), _p(ldj), B, x[0].numel() if B else 0, _stream()), 'logit_fwd')
+    _call('logit_fwd', (_p(x), _p(y), _p(ldj), B, x[0].numel() if B else 0, _stream()), 'logit_fwd')
     return y, ldj
 
 
@@ -113,7 +160,7 @@ def augment(x, eps):
         _need_cuda(x); x = _f32(x)
     y = torch.empty((B, Cc + A) + tuple(eps.shape[2:]), device=eps.device, dtype=eps.dtype)
     ldj = torch.empty(B, device=eps.device, dtype=eps.dtype)
-    check(lib().cfpp_augment_fwd(_p(x), _p(eps), _p(y), _p(ldj), B, Cc, A, HW, _stream()), 'augment_fwd')
+    _call('augment_fwd', (_p(x), _p(eps), _p(y), _p(ldj), B, Cc, A, HW, _stream()), 'augment_fwd')
     return y, ldj
 
 
@@ -125,7 +172,8 @@ def prologue(x, u, eps, s0, t0, s1, t1, ldj_const):
         eps = _f32(eps)
     y = torch.empty((B, Cc + A, H, W), device=x.device, dtype=x.dtype)
     ldj = torch.empty(B, device=x.device, dtype=x.dtype)
-    check(lib().cfpp_prologue_fwd(_p(x), _p(u), _p(eps), _p(y), _p(ldj), B, Cc, A, H * W, s0, t0, s1, t1, ldj_const, _stream()), 'prologue_fwd')
+    _set_work(bytes=4.0 * (2 * x.numel() + (0 if eps is None else eps.numel()) + y.numel()))
+    _call('prologue_fwd', (_p(x), _p(u), _p(eps), _p(y), _p(ldj), B, Cc, A, H * W, s0, t0, s1, t1, ldj_const, _stream()), 'prologue_fwd')
     return y, ldj
 
 
@@ -133,7 +181,7 @@ def prologue(x, u, eps, s0, t0, s1, t1, ldj_const):
 def slogdet(A):
     _need_cuda(A); A = _f32(A)
     out = torch.empty(1, device=A.device, dtype=A.dtype)
-    check(lib().cfpp_slogdet(_p(A), A.shape[0], _p(out), _stream()), 'slogdet')
+    _call('slogdet', (_p(A), A.shape[0], _p(out), _stream()), 'slogdet')
     return out
 
 
@@ -143,7 +191,8 @@ def conv1x1(x, NN, logabsdet, c=None, logp_c=None, contextflow=False, an_t=None,
     HW = x[0, 0].numel() if B else 1
     z = torch.empty_like(x); ldj = torch.empty(B, device=x.device, dtype=x.dtype)
     per_sample = int(an_t is not None and an_t.dim() == 2)
-    check(lib().cfpp_conv1x1_fwd(_p(x), _p(z), _p(ldj), _p(_f32(NN)), _p(logabsdet), _p(None if c is None else _f32(c)),
+    _set_work(bytes=8.0 * x.numel() + (0 if c is None else 4.0 * c.numel()), flops=2.0 * D * x.numel())
+    _call('conv1x1_fwd', (_p(x), _p(z), _p(ldj), _p(_f32(NN)), _p(logabsdet), _p(None if c is None else _f32(c)),
                                  _p(logp_c), int(bool(contextflow)), _p(an_t), _p(an_logs), per_sample, _p(an_logp_c),
                                  float(an_logp_scale), B, D, HW, _stream()), 'conv1x1_fwd')
     return z, ldj
@@ -154,7 +203,8 @@ def actnorm(x, base_t, base_logs, c=None, logp_c=None, logp_scale=0.0, mode=0):
     B, D = x.shape[0], x.shape[1]
     HW = x[0, 0].numel() if B else 1
     z = torch.empty_like(x); ldj = torch.empty(B, device=x.device, dtype=x.dtype)
-    check(lib().cfpp_actnorm_fwd(_p(x), _p(z), _p(ldj), _p(base_t), _p(base_logs), _p(None if c is None else _f32(c)), _p(logp_c),
+    _set_work(bytes=8.0 * x.numel())
+    _call('actnorm_fwd', (_p(x), _p(z), _p(ldj), _p(base_t), _p(base_logs), _p(None if c is None else _f32(c)), _p(logp_c),
                                  float(logp_scale), mode, B, D, HW, _stream()), 'actnorm_fwd')
     return z, ldj
 
@@ -164,7 +214,7 @@ def actnorm_stats(x):
     B, D = x.shape[0], x.shape[1]
     HW = x[0, 0].numel()
     mean = torch.empty(D, device=x.device, dtype=x.dtype); logstd = torch.empty_like(mean)
-    check(lib().cfpp_actnorm_stats(_p(x), _p(mean), _p(logstd), B, D, HW, _stream()), 'actnorm_stats')
+    _call('actnorm_stats', (_p(x), _p(mean), _p(logstd), B, D, HW, _stream()), 'actnorm_stats')
     return mean, logstd
 
 
@@ -174,7 +224,8 @@ def coupling(x, h, add=None, logp_c=None, logp_scale=0.0):
     B, Cc = x.shape[0], x.shape[1]
     HW = x[0, 0].numel() if B else 1
     z = torch.empty_like(x); ldj = torch.empty(B, device=x.device, dtype=x.dtype)
-    check(lib().cfpp_coupling_fwd(_p(x), _p(h), _p(None if add is None else _f32(add)), _p(logp_c), float(logp_scale),
+    _set_work(bytes=12.0 * x.numel())
+    _call('coupling_fwd', (_p(x), _p(h), _p(None if add is None else _f32(add)), _p(logp_c), float(logp_scale),
                                   _p(z), _p(ldj), B, Cc, HW, _stream()), 'coupling_fwd')
     return z, ldj
 
@@ -204,7 +255,8 @@ def conv_cond(x, cin, packed, H, W, KH, KW, cout, bias1_b=None):
     w1t, b1, w2t, b2, w3t, b3 = packed
     ch = w2t.shape[0] // (KH * KW)
     h = torch.empty((B, cout, H, W), device=x.device, dtype=torch.float32)
-    check(lib().cfpp_conv_cond_fwd(_p(xv), bstride, _p(h), _p(w1t), _p(b1), _p(None if bias1_b is None else _f32(bias1_b)),
+    _set_work(bytes=4.0 * B * H * W * (cin + cout), flops=2.0 * B * H * W * (cin * ch + ch * ch * KH * KW + ch * cout))
+    _call('conv_cond_fwd', (_p(xv), bstride, _p(h), _p(w1t), _p(b1), _p(None if bias1_b is None else _f32(bias1_b)),
                                    _p(w2t), _p(b2), _p(w3t), _p(b3), B, cin, ch, cout, H, W, KH, KW, _stream()), 'conv_cond_fwd')
     return h
 
@@ -215,7 +267,8 @@ def vit_cond(x, desc: _cabi.VitDesc, cout, extra=None):
     B = x.shape[0]
     h = torch.empty((B, cout, desc.H, desc.W), device=x.device, dtype=torch.float32)
     cextra = 0 if extra is None else extra.shape[1]
-    check(lib().cfpp_vit_cond_fwd(_p(xv), bstride, _p(None if extra is None else _f32(extra)), cextra, _p(h), C.byref(desc), B, _stream()),
+    _set_work(bytes=4.0 * B * desc.H * desc.W * (desc.Cin + cout), flops=2.0 * B * desc.n_tok * (desc.patch_dim * desc.T + desc.depth * (desc.T * 192 + 2 * desc.n_tok * 64 + 64 * desc.T + 2 * desc.T * desc.T)))
+    _call('vit_cond_fwd', (_p(xv), bstride, _p(None if extra is None else _f32(extra)), cextra, _p(h), C.byref(desc), B, _stream()),
           'vit_cond_fwd')
     return h
 
@@ -229,7 +282,8 @@ def gmm_logprob(x, mG, sG, wG, ctx_off=None, logp_c=None, logp_scale=0.0):
     HW = x.shape[2] * x.shape[3]
     out = torch.empty((B, M), device=x.device, dtype=torch.float32)
     ws = torch.empty(int(lib().cfpp_gmm_workspace_floats(M, K, D, HW)), device=x.device, dtype=torch.float32)
-    check(lib().cfpp_gmm_logprob(_p(xv), bstride, _p(_f32(mG)), _p(_f32(sG)), _p(_f32(wG)), _p(None if ctx_off is None else _f32(ctx_off)),
+    _set_work(bytes=4.0 * B * D * HW + 4.0 * B * M, flops=3.0 * B * M * K * D * HW)
+    _call('gmm_logprob', (_p(xv), bstride, _p(_f32(mG)), _p(_f32(sG)), _p(_f32(wG)), _p(None if ctx_off is None else _f32(ctx_off)),
                                  _p(logp_c), float(logp_scale), _p(out), _p(ws), B, M, K, D, HW, _stream()), 'gmm_logprob')
     return out
 
@@ -241,7 +295,7 @@ def embed_lookup(ctx, tables: Sequence[torch.Tensor]):
     width = tables[0].shape[1]
     out = torch.empty((B, n * width), device=ctx.device, dtype=torch.float32)
     arr = (vp * n)(*[vp(_f32(t).data_ptr()) for t in tables])
-    check(lib().cfpp_embed_lookup(_p(ctx.contiguous()), arr, n, width, _p(out), B, _stream()), 'embed_lookup')
+    _call('embed_lookup', (_p(ctx.contiguous()), arr, n, width, _p(out), B, _stream()), 'embed_lookup')
     return out
 
 
@@ -250,7 +304,7 @@ def ctx_encode(ctx, noise, desc: _cabi.EncDesc, emit_stage=-1):
     B = ctx.shape[0]
     c = torch.empty((B, desc.C), device=ctx.device, dtype=torch.float32)
     logp = torch.empty(B, device=ctx.device, dtype=torch.float32)
-    check(lib().cfpp_ctx_encode(_p(ctx.contiguous()), _p(None if noise is None else _f32(noise)), _p(c), _p(logp), C.byref(desc),
+    _call('ctx_encode', (_p(ctx.contiguous()), _p(None if noise is None else _f32(noise)), _p(c), _p(logp), C.byref(desc),
                                 emit_stage, B, _stream()), 'ctx_encode')
     return c, logp
 
@@ -261,7 +315,7 @@ def linear(x, wt, b=None, relu=False, n_out=None):
     B, K = x.shape
     N = wt.shape[1]
     y = torch.empty((B, N), device=x.device, dtype=torch.float32)
-    check(lib().cfpp_linear_fwd(_p(x), _p(wt), _p(b), _p(y), B, K, N, int(relu), _stream()), 'linear_fwd')
+    _call('linear_fwd', (_p(x), _p(wt), _p(b), _p(y), B, K, N, int(relu), _stream()), 'linear_fwd')
     return y if n_out is None or n_out == N else y[:, :n_out]
 
 
@@ -269,5 +323,5 @@ def ldj_accumulate(logdet, ldj):
     _need_cuda(logdet, ldj)
     B, M = logdet.shape
     cols = 1 if ldj.dim() == 1 else ldj.shape[1]
-    check(lib().cfpp_ldj_accumulate(_p(logdet), _p(_f32(ldj)), B, M, cols, _stream()), 'ldj_accumulate')
+    _call('ldj_accumulate', (_p(logdet), _p(_f32(ldj)), B, M, cols, _stream()), 'ldj_accumulate')
     return logdet

@@ -1,0 +1,55 @@
+"""Batch sharding of the log-density path over the GPUs of one box.
+
+Every sample's (z, ldj, logp) depends only on that sample, its context row and its noise rows; weights are replicated.
+One process per GPU evaluates a contiguous batch slice; the only exchange on the inference path is the final gather of
+the (B/N, M) log-probabilities (NCCL all-gather over NVLink; `gloo` in the CPU tests).  No data-path collective."""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous, near-equal slices: the first n % world ranks get one extra row."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class ShardedLogProb:
+    """log_prob over a global batch: each rank scores its slice with `local_fn(x, ctx) -> (b, M)`, then all-gather."""
+
+    def __init__(self, local_fn: Callable, mixtures: int, group: Optional[dist.ProcessGroup] = None):
+        self.local_fn, self.M, self.group = local_fn, mixtures, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def local_slice(self, x, ctx):
+        lo, hi = shard_bounds(x.shape[0], self.world, self.rank)
+        return x[lo:hi], (None if ctx is None else ctx[lo:hi])
+
+    def gather(self, local_logp: torch.Tensor, total: int) -> torch.Tensor:
+        """(b_r, M) per rank -> (total, M) on every rank, rows in global batch order (ragged slices are padded)."""
+        if self.world == 1:
+            return local_logp
+        width = -(-total // self.world)
+        pad = torch.zeros((width, self.M), device=local_logp.device, dtype=local_logp.dtype)
+        pad[: local_logp.shape[0]] = local_logp
+        out = torch.empty((self.world * width, self.M), device=local_logp.device, dtype=local_logp.dtype)
+        dist.all_gather_into_tensor(out, pad, group=self.group)
+        rows = []
+        for r in range(self.world):
+            lo, hi = shard_bounds(total, self.world, r)
+            rows.append(out[r * width: r * width + (hi - lo)])
+        return torch.cat(rows, 0)
+
+    def log_prob(self, x, ctx=None):
+        """x, ctx hold the GLOBAL batch on every rank (replicated loader); returns the global (B, M) log-prob."""
+        xs, cs = self.local_slice(x, ctx)
+        return self.gather(self.local_fn(xs, cs), x.shape[0])
+
+    def log_prob_local(self, x_local, ctx_local, total: int):
+        """Each rank already holds only its slice (sharded loader)."""
+        return self.gather(self.local_fn(x_local, ctx_local), total)

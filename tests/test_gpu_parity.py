@@ -29,7 +29,8 @@ def run_traced(model, x, ctx, tape):
     rec = {}
     hooks = []
     for i, m in enumerate(model.sequence_modules):
-        hooks.append(m.register_forward_hook(lambda mod, inp, out, i=i: rec.__setitem__(i, (out[0].detach().cpu(), out[1].detach().cpu()))))
+        hooks.append(m.register_forward_hook(
+            lambda mod, inp, out, i=i: rec.__setitem__(i, (out[0].detach().cpu(), out[1].detach().cpu(), inp[0].detach().cpu()))))
     with torch.no_grad(), rng.use_source(tape):
         z, logp = model(x.cuda(), ctx.cuda())
     for h in hooks:
@@ -49,7 +50,7 @@ def test_cuda_matches_reference_golden(name):
     z, logp, rec = run_traced(model, x, ctx, tape)
     assert [tuple(d) for d in tape.log] == [(k, tuple(s)) for k, s in g['draws']], 'RNG contract: draw order / shapes'
     for i in range(int(g['n_layers'])):
-        zi, ldj = rec[i]
+        zi, ldj = rec[i][:2]
         assert_close(ldj.numpy(), g[f'ldj_{i}'], L_RTOL, L_ATOL, f'{name} layer {i} {g["layer_types"][i]} ldj')
         zd = zi.double()
         ref = g[f'zsum_{i}']
@@ -81,9 +82,11 @@ def test_cuda_matches_oracle_per_layer(name, B):
     for i in sorted(ora):
         zo, lo = ora[i]
         scale = max(1.0, float(zo.abs().max()))
-        if stack['layers'][i]['op'] in ('squeeze', 'permute'):
-            assert torch.equal(rec[i][0], zo.float()), f'{name} layer {i}: index op must be bit exact'
-        else:
+        op = stack['layers'][i]['op']
+        if op in ('squeeze', 'permute'):        # index work: bit exact on the layer's own input
+            want = O.squeeze(rec[i][2], stack['layers'][i]['p']) if op == 'squeeze' else O.permute_chw(rec[i][2])
+            assert torch.equal(rec[i][0], want), f'{name} layer {i}: index op must be bit exact'
+        if True:
             assert_close(rec[i][0].numpy(), zo.numpy(), Z_RTOL, Z_ATOL * scale, f'{name} layer {i} {stack["layers"][i]["op"]} z')
         assert_close(rec[i][1].numpy(), lo.numpy(), L_RTOL, L_ATOL, f'{name} layer {i} {stack["layers"][i]["op"]} ldj')
     assert_close(logp.numpy(), logp_o.numpy(), L_RTOL, L_ATOL, f'{name} logp')
