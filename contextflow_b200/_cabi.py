@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(_HERE, 'libcfpp.so')
 
 MAX_CTX = 8
 ENC_MAXC = 64
+MAX_ENC_BATCH = 64
 EMB = dict(onehot=0, eye=1, embed=2, dense=3)
 ENC = dict(eyesample=0, uniform=1, vardeq=2, argmax=3, probsample=4)
 
@@ -53,8 +54,12 @@ _SIGNATURES = {
     'cfpp_vit_layer_floats': (i64, [i32]),
     'cfpp_vit_cond_fwd': (i32, [vp, i64, vp, i32, vp, C.POINTER(VitDesc), i32, vp]),
     'cfpp_gmm_logprob': (i32, [vp, i64, vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, vp]),
+    'cfpp_gmm_logprob_ctxtab': (i32, [vp, i64, vp, vp, vp, vp, i32, C.POINTER(i32), C.POINTER(vp), i32, vp, f32, vp, vp, i64,
+                                      i32, i32, i32, i32, i32, vp]),
+    'cfpp_gmm_ctxtab_workspace_bytes': (i64, [i32, i32, i32, i32, i32, i32, C.POINTER(i32)]),
     'cfpp_gmm_workspace_floats': (i64, [i32, i32, i32, i32]),
     'cfpp_ctx_encode': (i32, [vp, vp, vp, vp, C.POINTER(EncDesc), i32, i32, vp]),
+    'cfpp_ctx_encode_batch': (i32, [vp, vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i32, vp]),
     'cfpp_embed_lookup': (i32, [vp, C.POINTER(vp), i32, i32, vp, i32, vp]),
     'cfpp_linear_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     'cfpp_ldj_accumulate': (i32, [vp, vp, i32, i32, i32, vp]),

@@ -41,61 +41,77 @@ __global__ void slogdet_kernel(const float* __restrict__ A, int D, float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Conv1x1 (+ optional ActNorm epilogue).  One thread per pixel keeps the D input channels in registers; the DxD
-// matrix (shared, or assembled per sample from the raw context matrix c) sits in shared memory and is read as
-// warp-broadcast float4.  A CTA covers S samples x PT pixels (S>1 only when HW is small).
+// Conv1x1 (+ optional ActNorm epilogue): per sample a (D x D) by (D x HW) product.  A CTA owns NSUB sub-tiles, each
+// (one sample, PT pixels); the matrix (shared, or assembled per sample from the raw context matrix c) is kept TRANSPOSED
+// in shared memory so that a thread's 4 output rows are one 128-bit load, the pixel tile likewise; each thread owns a
+// 4 (rows) x 4 (pixels) register tile: 16 FMA per two LDS.128.
 // ---------------------------------------------------------------------------------------------------------------
 struct Conv1x1Args {
   const float* x; float* z; float* ldj; const float* NN; const float* logabsdet;
   const float* c; const float* logp_c; int contextflow;
   const float* an_t; const float* an_logs; int an_per_sample; const float* an_logp_c; float an_logp_scale;
-  int B, D, HW, S, PT, tiles_per_sample;
+  int B, D, HW, PT, NI, TPS, NSUB, tiles_per_sample, WS;
 };
 
-template <int DMAX>
+template <bool VEC>
 __global__ void __launch_bounds__(256) conv1x1_kernel(const Conv1x1Args a) {
   extern __shared__ float4 smem4[];
-  float* Wsm = reinterpret_cast<float*>(smem4);
-  const int D = a.D, HW = a.HW;
-  constexpr int DP = DMAX;                               // padded row length (multiple of 4)
-  const int mstride = D * DP + 4;                        // +4 floats: per-sample matrices land on different banks
-  const int group = blockIdx.x / a.tiles_per_sample, tile = blockIdx.x % a.tiles_per_sample;
-  const int b0 = group * a.S;
-  const int nmat = a.c ? a.S : 1;
+  const int D = a.D, HW = a.HW, PT = a.PT, WS = a.WS;
+  const int nmat = a.c ? a.NSUB : 1;
+  float* Wt = reinterpret_cast<float*>(smem4);                 // [nmat][D][WS]   Wt[j][i] = W[i][j]
+  float* xs = Wt + (int64_t)nmat * D * WS;                     // [NSUB][D][PT]
+  const int64_t total_sub = (int64_t)a.B * a.tiles_per_sample;
+  const int64_t st0 = (int64_t)blockIdx.x * a.NSUB;
 
-  // ---- assemble the matrices ----
-  for (int idx = threadIdx.x; idx < nmat * D * DP; idx += blockDim.x) {
-    const int m = idx / (D * DP), r = idx % (D * DP), i = r / DP, j = r % DP;
-    float v = 0.f;
-    const int b = b0 + m;
-    if (j < D && b < a.B) {
-      const float nn = a.NN[i * D + j];
-      if (a.c) {                                         // conv1x1.py:36-49
-        const float cij = a.c[((int64_t)b * D + i) * D + j];
-        v = (j < i) ? cij : (j == i ? expf(cij) : 0.f);
-        if (a.contextflow) v = (v - (i == j ? 1.f : 0.f)) + nn;
-      } else v = nn;
+  // ---- assemble the matrices (transposed) and the pixel tiles: one warp per (matrix row | channel row), lanes along it ----
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int mi = warp; mi < nmat * D; mi += nwarps) {
+    const int m = mi / D, i = mi - m * D;
+    const int64_t st = st0 + m;
+    float* Wm = Wt + (int64_t)m * D * WS + i;
+    if (!a.c) {
+      for (int j = lane; j < D; j += 32) Wm[j * WS] = a.NN[i * D + j];
+    } else if (st < total_sub) {                               // conv1x1.py:36-49
+      const float* crow = a.c + ((st / a.tiles_per_sample) * D + i) * D;
+      for (int j = lane; j < D; j += 32) {
+        const float cij = crow[j];
+        float v = (j < i) ? cij : (j == i ? expf(cij) : 0.f);
+        if (a.contextflow) v = (v - (i == j ? 1.f : 0.f)) + a.NN[i * D + j];
+        Wm[j * WS] = v;
+      }
     }
-    Wsm[m * mstride + i * DP + j] = v;
+  }
+  for (int mj = warp; mj < a.NSUB * D; mj += nwarps) {
+    const int m = mj / D, j = mj - m * D;
+    const int64_t st = st0 + m;
+    float* xr = xs + (int64_t)mj * PT;
+    if (st < total_sub) {
+      const int64_t b = st / a.tiles_per_sample; const int p0t = (int)(st % a.tiles_per_sample) * PT;
+      const float* xg = a.x + (b * D + j) * HW + p0t;
+      for (int pl = lane; pl < PT; pl += 32) xr[pl] = (p0t + pl < HW) ? xg[pl] : 0.f;
+    } else {
+      for (int pl = lane; pl < PT; pl += 32) xr[pl] = 0.f;
+    }
   }
   __syncthreads();
 
-  const int s = threadIdx.x / a.PT, pl = threadIdx.x % a.PT;
-  const int b = b0 + s, p = tile * a.PT + pl;
-  if (s >= a.S || b >= a.B) return;
-  const bool active = p < HW;
+  const int m = threadIdx.x / a.TPS, t = threadIdx.x % a.TPS;
+  const int64_t st = st0 + m;
+  if (m >= a.NSUB || st >= total_sub) return;
+  const int64_t b = st / a.tiles_per_sample;
+  const int ptile = (int)(st % a.tiles_per_sample);
 
-  // ---- per-sample ldj (first pixel of the first tile) ----
-  if (tile == 0 && pl == 0) {
+  // ---- per-sample ldj (one thread per sample) ----
+  if (ptile == 0 && t == 0) {
     float l = 0.f;
     if (a.c) {
       float cl = 0.f;
-      for (int i = 0; i < D; ++i) cl += a.c[((int64_t)b * D + i) * D + i];
+      for (int i = 0; i < D; ++i) cl += a.c[(b * D + i) * D + i];
       l = (float)HW * ((a.contextflow ? a.logabsdet[0] : 0.f) + cl);
       if (a.logp_c) l += a.logp_c[b] * (float)HW;
     } else l = a.logabsdet[0] * (float)HW;
     if (a.an_logs) {
-      const float* lg = a.an_logs + (a.an_per_sample ? (int64_t)b * D : 0);
+      const float* lg = a.an_logs + (a.an_per_sample ? b * D : 0);
       float sl = 0.f;
       for (int i = 0; i < D; ++i) sl += lg[i];
       l += sl;
@@ -103,29 +119,43 @@ __global__ void __launch_bounds__(256) conv1x1_kernel(const Conv1x1Args a) {
     }
     a.ldj[b] = l;
   }
-  if (!active) return;
 
-  float xr[DMAX];
-  const float* xb = a.x + (int64_t)b * D * HW + p;
+  const int ig = t % a.NI, pg = t / a.NI;
+  const int i0 = 4 * ig, p0 = 4 * pg;
+  const float* Wm = Wt + (a.c ? (int64_t)m * D * WS : 0) + i0;
+  const float* xm = xs + (int64_t)m * D * PT + p0;
+  float acc[4][4];
 #pragma unroll
-  for (int j = 0; j < DMAX; ++j) xr[j] = (j < D) ? xb[(int64_t)j * HW] : 0.f;
-
-  const float* Wm = Wsm + (a.c ? s * mstride : 0);
-  float* zb = a.z + (int64_t)b * D * HW + p;
-  const float* at = a.an_t ? a.an_t + (a.an_per_sample ? (int64_t)b * D : 0) : nullptr;
-  const float* al = a.an_logs ? a.an_logs + (a.an_per_sample ? (int64_t)b * D : 0) : nullptr;
-  for (int i = 0; i < D; ++i) {
-    const float4* wr = reinterpret_cast<const float4*>(Wm + i * DP);
-    float acc0 = 0.f, acc1 = 0.f;
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int j4 = 0; j4 < DMAX / 4; ++j4) {
-      const float4 w = wr[j4];
-      acc0 = fmaf(w.x, xr[4 * j4 + 0], acc0); acc1 = fmaf(w.y, xr[4 * j4 + 1], acc1);
-      acc0 = fmaf(w.z, xr[4 * j4 + 2], acc0); acc1 = fmaf(w.w, xr[4 * j4 + 3], acc1);
+    for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < D; ++j) {
+    const float4 w = *reinterpret_cast<const float4*>(Wm + j * WS);
+    const float4 xv = *reinterpret_cast<const float4*>(xm + j * PT);
+    const float wr[4] = {w.x, w.y, w.z, w.w}, xq[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[r][q] = fmaf(wr[r], xq[q], acc[r][q]);
+  }
+  const float* at = a.an_t ? a.an_t + (a.an_per_sample ? b * D : 0) : nullptr;
+  const float* al = a.an_logs ? a.an_logs + (a.an_per_sample ? b * D : 0) : nullptr;
+  const int p = ptile * PT + p0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + r;
+    if (i >= D) break;
+    float v[4] = {acc[r][0], acc[r][1], acc[r][2], acc[r][3]};
+    if (al) { const float tt = at[i], e = expf(-al[i]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = (v[q] - tt) * e; }
+    float* zp = a.z + (b * D + i) * HW + p;
+    if (VEC) { if (p < HW) *reinterpret_cast<float4*>(zp) = make_float4(v[0], v[1], v[2], v[3]); }
+    else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (p + q < HW) zp[q] = v[q];
     }
-    float v = acc0 + acc1;
-    if (al) v = (v - at[i]) * expf(-al[i]);
-    zb[(int64_t)i * HW] = v;
   }
 }
 
@@ -205,17 +235,6 @@ __global__ void actnorm_stats_kernel(const float* __restrict__ x, float* __restr
   }
 }
 
-template <int DMAX>
-static int launch_conv1x1(const Conv1x1Args& a, cudaStream_t st) {
-  const int nmat = a.c ? a.S : 1;
-  const size_t smem = ((size_t)nmat * (a.D * DMAX + 4)) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(conv1x1_kernel<DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-  const int groups = (a.B + a.S - 1) / a.S;
-  conv1x1_kernel<DMAX><<<groups * a.tiles_per_sample, a.S * a.PT, smem, st>>>(a);
-  return check_launch("conv1x1_fwd");
-}
-
 }  // namespace cfpp
 using namespace cfpp;
 
@@ -234,24 +253,37 @@ extern "C" int cfpp_conv1x1_fwd(const float* x, float* z, float* ldj, const floa
   CFPP_REQUIRE(D >= 1 && D <= 128 && HW >= 1, "conv1x1: D=%d HW=%d unsupported (D<=128)", D, HW);
   CFPP_REQUIRE((an_t == nullptr) == (an_logs == nullptr), "conv1x1: an_t and an_logs must be given together");
   if (B <= 0) return CFPP_OK;
-  Conv1x1Args a{x, z, ldj, NN, logabsdet, c, logp_c, contextflow, an_t, an_logs, an_per_sample, an_logp_c, an_logp_scale, B, D, HW, 1, 1, 1};
-  const int DMAX = D <= 8 ? 8 : D <= 16 ? 16 : D <= 32 ? 32 : D <= 64 ? 64 : D <= 80 ? 80 : 128;
-  // tile shape: up to 128 pixels per sample per CTA; pack samples when HW is small, bounded by shared memory
-  int PT = HW >= 128 ? 128 : ((HW + 31) / 32) * 32;
-  if (HW < 32) PT = HW;                                   // tiny images: exact, several samples per warp
-  int S = 128 / PT; if (S < 1) S = 1;
-  if (c) { const int maxS = (int)((160 * 1024) / ((size_t)(D * DMAX + 4) * sizeof(float))); if (S > maxS) S = maxS < 1 ? 1 : maxS; }
-  if (S > B) S = B;
-  a.S = S; a.PT = PT; a.tiles_per_sample = (HW + PT - 1) / PT;
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (DMAX) {
-    case 8: return launch_conv1x1<8>(a, st);
-    case 16: return launch_conv1x1<16>(a, st);
-    case 32: return launch_conv1x1<32>(a, st);
-    case 64: return launch_conv1x1<64>(a, st);
-    case 80: return launch_conv1x1<80>(a, st);
-    default: return launch_conv1x1<128>(a, st);
+  Conv1x1Args a{x, z, ldj, NN, logabsdet, c, logp_c, contextflow, an_t, an_logs, an_per_sample, an_logp_c, an_logp_scale, B, D, HW};
+  const int DP = (D + 3) / 4 * 4;
+  a.NI = DP / 4;
+  a.WS = DP + 4;                                            // row stride of the transposed matrix (16B aligned, bank-rotated)
+  int pt_cap = 4 * (128 / a.NI > 1 ? 128 / a.NI : 1);
+  int hw4 = ((HW < 128 ? HW : 128) + 3) / 4 * 4;
+  a.PT = hw4 < pt_cap ? hw4 : pt_cap;
+  a.TPS = a.NI * (a.PT / 4);
+  a.tiles_per_sample = (HW + a.PT - 1) / a.PT;
+  const size_t per_sub = ((size_t)D * a.PT + (c ? (size_t)D * a.WS : 0)) * sizeof(float);
+  const size_t fixed = c ? 0 : (size_t)D * a.WS * sizeof(float);
+  int nsub = 256 / a.TPS; if (nsub < 1) nsub = 1;
+  const int by_smem = (int)((100 * 1024 - fixed) / per_sub);
+  if (nsub > by_smem) nsub = by_smem < 1 ? 1 : by_smem;
+  const int64_t total_sub = (int64_t)B * a.tiles_per_sample;
+  if (nsub > total_sub) nsub = (int)total_sub;
+  a.NSUB = nsub;
+  const size_t smem = fixed + (size_t)nsub * per_sub;
+  CFPP_REQUIRE(a.TPS <= 256 && smem <= 200 * 1024, "conv1x1: tile does not fit (D=%d)", D);
+  const int threads = (nsub * a.TPS + 31) / 32 * 32;
+  const int64_t blocks = (total_sub + nsub - 1) / nsub;
+  const bool vec = (HW % 4 == 0) && (reinterpret_cast<uintptr_t>(z) % 16 == 0);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv1x1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv1x1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
   }
+  if (vec) conv1x1_kernel<true><<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(a);
+  else conv1x1_kernel<false><<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(a);
+  return check_launch("conv1x1_fwd");
 }
 
 extern "C" int cfpp_actnorm_fwd(const float* x, float* z, float* ldj, const float* base_t, const float* base_logs, const float* c,

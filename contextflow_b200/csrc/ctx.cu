@@ -17,11 +17,9 @@ __global__ void embed_lookup_kernel(const int64_t* __restrict__ ctx, EmbArgs a, 
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 
-__global__ void __launch_bounds__(128) ctx_encode_kernel(const int64_t* __restrict__ ctx, const float* __restrict__ noise,
-                                                         float* __restrict__ c_out, float* __restrict__ logp_out,
-                                                         const cfpp_enc_desc d, int emit_stage, int B) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+__device__ __forceinline__ void encode_sample(const int64_t* __restrict__ ctx, const float* __restrict__ noise,
+                                              float* __restrict__ c_out, float* __restrict__ logp_out,
+                                              const cfpp_enc_desc& d, int emit_stage, int b) {
   const int C = d.C, n = d.n_ctx;
   const int64_t* cb = ctx + (int64_t)b * n;
   float* co = c_out + (int64_t)b * C;
@@ -128,6 +126,29 @@ __global__ void __launch_bounds__(128) ctx_encode_kernel(const int64_t* __restri
   }
 }
 
+__global__ void __launch_bounds__(128) ctx_encode_kernel(const int64_t* __restrict__ ctx, const float* __restrict__ noise,
+                                                         float* __restrict__ c_out, float* __restrict__ logp_out,
+                                                         const cfpp_enc_desc d, int emit_stage, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) encode_sample(ctx, noise, c_out, logp_out, d, emit_stage, b);
+}
+
+// All the independent encoders of a run of flow layers in ONE launch: blockIdx.y selects the encoder.  Each layer of a
+// specialist model owns its own encoder (36 per forward for the CIFAR/ATM stacks); launched one by one they occupy a
+// fraction of the SMs and are latency bound.
+struct EncBatchPtrs { const float* noise[CFPP_MAX_ENC_BATCH]; float* c[CFPP_MAX_ENC_BATCH]; float* logp[CFPP_MAX_ENC_BATCH]; };
+
+__global__ void __launch_bounds__(128) ctx_encode_batch_kernel(const int64_t* __restrict__ ctx, const cfpp_enc_desc* __restrict__ descs,
+                                                               const EncBatchPtrs p, int B) {
+  __shared__ cfpp_enc_desc d;
+  const int e = blockIdx.y;
+  for (int i = threadIdx.x; i < (int)(sizeof(cfpp_enc_desc) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&d)[i] = reinterpret_cast<const uint32_t*>(descs + e)[i];
+  __syncthreads();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) encode_sample(ctx, p.noise[e], p.c[e], p.logp[e], d, -1, b);
+}
+
 // y (B,N) = act(x (B,K) @ wt (K,N) + bias): 64x64 tile, 4x4 per thread, K chunks of 16.
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
                                                      float* __restrict__ y, int B, int K, int N, int relu) {
@@ -196,6 +217,18 @@ extern "C" int cfpp_ctx_encode(const int64_t* ctx, const float* noise, float* c,
   if (B <= 0) return CFPP_OK;
   ctx_encode_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx, noise, c, logp_c, d, emit_stage, B);
   return check_launch("ctx_encode");
+}
+
+extern "C" int cfpp_ctx_encode_batch(const int64_t* ctx, const cfpp_enc_desc* descs_device, int n_enc, const float* const* noise,
+                                     float* const* c_out, float* const* logp_out, int B, void* stream) {
+  CFPP_REQUIRE(n_enc >= 1 && n_enc <= CFPP_MAX_ENC_BATCH, "ctx_encode_batch: n_enc=%d outside [1,%d]", n_enc, CFPP_MAX_ENC_BATCH);
+  CFPP_REQUIRE(descs_device && noise && c_out && logp_out, "ctx_encode_batch: null argument");
+  if (B <= 0) return CFPP_OK;
+  EncBatchPtrs p;
+  for (int i = 0; i < n_enc; ++i) { p.noise[i] = noise[i]; p.c[i] = c_out[i]; p.logp[i] = logp_out[i]; }
+  dim3 grid((B + 127) / 128, n_enc);
+  ctx_encode_batch_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(ctx, descs_device, p, B);
+  return check_launch("ctx_encode_batch");
 }
 
 extern "C" int cfpp_linear_fwd(const float* x, const float* wt, const float* b, float* y, int B, int K, int N, int relu, void* stream) {

@@ -186,6 +186,47 @@ class FusedEncoder:
         return ops.ctx_encode(context, noise, d)
 
 
+class EncoderBatch:
+    """The independent encoders of a run of consecutive flow layers, evaluated by ONE kernel launch (cfpp_ctx_encode_batch).
+    Noise is drawn per member in layer order, so the RNG contract is unchanged."""
+
+    def __init__(self, members):
+        self.members = members          # [(ContextPlan, FusedEncoder)]
+        self._key, self._dev = None, None
+
+    @staticmethod
+    def is_lookup(fused):
+        return fused.surj.kind == 'eyesample' and hasattr(fused.emb, 'tables')
+
+    def ready(self):
+        for _, f in self.members:
+            if f.surj.kind in ('vardeq', 'argmax', 'probsample'):
+                for _, an, _ in _inner_flow_parts(f.surj.encoder)[1]:
+                    if not an.is_initialized():
+                        return False
+        return True
+
+    def run(self, context):
+        if context.dim() != 2:
+            raise ValueError('The input must have two dimensions')
+        B, n_ctx = context.shape
+        widths = [f._width(n_ctx) for _, f in self.members]
+        descs = [f._descriptor(n_ctx, w) for (_, f), w in zip(self.members, widths)]
+        key = (context.device, tuple(id(d) for d in descs))
+        if key != self._key:
+            blob = bytearray(b''.join(bytes(d) for d in descs))
+            self._dev = torch.frombuffer(blob, dtype=torch.uint8).clone().to(context.device)
+            self._key, self._keep = key, descs
+        noises = [f._draw(B, w, context.device) for (_, f), w in zip(self.members, widths)]
+        step = _cabi.MAX_ENC_BATCH
+        dsize = ctypes.sizeof(_cabi.EncDesc)
+        for i0 in range(0, len(descs), step):
+            sl = slice(i0, i0 + step)
+            cs, lps = ops.ctx_encode_batch(context, self._dev[i0 * dsize:], noises[sl], widths[sl])
+            for (plan, _), c, lp in zip(self.members[sl], cs, lps):
+                plan.preset = (c, lp)
+
+
 def run_surjection(surj, x, context):
     """Standalone surjection.forward((x, context)) with an already-embedded x."""
     if not hasattr(surj, '_fused_dense'):

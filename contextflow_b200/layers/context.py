@@ -10,12 +10,19 @@ class ContextPlan:
     def __init__(self):
         self._fused = None
         self._owner = None
+        self.preset = None          # (c, logp_c) computed ahead by an EncoderBatch launch of the enclosing FlowSequential
 
-    def run(self, context_net, context):
+    def fused_for(self, context_net):
         from ._encoder_desc import FusedEncoder
         if self._owner is not context_net:
             self._owner = context_net
             self._fused = FusedEncoder.recognise(context_net)
-        if self._fused is not None:
+        return self._fused
+
+    def run(self, context_net, context):
+        if self.preset is not None:
+            out, self.preset = self.preset, None
+            return out
+        if self.fused_for(context_net) is not None:
             return self._fused(context)
         return context_net(context)

@@ -64,6 +64,14 @@ class GaussianMixtureDistribution(nn.Module):
         if isinstance(context, list):
             context = context[0]
         if self.context_net:
+            from .._encoder_desc import EncoderBatch
+            fused = self._plan.fused_for(self.context_net) if self._plan.preset is None else None
+            if fused is not None and EncoderBatch.is_lookup(fused) and context.dim() == 2:
+                # embed + eyesample (model.py:157,162): offsets are a table lookup with logp_c = 0 -> bucketed per-context tables
+                cards = [int(e.num_embeddings) for e in fused.emb._embeddings]
+                out = ops.gmm_logprob_ctxtab(input, self.mG, self.sG, self.wG, context, cards, fused.emb.tables())
+                if out is not None:
+                    return out
             c, logp_c = self._plan.run(self.context_net, context)       # c: 'b (p m k d)'
             return ops.gmm_logprob(input, self.mG, self.sG, self.wG, c, logp_c, float(H * W))
         return ops.gmm_logprob(input, self.mG, self.sG, self.wG)

@@ -20,11 +20,50 @@ class FlowSequential(nn.Module):
     def __iter__(self):
         yield from self.sequence_modules
 
+    def _encoder_groups(self):
+        """{index of first member layer: EncoderBatch}: runs of layers whose context encoders can share one launch.  A run
+        ends at any layer that draws noise itself (Augment, Dequantization) or whose context_net is an opaque callable."""
+        if getattr(self, '_groups', None) is not None:
+            return self._groups
+        from ._encoder_desc import EncoderBatch
+        from .augment import Augment
+        from .dequantize import Dequantization
+        groups, cur, start = {}, [], None
+
+        def close():
+            nonlocal cur, start
+            if len(cur) > 1:
+                groups[start] = EncoderBatch(cur)
+            cur, start = [], None
+
+        for i, m in enumerate(self.sequence_modules):
+            if isinstance(m, (Augment, Dequantization)):
+                close(); continue
+            owner = m.dist if hasattr(m, 'dist') and hasattr(m.dist, '_plan') else m
+            net = getattr(owner, 'context_net', None)
+            if net is None or not hasattr(owner, '_plan'):
+                continue
+            fused = owner._plan.fused_for(net)
+            if fused is None:
+                close(); continue
+            if EncoderBatch.is_lookup(fused):
+                continue
+            if start is None:
+                start = i
+            cur.append((owner._plan, fused))
+        close()
+        self._groups = groups
+        return groups
+
     def forward(self, input, context=None):
         B = input.shape[0]
         logdet = torch.zeros((B, self.mixtures), device=input.device, dtype=torch.float32)
         out = input
-        for module in self.sequence_modules:
+        groups = self._encoder_groups() if context is not None else {}
+        for i, module in enumerate(self.sequence_modules):
+            batch = groups.get(i)
+            if batch is not None and batch.ready():
+                batch.run(context)
             out, ldj = module(out, context)
             ops.ldj_accumulate(logdet, ldj)                     # (B,), (B,1) broadcast or (B,M)   (flowsequential.py:23)
         logprob = self.dist.log_prob(out, context)              # fresh (B, M) tensor: accumulate into it and return it

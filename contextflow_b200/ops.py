@@ -288,6 +288,26 @@ def gmm_logprob(x, mG, sG, wG, ctx_off=None, logp_c=None, logp_scale=0.0):
     return out
 
 
+def gmm_logprob_ctxtab(x, mG, sG, wG, ctx, cards, tables, logp_scale=0.0):
+    """GMM log-prob with embedding-lookup context offsets (bucketed per-context tables); None if the structure is unsupported."""
+    _need_cuda(x, mG, ctx)
+    M, K, D = mG.shape[0], mG.shape[1], mG.shape[2]
+    xv, bstride = _half_view(x)
+    B, HW, n = x.shape[0], x.shape[2] * x.shape[3], len(cards)
+    carr = (_cabi.i32 * n)(*cards)
+    need = int(lib().cfpp_gmm_ctxtab_workspace_bytes(B, M, K, D, HW, n, carr))
+    if need < 0:
+        return None
+    out = torch.empty((B, M), device=x.device, dtype=torch.float32)
+    ws = torch.empty(need, device=x.device, dtype=torch.uint8)
+    tabs = [_f32(t) for t in tables]
+    tarr = (vp * n)(*[vp(t.data_ptr()) for t in tabs])
+    _set_work(bytes=4.0 * B * D * HW + 4.0 * B * M, flops=3.0 * B * M * K * D * HW)
+    _call('gmm_logprob_ctxtab', (_p(xv), bstride, _p(_f32(mG)), _p(_f32(sG)), _p(_f32(wG)), _p(ctx.contiguous()), n, carr, tarr,
+                                 tabs[0].shape[1], None, float(logp_scale), _p(out), _p(ws), need, B, M, K, D, HW, _stream()))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- context
 def embed_lookup(ctx, tables: Sequence[torch.Tensor]):
     _need_cuda(ctx, *tables)
@@ -307,6 +327,21 @@ def ctx_encode(ctx, noise, desc: _cabi.EncDesc, emit_stage=-1):
     _call('ctx_encode', (_p(ctx.contiguous()), _p(None if noise is None else _f32(noise)), _p(c), _p(logp), C.byref(desc),
                                 emit_stage, B, _stream()), 'ctx_encode')
     return c, logp
+
+
+def ctx_encode_batch(ctx, descs_dev, noises, widths):
+    """n encoders over one context batch in a single launch; returns ([c_i (B, width_i)], [logp_i (B,)])."""
+    _need_cuda(ctx, descs_dev)
+    B, n = ctx.shape[0], len(widths)
+    c_all = torch.empty(B * sum(widths), device=ctx.device, dtype=torch.float32)
+    logp_all = torch.empty((n, B), device=ctx.device, dtype=torch.float32)
+    cs, off = [], 0
+    for w in widths:
+        cs.append(c_all[off: off + B * w].view(B, w)); off += B * w
+    arr = lambda ts: (vp * n)(*[vp(0 if t is None else t.data_ptr()) for t in ts])
+    noises = [None if t is None else _f32(t) for t in noises]
+    _call('ctx_encode_batch', (_p(ctx.contiguous()), _p(descs_dev), n, arr(noises), arr(cs), arr(list(logp_all)), B, _stream()))
+    return cs, list(logp_all)
 
 
 def linear(x, wt, b=None, relu=False, n_out=None):

@@ -123,6 +123,18 @@ int cfpp_gmm_logprob(const float* x, int64_t x_bstride, const float* mG, const f
 /* floats of caller-provided scratch cfpp_gmm_logprob needs (hoisted 1/(2 sigma^2) table + per-component constants) */
 int64_t cfpp_gmm_workspace_floats(int M, int K, int D, int HW);
 
+/* Same density when the context offsets are an embedding-table lookup (ContextEncoder(contexts,'embed','eyesample'), the only
+ * form create_model builds: model.py:157,162): ctx_off[b] = cat_i tables[i][ctx[b,i]] (each row `width` wide, n_ctx*width =
+ * 2*M*K*D).  The library buckets the batch by context tuple and hoists every sigma-dependent term per distinct scale
+ * context, so no transcendental is evaluated per Gaussian.  n_ctx <= 2 and prod(cards) <= 2048, else CFPP_ERR_UNSUPPORTED
+ * (use cfpp_embed_lookup + cfpp_gmm_logprob).  cards: HOST array; tables: HOST array of device pointers. */
+int cfpp_gmm_logprob_ctxtab(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* wG,
+                            const int64_t* ctx, int n_ctx, const int* cards, const float* const* tables, int width,
+                            const float* logp_c, float logp_scale, float* out, void* workspace, int64_t workspace_bytes,
+                            int B, int M, int K, int D, int HW, void* stream);
+/* bytes of scratch for cfpp_gmm_logprob_ctxtab, or -1 when that context structure is unsupported */
+int64_t cfpp_gmm_ctxtab_workspace_bytes(int B, int M, int K, int D, int HW, int n_ctx, const int* cards);
+
 /* ---- context encoders -------------------------------------------------------------------------------------- */
 #define CFPP_MAX_CTX 8
 #define CFPP_ENC_MAXC 64
@@ -159,6 +171,12 @@ typedef struct {
  * Gaussian draw and write (x, log q) -- ConditionalGaussianDistribution.sample alone (gaussian.py:263-270). */
 int cfpp_ctx_encode(const int64_t* ctx, const float* noise, float* c, float* logp_c, const cfpp_enc_desc* desc,
                     int emit_stage, int B, void* stream);
+/* Several independent encoders over the same context batch in one launch (every specialist layer owns its own encoder:
+ * 36 per forward for the CIFAR / ATM stacks).  descs_device: DEVICE array of n_enc descriptors (validated by the caller with
+ * the same rules as cfpp_ctx_encode); noise / c_out / logp_out: HOST arrays of n_enc device pointers. */
+#define CFPP_MAX_ENC_BATCH 64
+int cfpp_ctx_encode_batch(const int64_t* ctx, const cfpp_enc_desc* descs_device, int n_enc, const float* const* noise,
+                          float* const* c_out, float* const* logp_out, int B, void* stream);
 /* CatEmbeddings.forward (stack=False), layers/rtdl/nn/_embeddings.py:265-283: out[b] = cat_i tables[i][ctx[b,i]], each `width` wide.
  * `tables` is a HOST array of n_ctx device pointers. */
 int cfpp_embed_lookup(const int64_t* ctx, const float* const* tables, int n_ctx, int width, float* out, int B, void* stream);

@@ -1,0 +1,159 @@
+"""Op-level GPU tests through the C ABI: edge shapes (ragged / non-multiple-of-4 pixel counts, large D, B=1), both GMM context
+paths, index-op round trips, standalone module calls.  Reference values come from the CPU oracle's functions."""
+import math
+import pytest
+import torch
+
+from contextflow_b200 import layers as L, ops, rng, synth
+from contextflow_b200.layers.rtdl.nn._embeddings import CatEmbeddings, OneHotEncoder
+from oracle import flow_oracle as O
+from tests.helpers import L_ATOL, L_RTOL, Z_ATOL, Z_RTOL, assert_close
+
+pytestmark = pytest.mark.gpu
+dev = 'cuda'
+
+
+@pytest.mark.parametrize('B,C,H,W,p', [(3, 2, 4, 6, (2, 2)), (2, 38, 144, 1, (2, 1)), (1, 3, 32, 32, (2, 2)), (5, 4, 14, 14, (2, 2))])
+def test_squeeze_bit_exact_and_roundtrip(B, C, H, W, p):
+    x = synth.uniform('sq', (B, C, H, W))
+    y = ops.squeeze(x.to(dev), *p)
+    assert torch.equal(y.cpu(), O.squeeze(x, p))
+    assert torch.equal(ops.unsqueeze(y, *p).cpu(), x)
+
+
+@pytest.mark.parametrize('B,C,H,W', [(2, 76, 72, 1), (3, 5, 7, 3), (1, 33, 65, 1)])
+def test_permute_bit_exact(B, C, H, W):
+    x = synth.uniform('pm', (B, C, H, W))
+    assert torch.equal(ops.permute_chw(x.to(dev)).cpu(), x.permute(0, 2, 1, 3).contiguous())
+
+
+@pytest.mark.parametrize('B,D,HW,ctx', [(5, 8, 256, False), (7, 64, 16, True), (3, 76, 72, True), (2, 100, 49, False), (9, 26, 8, False),
+                                        (4, 12, 49, True), (1, 16, 256, True)])
+@pytest.mark.parametrize('contextflow', [True, False])
+def test_conv1x1_shapes(B, D, HW, ctx, contextflow):
+    x = synth.uniform('c1x', (B, D, HW, 1))
+    NN = torch.eye(D) + synth.uniform('c1w', (D, D)) * 0.2 / math.sqrt(D)
+    c = synth.uniform('c1c', (B, D * D)) * 0.1 if ctx else None
+    lp = synth.uniform('c1l', (B,)) if ctx else None
+    lad = ops.slogdet(NN.to(dev))
+    assert_close(lad.cpu().numpy(), torch.linalg.slogdet(NN.double())[1].float().reshape(1).numpy(), 1e-5, 1e-6, 'slogdet')
+    z, ldj = ops.conv1x1(x.to(dev), NN.to(dev), lad, None if c is None else c.to(dev), None if lp is None else lp.to(dev), contextflow)
+    if ctx:
+        cm = c.reshape(B, D, D)
+        diag = torch.diagonal(cm, dim1=-2, dim2=-1)
+        Wb = torch.tril(cm, -1) + torch.diag_embed(torch.exp(diag))
+        want_l = HW * diag.sum(-1)
+        if contextflow:
+            Wb = Wb - torch.eye(D) + NN
+            want_l = HW * (torch.linalg.slogdet(NN)[1] + diag.sum(-1))
+        want_l = want_l + lp * HW
+        want = torch.einsum('bij,bjhw->bihw', Wb, x)
+    else:
+        want = torch.einsum('ij,bjhw->bihw', NN, x)
+        want_l = (torch.linalg.slogdet(NN)[1] * HW).expand(B)
+    assert_close(z.cpu().numpy(), want.numpy(), Z_RTOL, Z_ATOL, 'conv1x1 z')
+    assert_close(ldj.cpu().numpy(), want_l.numpy(), L_RTOL, L_ATOL, 'conv1x1 ldj')
+
+
+@pytest.mark.parametrize('B,C,HW', [(3, 16, 256), (5, 26, 8), (2, 8, 49), (1, 76, 72), (70, 2, 1)])
+@pytest.mark.parametrize('with_ctx', [False, True])
+def test_coupling_elementwise(B, C, HW, with_ctx):
+    x = synth.uniform('cpx', (B, C, HW, 1)) * 2
+    h = synth.uniform('cph', (B, C, HW, 1)) * 3
+    add = synth.uniform('cpa', (B, C)) if with_ctx else None
+    lp = synth.uniform('cpl', (B,)) if with_ctx else None
+    z, ldj = ops.coupling(x.to(dev), h.to(dev), None if add is None else add.to(dev), None if lp is None else lp.to(dev), 3.0)
+    hh = h + add[:, :, None, None] if with_ctx else h
+    zo, lo = O.coupling_elementwise(x, hh)
+    if with_ctx:
+        lo = lo + 3.0 * lp
+    assert torch.equal(z.cpu()[:, :C // 2], x[:, :C // 2]), 'pass-through half must be copied bit exactly'
+    assert_close(z.cpu().numpy(), zo.numpy(), Z_RTOL, Z_ATOL, 'coupling z')
+    assert_close(ldj.cpu().numpy(), lo.numpy(), L_RTOL, L_ATOL, 'coupling ldj')
+
+
+def _gmm_oracle(x, mG, sG, wG, c, M, K):
+    state = {'g.mG': mG, 'g.sG': sG, 'g.wG': wG}
+    lay = dict(key='g', M=M, K=K, enc=None)
+    if c is None:
+        return O.gmm_log_prob(O._P(state, torch.float64), state, lay, x.double(), None, None, torch.float64)
+    B, D = x.shape[0], x.shape[1]
+    cc = c.double().reshape(B, 2, M, K, D, 1, 1)
+    mean = mG.double()[None] + cc[:, 0]; scale = torch.nn.functional.softplus(sG.double()[None] + cc[:, 1])
+    xx = x.double()[:, None, None]
+    comp = (-((xx - mean) ** 2) / (2 * scale ** 2) - scale.log() - math.log(math.sqrt(2 * math.pi))).sum((-3, -2, -1))
+    mix = torch.log_softmax(wG.double(), -1)
+    return torch.logsumexp(comp + mix[None], -1)
+
+
+@pytest.mark.parametrize('B,M,K,D,H,W,cards', [(11, 10, 8, 8, 16, 16, [15, 5]), (6, 2, 8, 38, 36, 1, [68]), (19, 1, 8, 26, 8, 1, [7]),
+                                                 (3, 3, 8, 4, 7, 7, [4, 3]), (1, 10, 8, 64, 4, 4, [15, 5])])
+def test_gmm_all_paths(B, M, K, D, H, W, cards):
+    x = synth.uniform('gx', (B, D, H, W)) * 2
+    mG, sG, wG = synth.uniform('gm', (M, K, D, H, W)), 1 + 0.3 * synth.uniform('gs', (M, K, D, H, W)), synth.uniform('gw', (M, K))
+    n = len(cards)
+    width = 2 * M * K * D // n
+    tabs = [synth.uniform(f'gt{i}', (card, width)) * 0.2 for i, card in enumerate(cards)]
+    ctx = torch.stack([synth.randint(f'gc{i}', (B,), card) for i, card in enumerate(cards)], 1)
+    c = torch.cat([t[ctx[:, i]] for i, t in enumerate(tabs)], 1)
+    want0 = _gmm_oracle(x, mG, sG, wG, None, M, K)
+    want1 = _gmm_oracle(x, mG, sG, wG, c, M, K)
+    cu = lambda t: t.to(dev)
+    got0 = ops.gmm_logprob(cu(x), cu(mG), cu(sG), cu(wG))
+    assert_close(got0.cpu().numpy(), want0.numpy(), L_RTOL, L_ATOL, 'gmm no-context')
+    c_dev = ops.embed_lookup(cu(ctx), [cu(t) for t in tabs])
+    assert torch.equal(c_dev.cpu(), c), 'embedding lookup is an exact gather'
+    got1 = ops.gmm_logprob(cu(x), cu(mG), cu(sG), cu(wG), c_dev)
+    assert_close(got1.cpu().numpy(), want1.numpy(), L_RTOL, L_ATOL, 'gmm per-sample context')
+    got2 = ops.gmm_logprob_ctxtab(cu(x), cu(mG), cu(sG), cu(wG), cu(ctx), cards, [cu(t) for t in tabs])
+    assert got2 is not None
+    assert_close(got2.cpu().numpy(), want1.numpy(), L_RTOL, L_ATOL, 'gmm bucketed context tables')
+    # in-place read of a channel-slice view (SplitPrior): same numbers from x embedded as the second half of a wider tensor
+    wide = torch.cat([torch.zeros_like(x), x], 1).to(dev)
+    got3 = ops.gmm_logprob(wide[:, D:], cu(mG), cu(sG), cu(wG))
+    assert torch.equal(got3, got0)
+
+
+def test_actnorm_stats_and_modes():
+    B, D, HW = 6, 10, 12
+    x = synth.uniform('anx', (B, D, HW, 1)) * 3 + 1
+    m, ls = ops.actnorm_stats(x.to(dev))
+    mo, lo = O.actnorm_init(x)
+    assert_close(m.cpu().numpy(), mo.numpy(), 1e-5, 1e-6, 'mean'); assert_close(ls.cpu().numpy(), lo.numpy(), 1e-5, 1e-6, 'logstd')
+    c = synth.uniform('anc', (B, 2 * D)); lp = synth.uniform('anl', (B,))
+    for mode in (0, 1, 2):
+        z, ldj = ops.actnorm(x.to(dev), m, ls, c.to(dev) if mode else None, lp.to(dev) if mode else None, 5.0, mode)
+        t = (mo if mode != 2 else 0) + (c[:, :D] if mode else 0)
+        lg = (lo if mode != 2 else 0) + (c[:, D:] if mode else 0)
+        t = t.expand(B, D) if torch.is_tensor(t) else t; lg = lg.expand(B, D)
+        want = (x - t[:, :, None, None]) * torch.exp(-lg[:, :, None, None])
+        assert_close(z.cpu().numpy(), want.numpy(), Z_RTOL, Z_ATOL, f'actnorm z mode {mode}')
+        assert_close(ldj.cpu().numpy(), (lg.sum(-1) + (5.0 * lp if mode else 0)).numpy(), L_RTOL, L_ATOL, f'actnorm ldj mode {mode}')
+
+
+def test_standalone_embedding_and_surjection_modules():
+    ctx = torch.stack([synth.randint('sc0', (9,), 6), synth.randint('sc1', (9,), 3)], 1)
+    oh, c2 = OneHotEncoder([6, 3]).to(dev)(ctx.to(dev))
+    want = torch.cat([torch.nn.functional.one_hot(ctx[:, 0], 6), torch.nn.functional.one_hot(ctx[:, 1], 3)], 1)
+    assert oh.dtype == torch.int64 and torch.equal(oh.cpu(), want) and torch.equal(c2.cpu(), ctx)
+    emb = CatEmbeddings([6, 3], 5).to(dev)
+    e, _ = emb(ctx.to(dev))
+    assert torch.equal(e.cpu(), torch.cat([emb._embeddings[i].weight.detach().cpu()[ctx[:, i]] for i in range(2)], 1))
+    surj = L.UniformCatDequantization(num_cats=[6, 3]).to(dev)
+    tape = synth.NoiseTape('su')
+    with rng.use_source(tape):
+        z, ldj = surj((ctx.to(dev), ctx.to(dev)))
+    u = synth.NoiseTape('su').rand((9, 2))
+    assert_close(z.cpu().numpy(), ((ctx.float() + u) / torch.tensor([6.0, 3.0])).numpy(), 1e-6, 1e-7, 'uniform dequant')
+    assert_close(ldj.cpu().numpy(), torch.full((9,), float(-2 * (math.log(6) + math.log(3)))).numpy(), 1e-6, 1e-6, 'uniform dequant ldj (x num_dims quirk)')
+    with pytest.raises(ValueError):
+        OneHotEncoder([6, 3]).to(dev)(ctx[:, 0].to(dev))
+
+
+def test_linear_and_ldj_accumulate():
+    x = synth.uniform('lx', (70, 20)); w = synth.uniform('lw', (33, 20)); b = synth.uniform('lb', (33,))
+    y = ops.linear(x.to(dev), ops.pack_kmajor(w.to(dev), 1), b.to(dev), relu=True)
+    assert_close(y.cpu().numpy(), torch.relu(x @ w.t() + b).numpy(), 1e-5, 1e-5, 'linear')
+    ld = torch.zeros(5, 3, device=dev)
+    ops.ldj_accumulate(ld, torch.arange(5., device=dev)); ops.ldj_accumulate(ld, torch.ones(5, 1, device=dev)); ops.ldj_accumulate(ld, torch.ones(5, 3, device=dev))
+    assert torch.equal(ld.cpu(), (torch.arange(5.)[:, None] + 2).expand(5, 3))
