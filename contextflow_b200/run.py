@@ -1,0 +1,44 @@
+"""Launcher: run the reference's UNMODIFIED model.py over this package's layers.
+
+    cd <reference>/contextflow && python -m contextflow_b200.run model.py --gpu 0 --dataset smap --action-type test ...
+
+model.py does `from layers import *` and `from layers.rtdl.nn._embeddings import *` (model.py:14-15) and is started from
+the reference directory, whose own `layers/` package would win on sys.path.  The replacement is therefore registered in
+sys.modules under those names BEFORE model.py executes; datasets/, utils/, config.py, experiment_*.py keep coming from
+the reference.
+"""
+import os
+import runpy
+import sys
+
+
+def install_layers():
+    """Register contextflow_b200.layers as the top-level `layers` package (and its rtdl sub-namespace)."""
+    import contextflow_b200.layers as L
+    import contextflow_b200.layers.rtdl as R
+    import contextflow_b200.layers.rtdl.nn as RN
+    import contextflow_b200.layers.rtdl.nn._embeddings as RE
+    sys.modules['layers'] = L
+    sys.modules['layers.rtdl'] = R
+    sys.modules['layers.rtdl.nn'] = RN
+    sys.modules['layers.rtdl.nn._embeddings'] = RE
+    for name, mod in list(sys.modules.items()):
+        if name.startswith('contextflow_b200.layers.'):
+            sys.modules.setdefault('layers.' + name[len('contextflow_b200.layers.'):], mod)
+    return L
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv:
+        raise SystemExit(__doc__)
+    script = os.path.abspath(argv[0])
+    install_layers()
+    sys.argv = [script] + argv[1:]
+    sys.path.insert(0, os.path.dirname(script))
+    os.chdir(os.path.dirname(script))
+    runpy.run_path(script, run_name='__main__')
+
+
+if __name__ == '__main__':
+    main()

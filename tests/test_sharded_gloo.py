@@ -1,0 +1,56 @@
+"""N>1 path on CPU: world_size-2 gloo processes shard a global batch, score their slices (the oracle stands in for the
+per-rank CUDA forward) and all-gather the log-probs; result must equal the single-process answer row for row."""
+import os, sys
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, B, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from contextflow_b200 import synth
+    from contextflow_b200.sharded import ShardedLogProb, shard_bounds
+    from oracle import flow_oracle as O
+    from tests.golden.cases import CASES
+    from tests.helpers import golden_state, load_golden
+    case = dict(CASES['cfg4'], B=B)
+    stack, state = golden_state(load_golden('cfg4'), case)
+    x, ctx = synth.make_inputs(case['conf'], B, 'shard')
+    eps = synth.normal('shard:eps', (B, 1, 8, 1))          # the Augment draw of cfg4, fixed per global row
+
+    class RowNoise:                                           # every rank draws the rows of ITS slice
+        def __init__(self, lo, hi): self.lo, self.hi = lo, hi
+        def randn(self, shape): return eps[self.lo:self.hi]
+        def rand(self, shape): raise AssertionError
+    lo, hi = shard_bounds(B, world, rank)
+    local = lambda xs, cs: O.log_prob(stack, state, xs, cs, RowNoise(lo, hi))
+    sh = ShardedLogProb(local, mixtures=1)
+    got = sh.log_prob(x, ctx)
+    got2 = sh.log_prob_local(x[lo:hi], ctx[lo:hi], B)
+    full = O.log_prob(stack, state, x, ctx, RowNoise(0, B))
+    ok = torch.allclose(got, full, rtol=1e-6, atol=1e-5) and torch.equal(got, got2) and got.shape == (B, 1)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('B', [10, 7])
+def test_world2_gloo_shard_and_gather(B):
+    port = 29500 + (os.getpid() % 2000) + B
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, B, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
+
+
+def test_shard_bounds_cover_batch():
+    from contextflow_b200.sharded import shard_bounds
+    for n in (0, 1, 7, 8, 9, 1000):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
