@@ -208,14 +208,15 @@ def main():
                              'GBps': round(v['bytes'] / sec / 1e9, 1) if sec > 0 else None, 'TFLOPps': round(v['flops'] / sec / 1e12, 3) if sec > 0 else None}
         top = next(iter(kernels))
         tv = summ[top]
-        hbm_bound = top not in ('conv_cond_fwd', 'vit_cond_fwd', 'gmm_logprob')
+        hbm_bound = top not in ('conv_cond_fwd', 'conv_cond_tc_fwd', 'vit_cond_fwd', 'gmm_logprob', 'gmm_logprob_ctxtab')
         if hbm_bound:
             ach = tv['bytes'] / (tv['ms'] / 1e3) / 1e9
             roof = {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': None, 'peak_source': hbm_src}
         else:
             ach = tv['flops'] / (tv['ms'] / 1e3) / 1e12
             roof = {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak, 'traffic': None,
-                    'peak_source': 'measured bf16 sustained (fp32-faithful 3xTF32 would be ~1/6 of it; this kernel is an FP32-FMA path)'}
+                    'peak_source': 'measured bf16 sustained; ' + ('tcgen05 kind::tf32 with the fp32-faithful 3-product split: the ceiling of this arithmetic is 1/6 of the bf16 peak'
+                                                                  if top == 'conv_cond_tc_fwd' else 'this kernel is an FP32-FMA path')}
         cv = summ.get('coupling_fwd')
         if cv:
             ach = cv['bytes'] / (cv['ms'] / 1e3) / 1e9

@@ -1,0 +1,524 @@
+// Conv-coupling conditioner (layers/coupling.py:26-29) on the 5th-generation tensor cores: tcgen05.mma kind::tf32 with
+// fp32-faithful 3xTF32 operand splitting, accumulators in TMEM, weights streamed by 1-D bulk TMA copies.
+//
+//   h = W3 * relu( conv_KHxKW_reflect( relu(W1 * x0 + b1) ) + b2 ) + b3          per pixel, per sample
+//
+// Mapping.  Pixels sit on the MMA M axis (128 rows per instruction), channels on N, input channels (x taps) on K (8 per
+// instruction).  A CTA keeps the activations of S whole samples resident in shared memory as K-major SWIZZLE_128B
+// operand rows (one 128-byte row = 32 channels of one stored pixel; `P` panels of 32 channels), each value stored twice:
+// v (the tensor core truncates it to tf32 = hi) and lo = v - trunc_tf32(v).  The kxk convolution needs no im2col copy:
+// a tap (ky,kx) is the same operand seen through a descriptor whose start row is shifted by ky*YS + kx.  Two layouts:
+//   plain   : stored row = s*RPS + yp*WP + xp over the reflect-padded image ((H+KH-1) x (W+KW-1)); accumulator row
+//             m = stored row of the output pixel; rows whose xp >= W are computed and thrown away;
+//   segment : (W % 8 == 0) the image row is cut into segments of 8 output pixels stored with their halo as GS = 8+KW-1
+//             rows; stored row = ((yp*S + s)*NSEG + seg)*GS + xs.  An MMA row-group of 8 is one segment and the descriptor's
+//             group stride (SBO) is GS*128 bytes, so every accumulator row is a real pixel (no waste on M).
+// fp32 accuracy from tf32 MMAs:  A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi.  The first two products are ONE instruction
+// with the stacked operand [B_hi ; B_lo] (N' = 2N, accumulator columns [0,N) and [N,2N)); the third accumulates into
+// [0,N); the epilogue adds the two column blocks.  (tools/umma_probe*.cu measured the descriptor conventions, the
+// 2^-21-grade accuracy of the split and the issue rates this layout is built on.)
+//
+// Roles (192 threads, one persistent CTA per SM): warps 0-3 = epilogue (TMEM -> bias/ReLU/split -> shared, final store
+// to HBM; also the x0 -> operand-row transform), warp 4 = MMA issuer (one thread), warp 5 = producer (weight chunks
+// through an mbarrier ring + next tile's x0 prefetch).  Per tile: stage 1 (1x1) -> epilogue 1 -> stage 2 (kxk, the
+// 94 %) -> epilogue 2 -> stage 3 (1x1) -> epilogue 3.
+#include "common.cuh"
+
+namespace cfpp {
+namespace tc {
+
+struct Plan {
+  int B, Cin, Ch, Cout, H, W, KH, KW;
+  int seg, S, NSEG, GS, YS, RPS, WP, HP;
+  int R, T1, T2, NG;                 // stored rows per tile, M-tiles of stage 1 / stages 2-3, row groups of stage 2 (segment)
+  int P, KS1, N2, N3;                // channel panels, k-steps of stage 1, N of stages 1-2, N of stage 3 (padded to 16)
+  int stage_bytes, nstages, ntiles;
+  int region_bytes;                  // bytes of one (hi|lo, panel) operand region
+  int off_ring, off_stage_x, off_bias, off_bar, smem_bytes;
+  long long x_bstride;
+};
+
+constexpr int kEpiThreads = 128;
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t sw128(int row, int k) { return row * 128 + ((((k >> 2) ^ row) & 7) << 4) + ((k & 3) << 2); }
+__device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok)
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor; sbo = byte stride between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int n) {   // kind::tf32, fp32 accumulate, A and B K-major, M = 128
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                 "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ int reflect(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+struct Args {
+  const float* x; float* h; const uint8_t* wpack; const float* b1; const float* b2; const float* b3; const float* bias1_b;
+};
+
+// Barrier slots (8 bytes each) inside the barrier block.
+enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_XFULL = 2 * kMaxStages, BAR_XEMPTY, BAR_AREADY, BAR_ACC1, BAR_ACC2, BAR_ACC3, BAR_H1, BAR_H2, BAR_COUNT };
+
+// stored operand row -> (sample, source pixel) of the reflect-padded image
+template <bool SEG>
+__device__ __forceinline__ void decode_stored(const Plan& p, int r, int& s, int& y, int& x) {
+  if (SEG) {
+    const int xs = r % p.GS; int q = r / p.GS;
+    const int sg = q % p.NSEG; q /= p.NSEG;
+    s = q % p.S; const int yp = q / p.S;
+    y = reflect(yp - p.KH / 2, p.H); x = reflect(sg * 8 + xs - p.KW / 2, p.W);
+  } else {
+    s = r / p.RPS; const int rem = r - s * p.RPS;
+    const int yp = rem / p.WP, xp = rem - yp * p.WP;
+    y = reflect(yp - p.KH / 2, p.H); x = reflect(xp - p.KW / 2, p.W);
+  }
+}
+// accumulator row of stages 2/3 -> output pixel; false for rows that are not a pixel
+template <bool SEG>
+__device__ __forceinline__ bool decode_out(const Plan& p, int m, int& s, int& y, int& x) {
+  if (SEG) {
+    int g = m >> 3; const int j = m & 7;
+    const int sg = g % p.NSEG; g /= p.NSEG;
+    s = g % p.S; y = g / p.S; x = sg * 8 + j;
+    return y < p.H;
+  } else {
+    s = m / p.RPS; const int rem = m - s * p.RPS;
+    y = rem / p.WP; x = rem - y * p.WP;
+    return s < p.S && y < p.H && x < p.W;
+  }
+}
+
+// TMEM accumulator (two column blocks of N) -> + bias -> ReLU -> (v, lo) -> operand row `row` of every panel.
+__device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, const float* __restrict__ bias, uint8_t* a_hi, uint8_t* a_lo,
+                                                    int region_bytes, int row, bool write) {
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16], u[16];
+    tmem_ld16(taddr + c0, v);
+    tmem_ld16(taddr + N + c0, u);
+    tmem_ld_wait();
+    if (write) {
+      uint8_t* ph = a_hi + (c0 >> 5) * region_bytes;
+      uint8_t* pl = a_lo + (c0 >> 5) * region_bytes;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 hi, lo;
+        float t;
+        t = fmaxf(v[4 * q + 0] + u[4 * q + 0] + bias[c0 + 4 * q + 0], 0.f); hi.x = t; lo.x = tf32_lo(t);
+        t = fmaxf(v[4 * q + 1] + u[4 * q + 1] + bias[c0 + 4 * q + 1], 0.f); hi.y = t; lo.y = tf32_lo(t);
+        t = fmaxf(v[4 * q + 2] + u[4 * q + 2] + bias[c0 + 4 * q + 2], 0.f); hi.z = t; lo.z = tf32_lo(t);
+        t = fmaxf(v[4 * q + 3] + u[4 * q + 3] + bias[c0 + 4 * q + 3], 0.f); hi.w = t; lo.w = tf32_lo(t);
+        const uint32_t off = sw128(row, (c0 & 31) + 4 * q);
+        *reinterpret_cast<float4*>(ph + off) = hi;
+        *reinterpret_cast<float4*>(pl + off) = lo;
+      }
+    }
+  }
+}
+
+template <bool SEG>
+__global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p, const Args a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* a_hi = base;                                     // [P][region]
+  uint8_t* a_lo = base + (size_t)p.P * p.region_bytes;      // [P][region]
+  uint8_t* ring = base + p.off_ring;
+  float* xstage = reinterpret_cast<float*>(base + p.off_stage_x);
+  float* sb1 = reinterpret_cast<float*>(base + p.off_bias);
+  float* sb2 = sb1 + p.N2;
+  float* sb3 = sb2 + p.N2;
+  const uint32_t bars = smem_u32(base + p.off_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + p.off_bar + BAR_COUNT * 8);
+  auto bar = [&](int i) { return bars + 8u * i; };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HW = p.H * p.W;
+  const int xfloats = p.Cin * HW;                           // staged floats per sample
+
+  if (tid == 0) {
+    for (int i = 0; i < p.nstages; ++i) { mbar_init(bar(BAR_FULL + i), 1); mbar_init(bar(BAR_EMPTY + i), 1); }
+    mbar_init(bar(BAR_XFULL), 1); mbar_init(bar(BAR_XEMPTY), kEpiThreads); mbar_init(bar(BAR_AREADY), kEpiThreads);
+    mbar_init(bar(BAR_ACC1), 1); mbar_init(bar(BAR_ACC2), 1); mbar_init(bar(BAR_ACC3), 1);
+    mbar_init(bar(BAR_H1), kEpiThreads); mbar_init(bar(BAR_H2), kEpiThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < p.N2; i += kThreads) { sb1[i] = i < p.Ch ? a.b1[i] : 0.f; sb2[i] = i < p.Ch ? a.b2[i] : 0.f; }
+  for (int i = tid; i < p.N3; i += kThreads) sb3[i] = i < p.Cout ? a.b3[i] : 0.f;
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int nchunks_tile = 1 + p.KH * p.KW * p.P + p.P;     // W1, W2 (tap, panel), W3 (panel)
+  const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 5) {
+    // ===================== producer: weight chunks through the ring, next tile's x0 into the staging buffer ==========
+    if (lane == 0) {
+      uint32_t chunk = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int b0 = tile * p.S, nS = min(p.S, p.B - b0);
+        mbar_wait(bar(BAR_XEMPTY), (it & 1) ^ 1);
+        mbar_expect_tx(bar(BAR_XFULL), (uint32_t)(nS * xfloats * 4));
+        for (int s = 0; s < nS; ++s)
+          bulk_g2s(smem_u32(xstage + (size_t)s * xfloats), a.x + (size_t)(b0 + s) * p.x_bstride, (uint32_t)(xfloats * 4), bar(BAR_XFULL));
+        for (int c = 0; c < nchunks_tile; ++c, ++chunk) {
+          const uint32_t st = chunk % p.nstages, round = chunk / p.nstages;
+          mbar_wait(bar(BAR_EMPTY + st), (round & 1) ^ 1);
+          const uint32_t bytes = (c < nchunks_tile - p.P) ? (uint32_t)(2 * p.N2 * 128) : (uint32_t)(2 * p.N3 * 128);
+          mbar_expect_tx(bar(BAR_FULL + st), bytes);
+          bulk_g2s(smem_u32(ring + (size_t)st * p.stage_bytes), a.wpack + (size_t)c * p.stage_bytes, bytes, bar(BAR_FULL + st));
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer ==================================================================================
+    if (lane == 0) {
+      const uint32_t idN2 = make_idesc(p.N2), id2N2 = make_idesc(2 * p.N2), idN3 = make_idesc(p.N3), id2N3 = make_idesc(2 * p.N3);
+      const uint32_t sbo2 = (uint32_t)p.GS * 128;
+      const uint32_t ahi0 = smem_u32(a_hi), alo0 = smem_u32(a_lo), ring0 = smem_u32(ring);
+      const uint32_t tile_cols2 = 2 * p.N2, tile_cols3 = 2 * p.N3;
+      uint32_t chunk = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const uint32_t ph = it & 1;
+        // ---- stage 1: H1 = W1 x0 over every stored row ----
+        mbar_wait(bar(BAR_AREADY), ph);
+        {
+          const uint32_t st = chunk % p.nstages, round = chunk / p.nstages; ++chunk;
+          mbar_wait(bar(BAR_FULL + st), round & 1);
+          tc_fence_after();
+          const uint64_t bdesc = make_desc(ring0 + st * p.stage_bytes, 1024);
+          for (int t = 0; t < p.T1; ++t) {
+            const uint64_t ah = make_desc(ahi0 + t * 16384, 1024), al = make_desc(alo0 + t * 16384, 1024);
+            const uint32_t d = tmem + t * tile_cols2;
+            for (int ks = 0; ks < p.KS1; ++ks) {
+              mma_tf32(d, ah + 2 * ks, bdesc + 2 * ks, id2N2, ks > 0);
+              mma_tf32(d, al + 2 * ks, bdesc + 2 * ks, idN2, 1);
+            }
+          }
+          tc_commit(bar(BAR_EMPTY + st));
+          tc_commit(bar(BAR_ACC1));
+        }
+        // ---- stage 2: KH x KW taps as shifted operand views ----
+        mbar_wait(bar(BAR_H1), ph);
+        tc_fence_after();
+        for (int tap = 0; tap < p.KH * p.KW; ++tap) {
+          const int ky = tap / p.KW, kx = tap - ky * p.KW;
+          const uint32_t tap_off = (uint32_t)(ky * p.YS + kx) * 128;
+          for (int pn = 0; pn < p.P; ++pn) {
+            const uint32_t st = chunk % p.nstages, round = chunk / p.nstages; ++chunk;
+            const int ksn = min(32, p.Ch - pn * 32) >> 3;
+            const uint32_t first = (tap | pn) == 0;
+            mbar_wait(bar(BAR_FULL + st), round & 1);
+            tc_fence_after();
+            const uint64_t bdesc = make_desc(ring0 + st * p.stage_bytes, 1024);
+            const uint32_t ah_base = ahi0 + pn * p.region_bytes + tap_off, al_base = alo0 + pn * p.region_bytes + tap_off;
+            for (int t = 0; t < p.T2; ++t) {
+              const uint64_t ah = make_desc(ah_base + t * 16 * sbo2, sbo2), al = make_desc(al_base + t * 16 * sbo2, sbo2);
+              const uint32_t d = tmem + t * tile_cols2;
+#pragma unroll 4
+              for (int ks = 0; ks < ksn; ++ks) {
+                mma_tf32(d, ah + 2 * ks, bdesc + 2 * ks, id2N2, !(first && ks == 0));
+                mma_tf32(d, al + 2 * ks, bdesc + 2 * ks, idN2, 1);
+              }
+            }
+            tc_commit(bar(BAR_EMPTY + st));
+          }
+        }
+        tc_commit(bar(BAR_ACC2));
+        // ---- stage 3: h = W3 H2 ----
+        mbar_wait(bar(BAR_H2), ph);
+        tc_fence_after();
+        for (int pn = 0; pn < p.P; ++pn) {
+          const uint32_t st = chunk % p.nstages, round = chunk / p.nstages; ++chunk;
+          const int ksn = min(32, p.Ch - pn * 32) >> 3;
+          mbar_wait(bar(BAR_FULL + st), round & 1);
+          tc_fence_after();
+          const uint64_t bdesc = make_desc(ring0 + st * p.stage_bytes, 1024);
+          for (int t = 0; t < p.T2; ++t) {
+            const uint64_t ah = make_desc(ahi0 + pn * p.region_bytes + t * 16384, 1024), al = make_desc(alo0 + pn * p.region_bytes + t * 16384, 1024);
+            const uint32_t d = tmem + t * tile_cols3;
+#pragma unroll 4
+            for (int ks = 0; ks < ksn; ++ks) {
+              mma_tf32(d, ah + 2 * ks, bdesc + 2 * ks, id2N3, !(pn == 0 && ks == 0));
+              mma_tf32(d, al + 2 * ks, bdesc + 2 * ks, idN3, 1);
+            }
+          }
+          tc_commit(bar(BAR_EMPTY + st));
+        }
+        tc_commit(bar(BAR_ACC3));
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM lanes 32*warp .. 32*warp+31) =============================================
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int row_in_tile = warp * 32 + lane;
+    const int kc1 = p.KS1 * 2;                                // 16-byte chunks of x0 per stored row
+    for (int it = 0; it < my_tiles; ++it) {
+      const uint32_t ph = it & 1;
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b0 = tile * p.S, nS = min(p.S, p.B - b0);
+      // ---- x0 staging -> operand rows (reflect halo / segment overlap applied here) ----
+      mbar_wait(bar(BAR_XFULL), ph);
+      for (int idx = tid; idx < p.R * kc1; idx += kEpiThreads) {
+        const int r = idx / kc1, j = idx - r * kc1;
+        int s, y, x;
+        decode_stored<SEG>(p, r, s, y, x);
+        const float* src = xstage + (size_t)s * xfloats + y * p.W + x;
+        float4 hi, lo;
+        const int c = 4 * j;
+        hi.x = (c + 0 < p.Cin && s < nS) ? src[(c + 0) * HW] : 0.f;
+        hi.y = (c + 1 < p.Cin && s < nS) ? src[(c + 1) * HW] : 0.f;
+        hi.z = (c + 2 < p.Cin && s < nS) ? src[(c + 2) * HW] : 0.f;
+        hi.w = (c + 3 < p.Cin && s < nS) ? src[(c + 3) * HW] : 0.f;
+        lo.x = tf32_lo(hi.x); lo.y = tf32_lo(hi.y); lo.z = tf32_lo(hi.z); lo.w = tf32_lo(hi.w);
+        const uint32_t off = sw128(r, c);
+        *reinterpret_cast<float4*>(a_hi + off) = hi;
+        *reinterpret_cast<float4*>(a_lo + off) = lo;
+      }
+      fence_async_smem();
+      mbar_arrive(bar(BAR_XEMPTY));
+      mbar_arrive(bar(BAR_AREADY));
+      // ---- epilogue 1: H1 = relu(acc + b1) for every stored row ----
+      mbar_wait(bar(BAR_ACC1), ph);
+      tc_fence_after();
+      for (int t = 0; t < p.T1; ++t) {
+        const int r = t * 128 + row_in_tile;
+        const float* bias = sb1;
+        if (a.bias1_b != nullptr && r < p.R) {
+          int s, y, x;
+          decode_stored<SEG>(p, r, s, y, x);
+          bias = a.bias1_b + (size_t)min(b0 + s, p.B - 1) * p.Ch;
+        }
+        epilogue_to_operand(tmem + lane_base + t * 2 * p.N2, p.N2, bias, a_hi, a_lo, p.region_bytes, r, r < p.R);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar(BAR_H1));
+      // ---- epilogue 2: H2 = relu(acc + b2) at the accumulator's own row index ----
+      mbar_wait(bar(BAR_ACC2), ph);
+      tc_fence_after();
+      for (int t = 0; t < p.T2; ++t) {
+        const int m = t * 128 + row_in_tile;
+        int s, y, x;
+        const bool valid = decode_out<SEG>(p, m, s, y, x);
+        epilogue_to_operand(tmem + lane_base + t * 2 * p.N2, p.N2, sb2, a_hi, a_lo, p.region_bytes, m, valid);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar(BAR_H2));
+      // ---- epilogue 3: h = acc + b3 -> HBM (NCHW) ----
+      mbar_wait(bar(BAR_ACC3), ph);
+      tc_fence_after();
+      for (int t = 0; t < p.T2; ++t) {
+        const int m = t * 128 + row_in_tile;
+        int s, y, x;
+        const bool valid = decode_out<SEG>(p, m, s, y, x) && s < nS;
+        float* dst = a.h + ((size_t)(b0 + (valid ? s : 0)) * p.Cout) * HW + y * p.W + x;
+        const uint32_t taddr = tmem + lane_base + t * 2 * p.N3;
+        for (int c0 = 0; c0 < p.N3; c0 += 16) {
+          float v[16], u[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld16(taddr + p.N3 + c0, u);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < p.Cout) dst[(size_t)(c0 + i) * HW] = v[i] + u[i] + sb3[c0 + i];
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+// One-time weight repack: torch-layout conv weights -> the chunk stream the producer copies verbatim into the ring.
+// chunk c (stride stage_bytes): [hi image: N rows x 128 B, K-major SW128][lo image], row n / column k of the image =
+//   c == 0           : W1[n][k]                                   (N = N2, k < Cin)
+//   1 + tap*P + pn   : W2[n][pn*32 + k][ky][kx]                   (N = N2)
+//   1 + taps*P + pn  : W3[n][pn*32 + k]                           (N = N3, rows >= Cout zero)
+__global__ void pack_tc_kernel(const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ w3, uint8_t* __restrict__ out,
+                               int Cin, int Ch, int Cout, int KH, int KW, int P, int N2, int N3, int stage_bytes, int w1_stride) {
+  const int taps = KH * KW;
+  const int nchunks = 1 + taps * P + P;
+  const int c = blockIdx.x;
+  if (c >= nchunks) return;
+  const int N = c < 1 + taps * P ? N2 : N3;
+  uint8_t* img = out + (size_t)c * stage_bytes;
+  for (int i = threadIdx.x; i < N * 32; i += blockDim.x) {
+    const int n = i >> 5, k = i & 31;
+    float v = 0.f;
+    if (c == 0) { if (n < Ch && k < Cin) v = w1[(size_t)n * w1_stride + k]; }
+    else if (c < 1 + taps * P) {
+      const int tap = (c - 1) / P, pn = (c - 1) % P, ci = pn * 32 + k;
+      if (n < Ch && ci < Ch) v = w2[((size_t)n * Ch + ci) * taps + tap];
+    } else {
+      const int pn = c - 1 - taps * P, ci = pn * 32 + k;
+      if (n < Cout && ci < Ch) v = w3[(size_t)n * Ch + ci];
+    }
+    const uint32_t off = sw128(n, k);
+    *reinterpret_cast<float*>(img + off) = v;
+    *reinterpret_cast<float*>(img + (size_t)N * 128 + off) = tf32_lo(v);
+  }
+}
+
+// ---- host-side geometry ------------------------------------------------------------------------------------------------
+static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, long long x_bstride, int sms) {
+  if (!((KH == 1 || KH == 3) && (KW == 1 || KW == 3))) return false;
+  if ((KH == 3 && H < 2) || (KW == 3 && W < 2)) return false;
+  if (Ch % 16 != 0 || Ch < 16 || Ch > 128 || Cin < 1 || Cin > 32 || Cout < 1 || Cout > 128) return false;
+  if ((Cin * H * W) % 4 != 0 || x_bstride % 4 != 0) return false;      // 16-byte bulk copies of x0
+  p = Plan{};
+  p.B = B; p.Cin = Cin; p.Ch = Ch; p.Cout = Cout; p.H = H; p.W = W; p.KH = KH; p.KW = KW; p.x_bstride = x_bstride;
+  p.P = (Ch + 31) / 32; p.KS1 = (Cin + 7) / 8; p.N2 = Ch; p.N3 = (Cout + 15) / 16 * 16;
+  p.HP = H + KH - 1; p.WP = W + KW - 1;
+  p.stage_bytes = 2 * p.N2 * 128;
+  const int HW = H * W;
+  const int kSmemMax = 227 * 1024 - 1024;                               // minus alignment slack
+  const int bias_bytes = (2 * p.N2 + p.N3) * 4, bar_bytes = BAR_COUNT * 8 + 16;
+  double best_cost = 1e30; Plan best{}; bool found = false;
+  for (int seg = 0; seg <= 1; ++seg) {
+    if (seg && (W % 8 != 0)) continue;
+    for (int S = 1; S <= 32 && S <= B; ++S) {
+      Plan q = p; q.seg = seg; q.S = S;
+      if (seg) {
+        q.NSEG = W / 8; q.GS = 8 + KW - 1; q.YS = S * q.NSEG * q.GS;
+        q.R = q.HP * S * q.NSEG * q.GS; q.NG = H * S * q.NSEG; q.T2 = (q.NG + 15) / 16;
+      } else {
+        q.NSEG = 1; q.GS = 8; q.YS = q.WP; q.RPS = q.HP * q.WP;
+        q.R = S * q.RPS;
+        const int mmax = (S - 1) * q.RPS + (H - 1) * q.WP + W;          // accumulator rows that can be pixels
+        q.T2 = (mmax + 127) / 128; q.NG = q.T2 * 16;
+      }
+      q.T1 = (q.R + 127) / 128;
+      if (q.T1 * 2 * q.N2 > 512 || q.T2 * 2 * q.N2 > 512 || q.T2 * 2 * q.N3 > 512) break;
+      q.region_bytes = ((q.R + 7) / 8 * 8) * 128;
+      // operand rows the MMAs may touch (garbage rows included) must stay inside this CTA's shared memory
+      q.off_ring = 2 * q.P * q.region_bytes;
+      const int xbytes = (S * Cin * HW * 4 + 127) / 128 * 128;
+      const int fixed = q.off_ring + xbytes + bias_bytes + bar_bytes + 256;
+      int nst = (kSmemMax - fixed) / q.stage_bytes;
+      if (nst < 2) break;
+      if (nst > kMaxStages) nst = kMaxStages;
+      q.nstages = nst;
+      const int reach1 = q.T1 * 128 * 128;                                                    // stage 1 / 3 tiles
+      const int reach2 = ((q.T2 * 16 - 1) * q.GS + (KH - 1) * q.YS + (KW - 1) + 8) * 128;      // last group of the last tap
+      const int reach = (reach1 > reach2 ? reach1 : reach2) + (2 * q.P - 1) * q.region_bytes;
+      if (reach > q.off_ring + nst * q.stage_bytes) continue;
+      q.off_stage_x = q.off_ring + nst * q.stage_bytes;
+      q.off_bias = q.off_stage_x + xbytes;
+      q.off_bar = (q.off_bias + bias_bytes + 15) / 16 * 16;
+      q.smem_bytes = q.off_bar + bar_bytes + 1024;
+      q.ntiles = (B + S - 1) / S;
+      // cost: MMA row-slots per real pixel, plus a penalty when the batch no longer fills the SMs evenly
+      const double waste = (double)(q.T2 * 128) / (double)(S * HW);
+      const int waves = (q.ntiles + sms - 1) / sms;
+      const double imbalance = (double)(waves * sms) / (double)q.ntiles;
+      const double cost = waste * (q.ntiles >= sms ? imbalance : 1.0) * (1.0 + 0.02 / S);
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = q; found = true; }
+    }
+  }
+  if (found) p = best;
+  return found;
+}
+
+static Plan g_last_plan;
+
+}  // namespace tc
+}  // namespace cfpp
+using namespace cfpp;
+
+static bool tc_channels_ok(int Cin, int Ch, int Cout, int KH, int KW) {
+  return Ch % 16 == 0 && Ch >= 16 && Ch <= 128 && Cin >= 1 && Cin <= 32 && Cout >= 1 && Cout <= 128 && (KH == 1 || KH == 3) && (KW == 1 || KW == 3);
+}
+
+extern "C" int64_t cfpp_conv_cond_tc_pack_bytes(int Cin, int Ch, int Cout, int KH, int KW) {
+  if (!tc_channels_ok(Cin, Ch, Cout, KH, KW)) return -1;
+  const int P = (Ch + 31) / 32;
+  return (int64_t)(1 + KH * KW * P + P) * (2 * Ch * 128);
+}
+
+extern "C" int cfpp_conv_cond_tc_pack(const float* w1, int w1_stride, const float* w2, const float* w3, void* out,
+                                      int Cin, int Ch, int Cout, int KH, int KW, void* stream) {
+  CFPP_REQUIRE(cfpp_conv_cond_tc_pack_bytes(Cin, Ch, Cout, KH, KW) > 0, "conv_cond_tc_pack: unsupported channel counts / kernel size");
+  const int P = (Ch + 31) / 32, N2 = Ch, N3 = (Cout + 15) / 16 * 16;
+  const int nchunks = 1 + KH * KW * P + P;
+  tc::pack_tc_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(w1, w2, w3, (uint8_t*)out, Cin, Ch, Cout, KH, KW, P, N2, N3, 2 * N2 * 128, w1_stride);
+  return check_launch("conv_cond_tc_pack");
+}
+
+extern "C" int cfpp_conv_cond_tc_supported(int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, int64_t x_bstride) {
+  tc::Plan p;
+  return B > 0 && tc::make_plan(p, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, num_sms()) ? 1 : 0;
+}
+
+extern "C" int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h, const void* wpack,
+                                     const float* b1, const float* bias1_b, const float* b2, const float* b3,
+                                     int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, void* stream) {
+  if (B <= 0) return CFPP_OK;
+  tc::Plan p;
+  if (!tc::make_plan(p, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, num_sms())) {
+    set_error("conv_cond_tc: shape (Cin %d, Ch %d, Cout %d, %dx%d, k %dx%d) has no tensor-core plan", Cin, Ch, Cout, H, W, KH, KW);
+    return CFPP_ERR_UNSUPPORTED;
+  }
+  CFPP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0, "conv_cond_tc: x / wpack must be 16-byte aligned");
+  tc::g_last_plan = p;
+  tc::Args a{x, h, (const uint8_t*)wpack, b1, b2, b3, bias1_b};
+  const int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr_set[2] = {false, false};
+  if (p.seg) {
+    if (!attr_set[1]) { cudaFuncSetAttribute(tc::conv_cond_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[1] = true; }
+    tc::conv_cond_tc_kernel<true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p, a);
+  } else {
+    if (!attr_set[0]) { cudaFuncSetAttribute(tc::conv_cond_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[0] = true; }
+    tc::conv_cond_tc_kernel<false><<<grid, tc::kThreads, p.smem_bytes, st>>>(p, a);
+  }
+  return check_launch("conv_cond_tc_fwd");
+}
+
+/* geometry of the last launch, for tests / bench reporting: {seg, S, R, T1, T2, nstages, smem_bytes, ntiles} */
+extern "C" void cfpp_conv_cond_tc_last_plan(int* out8) {
+  const tc::Plan& p = tc::g_last_plan;
+  out8[0] = p.seg; out8[1] = p.S; out8[2] = p.R; out8[3] = p.T1; out8[4] = p.T2; out8[5] = p.nstages; out8[6] = p.smem_bytes; out8[7] = p.ntiles;
+}

@@ -67,8 +67,20 @@ class Coupling(_CouplingBase):
             w1 = c1.weight.reshape(H, -1)
             return dict(main=(ops.pack_kmajor(w1[:, :D]), ops.pad_vec(c1.bias), ops.pack_kmajor(c2.weight.reshape(H, -1)),
                               ops.pad_vec(c2.bias), ops.pack_kmajor(c3.weight.reshape(O, -1)), ops.pad_vec(c3.bias)),
-                        ctx_w=ops.pack_kmajor(w1[:, D:], 1) if w1.shape[1] > D else None)
+                        ctx_w=ops.pack_kmajor(w1[:, D:], 1) if w1.shape[1] > D else None,
+                        tc=ops.conv_cond_tc_pack(c1.weight, c2.weight, c3.weight, D) if c1.weight.is_cuda else None)
         return self._packs.get('nn', [c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias], build)
+
+    def _conditioner(self, x, pk, bias1_b=None):
+        """h = NN(x0): tcgen05 kernel when the shape has a tensor-core plan, the FP32-FMA kernel otherwise (both CUDA, same result)."""
+        D, H, O = self._dims
+        Hh, Ww = x.shape[2], x.shape[3]
+        if pk['tc'] is not None and ops.conv_cond_tc_mode() != 'fma':
+            b1, b2, b3 = pk['main'][1], pk['main'][3], pk['main'][5]
+            h = ops.conv_cond_tc(x, D, pk['tc'], b1, b2, b3, H, Hh, Ww, self.krn[0], self.krn[1], O, bias1_b=bias1_b)
+            if h is not None:
+                return h
+        return ops.conv_cond(x, D, pk['main'], Hh, Ww, self.krn[0], self.krn[1], O, bias1_b=bias1_b)
 
     def forward(self, x, context=None):
         inference_only(x)
@@ -76,16 +88,13 @@ class Coupling(_CouplingBase):
         Hh, Ww = x.shape[2], x.shape[3]
         pk = self._packed_nn()
         if not self.context_net:
-            h = ops.conv_cond(x, D, pk['main'], Hh, Ww, self.krn[0], self.krn[1], O)
-            return ops.coupling(x, h)
+            return ops.coupling(x, self._conditioner(x, pk))
         cn, logp_c = self._context_terms(context)
         if self.contextflow:                                      # additive: h = NN(x0) + CN(c)   (coupling.py:45)
-            h = ops.conv_cond(x, D, pk['main'], Hh, Ww, self.krn[0], self.krn[1], O)
-            return ops.coupling(x, h, add=cn, logp_c=logp_c, logp_scale=float(Hh * Ww))
+            return ops.coupling(x, self._conditioner(x, pk), add=cn, logp_c=logp_c, logp_scale=float(Hh * Ww))
         # conventional: NN(cat(x0, CN(c) broadcast)) == first conv with the per-sample bias b1 + W1[:, D:] CN(c)  (coupling.py:47)
         bias1 = ops.linear(cn, pk['ctx_w'], self.NN[0].bias.detach())
-        h = ops.conv_cond(x, D, pk['main'], Hh, Ww, self.krn[0], self.krn[1], O, bias1_b=bias1)
-        return ops.coupling(x, h, logp_c=logp_c, logp_scale=float(Hh * Ww))
+        return ops.coupling(x, self._conditioner(x, pk, bias1_b=bias1), logp_c=logp_c, logp_scale=float(Hh * Ww))
 
 
 class CouplingFC(Coupling):

@@ -261,6 +261,45 @@ def conv_cond(x, cin, packed, H, W, KH, KW, cout, bias1_b=None):
     return h
 
 
+def conv_cond_tc_mode() -> str:
+    """'auto' (tensor cores whenever the shape has a plan), 'fma' (force the FP32-FMA kernel) -- env CFPP_CONV_COND."""
+    import os
+    return os.environ.get('CFPP_CONV_COND', 'auto')
+
+
+def conv_cond_tc_pack(w1, w2, w3, cin):
+    """Repack torch-layout conditioner weights for cfpp_conv_cond_tc_fwd; None when the channel counts have no tensor-core plan."""
+    _need_cuda(w1, w2, w3)
+    ch, cout, KH, KW = w2.shape[0], w3.shape[0], w2.shape[2], w2.shape[3]
+    nbytes = int(lib().cfpp_conv_cond_tc_pack_bytes(cin, ch, cout, KH, KW))
+    if nbytes < 0:
+        return None
+    w1 = _f32(w1.detach().reshape(ch, -1)); w2 = _f32(w2.detach()); w3 = _f32(w3.detach().reshape(cout, -1))
+    out = torch.empty(nbytes, device=w2.device, dtype=torch.uint8)
+    _call('conv_cond_tc_pack', (_p(w1), w1.shape[1], _p(w2), _p(w3), _p(out), cin, ch, cout, KH, KW, _stream()))
+    return out
+
+
+def conv_cond_tc(x, cin, wpack, b1, b2, b3, ch, H, W, KH, KW, cout, bias1_b=None):
+    """Tensor-core conditioner; returns None (nothing launched) when this shape has no plan so the caller can use conv_cond."""
+    _need_cuda(x, wpack)
+    xv, bstride = _half_view(x)
+    B = x.shape[0]
+    if not lib().cfpp_conv_cond_tc_supported(B, cin, ch, cout, H, W, KH, KW, bstride) or xv.data_ptr() % 16:
+        return None
+    h = torch.empty((B, cout, H, W), device=x.device, dtype=torch.float32)
+    _set_work(bytes=4.0 * B * H * W * (cin + cout), flops=2.0 * B * H * W * (cin * ch + ch * ch * KH * KW + ch * cout))
+    _call('conv_cond_tc_fwd', (_p(xv), bstride, _p(h), _p(wpack), _p(b1), _p(None if bias1_b is None else _f32(bias1_b)), _p(b2), _p(b3),
+                               B, cin, ch, cout, H, W, KH, KW, _stream()))
+    return h
+
+
+def conv_cond_tc_last_plan():
+    out = (_cabi.i32 * 8)()
+    lib().cfpp_conv_cond_tc_last_plan(out)
+    return dict(zip(('seg', 'S', 'R', 'T1', 'T2', 'nstages', 'smem_bytes', 'ntiles'), list(out)))
+
+
 def vit_cond(x, desc: _cabi.VitDesc, cout, extra=None):
     _need_cuda(x)
     xv, bstride = _half_view(x)

@@ -93,6 +93,23 @@ int cfpp_conv_cond_fwd(const float* x, int64_t x_bstride, float* h,
                        const float* w2t, const float* b2, const float* w3t, const float* b3,
                        int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, void* stream);
 
+/* The same conditioner on the tcgen05 tensor cores (kind::tf32, fp32-faithful 3xTF32 split, TMEM accumulators, weights streamed
+ * by bulk TMA copies; contextflow_b200/csrc/conv_cond_tc.cu).  Weights are repacked ONCE per parameter version by
+ * cfpp_conv_cond_tc_pack from the torch layouts: w1 (Ch, >=Cin) with row stride w1_stride, w2 (Ch, Ch, KH, KW), w3 (Cout, Ch);
+ * b1/b2/b3 are the plain bias vectors.  Supported: Ch % 16 == 0, 16 <= Ch <= 128, Cin <= 32, Cout <= 128, KH,KW in {1,3},
+ * (Cin*H*W) % 4 == 0, x_bstride % 4 == 0, x 16-byte aligned -- cfpp_conv_cond_tc_supported() answers for a shape; other shapes
+ * use cfpp_conv_cond_fwd (CFPP_ERR_UNSUPPORTED is returned, nothing is launched). */
+int64_t cfpp_conv_cond_tc_pack_bytes(int Cin, int Ch, int Cout, int KH, int KW);   /* -1 when unsupported */
+int cfpp_conv_cond_tc_pack(const float* w1, int w1_stride, const float* w2, const float* w3, void* out,
+                           int Cin, int Ch, int Cout, int KH, int KW, void* stream);
+int cfpp_conv_cond_tc_supported(int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, int64_t x_bstride);
+int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h, const void* wpack,
+                          const float* b1, const float* bias1_b, const float* b2, const float* b3,
+                          int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, void* stream);
+/* geometry of the last cfpp_conv_cond_tc_fwd launch (tests / bench): {segment layout, samples per tile, stored rows, M-tiles of
+ * stage 1, M-tiles of stages 2-3, ring stages, shared-memory bytes, tiles} */
+void cfpp_conv_cond_tc_last_plan(int* out8);
+
 /* SimpleViT conditioner of TransCoupling, layers/simple_vit.py:91-127 (heads=1, dim_head=64, dim=mlp_dim=T, GELU-erf,
  * LayerNorm eps 1e-5).  All weight matrices PACKED K-major (in_features, out_features). */
 typedef struct {

@@ -1,0 +1,115 @@
+"""tcgen05 conv conditioner (csrc/conv_cond_tc.cu) through the C ABI against an fp64 torch evaluation of Coupling.NN
+(reference layers/coupling.py:26-29) and against the FP32-FMA kernel: every BASELINE level shape, the time-series (3,1) kernel,
+ragged batches, several tiles per CTA, per-sample first-layer bias (conventional context), reading x0 in place from a wider tensor."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from contextflow_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+dev = 'cuda'
+
+
+def _weights(tag, cin, ch, cout, kh, kw, extra=0):
+    w1 = synth.uniform(tag + 'w1', (ch, cin + extra)) * (1.5 / (cin + extra) ** 0.5)
+    w2 = synth.uniform(tag + 'w2', (ch, ch, kh, kw)) * (1.5 / (ch * kh * kw) ** 0.5)
+    w3 = synth.uniform(tag + 'w3', (cout, ch)) * (1.5 / ch ** 0.5)
+    b1, b2, b3 = synth.uniform(tag + 'b1', (ch,)) * 0.3, synth.uniform(tag + 'b2', (ch,)) * 0.3, synth.uniform(tag + 'b3', (cout,)) * 0.3
+    return w1, b1, w2, b2, w3, b3
+
+
+def _ref64(x0, w1, b1, w2, b2, w3, b3, bias1_b=None):
+    x0 = x0.double()
+    cin = x0.shape[1]
+    h = F.conv2d(x0, w1[:, :cin].double()[:, :, None, None])
+    h = h + (b1.double()[None, :, None, None] if bias1_b is None else bias1_b.double()[:, :, None, None])
+    h = F.relu(h)
+    kh, kw = w2.shape[2], w2.shape[3]
+    if kh > 1 or kw > 1:
+        h = F.pad(h, (kw // 2, kw // 2, kh // 2, kh // 2), mode='reflect')
+    h = F.relu(F.conv2d(h, w2.double(), b2.double()))
+    return F.conv2d(h, w3.double()[:, :, None, None], b3.double())
+
+
+def _run_tc(x, cin, w1, b1, w2, b2, w3, b3, bias1_b=None):
+    ch, cout, kh, kw = w2.shape[0], w3.shape[0], w2.shape[2], w2.shape[3]
+    pack = ops.conv_cond_tc_pack(w1.to(dev), w2.to(dev), w3.to(dev), cin)
+    assert pack is not None, 'shape should have a tensor-core plan'
+    h = ops.conv_cond_tc(x, cin, pack, b1.to(dev), b2.to(dev), b3.to(dev), ch, x.shape[2], x.shape[3], kh, kw, cout,
+                         bias1_b=None if bias1_b is None else bias1_b.to(dev))
+    assert h is not None, 'shape should have a tensor-core plan'
+    torch.cuda.synchronize()
+    return h
+
+
+def _check(h, want, what):
+    scale = want.abs().max().item()
+    err = (h.double().cpu() - want).abs().max().item()
+    assert err <= 2e-5 * scale + 1e-6, f'{what}: max abs err {err:.3e} vs |ref|max {scale:.3e} (fp32-faithful budget 2e-5)'
+
+
+SHAPES = [  # B, C (coupling channels: Cin=C/2, Ch=2C, Cout=C), H, W, KH, KW
+    (5, 16, 16, 16, 3, 3),      # cfg2 level 1 (segment layout, two segments per row)
+    (7, 32, 8, 8, 3, 3),        # cfg2 level 2 / cfg1 level 2 (segment layout, samples interleaved)
+    (10, 64, 4, 4, 3, 3),       # cfg2 level 3 (plain padded layout, 4 channel panels)
+    (3, 8, 16, 16, 3, 3),       # cfg1 level 1 (Cin=4 -> zero-padded k-step, N=16)
+    (1, 16, 16, 16, 3, 3),
+    (700, 32, 8, 8, 3, 3),      # several tiles per persistent CTA
+    (333, 16, 16, 16, 3, 3),
+    (9, 56, 8, 1, 3, 1),        # MSL-shaped conv coupling: 56 channels (Ch=112, partial last panel), (3,1) kernel
+    (6, 8, 14, 14, 3, 3),       # MNIST 28x28 level 1 (W % 8 != 0 -> plain layout)
+    (4, 32, 7, 7, 3, 3),        # MNIST 28x28 level 2
+    (12, 24, 6, 10, 3, 3),      # Ch=48 (two panels, second half full), non-square
+    (5, 32, 4, 24, 3, 3),       # three segments per row
+    (33, 16, 1, 1, 1, 1),       # 1x1 kernel on single pixels
+]
+
+
+@pytest.mark.parametrize('B,C,H,W,KH,KW', SHAPES)
+def test_tc_conditioner_matches_fp64(B, C, H, W, KH, KW):
+    cin, ch, cout = C // 2, 2 * C, C
+    tag = f'tc{B}.{C}.{H}.{W}'
+    w = _weights(tag, cin, ch, cout, KH, KW)
+    x = synth.uniform(tag + 'x', (B, C, H, W)) * 2.0
+    xd = x.to(dev)
+    h = _run_tc(xd, cin, *w)                                   # x0 = first half of x, read in place (batch stride C*H*W)
+    want = _ref64(x[:, :cin], *w)
+    _check(h, want, f'tc conditioner {B}x{C}x{H}x{W} k{KH}x{KW}')
+    plan = ops.conv_cond_tc_last_plan()
+    assert plan['ntiles'] == (B + plan['S'] - 1) // plan['S']
+    # and the FP32-FMA kernel computes the same function
+    pk = (ops.pack_kmajor(w[0][:, :cin].to(dev)), ops.pad_vec(w[1].to(dev)), ops.pack_kmajor(w[2].reshape(ch, -1).to(dev)),
+          ops.pad_vec(w[3].to(dev)), ops.pack_kmajor(w[4].to(dev)), ops.pad_vec(w[5].to(dev)))
+    try:
+        h_fma = ops.conv_cond(xd, cin, pk, H, W, KH, KW, cout)
+    except RuntimeError:
+        return                                                 # shape outside the FMA kernel's tile limits
+    _check(h_fma, want, 'fma conditioner')
+
+
+def test_tc_per_sample_bias_and_plan_layouts():
+    B, C, H, W = 11, 32, 8, 8
+    cin, ch, cout = C // 2, 2 * C, C
+    w1, b1, w2, b2, w3, b3 = _weights('tcb', cin, ch, cout, 3, 3, extra=C)
+    cn = synth.uniform('tcb.cn', (B, C))
+    bias1 = b1[None, :] + cn @ w1[:, cin:].t()                  # conventional concat == per-sample bias (coupling.py:47)
+    x = synth.uniform('tcb.x', (B, C, H, W)) * 2.0
+    h = _run_tc(x.to(dev), cin, w1, b1, w2, b2, w3, b3, bias1_b=bias1)
+    xin = torch.cat([x[:, :cin], cn[:, :, None, None].expand(B, C, H, W)], 1).double()
+    hh = F.relu(F.conv2d(xin, w1.double()[:, :, None, None], b1.double()))
+    hh = F.relu(F.conv2d(F.pad(hh, (1, 1, 1, 1), mode='reflect'), w2.double(), b2.double()))
+    want = F.conv2d(hh, w3.double()[:, :, None, None], b3.double())
+    _check(h, want, 'tc conditioner, per-sample bias')
+    assert ops.conv_cond_tc_last_plan()['seg'] == 1
+    _run_tc(synth.uniform('tcb.y', (4, 128, 4, 4)).to(dev), 64 // 2, *_weights('tcb4', 32, 128, 64, 3, 3))
+    assert ops.conv_cond_tc_last_plan()['seg'] == 0
+
+
+def test_tc_unsupported_shapes_fall_back():
+    from contextflow_b200 import _cabi
+    lib = _cabi.lib()
+    assert lib.cfpp_conv_cond_tc_pack_bytes(10, 40, 20, 1, 1) == -1            # Ch % 16 != 0 (CouplingFC of a 20-wide encoder)
+    assert lib.cfpp_conv_cond_tc_pack_bytes(38, 152, 76, 3, 1) == -1           # Ch > 128
+    assert lib.cfpp_conv_cond_tc_supported(8, 8, 32, 16, 16, 16, 3, 3, 16 * 256) == 1
+    assert lib.cfpp_conv_cond_tc_supported(8, 8, 32, 16, 16, 16, 3, 3, 16 * 256 + 2) == 0   # batch stride not 16-byte aligned
