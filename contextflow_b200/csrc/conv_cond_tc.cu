@@ -18,10 +18,11 @@
 // [0,N); the epilogue adds the two column blocks.  (tools/umma_probe*.cu measured the descriptor conventions, the
 // 2^-21-grade accuracy of the split and the issue rates this layout is built on.)
 //
-// Roles (192 threads, one persistent CTA per SM): warps 0-3 = epilogue (TMEM -> bias/ReLU/split -> shared, final store
-// to HBM; also the x0 -> operand-row transform), warp 4 = MMA issuer (one thread), warp 5 = producer (weight chunks
+// Roles (448 threads, one persistent CTA per SM): warps 0-11 = epilogue (TMEM -> bias/ReLU/split -> shared, final store
+// to HBM; also the x0 -> operand-row transform), warp 12 = MMA issuer (one thread), warp 13 = producer (weight chunks
 // through an mbarrier ring + next tile's x0 prefetch).  Per tile: stage 1 (1x1) -> epilogue 1 -> stage 2 (kxk, the
 // 94 %) -> epilogue 2 -> stage 3 (1x1) -> epilogue 3.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cfpp {
@@ -34,12 +35,15 @@ struct Plan {
   int P, KS1, N2, N3;                // channel panels, k-steps of stage 1, N of stages 1-2, N of stage 3 (padded to 16)
   int stage_bytes, nstages, ntiles;
   int region_bytes;                  // bytes of one (hi|lo, panel) operand region
-  int off_ring, off_stage_x, off_bias, off_bar, smem_bytes;
+  int off_ring, off_stage_x, off_bias, off_tab, off_bar, smem_bytes;   // off_tab: R + T2*128 packed row-decode words
   long long x_bstride;
 };
 
-constexpr int kEpiThreads = 128;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 12;                  // 3 warps per TMEM lane quadrant (a warp reaches lanes 32*(warp%4) .. +31 only)
+constexpr int kEpiGroups = kEpiWarps / 4;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kMmaWarp = kEpiWarps, kProdWarp = kEpiWarps + 1;
+constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kMaxStages = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -82,10 +86,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {   // one lane of a converged warp (ptxas then knows the region is single-threaded)
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ int reflect(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
 struct Args {
   const float* x; float* h; const uint8_t* wpack; const float* b1; const float* b2; const float* b3; const float* bias1_b;
+  long long wrepl_stride; int nrepl;   // experiment: weight stream replicas (CTA uses replica blockIdx % nrepl)
+  long long* prof;   // optional (debug): 12 phase-cycle counters of CTA 0's epilogue thread 0, see cfpp_conv_cond_tc_set_profile
 };
 
 // Barrier slots (8 bytes each) inside the barrier block.
@@ -120,34 +131,41 @@ __device__ __forceinline__ bool decode_out(const Plan& p, int m, int& s, int& y,
   }
 }
 
-// TMEM accumulator (two column blocks of N) -> + bias -> ReLU -> (v, lo) -> operand row `row` of every panel.
-__device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, const float* __restrict__ bias, uint8_t* a_hi, uint8_t* a_lo,
-                                                    int region_bytes, int row, bool write) {
-  for (int c0 = 0; c0 < N; c0 += 16) {
-    float v[16], u[16];
-    tmem_ld16(taddr + c0, v);
-    tmem_ld16(taddr + N + c0, u);
-    tmem_ld_wait();
-    if (write) {
-      uint8_t* ph = a_hi + (c0 >> 5) * region_bytes;
-      uint8_t* pl = a_lo + (c0 >> 5) * region_bytes;
+// One epilogue item: 32 accumulator columns [c0, c0+32) (16 when only 16 remain) of one row, two column blocks of N each ->
+// + bias -> ReLU -> (v, lo) -> operand row `row`.  All four TMEM loads are in flight before the single wait.  All 32 lanes
+// must call (tcgen05.ld is warp-collective); `write` only guards the stores.
+__device__ __forceinline__ void store_split16(const float (&v)[16], const float (&u)[16], const float* __restrict__ bias, uint8_t* ph, uint8_t* pl,
+                                              int row, int col) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float4 hi, lo;
-        float t;
-        t = fmaxf(v[4 * q + 0] + u[4 * q + 0] + bias[c0 + 4 * q + 0], 0.f); hi.x = t; lo.x = tf32_lo(t);
-        t = fmaxf(v[4 * q + 1] + u[4 * q + 1] + bias[c0 + 4 * q + 1], 0.f); hi.y = t; lo.y = tf32_lo(t);
-        t = fmaxf(v[4 * q + 2] + u[4 * q + 2] + bias[c0 + 4 * q + 2], 0.f); hi.z = t; lo.z = tf32_lo(t);
-        t = fmaxf(v[4 * q + 3] + u[4 * q + 3] + bias[c0 + 4 * q + 3], 0.f); hi.w = t; lo.w = tf32_lo(t);
-        const uint32_t off = sw128(row, (c0 & 31) + 4 * q);
-        *reinterpret_cast<float4*>(ph + off) = hi;
-        *reinterpret_cast<float4*>(pl + off) = lo;
-      }
-    }
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
+    float4 hi, lo;
+    hi.x = fmaxf(v[4 * q + 0] + u[4 * q + 0] + b.x, 0.f); lo.x = tf32_lo(hi.x);
+    hi.y = fmaxf(v[4 * q + 1] + u[4 * q + 1] + b.y, 0.f); lo.y = tf32_lo(hi.y);
+    hi.z = fmaxf(v[4 * q + 2] + u[4 * q + 2] + b.z, 0.f); lo.z = tf32_lo(hi.z);
+    hi.w = fmaxf(v[4 * q + 3] + u[4 * q + 3] + b.w, 0.f); lo.w = tf32_lo(hi.w);
+    const uint32_t off = sw128(row, col + 4 * q);
+    *reinterpret_cast<float4*>(ph + off) = hi;
+    *reinterpret_cast<float4*>(pl + off) = lo;
+  }
+}
+__device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, int c0, const float* __restrict__ bias, uint8_t* a_hi, uint8_t* a_lo,
+                                                    int region_bytes, int row, bool write) {
+  float v0[16], u0[16], v1[16], u1[16];
+  const bool two = c0 + 16 < N;                               // warp-uniform
+  tmem_ld16(taddr + c0, v0);
+  tmem_ld16(taddr + N + c0, u0);
+  if (two) { tmem_ld16(taddr + c0 + 16, v1); tmem_ld16(taddr + N + c0 + 16, u1); }
+  tmem_ld_wait();
+  if (write) {
+    uint8_t* ph = a_hi + (c0 >> 5) * region_bytes;
+    uint8_t* pl = a_lo + (c0 >> 5) * region_bytes;
+    store_split16(v0, u0, bias + c0, ph, pl, row, c0 & 31);
+    if (two) store_split16(v1, u1, bias + c0 + 16, ph, pl, row, (c0 & 31) + 16);
   }
 }
 
-template <bool SEG>
+template <bool SEG, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p, const Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -175,7 +193,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
   }
   for (int i = tid; i < p.N2; i += kThreads) { sb1[i] = i < p.Ch ? a.b1[i] : 0.f; sb2[i] = i < p.Ch ? a.b2[i] : 0.f; }
   for (int i = tid; i < p.N3; i += kThreads) sb3[i] = i < p.Cout ? a.b3[i] : 0.f;
-  if (warp == 4) {
+  // Row-decode tables (the index arithmetic has runtime divisors: done once per CTA, not once per tile).
+  //   tab_in[r]  : stored operand row r  -> (s << 24) | (y << 12) | x of the source pixel (reflect / overlap applied)
+  //   tab_out[m] : accumulator row m     -> bit 31 = is a pixel, (s << 24) | (y << 12) | x
+  uint32_t* tab_in = reinterpret_cast<uint32_t*>(base + p.off_tab);
+  uint32_t* tab_out = tab_in + p.R;
+  for (int r = tid; r < p.R; r += kThreads) { int s_, y_, x_; decode_stored<SEG>(p, r, s_, y_, x_); tab_in[r] = ((uint32_t)s_ << 24) | ((uint32_t)y_ << 12) | (uint32_t)x_; }
+  for (int m = tid; m < p.T2 * 128; m += kThreads) {
+    int s_, y_, x_;
+    const bool ok = decode_out<SEG>(p, m, s_, y_, x_);
+    tab_out[m] = ok ? (0x80000000u | ((uint32_t)s_ << 24) | ((uint32_t)y_ << 12) | (uint32_t)x_) : 0u;
+  }
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -187,10 +216,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
   const int nchunks_tile = 1 + p.KH * p.KW * p.P + p.P;     // W1, W2 (tap, panel), W3 (panel)
   const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp == 5) {
+  if (warp == kProdWarp) {
     // ===================== producer: weight chunks through the ring, next tile's x0 into the staging buffer ==========
-    if (lane == 0) {
-      uint32_t chunk = 0;
+    if (elect_one()) {
+      uint32_t st = 0, rphase = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int b0 = tile * p.S, nS = min(p.S, p.B - b0);
@@ -198,178 +227,218 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
         mbar_expect_tx(bar(BAR_XFULL), (uint32_t)(nS * xfloats * 4));
         for (int s = 0; s < nS; ++s)
           bulk_g2s(smem_u32(xstage + (size_t)s * xfloats), a.x + (size_t)(b0 + s) * p.x_bstride, (uint32_t)(xfloats * 4), bar(BAR_XFULL));
-        for (int c = 0; c < nchunks_tile; ++c, ++chunk) {
-          const uint32_t st = chunk % p.nstages, round = chunk / p.nstages;
-          mbar_wait(bar(BAR_EMPTY + st), (round & 1) ^ 1);
+        for (int c = 0; c < nchunks_tile; ++c) {
+          mbar_wait(bar(BAR_EMPTY + st), rphase ^ 1);
           const uint32_t bytes = (c < nchunks_tile - p.P) ? (uint32_t)(2 * p.N2 * 128) : (uint32_t)(2 * p.N3 * 128);
           mbar_expect_tx(bar(BAR_FULL + st), bytes);
-          bulk_g2s(smem_u32(ring + (size_t)st * p.stage_bytes), a.wpack + (size_t)c * p.stage_bytes, bytes, bar(BAR_FULL + st));
+          bulk_g2s(smem_u32(ring + (size_t)st * p.stage_bytes), a.wpack + (size_t)(blockIdx.x % a.nrepl) * a.wrepl_stride + (size_t)c * p.stage_bytes, bytes, bar(BAR_FULL + st));
+          if (++st == (uint32_t)p.nstages) { st = 0; rphase ^= 1; }
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer ==================================================================================
-    if (lane == 0) {
+    // One thread.  tcgen05.mma issue blocks once ~2 instructions are queued, and this thread's own scalar work runs at
+    // dependent-instruction latency, so any work placed BETWEEN weight chunks starves the tensor pipe (measured: every
+    // cycle of gap beyond ~100 is lost, tools/umma_probe3.cu).  Hence: loop-invariant descriptors are hoisted, the ring
+    // position advances by adds, and the wait for the NEXT chunk sits in the middle of the current chunk's instructions.
+    if (elect_one()) {
       const uint32_t idN2 = make_idesc(p.N2), id2N2 = make_idesc(2 * p.N2), idN3 = make_idesc(p.N3), id2N3 = make_idesc(2 * p.N3);
       const uint32_t sbo2 = (uint32_t)p.GS * 128;
-      const uint32_t ahi0 = smem_u32(a_hi), alo0 = smem_u32(a_lo), ring0 = smem_u32(ring);
       const uint32_t tile_cols2 = 2 * p.N2, tile_cols3 = 2 * p.N3;
-      uint32_t chunk = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        const uint32_t ph = it & 1;
-        // ---- stage 1: H1 = W1 x0 over every stored row ----
-        mbar_wait(bar(BAR_AREADY), ph);
-        {
-          const uint32_t st = chunk % p.nstages, round = chunk / p.nstages; ++chunk;
-          mbar_wait(bar(BAR_FULL + st), round & 1);
+      const uint64_t ahi_lin = make_desc(smem_u32(a_hi), 1024), alo_lin = make_desc(smem_u32(a_lo), 1024);   // stages 1 / 3: plain 128-row tiles
+      const uint64_t ahi_seg = make_desc(smem_u32(a_hi), sbo2), alo_seg = make_desc(smem_u32(a_lo), sbo2);   // stage 2: group stride GS rows
+      const uint64_t bdesc0 = make_desc(smem_u32(ring), 1024);
+      const uint32_t stage_u = (uint32_t)p.stage_bytes >> 4, region_u = (uint32_t)p.region_bytes >> 4;        // descriptor address units (16 B)
+      const uint32_t tile_u2 = sbo2, ys_u = (uint32_t)p.YS * 8;                                                 // 16 groups * sbo2 / 16; image-row stride
+      const int nst = p.nstages, P = p.P, T1 = p.T1, T2 = p.T2, KH = p.KH, KW = p.KW, KS1 = p.KS1;
+      const int ks_last = (p.Ch - (P - 1) * 32) >> 3;
+      uint32_t st = 0, rphase = 0;                               // ring slot being consumed (persists across tiles)
+      const bool prof = PROF && a.prof != nullptr && blockIdx.x == 0;
+      long long tp = prof ? clock64() : 0, acc8 = 0, acc9 = 0, acc10 = 0;
+      auto tick = [&](int slot) {   // counters live in registers; a global read-modify-write here would distort the timeline
+        if (PROF && prof) { const long long now = clock64(); const long long d = now - tp; tp = now; if (slot == 8) acc8 += d; else if (slot == 9) acc9 += d; else acc10 += d; }
+      };
+      // wait until the chunk AFTER the one in slot `st` has landed (no-op when there is none: end of this CTA's work)
+      auto wait_next = [&](bool has_next) {
+        if (has_next) {
+          uint32_t ns = st + 1, nph = rphase;
+          if (ns == (uint32_t)nst) { ns = 0; nph ^= 1; }
+          mbar_wait(bar(BAR_FULL) + 8u * ns, nph);
           tc_fence_after();
-          const uint64_t bdesc = make_desc(ring0 + st * p.stage_bytes, 1024);
-          for (int t = 0; t < p.T1; ++t) {
-            const uint64_t ah = make_desc(ahi0 + t * 16384, 1024), al = make_desc(alo0 + t * 16384, 1024);
-            const uint32_t d = tmem + t * tile_cols2;
-            for (int ks = 0; ks < p.KS1; ++ks) {
-              mma_tf32(d, ah + 2 * ks, bdesc + 2 * ks, id2N2, ks > 0);
-              mma_tf32(d, al + 2 * ks, bdesc + 2 * ks, idN2, 1);
+        }
+      };
+      // issue the k-steps of the chunk in slot `st` against T M-tiles (concat product N' = 2N, then the lo product, per k-step);
+      // the next chunk's barrier is polled before the last M-tile's instructions so its latency hides behind queued MMAs
+      auto issue_chunk = [&](uint64_t ah, uint64_t al, uint32_t tile_u, uint32_t dcols, int T, int ksn, uint32_t id2, uint32_t id1,
+                             uint32_t first_acc, bool has_next) {
+        const uint64_t bd = bdesc0 + st * stage_u;
+        uint32_t d = tmem;
+        for (int t = 0; t < T; ++t) {
+          if (t == T - 1 && T > 1) wait_next(has_next);
+          if (ksn == 4) {
+            mma_tf32(d, ah, bd, id2, first_acc);     mma_tf32(d, al, bd, id1, 1);
+            mma_tf32(d, ah + 2, bd + 2, id2, 1);     mma_tf32(d, al + 2, bd + 2, id1, 1);
+            if (T == 1) wait_next(has_next);
+            mma_tf32(d, ah + 4, bd + 4, id2, 1);     mma_tf32(d, al + 4, bd + 4, id1, 1);
+            mma_tf32(d, ah + 6, bd + 6, id2, 1);     mma_tf32(d, al + 6, bd + 6, id1, 1);
+          } else {
+            if (T == 1) wait_next(has_next);
+            for (int ks = 0; ks < ksn; ++ks) {
+              mma_tf32(d, ah + 2 * ks, bd + 2 * ks, id2, ks > 0 ? 1u : first_acc);
+              mma_tf32(d, al + 2 * ks, bd + 2 * ks, id1, 1);
             }
           }
-          tc_commit(bar(BAR_EMPTY + st));
-          tc_commit(bar(BAR_ACC1));
+          ah += tile_u; al += tile_u; d += dcols;
         }
+        tc_commit(bar(BAR_EMPTY) + 8u * st);                   // frees the slot when these MMAs have read it
+        if (++st == (uint32_t)nst) { st = 0; rphase ^= 1; }
+      };
+
+      if (my_tiles > 0) { mbar_wait(bar(BAR_FULL), 0); tc_fence_after(); }   // first chunk of the first tile; every later chunk is pre-waited
+      for (int it = 0; it < my_tiles; ++it) {
+        const uint32_t ph = it & 1;
+        const bool last_tile = it == my_tiles - 1;
+        // ---- stage 1: H1 = W1 x0 over every stored row ----
+        mbar_wait(bar(BAR_AREADY), ph);
+        tc_fence_after();
+        tick(10);
+        issue_chunk(ahi_lin, alo_lin, 1024, tile_cols2, T1, KS1, id2N2, idN2, 0, true);
+        tc_commit(bar(BAR_ACC1));
+        tick(9);
         // ---- stage 2: KH x KW taps as shifted operand views ----
         mbar_wait(bar(BAR_H1), ph);
         tc_fence_after();
-        for (int tap = 0; tap < p.KH * p.KW; ++tap) {
-          const int ky = tap / p.KW, kx = tap - ky * p.KW;
-          const uint32_t tap_off = (uint32_t)(ky * p.YS + kx) * 128;
-          for (int pn = 0; pn < p.P; ++pn) {
-            const uint32_t st = chunk % p.nstages, round = chunk / p.nstages; ++chunk;
-            const int ksn = min(32, p.Ch - pn * 32) >> 3;
-            const uint32_t first = (tap | pn) == 0;
-            mbar_wait(bar(BAR_FULL + st), round & 1);
-            tc_fence_after();
-            const uint64_t bdesc = make_desc(ring0 + st * p.stage_bytes, 1024);
-            const uint32_t ah_base = ahi0 + pn * p.region_bytes + tap_off, al_base = alo0 + pn * p.region_bytes + tap_off;
-            for (int t = 0; t < p.T2; ++t) {
-              const uint64_t ah = make_desc(ah_base + t * 16 * sbo2, sbo2), al = make_desc(al_base + t * 16 * sbo2, sbo2);
-              const uint32_t d = tmem + t * tile_cols2;
-#pragma unroll 4
-              for (int ks = 0; ks < ksn; ++ks) {
-                mma_tf32(d, ah + 2 * ks, bdesc + 2 * ks, id2N2, !(first && ks == 0));
-                mma_tf32(d, al + 2 * ks, bdesc + 2 * ks, idN2, 1);
-              }
+        tick(10);
+        uint32_t first_acc = 0;
+        uint32_t row_u = 0;                                      // ky * YS rows, in descriptor units
+        for (int ky = 0; ky < KH; ++ky, row_u += ys_u) {
+          uint32_t tap_u = row_u;                                // + kx rows (8 units each)
+          for (int kx = 0; kx < KW; ++kx, tap_u += 8) {
+            uint32_t pan_u = tap_u;
+            for (int pn = 0; pn < P; ++pn, pan_u += region_u) {
+              issue_chunk(ahi_seg + pan_u, alo_seg + pan_u, tile_u2, tile_cols2, T2, pn == P - 1 ? ks_last : 4, id2N2, idN2, first_acc, true);
+              first_acc = 1;
             }
-            tc_commit(bar(BAR_EMPTY + st));
           }
         }
         tc_commit(bar(BAR_ACC2));
+        tick(9);
         // ---- stage 3: h = W3 H2 ----
         mbar_wait(bar(BAR_H2), ph);
         tc_fence_after();
-        for (int pn = 0; pn < p.P; ++pn) {
-          const uint32_t st = chunk % p.nstages, round = chunk / p.nstages; ++chunk;
-          const int ksn = min(32, p.Ch - pn * 32) >> 3;
-          mbar_wait(bar(BAR_FULL + st), round & 1);
-          tc_fence_after();
-          const uint64_t bdesc = make_desc(ring0 + st * p.stage_bytes, 1024);
-          for (int t = 0; t < p.T2; ++t) {
-            const uint64_t ah = make_desc(ahi0 + pn * p.region_bytes + t * 16384, 1024), al = make_desc(alo0 + pn * p.region_bytes + t * 16384, 1024);
-            const uint32_t d = tmem + t * tile_cols3;
-#pragma unroll 4
-            for (int ks = 0; ks < ksn; ++ks) {
-              mma_tf32(d, ah + 2 * ks, bdesc + 2 * ks, id2N3, !(pn == 0 && ks == 0));
-              mma_tf32(d, al + 2 * ks, bdesc + 2 * ks, idN3, 1);
-            }
-          }
-          tc_commit(bar(BAR_EMPTY + st));
-        }
+        tick(10);
+        uint32_t pan_u = 0;
+        for (int pn = 0; pn < P; ++pn, pan_u += region_u)
+          issue_chunk(ahi_lin + pan_u, alo_lin + pan_u, 1024, tile_cols3, T2, pn == P - 1 ? ks_last : 4, id2N3, idN3, pn > 0,
+                      !(last_tile && pn == P - 1));
         tc_commit(bar(BAR_ACC3));
+        tick(9);
       }
+      if (PROF && prof) { a.prof[8] = acc8; a.prof[9] = acc9; a.prof[10] = acc10; }
     }
   } else {
-    // ===================== epilogue warps (TMEM lanes 32*warp .. 32*warp+31) =============================================
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const int row_in_tile = warp * 32 + lane;
+    // ===================== epilogue warps: quadrant = warp % 4 (TMEM lanes 32*quadrant .. +31), group = warp / 4 ========
+    // An epilogue "item" is (M-tile, 16 accumulator columns); the kEpiGroups warps of a quadrant take items round-robin.
+    const int quad = warp & 3, grp = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const int row_in_tile = quad * 32 + lane;
     const int kc1 = p.KS1 * 2;                                // 16-byte chunks of x0 per stored row
+    const int nc2 = (p.N2 + 31) >> 5, nc3 = p.N3 >> 4;        // items per M-tile: 32 columns (stages 1-2), 16 columns (stage 3)
+    const bool prof = PROF && a.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    long long tp = 0, pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    auto tick = [&](int slot) { if (PROF && prof) { const long long now = clock64(); pacc[slot] += now - tp; tp = now; } };
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t ph = it & 1;
       const int tile = blockIdx.x + it * gridDim.x;
       const int b0 = tile * p.S, nS = min(p.S, p.B - b0);
       // ---- x0 staging -> operand rows (reflect halo / segment overlap applied here) ----
+      if (PROF && prof) tp = clock64();
       mbar_wait(bar(BAR_XFULL), ph);
-      for (int idx = tid; idx < p.R * kc1; idx += kEpiThreads) {
-        const int r = idx / kc1, j = idx - r * kc1;
-        int s, y, x;
-        decode_stored<SEG>(p, r, s, y, x);
+      tick(0);
+      for (int r = tid; r < p.R; r += kEpiThreads) {
+        const uint32_t w = tab_in[r];
+        const int s = w >> 24, y = (w >> 12) & 0xFFF, x = w & 0xFFF;
         const float* src = xstage + (size_t)s * xfloats + y * p.W + x;
-        float4 hi, lo;
-        const int c = 4 * j;
-        hi.x = (c + 0 < p.Cin && s < nS) ? src[(c + 0) * HW] : 0.f;
-        hi.y = (c + 1 < p.Cin && s < nS) ? src[(c + 1) * HW] : 0.f;
-        hi.z = (c + 2 < p.Cin && s < nS) ? src[(c + 2) * HW] : 0.f;
-        hi.w = (c + 3 < p.Cin && s < nS) ? src[(c + 3) * HW] : 0.f;
-        lo.x = tf32_lo(hi.x); lo.y = tf32_lo(hi.y); lo.z = tf32_lo(hi.z); lo.w = tf32_lo(hi.w);
-        const uint32_t off = sw128(r, c);
-        *reinterpret_cast<float4*>(a_hi + off) = hi;
-        *reinterpret_cast<float4*>(a_lo + off) = lo;
+        const bool live = s < nS;
+        for (int j = 0; j < kc1; ++j) {
+          float4 hi, lo;
+          const int c = 4 * j;
+          hi.x = (c + 0 < p.Cin && live) ? src[(c + 0) * HW] : 0.f;
+          hi.y = (c + 1 < p.Cin && live) ? src[(c + 1) * HW] : 0.f;
+          hi.z = (c + 2 < p.Cin && live) ? src[(c + 2) * HW] : 0.f;
+          hi.w = (c + 3 < p.Cin && live) ? src[(c + 3) * HW] : 0.f;
+          lo.x = tf32_lo(hi.x); lo.y = tf32_lo(hi.y); lo.z = tf32_lo(hi.z); lo.w = tf32_lo(hi.w);
+          const uint32_t off = sw128(r, c);
+          *reinterpret_cast<float4*>(a_hi + off) = hi;
+          *reinterpret_cast<float4*>(a_lo + off) = lo;
+        }
       }
       fence_async_smem();
       mbar_arrive(bar(BAR_XEMPTY));
       mbar_arrive(bar(BAR_AREADY));
+      tick(1);
       // ---- epilogue 1: H1 = relu(acc + b1) for every stored row ----
       mbar_wait(bar(BAR_ACC1), ph);
       tc_fence_after();
-      for (int t = 0; t < p.T1; ++t) {
+      tick(2);
+      for (int item = grp; item < p.T1 * nc2; item += kEpiGroups) {
+        const int t = item / nc2, c0 = (item - t * nc2) << 5;
         const int r = t * 128 + row_in_tile;
         const float* bias = sb1;
-        if (a.bias1_b != nullptr && r < p.R) {
-          int s, y, x;
-          decode_stored<SEG>(p, r, s, y, x);
-          bias = a.bias1_b + (size_t)min(b0 + s, p.B - 1) * p.Ch;
-        }
-        epilogue_to_operand(tmem + lane_base + t * 2 * p.N2, p.N2, bias, a_hi, a_lo, p.region_bytes, r, r < p.R);
+        if (a.bias1_b != nullptr && r < p.R) bias = a.bias1_b + (size_t)min(b0 + (int)(tab_in[r] >> 24), p.B - 1) * p.Ch;
+        epilogue_to_operand(tmem + lane_base + t * 2 * p.N2, p.N2, c0, bias, a_hi, a_lo, p.region_bytes, r, r < p.R);
       }
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(bar(BAR_H1));
+      tick(3);
       // ---- epilogue 2: H2 = relu(acc + b2) at the accumulator's own row index ----
       mbar_wait(bar(BAR_ACC2), ph);
       tc_fence_after();
-      for (int t = 0; t < p.T2; ++t) {
+      tick(4);
+      for (int item = grp; item < p.T2 * nc2; item += kEpiGroups) {
+        const int t = item / nc2, c0 = (item - t * nc2) << 5;
         const int m = t * 128 + row_in_tile;
-        int s, y, x;
-        const bool valid = decode_out<SEG>(p, m, s, y, x);
-        epilogue_to_operand(tmem + lane_base + t * 2 * p.N2, p.N2, sb2, a_hi, a_lo, p.region_bytes, m, valid);
+        epilogue_to_operand(tmem + lane_base + t * 2 * p.N2, p.N2, c0, sb2, a_hi, a_lo, p.region_bytes, m, (tab_out[m] >> 31) != 0);
       }
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(bar(BAR_H2));
+      tick(5);
       // ---- epilogue 3: h = acc + b3 -> HBM (NCHW) ----
       mbar_wait(bar(BAR_ACC3), ph);
       tc_fence_after();
-      for (int t = 0; t < p.T2; ++t) {
+      tick(6);
+      for (int item = grp; item < p.T2 * nc3; item += kEpiGroups) {
+        const int t = item / nc3, c0 = (item - t * nc3) << 4;
         const int m = t * 128 + row_in_tile;
-        int s, y, x;
-        const bool valid = decode_out<SEG>(p, m, s, y, x) && s < nS;
+        const uint32_t w = tab_out[m];
+        const int s = (w >> 24) & 0x7F, y = (w >> 12) & 0xFFF, x = w & 0xFFF;
+        const bool valid = (w >> 31) != 0 && s < nS;
         float* dst = a.h + ((size_t)(b0 + (valid ? s : 0)) * p.Cout) * HW + y * p.W + x;
         const uint32_t taddr = tmem + lane_base + t * 2 * p.N3;
-        for (int c0 = 0; c0 < p.N3; c0 += 16) {
-          float v[16], u[16];
-          tmem_ld16(taddr + c0, v);
-          tmem_ld16(taddr + p.N3 + c0, u);
-          tmem_ld_wait();
-          if (valid) {
+        float v[16], u[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld16(taddr + p.N3 + c0, u);
+        tmem_ld_wait();
+        if (valid) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c0 + i < p.Cout) dst[(size_t)(c0 + i) * HW] = v[i] + u[i] + sb3[c0 + i];
-          }
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < p.Cout) dst[(size_t)(c0 + i) * HW] = v[i] + u[i] + sb3[c0 + i];
         }
       }
       tc_fence_before();
+      tick(7);
+    }
+    if (PROF && prof) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a.prof[i] = pacc[i];
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 // One-time weight repack: torch-layout conv weights -> the chunk stream the producer copies verbatim into the ring.
@@ -403,7 +472,10 @@ __global__ void pack_tc_kernel(const float* __restrict__ w1, const float* __rest
 }
 
 // ---- host-side geometry ------------------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
+
 static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, long long x_bstride, int sms) {
+  const int max_s = env_int("CFPP_TC_MAXS", 32);
   if (!((KH == 1 || KH == 3) && (KW == 1 || KW == 3))) return false;
   if ((KH == 3 && H < 2) || (KW == 3 && W < 2)) return false;
   if (Ch % 16 != 0 || Ch < 16 || Ch > 128 || Cin < 1 || Cin > 32 || Cout < 1 || Cout > 128) return false;
@@ -419,7 +491,7 @@ static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, i
   double best_cost = 1e30; Plan best{}; bool found = false;
   for (int seg = 0; seg <= 1; ++seg) {
     if (seg && (W % 8 != 0)) continue;
-    for (int S = 1; S <= 32 && S <= B; ++S) {
+    for (int S = 1; S <= max_s && S <= B; ++S) {
       Plan q = p; q.seg = seg; q.S = S;
       if (seg) {
         q.NSEG = W / 8; q.GS = 8 + KW - 1; q.YS = S * q.NSEG * q.GS;
@@ -436,7 +508,8 @@ static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, i
       // operand rows the MMAs may touch (garbage rows included) must stay inside this CTA's shared memory
       q.off_ring = 2 * q.P * q.region_bytes;
       const int xbytes = (S * Cin * HW * 4 + 127) / 128 * 128;
-      const int fixed = q.off_ring + xbytes + bias_bytes + bar_bytes + 256;
+      const int tab_bytes = (q.R + q.T2 * 128) * 4;
+      const int fixed = q.off_ring + xbytes + bias_bytes + tab_bytes + bar_bytes + 256;
       int nst = (kSmemMax - fixed) / q.stage_bytes;
       if (nst < 2) break;
       if (nst > kMaxStages) nst = kMaxStages;
@@ -447,7 +520,8 @@ static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, i
       if (reach > q.off_ring + nst * q.stage_bytes) continue;
       q.off_stage_x = q.off_ring + nst * q.stage_bytes;
       q.off_bias = q.off_stage_x + xbytes;
-      q.off_bar = (q.off_bias + bias_bytes + 15) / 16 * 16;
+      q.off_tab = (q.off_bias + bias_bytes + 15) / 16 * 16;
+      q.off_bar = (q.off_tab + tab_bytes + 15) / 16 * 16;
       q.smem_bytes = q.off_bar + bar_bytes + 1024;
       q.ntiles = (B + S - 1) / S;
       // cost: MMA row-slots per real pixel, plus a penalty when the batch no longer fills the SMs evenly
@@ -463,6 +537,7 @@ static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, i
 }
 
 static Plan g_last_plan;
+static long long* g_prof = nullptr;
 
 }  // namespace tc
 }  // namespace cfpp
@@ -503,16 +578,25 @@ extern "C" int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h
   }
   CFPP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0, "conv_cond_tc: x / wpack must be 16-byte aligned");
   tc::g_last_plan = p;
-  tc::Args a{x, h, (const uint8_t*)wpack, b1, b2, b3, bias1_b};
+  const int P_ = (Ch + 31) / 32;
+  const long long pack_bytes = (long long)(1 + KH * KW * P_ + P_) * (2 * Ch * 128);
+  tc::Args a{x, h, (const uint8_t*)wpack, b1, b2, b3, bias1_b, pack_bytes, tc::env_int("CFPP_TC_REPL", 1), tc::g_prof};
   const int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set[2] = {false, false};
-  if (p.seg) {
-    if (!attr_set[1]) { cudaFuncSetAttribute(tc::conv_cond_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[1] = true; }
-    tc::conv_cond_tc_kernel<true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p, a);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc::conv_cond_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc::conv_cond_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc::conv_cond_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc::conv_cond_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  if (a.prof != nullptr) {
+    if (p.seg) tc::conv_cond_tc_kernel<true, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p, a);
+    else tc::conv_cond_tc_kernel<false, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p, a);
   } else {
-    if (!attr_set[0]) { cudaFuncSetAttribute(tc::conv_cond_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[0] = true; }
-    tc::conv_cond_tc_kernel<false><<<grid, tc::kThreads, p.smem_bytes, st>>>(p, a);
+    if (p.seg) tc::conv_cond_tc_kernel<true, false><<<grid, tc::kThreads, p.smem_bytes, st>>>(p, a);
+    else tc::conv_cond_tc_kernel<false, false><<<grid, tc::kThreads, p.smem_bytes, st>>>(p, a);
   }
   return check_launch("conv_cond_tc_fwd");
 }
@@ -522,3 +606,8 @@ extern "C" void cfpp_conv_cond_tc_last_plan(int* out8) {
   const tc::Plan& p = tc::g_last_plan;
   out8[0] = p.seg; out8[1] = p.S; out8[2] = p.R; out8[3] = p.T1; out8[4] = p.T2; out8[5] = p.nstages; out8[6] = p.smem_bytes; out8[7] = p.ntiles;
 }
+
+/* debug: device array of 12 int64 cycle counters accumulated by CTA 0 over its tiles (NULL = off):
+ * {wait x0, x0 transform, wait stage-1 MMAs, epilogue 1, wait stage-2 MMAs, epilogue 2, wait stage-3 MMAs, epilogue 3,
+ *  MMA thread: wait weight chunk, issue, wait operands, spare} */
+extern "C" void cfpp_conv_cond_tc_set_profile(void* counters8) { tc::g_prof = (long long*)counters8; }

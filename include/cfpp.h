@@ -109,6 +109,10 @@ int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h, const voi
 /* geometry of the last cfpp_conv_cond_tc_fwd launch (tests / bench): {segment layout, samples per tile, stored rows, M-tiles of
  * stage 1, M-tiles of stages 2-3, ring stages, shared-memory bytes, tiles} */
 void cfpp_conv_cond_tc_last_plan(int* out8);
+/* debug instrumentation: device array of 12 int64 cycle counters that CTA 0 accumulates over its tiles; NULL = off.
+ * epilogue thread 0: {wait x0, x0 transform, wait stage-1 MMAs, epilogue 1, wait stage-2 MMAs, epilogue 2, wait stage-3 MMAs,
+ * epilogue 3}; MMA thread: {wait weight chunk, issue, wait operands, spare} */
+void cfpp_conv_cond_tc_set_profile(void* counters8);
 
 /* SimpleViT conditioner of TransCoupling, layers/simple_vit.py:91-127 (heads=1, dim_head=64, dim=mlp_dim=T, GELU-erf,
  * LayerNorm eps 1e-5).  All weight matrices PACKED K-major (in_features, out_features). */

@@ -26,15 +26,16 @@ constexpr uint32_t AHI = 0, ALO = 64 * 1024, BHI = 128 * 1024;
 // variant 4: like 1 but tile outer, ks inner
 // variant 5: like 0 but passes outermost inside a k-step group: for pass: for ks: for tile
 template <int N, int T, int V>
-__global__ void __launch_bounds__(128) probe_kernel(int reps, long long* __restrict__ cycles) {
+__global__ void __launch_bounds__(128) probe_kernel(int reps, long long* __restrict__ cycles, int roff, int sbo, int nw, int gap) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar_[4];
+  uint64_t& bar = bar_[threadIdx.x >> 5];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < 48 * 1024; i += 128) ((float*)base)[i] = 0.001f * (i % 97);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  if (tid == 0) {
+  if ((tid & 31) == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -45,15 +46,16 @@ __global__ void __launch_bounds__(128) probe_kernel(int reps, long long* __restr
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = tmem_base_s;
-  if (tid == 0) {
+  const uint32_t tmem = tmem_base_s + (warp & 1) * 256;
+  if ((tid & 31) == 0 && warp < nw) {
     const uint32_t s0 = smem_u32(base);
     constexpr uint32_t idN = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t id2N = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr int stride = V == 0 || V == 5 ? N : (V == 2 || V == 3 ? 3 * N : 2 * N);
-    const uint64_t dAhi = make_desc(s0 + AHI, 1024), dAlo = make_desc(s0 + ALO, 1024), dBhi = make_desc(s0 + BHI, 1024), dBlo = make_desc(s0 + BHI + N * 128, 1024);
+    const uint64_t dAhi = make_desc(s0 + AHI + roff * 128, sbo), dAlo = make_desc(s0 + ALO + roff * 128, sbo), dBhi = make_desc(s0 + BHI, 1024), dBlo = make_desc(s0 + BHI + N * 128, 1024);
     const long long t0 = clock64();
     for (int rep = 0; rep < reps; ++rep) {
+      if (gap > 0) { const long long tg = clock64(); while (clock64() - tg < gap) {} }
       auto emit = [&](int t, int ks) {
         const uint32_t col = tmem + t * stride; const uint64_t a = (uint64_t)((t * 16384 + ks * 32) >> 4), b = (uint64_t)((ks * 32) >> 4);
         if (V == 0) {
@@ -91,37 +93,38 @@ __global__ void __launch_bounds__(128) probe_kernel(int reps, long long* __restr
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     uint32_t ok = 0;
     while (!ok) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0) : "memory");
-    *cycles = clock64() - t0;
+    cycles[warp] = clock64() - t0;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
+static int g_roff = 0, g_sbo = 1024, g_nw = 1, g_gap = 0;
 template <int N, int T, int V>
 void run(long long* dC) {
   constexpr int stride = V == 0 || V == 5 ? N : (V == 2 || V == 3 ? 3 * N : 2 * N);
-  if (T * stride > 512) return;
+  if (T * stride > 256) return;
   const size_t smem = 192 * 1024 + 1024;
   cudaFuncSetAttribute(probe_kernel<N, T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   long long best = 1LL << 60;
   const int reps = 64;
   for (int it = 0; it < 4; ++it) {
-    probe_kernel<N, T, V><<<1, 128, smem>>>(reps, dC);
+    probe_kernel<N, T, V><<<1, 128, smem>>>(reps, dC, g_roff, g_sbo, g_nw, g_gap);
     if (cudaDeviceSynchronize() != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(cudaGetLastError())); return; }
     long long c; cudaMemcpy(&c, dC, 8, cudaMemcpyDeviceToHost);
     if (c < best) best = c;
   }
   const int nmma = 4 * T * (V == 0 || V == 5 ? 3 : 2);
   const double per_kstep = (double)best / (reps * 4 * T);
-  printf("N=%3d tiles=%d variant=%d : %6.1f clk per (tile,k-step) -> %6.0f useful MAC/clk/SM (%.1f clk/MMA)\n", N, T, V, per_kstep,
+  printf("gap=%4d issuers=%d roff=%d sbo=%d N=%3d tiles=%d variant=%d : %6.1f clk per (tile,k-step) -> %6.0f useful MAC/clk/SM (%.1f clk/MMA)\n", g_gap, g_nw, g_roff, g_sbo, N, T, V, per_kstep,
          128.0 * N * 8 / per_kstep, (double)best / (reps * nmma));
 }
-template <int N, int T> void runv(long long* dC) { run<N, T, 0>(dC); run<N, T, 5>(dC); run<N, T, 1>(dC); run<N, T, 2>(dC); run<N, T, 3>(dC); run<N, T, 4>(dC); }
-template <int N> void runt(long long* dC) { runv<N, 1>(dC); runv<N, 2>(dC); runv<N, 4>(dC); }
+template <int N, int T> void runv(long long* dC) { run<N, T, 0>(dC); run<N, T, 1>(dC); }
+template <int N> void runt(long long* dC) { runv<N, 1>(dC); runv<N, 2>(dC); }
 
 int main() {
-  long long* dC; cudaMalloc(&dC, 8);
-  runt<16>(dC); runt<32>(dC); runt<64>(dC); runt<128>(dC);
+  long long* dC; cudaMalloc(&dC, 64);
+  for (int gap : {0, 50, 100, 200, 300, 400, 600}) { g_gap = gap; run<64, 1, 1>(dC); run<64, 2, 1>(dC); run<128, 1, 1>(dC); }
   return 0;
 }
