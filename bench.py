@@ -29,6 +29,7 @@ def parse():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=0, help='samples per GPU per step (0 = workload default)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying the captured CUDA graph')
     return ap.parse_args()
 
 
@@ -133,18 +134,25 @@ def main():
     host = [tuple(t.pin_memory() for t in fresh()) for _ in range(NBUF)]
     devb = [(x.to(dev), c.to(dev)) for x, c in host]
     sharder = ShardedLogProb(lambda x, c: model.log_prob(x, c), M)
+    from contextflow_b200.graphed import GraphedLogProb
+    graphed = None if a.eager else GraphedLogProb(model)
+
+    def run(x, c):
+        """One log_prob pass: a replay of the captured CUDA graph (x / c are copied into its static input buffers -- device to
+        device for resident inputs, pinned host to device for the end-to-end leg), or the eager launch sequence with --eager."""
+        if graphed is not None:
+            return graphed(x, c, clone=False)
+        return model.log_prob(x.to(dev, non_blocking=True), c.to(dev, non_blocking=True))
 
     def step(i):
         x, c = devb[i % NBUF]
         with torch.no_grad():
-            lp = model.log_prob(x, c)
-            return sharder.gather(lp, B * world)          # the path's only exchange: final score gather (no-op at N=1)
+            return sharder.gather(run(x, c), B * world)   # the path's only exchange: final score gather (no-op at N=1)
 
     def step_e2e(i, out_host):
         hx, hc = host[i % NBUF]
         with torch.no_grad():
-            x = hx.to(dev, non_blocking=True); c = hc.to(dev, non_blocking=True)
-            lp = sharder.gather(model.log_prob(x, c), B * world)
+            lp = sharder.gather(run(hx, hc), B * world)
             out_host.copy_(lp[:out_host.shape[0]], non_blocking=True)
         torch.cuda.synchronize()
 
@@ -158,7 +166,6 @@ def main():
         step(i)
     barrier()
     sampler = ClockSampler(local); sampler.start()
-    timer = ops.OpTimer(); ops.set_timer(timer)
     l0 = _cabi.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -167,14 +174,22 @@ def main():
         step(i)
     ev1.record()
     barrier()
-    ops.set_timer(None)
     ms = ev0.elapsed_time(ev1)
-    launches = _cabi.launch_count() - l0
+    launches = _cabi.launch_count() - l0 if graphed is None else graphed.launches_per_replay(*devb[0]) * a.steps
+    clocks = sampler.summary()
+    # per-kernel durations: the same steps launched eagerly with a CUDA-event pair around every libcfpp launch (events cannot be
+    # read back from inside a replayed graph); same kernels, same inputs, right after the timed region
+    timer = ops.OpTimer(); ops.set_timer(timer)
+    with torch.no_grad():
+        for i in range(a.steps):
+            x, c = devb[i % NBUF]
+            model.log_prob(x, c)
+    barrier()
+    ops.set_timer(None)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    clocks = sampler.summary()
 
     # end to end through the public API with host buffers (pinned H2D of x, ctx; D2H of the log-probs), timed on the host clock
     out_host = torch.empty((B * world if rank == 0 else B, M), dtype=torch.float32).pin_memory()
@@ -227,7 +242,9 @@ def main():
         line = {'metric': METRIC, 'value': world * B * a.steps / (ms / 1e3), 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
                 'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                 'config': {'workload': f'{workload}: {WORKLOADS[workload]}', 'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': f'dp{world} (batch-sharded, final all-gather of log-probs)',
-                           'l2_policy': f'{NBUF} rotating input batches; per-layer working set {12 * B * C * H * W / 1e6:.0f} MB > 126 MB L2', 'weights': 'synthetic fill (synth.fill_state)'},
+                           'l2_policy': f'{NBUF} rotating input batches; per-layer working set {12 * B * C * H * W / 1e6:.0f} MB > 126 MB L2', 'weights': 'synthetic fill (synth.fill_state)',
+                           'launch': 'eager (one Python call per kernel)' if graphed is None else 'CUDA graph replay of the whole log_prob (contextflow_b200/graphed.py)',
+                           'kernel_timing': 'per-launch CUDA events in an eager pass over the same steps right after the timed region'},
                 'clocks': clocks, 'gpu_launches': launches,
                 'e2e': {'value': world * B * a.steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': x0.numel() * 4 + c0.numel() * 8, 'd2h_bytes_per_step': B * world * M * 4},
                 'roofline': roof, 'roofline_coupling': roof_c, 'kernels': kernels}

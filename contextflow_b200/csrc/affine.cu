@@ -41,120 +41,189 @@ __global__ void slogdet_kernel(const float* __restrict__ A, int D, float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Conv1x1 (+ optional ActNorm epilogue): per sample a (D x D) by (D x HW) product.  A CTA owns NSUB sub-tiles, each
-// (one sample, PT pixels); the matrix (shared, or assembled per sample from the raw context matrix c) is kept TRANSPOSED
-// in shared memory so that a thread's 4 output rows are one 128-bit load, the pixel tile likewise; each thread owns a
-// 4 (rows) x 4 (pixels) register tile: 16 FMA per two LDS.128.
+// Conv1x1 (+ optional ActNorm epilogue): per sample a (D x D) by (D x HW) product, z[i][p] = sum_j W[i][j] x[j][p].
+// The matrix is per sample in specialist mode (assembled from the raw context matrix c) and used for only HW pixels, so
+// the kernel is organised around NOT moving it twice: a CTA takes NS samples, assembles their matrices row-major into
+// shared memory with coalesced reads of c (the only pass over c), and every thread owns ONE pixel column: its D inputs are
+// loaded from HBM straight into registers (coalesced along pixels, never staged), the matrix rows arrive as warp-broadcast
+// 128-bit shared loads (4 FMA per load), and outputs are stored coalesced along pixels.  When a sample has few pixels
+// (HW = 16) the output rows are split over G thread groups so a CTA still has 256 threads of work per 4 matrices.
 // ---------------------------------------------------------------------------------------------------------------
 struct Conv1x1Args {
   const float* x; float* z; float* ldj; const float* NN; const float* logabsdet;
   const float* c; const float* logp_c; int contextflow;
   const float* an_t; const float* an_logs; int an_per_sample; const float* an_logp_c; float an_logp_scale;
-  int B, D, HW, PT, NI, TPS, NSUB, tiles_per_sample, WS;
+  int B, D, HW, NS, PT, CPS, NCOLP, G, IR, DR, tiles_per_sample;   // CPS = thread columns per sample tile (PT / PX), DR = D rounded up to 4
 };
 
-template <bool VEC>
+template <int PX> struct PixVec;
+template <> struct PixVec<1> { using T = float; };
+template <> struct PixVec<2> { using T = float2; };
+template <> struct PixVec<4> { using T = float4; };
+__device__ __forceinline__ void pv_load(float (&d)[1], const float* p) { d[0] = __ldg(p); }
+__device__ __forceinline__ void pv_load(float (&d)[2], const float* p) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); d[0] = v.x; d[1] = v.y; }
+__device__ __forceinline__ void pv_load(float (&d)[4], const float* p) { const float4 v = ldg_stream(reinterpret_cast<const float4*>(p)); d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+__device__ __forceinline__ void pv_store(float* p, const float (&d)[1]) { *p = d[0]; }
+__device__ __forceinline__ void pv_store(float* p, const float (&d)[2]) { *reinterpret_cast<float2*>(p) = make_float2(d[0], d[1]); }
+__device__ __forceinline__ void pv_store(float* p, const float (&d)[4]) { stg_stream(reinterpret_cast<float4*>(p), make_float4(d[0], d[1], d[2], d[3])); }
+
+// DT = padded matrix width (>= D, multiple of 16), PX = consecutive pixels per thread (register tile along pixels: every matrix
+// value fetched from shared memory feeds PX FMAs and the loads / stores of x and z are PX-wide).
+template <int DT, int PX>
 __global__ void __launch_bounds__(256) conv1x1_kernel(const Conv1x1Args a) {
   extern __shared__ float4 smem4[];
-  const int D = a.D, HW = a.HW, PT = a.PT, WS = a.WS;
-  const int nmat = a.c ? a.NSUB : 1;
-  float* Wt = reinterpret_cast<float*>(smem4);                 // [nmat][D][WS]   Wt[j][i] = W[i][j]
-  float* xs = Wt + (int64_t)nmat * D * WS;                     // [NSUB][D][PT]
-  const int64_t total_sub = (int64_t)a.B * a.tiles_per_sample;
-  const int64_t st0 = (int64_t)blockIdx.x * a.NSUB;
+  const int D = a.D, HW = a.HW, DR = a.DR;
+  const int nmat = a.c ? a.NS : 1;
+  float* Ws = reinterpret_cast<float*>(smem4);                 // [nmat][DR][DT] row-major; rows >= D and columns >= D are zero
+  float* sh = Ws + (size_t)nmat * DR * DT;                     // [NS][DR] ActNorm shift
+  float* sc = sh + (size_t)a.NS * DR;                          // [NS][DR] ActNorm exp(-logs)
+  const int64_t grp = blockIdx.x;                              // group of NS samples x one pixel tile
+  const int64_t sg = grp / a.tiles_per_sample;
+  const int ptile = (int)(grp - sg * a.tiles_per_sample);
+  const int64_t b0 = sg * a.NS;
+  const int nS = (int)min((int64_t)a.NS, (int64_t)a.B - b0);
+  const int tid = threadIdx.x, nthr = blockDim.x;
 
-  // ---- assemble the matrices (transposed) and the pixel tiles: one warp per (matrix row | channel row), lanes along it ----
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int mi = warp; mi < nmat * D; mi += nwarps) {
-    const int m = mi / D, i = mi - m * D;
-    const int64_t st = st0 + m;
-    float* Wm = Wt + (int64_t)m * D * WS + i;
-    if (!a.c) {
-      for (int j = lane; j < D; j += 32) Wm[j * WS] = a.NN[i * D + j];
-    } else if (st < total_sub) {                               // conv1x1.py:36-49
-      const float* crow = a.c + ((st / a.tiles_per_sample) * D + i) * D;
-      for (int j = lane; j < D; j += 32) {
-        const float cij = crow[j];
-        float v = (j < i) ? cij : (j == i ? expf(cij) : 0.f);
-        if (a.contextflow) v = (v - (i == j ? 1.f : 0.f)) + a.NN[i * D + j];
-        Wm[j * WS] = v;
+  // ---- this thread's PX pixel columns: their D inputs go straight from HBM to registers, issued first so the latency overlaps
+  //      the matrix assembly below ----
+  const int g = tid / a.NCOLP, col = tid - g * a.NCOLP;
+  const int m = col / a.CPS, pl = (col - m * a.CPS) * PX;
+  const int p = ptile * a.PT + pl;
+  const bool live = col < a.NS * a.CPS && m < nS && p < HW;    // HW % PX == 0 (host): a live thread owns PX real pixels
+  const int64_t b = b0 + (live ? m : 0);
+  float xc[DT][PX];
+  {
+    const float* xg = a.x + (b * D) * (int64_t)HW + (live ? p : 0);
+#pragma unroll
+    for (int j = 0; j < DT; ++j) {
+      if (live && j < D) pv_load(xc[j], xg + (int64_t)j * HW);
+      else {
+#pragma unroll
+        for (int q = 0; q < PX; ++q) xc[j][q] = 0.f;
       }
     }
   }
-  for (int mj = warp; mj < a.NSUB * D; mj += nwarps) {
-    const int m = mj / D, j = mj - m * D;
-    const int64_t st = st0 + m;
-    float* xr = xs + (int64_t)mj * PT;
-    if (st < total_sub) {
-      const int64_t b = st / a.tiles_per_sample; const int p0t = (int)(st % a.tiles_per_sample) * PT;
-      const float* xg = a.x + (b * D + j) * HW + p0t;
-      for (int pl = lane; pl < PT; pl += 32) xr[pl] = (p0t + pl < HW) ? xg[pl] : 0.f;
-    } else {
-      for (int pl = lane; pl < PT; pl += 32) xr[pl] = 0.f;
+
+  // ---- matrices: W = NN (shared) or tril(c,-1) + diag(exp(diag c)) [- I + NN]   (conv1x1.py:36-49), row-major in shared memory.
+  //      c is streamed exactly once: the NS matrices of this CTA are one contiguous run of floats, read as 128-bit loads with four
+  //      loads in flight per thread before any of them is consumed ----
+  if (D != DT) {                                                 // padding rows / columns must read as zero
+    for (int idx = tid; idx < nmat * DR * DT; idx += nthr) Ws[idx] = 0.f;
+    __syncthreads();
+  }
+  if (!a.c) {
+    for (int idx = tid; idx < D * D; idx += nthr) { const int i = idx / D, j = idx - i * D; Ws[i * DT + j] = a.NN[idx]; }
+  } else if ((D & 3) == 0) {
+    const int D4 = D >> 2, units = nS * D * D4;
+    const float4* c4 = reinterpret_cast<const float4*>(a.c + b0 * (int64_t)D * D);
+    const float4* n4 = reinterpret_cast<const float4*>(a.NN);
+    for (int u0 = tid; u0 < units; u0 += 4 * nthr) {
+      float4 cv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const int u = u0 + k * nthr; if (u < units) cv[k] = ldg_stream(c4 + u); }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int u = u0 + k * nthr;
+        if (u < units) {
+          int row, j0, mm, i;
+          if (D == DT) { row = u / (DT / 4); j0 = (u % (DT / 4)) << 2; mm = row / DT; i = row % DT; }     // compile-time divisors
+          else { row = u / D4; j0 = (u - row * D4) << 2; mm = row / D; i = row - mm * D; }
+          float v[4] = {cv[k].x, cv[k].y, cv[k].z, cv[k].w};
+          if (j0 + 3 < i) {}                                               // strictly below the diagonal: W = c
+          else if (j0 > i) { v[0] = v[1] = v[2] = v[3] = 0.f; }            // strictly above: 0
+          else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int j = j0 + q; v[q] = (j < i) ? v[q] : (j == i ? expf(v[q]) : 0.f); }
+          }
+          if (a.contextflow) {
+            const float4 nn = __ldg(n4 + (i * D4 + (j0 >> 2)));
+            v[0] += nn.x; v[1] += nn.y; v[2] += nn.z; v[3] += nn.w;
+            if (j0 <= i && i <= j0 + 3) v[i - j0] -= 1.f;
+          }
+          *reinterpret_cast<float4*>(Ws + ((size_t)mm * DR + i) * DT + j0) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    }
+  } else {
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+    for (int row = warp; row < nS * D; row += nwarps) {
+      const int mm = row / D, i = row - mm * D;
+      float* wrow = Ws + ((size_t)mm * DR + i) * DT;
+      const float* nrow = a.NN + (size_t)i * D;
+      const float* crow = a.c + ((b0 + mm) * D + i) * (int64_t)D;
+      for (int j = lane; j < D; j += 32) {
+        const float cij = crow[j];
+        float v = (j < i) ? cij : (j == i ? expf(cij) : 0.f);
+        if (a.contextflow) v = (v - (i == j ? 1.f : 0.f)) + nrow[j];
+        wrow[j] = v;
+      }
+    }
+  }
+  if (a.an_logs) {
+    for (int idx = tid; idx < a.NS * D; idx += nthr) {
+      const int mm = idx / D, i = idx - mm * D;
+      const int64_t bb = min(b0 + mm, (int64_t)a.B - 1);
+      sh[mm * DR + i] = a.an_t[(a.an_per_sample ? bb * D : 0) + i];
+      sc[mm * DR + i] = expf(-a.an_logs[(a.an_per_sample ? bb * D : 0) + i]);
+    }
+  }
+  // ---- per-sample ldj: one warp per sample (only the CTA of the sample's first pixel tile writes it) ----
+  if (ptile == 0) {
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+    for (int ms = warp; ms < nS; ms += nwarps) {
+      const int64_t bb = b0 + ms;
+      float part = 0.f, part_an = 0.f;
+      if (a.c) for (int i = lane; i < D; i += 32) part += a.c[(bb * D + i) * (int64_t)D + i];
+      if (a.an_logs) for (int i = lane; i < D; i += 32) part_an += a.an_logs[(a.an_per_sample ? bb * D : 0) + i];
+      part = warp_sum(part); part_an = warp_sum(part_an);
+      if (lane == 0) {
+        float l;
+        if (a.c) { l = (float)HW * ((a.contextflow ? a.logabsdet[0] : 0.f) + part); if (a.logp_c) l += a.logp_c[bb] * (float)HW; }
+        else l = a.logabsdet[0] * (float)HW;
+        if (a.an_logs) { l += part_an; if (a.an_logp_c) l += a.an_logp_scale * a.an_logp_c[bb]; }
+        a.ldj[bb] = l;
+      }
     }
   }
   __syncthreads();
+  if (!live) return;
 
-  const int m = threadIdx.x / a.TPS, t = threadIdx.x % a.TPS;
-  const int64_t st = st0 + m;
-  if (m >= a.NSUB || st >= total_sub) return;
-  const int64_t b = st / a.tiles_per_sample;
-  const int ptile = (int)(st % a.tiles_per_sample);
-
-  // ---- per-sample ldj (one thread per sample) ----
-  if (ptile == 0 && t == 0) {
-    float l = 0.f;
-    if (a.c) {
-      float cl = 0.f;
-      for (int i = 0; i < D; ++i) cl += a.c[(b * D + i) * D + i];
-      l = (float)HW * ((a.contextflow ? a.logabsdet[0] : 0.f) + cl);
-      if (a.logp_c) l += a.logp_c[b] * (float)HW;
-    } else l = a.logabsdet[0] * (float)HW;
-    if (a.an_logs) {
-      const float* lg = a.an_logs + (a.an_per_sample ? b * D : 0);
-      float sl = 0.f;
-      for (int i = 0; i < D; ++i) sl += lg[i];
-      l += sl;
-      if (a.an_logp_c) l += a.an_logp_scale * a.an_logp_c[b];
-    }
-    a.ldj[b] = l;
-  }
-
-  const int ig = t % a.NI, pg = t / a.NI;
-  const int i0 = 4 * ig, p0 = 4 * pg;
-  const float* Wm = Wt + (a.c ? (int64_t)m * D * WS : 0) + i0;
-  const float* xm = xs + (int64_t)m * D * PT + p0;
-  float acc[4][4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
-#pragma unroll 4
-  for (int j = 0; j < D; ++j) {
-    const float4 w = *reinterpret_cast<const float4*>(Wm + j * WS);
-    const float4 xv = *reinterpret_cast<const float4*>(xm + j * PT);
-    const float wr[4] = {w.x, w.y, w.z, w.w}, xq[4] = {xv.x, xv.y, xv.z, xv.w};
+  // ---- 4 output rows x PX pixels per pass; matrix rows arrive as warp-broadcast 128-bit shared loads ----
+  const float* Wm = Ws + (a.c ? (size_t)m * DR * DT : 0);
+  const float* shm = sh + (size_t)m * DR; const float* scm = sc + (size_t)m * DR;
+  float* zg = a.z + (b * D) * (int64_t)HW + p;
+  const int i_beg = g * a.IR, i_end = min(DR, i_beg + a.IR);
+  const bool an = a.an_logs != nullptr;
+  for (int i0 = i_beg; i0 < i_end; i0 += 4) {
+    float acc[4][PX];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[r][q] = fmaf(wr[r], xq[q], acc[r][q]);
-  }
-  const float* at = a.an_t ? a.an_t + (a.an_per_sample ? b * D : 0) : nullptr;
-  const float* al = a.an_logs ? a.an_logs + (a.an_per_sample ? b * D : 0) : nullptr;
-  const int p = ptile * PT + p0;
+      for (int q = 0; q < PX; ++q) acc[r][q] = 0.f;
+    const float* w0 = Wm + (size_t)i0 * DT;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int i = i0 + r;
-    if (i >= D) break;
-    float v[4] = {acc[r][0], acc[r][1], acc[r][2], acc[r][3]};
-    if (al) { const float tt = at[i], e = expf(-al[i]);
+    for (int j = 0; j < DT; j += 4) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) v[q] = (v[q] - tt) * e; }
-    float* zp = a.z + (b * D + i) * HW + p;
-    if (VEC) { if (p < HW) *reinterpret_cast<float4*>(zp) = make_float4(v[0], v[1], v[2], v[3]); }
-    else {
+      for (int r = 0; r < 4; ++r) {
+        const float4 w = *reinterpret_cast<const float4*>(w0 + r * DT + j);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) if (p + q < HW) zp[q] = v[q];
+        for (int q = 0; q < PX; ++q) {
+          acc[r][q] = fmaf(w.x, xc[j][q], acc[r][q]); acc[r][q] = fmaf(w.y, xc[j + 1][q], acc[r][q]);
+          acc[r][q] = fmaf(w.z, xc[j + 2][q], acc[r][q]); acc[r][q] = fmaf(w.w, xc[j + 3][q], acc[r][q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + r;
+      if (i < D) {
+        if (an) {
+          const float t = shm[i], e = scm[i];
+#pragma unroll
+          for (int q = 0; q < PX; ++q) acc[r][q] = (acc[r][q] - t) * e;
+        }
+        pv_store(zg + (int64_t)i * HW, acc[r]);
+      }
     }
   }
 }
@@ -254,35 +323,37 @@ extern "C" int cfpp_conv1x1_fwd(const float* x, float* z, float* ldj, const floa
   CFPP_REQUIRE((an_t == nullptr) == (an_logs == nullptr), "conv1x1: an_t and an_logs must be given together");
   if (B <= 0) return CFPP_OK;
   Conv1x1Args a{x, z, ldj, NN, logabsdet, c, logp_c, contextflow, an_t, an_logs, an_per_sample, an_logp_c, an_logp_scale, B, D, HW};
-  const int DP = (D + 3) / 4 * 4;
-  a.NI = DP / 4;
-  a.WS = DP + 4;                                            // row stride of the transposed matrix (16B aligned, bank-rotated)
-  int pt_cap = 4 * (128 / a.NI > 1 ? 128 / a.NI : 1);
-  int hw4 = ((HW < 128 ? HW : 128) + 3) / 4 * 4;
-  a.PT = hw4 < pt_cap ? hw4 : pt_cap;
-  a.TPS = a.NI * (a.PT / 4);
+  const int DT = D <= 16 ? 16 : D <= 32 ? 32 : D <= 64 ? 64 : D <= 96 ? 96 : 128;
+  const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(z)) & 15) == 0;
+  int PX = DT == 16 ? 4 : DT == 32 ? 2 : 1;                 // DT * PX = 64 input registers per thread
+  while (PX > 1 && (HW % PX != 0 || !al16)) PX >>= 1;
+  a.DR = (D + 3) / 4 * 4;
+  a.PT = HW < 256 * PX ? HW : 256 * PX;
+  a.CPS = (a.PT + PX - 1) / PX;
   a.tiles_per_sample = (HW + a.PT - 1) / a.PT;
-  const size_t per_sub = ((size_t)D * a.PT + (c ? (size_t)D * a.WS : 0)) * sizeof(float);
-  const size_t fixed = c ? 0 : (size_t)D * a.WS * sizeof(float);
-  int nsub = 256 / a.TPS; if (nsub < 1) nsub = 1;
-  const int by_smem = (int)((100 * 1024 - fixed) / per_sub);
-  if (nsub > by_smem) nsub = by_smem < 1 ? 1 : by_smem;
-  const int64_t total_sub = (int64_t)B * a.tiles_per_sample;
-  if (nsub > total_sub) nsub = (int)total_sub;
-  a.NSUB = nsub;
-  const size_t smem = fixed + (size_t)nsub * per_sub;
-  CFPP_REQUIRE(a.TPS <= 256 && smem <= 200 * 1024, "conv1x1: tile does not fit (D=%d)", D);
-  const int threads = (nsub * a.TPS + 31) / 32 * 32;
-  const int64_t blocks = (total_sub + nsub - 1) / nsub;
-  const bool vec = (HW % 4 == 0) && (reinterpret_cast<uintptr_t>(z) % 16 == 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(conv1x1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv1x1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
-  if (vec) conv1x1_kernel<true><<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(a);
-  else conv1x1_kernel<false><<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(a);
+  int ns = 256 / a.CPS; if (ns < 1) ns = 1;
+  const size_t mat_bytes = (size_t)a.DR * DT * sizeof(float);
+  if (c) { const int by_smem = (int)((72 * 1024) / mat_bytes); if (ns > by_smem) ns = by_smem < 1 ? 1 : by_smem; }
+  if (ns > B) ns = B;
+  a.NS = ns;
+  a.NCOLP = (ns * a.CPS + 31) / 32 * 32;
+  int G = 256 / a.NCOLP; if (G < 1) G = 1;
+  int IR = ((a.DR + G - 1) / G + 3) / 4 * 4;
+  G = (a.DR + IR - 1) / IR;
+  a.G = G; a.IR = IR;
+  const int threads = G * a.NCOLP;
+  const size_t smem = (size_t)(c ? ns : 1) * mat_bytes + (size_t)2 * ns * a.DR * sizeof(float);
+  CFPP_REQUIRE(threads <= 256 && smem <= 200 * 1024, "conv1x1: tile does not fit (D=%d)", D);
+  const int64_t blocks = (int64_t)((B + ns - 1) / ns) * a.tiles_per_sample;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CFPP_C1(DT_, PX_) do { static bool set_ = false; if (!set_) { cudaFuncSetAttribute(conv1x1_kernel<DT_, PX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set_ = true; } \
+    conv1x1_kernel<DT_, PX_><<<(unsigned)blocks, threads, smem, st>>>(a); } while (0)
+  if (DT == 16) { if (PX == 4) CFPP_C1(16, 4); else if (PX == 2) CFPP_C1(16, 2); else CFPP_C1(16, 1); }
+  else if (DT == 32) { if (PX == 2) CFPP_C1(32, 2); else CFPP_C1(32, 1); }
+  else if (DT == 64) CFPP_C1(64, 1);
+  else if (DT == 96) CFPP_C1(96, 1);
+  else CFPP_C1(128, 1);
+#undef CFPP_C1
   return check_launch("conv1x1_fwd");
 }
 

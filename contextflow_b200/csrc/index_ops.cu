@@ -23,6 +23,22 @@ __global__ void squeeze_kernel(const float* __restrict__ x, float* __restrict__ 
   }
 }
 
+// Squeeze with a (2,2) patch and W % 8 == 0 (the image stacks): a thread moves 8 consecutive input floats of one input row
+// (two 128-bit streaming loads) to the two output planes j = 0 / 1 (one 128-bit streaming store each); no per-element index math.
+__global__ void __launch_bounds__(256) squeeze22_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t units, int H, int W) {
+  const int W8 = W >> 3, Ho = H >> 1, Wo = W >> 1;
+  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < units; u += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = u / W8; const int wq = (int)(u - r * W8);
+    const int64_t bc = r / H; const int hi = (int)(r - bc * H);
+    const int h = hi >> 1, i = hi & 1;
+    const float4* src = reinterpret_cast<const float4*>(x + r * W + wq * 8);
+    const float4 a = ldg_stream(src), b = ldg_stream(src + 1);
+    float* dst = y + ((bc * 4 + i * 2) * Ho + h) * (int64_t)Wo + wq * 4;
+    stg_stream(reinterpret_cast<float4*>(dst), make_float4(a.x, a.z, b.x, b.z));
+    stg_stream(reinterpret_cast<float4*>(dst + (int64_t)Ho * Wo), make_float4(a.y, a.w, b.y, b.w));
+  }
+}
+
 // ---- PermuteAxes (0,2,1,3): y[b,h,c,w] = x[b,c,h,w];  32x32 smem tile transpose over (c,h) per (b,w) ---------
 __global__ void permute_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int H, int W) {
   __shared__ float tile[32][33];
@@ -126,7 +142,10 @@ extern "C" int cfpp_squeeze_fwd(const float* x, float* y, int B, int C, int H, i
   CFPP_REQUIRE(B >= 0 && C > 0 && p1 > 0 && p2 > 0 && H % p1 == 0 && W % p2 == 0, "squeeze: bad dims C=%d H=%d W=%d p=(%d,%d)", C, H, W, p1, p2);
   int64_t total = (int64_t)B * C * H * W;
   if (!total) return CFPP_OK;
-  squeeze_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, total, C, H, W, p1, p2, false);
+  if (p1 == 2 && p2 == 2 && W % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)
+    squeeze22_kernel<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(x, y, total / 8, H, W);
+  else
+    squeeze_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, total, C, H, W, p1, p2, false);
   return check_launch("squeeze_fwd");
 }
 extern "C" int cfpp_squeeze_inv(const float* y, float* x, int B, int C, int H, int W, int p1, int p2, void* stream) {

@@ -1,0 +1,84 @@
+"""CUDA-graph replay of the log-density forward.
+
+One `log_prob` is 150-200 kernel launches, most of them microseconds long; issued one by one from Python the launch
+overhead (ctypes call + torch allocation + driver launch, ~10-20 us each) exceeds the device time of the small kernels and
+the GPU idles between them.  `GraphedLogProb` captures the whole forward for a fixed input shape once (torch.cuda.CUDAGraph
+over the stream the C-ABI kernels are launched on) and replays it per batch: inputs are copied into the capture's static
+buffers (a pinned host tensor is copied host->device straight into them), one `cudaGraphLaunch` runs the step, the (B, M)
+log-probabilities are returned as a fresh tensor.  The RNG draws inside the path (torch.rand / torch.randn) are graph-safe:
+torch advances the Philox offset on every replay.
+
+Capture requirements met by the path: no host synchronisation inside a forward (ActNorm's one-time initialisation read happens
+in the eager warm-up), no host memory copies inside the library, every buffer allocated through torch's graph pool.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi
+
+
+class _Entry:
+    __slots__ = ('graph', 'x', 'ctx', 'out', 'launches', 'signature')
+
+
+class GraphedLogProb:
+    def __init__(self, model, warmup: int = 2):
+        self.model, self.warmup = model, max(1, warmup)
+        self._entries = {}
+        self._pool = None
+
+    def _signature(self):
+        """Changes whenever a parameter / buffer is written in place or replaced: the layers repack weights on the host side keyed on
+        these versions, so a captured graph is only valid for the signature it was captured under."""
+        sig = 0
+        for t in self.model.state_dict(keep_vars=True).values():
+            sig = (sig * 1000003 + t._version + (t.data_ptr() & 0xFFFFF)) & 0xFFFFFFFFFFFF
+        return sig
+
+    def _capture(self, x, ctx, device):
+        e = _Entry()
+        e.x = torch.empty(x.shape, device=device, dtype=x.dtype)
+        e.ctx = None if ctx is None else torch.empty(ctx.shape, device=device, dtype=ctx.dtype)
+        e.x.copy_(x)
+        if ctx is not None:
+            e.ctx.copy_(ctx)
+        cur = torch.cuda.current_stream(device)
+        side = torch.cuda.Stream(device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(self.warmup):                       # eager: ActNorm init, weight repacking, attribute setup
+                self.model.forward(e.x, e.ctx)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(device)
+        e.graph = torch.cuda.CUDAGraph()
+        l0 = _cabi.launch_count()
+        with torch.no_grad(), torch.cuda.graph(e.graph, pool=self._pool):
+            e.out = self.model.forward(e.x, e.ctx)[1]
+        e.launches = _cabi.launch_count() - l0
+        if self._pool is None:
+            self._pool = e.graph.pool()
+        e.signature = self._signature()
+        return e
+
+    def entry(self, x, ctx):
+        key = (tuple(x.shape), x.dtype, None if ctx is None else (tuple(ctx.shape), ctx.dtype))
+        e = self._entries.get(key)
+        if e is not None and e.signature != self._signature():    # weights changed since capture (training step, load_state_dict)
+            e = None
+        if e is None:
+            dev = x.device if x.is_cuda else torch.device('cuda', torch.cuda.current_device())
+            e = self._entries[key] = self._capture(x, ctx, dev)
+        return e
+
+    def launches_per_replay(self, x, ctx):
+        return self.entry(x, ctx).launches
+
+    def __call__(self, x, ctx=None, clone: bool = True):
+        """x / ctx may live on the device or in (pinned) host memory; returns the (B, M) log-probabilities."""
+        e = self.entry(x, ctx)
+        e.x.copy_(x, non_blocking=True)
+        if ctx is not None:
+            e.ctx.copy_(ctx, non_blocking=True)
+        e.graph.replay()
+        return e.out.clone() if clone else e.out

@@ -16,6 +16,10 @@ class FlowSequential(nn.Module):
         for i, module in enumerate(modules):
             self.add_module(str(i), module)
         self.sequence_modules = modules
+        import os
+        self._graphed = None
+        if os.environ.get('CFPP_CUDA_GRAPHS', '0') == '1':
+            self.enable_cuda_graphs()
 
     def __iter__(self):
         yield from self.sequence_modules
@@ -70,7 +74,20 @@ class FlowSequential(nn.Module):
         ops.ldj_accumulate(logprob, logdet)
         return out, logprob
 
+    def enable_cuda_graphs(self, flag: bool = True):
+        """Replay `log_prob` from a captured CUDA graph (one graph per input shape) whenever autograd is off: removes the per-launch
+        host overhead of the ~10^2 kernels of a forward.  Off by default; `python -m contextflow_b200.run` turns it on with
+        CFPP_CUDA_GRAPHS=1.  forward() (which also returns z) always runs eagerly."""
+        from ..graphed import GraphedLogProb
+        self._graphed = GraphedLogProb(self) if flag else None
+        return self
+
     def log_prob(self, input, context=None):
+        g = getattr(self, '_graphed', None)
+        if g is not None and input.is_cuda and not torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing():
+            from .. import rng
+            if rng._source is None:                            # replayed noise tapes (tests) are host-driven: stay eager
+                return g(input, context)
         return self.forward(input, context)[1]
 
     def sample(self, n_samples, context=None):
