@@ -32,6 +32,12 @@ class EncDesc(C.Structure):
                 ('cw1t', vp * 2), ('cb1', vp * 2), ('cw2t', vp * 2), ('cb2', vp * 2), ('cw3t', vp * 2), ('cb3', vp * 2)]
 
 
+class CnJob(C.Structure):
+    _fields_ = [('w', vp * 3), ('b', vp * 3), ('n_layers', i32), ('K', i32), ('N', i32 * 3), ('tril_dim', i32)]
+
+
+MAX_CN_JOBS = 64
+
 _SIGNATURES = {
     'cfpp_version': (i32, []),
     'cfpp_last_error': (C.c_char_p, []),
@@ -68,7 +74,9 @@ _SIGNATURES = {
     'cfpp_ctx_encode_batch': (i32, [vp, vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i32, vp]),
     'cfpp_embed_lookup': (i32, [vp, C.POINTER(vp), i32, i32, vp, i32, vp]),
     'cfpp_linear_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    'cfpp_cn_batch': (i32, [C.POINTER(CnJob), i32, C.POINTER(vp), C.POINTER(vp), i32, vp]),
     'cfpp_ldj_accumulate': (i32, [vp, vp, i32, i32, i32, vp]),
+    'cfpp_ldj_sum': (i32, [vp, vp, vp, C.POINTER(vp), C.POINTER(i32), i32, i32, i32, vp]),
 }
 
 _lib = None

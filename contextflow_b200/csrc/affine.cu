@@ -53,7 +53,7 @@ struct Conv1x1Args {
   const float* x; float* z; float* ldj; const float* NN; const float* logabsdet;
   const float* c; const float* logp_c; int contextflow;
   const float* an_t; const float* an_logs; int an_per_sample; const float* an_logp_c; float an_logp_scale;
-  int B, D, HW, NS, PT, CPS, NCOLP, G, IR, DR, tiles_per_sample;   // CPS = thread columns per sample tile (PT / PX), DR = D rounded up to 4
+  int B, D, HW, NS, PT, CPS, NCOLP, G, IR, DR, tiles_per_sample, an_stride;   // CPS = thread columns per sample tile (PT / PX), DR = D rounded up to 4
 };
 
 template <int PX> struct PixVec;
@@ -163,8 +163,8 @@ __global__ void __launch_bounds__(256) conv1x1_kernel(const Conv1x1Args a) {
     for (int idx = tid; idx < a.NS * D; idx += nthr) {
       const int mm = idx / D, i = idx - mm * D;
       const int64_t bb = min(b0 + mm, (int64_t)a.B - 1);
-      sh[mm * DR + i] = a.an_t[(a.an_per_sample ? bb * D : 0) + i];
-      sc[mm * DR + i] = expf(-a.an_logs[(a.an_per_sample ? bb * D : 0) + i]);
+      sh[mm * DR + i] = a.an_t[bb * a.an_stride + i];
+      sc[mm * DR + i] = expf(-a.an_logs[bb * a.an_stride + i]);
     }
   }
   // ---- per-sample ldj: one warp per sample (only the CTA of the sample's first pixel tile writes it) ----
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) conv1x1_kernel(const Conv1x1Args a) {
       const int64_t bb = b0 + ms;
       float part = 0.f, part_an = 0.f;
       if (a.c) for (int i = lane; i < D; i += 32) part += a.c[(bb * D + i) * (int64_t)D + i];
-      if (a.an_logs) for (int i = lane; i < D; i += 32) part_an += a.an_logs[(a.an_per_sample ? bb * D : 0) + i];
+      if (a.an_logs) for (int i = lane; i < D; i += 32) part_an += a.an_logs[bb * a.an_stride + i];
       part = warp_sum(part); part_an = warp_sum(part_an);
       if (lane == 0) {
         float l;
@@ -321,8 +321,10 @@ extern "C" int cfpp_conv1x1_fwd(const float* x, float* z, float* ldj, const floa
                                 int B, int D, int HW, void* stream) {
   CFPP_REQUIRE(D >= 1 && D <= 128 && HW >= 1, "conv1x1: D=%d HW=%d unsupported (D<=128)", D, HW);
   CFPP_REQUIRE((an_t == nullptr) == (an_logs == nullptr), "conv1x1: an_t and an_logs must be given together");
+  CFPP_REQUIRE(an_per_sample >= 0 && an_per_sample <= 2, "conv1x1: an_per_sample must be 0, 1 or 2");
   if (B <= 0) return CFPP_OK;
   Conv1x1Args a{x, z, ldj, NN, logabsdet, c, logp_c, contextflow, an_t, an_logs, an_per_sample, an_logp_c, an_logp_scale, B, D, HW};
+  a.an_stride = an_per_sample == 0 ? 0 : (an_per_sample == 1 ? D : 2 * D);
   const int DT = D <= 16 ? 16 : D <= 32 ? 32 : D <= 64 ? 64 : D <= 96 ? 96 : 128;
   const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(z)) & 15) == 0;
   int PX = DT == 16 ? 4 : DT == 32 ? 2 : 1;                 // DT * PX = 64 input registers per thread

@@ -1,0 +1,143 @@
+// The CN context networks of a whole forward in one launch (coupling.py:37,45; actnorm.py:21,44; conv1x1.py:22,32).
+// Every specialist layer maps its encoded context c (B, C_ctx <= 64) through a tiny MLP or a single nn.Linear; issued one
+// nn.Linear at a time that is 60 launches per forward (cfg2), each a few microseconds of work on a fraction of the SMs.  Here
+// blockIdx.y selects the job (one chain of 1..3 linear layers) and blockIdx.x a tile of 16 samples whose activations stay in
+// shared memory between the layers.  A thread owns one output column for a group of samples: the weight column streams
+// through registers once per group (coalesced along the output dimension, L1/L2 resident), the activations arrive as
+// warp-broadcast 128-bit shared loads (4 FMA per load).
+#include "common.cuh"
+#include <algorithm>
+
+namespace cfpp {
+
+constexpr int CN_SPB = 16;          // samples per CTA
+constexpr int CN_THREADS = 256;
+
+struct CnBatchArgs {
+  cfpp_cn_job job[CFPP_MAX_CN_JOBS];
+  const float* in[CFPP_MAX_CN_JOBS];
+  float* out[CFPP_MAX_CN_JOBS];
+  int stride;                       // shared-memory row stride in floats (multiple of 4, >= every staged width)
+};
+
+template <int SPG>
+__device__ __forceinline__ void cn_layer(const float* __restrict__ src, float* __restrict__ dst, int stride, float* __restrict__ gout,
+                                         const float* __restrict__ wt, const float* __restrict__ bias, int K, int N, bool last,
+                                         int tril, int nS, int s0, int col, int cols_per_pass) {
+  for (int n = col; n < N; n += cols_per_pass) {
+    if (last && tril > 0) { const int i = n / tril; if (n - i * tril > i) continue; }
+    float acc[SPG];
+#pragma unroll
+    for (int s = 0; s < SPG; ++s) acc[s] = 0.f;
+    const float* wcol = wt + n;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      float w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) w[q] = (k0 + q < K) ? __ldg(wcol + (int64_t)(k0 + q) * N) : 0.f;
+#pragma unroll
+      for (int s = 0; s < SPG; ++s) {
+        const float4 c = *reinterpret_cast<const float4*>(src + (s0 + s) * stride + k0);
+        acc[s] = fmaf(c.x, w[0], acc[s]); acc[s] = fmaf(c.y, w[1], acc[s]);
+        acc[s] = fmaf(c.z, w[2], acc[s]); acc[s] = fmaf(c.w, w[3], acc[s]);
+      }
+    }
+    const float bv = bias ? __ldg(bias + n) : 0.f;
+#pragma unroll
+    for (int s = 0; s < SPG; ++s) {
+      const float v = acc[s] + bv;
+      if (last) { if (s0 + s < nS) gout[(int64_t)(s0 + s) * N + n] = v; }
+      else dst[(s0 + s) * stride + n] = fmaxf(v, 0.f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CN_THREADS) cn_batch_kernel(const __grid_constant__ CnBatchArgs a, int B) {
+  extern __shared__ float4 cn_smem4[];
+  const int stride = a.stride;
+  float* buf0 = reinterpret_cast<float*>(cn_smem4);
+  float* buf1 = buf0 + CN_SPB * stride;
+  const cfpp_cn_job& J = a.job[blockIdx.y];
+  const int64_t b0 = (int64_t)blockIdx.x * CN_SPB;
+  const int nS = (int)min((int64_t)CN_SPB, (int64_t)B - b0);
+  const int tid = threadIdx.x;
+  {
+    const int K = J.K, K4 = (K + 3) & ~3;
+    const float* in = a.in[blockIdx.y] + b0 * K;
+    for (int idx = tid; idx < CN_SPB * K4; idx += CN_THREADS) {
+      const int s = idx / K4, k = idx - s * K4;
+      buf0[s * stride + k] = (s < nS && k < K) ? __ldg(in + s * K + k) : 0.f;
+    }
+  }
+  __syncthreads();
+  float* src = buf0; float* dst = buf1;
+  float* gout = a.out[blockIdx.y] + b0 * J.N[J.n_layers - 1];
+  for (int l = 0; l < J.n_layers; ++l) {
+    const int K = l ? J.N[l - 1] : J.K, N = J.N[l];
+    const bool last = l == J.n_layers - 1;
+    const int cpp = min(CN_THREADS, (N + 31) & ~31);
+    int groups = CN_THREADS / cpp;                       // 1, 2, 4 or 8 sample groups
+    groups = groups >= 8 ? 8 : groups >= 4 ? 4 : groups >= 2 ? 2 : 1;
+    const int g = tid / cpp, col = tid - g * cpp;
+    if (g < groups) {
+      const int spg = CN_SPB / groups;
+      switch (spg) {
+        case 16: cn_layer<16>(src, dst, stride, gout, J.w[l], J.b[l], K, N, last, J.tril_dim, nS, g * 16, col, cpp); break;
+        case 8:  cn_layer<8>(src, dst, stride, gout, J.w[l], J.b[l], K, N, last, J.tril_dim, nS, g * 8, col, cpp); break;
+        case 4:  cn_layer<4>(src, dst, stride, gout, J.w[l], J.b[l], K, N, last, J.tril_dim, nS, g * 4, col, cpp); break;
+        default: cn_layer<2>(src, dst, stride, gout, J.w[l], J.b[l], K, N, last, J.tril_dim, nS, g * 2, col, cpp); break;
+      }
+    }
+    if (!last) {                                         // zero the K-padding columns the next layer's 128-bit loads touch
+      const int N4 = (N + 3) & ~3;
+      if (N4 != N) for (int idx = tid; idx < CN_SPB * (N4 - N); idx += CN_THREADS) { const int s = idx / (N4 - N); dst[s * stride + N + idx % (N4 - N)] = 0.f; }
+      __syncthreads();
+      float* t = src; src = dst; dst = t;
+    }
+  }
+}
+
+}  // namespace cfpp
+using namespace cfpp;
+
+extern "C" int cfpp_cn_batch(const cfpp_cn_job* jobs, int n_jobs, const float* const* in, float* const* out, int B, void* stream) {
+  CFPP_REQUIRE(n_jobs >= 1 && n_jobs <= CFPP_MAX_CN_JOBS, "cn_batch: n_jobs=%d outside [1,%d]", n_jobs, CFPP_MAX_CN_JOBS);
+  CFPP_REQUIRE(jobs && in && out, "cn_batch: null argument");
+  int order[CFPP_MAX_CN_JOBS]; double cost[CFPP_MAX_CN_JOBS];
+  int width = 4;
+  for (int j = 0; j < n_jobs; ++j) {
+    const cfpp_cn_job& J = jobs[j];
+    CFPP_REQUIRE(J.n_layers >= 1 && J.n_layers <= 3, "cn_batch: job %d has %d layers (1..3)", j, J.n_layers);
+    CFPP_REQUIRE(J.K >= 1 && J.K <= CFPP_CN_MAX_WIDTH, "cn_batch: job %d K=%d outside [1,%d]", j, J.K, CFPP_CN_MAX_WIDTH);
+    width = std::max(width, J.K);
+    double c = 0; int K = J.K;
+    for (int l = 0; l < J.n_layers; ++l) {
+      CFPP_REQUIRE(J.N[l] >= 1 && J.w[l], "cn_batch: job %d layer %d: N=%d / null weight", j, l, J.N[l]);
+      if (l + 1 < J.n_layers) {
+        CFPP_REQUIRE(J.N[l] <= CFPP_CN_MAX_WIDTH, "cn_batch: job %d hidden width %d > %d", j, J.N[l], CFPP_CN_MAX_WIDTH);
+        width = std::max(width, J.N[l]);
+      }
+      c += (double)K * J.N[l]; K = J.N[l];
+    }
+    const int NL = J.N[J.n_layers - 1];
+    CFPP_REQUIRE(J.tril_dim == 0 || (J.tril_dim > 0 && (int64_t)J.tril_dim * J.tril_dim == NL), "cn_batch: job %d tril_dim=%d does not match N=%d", j, J.tril_dim, NL);
+    CFPP_REQUIRE(in[j] && out[j], "cn_batch: job %d null in/out", j);
+    order[j] = j; cost[j] = c;
+  }
+  if (B <= 0) return CFPP_OK;
+  std::stable_sort(order, order + n_jobs, [&](int x, int y) { return cost[x] > cost[y]; });   // heavy chains first: no tail
+  CnBatchArgs a;
+  for (int j = 0; j < n_jobs; ++j) { a.job[j] = jobs[order[j]]; a.in[j] = in[order[j]]; a.out[j] = out[order[j]]; }
+  a.stride = (width + 3) & ~3;
+  const size_t smem = 2ull * CN_SPB * a.stride * sizeof(float);
+  static size_t smem_set = 48 * 1024;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(cn_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("cn_batch: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return CFPP_ERR_CUDA; }
+    smem_set = smem;
+  }
+  const int64_t tiles = ((int64_t)B + CN_SPB - 1) / CN_SPB;
+  CFPP_REQUIRE(tiles <= 0x7fffffff, "cn_batch: batch too large");
+  dim3 grid((unsigned)tiles, n_jobs);
+  cn_batch_kernel<<<grid, CN_THREADS, smem, (cudaStream_t)stream>>>(a, B);
+  return check_launch("cn_batch");
+}

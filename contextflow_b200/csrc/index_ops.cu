@@ -205,6 +205,34 @@ __global__ void ldj_accumulate_kernel(float* __restrict__ logdet, const float* _
     logdet[i] += ldj[(i / M) * cols + (cols == 1 ? 0 : i % M)];
 }
 }  // namespace cfpp
+// The whole `logdet += ldj` chain of one forward in a single launch: out = [last +] (((first|0) + t_0) + t_1) + ... in that order,
+// i.e. bit-identical to accumulating the terms one launch at a time.
+namespace cfpp {
+struct LdjSumArgs { const float* term[CFPP_LDJ_SUM_MAX]; int cols[CFPP_LDJ_SUM_MAX]; int n; };
+__global__ void ldj_sum_kernel(float* __restrict__ out, const float* __restrict__ first, const float* __restrict__ last, const LdjSumArgs t,
+                               int64_t total, int M) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / M; const int m = (int)(i - b * M);
+    float acc = first ? first[i] : 0.f;
+    for (int k = 0; k < t.n; ++k) acc += t.term[k][t.cols[k] == 1 ? b : i];
+    out[i] = last ? last[i] + acc : acc;
+  }
+}
+}  // namespace cfpp
+extern "C" int cfpp_ldj_sum(float* out, const float* first, const float* last, const float* const* terms, const int* cols, int n,
+                            int B, int M, void* stream) {
+  CFPP_REQUIRE(n >= 0 && n <= CFPP_LDJ_SUM_MAX, "ldj_sum: %d terms (max %d per launch)", n, CFPP_LDJ_SUM_MAX);
+  cfpp::LdjSumArgs t; t.n = n;
+  for (int k = 0; k < n; ++k) {
+    CFPP_REQUIRE(cols[k] == 1 || cols[k] == M, "ldj_sum: term %d has %d columns, expected 1 or %d", k, cols[k], M);
+    t.term[k] = terms[k]; t.cols[k] = cols[k];
+  }
+  const int64_t total = (int64_t)B * M;
+  if (total <= 0) return CFPP_OK;
+  cfpp::ldj_sum_kernel<<<cfpp::grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(out, first, last, t, total, M);
+  return cfpp::check_launch("ldj_sum");
+}
+
 extern "C" int cfpp_ldj_accumulate(float* logdet, const float* ldj, int B, int M, int cols, void* stream) {
   CFPP_REQUIRE(cols == 1 || cols == M, "ldj_accumulate: ldj has %d columns, expected 1 or %d", cols, M);
   const int64_t total = (int64_t)B * M;

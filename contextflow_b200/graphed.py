@@ -48,13 +48,13 @@ class GraphedLogProb:
         side.wait_stream(cur)
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(self.warmup):                       # eager: ActNorm init, weight repacking, attribute setup
-                self.model.forward(e.x, e.ctx)
+                self.model.log_prob_eager(e.x, e.ctx)
         cur.wait_stream(side)
         torch.cuda.synchronize(device)
         e.graph = torch.cuda.CUDAGraph()
         l0 = _cabi.launch_count()
         with torch.no_grad(), torch.cuda.graph(e.graph, pool=self._pool):
-            e.out = self.model.forward(e.x, e.ctx)[1]
+            e.out = self.model.log_prob_eager(e.x, e.ctx)
         e.launches = _cabi.launch_count() - l0
         if self._pool is None:
             self._pool = e.graph.pool()

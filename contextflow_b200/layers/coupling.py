@@ -25,6 +25,10 @@ class _CouplingBase(FlowLayer):
     """Shared context plumbing: CN is Linear-ReLU-Linear-ReLU-Linear on the encoded context (coupling.py:37,121)."""
 
     def _context_terms(self, context):
+        pre = getattr(self, '_cn_preset', None)                 # (CN(c), logp_c) from the fused plan's context pre-pass
+        if pre is not None:
+            self._cn_preset = None
+            return pre
         c, logp_c = self._plan.run(self.context_net, context)
         lin = [self.CN[0], self.CN[2], self.CN[4]]
         packs = self._packs.get('cn', [l.weight for l in lin], lambda: [ops.pack_kmajor(l.weight, 1) for l in lin])

@@ -61,18 +61,18 @@ class FlowSequential(nn.Module):
 
     def forward(self, input, context=None):
         B = input.shape[0]
-        logdet = torch.zeros((B, self.mixtures), device=input.device, dtype=torch.float32)
         out = input
+        terms = []
         groups = self._encoder_groups() if context is not None else {}
         for i, module in enumerate(self.sequence_modules):
             batch = groups.get(i)
             if batch is not None and batch.ready():
                 batch.run(context)
             out, ldj = module(out, context)
-            ops.ldj_accumulate(logdet, ldj)                     # (B,), (B,1) broadcast or (B,M)   (flowsequential.py:23)
-        logprob = self.dist.log_prob(out, context)              # fresh (B, M) tensor: accumulate into it and return it
-        ops.ldj_accumulate(logprob, logdet)
-        return out, logprob
+            terms.append(ldj)                                   # (B,), (B,1) broadcast or (B,M)   (flowsequential.py:23)
+        logprob = self.dist.log_prob(out, context)
+        # logdet = ((0 + ldj_0) + ldj_1) + ...; logprob + logdet  (flowsequential.py:20-27), same order, one launch
+        return out, ops.ldj_sum(terms, B, self.mixtures, input.device, last=logprob)
 
     def enable_cuda_graphs(self, flag: bool = True):
         """Replay `log_prob` from a captured CUDA graph (one graph per input shape) whenever autograd is off: removes the per-launch
@@ -82,13 +82,26 @@ class FlowSequential(nn.Module):
         self._graphed = GraphedLogProb(self) if flag else None
         return self
 
+    def log_prob_eager(self, input, context=None):
+        """log_prob launched kernel by kernel: the fused plan (layers/_fastpath.py) when it applies, else layer by layer."""
+        import os
+        if os.environ.get('CFPP_FASTPATH', '1') != '0':
+            fp = getattr(self, '_fastpath', None)
+            if fp is None:
+                from ._fastpath import FastLogProb
+                fp = FastLogProb(self)
+                object.__setattr__(self, '_fastpath', fp)
+            if fp.usable(input, context):
+                return fp(input, context)
+        return self.forward(input, context)[1]
+
     def log_prob(self, input, context=None):
         g = getattr(self, '_graphed', None)
         if g is not None and input.is_cuda and not torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing():
             from .. import rng
             if rng._source is None:                            # replayed noise tapes (tests) are host-driven: stay eager
                 return g(input, context)
-        return self.forward(input, context)[1]
+        return self.log_prob_eager(input, context)
 
     def sample(self, n_samples, context=None):
         raise NotImplementedError('sampling / inverse path is outside this round (SURVEY §8f-3)')

@@ -44,10 +44,13 @@ class Normalization(PreprocessingFlowLayer):
         s, t, _ = self.host_constants()
         return ops.normalize(input, 1.0 / s, -t * s)                 # (x - t) * s
 
+    def logdet_value(self, C, D):
+        """The per-sample ldj as a python float: float32 arithmetic in the reference's order, C * (-1 * D * log(scale))
+        (normalize.py:42-47)."""
+        _, _, logs = self.host_constants()
+        return float(torch.tensor(C, dtype=torch.float32) * (torch.tensor(-1 * D, dtype=torch.float32) * torch.tensor(logs, dtype=torch.float32)))
+
     def logdet(self, input, context=None):
         B, C = input.shape[:2]
         D = input.numel() / B / C
-        _, _, logs = self.host_constants()
-        # float32 arithmetic in the reference's order: C * (-1 * D * log(scale))   (normalize.py:42-47)
-        val = float(torch.tensor(C, dtype=torch.float32) * (torch.tensor(-1 * D, dtype=torch.float32) * torch.tensor(logs, dtype=torch.float32)))
-        return torch.full((B,), val, device=input.device, dtype=torch.float32)
+        return torch.full((B,), self.logdet_value(C, D), device=input.device, dtype=torch.float32)

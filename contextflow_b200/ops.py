@@ -190,7 +190,10 @@ def conv1x1(x, NN, logabsdet, c=None, logp_c=None, contextflow=False, an_t=None,
     B, D = x.shape[0], x.shape[1]
     HW = x[0, 0].numel() if B else 1
     z = torch.empty_like(x); ldj = torch.empty(B, device=x.device, dtype=x.dtype)
-    per_sample = int(an_t is not None and an_t.dim() == 2)
+    if an_t is not None and an_logs is None:                      # one (B, 2D) 'b (p d)' matrix: [t | logs] per sample
+        per_sample, an_logs = 2, an_t[:, D:]
+    else:
+        per_sample = int(an_t is not None and an_t.dim() == 2)
     _set_work(bytes=8.0 * x.numel() + (0 if c is None else 4.0 * c.numel()), flops=2.0 * D * x.numel())
     _call('conv1x1_fwd', (_p(x), _p(z), _p(ldj), _p(_f32(NN)), _p(logabsdet), _p(None if c is None else _f32(c)),
                                  _p(logp_c), int(bool(contextflow)), _p(an_t), _p(an_logs), per_sample, _p(an_logp_c),
@@ -393,9 +396,62 @@ def linear(x, wt, b=None, relu=False, n_out=None):
     return y if n_out is None or n_out == N else y[:, :n_out]
 
 
+def cn_job(layers, tril_dim=0):
+    """Descriptor of one CN chain: layers = [(wt K-major (K, N), bias (N) or None), ...] (1..3 entries, ReLU between).
+    Returns (CnJob, keep-alive list)."""
+    j = _cabi.CnJob()
+    j.n_layers, j.K, j.tril_dim = len(layers), layers[0][0].shape[0], tril_dim
+    keep = []
+    for l, (wt, b) in enumerate(layers):
+        wt = _f32(wt); keep.append(wt)
+        j.w[l], j.N[l] = vp(wt.data_ptr()), wt.shape[1]
+        if b is not None:
+            b = _f32(b); keep.append(b); j.b[l] = vp(b.data_ptr())
+    return j, keep
+
+
+def cn_batch(jobs, ins):
+    """All CN context networks of a forward in one launch: jobs[i] (cn_job descriptors) applied to ins[i] (B, K_i)."""
+    _need_cuda(*ins)
+    n, B = len(jobs), ins[0].shape[0]
+    widths = [int(j.N[j.n_layers - 1]) for j in jobs]
+    flat = torch.empty(B * sum(widths), device=ins[0].device, dtype=torch.float32)
+    outs, off = [], 0
+    for w in widths:
+        outs.append(flat[off: off + B * w].view(B, w)); off += B * w
+    ins = [_f32(t) for t in ins]
+    for i0 in range(0, n, _cabi.MAX_CN_JOBS):
+        m = min(_cabi.MAX_CN_JOBS, n - i0)
+        jarr = (_cabi.CnJob * m)(*jobs[i0: i0 + m])
+        iarr = (vp * m)(*[vp(t.data_ptr()) for t in ins[i0: i0 + m]])
+        oarr = (vp * m)(*[vp(t.data_ptr()) for t in outs[i0: i0 + m]])
+        _call('cn_batch', (jarr, m, iarr, oarr, B, _stream()))
+    return outs
+
+
 def ldj_accumulate(logdet, ldj):
     _need_cuda(logdet, ldj)
     B, M = logdet.shape
     cols = 1 if ldj.dim() == 1 else ldj.shape[1]
     _call('ldj_accumulate', (_p(logdet), _p(_f32(ldj)), B, M, cols, _stream()), 'ldj_accumulate')
     return logdet
+
+
+LDJ_SUM_MAX = 64
+
+
+def ldj_sum(terms, B, M, device, last=None):
+    """logdet (B,M) = ((0 + t_0) + t_1) + ... [then last + logdet], in order, one launch per 64 terms."""
+    _need_cuda(*terms)
+    out = torch.empty((B, M), device=device, dtype=torch.float32)
+    terms = [_f32(t) for t in terms]
+    first = None
+    for k0 in range(0, max(len(terms), 1), LDJ_SUM_MAX):
+        chunk = terms[k0: k0 + LDJ_SUM_MAX]
+        n = len(chunk)
+        final = k0 + LDJ_SUM_MAX >= len(terms)
+        parr = (vp * max(n, 1))(*[vp(t.data_ptr()) for t in chunk])
+        carr = (_cabi.i32 * max(n, 1))(*[1 if t.dim() == 1 else t.shape[1] for t in chunk])
+        _call('ldj_sum', (_p(out), _p(first), _p(last if final else None), parr, carr, n, B, M, _stream()))
+        first = out
+    return out

@@ -63,7 +63,8 @@ int cfpp_slogdet(const float* A, int D, float* logabsdet, void* stream);
  *   c == NULL : z = NN x per pixel; ldj[b] = HW * logabsdet.
  *   c != NULL : c is the raw CN output (B,D,D); W_b = tril(c,-1) + diag(exp(diag c)) [- I + NN if contextflow];
  *               ldj[b] = HW * ((contextflow ? logabsdet : 0) + sum diag c_b) + HW * logp_c[b].
- * Optional fused ActNorm epilogue (t, logs non-NULL, per-sample (B,D) when an_per_sample else (D)):
+ * Optional fused ActNorm epilogue (t, logs non-NULL; an_per_sample 0: shared (D) vectors; 1: per-sample (B,D) arrays;
+ * 2: one (B,2D) array 'b (p d)' as ActNorm.CN produces it -- an_t points at it and an_logs = an_t + D):
  *   z = (z - t) * exp(-logs); ldj[b] += sum_d logs (+ an_logp_scale * an_logp_c[b]).   (layers/actnorm.py:37-60) */
 int cfpp_conv1x1_fwd(const float* x, float* z, float* ldj, const float* NN, const float* logabsdet,
                      const float* c, const float* logp_c, int contextflow,
@@ -203,11 +204,34 @@ int cfpp_ctx_encode_batch(const int64_t* ctx, const cfpp_enc_desc* descs_device,
 int cfpp_embed_lookup(const int64_t* ctx, const float* const* tables, int n_ctx, int width, float* out, int B, void* stream);
 /* y (B,N) = act(x (B,K) @ wt (K,N) + b): the CN context networks (nn.Linear; coupling.py:37, actnorm.py:21, conv1x1.py:22). */
 int cfpp_linear_fwd(const float* x, const float* wt, const float* b, float* y, int B, int K, int N, int relu, void* stream);
+/* Every CN context network of a forward in ONE launch (coupling.py:37,45: Linear-ReLU-Linear-ReLU-Linear on the encoded context;
+ * actnorm.py:21,44: Linear(C, 2D); conv1x1.py:22,32: Linear(C, D*D)).  Job j maps in[j] (B, K) through its chain of 1..3 linear
+ * layers (ReLU between layers, none after the last) into out[j] (B, N[n_layers-1]).  Weights are K-major (K_l, N_l), K_0 = K,
+ * K_l = N[l-1].  tril_dim = D > 0 declares the last layer's output a row-major (D, D) matrix of which the consumer reads only the
+ * lower triangle and the diagonal (Conv1x1: tril(c,-1) + diag(exp(diag c)), conv1x1.py:36-40): the strictly upper entries are
+ * neither computed nor written.  `jobs`, `in`, `out` are HOST arrays (n_jobs entries) of device pointers. */
+#define CFPP_MAX_CN_JOBS 64
+#define CFPP_CN_MAX_WIDTH 1024      /* K and hidden widths (everything staged in shared memory); the last N is unbounded */
+typedef struct cfpp_cn_job {
+  const float* w[3];
+  const float* b[3];                /* (N_l) or NULL */
+  int n_layers, K;
+  int N[3];
+  int tril_dim;
+} cfpp_cn_job;
+int cfpp_cn_batch(const cfpp_cn_job* jobs, int n_jobs, const float* const* in, float* const* out, int B, void* stream);
 
 
 /* ---- container ------------------------------------------------------------------------------------------------ */
 /* FlowSequential.forward, layers/flowsequential.py:23: logdet (B,M) += ldj (B,cols) with cols = 1 (broadcast) or M. */
 int cfpp_ldj_accumulate(float* logdet, const float* ldj, int B, int M, int cols, void* stream);
+/* The same accumulation for up to CFPP_LDJ_SUM_MAX terms in one launch, in the same order (bit-identical to the chain of
+ * cfpp_ldj_accumulate calls): out (B,M) = [last +] (((first | 0) + terms[0]) + terms[1]) + ...; terms[k] is (B,cols[k]),
+ * cols[k] in {1, M}; first / last optional (B,M) (flowsequential.py:20-27: logdet = 0 + sum ldj; logprob + logdet).
+ * terms / cols: HOST arrays. */
+#define CFPP_LDJ_SUM_MAX 64
+int cfpp_ldj_sum(float* out, const float* first, const float* last, const float* const* terms, const int* cols, int n,
+                 int B, int M, void* stream);
 
 #ifdef __cplusplus
 }

@@ -157,3 +157,52 @@ def test_linear_and_ldj_accumulate():
     ld = torch.zeros(5, 3, device=dev)
     ops.ldj_accumulate(ld, torch.arange(5., device=dev)); ops.ldj_accumulate(ld, torch.ones(5, 1, device=dev)); ops.ldj_accumulate(ld, torch.ones(5, 3, device=dev))
     assert torch.equal(ld.cpu(), (torch.arange(5.)[:, None] + 2).expand(5, 3))
+
+
+@pytest.mark.parametrize('B', [1, 16, 45])
+def test_cn_batch_matches_linear_chain(B):
+    """cfpp_cn_batch: heterogeneous chains (3-layer ReLU MLP, single Linear, Linear into a lower-triangular D x D matrix) in one
+    launch, against fp64 torch on the CPU."""
+    specs = [dict(K=20, N=[32, 32, 16], tril=0), dict(K=20, N=[32], tril=0), dict(K=20, N=[64 * 64], tril=64), dict(K=8, N=[152, 152, 76], tril=0),
+             dict(K=7, N=[9], tril=3), dict(K=20, N=[256, 256, 128], tril=0), dict(K=5, N=[5 * 5], tril=5)]
+    jobs, ins, keep, want = [], [], [], []
+    for i, s in enumerate(specs):
+        x = synth.uniform(f'cnx{i}', (B, s['K'])) * 2 - 1
+        layers, h, K = [], x.double(), s['K']
+        for l, N in enumerate(s['N']):
+            w = (synth.uniform(f'cnw{i}{l}', (N, K)) * 2 - 1) / math.sqrt(K)
+            b = synth.uniform(f'cnb{i}{l}', (N,)) - 0.5 if (i + l) % 3 else None
+            layers.append((ops.pack_kmajor(w.to(dev), 1), None if b is None else b.to(dev)))
+            h = h @ w.double().t() + (0 if b is None else b.double())
+            if l + 1 < len(s['N']):
+                h = torch.relu(h)
+            K = N
+        j, k = ops.cn_job(layers, s['tril'])
+        jobs.append(j); keep.append(k); ins.append(x.to(dev)); want.append(h)
+    outs = ops.cn_batch(jobs, ins)
+    torch.cuda.synchronize()
+    for s, o, w in zip(specs, outs, want):
+        o = o.cpu().double()
+        if s['tril']:
+            D = s['tril']
+            mask = torch.tril(torch.ones(D, D, dtype=torch.bool)).reshape(-1)
+            o, w = o[:, mask], w[:, mask]
+        assert_close(o.numpy(), w.numpy(), 1e-5, 1e-5, f'cn_batch {s}')
+
+
+def test_ldj_sum_is_the_ordered_chain():
+    B, M = 13, 10
+    terms = [synth.uniform('ls0', (B,)) * 100, synth.uniform('ls1', (B, 1)) * 1e-3, synth.uniform('ls2', (B, M)), synth.uniform('ls3', (B,)) * 7]
+    last = synth.uniform('ls4', (B, M)) * 1000
+    want = torch.zeros(B, M)
+    for t in terms:
+        want += t if t.dim() == 2 else t.unsqueeze(-1)
+    want = last + want
+    got = ops.ldj_sum([t.to(dev) for t in terms], B, M, dev, last=last.to(dev))
+    assert torch.equal(got.cpu(), want)                          # same order of fp32 additions: bit identical
+    many = [synth.uniform(f'lm{i}', (B,)) for i in range(150)]   # more than one launch worth of terms
+    want = torch.zeros(B, M)
+    for t in many:
+        want += t.unsqueeze(-1)
+    assert torch.equal(ops.ldj_sum([t.to(dev) for t in many], B, M, dev).cpu(), want)
+    assert torch.equal(ops.ldj_sum([], B, M, dev).cpu(), torch.zeros(B, M))
