@@ -120,7 +120,15 @@ __global__ void __launch_bounds__(256) conv1x1_kernel(const Conv1x1Args a) {
     for (int u0 = tid; u0 < units; u0 += 4 * nthr) {
       float4 cv[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const int u = u0 + k * nthr; if (u < units) cv[k] = ldg_stream(c4 + u); }
+      for (int k = 0; k < 4; ++k) {                // entries strictly above the diagonal are never used (and never produced by cfpp_cn_batch)
+        const int u = u0 + k * nthr;
+        if (u < units) {
+          int row, j0, i;
+          if (D == DT) { row = u / (DT / 4); j0 = (u % (DT / 4)) << 2; i = row % DT; }
+          else { row = u / D4; j0 = (u - row * D4) << 2; i = row - (row / D) * D; }
+          cv[k] = (j0 > i) ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg_stream(c4 + u);
+        }
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int u = u0 + k * nthr;
@@ -152,7 +160,7 @@ __global__ void __launch_bounds__(256) conv1x1_kernel(const Conv1x1Args a) {
       const float* nrow = a.NN + (size_t)i * D;
       const float* crow = a.c + ((b0 + mm) * D + i) * (int64_t)D;
       for (int j = lane; j < D; j += 32) {
-        const float cij = crow[j];
+        const float cij = j <= i ? crow[j] : 0.f;
         float v = (j < i) ? cij : (j == i ? expf(cij) : 0.f);
         if (a.contextflow) v = (v - (i == j ? 1.f : 0.f)) + nrow[j];
         wrow[j] = v;

@@ -24,8 +24,16 @@ template <int SPG>
 __device__ __forceinline__ void cn_layer(const float* __restrict__ src, float* __restrict__ dst, int stride, float* __restrict__ gout,
                                          const float* __restrict__ wt, const float* __restrict__ bias, int K, int N, bool last,
                                          int tril, int nS, int s0, int col, int cols_per_pass) {
-  for (int n = col; n < N; n += cols_per_pass) {
-    if (last && tril > 0) { const int i = n / tril; if (n - i * tril > i) continue; }
+  const bool tri = last && tril > 0;                       // enumerate only the lower triangle + diagonal: D (D + 1) / 2 columns
+  const int ncols = tri ? tril * (tril + 1) / 2 : N;
+  for (int t = col; t < ncols; t += cols_per_pass) {
+    int n = t;
+    if (tri) {
+      int i = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+      while (i * (i + 1) / 2 > t) --i;
+      while ((i + 1) * (i + 2) / 2 <= t) ++i;
+      n = i * tril + (t - i * (i + 1) / 2);
+    }
     float acc[SPG];
 #pragma unroll
     for (int s = 0; s < SPG; ++s) acc[s] = 0.f;
@@ -51,7 +59,7 @@ __device__ __forceinline__ void cn_layer(const float* __restrict__ src, float* _
   }
 }
 
-__global__ void __launch_bounds__(CN_THREADS) cn_batch_kernel(const __grid_constant__ CnBatchArgs a, int B) {
+__global__ void __launch_bounds__(CN_THREADS, 4) cn_batch_kernel(const __grid_constant__ CnBatchArgs a, int B) {
   extern __shared__ float4 cn_smem4[];
   const int stride = a.stride;
   float* buf0 = reinterpret_cast<float*>(cn_smem4);
@@ -74,7 +82,8 @@ __global__ void __launch_bounds__(CN_THREADS) cn_batch_kernel(const __grid_const
   for (int l = 0; l < J.n_layers; ++l) {
     const int K = l ? J.N[l - 1] : J.K, N = J.N[l];
     const bool last = l == J.n_layers - 1;
-    const int cpp = min(CN_THREADS, (N + 31) & ~31);
+    const int ncols = (last && J.tril_dim > 0) ? J.tril_dim * (J.tril_dim + 1) / 2 : N;
+    const int cpp = min(CN_THREADS, (ncols + 31) & ~31);
     int groups = CN_THREADS / cpp;                       // 1, 2, 4 or 8 sample groups
     groups = groups >= 8 ? 8 : groups >= 4 ? 4 : groups >= 2 ? 2 : 1;
     const int g = tid / cpp, col = tid - g * cpp;

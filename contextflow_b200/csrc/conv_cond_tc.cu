@@ -1,5 +1,6 @@
-// Conv-coupling conditioner (layers/coupling.py:26-29) on the 5th-generation tensor cores: tcgen05.mma kind::tf32 with
-// fp32-faithful 3xTF32 operand splitting, accumulators in TMEM, weights streamed by 1-D bulk TMA copies.
+// Conv-coupling conditioner (layers/coupling.py:26-29) on the 5th-generation tensor cores: tcgen05.mma with fp32-faithful
+// two-term operand splitting (kind::f16 with scaled fp16 hi/lo pairs by default, kind::tf32 hi/lo as the alternative),
+// accumulators in TMEM, weights streamed by 1-D bulk TMA copies.
 //
 //   h = W3 * relu( conv_KHxKW_reflect( relu(W1 * x0 + b1) ) + b2 ) + b3          per pixel, per sample
 //
@@ -13,9 +14,15 @@
 //   segment : (W % 8 == 0) the image row is cut into segments of 8 output pixels stored with their halo as GS = 8+KW-1
 //             rows; stored row = ((yp*S + s)*NSEG + seg)*GS + xs.  An MMA row-group of 8 is one segment and the descriptor's
 //             group stride (SBO) is GS*128 bytes, so every accumulator row is a real pixel (no waste on M).
-// fp32 accuracy from tf32 MMAs:  A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi.  The first two products are ONE instruction
+// Operand kinds.  F16 (default): hi = fp16_rn(v), lo' = fp16_rn((v - hi) * 2^11): two 11-bit significands = 22+ bits of v, the
+// 2^11 scale keeps lo' a normal fp16 number; a 128-byte row holds 64 channels, K = 16 per instruction, and the accumulator
+// columns that collect the two cross products are scaled back by 2^-11 in the epilogue.  Values beyond +-65504 (never seen in
+// ActNorm-normalised flows) saturate; CFPP_TC_KIND=tf32 selects the tf32 pair (hi = trunc_tf32(v), lo = v - hi; 32 channels per
+// row, K = 8, twice the shared-memory bytes and MMA time) which has fp32 range.
+// fp32 accuracy from two-term operands:  A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi.  The first two products are ONE instruction
 // with the stacked operand [B_hi ; B_lo] (N' = 2N, accumulator columns [0,N) and [N,2N)); the third accumulates into
-// [0,N); the epilogue adds the two column blocks.  (tools/umma_probe*.cu measured the descriptor conventions, the
+// [N,2N) as well, so that block holds both cross products (both carry the 2^11 scale of the fp16 kind); the epilogue adds
+// the (rescaled) second block to the first.  (tools/umma_probe*.cu measured the descriptor conventions, the
 // 2^-21-grade accuracy of the split and the issue rates this layout is built on.)
 //
 // Roles (448 threads, one persistent CTA per SM): warps 0-11 = epilogue (TMEM -> bias/ReLU/split -> shared, final store
@@ -23,6 +30,8 @@
 // through an mbarrier ring + next tile's x0 prefetch).  Per tile: stage 1 (1x1) -> epilogue 1 -> stage 2 (kxk, the
 // 94 %) -> epilogue 2 -> stage 3 (1x1) -> epilogue 3.
 #include <stdlib.h>
+#include <string.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace cfpp {
@@ -30,6 +39,7 @@ namespace tc {
 
 struct Plan {
   int B, Cin, Ch, Cout, H, W, KH, KW;
+  int kind;                          // 0 = tf32 pair (32 channels / row, K = 8), 1 = scaled fp16 pair (64 channels / row, K = 16)
   int seg, S, NSEG, GS, YS, RPS, WP, HP;
   int R, T1, T2, NG;                 // stored rows per tile, M-tiles of stage 1 / stages 2-3, row groups of stage 2 (segment)
   int P, KS1, N2, N3;                // channel panels, k-steps of stage 1, N of stages 1-2, N of stage 3 (padded to 16)
@@ -49,6 +59,34 @@ constexpr int kMaxStages = 8;
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t sw128(int row, int k) { return row * 128 + ((((k >> 2) ^ row) & 7) << 4) + ((k & 3) << 2); }
 __device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
+// (hi, lo') fp16 pair of two values, packed as two half2 words: hi = rn(v) saturated to the finite range, lo' = rn((v - hi) * 2^11)
+__device__ __forceinline__ void f16_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((a - hf.x) * kLoScale, (b - hf.y) * kLoScale);
+  hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// Store 8 consecutive channels (col8 = first channel within the panel, multiple of 8) of operand row `row` as (hi, lo) operands.
+template <bool F16>
+__device__ __forceinline__ void store_group8(uint8_t* ph, uint8_t* pl, int row, int col8, const float (&v)[8]) {
+  if (F16) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f16_split2(v[2 * q], v[2 * q + 1], h[q], l[q]);
+    const uint32_t off = row * 128 + ((((col8 >> 3) ^ row) & 7) << 4);
+    *reinterpret_cast<uint4*>(ph + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(pl + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t off = sw128(row, col8 + 4 * q);
+      *reinterpret_cast<float4*>(ph + off) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      *reinterpret_cast<float4*>(pl + off) = make_float4(tf32_lo(v[4 * q]), tf32_lo(v[4 * q + 1]), tf32_lo(v[4 * q + 2]), tf32_lo(v[4 * q + 3]));
+    }
+  }
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
@@ -65,16 +103,21 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
-               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+template <bool F16>
+__device__ __forceinline__ void mma_k(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (F16)
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 // K-major SWIZZLE_128B shared-memory matrix descriptor; sbo = byte stride between 8-row groups.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-__host__ __device__ constexpr uint32_t make_idesc(int n) {   // kind::tf32, fp32 accumulate, A and B K-major, M = 128
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool f16) {   // fp32 accumulate, A and B K-major, M = 128; operand format 0 = F16, 2 = TF32
+  return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -134,23 +177,31 @@ __device__ __forceinline__ bool decode_out(const Plan& p, int m, int& s, int& y,
 // One epilogue item: 32 accumulator columns [c0, c0+32) (16 when only 16 remain) of one row, two column blocks of N each ->
 // + bias -> ReLU -> (v, lo) -> operand row `row`.  All four TMEM loads are in flight before the single wait.  All 32 lanes
 // must call (tcgen05.ld is warp-collective); `write` only guards the stores.
+template <bool F16>
 __device__ __forceinline__ void store_split16(const float (&v)[16], const float (&u)[16], const float* __restrict__ bias, uint8_t* ph, uint8_t* pl,
                                               int row, int col) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
-    float4 hi, lo;
-    hi.x = fmaxf(v[4 * q + 0] + u[4 * q + 0] + b.x, 0.f); lo.x = tf32_lo(hi.x);
-    hi.y = fmaxf(v[4 * q + 1] + u[4 * q + 1] + b.y, 0.f); lo.y = tf32_lo(hi.y);
-    hi.z = fmaxf(v[4 * q + 2] + u[4 * q + 2] + b.z, 0.f); lo.z = tf32_lo(hi.z);
-    hi.w = fmaxf(v[4 * q + 3] + u[4 * q + 3] + b.w, 0.f); lo.w = tf32_lo(hi.w);
-    const uint32_t off = sw128(row, col + 4 * q);
-    *reinterpret_cast<float4*>(ph + off) = hi;
-    *reinterpret_cast<float4*>(pl + off) = lo;
+  for (int g = 0; g < 2; ++g) {
+    float o[8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + 8 * g + 4 * q);
+      const int i = 8 * g + 4 * q;
+      if (F16) {
+        o[4 * q + 0] = fmaxf(fmaf(u[i + 0], kLoInv, v[i + 0]) + b.x, 0.f); o[4 * q + 1] = fmaxf(fmaf(u[i + 1], kLoInv, v[i + 1]) + b.y, 0.f);
+        o[4 * q + 2] = fmaxf(fmaf(u[i + 2], kLoInv, v[i + 2]) + b.z, 0.f); o[4 * q + 3] = fmaxf(fmaf(u[i + 3], kLoInv, v[i + 3]) + b.w, 0.f);
+      } else {
+        o[4 * q + 0] = fmaxf(v[i + 0] + u[i + 0] + b.x, 0.f); o[4 * q + 1] = fmaxf(v[i + 1] + u[i + 1] + b.y, 0.f);
+        o[4 * q + 2] = fmaxf(v[i + 2] + u[i + 2] + b.z, 0.f); o[4 * q + 3] = fmaxf(v[i + 3] + u[i + 3] + b.w, 0.f);
+      }
+    }
+    store_group8<F16>(ph, pl, row, col + 8 * g, o);
   }
 }
+template <bool F16>
 __device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, int c0, const float* __restrict__ bias, uint8_t* a_hi, uint8_t* a_lo,
                                                     int region_bytes, int row, bool write) {
+  constexpr int CPR = F16 ? 64 : 32;                          // channels per 128-byte operand row
   float v0[16], u0[16], v1[16], u1[16];
   const bool two = c0 + 16 < N;                               // warp-uniform
   tmem_ld16(taddr + c0, v0);
@@ -158,15 +209,16 @@ __device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, int c
   if (two) { tmem_ld16(taddr + c0 + 16, v1); tmem_ld16(taddr + N + c0 + 16, u1); }
   tmem_ld_wait();
   if (write) {
-    uint8_t* ph = a_hi + (c0 >> 5) * region_bytes;
-    uint8_t* pl = a_lo + (c0 >> 5) * region_bytes;
-    store_split16(v0, u0, bias + c0, ph, pl, row, c0 & 31);
-    if (two) store_split16(v1, u1, bias + c0 + 16, ph, pl, row, (c0 & 31) + 16);
+    uint8_t* ph = a_hi + (c0 / CPR) * region_bytes;
+    uint8_t* pl = a_lo + (c0 / CPR) * region_bytes;
+    store_split16<F16>(v0, u0, bias + c0, ph, pl, row, c0 % CPR);
+    if (two) store_split16<F16>(v1, u1, bias + c0 + 16, ph, pl, row, (c0 % CPR) + 16);
   }
 }
 
-template <bool SEG, bool PROF>
+template <bool SEG, bool PROF, bool F16>
 __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p, const Args a) {
+  constexpr int CPR = F16 ? 64 : 32, KE = F16 ? 16 : 8;     // channels per operand row (panel), channels per MMA k-step
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_hi = base;                                     // [P][region]
@@ -243,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
     // cycle of gap beyond ~100 is lost, tools/umma_probe3.cu).  Hence: loop-invariant descriptors are hoisted, the ring
     // position advances by adds, and the wait for the NEXT chunk sits in the middle of the current chunk's instructions.
     if (elect_one()) {
-      const uint32_t idN2 = make_idesc(p.N2), id2N2 = make_idesc(2 * p.N2), idN3 = make_idesc(p.N3), id2N3 = make_idesc(2 * p.N3);
+      const uint32_t idN2 = make_idesc(p.N2, F16), id2N2 = make_idesc(2 * p.N2, F16), idN3 = make_idesc(p.N3, F16), id2N3 = make_idesc(2 * p.N3, F16);
       const uint32_t sbo2 = (uint32_t)p.GS * 128;
       const uint32_t tile_cols2 = 2 * p.N2, tile_cols3 = 2 * p.N3;
       const uint64_t ahi_lin = make_desc(smem_u32(a_hi), 1024), alo_lin = make_desc(smem_u32(a_lo), 1024);   // stages 1 / 3: plain 128-row tiles
@@ -252,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
       const uint32_t stage_u = (uint32_t)p.stage_bytes >> 4, region_u = (uint32_t)p.region_bytes >> 4;        // descriptor address units (16 B)
       const uint32_t tile_u2 = sbo2, ys_u = (uint32_t)p.YS * 8;                                                 // 16 groups * sbo2 / 16; image-row stride
       const int nst = p.nstages, P = p.P, T1 = p.T1, T2 = p.T2, KH = p.KH, KW = p.KW, KS1 = p.KS1;
-      const int ks_last = (p.Ch - (P - 1) * 32) >> 3;
+      const int ks_last = (p.Ch - (P - 1) * CPR) / KE;
       uint32_t st = 0, rphase = 0;                               // ring slot being consumed (persists across tiles)
       const bool prof = PROF && a.prof != nullptr && blockIdx.x == 0;
       long long tp = prof ? clock64() : 0, acc8 = 0, acc9 = 0, acc10 = 0;
@@ -276,17 +328,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
         uint32_t d = tmem;
         for (int t = 0; t < T; ++t) {
           if (t == T - 1 && T > 1) wait_next(has_next);
+          const uint32_t dl = d + (dcols >> 1);              // the (scaled) cross products collect in the second column block [N, 2N)
           if (ksn == 4) {
-            mma_tf32(d, ah, bd, id2, first_acc);     mma_tf32(d, al, bd, id1, 1);
-            mma_tf32(d, ah + 2, bd + 2, id2, 1);     mma_tf32(d, al + 2, bd + 2, id1, 1);
+            mma_k<F16>(d, ah, bd, id2, first_acc);     mma_k<F16>(dl, al, bd, id1, 1);
+            mma_k<F16>(d, ah + 2, bd + 2, id2, 1);     mma_k<F16>(dl, al + 2, bd + 2, id1, 1);
             if (T == 1) wait_next(has_next);
-            mma_tf32(d, ah + 4, bd + 4, id2, 1);     mma_tf32(d, al + 4, bd + 4, id1, 1);
-            mma_tf32(d, ah + 6, bd + 6, id2, 1);     mma_tf32(d, al + 6, bd + 6, id1, 1);
+            mma_k<F16>(d, ah + 4, bd + 4, id2, 1);     mma_k<F16>(dl, al + 4, bd + 4, id1, 1);
+            mma_k<F16>(d, ah + 6, bd + 6, id2, 1);     mma_k<F16>(dl, al + 6, bd + 6, id1, 1);
           } else {
             if (T == 1) wait_next(has_next);
             for (int ks = 0; ks < ksn; ++ks) {
-              mma_tf32(d, ah + 2 * ks, bd + 2 * ks, id2, ks > 0 ? 1u : first_acc);
-              mma_tf32(d, al + 2 * ks, bd + 2 * ks, id1, 1);
+              mma_k<F16>(d, ah + 2 * ks, bd + 2 * ks, id2, ks > 0 ? 1u : first_acc);
+              mma_k<F16>(dl, al + 2 * ks, bd + 2 * ks, id1, 1);
             }
           }
           ah += tile_u; al += tile_u; d += dcols;
@@ -343,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
     const int quad = warp & 3, grp = warp >> 2;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const int row_in_tile = quad * 32 + lane;
-    const int kc1 = p.KS1 * 2;                                // 16-byte chunks of x0 per stored row
+    const int ng1 = p.KS1 * KE / 8;                           // groups of 8 channels of x0 per stored row (K zero-padded to whole k-steps)
     const int nc2 = (p.N2 + 31) >> 5, nc3 = p.N3 >> 4;        // items per M-tile: 32 columns (stages 1-2), 16 columns (stage 3)
     const bool prof = PROF && a.prof != nullptr && blockIdx.x == 0 && tid == 0;
     long long tp = 0, pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -361,17 +414,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
         const int s = w >> 24, y = (w >> 12) & 0xFFF, x = w & 0xFFF;
         const float* src = xstage + (size_t)s * xfloats + y * p.W + x;
         const bool live = s < nS;
-        for (int j = 0; j < kc1; ++j) {
-          float4 hi, lo;
-          const int c = 4 * j;
-          hi.x = (c + 0 < p.Cin && live) ? src[(c + 0) * HW] : 0.f;
-          hi.y = (c + 1 < p.Cin && live) ? src[(c + 1) * HW] : 0.f;
-          hi.z = (c + 2 < p.Cin && live) ? src[(c + 2) * HW] : 0.f;
-          hi.w = (c + 3 < p.Cin && live) ? src[(c + 3) * HW] : 0.f;
-          lo.x = tf32_lo(hi.x); lo.y = tf32_lo(hi.y); lo.z = tf32_lo(hi.z); lo.w = tf32_lo(hi.w);
-          const uint32_t off = sw128(r, c);
-          *reinterpret_cast<float4*>(a_hi + off) = hi;
-          *reinterpret_cast<float4*>(a_lo + off) = lo;
+        for (int j = 0; j < ng1; ++j) {
+          float o[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { const int c = 8 * j + q; o[q] = (c < p.Cin && live) ? src[c * HW] : 0.f; }
+          store_group8<F16>(a_hi, a_lo, r, 8 * j, o);
         }
       }
       fence_async_smem();
@@ -387,7 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
         const int r = t * 128 + row_in_tile;
         const float* bias = sb1;
         if (a.bias1_b != nullptr && r < p.R) bias = a.bias1_b + (size_t)min(b0 + (int)(tab_in[r] >> 24), p.B - 1) * p.Ch;
-        epilogue_to_operand(tmem + lane_base + t * 2 * p.N2, p.N2, c0, bias, a_hi, a_lo, p.region_bytes, r, r < p.R);
+        epilogue_to_operand<F16>(tmem + lane_base + t * 2 * p.N2, p.N2, c0, bias, a_hi, a_lo, p.region_bytes, r, r < p.R);
       }
       fence_async_smem();
       tc_fence_before();
@@ -400,7 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
       for (int item = grp; item < p.T2 * nc2; item += kEpiGroups) {
         const int t = item / nc2, c0 = (item - t * nc2) << 5;
         const int m = t * 128 + row_in_tile;
-        epilogue_to_operand(tmem + lane_base + t * 2 * p.N2, p.N2, c0, sb2, a_hi, a_lo, p.region_bytes, m, (tab_out[m] >> 31) != 0);
+        epilogue_to_operand<F16>(tmem + lane_base + t * 2 * p.N2, p.N2, c0, sb2, a_hi, a_lo, p.region_bytes, m, (tab_out[m] >> 31) != 0);
       }
       fence_async_smem();
       tc_fence_before();
@@ -425,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
         if (valid) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (c0 + i < p.Cout) dst[(size_t)(c0 + i) * HW] = v[i] + u[i] + sb3[c0 + i];
+            if (c0 + i < p.Cout) dst[(size_t)(c0 + i) * HW] = (F16 ? fmaf(u[i], kLoInv, v[i]) : v[i] + u[i]) + sb3[c0 + i];
         }
       }
       tc_fence_before();
@@ -447,42 +494,60 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
 //   1 + tap*P + pn   : W2[n][pn*32 + k][ky][kx]                   (N = N2)
 //   1 + taps*P + pn  : W3[n][pn*32 + k]                           (N = N3, rows >= Cout zero)
 __global__ void pack_tc_kernel(const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ w3, uint8_t* __restrict__ out,
-                               int Cin, int Ch, int Cout, int KH, int KW, int P, int N2, int N3, int stage_bytes, int w1_stride) {
+                               int Cin, int Ch, int Cout, int KH, int KW, int P, int N2, int N3, int stage_bytes, int w1_stride, int f16) {
   const int taps = KH * KW;
+  const int CPR = f16 ? 64 : 32;
   const int nchunks = 1 + taps * P + P;
   const int c = blockIdx.x;
   if (c >= nchunks) return;
   const int N = c < 1 + taps * P ? N2 : N3;
   uint8_t* img = out + (size_t)c * stage_bytes;
-  for (int i = threadIdx.x; i < N * 32; i += blockDim.x) {
-    const int n = i >> 5, k = i & 31;
+  for (int i = threadIdx.x; i < N * CPR; i += blockDim.x) {
+    const int n = i / CPR, k = i % CPR;
     float v = 0.f;
     if (c == 0) { if (n < Ch && k < Cin) v = w1[(size_t)n * w1_stride + k]; }
     else if (c < 1 + taps * P) {
-      const int tap = (c - 1) / P, pn = (c - 1) % P, ci = pn * 32 + k;
+      const int tap = (c - 1) / P, pn = (c - 1) % P, ci = pn * CPR + k;
       if (n < Ch && ci < Ch) v = w2[((size_t)n * Ch + ci) * taps + tap];
     } else {
-      const int pn = c - 1 - taps * P, ci = pn * 32 + k;
+      const int pn = c - 1 - taps * P, ci = pn * CPR + k;
       if (n < Cout && ci < Ch) v = w3[(size_t)n * Ch + ci];
     }
-    const uint32_t off = sw128(n, k);
-    *reinterpret_cast<float*>(img + off) = v;
-    *reinterpret_cast<float*>(img + (size_t)N * 128 + off) = tf32_lo(v);
+    if (f16) {
+      const uint32_t off = n * 128 + ((((k >> 3) ^ n) & 7) << 4) + ((k & 7) << 1);
+      const float vc = fminf(fmaxf(v, -65504.f), 65504.f);
+      const __half hi = __float2half_rn(vc);
+      *reinterpret_cast<__half*>(img + off) = hi;
+      *reinterpret_cast<__half*>(img + (size_t)N * 128 + off) = __float2half_rn((vc - __half2float(hi)) * kLoScale);
+    } else {
+      const uint32_t off = sw128(n, k);
+      *reinterpret_cast<float*>(img + off) = v;
+      *reinterpret_cast<float*>(img + (size_t)N * 128 + off) = tf32_lo(v);
+    }
   }
 }
 
 // ---- host-side geometry ------------------------------------------------------------------------------------------------
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 
+// operand kind of this process: 1 = scaled fp16 pairs (default), 0 = tf32 pairs (CFPP_TC_KIND=tf32)
+static int tc_kind() {
+  static int k = -1;
+  if (k < 0) { const char* v = getenv("CFPP_TC_KIND"); k = (v && strcmp(v, "tf32") == 0) ? 0 : 1; }
+  return k;
+}
+
 static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, long long x_bstride, int sms) {
   const int max_s = env_int("CFPP_TC_MAXS", 32);
+  const int kind = tc_kind(), CPR = kind ? 64 : 32, KE = kind ? 16 : 8;
   if (!((KH == 1 || KH == 3) && (KW == 1 || KW == 3))) return false;
   if ((KH == 3 && H < 2) || (KW == 3 && W < 2)) return false;
-  if (Ch % 16 != 0 || Ch < 16 || Ch > 128 || Cin < 1 || Cin > 32 || Cout < 1 || Cout > 128) return false;
+  if (Ch % 16 != 0 || Ch < 16 || Ch > 128 || Cin < 1 || Cin > CPR || Cout < 1 || Cout > 128) return false;
   if ((Cin * H * W) % 4 != 0 || x_bstride % 4 != 0) return false;      // 16-byte bulk copies of x0
   p = Plan{};
   p.B = B; p.Cin = Cin; p.Ch = Ch; p.Cout = Cout; p.H = H; p.W = W; p.KH = KH; p.KW = KW; p.x_bstride = x_bstride;
-  p.P = (Ch + 31) / 32; p.KS1 = (Cin + 7) / 8; p.N2 = Ch; p.N3 = (Cout + 15) / 16 * 16;
+  p.kind = kind;
+  p.P = (Ch + CPR - 1) / CPR; p.KS1 = (Cin + KE - 1) / KE; p.N2 = Ch; p.N3 = (Cout + 15) / 16 * 16;
   p.HP = H + KH - 1; p.WP = W + KW - 1;
   p.stage_bytes = 2 * p.N2 * 128;
   const int HW = H * W;
@@ -544,21 +609,21 @@ static long long* g_prof = nullptr;
 using namespace cfpp;
 
 static bool tc_channels_ok(int Cin, int Ch, int Cout, int KH, int KW) {
-  return Ch % 16 == 0 && Ch >= 16 && Ch <= 128 && Cin >= 1 && Cin <= 32 && Cout >= 1 && Cout <= 128 && (KH == 1 || KH == 3) && (KW == 1 || KW == 3);
+  return Ch % 16 == 0 && Ch >= 16 && Ch <= 128 && Cin >= 1 && Cin <= (tc::tc_kind() ? 64 : 32) && Cout >= 1 && Cout <= 128 && (KH == 1 || KH == 3) && (KW == 1 || KW == 3);
 }
 
 extern "C" int64_t cfpp_conv_cond_tc_pack_bytes(int Cin, int Ch, int Cout, int KH, int KW) {
   if (!tc_channels_ok(Cin, Ch, Cout, KH, KW)) return -1;
-  const int P = (Ch + 31) / 32;
+  const int CPR = tc::tc_kind() ? 64 : 32, P = (Ch + CPR - 1) / CPR;
   return (int64_t)(1 + KH * KW * P + P) * (2 * Ch * 128);
 }
 
 extern "C" int cfpp_conv_cond_tc_pack(const float* w1, int w1_stride, const float* w2, const float* w3, void* out,
                                       int Cin, int Ch, int Cout, int KH, int KW, void* stream) {
   CFPP_REQUIRE(cfpp_conv_cond_tc_pack_bytes(Cin, Ch, Cout, KH, KW) > 0, "conv_cond_tc_pack: unsupported channel counts / kernel size");
-  const int P = (Ch + 31) / 32, N2 = Ch, N3 = (Cout + 15) / 16 * 16;
+  const int CPR = tc::tc_kind() ? 64 : 32, P = (Ch + CPR - 1) / CPR, N2 = Ch, N3 = (Cout + 15) / 16 * 16;
   const int nchunks = 1 + KH * KW * P + P;
-  tc::pack_tc_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(w1, w2, w3, (uint8_t*)out, Cin, Ch, Cout, KH, KW, P, N2, N3, 2 * N2 * 128, w1_stride);
+  tc::pack_tc_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(w1, w2, w3, (uint8_t*)out, Cin, Ch, Cout, KH, KW, P, N2, N3, 2 * N2 * 128, w1_stride, tc::tc_kind());
   return check_launch("conv_cond_tc_pack");
 }
 
@@ -578,28 +643,28 @@ extern "C" int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h
   }
   CFPP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0, "conv_cond_tc: x / wpack must be 16-byte aligned");
   tc::g_last_plan = p;
-  const int P_ = (Ch + 31) / 32;
+  const int P_ = p.P;
   const long long pack_bytes = (long long)(1 + KH * KW * P_ + P_) * (2 * Ch * 128);
   tc::Args a{x, h, (const uint8_t*)wpack, b1, b2, b3, bias1_b, pack_bytes, tc::env_int("CFPP_TC_REPL", 1), tc::g_prof};
   const int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
   cudaStream_t st = (cudaStream_t)stream;
+  using KernelFn = void (*)(const tc::Plan, const tc::Args);
+  static const KernelFn kernels[8] = {
+      tc::conv_cond_tc_kernel<false, false, false>, tc::conv_cond_tc_kernel<false, false, true>,
+      tc::conv_cond_tc_kernel<false, true, false>,  tc::conv_cond_tc_kernel<false, true, true>,
+      tc::conv_cond_tc_kernel<true, false, false>,  tc::conv_cond_tc_kernel<true, false, true>,
+      tc::conv_cond_tc_kernel<true, true, false>,   tc::conv_cond_tc_kernel<true, true, true>};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc::conv_cond_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(tc::conv_cond_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(tc::conv_cond_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(tc::conv_cond_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    for (KernelFn k : kernels) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  if (a.prof != nullptr) {
-    if (p.seg) tc::conv_cond_tc_kernel<true, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p, a);
-    else tc::conv_cond_tc_kernel<false, true><<<grid, tc::kThreads, p.smem_bytes, st>>>(p, a);
-  } else {
-    if (p.seg) tc::conv_cond_tc_kernel<true, false><<<grid, tc::kThreads, p.smem_bytes, st>>>(p, a);
-    else tc::conv_cond_tc_kernel<false, false><<<grid, tc::kThreads, p.smem_bytes, st>>>(p, a);
-  }
+  kernels[(p.seg ? 4 : 0) | (a.prof != nullptr ? 2 : 0) | (p.kind ? 1 : 0)]<<<grid, tc::kThreads, p.smem_bytes, st>>>(p, a);
   return check_launch("conv_cond_tc_fwd");
 }
+
+/* operand kind of this process: 1 = scaled fp16 pairs (default), 0 = tf32 pairs (environment CFPP_TC_KIND=tf32) */
+extern "C" int cfpp_conv_cond_tc_kind(void) { return tc::tc_kind(); }
 
 /* geometry of the last launch, for tests / bench reporting: {seg, S, R, T1, T2, nstages, smem_bytes, ntiles} */
 extern "C" void cfpp_conv_cond_tc_last_plan(int* out8) {

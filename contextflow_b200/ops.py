@@ -371,15 +371,22 @@ def ctx_encode(ctx, noise, desc: _cabi.EncDesc, emit_stage=-1):
     return c, logp
 
 
+def _carve(B, widths, device, align=64):
+    """(B, w_i) fp32 matrices carved out of one allocation, each starting on a 256-byte boundary (consumers use 128-bit loads)."""
+    sizes = [(B * w + align - 1) // align * align for w in widths]
+    flat = torch.empty(sum(sizes), device=device, dtype=torch.float32)
+    outs, off = [], 0
+    for w, sz in zip(widths, sizes):
+        outs.append(flat[off: off + B * w].view(B, w)); off += sz
+    return outs
+
+
 def ctx_encode_batch(ctx, descs_dev, noises, widths):
     """n encoders over one context batch in a single launch; returns ([c_i (B, width_i)], [logp_i (B,)])."""
     _need_cuda(ctx, descs_dev)
     B, n = ctx.shape[0], len(widths)
-    c_all = torch.empty(B * sum(widths), device=ctx.device, dtype=torch.float32)
     logp_all = torch.empty((n, B), device=ctx.device, dtype=torch.float32)
-    cs, off = [], 0
-    for w in widths:
-        cs.append(c_all[off: off + B * w].view(B, w)); off += B * w
+    cs = _carve(B, widths, ctx.device)
     arr = lambda ts: (vp * n)(*[vp(0 if t is None else t.data_ptr()) for t in ts])
     noises = [None if t is None else _f32(t) for t in noises]
     _call('ctx_encode_batch', (_p(ctx.contiguous()), _p(descs_dev), n, arr(noises), arr(cs), arr(list(logp_all)), B, _stream()))
@@ -415,10 +422,7 @@ def cn_batch(jobs, ins):
     _need_cuda(*ins)
     n, B = len(jobs), ins[0].shape[0]
     widths = [int(j.N[j.n_layers - 1]) for j in jobs]
-    flat = torch.empty(B * sum(widths), device=ins[0].device, dtype=torch.float32)
-    outs, off = [], 0
-    for w in widths:
-        outs.append(flat[off: off + B * w].view(B, w)); off += B * w
+    outs = _carve(B, widths, ins[0].device)
     ins = [_f32(t) for t in ins]
     for i0 in range(0, n, _cabi.MAX_CN_JOBS):
         m = min(_cabi.MAX_CN_JOBS, n - i0)

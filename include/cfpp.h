@@ -97,7 +97,7 @@ int cfpp_conv_cond_fwd(const float* x, int64_t x_bstride, float* h,
 /* The same conditioner on the tcgen05 tensor cores (kind::tf32, fp32-faithful 3xTF32 split, TMEM accumulators, weights streamed
  * by bulk TMA copies; contextflow_b200/csrc/conv_cond_tc.cu).  Weights are repacked ONCE per parameter version by
  * cfpp_conv_cond_tc_pack from the torch layouts: w1 (Ch, >=Cin) with row stride w1_stride, w2 (Ch, Ch, KH, KW), w3 (Cout, Ch);
- * b1/b2/b3 are the plain bias vectors.  Supported: Ch % 16 == 0, 16 <= Ch <= 128, Cin <= 32, Cout <= 128, KH,KW in {1,3},
+ * b1/b2/b3 are the plain bias vectors.  Supported: Ch % 16 == 0, 16 <= Ch <= 128, Cin <= 64 (32 for the tf32 kind), Cout <= 128, KH,KW in {1,3},
  * (Cin*H*W) % 4 == 0, x_bstride % 4 == 0, x 16-byte aligned -- cfpp_conv_cond_tc_supported() answers for a shape; other shapes
  * use cfpp_conv_cond_fwd (CFPP_ERR_UNSUPPORTED is returned, nothing is launched). */
 int64_t cfpp_conv_cond_tc_pack_bytes(int Cin, int Ch, int Cout, int KH, int KW);   /* -1 when unsupported */
@@ -107,6 +107,10 @@ int cfpp_conv_cond_tc_supported(int B, int Cin, int Ch, int Cout, int H, int W, 
 int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h, const void* wpack,
                           const float* b1, const float* bias1_b, const float* b2, const float* b3,
                           int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, void* stream);
+/* Operand arithmetic of the tensor-core conditioner in this process: 1 (default) = scaled fp16 hi/lo pairs, tcgen05 kind::f16
+ * (22+ significand bits, values saturate at +-65504); 0 = tf32 hi/lo pairs, kind::tf32 (fp32 range; environment
+ * CFPP_TC_KIND=tf32).  Packed weights are specific to the kind they were packed under. */
+int cfpp_conv_cond_tc_kind(void);
 /* geometry of the last cfpp_conv_cond_tc_fwd launch (tests / bench): {segment layout, samples per tile, stored rows, M-tiles of
  * stage 1, M-tiles of stages 2-3, ring stages, shared-memory bytes, tiles} */
 void cfpp_conv_cond_tc_last_plan(int* out8);

