@@ -40,6 +40,7 @@ namespace tc {
 struct Plan {
   int B, Cin, Ch, Cout, H, W, KH, KW;
   int kind;                          // 0 = tf32 pair (32 channels / row, K = 8), 1 = scaled fp16 pair (64 channels / row, K = 16)
+  int rb;                            // operand row bytes: 128 (SWIZZLE_128B) or, fp16 kind with <= 32 channels, 64 (SWIZZLE_64B)
   int seg, S, NSEG, GS, YS, RPS, WP, HP;
   int R, T1, T2, NG;                 // stored rows per tile, M-tiles of stage 1 / stages 2-3, row groups of stage 2 (segment)
   int P, KS1, N2, N3;                // channel panels, k-steps of stage 1, N of stages 1-2, N of stage 3 (padded to 16)
@@ -57,6 +58,10 @@ constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kMaxStages = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// byte offset of 16-byte chunk `chunk` of operand row `row`: SWIZZLE_128B (chunk ^= row % 8) or SWIZZLE_64B (chunk ^= (row / 2) % 4)
+__host__ __device__ __forceinline__ uint32_t row_off(int row, int chunk, int rb) {
+  return rb == 128 ? (uint32_t)row * 128u + (uint32_t)(((chunk ^ row) & 7) << 4) : (uint32_t)row * 64u + (uint32_t)(((chunk ^ (row >> 1)) & 3) << 4);
+}
 __device__ __forceinline__ uint32_t sw128(int row, int k) { return row * 128 + ((((k >> 2) ^ row) & 7) << 4) + ((k & 3) << 2); }
 __device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
@@ -70,12 +75,12 @@ __device__ __forceinline__ void f16_split2(float a, float b, uint32_t& hi, uint3
 }
 // Store 8 consecutive channels (col8 = first channel within the panel, multiple of 8) of operand row `row` as (hi, lo) operands.
 template <bool F16>
-__device__ __forceinline__ void store_group8(uint8_t* ph, uint8_t* pl, int row, int col8, const float (&v)[8]) {
+__device__ __forceinline__ void store_group8(uint8_t* ph, uint8_t* pl, int row, int col8, const float (&v)[8], int rb) {
   if (F16) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) f16_split2(v[2 * q], v[2 * q + 1], h[q], l[q]);
-    const uint32_t off = row * 128 + ((((col8 >> 3) ^ row) & 7) << 4);
+    const uint32_t off = row_off(row, col8 >> 3, rb);
     *reinterpret_cast<uint4*>(ph + off) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(pl + off) = make_uint4(l[0], l[1], l[2], l[3]);
   } else {
@@ -113,8 +118,8 @@ __device__ __forceinline__ void mma_k(uint32_t tmem_d, uint64_t adesc, uint64_t 
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 // K-major SWIZZLE_128B shared-memory matrix descriptor; sbo = byte stride between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, int rb = 128) {   // layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(rb == 128 ? 2 : 4) << 61);
 }
 __host__ __device__ constexpr uint32_t make_idesc(int n, bool f16) {   // fp32 accumulate, A and B K-major, M = 128; operand format 0 = F16, 2 = TF32
   return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -179,7 +184,7 @@ __device__ __forceinline__ bool decode_out(const Plan& p, int m, int& s, int& y,
 // must call (tcgen05.ld is warp-collective); `write` only guards the stores.
 template <bool F16>
 __device__ __forceinline__ void store_split16(const float (&v)[16], const float (&u)[16], const float* __restrict__ bias, uint8_t* ph, uint8_t* pl,
-                                              int row, int col) {
+                                              int row, int col, int rb) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     float o[8];
@@ -195,13 +200,13 @@ __device__ __forceinline__ void store_split16(const float (&v)[16], const float 
         o[4 * q + 2] = fmaxf(v[i + 2] + u[i + 2] + b.z, 0.f); o[4 * q + 3] = fmaxf(v[i + 3] + u[i + 3] + b.w, 0.f);
       }
     }
-    store_group8<F16>(ph, pl, row, col + 8 * g, o);
+    store_group8<F16>(ph, pl, row, col + 8 * g, o, rb);
   }
 }
 template <bool F16>
 __device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, int c0, const float* __restrict__ bias, uint8_t* a_hi, uint8_t* a_lo,
-                                                    int region_bytes, int row, bool write) {
-  constexpr int CPR = F16 ? 64 : 32;                          // channels per 128-byte operand row
+                                                    int region_bytes, int row, bool write, int rb) {
+  const int CPR = F16 ? rb >> 1 : 32;                         // channels per operand row
   float v0[16], u0[16], v1[16], u1[16];
   const bool two = c0 + 16 < N;                               // warp-uniform
   tmem_ld16(taddr + c0, v0);
@@ -211,14 +216,15 @@ __device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, int c
   if (write) {
     uint8_t* ph = a_hi + (c0 / CPR) * region_bytes;
     uint8_t* pl = a_lo + (c0 / CPR) * region_bytes;
-    store_split16<F16>(v0, u0, bias + c0, ph, pl, row, c0 % CPR);
-    if (two) store_split16<F16>(v1, u1, bias + c0 + 16, ph, pl, row, (c0 % CPR) + 16);
+    store_split16<F16>(v0, u0, bias + c0, ph, pl, row, c0 % CPR, rb);
+    if (two) store_split16<F16>(v1, u1, bias + c0 + 16, ph, pl, row, (c0 % CPR) + 16, rb);
   }
 }
 
 template <bool SEG, bool PROF, bool F16>
 __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p, const Args a) {
-  constexpr int CPR = F16 ? 64 : 32, KE = F16 ? 16 : 8;     // channels per operand row (panel), channels per MMA k-step
+  constexpr int KE = F16 ? 16 : 8;                          // channels per MMA k-step
+  const int rb = p.rb, CPR = F16 ? rb >> 1 : 32;            // operand row bytes, channels per operand row (panel)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_hi = base;                                     // [P][region]
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
           bulk_g2s(smem_u32(xstage + (size_t)s * xfloats), a.x + (size_t)(b0 + s) * p.x_bstride, (uint32_t)(xfloats * 4), bar(BAR_XFULL));
         for (int c = 0; c < nchunks_tile; ++c) {
           mbar_wait(bar(BAR_EMPTY + st), rphase ^ 1);
-          const uint32_t bytes = (c < nchunks_tile - p.P) ? (uint32_t)(2 * p.N2 * 128) : (uint32_t)(2 * p.N3 * 128);
+          const uint32_t bytes = (c < nchunks_tile - p.P) ? (uint32_t)(2 * p.N2 * rb) : (uint32_t)(2 * p.N3 * rb);
           mbar_expect_tx(bar(BAR_FULL + st), bytes);
           bulk_g2s(smem_u32(ring + (size_t)st * p.stage_bytes), a.wpack + (size_t)(blockIdx.x % a.nrepl) * a.wrepl_stride + (size_t)c * p.stage_bytes, bytes, bar(BAR_FULL + st));
           if (++st == (uint32_t)p.nstages) { st = 0; rphase ^= 1; }
@@ -296,15 +302,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
     // position advances by adds, and the wait for the NEXT chunk sits in the middle of the current chunk's instructions.
     if (elect_one()) {
       const uint32_t idN2 = make_idesc(p.N2, F16), id2N2 = make_idesc(2 * p.N2, F16), idN3 = make_idesc(p.N3, F16), id2N3 = make_idesc(2 * p.N3, F16);
-      const uint32_t sbo2 = (uint32_t)p.GS * 128;
+      const uint32_t sbo2 = (uint32_t)(p.GS * rb), sbo1 = (uint32_t)(8 * rb), lin_u = (uint32_t)(8 * rb), row_u1 = (uint32_t)rb >> 4;   // lin_u: 128 rows / 16
       const uint32_t tile_cols2 = 2 * p.N2, tile_cols3 = 2 * p.N3;
-      const uint64_t ahi_lin = make_desc(smem_u32(a_hi), 1024), alo_lin = make_desc(smem_u32(a_lo), 1024);   // stages 1 / 3: plain 128-row tiles
-      const uint64_t ahi_seg = make_desc(smem_u32(a_hi), sbo2), alo_seg = make_desc(smem_u32(a_lo), sbo2);   // stage 2: group stride GS rows
-      const uint64_t bdesc0 = make_desc(smem_u32(ring), 1024);
+      const uint64_t ahi_lin = make_desc(smem_u32(a_hi), sbo1, rb), alo_lin = make_desc(smem_u32(a_lo), sbo1, rb);   // stages 1 / 3: plain 128-row tiles
+      const uint64_t ahi_seg = make_desc(smem_u32(a_hi), sbo2, rb), alo_seg = make_desc(smem_u32(a_lo), sbo2, rb);   // stage 2: group stride GS rows
+      const uint64_t bdesc0 = make_desc(smem_u32(ring), sbo1, rb);
       const uint32_t stage_u = (uint32_t)p.stage_bytes >> 4, region_u = (uint32_t)p.region_bytes >> 4;        // descriptor address units (16 B)
-      const uint32_t tile_u2 = sbo2, ys_u = (uint32_t)p.YS * 8;                                                 // 16 groups * sbo2 / 16; image-row stride
+      const uint32_t tile_u2 = sbo2, ys_u = (uint32_t)p.YS * row_u1;                                                 // 16 groups * sbo2 / 16; image-row stride
       const int nst = p.nstages, P = p.P, T1 = p.T1, T2 = p.T2, KH = p.KH, KW = p.KW, KS1 = p.KS1;
-      const int ks_last = (p.Ch - (P - 1) * CPR) / KE;
+      const int ks_last = (p.Ch - (P - 1) * CPR) / KE, ks_full = CPR / KE;
       uint32_t st = 0, rphase = 0;                               // ring slot being consumed (persists across tiles)
       const bool prof = PROF && a.prof != nullptr && blockIdx.x == 0;
       long long tp = prof ? clock64() : 0, acc8 = 0, acc9 = 0, acc10 = 0;
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
         mbar_wait(bar(BAR_AREADY), ph);
         tc_fence_after();
         tick(10);
-        issue_chunk(ahi_lin, alo_lin, 1024, tile_cols2, T1, KS1, id2N2, idN2, 0, true);
+        issue_chunk(ahi_lin, alo_lin, lin_u, tile_cols2, T1, KS1, id2N2, idN2, 0, true);
         tc_commit(bar(BAR_ACC1));
         tick(9);
         // ---- stage 2: KH x KW taps as shifted operand views ----
@@ -367,10 +373,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
         uint32_t row_u = 0;                                      // ky * YS rows, in descriptor units
         for (int ky = 0; ky < KH; ++ky, row_u += ys_u) {
           uint32_t tap_u = row_u;                                // + kx rows (8 units each)
-          for (int kx = 0; kx < KW; ++kx, tap_u += 8) {
+          for (int kx = 0; kx < KW; ++kx, tap_u += row_u1) {
             uint32_t pan_u = tap_u;
             for (int pn = 0; pn < P; ++pn, pan_u += region_u) {
-              issue_chunk(ahi_seg + pan_u, alo_seg + pan_u, tile_u2, tile_cols2, T2, pn == P - 1 ? ks_last : 4, id2N2, idN2, first_acc, true);
+              issue_chunk(ahi_seg + pan_u, alo_seg + pan_u, tile_u2, tile_cols2, T2, pn == P - 1 ? ks_last : ks_full, id2N2, idN2, first_acc, true);
               first_acc = 1;
             }
           }
@@ -383,7 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
         tick(10);
         uint32_t pan_u = 0;
         for (int pn = 0; pn < P; ++pn, pan_u += region_u)
-          issue_chunk(ahi_lin + pan_u, alo_lin + pan_u, 1024, tile_cols3, T2, pn == P - 1 ? ks_last : 4, id2N3, idN3, pn > 0,
+          issue_chunk(ahi_lin + pan_u, alo_lin + pan_u, lin_u, tile_cols3, T2, pn == P - 1 ? ks_last : ks_full, id2N3, idN3, pn > 0,
                       !(last_tile && pn == P - 1));
         tc_commit(bar(BAR_ACC3));
         tick(9);
@@ -418,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
           float o[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) { const int c = 8 * j + q; o[q] = (c < p.Cin && live) ? src[c * HW] : 0.f; }
-          store_group8<F16>(a_hi, a_lo, r, 8 * j, o);
+          store_group8<F16>(a_hi, a_lo, r, 8 * j, o, rb);
         }
       }
       fence_async_smem();
@@ -434,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
         const int r = t * 128 + row_in_tile;
         const float* bias = sb1;
         if (a.bias1_b != nullptr && r < p.R) bias = a.bias1_b + (size_t)min(b0 + (int)(tab_in[r] >> 24), p.B - 1) * p.Ch;
-        epilogue_to_operand<F16>(tmem + lane_base + t * 2 * p.N2, p.N2, c0, bias, a_hi, a_lo, p.region_bytes, r, r < p.R);
+        epilogue_to_operand<F16>(tmem + lane_base + t * 2 * p.N2, p.N2, c0, bias, a_hi, a_lo, p.region_bytes, r, r < p.R, rb);
       }
       fence_async_smem();
       tc_fence_before();
@@ -447,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
       for (int item = grp; item < p.T2 * nc2; item += kEpiGroups) {
         const int t = item / nc2, c0 = (item - t * nc2) << 5;
         const int m = t * 128 + row_in_tile;
-        epilogue_to_operand<F16>(tmem + lane_base + t * 2 * p.N2, p.N2, c0, sb2, a_hi, a_lo, p.region_bytes, m, (tab_out[m] >> 31) != 0);
+        epilogue_to_operand<F16>(tmem + lane_base + t * 2 * p.N2, p.N2, c0, sb2, a_hi, a_lo, p.region_bytes, m, (tab_out[m] >> 31) != 0, rb);
       }
       fence_async_smem();
       tc_fence_before();
@@ -494,9 +500,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
 //   1 + tap*P + pn   : W2[n][pn*32 + k][ky][kx]                   (N = N2)
 //   1 + taps*P + pn  : W3[n][pn*32 + k]                           (N = N3, rows >= Cout zero)
 __global__ void pack_tc_kernel(const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ w3, uint8_t* __restrict__ out,
-                               int Cin, int Ch, int Cout, int KH, int KW, int P, int N2, int N3, int stage_bytes, int w1_stride, int f16) {
+                               int Cin, int Ch, int Cout, int KH, int KW, int P, int N2, int N3, int stage_bytes, int w1_stride, int f16, int rb) {
   const int taps = KH * KW;
-  const int CPR = f16 ? 64 : 32;
+  const int CPR = f16 ? rb >> 1 : 32;
   const int nchunks = 1 + taps * P + P;
   const int c = blockIdx.x;
   if (c >= nchunks) return;
@@ -514,11 +520,11 @@ __global__ void pack_tc_kernel(const float* __restrict__ w1, const float* __rest
       if (n < Cout && ci < Ch) v = w3[(size_t)n * Ch + ci];
     }
     if (f16) {
-      const uint32_t off = n * 128 + ((((k >> 3) ^ n) & 7) << 4) + ((k & 7) << 1);
+      const uint32_t off = row_off(n, k >> 3, rb) + ((k & 7) << 1);
       const float vc = fminf(fmaxf(v, -65504.f), 65504.f);
       const __half hi = __float2half_rn(vc);
       *reinterpret_cast<__half*>(img + off) = hi;
-      *reinterpret_cast<__half*>(img + (size_t)N * 128 + off) = __float2half_rn((vc - __half2float(hi)) * kLoScale);
+      *reinterpret_cast<__half*>(img + (size_t)N * rb + off) = __float2half_rn((vc - __half2float(hi)) * kLoScale);
     } else {
       const uint32_t off = sw128(n, k);
       *reinterpret_cast<float*>(img + off) = v;
@@ -537,19 +543,22 @@ static int tc_kind() {
   return k;
 }
 
+// operand row bytes: the fp16 kind stores <= 32 channels in 64-byte rows (SWIZZLE_64B) -- half the shared memory of a padded 128-byte row
+static int row_bytes(int kind, int Cin, int Ch) { return (kind == 1 && Ch <= 32 && Cin <= 32 && env_int("CFPP_TC_RB64", 1)) ? 64 : 128; }
+
 static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, long long x_bstride, int sms) {
   const int max_s = env_int("CFPP_TC_MAXS", 32);
-  const int kind = tc_kind(), CPR = kind ? 64 : 32, KE = kind ? 16 : 8;
+  const int kind = tc_kind(), rb = row_bytes(kind, Cin, Ch), CPR = kind ? rb >> 1 : 32, KE = kind ? 16 : 8;
   if (!((KH == 1 || KH == 3) && (KW == 1 || KW == 3))) return false;
   if ((KH == 3 && H < 2) || (KW == 3 && W < 2)) return false;
   if (Ch % 16 != 0 || Ch < 16 || Ch > 128 || Cin < 1 || Cin > CPR || Cout < 1 || Cout > 128) return false;
   if ((Cin * H * W) % 4 != 0 || x_bstride % 4 != 0) return false;      // 16-byte bulk copies of x0
   p = Plan{};
   p.B = B; p.Cin = Cin; p.Ch = Ch; p.Cout = Cout; p.H = H; p.W = W; p.KH = KH; p.KW = KW; p.x_bstride = x_bstride;
-  p.kind = kind;
+  p.kind = kind; p.rb = rb;
   p.P = (Ch + CPR - 1) / CPR; p.KS1 = (Cin + KE - 1) / KE; p.N2 = Ch; p.N3 = (Cout + 15) / 16 * 16;
   p.HP = H + KH - 1; p.WP = W + KW - 1;
-  p.stage_bytes = 2 * p.N2 * 128;
+  p.stage_bytes = 2 * p.N2 * rb;
   const int HW = H * W;
   const int kSmemMax = 227 * 1024 - 1024;                               // minus alignment slack
   const int bias_bytes = (2 * p.N2 + p.N3) * 4, bar_bytes = BAR_COUNT * 8 + 16;
@@ -569,7 +578,7 @@ static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, i
       }
       q.T1 = (q.R + 127) / 128;
       if (q.T1 * 2 * q.N2 > 512 || q.T2 * 2 * q.N2 > 512 || q.T2 * 2 * q.N3 > 512) break;
-      q.region_bytes = ((q.R + 7) / 8 * 8) * 128;
+      q.region_bytes = ((q.R + 15) / 16 * 16) * rb;          // multiple of 1024 bytes: every region starts on a swizzle-atom boundary
       // operand rows the MMAs may touch (garbage rows included) must stay inside this CTA's shared memory
       q.off_ring = 2 * q.P * q.region_bytes;
       const int xbytes = (S * Cin * HW * 4 + 127) / 128 * 128;
@@ -579,8 +588,8 @@ static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, i
       if (nst < 2) break;
       if (nst > kMaxStages) nst = kMaxStages;
       q.nstages = nst;
-      const int reach1 = q.T1 * 128 * 128;                                                    // stage 1 / 3 tiles
-      const int reach2 = ((q.T2 * 16 - 1) * q.GS + (KH - 1) * q.YS + (KW - 1) + 8) * 128;      // last group of the last tap
+      const int reach1 = q.T1 * 128 * rb;                                                     // stage 1 / 3 tiles
+      const int reach2 = ((q.T2 * 16 - 1) * q.GS + (KH - 1) * q.YS + (KW - 1) + 8) * rb;       // last group of the last tap
       const int reach = (reach1 > reach2 ? reach1 : reach2) + (2 * q.P - 1) * q.region_bytes;
       if (reach > q.off_ring + nst * q.stage_bytes) continue;
       q.off_stage_x = q.off_ring + nst * q.stage_bytes;
@@ -614,16 +623,16 @@ static bool tc_channels_ok(int Cin, int Ch, int Cout, int KH, int KW) {
 
 extern "C" int64_t cfpp_conv_cond_tc_pack_bytes(int Cin, int Ch, int Cout, int KH, int KW) {
   if (!tc_channels_ok(Cin, Ch, Cout, KH, KW)) return -1;
-  const int CPR = tc::tc_kind() ? 64 : 32, P = (Ch + CPR - 1) / CPR;
-  return (int64_t)(1 + KH * KW * P + P) * (2 * Ch * 128);
+  const int rb = tc::row_bytes(tc::tc_kind(), Cin, Ch), CPR = tc::tc_kind() ? rb >> 1 : 32, P = (Ch + CPR - 1) / CPR;
+  return (int64_t)(1 + KH * KW * P + P) * (2 * Ch * rb);
 }
 
 extern "C" int cfpp_conv_cond_tc_pack(const float* w1, int w1_stride, const float* w2, const float* w3, void* out,
                                       int Cin, int Ch, int Cout, int KH, int KW, void* stream) {
   CFPP_REQUIRE(cfpp_conv_cond_tc_pack_bytes(Cin, Ch, Cout, KH, KW) > 0, "conv_cond_tc_pack: unsupported channel counts / kernel size");
-  const int CPR = tc::tc_kind() ? 64 : 32, P = (Ch + CPR - 1) / CPR, N2 = Ch, N3 = (Cout + 15) / 16 * 16;
+  const int rb = tc::row_bytes(tc::tc_kind(), Cin, Ch), CPR = tc::tc_kind() ? rb >> 1 : 32, P = (Ch + CPR - 1) / CPR, N2 = Ch, N3 = (Cout + 15) / 16 * 16;
   const int nchunks = 1 + KH * KW * P + P;
-  tc::pack_tc_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(w1, w2, w3, (uint8_t*)out, Cin, Ch, Cout, KH, KW, P, N2, N3, 2 * N2 * 128, w1_stride, tc::tc_kind());
+  tc::pack_tc_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(w1, w2, w3, (uint8_t*)out, Cin, Ch, Cout, KH, KW, P, N2, N3, 2 * N2 * rb, w1_stride, tc::tc_kind(), rb);
   return check_launch("conv_cond_tc_pack");
 }
 
@@ -644,7 +653,7 @@ extern "C" int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h
   CFPP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0, "conv_cond_tc: x / wpack must be 16-byte aligned");
   tc::g_last_plan = p;
   const int P_ = p.P;
-  const long long pack_bytes = (long long)(1 + KH * KW * P_ + P_) * (2 * Ch * 128);
+  const long long pack_bytes = (long long)(1 + KH * KW * P_ + P_) * (2 * Ch * p.rb);
   tc::Args a{x, h, (const uint8_t*)wpack, b1, b2, b3, bias1_b, pack_bytes, tc::env_int("CFPP_TC_REPL", 1), tc::g_prof};
   const int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
   cudaStream_t st = (cudaStream_t)stream;
