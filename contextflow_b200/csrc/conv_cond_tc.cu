@@ -31,6 +31,7 @@
 // 94 %) -> epilogue 2 -> stage 3 (1x1) -> epilogue 3.
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 #include <cuda_fp16.h>
 #include "common.cuh"
 
@@ -41,21 +42,23 @@ struct Plan {
   int B, Cin, Ch, Cout, H, W, KH, KW;
   int kind;                          // 0 = tf32 pair (32 channels / row, K = 8), 1 = scaled fp16 pair (64 channels / row, K = 16)
   int rb;                            // operand row bytes: 128 (SWIZZLE_128B) or, fp16 kind with <= 32 channels, 64 (SWIZZLE_64B)
+  int occ;                           // CTAs per SM this plan is sized for (1 or 2)
   int seg, S, NSEG, GS, YS, RPS, WP, HP;
   int R, T1, T2, NG;                 // stored rows per tile, M-tiles of stage 1 / stages 2-3, row groups of stage 2 (segment)
   int P, KS1, N2, N3;                // channel panels, k-steps of stage 1, N of stages 1-2, N of stage 3 (padded to 16)
   int stage_bytes, nstages, ntiles;
+  int resident;                      // 1: nstages == chunks per tile, the weight chunks are loaded once per CTA and never recycled
   int region_bytes;                  // bytes of one (hi|lo, panel) operand region
   int off_ring, off_stage_x, off_bias, off_tab, off_bar, smem_bytes;   // off_tab: R + T2*128 packed row-decode words
   long long x_bstride;
 };
 
-constexpr int kEpiWarps = 12;                  // 3 warps per TMEM lane quadrant (a warp reaches lanes 32*(warp%4) .. +31 only)
-constexpr int kEpiGroups = kEpiWarps / 4;
-constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kMmaWarp = kEpiWarps, kProdWarp = kEpiWarps + 1;
-constexpr int kThreads = (kEpiWarps + 2) * 32;
-constexpr int kMaxStages = 8;
+// OCC = CTAs resident per SM.  OCC 1: one CTA owns the SM (12 epilogue warps, 512 TMEM columns, ~226 KB).  OCC 2: two CTAs with half
+// the shared memory and TMEM columns each (8 epilogue warps): a tile's stages are serial inside a CTA (MMA -> epilogue -> MMA ...),
+// so a second resident CTA lets the tensor pipe work on its tile while this one's epilogue warps transform accumulators.
+__host__ __device__ constexpr int epi_warps(int occ) { return occ == 1 ? 12 : 8; }   // multiple of 4: a warp reaches TMEM lanes 32*(warp%4) .. +31 only
+__host__ __device__ constexpr int cta_threads(int occ) { return (epi_warps(occ) + 2) * 32; }
+constexpr int kMaxStages = 12;                 // ring slots; when every weight chunk of a tile fits (<= 12 chunks) the weights stay resident
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // byte offset of 16-byte chunk `chunk` of operand row `row`: SWIZZLE_128B (chunk ^= row % 8) or SWIZZLE_64B (chunk ^= (row / 2) % 4)
@@ -116,6 +119,22 @@ __device__ __forceinline__ void mma_k(uint32_t tmem_d, uint64_t adesc, uint64_t 
   else
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// TT consecutive M-tiles x KS k-steps of one weight chunk, fully unrolled: per k-step the stacked product (N' = 2N into [0,2N)) and
+// the lo-activation product (N into [N,2N)).
+template <bool F16, int KS, int TT, int KS0 = 0>
+__device__ __forceinline__ void mma_tiles(uint32_t d, uint32_t dcols, uint64_t ah, uint64_t al, uint32_t tile_u, uint64_t bd,
+                                          uint32_t id2, uint32_t id1, uint32_t first_acc) {
+#pragma unroll
+  for (int tt = 0; tt < TT; ++tt) {
+    const uint32_t dd = d + tt * dcols, dl = dd + (dcols >> 1);
+    const uint64_t a0 = ah + (uint64_t)(tt * tile_u), a1 = al + (uint64_t)(tt * tile_u);
+#pragma unroll
+    for (int ks = KS0; ks < KS; ++ks) {
+      mma_k<F16>(dd, a0 + 2 * ks, bd + 2 * ks, id2, ks ? 1u : first_acc);
+      mma_k<F16>(dl, a1 + 2 * ks, bd + 2 * ks, id1, 1);
+    }
+  }
 }
 // K-major SWIZZLE_128B shared-memory matrix descriptor; sbo = byte stride between 8-row groups.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, int rb = 128) {   // layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
@@ -203,12 +222,12 @@ __device__ __forceinline__ void store_split16(const float (&v)[16], const float 
     store_group8<F16>(ph, pl, row, col + 8 * g, o, rb);
   }
 }
-template <bool F16>
+template <bool F16, bool WIDE>
 __device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, int c0, const float* __restrict__ bias, uint8_t* a_hi, uint8_t* a_lo,
                                                     int region_bytes, int row, bool write, int rb) {
   const int CPR = F16 ? rb >> 1 : 32;                         // channels per operand row
   float v0[16], u0[16], v1[16], u1[16];
-  const bool two = c0 + 16 < N;                               // warp-uniform
+  const bool two = WIDE && c0 + 16 < N;                       // warp-uniform; narrow items (16 columns) halve the live registers
   tmem_ld16(taddr + c0, v0);
   tmem_ld16(taddr + N + c0, u0);
   if (two) { tmem_ld16(taddr + c0 + 16, v1); tmem_ld16(taddr + N + c0 + 16, u1); }
@@ -221,8 +240,10 @@ __device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, int c
   }
 }
 
-template <bool SEG, bool PROF, bool F16>
-__global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p, const Args a) {
+template <bool SEG, bool PROF, bool F16, int OCC>
+__global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(const Plan p, const Args a) {
+  constexpr int kEpiWarps = epi_warps(OCC), kEpiGroups = kEpiWarps / 4, kEpiThreads = kEpiWarps * 32;
+  constexpr int kMmaWarp = kEpiWarps, kProdWarp = kEpiWarps + 1, kThreads = cta_threads(OCC), kTmemCols = 512 / OCC;
   constexpr int KE = F16 ? 16 : 8;                          // channels per MMA k-step
   const int rb = p.rb, CPR = F16 ? rb >> 1 : 32;            // operand row bytes, channels per operand row (panel)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -263,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
     tab_out[m] = ok ? (0x80000000u | ((uint32_t)s_ << 24) | ((uint32_t)y_ << 12) | (uint32_t)x_) : 0u;
   }
   if (warp == kMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -286,6 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
         for (int s = 0; s < nS; ++s)
           bulk_g2s(smem_u32(xstage + (size_t)s * xfloats), a.x + (size_t)(b0 + s) * p.x_bstride, (uint32_t)(xfloats * 4), bar(BAR_XFULL));
         for (int c = 0; c < nchunks_tile; ++c) {
+          if (p.resident && it > 0) break;                       // resident weights: loaded for the first tile only
           mbar_wait(bar(BAR_EMPTY + st), rphase ^ 1);
           const uint32_t bytes = (c < nchunks_tile - p.P) ? (uint32_t)(2 * p.N2 * rb) : (uint32_t)(2 * p.N3 * rb);
           mbar_expect_tx(bar(BAR_FULL + st), bytes);
@@ -318,10 +340,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
         if (PROF && prof) { const long long now = clock64(); const long long d = now - tp; tp = now; if (slot == 8) acc8 += d; else if (slot == 9) acc9 += d; else acc10 += d; }
       };
       // wait until the chunk AFTER the one in slot `st` has landed (no-op when there is none: end of this CTA's work)
+      const bool resident = p.resident != 0;
+      bool wskip = false;                                        // resident weights already in place (every tile after the first)
       auto wait_next = [&](bool has_next) {
-        if (has_next) {
+        if (has_next && !wskip) {
           uint32_t ns = st + 1, nph = rphase;
-          if (ns == (uint32_t)nst) { ns = 0; nph ^= 1; }
+          if (ns == (uint32_t)nst) { if (resident) return; ns = 0; nph ^= 1; }
           mbar_wait(bar(BAR_FULL) + 8u * ns, nph);
           tc_fence_after();
         }
@@ -332,32 +356,93 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
                              uint32_t first_acc, bool has_next) {
         const uint64_t bd = bdesc0 + st * stage_u;
         uint32_t d = tmem;
-        for (int t = 0; t < T; ++t) {
-          if (t == T - 1 && T > 1) wait_next(has_next);
-          const uint32_t dl = d + (dcols >> 1);              // the (scaled) cross products collect in the second column block [N, 2N)
-          if (ksn == 4) {
-            mma_k<F16>(d, ah, bd, id2, first_acc);     mma_k<F16>(dl, al, bd, id1, 1);
-            mma_k<F16>(d, ah + 2, bd + 2, id2, 1);     mma_k<F16>(dl, al + 2, bd + 2, id1, 1);
-            if (T == 1) wait_next(has_next);
-            mma_k<F16>(d, ah + 4, bd + 4, id2, 1);     mma_k<F16>(dl, al + 4, bd + 4, id1, 1);
-            mma_k<F16>(d, ah + 6, bd + 6, id2, 1);     mma_k<F16>(dl, al + 6, bd + 6, id1, 1);
-          } else {
-            if (T == 1) wait_next(has_next);
-            for (int ks = 0; ks < ksn; ++ks) {
-              mma_k<F16>(d, ah + 2 * ks, bd + 2 * ks, id2, ks > 0 ? 1u : first_acc);
-              mma_k<F16>(dl, al + 2 * ks, bd + 2 * ks, id1, 1);
-            }
+        // Straight-line blocks: the issuing thread's operands live in vector registers and every distinct value costs an R2UR move
+        // per use inside a loop body, so k-steps are unrolled at compile time (descriptor + immediate) and M-tiles go two per
+        // iteration; the next chunk's barrier is polled before the last block so its latency hides behind queued MMAs.
+        if (T == 1) {
+          const uint32_t dl = d + (dcols >> 1);
+          switch (ksn) {
+            case 4:
+              mma_k<F16>(d, ah, bd, id2, first_acc);     mma_k<F16>(dl, al, bd, id1, 1);
+              mma_k<F16>(d, ah + 2, bd + 2, id2, 1);     mma_k<F16>(dl, al + 2, bd + 2, id1, 1);
+              wait_next(has_next);
+              mma_k<F16>(d, ah + 4, bd + 4, id2, 1);     mma_k<F16>(dl, al + 4, bd + 4, id1, 1);
+              mma_k<F16>(d, ah + 6, bd + 6, id2, 1);     mma_k<F16>(dl, al + 6, bd + 6, id1, 1);
+              break;
+            case 3: wait_next(has_next); mma_tiles<F16, 3, 1>(d, dcols, ah, al, tile_u, bd, id2, id1, first_acc); break;
+            case 2: wait_next(has_next); mma_tiles<F16, 2, 1>(d, dcols, ah, al, tile_u, bd, id2, id1, first_acc); break;
+            default: wait_next(has_next); mma_tiles<F16, 1, 1>(d, dcols, ah, al, tile_u, bd, id2, id1, first_acc); break;
           }
-          ah += tile_u; al += tile_u; d += dcols;
+        } else {
+          auto tiles = [&](int n) {                            // n = 1 or 2 M-tiles at the current position
+            if (n == 2) {
+              switch (ksn) {
+                case 4: mma_tiles<F16, 4, 2>(d, dcols, ah, al, tile_u, bd, id2, id1, first_acc); break;
+                case 3: mma_tiles<F16, 3, 2>(d, dcols, ah, al, tile_u, bd, id2, id1, first_acc); break;
+                case 2: mma_tiles<F16, 2, 2>(d, dcols, ah, al, tile_u, bd, id2, id1, first_acc); break;
+                default: mma_tiles<F16, 1, 2>(d, dcols, ah, al, tile_u, bd, id2, id1, first_acc); break;
+              }
+            } else {
+              switch (ksn) {
+                case 4: mma_tiles<F16, 4, 1>(d, dcols, ah, al, tile_u, bd, id2, id1, first_acc); break;
+                case 3: mma_tiles<F16, 3, 1>(d, dcols, ah, al, tile_u, bd, id2, id1, first_acc); break;
+                case 2: mma_tiles<F16, 2, 1>(d, dcols, ah, al, tile_u, bd, id2, id1, first_acc); break;
+                default: mma_tiles<F16, 1, 1>(d, dcols, ah, al, tile_u, bd, id2, id1, first_acc); break;
+              }
+            }
+            ah += n * tile_u; al += n * tile_u; d += n * dcols;
+          };
+          int t = 0;
+          for (; t + 2 <= T - 1; t += 2) tiles(2);
+          for (; t < T - 1; ++t) tiles(1);
+          wait_next(has_next);                                 // behind all but the last tile's queued MMAs
+          tiles(1);
         }
-        tc_commit(bar(BAR_EMPTY) + 8u * st);                   // frees the slot when these MMAs have read it
+        if (!resident) tc_commit(bar(BAR_EMPTY) + 8u * st);    // frees the slot when these MMAs have read it
         if (++st == (uint32_t)nst) { st = 0; rphase ^= 1; }
       };
+
+      // the same with the M-tile count and the k-steps per chunk known at compile time (the BASELINE level shapes): one straight-line
+      // block per chunk, nothing but the tap's base descriptors changes between chunks
+      auto issue_ct = [&](auto Tc, auto KSc, uint64_t ah, uint64_t al, uint32_t tile_u, uint32_t dcols, uint32_t id2, uint32_t id1,
+                          uint32_t first_acc, bool has_next) {
+        constexpr int T = decltype(Tc)::value, KS = decltype(KSc)::value;
+        const uint64_t bd = bdesc0 + st * stage_u;
+        if constexpr (T == 1) {
+          constexpr int H = (KS + 1) / 2;
+          mma_tiles<F16, H, 1>(tmem, dcols, ah, al, tile_u, bd, id2, id1, first_acc);
+          wait_next(has_next);
+          if constexpr (H < KS) mma_tiles<F16, KS, 1, H>(tmem, dcols, ah, al, tile_u, bd, id2, id1, first_acc);
+        } else {
+          mma_tiles<F16, KS, T - 1>(tmem, dcols, ah, al, tile_u, bd, id2, id1, first_acc);
+          wait_next(has_next);
+          mma_tiles<F16, KS, 1>(tmem + (T - 1) * dcols, dcols, ah + (uint64_t)((T - 1) * tile_u), al + (uint64_t)((T - 1) * tile_u), tile_u, bd, id2, id1, first_acc);
+        }
+        if (!resident) tc_commit(bar(BAR_EMPTY) + 8u * st);
+        if (++st == (uint32_t)nst) { st = 0; rphase ^= 1; }
+      };
+      auto stage2_ct = [&](auto Tc, auto KSc) {
+        uint32_t first_acc = 0, row_u = 0;
+        for (int ky = 0; ky < KH; ++ky, row_u += ys_u) {
+          uint32_t tap_u = row_u;
+          for (int kx = 0; kx < KW; ++kx, tap_u += row_u1) {
+            uint32_t pan_u = tap_u;
+            for (int pn = 0; pn < P; ++pn, pan_u += region_u) {
+              issue_ct(Tc, KSc, ahi_seg + pan_u, alo_seg + pan_u, tile_u2, tile_cols2, id2N2, idN2, first_acc, true);
+              first_acc = 1;
+            }
+          }
+        }
+      };
+      using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>; using I4 = std::integral_constant<int, 4>;
+      const int s2class = (ks_last != ks_full) ? 0 : (T2 == 1 && ks_full == 4) ? 1 : (T2 == 2 && ks_full == 4) ? 2 : (T2 == 2 && ks_full == 2) ? 3
+                          : (T2 == 4 && ks_full == 2) ? 4 : (T2 == 4 && ks_full == 4) ? 5 : 0;
 
       if (my_tiles > 0) { mbar_wait(bar(BAR_FULL), 0); tc_fence_after(); }   // first chunk of the first tile; every later chunk is pre-waited
       for (int it = 0; it < my_tiles; ++it) {
         const uint32_t ph = it & 1;
         const bool last_tile = it == my_tiles - 1;
+        wskip = resident && it > 0;
         // ---- stage 1: H1 = W1 x0 over every stored row ----
         mbar_wait(bar(BAR_AREADY), ph);
         tc_fence_after();
@@ -371,6 +456,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
         tick(10);
         uint32_t first_acc = 0;
         uint32_t row_u = 0;                                      // ky * YS rows, in descriptor units
+        if (s2class == 1) stage2_ct(I1{}, I4{});
+        else if (s2class == 2) stage2_ct(I2{}, I4{});
+        else if (s2class == 3) stage2_ct(I2{}, I2{});
+        else if (s2class == 4) stage2_ct(std::integral_constant<int, 4>{}, I2{});
+        else if (s2class == 5) stage2_ct(std::integral_constant<int, 4>{}, I4{});
+        else
         for (int ky = 0; ky < KH; ++ky, row_u += ys_u) {
           uint32_t tap_u = row_u;                                // + kx rows (8 units each)
           for (int kx = 0; kx < KW; ++kx, tap_u += row_u1) {
@@ -403,7 +494,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const int row_in_tile = quad * 32 + lane;
     const int ng1 = p.KS1 * KE / 8;                           // groups of 8 channels of x0 per stored row (K zero-padded to whole k-steps)
-    const int nc2 = (p.N2 + 31) >> 5, nc3 = p.N3 >> 4;        // items per M-tile: 32 columns (stages 1-2), 16 columns (stage 3)
+    constexpr bool kWide = OCC == 1;                          // epilogue item width of stages 1-2: 32 columns, 16 under the two-CTA register budget
+    constexpr int kIW = kWide ? 32 : 16;
+    const int nc2 = (p.N2 + kIW - 1) / kIW, nc3 = p.N3 >> 4;  // items per M-tile (stage 3 items are 16 columns)
     const bool prof = PROF && a.prof != nullptr && blockIdx.x == 0 && tid == 0;
     long long tp = 0, pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     auto tick = [&](int slot) { if (PROF && prof) { const long long now = clock64(); pacc[slot] += now - tp; tp = now; } };
@@ -436,11 +529,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
       tc_fence_after();
       tick(2);
       for (int item = grp; item < p.T1 * nc2; item += kEpiGroups) {
-        const int t = item / nc2, c0 = (item - t * nc2) << 5;
+        const int t = item / nc2, c0 = (item - t * nc2) * kIW;
         const int r = t * 128 + row_in_tile;
         const float* bias = sb1;
         if (a.bias1_b != nullptr && r < p.R) bias = a.bias1_b + (size_t)min(b0 + (int)(tab_in[r] >> 24), p.B - 1) * p.Ch;
-        epilogue_to_operand<F16>(tmem + lane_base + t * 2 * p.N2, p.N2, c0, bias, a_hi, a_lo, p.region_bytes, r, r < p.R, rb);
+        epilogue_to_operand<F16, kWide>(tmem + lane_base + t * 2 * p.N2, p.N2, c0, bias, a_hi, a_lo, p.region_bytes, r, r < p.R, rb);
       }
       fence_async_smem();
       tc_fence_before();
@@ -451,9 +544,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
       tc_fence_after();
       tick(4);
       for (int item = grp; item < p.T2 * nc2; item += kEpiGroups) {
-        const int t = item / nc2, c0 = (item - t * nc2) << 5;
+        const int t = item / nc2, c0 = (item - t * nc2) * kIW;
         const int m = t * 128 + row_in_tile;
-        epilogue_to_operand<F16>(tmem + lane_base + t * 2 * p.N2, p.N2, c0, sb2, a_hi, a_lo, p.region_bytes, m, (tab_out[m] >> 31) != 0, rb);
+        epilogue_to_operand<F16, kWide>(tmem + lane_base + t * 2 * p.N2, p.N2, c0, sb2, a_hi, a_lo, p.region_bytes, m, (tab_out[m] >> 31) != 0, rb);
       }
       fence_async_smem();
       tc_fence_before();
@@ -491,7 +584,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_cond_tc_kernel(const Plan p,
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
 }
 
 // One-time weight repack: torch-layout conv weights -> the chunk stream the producer copies verbatim into the ring.
@@ -546,7 +639,7 @@ static int tc_kind() {
 // operand row bytes: the fp16 kind stores <= 32 channels in 64-byte rows (SWIZZLE_64B) -- half the shared memory of a padded 128-byte row
 static int row_bytes(int kind, int Cin, int Ch) { return (kind == 1 && Ch <= 32 && Cin <= 32 && env_int("CFPP_TC_RB64", 1)) ? 64 : 128; }
 
-static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, long long x_bstride, int sms) {
+static bool make_plan_occ(Plan& p, double& waste_out, int occ, int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, long long x_bstride, int sms) {
   const int max_s = env_int("CFPP_TC_MAXS", 32);
   const int kind = tc_kind(), rb = row_bytes(kind, Cin, Ch), CPR = kind ? rb >> 1 : 32, KE = kind ? 16 : 8;
   if (!((KH == 1 || KH == 3) && (KW == 1 || KW == 3))) return false;
@@ -555,12 +648,15 @@ static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, i
   if ((Cin * H * W) % 4 != 0 || x_bstride % 4 != 0) return false;      // 16-byte bulk copies of x0
   p = Plan{};
   p.B = B; p.Cin = Cin; p.Ch = Ch; p.Cout = Cout; p.H = H; p.W = W; p.KH = KH; p.KW = KW; p.x_bstride = x_bstride;
-  p.kind = kind; p.rb = rb;
+  p.kind = kind; p.rb = rb; p.occ = occ;
+  sms *= occ;                                                            // resident CTA slots
+  const int tmem_cols = 512 / occ;
   p.P = (Ch + CPR - 1) / CPR; p.KS1 = (Cin + KE - 1) / KE; p.N2 = Ch; p.N3 = (Cout + 15) / 16 * 16;
   p.HP = H + KH - 1; p.WP = W + KW - 1;
   p.stage_bytes = 2 * p.N2 * rb;
   const int HW = H * W;
-  const int kSmemMax = 227 * 1024 - 1024;                               // minus alignment slack
+  // dynamic shared memory per CTA: 227 KB alone; two co-resident CTAs share the SM's 228 KB less 1 KB reserved per CTA; minus alignment slack
+  const int kSmemMax = (occ == 1 ? 227 * 1024 : (228 * 1024) / 2 - 1024) - 1024;
   const int bias_bytes = (2 * p.N2 + p.N3) * 4, bar_bytes = BAR_COUNT * 8 + 16;
   double best_cost = 1e30; Plan best{}; bool found = false;
   for (int seg = 0; seg <= 1; ++seg) {
@@ -577,7 +673,7 @@ static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, i
         q.T2 = (mmax + 127) / 128; q.NG = q.T2 * 16;
       }
       q.T1 = (q.R + 127) / 128;
-      if (q.T1 * 2 * q.N2 > 512 || q.T2 * 2 * q.N2 > 512 || q.T2 * 2 * q.N3 > 512) break;
+      if (q.T1 * 2 * q.N2 > tmem_cols || q.T2 * 2 * q.N2 > tmem_cols || q.T2 * 2 * q.N3 > tmem_cols) break;
       q.region_bytes = ((q.R + 15) / 16 * 16) * rb;          // multiple of 1024 bytes: every region starts on a swizzle-atom boundary
       // operand rows the MMAs may touch (garbage rows included) must stay inside this CTA's shared memory
       q.off_ring = 2 * q.P * q.region_bytes;
@@ -586,6 +682,9 @@ static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, i
       const int fixed = q.off_ring + xbytes + bias_bytes + tab_bytes + bar_bytes + 256;
       int nst = (kSmemMax - fixed) / q.stage_bytes;
       if (nst < 2) break;
+      const int nchunks = 1 + KH * KW * q.P + q.P;
+      q.resident = (nchunks <= kMaxStages && nst >= nchunks && env_int("CFPP_TC_RESIDENT", 1)) ? 1 : 0;
+      if (q.resident) nst = nchunks;
       if (nst > kMaxStages) nst = kMaxStages;
       q.nstages = nst;
       const int reach1 = q.T1 * 128 * rb;                                                     // stage 1 / 3 tiles
@@ -603,11 +702,22 @@ static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, i
       const int waves = (q.ntiles + sms - 1) / sms;
       const double imbalance = (double)(waves * sms) / (double)q.ntiles;
       const double cost = waste * (q.ntiles >= sms ? imbalance : 1.0) * (1.0 + 0.02 / S);
-      if (cost < best_cost - 1e-9) { best_cost = cost; best = q; found = true; }
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = q; found = true; waste_out = waste; }
     }
   }
   if (found) p = best;
   return found;
+}
+
+// CFPP_TC_OCC = 1 / 2 forces the residency; default: two CTAs per SM when such a plan exists and wastes at most 30 % more MMA rows
+static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, long long x_bstride, int sms) {
+  const int force = env_int("CFPP_TC_OCC", 0);
+  Plan p1, p2; double w1 = 0, w2 = 0;
+  const bool ok1 = force != 2 && make_plan_occ(p1, w1, 1, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, sms);
+  const bool ok2 = force != 1 && make_plan_occ(p2, w2, 2, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, sms);
+  if (ok2 && (!ok1 || w2 <= 1.3 * w1)) { p = p2; return true; }
+  if (ok1) { p = p1; return true; }
+  return false;
 }
 
 static Plan g_last_plan;
@@ -655,29 +765,35 @@ extern "C" int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h
   const int P_ = p.P;
   const long long pack_bytes = (long long)(1 + KH * KW * P_ + P_) * (2 * Ch * p.rb);
   tc::Args a{x, h, (const uint8_t*)wpack, b1, b2, b3, bias1_b, pack_bytes, tc::env_int("CFPP_TC_REPL", 1), tc::g_prof};
-  const int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
+  const int slots = num_sms() * p.occ;
+  const int grid = p.ntiles < slots ? p.ntiles : slots;
   cudaStream_t st = (cudaStream_t)stream;
   using KernelFn = void (*)(const tc::Plan, const tc::Args);
-  static const KernelFn kernels[8] = {
-      tc::conv_cond_tc_kernel<false, false, false>, tc::conv_cond_tc_kernel<false, false, true>,
-      tc::conv_cond_tc_kernel<false, true, false>,  tc::conv_cond_tc_kernel<false, true, true>,
-      tc::conv_cond_tc_kernel<true, false, false>,  tc::conv_cond_tc_kernel<true, false, true>,
-      tc::conv_cond_tc_kernel<true, true, false>,   tc::conv_cond_tc_kernel<true, true, true>};
+  static const KernelFn kernels[16] = {
+      tc::conv_cond_tc_kernel<false, false, false, 1>, tc::conv_cond_tc_kernel<false, false, true, 1>,
+      tc::conv_cond_tc_kernel<false, true, false, 1>,  tc::conv_cond_tc_kernel<false, true, true, 1>,
+      tc::conv_cond_tc_kernel<true, false, false, 1>,  tc::conv_cond_tc_kernel<true, false, true, 1>,
+      tc::conv_cond_tc_kernel<true, true, false, 1>,   tc::conv_cond_tc_kernel<true, true, true, 1>,
+      tc::conv_cond_tc_kernel<false, false, false, 2>, tc::conv_cond_tc_kernel<false, false, true, 2>,
+      tc::conv_cond_tc_kernel<false, true, false, 2>,  tc::conv_cond_tc_kernel<false, true, true, 2>,
+      tc::conv_cond_tc_kernel<true, false, false, 2>,  tc::conv_cond_tc_kernel<true, false, true, 2>,
+      tc::conv_cond_tc_kernel<true, true, false, 2>,   tc::conv_cond_tc_kernel<true, true, true, 2>};
   static bool attr_set = false;
   if (!attr_set) {
-    for (KernelFn k : kernels) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    for (int i = 0; i < 16; ++i) cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, i < 8 ? 227 * 1024 : (228 * 1024) / 2 - 1024);
     attr_set = true;
   }
-  kernels[(p.seg ? 4 : 0) | (a.prof != nullptr ? 2 : 0) | (p.kind ? 1 : 0)]<<<grid, tc::kThreads, p.smem_bytes, st>>>(p, a);
+  kernels[(p.occ == 2 ? 8 : 0) | (p.seg ? 4 : 0) | (a.prof != nullptr ? 2 : 0) | (p.kind ? 1 : 0)]<<<grid, tc::cta_threads(p.occ), p.smem_bytes, st>>>(p, a);
   return check_launch("conv_cond_tc_fwd");
 }
 
 /* operand kind of this process: 1 = scaled fp16 pairs (default), 0 = tf32 pairs (environment CFPP_TC_KIND=tf32) */
 extern "C" int cfpp_conv_cond_tc_kind(void) { return tc::tc_kind(); }
 
-/* geometry of the last launch, for tests / bench reporting: {seg, S, R, T1, T2, nstages, smem_bytes, ntiles} */
+/* geometry of the last launch, for tests / bench reporting: {seg, S, R, T1, T2, nstages, smem_bytes, ntiles, CTAs per SM, row bytes} */
 extern "C" void cfpp_conv_cond_tc_last_plan(int* out8) {
   const tc::Plan& p = tc::g_last_plan;
+  out8[8] = p.occ; out8[9] = p.rb;
   out8[0] = p.seg; out8[1] = p.S; out8[2] = p.R; out8[3] = p.T1; out8[4] = p.T2; out8[5] = p.nstages; out8[6] = p.smem_bytes; out8[7] = p.ntiles;
 }
 

@@ -298,9 +298,9 @@ def conv_cond_tc(x, cin, wpack, b1, b2, b3, ch, H, W, KH, KW, cout, bias1_b=None
 
 
 def conv_cond_tc_last_plan():
-    out = (_cabi.i32 * 8)()
+    out = (_cabi.i32 * 10)()
     lib().cfpp_conv_cond_tc_last_plan(out)
-    return dict(zip(('seg', 'S', 'R', 'T1', 'T2', 'nstages', 'smem_bytes', 'ntiles'), list(out)))
+    return dict(zip(('seg', 'S', 'R', 'T1', 'T2', 'nstages', 'smem_bytes', 'ntiles', 'occ', 'row_bytes'), list(out)))
 
 
 def vit_cond(x, desc: _cabi.VitDesc, cout, extra=None):

@@ -112,8 +112,8 @@ int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h, const voi
  * CFPP_TC_KIND=tf32).  Packed weights are specific to the kind they were packed under. */
 int cfpp_conv_cond_tc_kind(void);
 /* geometry of the last cfpp_conv_cond_tc_fwd launch (tests / bench): {segment layout, samples per tile, stored rows, M-tiles of
- * stage 1, M-tiles of stages 2-3, ring stages, shared-memory bytes, tiles} */
-void cfpp_conv_cond_tc_last_plan(int* out8);
+ * stage 1, M-tiles of stages 2-3, ring stages, shared-memory bytes, tiles, CTAs resident per SM, operand row bytes} (10 ints) */
+void cfpp_conv_cond_tc_last_plan(int* out10);
 /* debug instrumentation: device array of 12 int64 cycle counters that CTA 0 accumulates over its tiles; NULL = off.
  * epilogue thread 0: {wait x0, x0 transform, wait stage-1 MMAs, epilogue 1, wait stage-2 MMAs, epilogue 2, wait stage-3 MMAs,
  * epilogue 3}; MMA thread: {wait weight chunk, issue, wait operands, spare} */

@@ -37,7 +37,8 @@ for B, C, H, W in LEVELS:
     torch.cuda.synchronize()
     _cabi.lib().cfpp_conv_cond_tc_set_profile(None)
     pr = prof.cpu().tolist()
-    ntile0 = (plan['ntiles'] + 147) // 148
+    slots = 148 * plan['occ']
+    ntile0 = (plan['ntiles'] + slots - 1) // slots
     names = ['wait_x0', 'xform', 'wait_S1', 'epi1', 'wait_S2', 'epi2', 'wait_S3', 'epi3', 'mma_wait_w', 'mma_issue', 'mma_wait_ops', 'spare']
     print(json.dumps({'shape': [B, C, H, W], 'tc_ms': round(t_tc, 4), 'tc_TFLOPs': round(flops / t_tc / 1e9, 1), 'fma_ms': round(t_fma, 4),
                       'fma_TFLOPs': round(flops / t_fma / 1e9, 1), 'plan': plan,
