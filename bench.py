@@ -169,11 +169,16 @@ def main():
     l0 = _cabi.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    prof_range = os.environ.get('CFPP_PROFILE_RANGE') == '1'       # ncu --profile-from-start off: capture the timed steps only
+    if prof_range:
+        torch.cuda.profiler.start()
     ev0.record()
     for i in range(a.steps):
         step(i)
     ev1.record()
     barrier()
+    if prof_range:
+        torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = _cabi.launch_count() - l0 if graphed is None else graphed.launches_per_replay(*devb[0]) * a.steps
     clocks = sampler.summary()

@@ -71,6 +71,10 @@ _SIGNATURES = {
                                       i32, i32, i32, i32, i32, vp]),
     'cfpp_gmm_ctxtab_workspace_bytes': (i64, [i32, i32, i32, i32, i32, i32, C.POINTER(i32)]),
     'cfpp_gmm_workspace_floats': (i64, [i32, i32, i32, i32]),
+    'cfpp_gmm_tile_table_bytes': (i64, [i32, i32, i32, i32, i32]),
+    'cfpp_gmm_tile_prepare': (i32, [vp, vp, vp, vp, i32, i32, i32, vp, i32, i32, i32, i32, vp]),
+    'cfpp_gmm_tile_workspace_bytes': (i64, [i32, i32, i32, i32, i32, i32]),
+    'cfpp_gmm_tile_logprob': (i32, [vp, i64, vp, vp, i32, C.POINTER(i32), vp, i32, i32, vp, f32, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
     'cfpp_ctx_encode': (i32, [vp, vp, vp, vp, C.POINTER(EncDesc), i32, i32, vp]),
     'cfpp_ctx_encode_batch': (i32, [vp, vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i32, vp]),
     'cfpp_embed_lookup': (i32, [vp, C.POINTER(vp), i32, i32, vp, i32, vp]),

@@ -780,7 +780,10 @@ extern "C" int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h
       tc::conv_cond_tc_kernel<true, true, false, 2>,   tc::conv_cond_tc_kernel<true, true, true, 2>};
   static bool attr_set = false;
   if (!attr_set) {
-    for (int i = 0; i < 16; ++i) cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, i < 8 ? 227 * 1024 : (228 * 1024) / 2 - 1024);
+    for (int i = 0; i < 16; ++i) {
+      cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, i < 8 ? 227 * 1024 : (228 * 1024) / 2 - 1024);
+      cudaFuncSetAttribute(kernels[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     attr_set = true;
   }
   kernels[(p.occ == 2 ? 8 : 0) | (p.seg ? 4 : 0) | (a.prof != nullptr ? 2 : 0) | (p.kind ? 1 : 0)]<<<grid, tc::cta_threads(p.occ), p.smem_bytes, st>>>(p, a);

@@ -206,6 +206,24 @@ class EncoderBatch:
                         return False
         return True
 
+    def _draw_all(self, B, widths, device):
+        """Noise of every member in layer order.  With a replayed tape (tests) each member draws on its own, with the reference's
+        shapes; from torch's generator the normal and the uniform draws are each ONE call cut into per-member (B, width) blocks
+        (same distribution, ~40 launches fewer per forward)."""
+        if rng._source is not None:
+            return [f._draw(B, w, device) for (_, f), w in zip(self.members, widths)]
+        kinds = ['none' if f.surj.kind == 'eyesample' else ('rand' if f.surj.kind == 'uniform' else 'randn') for _, f in self.members]
+        out = [None] * len(kinds)
+        for kind, fn in (('rand', rng.rand), ('randn', rng.randn)):
+            idx = [i for i, k in enumerate(kinds) if k == kind]
+            if not idx:
+                continue
+            total = sum(B * widths[i] for i in idx)
+            flat, off = fn((total,), device), 0
+            for i in idx:
+                out[i] = flat[off: off + B * widths[i]].view(B, widths[i]); off += B * widths[i]
+        return out
+
     def run(self, context):
         if context.dim() != 2:
             raise ValueError('The input must have two dimensions')
@@ -217,7 +235,7 @@ class EncoderBatch:
             blob = bytearray(b''.join(bytes(d) for d in descs))
             self._dev = torch.frombuffer(blob, dtype=torch.uint8).clone().to(context.device)
             self._key, self._keep = key, descs
-        noises = [f._draw(B, w, context.device) for (_, f), w in zip(self.members, widths)]
+        noises = self._draw_all(B, widths, context.device)
         step = _cabi.MAX_ENC_BATCH
         dsize = ctypes.sizeof(_cabi.EncDesc)
         for i0 in range(0, len(descs), step):

@@ -6,7 +6,7 @@ import torch.nn as nn
 
 from ... import ops, rng
 from ..context import ContextPlan
-from ..flowlayer import inference_only
+from ..flowlayer import PackCache, inference_only
 
 
 __all__ = ['StandardNormal', 'GaussianMixtureDistribution', 'ConditionalGaussianDistribution']
@@ -57,23 +57,40 @@ class GaussianMixtureDistribution(nn.Module):
                 for p in (self.mG, self.sG, self.wG):
                     p.requires_grad_(False)
         self._plan = ContextPlan()
+        self._tables = PackCache()
 
     def log_prob(self, input, context=None):
         inference_only(self.mG); inference_only(input)
         H, W = input.shape[2], input.shape[3]
         if isinstance(context, list):
             context = context[0]
+        B = input.shape[0]
         if self.context_net:
             from .._encoder_desc import EncoderBatch
             fused = self._plan.fused_for(self.context_net) if self._plan.preset is None else None
             if fused is not None and EncoderBatch.is_lookup(fused) and context.dim() == 2:
-                # embed + eyesample (model.py:157,162): offsets are a table lookup with logp_c = 0 -> bucketed per-context tables
+                # embed + eyesample (model.py:157,162): offsets are a table lookup with logp_c = 0
                 cards = [int(e.num_embeddings) for e in fused.emb._embeddings]
-                out = ops.gmm_logprob_ctxtab(input, self.mG, self.sG, self.wG, context, cards, fused.emb.tables())
+                tables = fused.emb.tables()
+                MKD = self.M * self.K * self.D
+                n = len(cards)
+                if n in (1, 2) and tables[0].shape[1] * n == 2 * MKD:
+                    sf = n - 1                                              # 'b (p m k d)': the scale half comes from the last feature
+                    soff = 0 if n == 2 else MKD
+                    nkeys = cards[0] * (cards[1] if n == 2 else 1)
+                    if B >= 32 * nkeys and nkeys <= 4096:                   # context buckets fill the 64-sample tiles at least half
+                        tab = self._tables.get('ctx', [self.mG, self.sG, self.wG, tables[sf]],
+                                               lambda: ops.gmm_tile_table(self.mG, self.sG, self.wG, tables[sf], soff))
+                        if tab is not None:
+                            return ops.gmm_tile_logprob(input, tab, self.M, self.K, context, cards, tables[0], 0)
+                out = ops.gmm_logprob_ctxtab(input, self.mG, self.sG, self.wG, context, cards, tables)
                 if out is not None:
                     return out
             c, logp_c = self._plan.run(self.context_net, context)       # c: 'b (p m k d)'
             return ops.gmm_logprob(input, self.mG, self.sG, self.wG, c, logp_c, float(H * W))
+        tab = self._tables.get('plain', [self.mG, self.sG, self.wG], lambda: ops.gmm_tile_table(self.mG, self.sG, self.wG))
+        if tab is not None and B > 0:
+            return ops.gmm_tile_logprob(input, tab, self.M, self.K)
         return ops.gmm_logprob(input, self.mG, self.sG, self.wG)
 
     def sample(self, n_samples, context=None):

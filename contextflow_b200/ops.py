@@ -350,6 +350,46 @@ def gmm_logprob_ctxtab(x, mG, sG, wG, ctx, cards, tables, logp_scale=0.0):
     return out
 
 
+def gmm_tile_table(mG, sG, wG, scale_table=None, scale_off=0):
+    """(mu, 1/(2 sigma^2)) table of cfpp_gmm_tile_logprob, one per row of scale_table; None when the sizes are unsupported.
+    A function of the parameters only: callers cache it per parameter version."""
+    _need_cuda(mG, sG, wG, scale_table)
+    M, K, D = mG.shape[0], mG.shape[1], mG.shape[2]
+    HW = mG.shape[3] * mG.shape[4]
+    nv = 1 if scale_table is None else scale_table.shape[0]
+    nbytes = int(lib().cfpp_gmm_tile_table_bytes(M, K, D, HW, nv))
+    if nbytes < 0:
+        return None
+    tab = torch.empty(nbytes, device=mG.device, dtype=torch.uint8)
+    st = None if scale_table is None else _f32(scale_table)
+    _call('gmm_tile_prepare', (_p(_f32(mG)), _p(_f32(sG)), _p(_f32(wG)), _p(st), 0 if st is None else st.shape[1], int(scale_off), nv,
+                               _p(tab), M, K, D, HW, _stream()))
+    return tab
+
+
+def gmm_tile_logprob(x, table, M, K, ctx=None, cards=(), mean_table=None, mean_off=0, logp_c=None, logp_scale=0.0):
+    """cards: cardinalities of the 0, 1 or 2 context features; the table must hold cards[-1] scale contexts (1 without context)."""
+    _need_cuda(x, table, ctx, mean_table)
+    xv, bstride = _half_view(x)
+    B, D, HW = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+    n = len(cards)
+    n_keys = 1
+    for c in cards:
+        n_keys *= int(c)
+    out = torch.empty((B, M), device=x.device, dtype=torch.float32)
+    need = int(lib().cfpp_gmm_tile_workspace_bytes(B, M, K, D, HW, n_keys))
+    if need < 0:
+        raise RuntimeError(f'gmm_tile_logprob: {n_keys} context tuples unsupported')
+    ws = torch.empty(max(need, 1), device=x.device, dtype=torch.uint8)
+    mt = None if mean_table is None else _f32(mean_table)
+    carr = (_cabi.i32 * max(n, 1))(*[int(c) for c in cards])
+    _set_work(bytes=4.0 * B * D * HW + 4.0 * B * M, flops=3.0 * B * M * K * D * HW)
+    _call('gmm_tile_logprob', (_p(xv), bstride, _p(table), _p(None if ctx is None else ctx.contiguous()), n, carr,
+                               _p(mt), 0 if mt is None else mt.shape[1], int(mean_off), _p(logp_c), float(logp_scale),
+                               _p(out), _p(ws), need, B, M, K, D, HW, _stream()))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- context
 def embed_lookup(ctx, tables: Sequence[torch.Tensor]):
     _need_cuda(ctx, *tables)

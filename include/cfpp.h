@@ -161,6 +161,25 @@ int cfpp_gmm_logprob_ctxtab(const float* x, int64_t x_bstride, const float* mG, 
 /* bytes of scratch for cfpp_gmm_logprob_ctxtab, or -1 when that context structure is unsupported */
 int64_t cfpp_gmm_ctxtab_workspace_bytes(int B, int M, int K, int D, int HW, int n_ctx, const int* cards);
 
+/* The same density as a register-tiled contraction (csrc/gmm_tile.cu): a tile of 64 samples x all M*K components per CTA, x and an
+ * interleaved (mu, 1/(2 sigma^2)) table streamed through shared memory.  Two calls:
+ *   cfpp_gmm_tile_prepare : builds the table (a function of the parameters only -- cache it per parameter version);
+ *                           scale_table (n_scale_ctx, scale_width) optional: sigma = softplus(sG[m,k,e] + scale_table[v][scale_off + (m*K+k)*D + d])
+ *                           gives one table per distinct scale context v (NULL: n_scale_ctx = 1, no offsets);
+ *   cfpp_gmm_tile_logprob : ctx (B, n_ctx) int64 with n_ctx in {0, 1, 2} and cards (HOST) their cardinalities.  The batch is bucketed by
+ *                           context tuple so that a tile shares one scale context (the LAST feature: the table must have cards[n_ctx-1]
+ *                           scale contexts) and one mean-offset row mean_table[ctx[b,0]][mean_off + (m*K+k)*D + d] (mean_table NULL: none).
+ * For ContextEncoder(contexts,'embed','eyesample') ('b (p m k d)', model.py:157,162): n_ctx == 2 -> means = tables[0], scales = tables[1],
+ * offsets 0; n_ctx == 1 -> both from tables[0]: mean_off 0, scale_off M*K*D.  n_keys = product of cards (<= 4096).
+ * M*K <= 128 (padded to a multiple of 4), K <= 64.  *_bytes return -1 when unsupported. */
+int64_t cfpp_gmm_tile_table_bytes(int M, int K, int D, int HW, int n_scale_ctx);
+int cfpp_gmm_tile_prepare(const float* mG, const float* sG, const float* wG, const float* scale_table, int scale_width,
+                          int scale_off, int n_scale_ctx, void* table, int M, int K, int D, int HW, void* stream);
+int64_t cfpp_gmm_tile_workspace_bytes(int B, int M, int K, int D, int HW, int n_keys);
+int cfpp_gmm_tile_logprob(const float* x, int64_t x_bstride, const void* table, const int64_t* ctx, int n_ctx, const int* cards,
+                          const float* mean_table, int mean_width, int mean_off, const float* logp_c, float logp_scale,
+                          float* out, void* workspace, int64_t workspace_bytes, int B, int M, int K, int D, int HW, void* stream);
+
 /* ---- context encoders -------------------------------------------------------------------------------------- */
 #define CFPP_MAX_CTX 8
 #define CFPP_ENC_MAXC 64

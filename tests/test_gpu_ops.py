@@ -87,7 +87,7 @@ def _gmm_oracle(x, mG, sG, wG, c, M, K):
 
 
 @pytest.mark.parametrize('B,M,K,D,H,W,cards', [(11, 10, 8, 8, 16, 16, [15, 5]), (6, 2, 8, 38, 36, 1, [68]), (19, 1, 8, 26, 8, 1, [7]),
-                                                 (3, 3, 8, 4, 7, 7, [4, 3]), (1, 10, 8, 64, 4, 4, [15, 5])])
+                                                 (3, 3, 8, 4, 7, 7, [4, 3]), (1, 10, 8, 64, 4, 4, [15, 5]), (300, 10, 8, 16, 8, 8, [15, 5]), (150, 5, 3, 6, 5, 3, [9])])
 def test_gmm_all_paths(B, M, K, D, H, W, cards):
     x = synth.uniform('gx', (B, D, H, W)) * 2
     mG, sG, wG = synth.uniform('gm', (M, K, D, H, W)), 1 + 0.3 * synth.uniform('gs', (M, K, D, H, W)), synth.uniform('gw', (M, K))
@@ -112,6 +112,18 @@ def test_gmm_all_paths(B, M, K, D, H, W, cards):
     wide = torch.cat([torch.zeros_like(x), x], 1).to(dev)
     got3 = ops.gmm_logprob(wide[:, D:], cu(mG), cu(sG), cu(wG))
     assert torch.equal(got3, got0)
+    # register-tiled kernel (csrc/gmm_tile.cu): no context, bucketed scale context + per-sample mean offsets, strided view
+    tab0 = ops.gmm_tile_table(cu(mG), cu(sG), cu(wG))
+    assert tab0 is not None
+    assert_close(ops.gmm_tile_logprob(cu(x), tab0, M, K).cpu().numpy(), want0.numpy(), L_RTOL, L_ATOL, 'gmm tile no-context')
+    assert_close(ops.gmm_tile_logprob(wide[:, D:], tab0, M, K).cpu().numpy(), want0.numpy(), L_RTOL, L_ATOL, 'gmm tile strided view')
+    sf, soff = n - 1, (0 if n == 2 else M * K * D)
+    tab1 = ops.gmm_tile_table(cu(mG), cu(sG), cu(wG), cu(tabs[sf]), soff)
+    got4 = ops.gmm_tile_logprob(cu(x), tab1, M, K, cu(ctx), cards, cu(tabs[0]), 0)
+    assert_close(got4.cpu().numpy(), want1.numpy(), L_RTOL, L_ATOL, 'gmm tile context tables')
+    if (D * H * W) % 4 == 0:                                      # misaligned view: element-wise cp.async path
+        flat = torch.zeros(B * D * H * W + 1, device=dev); flat[1:] = cu(x).flatten()
+        assert_close(ops.gmm_tile_logprob(flat[1:].view(B, D, H, W), tab0, M, K).cpu().numpy(), want0.numpy(), L_RTOL, L_ATOL, 'gmm tile misaligned x')
 
 
 def test_actnorm_stats_and_modes():
