@@ -1,5 +1,6 @@
 // Invertible 1x1 convolution (shared or per-sample weights), ActNorm, their fusion, slogdet and the ActNorm
 // data-dependent initialisation statistics.   Reference: layers/conv1x1.py:28-57, layers/actnorm.py:28-60.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cfpp {
@@ -315,6 +316,10 @@ __global__ void actnorm_stats_kernel(const float* __restrict__ x, float* __restr
 }  // namespace cfpp
 using namespace cfpp;
 
+int cfpp_conv1x1_rt_launch(const float* x, float* z, float* ldj, const float* NN, const float* logabsdet, const float* c, const float* logp_c,
+                           int contextflow, const float* an_t, const float* an_logs, int an_stride, const float* an_logp_c, float an_logp_scale,
+                           int B, int D, int HW, cudaStream_t st);
+
 extern "C" int cfpp_slogdet(const float* A, int D, float* logabsdet, void* stream) {
   CFPP_REQUIRE(D >= 1 && D <= 128, "slogdet: D=%d outside [1,128]", D);
   static bool attr_set = false;
@@ -333,6 +338,18 @@ extern "C" int cfpp_conv1x1_fwd(const float* x, float* z, float* ldj, const floa
   if (B <= 0) return CFPP_OK;
   Conv1x1Args a{x, z, ldj, NN, logabsdet, c, logp_c, contextflow, an_t, an_logs, an_per_sample, an_logp_c, an_logp_scale, B, D, HW};
   a.an_stride = an_per_sample == 0 ? 0 : (an_per_sample == 1 ? D : 2 * D);
+  {   // register-tiled kernel (conv1x1_rt.cu) whenever its tile fits; CFPP_C1X1=col forces the column-per-thread kernel below
+    static int force_col = -1;
+    if (force_col < 0) { const char* v = getenv("CFPP_C1X1"); force_col = (v && v[0] == 'c') ? 1 : 0; }
+    // measured on B200 (B = 8192): shared matrix D=16/32/64 rt 80/57/47 us vs column kernel 61/55/59 us; per-sample matrices
+    // rt 100/80/161 us vs 72/86/148 us -- the per-sample assembly of W from c dominates both; rt is used where it wins
+    const bool use_rt = c ? (D > 16 && D <= 32) : (D > 32);
+    if (!force_col && use_rt) {
+      const int rc = cfpp_conv1x1_rt_launch(x, z, ldj, NN, logabsdet, c, logp_c, contextflow, an_t, an_logs, a.an_stride, an_logp_c, an_logp_scale,
+                                            B, D, HW, (cudaStream_t)stream);
+      if (rc != CFPP_ERR_UNSUPPORTED) return rc;
+    }
+  }
   const int DT = D <= 16 ? 16 : D <= 32 ? 32 : D <= 64 ? 64 : D <= 96 ? 96 : 128;
   const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(z)) & 15) == 0;
   int PX = DT == 16 ? 4 : DT == 32 ? 2 : 1;                 // DT * PX = 64 input registers per thread
