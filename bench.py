@@ -23,8 +23,8 @@ REF_BATCH = {'cfg1': 256, 'cfg2': 128, 'cfg3': 32, 'cfg4': 4096}
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=0, help='samples per GPU per step (0 = workload default)')
@@ -51,7 +51,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(',')])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         self.stop_flag.set()
@@ -196,14 +196,23 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
 
-    # end to end through the public API with host buffers (pinned H2D of x, ctx; D2H of the log-probs), timed on the host clock
-    out_host = torch.empty((B * world if rank == 0 else B, M), dtype=torch.float32).pin_memory()
-    for i in range(2):
-        step_e2e(i, out_host)
+    # end to end through the public API with host buffers (pinned H2D of x, ctx every step; D2H of every step's log-probs), timed on
+    # the host clock.  Graph mode uses GraphedLogProb.stream: the copy of batch i+1 overlaps the replay of batch i.
+    nout = B * world if rank == 0 else B
+    outs_host = [torch.empty((nout, M), dtype=torch.float32).pin_memory() for _ in range(min(a.steps, 4))]
+    gather = (lambda lp: sharder.gather(lp, B * world))
+
+    def e2e_pass(n):
+        if graphed is not None:
+            with torch.no_grad():
+                graphed.stream((host[i % NBUF] for i in range(n)), [outs_host[i % len(outs_host)] for i in range(n)], post=gather if world > 1 else None)
+        else:
+            for i in range(n):
+                step_e2e(i, outs_host[i % len(outs_host)])
+    e2e_pass(2)
     barrier()
     t0 = time.perf_counter()
-    for i in range(a.steps):
-        step_e2e(i, out_host)
+    e2e_pass(a.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -249,7 +258,8 @@ def main():
                 'config': {'workload': f'{workload}: {WORKLOADS[workload]}', 'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': f'dp{world} (batch-sharded, final all-gather of log-probs)',
                            'l2_policy': f'{NBUF} rotating input batches; per-layer working set {12 * B * C * H * W / 1e6:.0f} MB > 126 MB L2', 'weights': 'synthetic fill (synth.fill_state)',
                            'launch': 'eager (one Python call per kernel)' if graphed is None else 'CUDA graph replay of the whole log_prob (contextflow_b200/graphed.py)',
-                           'kernel_timing': 'per-launch CUDA events in an eager pass over the same steps right after the timed region'},
+                           'kernel_timing': 'per-launch CUDA events in an eager pass over the same steps right after the timed region',
+                           'e2e_mode': 'per-step blocking copies' if graphed is None else 'GraphedLogProb.stream: pinned H2D of batch i+1 on a copy stream overlaps the replay of batch i; D2H of every result'},
                 'clocks': clocks, 'gpu_launches': launches,
                 'e2e': {'value': world * B * a.steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': x0.numel() * 4 + c0.numel() * 8, 'd2h_bytes_per_step': B * world * M * 4},
                 'roofline': roof, 'roofline_coupling': roof_c, 'kernels': kernels}

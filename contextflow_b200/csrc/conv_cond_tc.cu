@@ -68,21 +68,25 @@ __host__ __device__ __forceinline__ uint32_t row_off(int row, int chunk, int rb)
 __device__ __forceinline__ uint32_t sw128(int row, int k) { return row * 128 + ((((k >> 2) ^ row) & 7) << 4) + ((k & 3) << 2); }
 __device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
-// (hi, lo') fp16 pair of two values, packed as two half2 words: hi = rn(v) saturated to the finite range, lo' = rn((v - hi) * 2^11)
+// (hi, lo') fp16 pair of two values, packed as two half2 words.  hi = v truncated to 11 significant bits (a mask: exactly
+// representable in fp16 over its normal range, so the conversion is exact and v - hi needs no conversion back), lo' = rn((v - hi) * 2^11);
+// saturated to the finite fp16 range.  NONNEG: the value is known to be >= 0 (after ReLU), one clamp less.  5 instructions per element.
+template <bool NONNEG>
 __device__ __forceinline__ void f16_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn((a - hf.x) * kLoScale, (b - hf.y) * kLoScale);
+  a = fminf(a, 65504.f); b = fminf(b, 65504.f);
+  if (!NONNEG) { a = fmaxf(a, -65504.f); b = fmaxf(b, -65504.f); }
+  const float ha = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), hb = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+  const __half2 h = __floats2half2_rn(ha, hb);
+  const __half2 l = __floats2half2_rn((a - ha) * kLoScale, (b - hb) * kLoScale);
   hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 // Store 8 consecutive channels (col8 = first channel within the panel, multiple of 8) of operand row `row` as (hi, lo) operands.
-template <bool F16>
+template <bool F16, bool NONNEG = false>
 __device__ __forceinline__ void store_group8(uint8_t* ph, uint8_t* pl, int row, int col8, const float (&v)[8], int rb) {
   if (F16) {
     uint32_t h[4], l[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) f16_split2(v[2 * q], v[2 * q + 1], h[q], l[q]);
+    for (int q = 0; q < 4; ++q) f16_split2<NONNEG>(v[2 * q], v[2 * q + 1], h[q], l[q]);
     const uint32_t off = row_off(row, col8 >> 3, rb);
     *reinterpret_cast<uint4*>(ph + off) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(pl + off) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -212,20 +216,20 @@ __device__ __forceinline__ void store_split16(const float (&v)[16], const float 
       const float4 b = *reinterpret_cast<const float4*>(bias + 8 * g + 4 * q);
       const int i = 8 * g + 4 * q;
       if (F16) {
-        o[4 * q + 0] = fmaxf(fmaf(u[i + 0], kLoInv, v[i + 0]) + b.x, 0.f); o[4 * q + 1] = fmaxf(fmaf(u[i + 1], kLoInv, v[i + 1]) + b.y, 0.f);
-        o[4 * q + 2] = fmaxf(fmaf(u[i + 2], kLoInv, v[i + 2]) + b.z, 0.f); o[4 * q + 3] = fmaxf(fmaf(u[i + 3], kLoInv, v[i + 3]) + b.w, 0.f);
+        o[4 * q + 0] = fmaxf(fmaf(u[i + 0], kLoInv, v[i + 0] + b.x), 0.f); o[4 * q + 1] = fmaxf(fmaf(u[i + 1], kLoInv, v[i + 1] + b.y), 0.f);
+        o[4 * q + 2] = fmaxf(fmaf(u[i + 2], kLoInv, v[i + 2] + b.z), 0.f); o[4 * q + 3] = fmaxf(fmaf(u[i + 3], kLoInv, v[i + 3] + b.w), 0.f);
       } else {
         o[4 * q + 0] = fmaxf(v[i + 0] + u[i + 0] + b.x, 0.f); o[4 * q + 1] = fmaxf(v[i + 1] + u[i + 1] + b.y, 0.f);
         o[4 * q + 2] = fmaxf(v[i + 2] + u[i + 2] + b.z, 0.f); o[4 * q + 3] = fmaxf(v[i + 3] + u[i + 3] + b.w, 0.f);
       }
     }
-    store_group8<F16>(ph, pl, row, col + 8 * g, o, rb);
+    store_group8<F16, true>(ph, pl, row, col + 8 * g, o, rb);
   }
 }
 template <bool F16, bool WIDE>
 __device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, int c0, const float* __restrict__ bias, uint8_t* a_hi, uint8_t* a_lo,
                                                     int region_bytes, int row, bool write, int rb) {
-  const int CPR = F16 ? rb >> 1 : 32;                         // channels per operand row
+  const int cps = F16 ? (rb == 64 ? 5 : 6) : 5;               // log2(channels per operand row)
   float v0[16], u0[16], v1[16], u1[16];
   const bool two = WIDE && c0 + 16 < N;                       // warp-uniform; narrow items (16 columns) halve the live registers
   tmem_ld16(taddr + c0, v0);
@@ -233,10 +237,11 @@ __device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, int c
   if (two) { tmem_ld16(taddr + c0 + 16, v1); tmem_ld16(taddr + N + c0 + 16, u1); }
   tmem_ld_wait();
   if (write) {
-    uint8_t* ph = a_hi + (c0 / CPR) * region_bytes;
-    uint8_t* pl = a_lo + (c0 / CPR) * region_bytes;
-    store_split16<F16>(v0, u0, bias + c0, ph, pl, row, c0 % CPR, rb);
-    if (two) store_split16<F16>(v1, u1, bias + c0 + 16, ph, pl, row, (c0 % CPR) + 16, rb);
+    const int pn = c0 >> cps, cc = c0 & ((1 << cps) - 1);
+    uint8_t* ph = a_hi + pn * region_bytes;
+    uint8_t* pl = a_lo + pn * region_bytes;
+    store_split16<F16>(v0, u0, bias + c0, ph, pl, row, cc, rb);
+    if (two) store_split16<F16>(v1, u1, bias + c0 + 16, ph, pl, row, cc + 16, rb);
   }
 }
 
@@ -528,8 +533,9 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
       mbar_wait(bar(BAR_ACC1), ph);
       tc_fence_after();
       tick(2);
-      for (int item = grp; item < p.T1 * nc2; item += kEpiGroups) {
-        const int t = item / nc2, c0 = (item - t * nc2) * kIW;
+      for (int item = grp, t = 0, ci = grp; item < p.T1 * nc2; item += kEpiGroups, ci += kEpiGroups) {
+        while (ci >= nc2) { ci -= nc2; ++t; }                  // item -> (M-tile t, column item ci) without a division
+        const int c0 = ci * kIW;
         const int r = t * 128 + row_in_tile;
         const float* bias = sb1;
         if (a.bias1_b != nullptr && r < p.R) bias = a.bias1_b + (size_t)min(b0 + (int)(tab_in[r] >> 24), p.B - 1) * p.Ch;
@@ -543,8 +549,9 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
       mbar_wait(bar(BAR_ACC2), ph);
       tc_fence_after();
       tick(4);
-      for (int item = grp; item < p.T2 * nc2; item += kEpiGroups) {
-        const int t = item / nc2, c0 = (item - t * nc2) * kIW;
+      for (int item = grp, t = 0, ci = grp; item < p.T2 * nc2; item += kEpiGroups, ci += kEpiGroups) {
+        while (ci >= nc2) { ci -= nc2; ++t; }
+        const int c0 = ci * kIW;
         const int m = t * 128 + row_in_tile;
         epilogue_to_operand<F16, kWide>(tmem + lane_base + t * 2 * p.N2, p.N2, c0, sb2, a_hi, a_lo, p.region_bytes, m, (tab_out[m] >> 31) != 0, rb);
       }
@@ -556,8 +563,9 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
       mbar_wait(bar(BAR_ACC3), ph);
       tc_fence_after();
       tick(6);
-      for (int item = grp; item < p.T2 * nc3; item += kEpiGroups) {
-        const int t = item / nc3, c0 = (item - t * nc3) << 4;
+      for (int item = grp, t = 0, ci = grp; item < p.T2 * nc3; item += kEpiGroups, ci += kEpiGroups) {
+        while (ci >= nc3) { ci -= nc3; ++t; }
+        const int c0 = ci << 4;
         const int m = t * 128 + row_in_tile;
         const uint32_t w = tab_out[m];
         const int s = (w >> 24) & 0x7F, y = (w >> 12) & 0xFFF, x = w & 0xFFF;

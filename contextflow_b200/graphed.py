@@ -82,3 +82,42 @@ class GraphedLogProb:
             e.ctx.copy_(ctx, non_blocking=True)
         e.graph.replay()
         return e.out.clone() if clone else e.out
+
+    def stream(self, batches, outs, post=None):
+        """Throughput mode for host-resident data: `batches` yields (x, ctx) pinned host tensors of one shape, `outs[i]` is the
+        pinned host tensor that receives batch i's (B, M) log-probabilities.  The host-to-device copy of batch i+1 runs on a copy
+        stream while the captured graph of batch i replays (two device staging buffers); the device-to-host copy of each result
+        is queued right behind its replay.  Returns after everything has completed.  `post(logp)` (optional) maps the replay's
+        output to the tensor that is copied out (e.g. the all-gather of a sharded batch)."""
+        dev = torch.device('cuda', torch.cuda.current_device())
+        comp = torch.cuda.current_stream(dev)
+        copy_stream = getattr(self, '_copy_stream', None)
+        if copy_stream is None:
+            copy_stream = self._copy_stream = torch.cuda.Stream(dev)
+        e, stage, ready, consumed = None, None, None, None
+        for i, (hx, hc) in enumerate(batches):
+            if e is None:
+                e = self.entry(hx, hc)
+                stage = [(torch.empty_like(e.x), None if e.ctx is None else torch.empty_like(e.ctx)) for _ in range(2)]
+                ready = [torch.cuda.Event() for _ in range(2)]
+                consumed = [torch.cuda.Event() for _ in range(2)]
+                for ev in consumed:
+                    ev.record(comp)
+            k = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[k])              # staging buffer k has been drained into the graph's input
+                stage[k][0].copy_(hx, non_blocking=True)
+                if hc is not None:
+                    stage[k][1].copy_(hc, non_blocking=True)
+                ready[k].record(copy_stream)
+            comp.wait_event(ready[k])
+            e.x.copy_(stage[k][0], non_blocking=True)
+            if hc is not None:
+                e.ctx.copy_(stage[k][1], non_blocking=True)
+            consumed[k].record(comp)
+            e.graph.replay()
+            res = e.out if post is None else post(e.out)
+            outs[i].copy_(res[:outs[i].shape[0]], non_blocking=True)
+        comp.synchronize()
+        return outs
+
