@@ -115,7 +115,13 @@ def main():
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    saved_stdout = None
     if world > 1:
+        # NCCL writes its version banner to stdout at communicator creation: keep this process's stdout for the ONE JSON line by
+        # pointing fd 1 at stderr until the timed runs are over
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=dev)
     B = a.batch or DEFAULT_BATCH[workload]
     conf = synth.CONFIGS[workload]
@@ -220,6 +226,10 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
 
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if rank == 0:
         peaks = {}
         try:
