@@ -253,9 +253,17 @@ def main():
             roof = {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': None, 'peak_source': hbm_src}
         else:
             ach = tv['flops'] / (tv['ms'] / 1e3) / 1e12
-            roof = {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak, 'traffic': None,
-                    'peak_source': 'measured bf16 sustained; ' + ('tcgen05 kind::tf32 with the fp32-faithful 3-product split: the ceiling of this arithmetic is 1/6 of the bf16 peak'
-                                                                  if top == 'conv_cond_tc_fwd' else 'this kernel is an FP32-FMA path')}
+            traffic = None
+            try:                                                   # DRAM bytes of one launch from the committed ncu --set full capture
+                tj = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(top)
+                if tj and tj.get('batch') == B and tj.get('workload') == workload:
+                    traffic = tj['dram_bytes_per_launch']
+            except Exception:
+                pass
+            roof = {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak, 'traffic': traffic,
+                    'peak_source': 'measured bf16 sustained (MEASURED_PEAKS.json); ' +
+                                   ('achieved counts ALGORITHMIC flops: the fp32-faithful fp16-pair arithmetic issues 3 tensor products per algorithmic one, so its ceiling is 1/3 of this peak'
+                                    if top == 'conv_cond_tc_fwd' else 'this kernel is an FP32-FMA path')}
         cv = summ.get('coupling_fwd')
         if cv:
             ach = cv['bytes'] / (cv['ms'] / 1e3) / 1e9
