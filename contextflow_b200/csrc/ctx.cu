@@ -70,18 +70,69 @@ __device__ __forceinline__ void encode_sample(const int64_t* __restrict__ ctx, c
   }
   if (emit_stage == 2) { for (int j = 0; j < C; ++j) co[j] = x[j]; logp_out[b] = logq; return; }
   const int Ch = C / 2, H2 = 2 * C;
+  // One thread evaluates the whole inner flow of its sample; weights are warp-uniform global loads.  A scalar inner product costs two
+  // loads per FMA (weight + activation) and is load-pipe bound, so when C % 4 == 0 the products are blocked by four: one 128-bit
+  // weight load + one activation load per 4 FMAs.
+  const bool v4 = (C & 3) == 0;
   for (int L = 0; L < 2; ++L) {
     const float* NN = d.fc[L];                            // FC: conv1x1.py:80-96 (H=W=1)
-    for (int i = 0; i < C; ++i) {
-      float acc = 0.f;
-      for (int j = 0; j < C; ++j) acc = fmaf(NN[i * C + j], x[j], acc);
-      y[i] = acc;
+    if (v4 && (reinterpret_cast<uintptr_t>(NN) & 15) == 0) {
+      for (int i = 0; i < C; ++i) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float4* row = reinterpret_cast<const float4*>(NN + i * C);
+        for (int j = 0; j < C; j += 4) {
+          const float4 w = __ldg(row + (j >> 2));
+          a0 = fmaf(w.x, x[j], a0); a1 = fmaf(w.y, x[j + 1], a1); a2 = fmaf(w.z, x[j + 2], a2); a3 = fmaf(w.w, x[j + 3], a3);
+        }
+        y[i] = (a0 + a1) + (a2 + a3);
+      }
+    } else {
+      for (int i = 0; i < C; ++i) {
+        float acc = 0.f;
+        for (int j = 0; j < C; ++j) acc = fmaf(NN[i * C + j], x[j], acc);
+        y[i] = acc;
+      }
     }
     logq -= d.fc_logabsdet[L][0];
     if (emit_stage == L) { for (int j = 0; j < C; ++j) co[j] = y[j]; logp_out[b] = 0.f; return; }
     float sl = 0.f;                                       // ActNormFC: actnorm.py:86-102
     for (int i = 0; i < C; ++i) { const float lg = d.an_logs[L][i]; x[i] = (y[i] - d.an_t[L][i]) * expf(-lg); sl += lg; }
     logq -= sl;
+    const bool w4ok = v4 && ((reinterpret_cast<uintptr_t>(d.cw1t[L]) | reinterpret_cast<uintptr_t>(d.cw2t[L]) | reinterpret_cast<uintptr_t>(d.cw3t[L])) & 15) == 0;
+    if (w4ok) {                                           // CouplingFC: coupling.py:80-97, four outputs per pass
+      for (int o = 0; o < H2; o += 4) {
+        float a0 = d.cb1[L][o], a1 = d.cb1[L][o + 1], a2 = d.cb1[L][o + 2], a3 = d.cb1[L][o + 3];
+        for (int k = 0; k < Ch; ++k) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(d.cw1t[L] + k * H2 + o)); const float xk = x[k];
+          a0 = fmaf(xk, w.x, a0); a1 = fmaf(xk, w.y, a1); a2 = fmaf(xk, w.z, a2); a3 = fmaf(xk, w.w, a3);
+        }
+        h1[o] = fmaxf(a0, 0.f); h1[o + 1] = fmaxf(a1, 0.f); h1[o + 2] = fmaxf(a2, 0.f); h1[o + 3] = fmaxf(a3, 0.f);
+      }
+      for (int o = 0; o < H2; o += 4) {
+        float a0 = d.cb2[L][o], a1 = d.cb2[L][o + 1], a2 = d.cb2[L][o + 2], a3 = d.cb2[L][o + 3];
+        for (int k = 0; k < H2; ++k) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(d.cw2t[L] + k * H2 + o)); const float hk = h1[k];
+          a0 = fmaf(hk, w.x, a0); a1 = fmaf(hk, w.y, a1); a2 = fmaf(hk, w.z, a2); a3 = fmaf(hk, w.w, a3);
+        }
+        h2[o] = fmaxf(a0, 0.f); h2[o + 1] = fmaxf(a1, 0.f); h2[o + 2] = fmaxf(a2, 0.f); h2[o + 3] = fmaxf(a3, 0.f);
+      }
+      for (int o = 0; o < C; o += 4) {                    // (t | r) = cb3 + h2 W3, kept in y
+        float a0 = d.cb3[L][o], a1 = d.cb3[L][o + 1], a2 = d.cb3[L][o + 2], a3 = d.cb3[L][o + 3];
+        for (int k = 0; k < H2; ++k) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(d.cw3t[L] + k * C + o)); const float hk = h2[k];
+          a0 = fmaf(hk, w.x, a0); a1 = fmaf(hk, w.y, a1); a2 = fmaf(hk, w.z, a2); a3 = fmaf(hk, w.w, a3);
+        }
+        y[o] = a0; y[o + 1] = a1; y[o + 2] = a2; y[o + 3] = a3;
+      }
+      float ssum = 0.f;
+      for (int o = 0; o < Ch; ++o) {
+        const float ls = 2.0f * tanhf(y[Ch + o] * 0.5f);
+        x[Ch + o] = fmaf(x[Ch + o], expf(ls), y[o]);
+        ssum += ls;
+      }
+      logq -= ssum;
+      continue;
+    }
     for (int o = 0; o < H2; ++o) {                        // CouplingFC: coupling.py:80-97
       float acc = d.cb1[L][o];
       for (int k = 0; k < Ch; ++k) acc = fmaf(x[k], d.cw1t[L][k * H2 + o], acc);
