@@ -61,6 +61,8 @@ _SIGNATURES = {
     'cfpp_conv_cond_tc_pack': (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     'cfpp_conv_cond_tc_supported': (i32, [i32, i32, i32, i32, i32, i32, i32, i32, i64]),
     'cfpp_conv_cond_tc_fwd': (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    'cfpp_conv_cond_tc_coupling_supported': (i32, [i32, i32, i32, i32, i32, i32, i32]),
+    'cfpp_conv_cond_tc_coupling_fwd': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'cfpp_conv_cond_tc_kind': (i32, []),
     'cfpp_conv_cond_tc_last_plan': (None, [C.POINTER(i32)]),
     'cfpp_conv_cond_tc_set_profile': (None, [vp]),

@@ -49,7 +49,7 @@ struct Plan {
   int stage_bytes, nstages, ntiles;
   int resident;                      // 1: nstages == chunks per tile, the weight chunks are loaded once per CTA and never recycled
   int region_bytes;                  // bytes of one (hi|lo, panel) operand region
-  int off_ring, off_stage_x, off_bias, off_tab, off_bar, smem_bytes;   // off_tab: R + T2*128 packed row-decode words
+  int off_ring, off_stage_x, off_bias, off_tab, off_ls, off_bar, smem_bytes;   // off_tab: R + T2*128 packed row-decode words; off_ls: per-row log-scale partials
   long long x_bstride;
 };
 
@@ -111,6 +111,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// shared -> global bulk copy (async proxy), tracked by the issuing thread's bulk group
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -156,6 +162,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {   // one lane of a converged warp (ptxas then knows the region is single-threaded)
   uint32_t pred;
@@ -166,6 +179,8 @@ __device__ __forceinline__ int reflect(int i, int n) { return i < 0 ? -i : (i >=
 
 struct Args {
   const float* x; float* h; const uint8_t* wpack; const float* b1; const float* b2; const float* b3; const float* bias1_b;
+  // fused affine coupling (coupling.py:50-66), z != NULL: h is not written; x must be the full (B, 2 Cin, H, W) tensor
+  float* z; float* ldj; const float* add; const float* logp_c; float logp_scale;
   long long wrepl_stride; int nrepl;   // experiment: weight stream replicas (CTA uses replica blockIdx % nrepl)
   long long* prof;   // optional (debug): 12 phase-cycle counters of CTA 0's epilogue thread 0, see cfpp_conv_cond_tc_set_profile
 };
@@ -288,6 +303,7 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
     const bool ok = decode_out<SEG>(p, m, s_, y_, x_);
     tab_out[m] = ok ? (0x80000000u | ((uint32_t)s_ << 24) | ((uint32_t)y_ << 12) | (uint32_t)x_) : 0u;
   }
+  if (a.z != nullptr) for (int i = tid; i < kEpiGroups * p.T2 * 128; i += kThreads) reinterpret_cast<float*>(base + p.off_ls)[i] = 0.f;
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -513,6 +529,11 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
       if (PROF && prof) tp = clock64();
       mbar_wait(bar(BAR_XFULL), ph);
       tick(0);
+      if (a.z != nullptr && tid == 0) {                        // fused coupling: z[:, :C/2] = x0, straight from the staged copy (contiguous per sample)
+        for (int s = 0; s < nS; ++s)
+          bulk_s2g(a.z + (size_t)(b0 + s) * p.Cout * HW, smem_u32(xstage + (size_t)s * xfloats), (uint32_t)(xfloats * 4));
+        bulk_commit();
+      }
       for (int r = tid; r < p.R; r += kEpiThreads) {
         const uint32_t w = tab_in[r];
         const int s = w >> 24, y = (w >> 12) & 0xFFF, x = w & 0xFFF;
@@ -526,6 +547,7 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
         }
       }
       fence_async_smem();
+      if (a.z != nullptr && tid == 0) bulk_wait_read();        // the staging buffer may be refilled once the bulk store has read it
       mbar_arrive(bar(BAR_XEMPTY));
       mbar_arrive(bar(BAR_AREADY));
       tick(1);
@@ -563,6 +585,68 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
       mbar_wait(bar(BAR_ACC3), ph);
       tc_fence_after();
       tick(6);
+      if (a.z != nullptr) {
+        // ---- fused affine coupling: (t | r) = acc + b3 (+ CN(c)); z0 = x0, z1 = x1 * exp(2 tanh(r / 2)) + t; ldj = sum log-scale ----
+        const int half = p.Cout >> 1, nck = half >> 3;           // items of 8 (t, r) channel pairs; half % 8 == 0 (host)
+        float* lsp = reinterpret_cast<float*>(base + p.off_ls) + grp * (p.T2 * 128);
+        for (int item = grp, t = 0, ci = grp; item < p.T2 * nck; item += kEpiGroups, ci += kEpiGroups) {
+          while (ci >= nck) { ci -= nck; ++t; }
+          const int k0 = ci << 3;
+          const int m = t * 128 + row_in_tile;
+          const uint32_t w = tab_out[m];
+          const int s = (w >> 24) & 0x7F, y = (w >> 12) & 0xFFF, x = w & 0xFFF;
+          const bool valid = (w >> 31) != 0 && s < nS;
+          const size_t bb = (size_t)(b0 + (valid ? s : 0));
+          const int pix = y * p.W + x;
+          const uint32_t taddr = tmem + lane_base + t * 2 * p.N3;
+          float vt[8], ut[8], vr[8], ur[8];
+          tmem_ld8(taddr + k0, vt); tmem_ld8(taddr + p.N3 + k0, ut);
+          tmem_ld8(taddr + half + k0, vr); tmem_ld8(taddr + p.N3 + half + k0, ur);
+          float x1v[8];
+          if (valid) {
+            const float* xs1 = a.x + bb * p.x_bstride + (size_t)(half + k0) * HW + pix;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x1v[i] = __ldg(xs1 + (size_t)i * HW);
+          }
+          tmem_ld_wait();
+          if (valid) {
+            float* zd = a.z + (bb * p.Cout + k0) * HW + pix;
+            const float* addb = a.add ? a.add + bb * p.Cout : nullptr;
+            float lsum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float tt = (F16 ? fmaf(ut[i], kLoInv, vt[i]) : vt[i] + ut[i]) + sb3[k0 + i];
+              float rr = (F16 ? fmaf(ur[i], kLoInv, vr[i]) : vr[i] + ur[i]) + sb3[half + k0 + i];
+              if (addb) { tt += __ldg(addb + k0 + i); rr += __ldg(addb + half + k0 + i); }
+              // log_s = 2 tanh(r/2) = 2 (1 - e^-r) / (1 + e^-r) with the SFU exponential (relative error ~2^-21; tanh saturates in fp32 beyond
+              // |r| = 18, the clamp keeps e^-r finite): ~12 instructions instead of ~60 for tanhf + expf on the epilogue warps' critical path
+              const float e = __expf(-fminf(fmaxf(rr, -30.f), 30.f));
+              const float ls = 2.0f * __fdividef(1.0f - e, 1.0f + e);
+              zd[(size_t)(half + i) * HW] = fmaf(x1v[i], __expf(ls), tt);
+              lsum += ls;
+            }
+            lsp[m] += lsum;
+          }
+        }
+        tc_fence_before();
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        {   // per-sample sum: one warp per sample, lanes stride over the accumulator rows in a fixed order, then a shuffle tree -- deterministic
+          const float* l0 = reinterpret_cast<const float*>(base + p.off_ls);
+          const int nrows = p.T2 * 128;
+          for (int smp = warp; smp < nS; smp += kEpiWarps) {
+            float acc = 0.f;
+            for (int m = lane; m < nrows; m += 32) {
+              const uint32_t w = tab_out[m];
+              if ((w >> 31) != 0 && (int)((w >> 24) & 0x7F) == smp)
+                for (int g2 = 0; g2 < kEpiGroups; ++g2) acc += l0[g2 * nrows + m];
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) a.ldj[b0 + smp] = acc + (a.logp_c ? a.logp_scale * a.logp_c[b0 + smp] : 0.f);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        for (int i = tid; i < kEpiGroups * p.T2 * 128; i += kEpiThreads) reinterpret_cast<float*>(base + p.off_ls)[i] = 0.f;
+      } else
       for (int item = grp, t = 0, ci = grp; item < p.T2 * nc3; item += kEpiGroups, ci += kEpiGroups) {
         while (ci >= nc3) { ci -= nc3; ++t; }
         const int c0 = ci << 4;
@@ -687,7 +771,8 @@ static bool make_plan_occ(Plan& p, double& waste_out, int occ, int B, int Cin, i
       q.off_ring = 2 * q.P * q.region_bytes;
       const int xbytes = (S * Cin * HW * 4 + 127) / 128 * 128;
       const int tab_bytes = (q.R + q.T2 * 128) * 4;
-      const int fixed = q.off_ring + xbytes + bias_bytes + tab_bytes + bar_bytes + 256;
+      const int ls_bytes = epi_warps(occ) / 4 * q.T2 * 128 * 4;          // per (epilogue group, accumulator row) log-scale partials of the fused coupling
+      const int fixed = q.off_ring + xbytes + bias_bytes + tab_bytes + ls_bytes + bar_bytes + 256;
       int nst = (kSmemMax - fixed) / q.stage_bytes;
       if (nst < 2) break;
       const int nchunks = 1 + KH * KW * q.P + q.P;
@@ -702,7 +787,8 @@ static bool make_plan_occ(Plan& p, double& waste_out, int occ, int B, int Cin, i
       q.off_stage_x = q.off_ring + nst * q.stage_bytes;
       q.off_bias = q.off_stage_x + xbytes;
       q.off_tab = (q.off_bias + bias_bytes + 15) / 16 * 16;
-      q.off_bar = (q.off_tab + tab_bytes + 15) / 16 * 16;
+      q.off_ls = (q.off_tab + tab_bytes + 15) / 16 * 16;
+      q.off_bar = (q.off_ls + ls_bytes + 15) / 16 * 16;
       q.smem_bytes = q.off_bar + bar_bytes + 1024;
       q.ntiles = (B + S - 1) / S;
       // cost: MMA row-slots per real pixel, plus a penalty when the batch no longer fills the SMs evenly
@@ -759,9 +845,9 @@ extern "C" int cfpp_conv_cond_tc_supported(int B, int Cin, int Ch, int Cout, int
   return B > 0 && tc::make_plan(p, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, num_sms()) ? 1 : 0;
 }
 
-extern "C" int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h, const void* wpack,
-                                     const float* b1, const float* bias1_b, const float* b2, const float* b3,
-                                     int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, void* stream) {
+static int conv_cond_tc_launch(const float* x, int64_t x_bstride, float* h, const void* wpack, const float* b1, const float* bias1_b,
+                               const float* b2, const float* b3, float* z, float* ldj, const float* add, const float* logp_c, float logp_scale,
+                               int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, void* stream) {
   if (B <= 0) return CFPP_OK;
   tc::Plan p;
   if (!tc::make_plan(p, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, num_sms())) {
@@ -772,7 +858,7 @@ extern "C" int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h
   tc::g_last_plan = p;
   const int P_ = p.P;
   const long long pack_bytes = (long long)(1 + KH * KW * P_ + P_) * (2 * Ch * p.rb);
-  tc::Args a{x, h, (const uint8_t*)wpack, b1, b2, b3, bias1_b, pack_bytes, tc::env_int("CFPP_TC_REPL", 1), tc::g_prof};
+  tc::Args a{x, h, (const uint8_t*)wpack, b1, b2, b3, bias1_b, z, ldj, add, logp_c, logp_scale, pack_bytes, tc::env_int("CFPP_TC_REPL", 1), tc::g_prof};
   const int slots = num_sms() * p.occ;
   const int grid = p.ntiles < slots ? p.ntiles : slots;
   cudaStream_t st = (cudaStream_t)stream;
@@ -796,6 +882,25 @@ extern "C" int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h
   }
   kernels[(p.occ == 2 ? 8 : 0) | (p.seg ? 4 : 0) | (a.prof != nullptr ? 2 : 0) | (p.kind ? 1 : 0)]<<<grid, tc::cta_threads(p.occ), p.smem_bytes, st>>>(p, a);
   return check_launch("conv_cond_tc_fwd");
+}
+
+extern "C" int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h, const void* wpack,
+                                     const float* b1, const float* bias1_b, const float* b2, const float* b3,
+                                     int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, void* stream) {
+  return conv_cond_tc_launch(x, x_bstride, h, wpack, b1, bias1_b, b2, b3, nullptr, nullptr, nullptr, nullptr, 0.f, B, Cin, Ch, Cout, H, W, KH, KW, stream);
+}
+
+extern "C" int cfpp_conv_cond_tc_coupling_supported(int B, int C, int Ch, int H, int W, int KH, int KW) {
+  tc::Plan p;
+  return B > 0 && C % 16 == 0 && tc::make_plan(p, B, C / 2, Ch, C, H, W, KH, KW, (long long)C * H * W, num_sms()) ? 1 : 0;
+}
+
+extern "C" int cfpp_conv_cond_tc_coupling_fwd(const float* x, float* z, float* ldj, const void* wpack, const float* b1, const float* bias1_b,
+                                              const float* b2, const float* b3, const float* add, const float* logp_c, float logp_scale,
+                                              int B, int C, int Ch, int H, int W, int KH, int KW, void* stream) {
+  CFPP_REQUIRE(C % 16 == 0, "conv_cond_tc_coupling: C=%d must be a multiple of 16 (8 (t, r) channel pairs per epilogue item)", C);
+  CFPP_REQUIRE(z && ldj, "conv_cond_tc_coupling: null output");
+  return conv_cond_tc_launch(x, (int64_t)C * H * W, nullptr, wpack, b1, bias1_b, b2, b3, z, ldj, add, logp_c, logp_scale, B, C / 2, Ch, C, H, W, KH, KW, stream);
 }
 
 /* operand kind of this process: 1 = scaled fp16 pairs (default), 0 = tf32 pairs (environment CFPP_TC_KIND=tf32) */

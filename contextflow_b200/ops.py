@@ -265,7 +265,8 @@ def conv_cond(x, cin, packed, H, W, KH, KW, cout, bias1_b=None):
 
 
 def conv_cond_tc_mode() -> str:
-    """'auto' (tensor cores whenever the shape has a plan), 'fma' (force the FP32-FMA kernel) -- env CFPP_CONV_COND."""
+    """'auto' (tensor cores whenever the shape has a plan), 'fused' (conditioner + coupling transform in one kernel),
+    'fma' (force the FP32-FMA kernel) -- env CFPP_CONV_COND."""
     import os
     return os.environ.get('CFPP_CONV_COND', 'auto')
 
@@ -295,6 +296,22 @@ def conv_cond_tc(x, cin, wpack, b1, b2, b3, ch, H, W, KH, KW, cout, bias1_b=None
     _call('conv_cond_tc_fwd', (_p(xv), bstride, _p(h), _p(wpack), _p(b1), _p(None if bias1_b is None else _f32(bias1_b)), _p(b2), _p(b3),
                                B, cin, ch, cout, H, W, KH, KW, _stream()))
     return h
+
+
+def conv_cond_tc_coupling(x, wpack, b1, b2, b3, ch, KH, KW, add=None, logp_c=None, logp_scale=0.0, bias1_b=None):
+    """Conditioner + affine coupling in one kernel: (z, ldj), or None (nothing launched) when the shape has no fused plan."""
+    _need_cuda(x, wpack)
+    if x.dtype != torch.float32 or not x.is_contiguous() or x.data_ptr() % 16:
+        return None
+    B, Cc, H, W = x.shape
+    if Cc % 16 or not lib().cfpp_conv_cond_tc_coupling_supported(B, Cc, ch, H, W, KH, KW):
+        return None
+    z = torch.empty_like(x); ldj = torch.empty(B, device=x.device, dtype=torch.float32)
+    cin = Cc // 2
+    _set_work(bytes=8.0 * x.numel(), flops=2.0 * B * H * W * (cin * ch + ch * ch * KH * KW + ch * Cc))
+    _call('conv_cond_tc_coupling_fwd', (_p(x), _p(z), _p(ldj), _p(wpack), _p(b1), _p(None if bias1_b is None else _f32(bias1_b)), _p(b2), _p(b3),
+                                        _p(None if add is None else _f32(add)), _p(logp_c), float(logp_scale), B, Cc, ch, H, W, KH, KW, _stream()))
+    return z, ldj
 
 
 def conv_cond_tc_last_plan():

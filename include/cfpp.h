@@ -107,6 +107,15 @@ int cfpp_conv_cond_tc_supported(int B, int Cin, int Ch, int Cout, int H, int W, 
 int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h, const void* wpack,
                           const float* b1, const float* bias1_b, const float* b2, const float* b3,
                           int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, void* stream);
+/* The conditioner and the affine coupling transform it feeds (coupling.py:39-66) in ONE kernel: the conditioner output h never reaches
+ * HBM.  x, z (B, C, H, W) contiguous; x0 = x[:, :C/2] is the conditioner input, h = NN(x0) (+ add[b, :] per channel: CN(c), additive
+ * contextflow conditioning, coupling.py:45; NULL: none; bias1_b as in cfpp_conv_cond_tc_fwd for the concatenated form);
+ * t = h[:, :C/2], log_s = 2 tanh(h[:, C/2:] / 2); z = cat(x0, x1 * exp(log_s) + t); ldj[b] = sum log_s + logp_scale * logp_c[b].
+ * Weights as packed by cfpp_conv_cond_tc_pack(Cin = C/2, Cout = C).  C % 16 == 0; cfpp_conv_cond_tc_coupling_supported answers for a shape. */
+int cfpp_conv_cond_tc_coupling_supported(int B, int C, int Ch, int H, int W, int KH, int KW);
+int cfpp_conv_cond_tc_coupling_fwd(const float* x, float* z, float* ldj, const void* wpack, const float* b1, const float* bias1_b,
+                                   const float* b2, const float* b3, const float* add, const float* logp_c, float logp_scale,
+                                   int B, int C, int Ch, int H, int W, int KH, int KW, void* stream);
 /* Operand arithmetic of the tensor-core conditioner in this process: 1 (default) = scaled fp16 hi/lo pairs, tcgen05 kind::f16
  * (22+ significand bits, values saturate at +-65504); 0 = tf32 hi/lo pairs, kind::tf32 (fp32 range; environment
  * CFPP_TC_KIND=tf32).  Packed weights are specific to the kind they were packed under. */

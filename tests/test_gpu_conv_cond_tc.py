@@ -113,3 +113,31 @@ def test_tc_unsupported_shapes_fall_back():
     assert lib.cfpp_conv_cond_tc_pack_bytes(38, 152, 76, 3, 1) == -1           # Ch > 128
     assert lib.cfpp_conv_cond_tc_supported(8, 8, 32, 16, 16, 16, 3, 3, 16 * 256) == 1
     assert lib.cfpp_conv_cond_tc_supported(8, 8, 32, 16, 16, 16, 3, 3, 16 * 256 + 2) == 0   # batch stride not 16-byte aligned
+
+
+@pytest.mark.parametrize('B,C,H,W', [(5, 16, 16, 16), (9, 32, 8, 8), (10, 64, 4, 4), (3, 16, 14, 14), (301, 32, 8, 8)])
+@pytest.mark.parametrize('ctx', [False, True])
+def test_tc_fused_coupling_matches_fp64(B, C, H, W, ctx):
+    """cfpp_conv_cond_tc_coupling_fwd: conditioner + affine coupling in one kernel (coupling.py:39-66) against fp64."""
+    cin, ch = C // 2, 2 * C
+    tag = f'tcf{B}.{C}.{H}.{W}'
+    w1, b1, w2, b2, w3, b3 = _weights(tag, cin, ch, C, 3, 3)
+    x = synth.uniform(tag + 'x', (B, C, H, W)) * 2.0 - 1.0
+    add = (synth.uniform(tag + 'a', (B, C)) - 0.5) if ctx else None
+    lp = synth.uniform(tag + 'l', (B,)) if ctx else None
+    pack = ops.conv_cond_tc_pack(w1.to(dev), w2.to(dev), w3.to(dev), cin)
+    out = ops.conv_cond_tc_coupling(x.to(dev), pack, b1.to(dev), b2.to(dev), b3.to(dev), ch, 3, 3,
+                                    add=None if add is None else add.to(dev), logp_c=None if lp is None else lp.to(dev), logp_scale=float(H * W))
+    assert out is not None, 'shape should have a fused plan'
+    z, ldj = out
+    h = _ref64(x[:, :cin], w1, b1, w2, b2, w3, b3)
+    if ctx:
+        h = h + add.double()[:, :, None, None]
+    t, r = h[:, :cin], h[:, cin:]
+    ls = 2 * torch.tanh(r / 2)
+    want_z = torch.cat([x[:, :cin].double(), x[:, cin:].double() * torch.exp(ls) + t], 1)
+    want_l = ls.sum((1, 2, 3)) + (lp.double() * H * W if ctx else 0)
+    assert torch.equal(z[:, :cin].cpu(), x[:, :cin]), 'pass-through half must be bit exact'
+    from tests.helpers import L_ATOL, L_RTOL, Z_ATOL, Z_RTOL, assert_close
+    assert_close(z.cpu().numpy(), want_z.numpy(), Z_RTOL, Z_ATOL * max(1.0, float(want_z.abs().max())), 'fused coupling z')
+    assert_close(ldj.cpu().numpy(), want_l.numpy(), L_RTOL, L_ATOL, 'fused coupling ldj')
