@@ -29,6 +29,9 @@ def parse():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=0, help='samples per GPU per step (0 = workload default)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ref-device', default='cpu', choices=['cpu', 'cuda'],
+                    help='--impl reference only: cpu (the contract: host cores) or cuda (the same torch op sequence run eagerly on the GPU, '
+                         'the "reference torch-on-CUDA" figure of the north star; informative)')
     ap.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying the captured CUDA graph')
     return ap.parse_args()
 
@@ -64,8 +67,10 @@ class ClockSampler(threading.Thread):
                 'samples': len(self.rows), 'power_w_max': max(float(r[2]) for r in self.rows)}
 
 
-def cpu_reference_run(workload, batch, steps, warmup):
-    """The reference algorithm (oracle/ CPU restatement, pinned to the reference by tests/golden) on all host cores."""
+def cpu_reference_run(workload, batch, steps, warmup, device='cpu'):
+    """The reference algorithm (oracle/ restatement of the reference's torch op sequence, pinned to the reference by tests/golden) on all
+    host cores -- or, device='cuda', the same eager op sequence on the GPU."""
+    import contextlib
     import torch
     from contextflow_b200 import synth
     from oracle import flow_oracle as O
@@ -77,19 +82,31 @@ def cpu_reference_run(workload, batch, steps, warmup):
     model = builder.build_named(conf)
     state = model.state_dict(); synth.fill_state(state, 'bench')
     x, ctx = synth.make_inputs(conf, batch, 'bench')
+    on_gpu = device == 'cuda'
+    O.DEVICE = device
+    if on_gpu:
+        state = {k: v.cuda() for k, v in state.items()}
+        x, ctx = x.cuda(), ctx.cuda()
+    dev_ctx = torch.device('cuda') if on_gpu else contextlib.nullcontext()
+    sync = torch.cuda.synchronize if on_gpu else (lambda: None)
+
+    ndev = 'cuda' if on_gpu else 'cpu'
 
     class TorchNoise:
-        def rand(self, shape): return torch.rand(shape)
-        def randn(self, shape): return torch.randn(shape)
-    with torch.no_grad():
+        def rand(self, shape): return torch.rand(shape, device=ndev)
+        def randn(self, shape): return torch.randn(shape, device=ndev)
+    with torch.no_grad(), dev_ctx:
         for _ in range(warmup):
             O.log_prob(stack, state, x, ctx, TorchNoise())
+        sync()
         t0 = time.perf_counter()
         for _ in range(steps):
             O.log_prob(stack, state, x, ctx, TorchNoise())
+        sync()
         dt = time.perf_counter() - t0
+    how = f'torch CUDA eager fp32 on {torch.cuda.get_device_name(0)}' if on_gpu else f'torch CPU fp32, {torch.get_num_threads()} threads'
     return dict(value=batch * steps / dt, unit=UNIT, cores=cores, kind='port',
-                sample=f'{steps} x log_prob of a {batch}-sample {workload} batch, torch CPU fp32, {torch.get_num_threads()} threads'), dt
+                sample=f'{steps} x log_prob of a {batch}-sample {workload} batch, {how}'), dt
 
 
 def main():
@@ -101,10 +118,10 @@ def main():
         if rank != 0:
             return
         B = a.batch or REF_BATCH[workload]
-        base, dt = cpu_reference_run(workload, B, a.steps, max(1, min(a.warmup, 2)))
+        base, dt = cpu_reference_run(workload, B, a.steps, max(1, min(a.warmup, 2)), a.ref_device)
         print(json.dumps({'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'impl': 'reference', 'n_gpus': a.gpus, 'steps': a.steps,
                           'warmup': a.warmup, 'ms_per_step': 1e3 * dt / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                          'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': f'{workload}: {WORKLOADS[workload]}', 'batch_per_step': B},
+                          'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': f'{workload}: {WORKLOADS[workload]}', 'batch_per_step': B, 'ref_device': a.ref_device},
                           'cpu_baseline': base, 'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
         return
 

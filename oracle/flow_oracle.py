@@ -25,6 +25,10 @@ from typing import Callable, Dict, List, Optional
 
 import numpy as np
 import torch
+
+# Where the restatement evaluates.  'cpu' always, except bench.py --impl reference --ref-device cuda, which runs the same eager torch op
+# sequence on the GPU (inside `with torch.device('cuda')`) to time the reference's torch-on-CUDA path.
+DEVICE = 'cpu'
 import torch.nn.functional as F
 
 LOG2PI_HALF = 0.5 * math.log(2 * math.pi)
@@ -125,7 +129,7 @@ class _P:
 
     def __call__(self, key):
         v = self.s[key]
-        return v.detach().to('cpu', self.dt) if v.is_floating_point() else v.detach().to('cpu')
+        return v.detach().to(DEVICE, self.dt) if v.is_floating_point() else v.detach().to(DEVICE)
 
     def has(self, key):
         return key in self.s
@@ -428,9 +432,9 @@ def forward(stack: dict, state: Dict[str, torch.Tensor], x: torch.Tensor, ctx: O
     """Returns (z, logp (B,M)).  `noise` provides rand(shape)/randn(shape) in the reference's draw order."""
     dt = dtype
     P = _P(state, dt)
-    x = x.detach().to('cpu', dt)
+    x = x.detach().to(DEVICE, dt)
     if ctx is not None:
-        ctx = ctx.detach().to('cpu')
+        ctx = ctx.detach().to(DEVICE)
     B, M = x.shape[0], stack['M']
     logdet = torch.zeros(B, M, dtype=dt)
     for lay in stack['layers']:
