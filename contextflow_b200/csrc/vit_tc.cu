@@ -1,0 +1,376 @@
+// SimpleViT conditioner of TransCoupling (layers/simple_vit.py:91-127; heads = 1, dim_head = 64, dim = mlp_dim = T) on the
+// 5th-generation tensor cores, for token widths T <= 64 (the SMAP stack: T = 52, 4 tokens per sample).
+//
+// Mapping.  A CTA owns 128 token rows (128 / n_tok whole samples) = one MMA M-tile; compute thread r (4 warps) IS token row r for the
+// whole network: its residual stream x[T] lives in registers, LayerNorm / GELU / softmax are loops over the thread's own registers
+// (no shuffles, no shared-memory round trips), and after a GEMM the thread reads exactly its own accumulator row from TMEM
+// (tcgen05.ld 32x32b: lane = row).  Every linear layer (patch embedding, q, k, v, out-projection, the two MLP layers) is a 128 x 64 x 64
+// tcgen05.mma group: the thread writes its activation row as one 128-byte K-major operand row (64 channels, fp16 hi / scaled-lo pair,
+// SWIZZLE_128B -- the operand arithmetic of conv_cond_tc.cu: 22+ significand bits, three products, two instructions per k-step through
+// the stacked [B_hi; B_lo'] weight image); weights stream through a bulk-TMA mbarrier ring, one 16 KB chunk per 64 x 64 matrix.
+// Attention (n_tok <= 32 keys, all inside the thread's own warp) runs on the CUDA cores from k / v rows staged in shared memory.
+// Roles: warps 0-3 compute (thread = row), warp 4 = MMA issuer, warp 5 = weight producer.
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace cfpp {
+namespace vt {
+
+constexpr int kRows = 128, kW = 64;                 // rows per CTA tile; padded feature width (one operand panel)
+constexpr int kThreads = 192, kStages = 4;
+constexpr int kChunkBytes = 2 * kW * 128;           // [hi image 64 rows x 128 B][lo image]
+constexpr int kKVStride = 68;                       // floats per staged k / v row (16-byte aligned, rows of a warp in distinct bank groups)
+constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok)
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {       // K-major SWIZZLE_128B, 8-row group stride 1024 bytes
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int n) {           // kind::f16: fp16 operands, fp32 accumulate, K-major A and B, M = 128
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                 "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+// (hi, lo') fp16 pair of two values: hi = v truncated to 11 significant bits (exact in fp16), lo' = rn((v - hi) * 2^11); saturating
+__device__ __forceinline__ void f16_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
+  const float ha = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), hb = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+  const __half2 h = __floats2half2_rn(ha, hb);
+  const __half2 l = __floats2half2_rn((a - ha) * kLoScale, (b - hb) * kLoScale);
+  hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// the thread's activation row (64 channels, zero beyond the live width) -> operand row `row` of the hi / lo regions
+__device__ __forceinline__ void store_operand_row(uint8_t* a_hi, uint8_t* a_lo, int row, const float (&v)[kW]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f16_split2(v[8 * c + 2 * q], v[8 * c + 2 * q + 1], h[q], l[q]);
+    const uint32_t off = (uint32_t)row * 128u + (uint32_t)(((c ^ row) & 7) << 4);
+    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+// the thread's accumulator row of one 64-wide GEMM output: main block [c0, c0+64) + 2^-11 * cross block [c0+64, c0+128)
+__device__ __forceinline__ void load_acc_row(uint32_t taddr, float (&o)[kW]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float v[16], u[16];
+    tmem_ld16(taddr + 16 * q, v);
+    tmem_ld16(taddr + kW + 16 * q, u);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[16 * q + i] = fmaf(u[i], kLoInv, v[i]);
+  }
+}
+// LayerNorm (eps 1e-5) over the first T entries of the thread's row; entries >= T of `out` are zero
+__device__ __forceinline__ void layer_norm_row(const float (&x)[kW], float (&out)[kW], int T, const float* __restrict__ w, const float* __restrict__ b) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kW; ++i) if (i < T) s += x[i];
+  const float mean = s / (float)T;
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < kW; ++i) if (i < T) { const float d = x[i] - mean; v = fmaf(d, d, v); }
+  const float rstd = 1.0f / sqrtf(v / (float)T + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < kW; ++i) out[i] = i < T ? (x[i] - mean) * rstd * __ldg(w + i) + __ldg(b + i) : 0.f;
+}
+
+struct Args {
+  const float* x; int64_t x_bstride; float* h; cfpp_vit_desc d; const uint8_t* wpack; int B, S, ntiles, NPT;
+};
+
+enum { BAR_FULL = 0, BAR_EMPTY = kStages, BAR_AREADY = 2 * kStages, BAR_ACC, BAR_COUNT };
+
+__global__ void __launch_bounds__(kThreads, 1) vit_tc_kernel(const Args a) {
+  extern __shared__ __align__(1024) uint8_t vt_smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(vt_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* a_hi = base;                                       // 128 rows x 128 B
+  uint8_t* a_lo = base + kRows * 128;
+  uint8_t* ring = base + 2 * kRows * 128;                     // kStages x kChunkBytes
+  float* Ks = reinterpret_cast<float*>(ring + kStages * kChunkBytes);   // [128][kKVStride]
+  float* Vs = Ks + kRows * kKVStride;
+  const uint32_t bars = smem_u32(Vs + kRows * kKVStride);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(Vs + kRows * kKVStride) + 2 * BAR_COUNT;
+  auto bar = [&](int i) { return bars + 8u * i; };
+  const cfpp_vit_desc& d = a.d;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int T = d.T, ntok = d.n_tok, depth = d.depth;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(bar(BAR_FULL + i), 1); mbar_init(bar(BAR_EMPTY + i), 1); }
+    mbar_init(bar(BAR_AREADY), kRows); mbar_init(bar(BAR_ACC), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int chunks_per_tile = 1 + 6 * depth;                  // patch embedding; per layer q, k, v, out, mlp1, mlp2
+  const int my_tiles = (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 5) {
+    // ===================== producer: the tile's weight chunks, in consumption order, through the ring =====================
+    if (elect_one()) {
+      uint32_t st = 0, ph = 0;
+      for (int it = 0; it < my_tiles; ++it)
+        for (int c = 0; c < chunks_per_tile; ++c) {
+          mbar_wait(bar(BAR_EMPTY + st), ph ^ 1);
+          mbar_expect_tx(bar(BAR_FULL + st), kChunkBytes);
+          bulk_g2s(smem_u32(ring + (size_t)st * kChunkBytes), a.wpack + (size_t)c * kChunkBytes, kChunkBytes, bar(BAR_FULL + st));
+          if (++st == kStages) { st = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer: one thread; a GEMM group = 1 or 3 chunks against the resident operand tile =====================
+    if (elect_one()) {
+      const uint32_t id128 = make_idesc(2 * kW), id64 = make_idesc(kW);
+      const uint64_t ah = make_desc(smem_u32(a_hi)), al = make_desc(smem_u32(a_lo)), b0 = make_desc(smem_u32(ring));
+      uint32_t st = 0, ph = 0, na = 0;                         // ring slot / phase; A-ready count
+      auto group = [&](int nchunks) {
+        mbar_wait(bar(BAR_AREADY), na & 1); ++na;
+        tc_fence_after();
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(bar(BAR_FULL + st), ph);
+          tc_fence_after();
+          const uint64_t bd = b0 + (uint64_t)(st * (kChunkBytes >> 4));
+          const uint32_t dd = tmem + c * 2 * kW;               // stacked product -> [dd, dd+128); cross product of the lo activations -> [dd+64, dd+128)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            mma_f16(dd, ah + 2 * ks, bd + 2 * ks, id128, ks ? 1u : 0u);
+            mma_f16(dd + kW, al + 2 * ks, bd + 2 * ks, id64, 1u);
+          }
+          tc_commit(bar(BAR_EMPTY + st));
+          if (++st == kStages) { st = 0; ph ^= 1; }
+        }
+        tc_commit(bar(BAR_ACC));
+      };
+      for (int it = 0; it < my_tiles; ++it) {
+        group(1);                                               // patch embedding
+        for (int l = 0; l < depth; ++l) { group(3); group(1); group(1); group(1); }
+      }
+    }
+  } else {
+    // ===================== compute threads: thread = token row =====================
+    const int r = tid;
+    const int HW = d.H * d.W, tw = d.W / d.p2, Cout = T / (d.p1 * d.p2);
+    const int64_t lstride = 4 * (int64_t)T + (int64_t)T * 192 + 64 * (int64_t)a.NPT + 2 * (int64_t)T * a.NPT + 2 * (int64_t)a.NPT;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);    // this warp's TMEM lane quadrant
+    uint32_t nacc = 0;                                           // ACC barrier uses so far (phase parity)
+    auto a_ready = [&]() { fence_async_smem(); mbar_arrive(bar(BAR_AREADY)); };
+    auto acc_wait = [&]() { mbar_wait(bar(BAR_ACC), nacc & 1); ++nacc; tc_fence_after(); };
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b0 = tile * a.S;
+      const int s = r / ntok, tok = r - s * ntok;
+      const bool live = r < a.S * ntok && b0 + s < a.B;
+      const int th = tok / tw, tww = tok - th * tw;
+      float x[kW], y[kW];
+      // ---- patchify 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)', LayerNorm(patch_dim), Linear, LayerNorm(T), + positional embedding ----
+#pragma unroll
+      for (int f = 0; f < kW; ++f) {
+        float v = 0.f;
+        if (live && f < d.patch_dim) {
+          const int c = f % d.Cin, pp = f / d.Cin, i = pp / d.p2, j = pp - i * d.p2;
+          v = __ldg(a.x + (int64_t)(b0 + s) * a.x_bstride + (int64_t)c * HW + (th * d.p1 + i) * d.W + (tww * d.p2 + j));
+        }
+        x[f] = v;
+      }
+      layer_norm_row(x, y, d.patch_dim, d.ln0_w, d.ln0_b);
+      store_operand_row(a_hi, a_lo, r, y);
+      a_ready();
+      acc_wait();
+      load_acc_row(trow, x);
+      tc_fence_before();
+#pragma unroll
+      for (int i = 0; i < kW; ++i) x[i] = i < T ? x[i] + __ldg(d.pe_b + i) : 0.f;
+      layer_norm_row(x, x, T, d.ln1_w, d.ln1_b);
+#pragma unroll
+      for (int i = 0; i < kW; ++i) if (i < T) x[i] += __ldg(d.pos + tok * T + i);
+
+      for (int l = 0; l < depth; ++l) {
+        const float* Lp = d.layers + l * lstride;
+        const float* lna_w = Lp; const float* lna_b = Lp + T;
+        const float* lnf_w = Lp + 2 * T + (int64_t)T * 192 + 64 * (int64_t)a.NPT; const float* lnf_b = lnf_w + T;
+        const float* b1 = lnf_b + T + (int64_t)T * a.NPT; const float* b2 = b1 + a.NPT + (int64_t)T * a.NPT;
+        // ---- attention: x += Wo softmax(q k^T / 8) v ----
+        layer_norm_row(x, y, T, lna_w, lna_b);
+        store_operand_row(a_hi, a_lo, r, y);
+        a_ready();
+        acc_wait();
+        {
+          float kv[kW];
+          load_acc_row(trow + 2 * kW, kv);                        // k
+#pragma unroll
+          for (int q = 0; q < 16; ++q) *reinterpret_cast<float4*>(Ks + r * kKVStride + 4 * q) = make_float4(kv[4 * q], kv[4 * q + 1], kv[4 * q + 2], kv[4 * q + 3]);
+          load_acc_row(trow + 4 * kW, kv);                        // v
+#pragma unroll
+          for (int q = 0; q < 16; ++q) *reinterpret_cast<float4*>(Vs + r * kKVStride + 4 * q) = make_float4(kv[4 * q], kv[4 * q + 1], kv[4 * q + 2], kv[4 * q + 3]);
+        }
+        load_acc_row(trow, y);                                    // q (row r) stays in registers
+        tc_fence_before();
+        __syncwarp();                                             // the keys / values of a sample are rows of this warp (n_tok divides 32)
+        {
+          float o[kW];
+#pragma unroll
+          for (int i = 0; i < kW; ++i) o[i] = 0.f;
+          float mx = -INFINITY, den = 0.f;
+          const int r0 = r - tok;
+          for (int j = 0; j < ntok; ++j) {
+            const float* kr = Ks + (r0 + j) * kKVStride;
+            float dot = 0.f;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const float4 k4 = *reinterpret_cast<const float4*>(kr + 4 * q);
+              dot = fmaf(y[4 * q], k4.x, dot); dot = fmaf(y[4 * q + 1], k4.y, dot); dot = fmaf(y[4 * q + 2], k4.z, dot); dot = fmaf(y[4 * q + 3], k4.w, dot);
+            }
+            dot *= 0.125f;                                         // dim_head ** -0.5
+            const float nm = fmaxf(mx, dot), corr = expf(mx - nm), pj = expf(dot - nm);
+            den = den * corr + pj;
+            const float* vr = Vs + (r0 + j) * kKVStride;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const float4 v4 = *reinterpret_cast<const float4*>(vr + 4 * q);
+              o[4 * q] = fmaf(o[4 * q], corr, pj * v4.x); o[4 * q + 1] = fmaf(o[4 * q + 1], corr, pj * v4.y);
+              o[4 * q + 2] = fmaf(o[4 * q + 2], corr, pj * v4.z); o[4 * q + 3] = fmaf(o[4 * q + 3], corr, pj * v4.w);
+            }
+            mx = nm;
+          }
+          const float inv = 1.0f / den;
+#pragma unroll
+          for (int i = 0; i < kW; ++i) o[i] *= inv;
+          __syncwarp();                                           // every lane has finished reading k / v before the next layer overwrites them
+          store_operand_row(a_hi, a_lo, r, o);
+        }
+        a_ready();
+        acc_wait();
+        load_acc_row(trow, y);
+        tc_fence_before();
+#pragma unroll
+        for (int i = 0; i < kW; ++i) if (i < T) x[i] += y[i];
+        // ---- MLP: x += W2 gelu(W1 LN(x) + b1) + b2 ----
+        layer_norm_row(x, y, T, lnf_w, lnf_b);
+        store_operand_row(a_hi, a_lo, r, y);
+        a_ready();
+        acc_wait();
+        load_acc_row(trow, y);
+        tc_fence_before();
+#pragma unroll
+        for (int i = 0; i < kW; ++i) {
+          const float u = y[i] + (i < T ? __ldg(b1 + i) : 0.f);
+          y[i] = i < T ? 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f)) : 0.f;
+        }
+        store_operand_row(a_hi, a_lo, r, y);
+        a_ready();
+        acc_wait();
+        load_acc_row(trow, y);
+        tc_fence_before();
+#pragma unroll
+        for (int i = 0; i < kW; ++i) if (i < T) x[i] += y[i] + __ldg(b2 + i);
+      }
+      layer_norm_row(x, x, T, d.lnf_w, d.lnf_b);
+      // ---- un-patchify 'b (h w) (p1 p2 c) -> b c (h p1) (w p2)', c = T / (p1 p2) ----
+      if (live) {
+#pragma unroll
+        for (int f = 0; f < kW; ++f) {
+          if (f < T) {
+            const int c = f % Cout, pp = f / Cout, i = pp / d.p2, j = pp - i * d.p2;
+            a.h[((int64_t)(b0 + s) * Cout + c) * HW + (th * d.p1 + i) * d.W + (tww * d.p2 + j)] = x[f];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+// One 64 x 64 weight matrix -> one chunk: [hi image][lo image], rows = output features (zero beyond n_rows), 64 input channels per
+// 128-byte row (zero beyond k_cols), SWIZZLE_128B.  w is row-major (out, in) with leading dimension ld (nn.Linear.weight).
+__global__ void pack_chunk_kernel(const float* __restrict__ w, int ld, int n_rows, int k_cols, uint8_t* __restrict__ out) {
+  for (int i = threadIdx.x; i < kW * kW; i += blockDim.x) {
+    const int n = i / kW, k = i % kW;
+    const float v = (n < n_rows && k < k_cols) ? w[(size_t)n * ld + k] : 0.f;
+    const float vc = fminf(fmaxf(v, -65504.f), 65504.f);
+    const __half hi = __float2half_rn(vc);
+    const uint32_t off = (uint32_t)n * 128u + (uint32_t)((((k >> 3) ^ n) & 7) << 4) + (uint32_t)((k & 7) << 1);
+    *reinterpret_cast<__half*>(out + off) = hi;
+    *reinterpret_cast<__half*>(out + kW * 128 + off) = __float2half_rn((vc - __half2float(hi)) * kLoScale);
+  }
+}
+
+static size_t smem_bytes() {
+  return 1024 + 2 * kRows * 128 + (size_t)kStages * kChunkBytes + 2 * (size_t)kRows * kKVStride * 4 + BAR_COUNT * 8 + 64;
+}
+
+}  // namespace vt
+}  // namespace cfpp
+using namespace cfpp;
+
+extern "C" int cfpp_vit_tc_supported(int T, int patch_dim, int n_tok, int Cextra) {
+  return (T >= 4 && T <= vt::kW && patch_dim >= 1 && patch_dim <= vt::kW && Cextra == 0 && n_tok >= 1 && n_tok <= 32 && 32 % n_tok == 0) ? 1 : 0;
+}
+
+extern "C" int64_t cfpp_vit_tc_pack_bytes(int depth) { return (int64_t)(1 + 6 * depth) * vt::kChunkBytes; }
+
+extern "C" int cfpp_vit_tc_pack_chunk(const float* w, int ld, int n_rows, int k_cols, void* out_chunk, void* stream) {
+  CFPP_REQUIRE(w && out_chunk && n_rows >= 1 && n_rows <= vt::kW && k_cols >= 1 && k_cols <= vt::kW && ld >= k_cols, "vit_tc_pack_chunk: %d x %d (ld %d)", n_rows, k_cols, ld);
+  vt::pack_chunk_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(w, ld, n_rows, k_cols, (uint8_t*)out_chunk);
+  return check_launch("vit_tc_pack_chunk");
+}
+
+extern "C" int cfpp_vit_tc_fwd(const float* x, int64_t x_bstride, float* h, const cfpp_vit_desc* desc, const void* wpack, int B, void* stream) {
+  CFPP_REQUIRE(desc && wpack, "vit_tc: null descriptor / weights");
+  const cfpp_vit_desc& d = *desc;
+  CFPP_REQUIRE(cfpp_vit_tc_supported(d.T, d.patch_dim, d.n_tok, 0), "vit_tc: T=%d patch_dim=%d n_tok=%d has no tensor-core plan", d.T, d.patch_dim, d.n_tok);
+  CFPP_REQUIRE(d.n_tok == (d.H / d.p1) * (d.W / d.p2) && d.patch_dim == d.Cin * d.p1 * d.p2 && d.T % (d.p1 * d.p2) == 0, "vit_tc: inconsistent descriptor");
+  CFPP_REQUIRE((reinterpret_cast<uintptr_t>(wpack) & 15) == 0, "vit_tc: wpack must be 16-byte aligned");
+  if (B <= 0) return CFPP_OK;
+  vt::Args a{x, x_bstride, h, d, (const uint8_t*)wpack, B, vt::kRows / d.n_tok, 0, (d.T + 15) / 16 * 16};
+  a.ntiles = (B + a.S - 1) / a.S;
+  const size_t smem = vt::smem_bytes();
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(vt::vit_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
+  vt::vit_tc_kernel<<<grid, vt::kThreads, smem, (cudaStream_t)stream>>>(a);
+  return check_launch("vit_cond_tc_fwd");
+}

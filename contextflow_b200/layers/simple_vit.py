@@ -101,8 +101,29 @@ class SimpleViT(nn.Module):
         d.Cin = cin
         return d
 
+    def _tc_pack(self):
+        """fp16 hi/lo weight stream of the tensor-core kernel (chunk order of cfpp_vit_tc_fwd), or None when the shape has no plan."""
+        g = self.geom
+        if not _cabi.lib().cfpp_vit_tc_supported(g['T'], g['patch_dim'], g['n_tok'], 0):
+            return None
+
+        def build():
+            T = g['T']
+            mats = [(self.to_patch_embedding[2].weight, T, g['patch_dim'])]
+            for attn, ff in self.transformer.layers:
+                wqkv = attn.to_qkv.weight
+                mats += [(wqkv[0:64], 64, T), (wqkv[64:128], 64, T), (wqkv[128:192], 64, T), (attn.to_out.weight, T, 64),
+                         (ff.net[1].weight, T, T), (ff.net[3].weight, T, T)]
+            return ops.vit_tc_pack(mats)
+        return self._packs.get('tc', self._sources(), build)
+
     def forward(self, img, extra=None):
         """img (B, channels, H, W) [or (B, channels - extra.shape[1], H, W) plus per-sample constant channels `extra`]."""
         g = self.geom
         cextra = 0 if extra is None else extra.shape[1]
-        return ops.vit_cond(img, self.descriptor(g['Cin'] - cextra), g['T'] // (g['p1'] * g['p2']), extra)
+        cout = g['T'] // (g['p1'] * g['p2'])
+        if extra is None and img.is_cuda and ops.vit_tc_mode() != 'fma':
+            pack = self._tc_pack()
+            if pack is not None:
+                return ops.vit_cond_tc(img, self.descriptor(g['Cin']), pack, cout)
+        return ops.vit_cond(img, self.descriptor(g['Cin'] - cextra), cout, extra)

@@ -332,6 +332,33 @@ def vit_cond(x, desc: _cabi.VitDesc, cout, extra=None):
     return h
 
 
+def vit_tc_mode() -> str:
+    """'auto' (tensor cores whenever the shape has a plan) or 'fma' (force the FP32-FMA kernel) -- env CFPP_VIT."""
+    import os
+    return os.environ.get('CFPP_VIT', 'auto')
+
+
+def vit_tc_pack(mats):
+    """mats: [(weight (out, in) row-major, n_rows, k_cols)] in chunk order -> packed fp16 hi/lo weight stream of cfpp_vit_tc_fwd."""
+    chunk = int(lib().cfpp_vit_tc_pack_bytes(0))
+    out = torch.empty(chunk * len(mats), device=mats[0][0].device, dtype=torch.uint8)
+    keep = []
+    for i, (w, n_rows, k_cols) in enumerate(mats):
+        w = _f32(w.detach()); keep.append(w)
+        _call('vit_tc_pack_chunk', (_p(w), w.stride(0), n_rows, k_cols, vp(out.data_ptr() + i * chunk), _stream()))
+    return out
+
+
+def vit_cond_tc(x, desc: _cabi.VitDesc, wpack, cout):
+    _need_cuda(x, wpack)
+    xv, bstride = _half_view(x)
+    B = x.shape[0]
+    h = torch.empty((B, cout, desc.H, desc.W), device=x.device, dtype=torch.float32)
+    _set_work(bytes=4.0 * B * desc.H * desc.W * (desc.Cin + cout), flops=2.0 * B * desc.n_tok * (desc.patch_dim * desc.T + desc.depth * (desc.T * 192 + 2 * desc.n_tok * 64 + 64 * desc.T + 2 * desc.T * desc.T)))
+    _call('vit_tc_fwd', (_p(xv), bstride, _p(h), C.byref(desc), _p(wpack), B, _stream()), 'vit_cond_tc_fwd')
+    return h
+
+
 # ---------------------------------------------------------------------------------------------- GMM
 def gmm_logprob(x, mG, sG, wG, ctx_off=None, logp_c=None, logp_scale=0.0):
     _need_cuda(x, mG)

@@ -147,6 +147,18 @@ int64_t cfpp_vit_layer_floats(int T);
 int cfpp_vit_cond_fwd(const float* x, int64_t x_bstride, const float* extra, int Cextra, float* h,
                       const cfpp_vit_desc* desc, int B, void* stream);
 
+/* The same conditioner on the tensor cores (csrc/vit_tc.cu) for token widths T <= 64, patch_dim <= 64, n_tok dividing 32 and no
+ * concatenated context channels (the SMAP stack: T = 52, 4 tokens): thread = token row with the residual stream in registers, every
+ * linear layer a 128 x 64 x 64 tcgen05.mma group on fp16 hi / scaled-lo operand pairs (fp32-faithful, as the conv conditioner).
+ * Weights: cfpp_vit_tc_pack_bytes(depth) bytes holding 1 + 6*depth chunks in the order patch-embedding, then per layer q, k, v
+ * (rows 0-63 / 64-127 / 128-191 of to_qkv.weight), to_out, mlp[1], mlp[3]; each chunk written by cfpp_vit_tc_pack_chunk from the
+ * row-major nn.Linear weight (out_features = n_rows <= 64, in_features = k_cols <= 64, leading dimension ld).  LayerNorm parameters,
+ * biases and the positional table are read from the descriptor exactly as cfpp_vit_cond_fwd reads them. */
+int cfpp_vit_tc_supported(int T, int patch_dim, int n_tok, int Cextra);
+int64_t cfpp_vit_tc_pack_bytes(int depth);
+int cfpp_vit_tc_pack_chunk(const float* w, int ld, int n_rows, int k_cols, void* out_chunk, void* stream);
+int cfpp_vit_tc_fwd(const float* x, int64_t x_bstride, float* h, const cfpp_vit_desc* desc, const void* wpack, int B, void* stream);
+
 /* ---- Gaussian-mixture log-prob ----------------------------------------------------------------------------- */
 /* GaussianMixtureDistribution.log_prob, layers/distributions/gaussian.py:142-161 (torch.distributions semantics):
  * out[b,m] = logsumexp_k( logmix[m,k] + sum_e N(x[b,e]; mG[m,k,e] (+cm), softplus(sG[m,k,e] (+cs))) ) + logp_scale*logp_c[b]
