@@ -63,13 +63,18 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
   return pred != 0;
 }
-// (hi, lo') fp16 pair of two values: hi = v truncated to 11 significant bits (exact in fp16), lo' = rn((v - hi) * 2^11); saturating
+// packed fp16 pair {lo half = a, hi half = b}, round to nearest, saturating to the finite range (one F2FP instruction)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// (hi, lo') fp16 pair of two values: hi = v truncated to 11 significant bits (exact in fp16 over its normal range), lo' = rn((v - hi) * 2^11);
+// 4 instructions per element
 __device__ __forceinline__ void f16_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
   const float ha = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), hb = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
-  const __half2 h = __floats2half2_rn(ha, hb);
-  const __half2 l = __floats2half2_rn((a - ha) * kLoScale, (b - hb) * kLoScale);
-  hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
+  hi = pack_f16x2_sat(ha, hb);
+  lo = pack_f16x2_sat((a - ha) * kLoScale, (b - hb) * kLoScale);
 }
 // the thread's activation row (64 channels, zero beyond the live width) -> operand row `row` of the hi / lo regions
 __device__ __forceinline__ void store_operand_row(uint8_t* a_hi, uint8_t* a_lo, int row, const float (&v)[kW]) {
@@ -95,18 +100,36 @@ __device__ __forceinline__ void load_acc_row(uint32_t taddr, float (&o)[kW]) {
     for (int i = 0; i < 16; ++i) o[16 * q + i] = fmaf(u[i], kLoInv, v[i]);
   }
 }
-// LayerNorm (eps 1e-5) over the first T entries of the thread's row; entries >= T of `out` are zero
-__device__ __forceinline__ void layer_norm_row(const float (&x)[kW], float (&out)[kW], int T, const float* __restrict__ w, const float* __restrict__ b) {
-  float s = 0.f;
+// LayerNorm (eps 1e-5) over the first T entries of the thread's row.  The row is zero beyond T (invariant of every caller), so the sums
+// run over all 64 registers without predicates: the padding adds nothing to the mean and (64 - T) mean^2 to the centred sum of squares,
+// which is subtracted.  w / b: shared-memory rows of 64 floats, zero beyond T (the output keeps the invariant).  Four partial sums for ILP.
+__device__ __forceinline__ void layer_norm_row(const float (&x)[kW], float (&out)[kW], int T, const float* w, const float* b) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-  for (int i = 0; i < kW; ++i) if (i < T) s += x[i];
-  const float mean = s / (float)T;
-  float v = 0.f;
+  for (int i = 0; i < kW; i += 4) { s0 += x[i]; s1 += x[i + 1]; s2 += x[i + 2]; s3 += x[i + 3]; }
+  const float mean = ((s0 + s1) + (s2 + s3)) / (float)T;
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
 #pragma unroll
-  for (int i = 0; i < kW; ++i) if (i < T) { const float d = x[i] - mean; v = fmaf(d, d, v); }
-  const float rstd = 1.0f / sqrtf(v / (float)T + 1e-5f);
+  for (int i = 0; i < kW; i += 4) {
+    const float d0 = x[i] - mean, d1 = x[i + 1] - mean, d2 = x[i + 2] - mean, d3 = x[i + 3] - mean;
+    v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); v2 = fmaf(d2, d2, v2); v3 = fmaf(d3, d3, v3);
+  }
+  const float var = fmaxf(((v0 + v1) + (v2 + v3)) - (float)(kW - T) * mean * mean, 0.f) / (float)T;
+  const float rstd = 1.0f / sqrtf(var + 1e-5f);
 #pragma unroll
-  for (int i = 0; i < kW; ++i) out[i] = i < T ? (x[i] - mean) * rstd * __ldg(w + i) + __ldg(b + i) : 0.f;
+  for (int i = 0; i < kW; i += 4) {
+    const float4 w4 = *reinterpret_cast<const float4*>(w + i), b4 = *reinterpret_cast<const float4*>(b + i);
+    out[i] = fmaf((x[i] - mean) * rstd, w4.x, b4.x); out[i + 1] = fmaf((x[i + 1] - mean) * rstd, w4.y, b4.y);
+    out[i + 2] = fmaf((x[i + 2] - mean) * rstd, w4.z, b4.z); out[i + 3] = fmaf((x[i + 3] - mean) * rstd, w4.w, b4.w);
+  }
+}
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7) with the SFU exponential / reciprocal: ~14 instructions instead of ~40 for erff
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  const float r = 1.0f - poly * __expf(-ax * ax);
+  return copysignf(r, x);
 }
 
 struct Args {
@@ -123,8 +146,10 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc_kernel(const Args a) {
   uint8_t* ring = base + 2 * kRows * 128;                     // kStages x kChunkBytes
   float* Ks = reinterpret_cast<float*>(ring + kStages * kChunkBytes);   // [128][kKVStride]
   float* Vs = Ks + kRows * kKVStride;
-  const uint32_t bars = smem_u32(Vs + kRows * kKVStride);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(Vs + kRows * kKVStride) + 2 * BAR_COUNT;
+  float* prm = Vs + kRows * kKVStride;                         // parameter rows of 64 floats, zero padded (see fill below)
+  const int prm_rows = 7 + a.d.n_tok + 6 * a.d.depth;
+  const uint32_t bars = smem_u32(prm + prm_rows * kW);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(prm + prm_rows * kW) + 2 * BAR_COUNT;
   auto bar = [&](int i) { return bars + 8u * i; };
   const cfpp_vit_desc& d = a.d;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -134,6 +159,26 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc_kernel(const Args a) {
     for (int i = 0; i < kStages; ++i) { mbar_init(bar(BAR_FULL + i), 1); mbar_init(bar(BAR_EMPTY + i), 1); }
     mbar_init(bar(BAR_AREADY), kRows); mbar_init(bar(BAR_ACC), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {   // LayerNorm weights / biases, Linear biases and the positional table: rows of 64 floats in shared memory, zero beyond the live width
+    //   0 ln0_w  1 ln0_b  2 pe_b  3 ln1_w  4 ln1_b  5 lnf_w  6 lnf_b | 7.. pos[tok] | per layer: lna_w lna_b lnf_w lnf_b b1 b2
+    const int64_t lstride = 4 * (int64_t)T + (int64_t)T * 192 + 64 * (int64_t)a.NPT + 2 * (int64_t)T * a.NPT + 2 * (int64_t)a.NPT;
+    for (int idx = tid; idx < prm_rows * kW; idx += kThreads) {
+      const int row = idx / kW, i = idx - row * kW;
+      const float* src = nullptr; int n = T;
+      if (row == 0) { src = d.ln0_w; n = d.patch_dim; } else if (row == 1) { src = d.ln0_b; n = d.patch_dim; }
+      else if (row == 2) src = d.pe_b; else if (row == 3) src = d.ln1_w; else if (row == 4) src = d.ln1_b;
+      else if (row == 5) src = d.lnf_w; else if (row == 6) src = d.lnf_b;
+      else if (row < 7 + ntok) src = d.pos + (row - 7) * T;
+      else {
+        const int l = (row - 7 - ntok) / 6, k = (row - 7 - ntok) % 6;
+        const float* Lp = d.layers + l * lstride;
+        const float* lnf = Lp + 2 * T + (int64_t)T * 192 + 64 * (int64_t)a.NPT;
+        const float* b1 = lnf + 2 * T + (int64_t)T * a.NPT;
+        src = k == 0 ? Lp : k == 1 ? Lp + T : k == 2 ? lnf : k == 3 ? lnf + T : k == 4 ? b1 : b1 + a.NPT + (int64_t)T * a.NPT;
+      }
+      prm[idx] = i < n ? __ldg(src + i) : 0.f;
+    }
   }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
@@ -192,18 +237,18 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc_kernel(const Args a) {
     // ===================== compute threads: thread = token row =====================
     const int r = tid;
     const int HW = d.H * d.W, tw = d.W / d.p2, Cout = T / (d.p1 * d.p2);
-    const int64_t lstride = 4 * (int64_t)T + (int64_t)T * 192 + 64 * (int64_t)a.NPT + 2 * (int64_t)T * a.NPT + 2 * (int64_t)a.NPT;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);    // this warp's TMEM lane quadrant
     uint32_t nacc = 0;                                           // ACC barrier uses so far (phase parity)
     auto a_ready = [&]() { fence_async_smem(); mbar_arrive(bar(BAR_AREADY)); };
     auto acc_wait = [&]() { mbar_wait(bar(BAR_ACC), nacc & 1); ++nacc; tc_fence_after(); };
+    auto prow = [&](int row) { return prm + row * kW; };
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int b0 = tile * a.S;
       const int s = r / ntok, tok = r - s * ntok;
       const bool live = r < a.S * ntok && b0 + s < a.B;
       const int th = tok / tw, tww = tok - th * tw;
-      float x[kW], y[kW];
+      float x[kW], y[kW];                                        // invariant: entries beyond the live width are zero
       // ---- patchify 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)', LayerNorm(patch_dim), Linear, LayerNorm(T), + positional embedding ----
 #pragma unroll
       for (int f = 0; f < kW; ++f) {
@@ -214,25 +259,28 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc_kernel(const Args a) {
         }
         x[f] = v;
       }
-      layer_norm_row(x, y, d.patch_dim, d.ln0_w, d.ln0_b);
+      layer_norm_row(x, y, d.patch_dim, prow(0), prow(1));
       store_operand_row(a_hi, a_lo, r, y);
       a_ready();
       acc_wait();
       load_acc_row(trow, x);
       tc_fence_before();
+      {
+        const float* pb = prow(2);
 #pragma unroll
-      for (int i = 0; i < kW; ++i) x[i] = i < T ? x[i] + __ldg(d.pe_b + i) : 0.f;
-      layer_norm_row(x, x, T, d.ln1_w, d.ln1_b);
+        for (int i = 0; i < kW; ++i) x[i] += pb[i];
+      }
+      layer_norm_row(x, x, T, prow(3), prow(4));
+      {
+        const float* pp = prow(7 + tok);
 #pragma unroll
-      for (int i = 0; i < kW; ++i) if (i < T) x[i] += __ldg(d.pos + tok * T + i);
+        for (int i = 0; i < kW; ++i) x[i] += pp[i];
+      }
 
       for (int l = 0; l < depth; ++l) {
-        const float* Lp = d.layers + l * lstride;
-        const float* lna_w = Lp; const float* lna_b = Lp + T;
-        const float* lnf_w = Lp + 2 * T + (int64_t)T * 192 + 64 * (int64_t)a.NPT; const float* lnf_b = lnf_w + T;
-        const float* b1 = lnf_b + T + (int64_t)T * a.NPT; const float* b2 = b1 + a.NPT + (int64_t)T * a.NPT;
+        const float* lp = prow(7 + ntok + 6 * l);                  // lna_w lna_b lnf_w lnf_b b1 b2
         // ---- attention: x += Wo softmax(q k^T / 8) v ----
-        layer_norm_row(x, y, T, lna_w, lna_b);
+        layer_norm_row(x, y, T, lp, lp + kW);
         store_operand_row(a_hi, a_lo, r, y);
         a_ready();
         acc_wait();
@@ -256,14 +304,14 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc_kernel(const Args a) {
           const int r0 = r - tok;
           for (int j = 0; j < ntok; ++j) {
             const float* kr = Ks + (r0 + j) * kKVStride;
-            float dot = 0.f;
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
               const float4 k4 = *reinterpret_cast<const float4*>(kr + 4 * q);
-              dot = fmaf(y[4 * q], k4.x, dot); dot = fmaf(y[4 * q + 1], k4.y, dot); dot = fmaf(y[4 * q + 2], k4.z, dot); dot = fmaf(y[4 * q + 3], k4.w, dot);
+              d0 = fmaf(y[4 * q], k4.x, d0); d1 = fmaf(y[4 * q + 1], k4.y, d1); d2 = fmaf(y[4 * q + 2], k4.z, d2); d3 = fmaf(y[4 * q + 3], k4.w, d3);
             }
-            dot *= 0.125f;                                         // dim_head ** -0.5
-            const float nm = fmaxf(mx, dot), corr = expf(mx - nm), pj = expf(dot - nm);
+            const float dot = ((d0 + d1) + (d2 + d3)) * 0.125f;    // dim_head ** -0.5
+            const float nm = fmaxf(mx, dot), corr = __expf(mx - nm), pj = __expf(dot - nm);
             den = den * corr + pj;
             const float* vr = Vs + (r0 + j) * kKVStride;
 #pragma unroll
@@ -285,28 +333,31 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc_kernel(const Args a) {
         load_acc_row(trow, y);
         tc_fence_before();
 #pragma unroll
-        for (int i = 0; i < kW; ++i) if (i < T) x[i] += y[i];
+        for (int i = 0; i < kW; ++i) x[i] += y[i];
         // ---- MLP: x += W2 gelu(W1 LN(x) + b1) + b2 ----
-        layer_norm_row(x, y, T, lnf_w, lnf_b);
+        layer_norm_row(x, y, T, lp + 2 * kW, lp + 3 * kW);
         store_operand_row(a_hi, a_lo, r, y);
         a_ready();
         acc_wait();
         load_acc_row(trow, y);
         tc_fence_before();
+        {
+          const float* pb1 = lp + 4 * kW;
 #pragma unroll
-        for (int i = 0; i < kW; ++i) {
-          const float u = y[i] + (i < T ? __ldg(b1 + i) : 0.f);
-          y[i] = i < T ? 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f)) : 0.f;
+          for (int i = 0; i < kW; ++i) { const float u = y[i] + pb1[i]; y[i] = 0.5f * u * (1.0f + erf_as(u * 0.70710678118654752440f)); }
         }
         store_operand_row(a_hi, a_lo, r, y);
         a_ready();
         acc_wait();
         load_acc_row(trow, y);
         tc_fence_before();
+        {
+          const float* pb2 = lp + 5 * kW;
 #pragma unroll
-        for (int i = 0; i < kW; ++i) if (i < T) x[i] += y[i] + __ldg(b2 + i);
+          for (int i = 0; i < kW; ++i) x[i] += y[i] + pb2[i];
+        }
       }
-      layer_norm_row(x, x, T, d.lnf_w, d.lnf_b);
+      layer_norm_row(x, x, T, prow(5), prow(6));
       // ---- un-patchify 'b (h w) (p1 p2 c) -> b c (h p1) (w p2)', c = T / (p1 p2) ----
       if (live) {
 #pragma unroll
@@ -338,8 +389,9 @@ __global__ void pack_chunk_kernel(const float* __restrict__ w, int ld, int n_row
   }
 }
 
-static size_t smem_bytes() {
-  return 1024 + 2 * kRows * 128 + (size_t)kStages * kChunkBytes + 2 * (size_t)kRows * kKVStride * 4 + BAR_COUNT * 8 + 64;
+static size_t smem_bytes(int n_tok, int depth) {
+  return 1024 + 2 * kRows * 128 + (size_t)kStages * kChunkBytes + 2 * (size_t)kRows * kKVStride * 4 + (size_t)(7 + n_tok + 6 * depth) * kW * 4 +
+         BAR_COUNT * 8 + 64;
 }
 
 }  // namespace vt
@@ -367,9 +419,10 @@ extern "C" int cfpp_vit_tc_fwd(const float* x, int64_t x_bstride, float* h, cons
   if (B <= 0) return CFPP_OK;
   vt::Args a{x, x_bstride, h, d, (const uint8_t*)wpack, B, vt::kRows / d.n_tok, 0, (d.T + 15) / 16 * 16};
   a.ntiles = (B + a.S - 1) / a.S;
-  const size_t smem = vt::smem_bytes();
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(vt::vit_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  const size_t smem = vt::smem_bytes(d.n_tok, d.depth);
+  CFPP_REQUIRE(smem <= 227 * 1024, "vit_tc: depth %d does not fit the shared-memory parameter table", d.depth);
+  static size_t attr = 0;
+  if (smem > attr) { cudaFuncSetAttribute(vt::vit_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
   const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
   vt::vit_tc_kernel<<<grid, vt::kThreads, smem, (cudaStream_t)stream>>>(a);
   return check_launch("vit_cond_tc_fwd");
