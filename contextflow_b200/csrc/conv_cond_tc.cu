@@ -68,17 +68,20 @@ __host__ __device__ __forceinline__ uint32_t row_off(int row, int chunk, int rb)
 __device__ __forceinline__ uint32_t sw128(int row, int k) { return row * 128 + ((((k >> 2) ^ row) & 7) << 4) + ((k & 3) << 2); }
 __device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
+// packed fp16 pair {low half = a, high half = b}: round to nearest, saturating to the finite range (one F2FP instruction)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 // (hi, lo') fp16 pair of two values, packed as two half2 words.  hi = v truncated to 11 significant bits (a mask: exactly
 // representable in fp16 over its normal range, so the conversion is exact and v - hi needs no conversion back), lo' = rn((v - hi) * 2^11);
-// saturated to the finite fp16 range.  NONNEG: the value is known to be >= 0 (after ReLU), one clamp less.  5 instructions per element.
+// the conversions saturate to the finite fp16 range.  4 instructions per element.
 template <bool NONNEG>
 __device__ __forceinline__ void f16_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  a = fminf(a, 65504.f); b = fminf(b, 65504.f);
-  if (!NONNEG) { a = fmaxf(a, -65504.f); b = fmaxf(b, -65504.f); }
   const float ha = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), hb = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
-  const __half2 h = __floats2half2_rn(ha, hb);
-  const __half2 l = __floats2half2_rn((a - ha) * kLoScale, (b - hb) * kLoScale);
-  hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
+  hi = pack_f16x2_sat(ha, hb);
+  lo = pack_f16x2_sat((a - ha) * kLoScale, (b - hb) * kLoScale);
 }
 // Store 8 consecutive channels (col8 = first channel within the panel, multiple of 8) of operand row `row` as (hi, lo) operands.
 template <bool F16, bool NONNEG = false>
