@@ -20,12 +20,18 @@ struct CnBatchArgs {
   int stride;                       // shared-memory row stride in floats (multiple of 4, >= every staged width)
 };
 
+// Activations of the CTA's 16 samples live in shared memory as float4 [K/4][CN_SPB]: element (sample s, channel k) is component k % 4 of
+// entry (k / 4) * CN_SPB + s.  A thread's SPG samples are then SPG consecutive float4 at a compile-time offset from one base register,
+// and the inner loop carries two pointers (weights, activations) that advance by a constant -- the first version recomputed
+// `row * stride + k` and `k * N + n` per load and spent 45 % of its instructions on integer address arithmetic (ncu, r1u).
 template <int SPG>
-__device__ __forceinline__ void cn_layer(const float* __restrict__ src, float* __restrict__ dst, int stride, float* __restrict__ gout,
+__device__ __forceinline__ void cn_layer(const float4* __restrict__ src, float* __restrict__ dst, float* __restrict__ gout,
                                          const float* __restrict__ wt, const float* __restrict__ bias, int K, int N, bool last,
                                          int tril, int nS, int s0, int col, int cols_per_pass) {
   const bool tri = last && tril > 0;                       // enumerate only the lower triangle + diagonal: D (D + 1) / 2 columns
   const int ncols = tri ? tril * (tril + 1) / 2 : N;
+  const int K4 = (K + 3) >> 2;
+  const int64_t N4 = 4 * (int64_t)N;
   for (int t = col; t < ncols; t += cols_per_pass) {
     int n = t;
     if (tri) {
@@ -37,47 +43,56 @@ __device__ __forceinline__ void cn_layer(const float* __restrict__ src, float* _
     float acc[SPG];
 #pragma unroll
     for (int s = 0; s < SPG; ++s) acc[s] = 0.f;
-    const float* wcol = wt + n;
-    for (int k0 = 0; k0 < K; k0 += 4) {
+    const float* wp = wt + n;
+    const float4* ap = src + s0;
+    int krem = K;
+    for (int k4 = 0; k4 < K4; ++k4, wp += N4, ap += CN_SPB, krem -= 4) {
       float w[4];
+      if (krem >= 4) { w[0] = __ldg(wp); w[1] = __ldg(wp + N); w[2] = __ldg(wp + 2 * N); w[3] = __ldg(wp + 3 * N); }
+      else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) w[q] = (k0 + q < K) ? __ldg(wcol + (int64_t)(k0 + q) * N) : 0.f;
+        for (int q = 0; q < 4; ++q) w[q] = q < krem ? __ldg(wp + (int64_t)q * N) : 0.f;
+      }
 #pragma unroll
       for (int s = 0; s < SPG; ++s) {
-        const float4 c = *reinterpret_cast<const float4*>(src + (s0 + s) * stride + k0);
+        const float4 c = ap[s];
         acc[s] = fmaf(c.x, w[0], acc[s]); acc[s] = fmaf(c.y, w[1], acc[s]);
         acc[s] = fmaf(c.z, w[2], acc[s]); acc[s] = fmaf(c.w, w[3], acc[s]);
       }
     }
     const float bv = bias ? __ldg(bias + n) : 0.f;
+    if (last) {
+      float* gp = gout + (int64_t)s0 * N + n;
 #pragma unroll
-    for (int s = 0; s < SPG; ++s) {
-      const float v = acc[s] + bv;
-      if (last) { if (s0 + s < nS) gout[(int64_t)(s0 + s) * N + n] = v; }
-      else dst[(s0 + s) * stride + n] = fmaxf(v, 0.f);
+      for (int s = 0; s < SPG; ++s) if (s0 + s < nS) gp[(int64_t)s * N] = acc[s] + bv;
+    } else {
+      float* dp = dst + ((n >> 2) * CN_SPB + s0) * 4 + (n & 3);
+#pragma unroll
+      for (int s = 0; s < SPG; ++s) dp[4 * s] = fmaxf(acc[s] + bv, 0.f);
     }
   }
 }
 
 __global__ void __launch_bounds__(CN_THREADS, 4) cn_batch_kernel(const __grid_constant__ CnBatchArgs a, int B) {
   extern __shared__ float4 cn_smem4[];
-  const int stride = a.stride;
-  float* buf0 = reinterpret_cast<float*>(cn_smem4);
-  float* buf1 = buf0 + CN_SPB * stride;
+  const int rows4 = a.stride >> 2;                           // float4 rows per buffer
+  float4* buf0 = cn_smem4;                                   // [rows4][CN_SPB]
+  float4* buf1 = buf0 + rows4 * CN_SPB;
   const cfpp_cn_job& J = a.job[blockIdx.y];
   const int64_t b0 = (int64_t)blockIdx.x * CN_SPB;
   const int nS = (int)min((int64_t)CN_SPB, (int64_t)B - b0);
   const int tid = threadIdx.x;
   {
-    const int K = J.K, K4 = (K + 3) & ~3;
+    const int K = J.K, K4 = (K + 3) >> 2;
     const float* in = a.in[blockIdx.y] + b0 * K;
-    for (int idx = tid; idx < CN_SPB * K4; idx += CN_THREADS) {
-      const int s = idx / K4, k = idx - s * K4;
-      buf0[s * stride + k] = (s < nS && k < K) ? __ldg(in + s * K + k) : 0.f;
+    float* b0f = reinterpret_cast<float*>(buf0);
+    for (int idx = tid; idx < K4 * 4 * CN_SPB; idx += CN_THREADS) {          // idx = (k, s), s fastest within a k: coalesced enough for a (16, K) tile
+      const int k = idx / CN_SPB, s = idx - k * CN_SPB;
+      b0f[((k >> 2) * CN_SPB + s) * 4 + (k & 3)] = (s < nS && k < K) ? __ldg(in + s * K + k) : 0.f;
     }
   }
   __syncthreads();
-  float* src = buf0; float* dst = buf1;
+  float4* src = buf0; float4* dst = buf1;
   float* gout = a.out[blockIdx.y] + b0 * J.N[J.n_layers - 1];
   for (int l = 0; l < J.n_layers; ++l) {
     const int K = l ? J.N[l - 1] : J.K, N = J.N[l];
@@ -87,21 +102,21 @@ __global__ void __launch_bounds__(CN_THREADS, 4) cn_batch_kernel(const __grid_co
     int groups = CN_THREADS / cpp;                       // 1, 2, 4 or 8 sample groups
     groups = groups >= 8 ? 8 : groups >= 4 ? 4 : groups >= 2 ? 2 : 1;
     const int g = tid / cpp, col = tid - g * cpp;
+    float* dstf = reinterpret_cast<float*>(dst);
+    if (!last) {                                         // zero the channel padding the next layer's float4 reads touch
+      const int N4 = (N + 3) & ~3;
+      for (int idx = tid; idx < (N4 - N) * CN_SPB; idx += CN_THREADS) { const int n = N + idx / CN_SPB, sidx = idx % CN_SPB; dstf[((n >> 2) * CN_SPB + sidx) * 4 + (n & 3)] = 0.f; }
+    }
     if (g < groups) {
       const int spg = CN_SPB / groups;
       switch (spg) {
-        case 16: cn_layer<16>(src, dst, stride, gout, J.w[l], J.b[l], K, N, last, J.tril_dim, nS, g * 16, col, cpp); break;
-        case 8:  cn_layer<8>(src, dst, stride, gout, J.w[l], J.b[l], K, N, last, J.tril_dim, nS, g * 8, col, cpp); break;
-        case 4:  cn_layer<4>(src, dst, stride, gout, J.w[l], J.b[l], K, N, last, J.tril_dim, nS, g * 4, col, cpp); break;
-        default: cn_layer<2>(src, dst, stride, gout, J.w[l], J.b[l], K, N, last, J.tril_dim, nS, g * 2, col, cpp); break;
+        case 16: cn_layer<16>(src, dstf, gout, J.w[l], J.b[l], K, N, last, J.tril_dim, nS, g * 16, col, cpp); break;
+        case 8:  cn_layer<8>(src, dstf, gout, J.w[l], J.b[l], K, N, last, J.tril_dim, nS, g * 8, col, cpp); break;
+        case 4:  cn_layer<4>(src, dstf, gout, J.w[l], J.b[l], K, N, last, J.tril_dim, nS, g * 4, col, cpp); break;
+        default: cn_layer<2>(src, dstf, gout, J.w[l], J.b[l], K, N, last, J.tril_dim, nS, g * 2, col, cpp); break;
       }
     }
-    if (!last) {                                         // zero the K-padding columns the next layer's 128-bit loads touch
-      const int N4 = (N + 3) & ~3;
-      if (N4 != N) for (int idx = tid; idx < CN_SPB * (N4 - N); idx += CN_THREADS) { const int s = idx / (N4 - N); dst[s * stride + N + idx % (N4 - N)] = 0.f; }
-      __syncthreads();
-      float* t = src; src = dst; dst = t;
-    }
+    if (!last) { __syncthreads(); float4* t = src; src = dst; dst = t; }
   }
 }
 
