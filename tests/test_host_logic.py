@@ -1,0 +1,64 @@
+"""CPU tests of the host-side logic that needs no kernel launch: the fused log_prob plan's segmentation of the BASELINE stacks, the
+reference arm of bench.py, and the C-ABI descriptors the Python layer builds."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from contextflow_b200 import builder, synth
+from contextflow_b200.layers._fastpath import FastLogProb, _ConvAct, _Coup, _Generic, _Prologue
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _segments(name):
+    model = builder.build_named(synth.CONFIGS[name])
+    return model, FastLogProb(model).segs
+
+
+def test_fused_plan_segments_cfg2():
+    model, segs = _segments('cfg2')
+    kinds = [type(s).__name__ for s in segs]
+    assert kinds[0] == '_Prologue' and len(segs[0].mods) == 5                      # Dequant, Norm, Norm, Logit, Augment (model.py:97-100,121-123)
+    assert kinds.count('_ConvAct') == 12 and kinds.count('_Coup') == 12            # 3 levels x 4 steps (SURVEY §8 stack table)
+    assert sum(len(s.mods) for s in segs) == len(model.sequence_modules)            # every layer belongs to exactly one segment, in order
+    flat = [m for s in segs for m in s.mods]
+    assert all(a is b for a, b in zip(flat, model.sequence_modules))
+    # context pre-pass: one CN job per contextual Conv1x1 / ActNorm / Coupling, the Conv1x1 ones flagged lower-triangular
+    jobs = [j for s in segs if isinstance(s, (_ConvAct, _Coup)) for j in s.cn_jobs()]
+    assert len(jobs) == 36
+    assert sorted({tril for _, _, tril, _, _ in jobs}) == [0, 16, 32, 64]
+
+
+@pytest.mark.parametrize('name,n_conv,n_coup,prologue', [('cfg1', 4, 4, True), ('cfg3', 12, 12, False), ('cfg4', 8, 8, False)])
+def test_fused_plan_segments_other_stacks(name, n_conv, n_coup, prologue):
+    model, segs = _segments(name)
+    kinds = [type(s).__name__ for s in segs]
+    assert (kinds[0] == '_Prologue') == prologue
+    assert kinds.count('_ConvAct') == n_conv and kinds.count('_Coup') == n_coup
+    assert sum(len(s.mods) for s in segs) == len(model.sequence_modules)
+
+
+def test_fused_plan_is_not_used_on_cpu_tensors():
+    model, _ = _segments('cfg1')
+    x, ctx = synth.make_inputs(synth.CONFIGS['cfg1'], 2, 'h0')
+    with torch.no_grad():
+        assert not FastLogProb(model).usable(x, ctx)                                 # CPU tensors: the plan (and every kernel) is CUDA only
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        with torch.no_grad():
+            model.log_prob(x, ctx)
+
+
+def test_reference_arm_prints_one_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', 'cfg4', '--batch', '64',
+                          '--steps', '1', '--warmup', '1'], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'flow_log_prob_samples_per_sec' and d['value'] > 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e'] == {'value': d['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
