@@ -37,34 +37,69 @@ def parse():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks + throttle reasons during the timed region (B200_PROFILING.md recipe).  NVML through pynvml when importable (a
+    sample per ~20 ms), else the recipe's nvidia-smi query line (one sample per ~0.3 s).  Samples carry a timestamp; summary() keeps
+    those inside the timed window [t0, t1] and, when the window was too short for any, the nearest ones taken under the same load."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+        except Exception:
+            power = 0.0
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        bits = [getattr(n, 'nvmlClocksEventReasonHwSlowdown', 0x8), getattr(n, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+                getattr(n, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20), getattr(n, 'nvmlClocksEventReasonSwPowerCap', 0x4)]
+        return [sm, self.max_sm, power] + [bool(mask & b) for b in bits]
+
+    def _sample_smi(self):
+        out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        c = [v.strip() for v in out.split(',')]
+        return [float(c[0]), float(c[1]), float(c[2])] + [v.lower().startswith('active') for v in c[3:7]]
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(',')])
+                row = self._sample_nvml() if self.nvml is not None else self._sample_smi()
+                self.rows.append((time.perf_counter(), row))
             except Exception:
                 pass
-            self.stop_flag.wait(0.05)
+            self.stop_flag.wait(0.02 if self.nvml is not None else 0.05)
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
         self.stop_flag.set()
-        if not self.rows:
+        rows = [r for t, r in self.rows if t0 is None or (t0 <= t <= t1)]
+        window = 'timed region'
+        if not rows and self.rows:                                      # window shorter than one sample: the samples closest to it (warm-up / e2e legs, same load)
+            mid = 0.5 * (t0 + t1)
+            rows = [r for _, r in sorted(self.rows, key=lambda tr: abs(tr[0] - mid))[:3]]
+            window = 'nearest samples (timed region shorter than the sampling period)'
+        if not rows:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unsampled']}
-        sm = [float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith('active') for r in self.rows)]
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons,
-                'samples': len(self.rows), 'power_w_max': max(float(r[2]) for r in self.rows)}
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[3 + i] for r in rows)]
+        return {'sm_mhz': statistics.median(r[0] for r in rows), 'sm_max_mhz': rows[0][1], 'reasons': reasons, 'samples': len(rows),
+                'power_w_max': max(r[2] for r in rows), 'window': window, 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 def cpu_reference_run(workload, batch, steps, warmup, device='cpu'):
@@ -185,26 +220,27 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local); sampler.start()
     for i in range(max(a.warmup, 3)):
         step(i)
     barrier()
-    sampler = ClockSampler(local); sampler.start()
     l0 = _cabi.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     prof_range = os.environ.get('CFPP_PROFILE_RANGE') == '1'       # ncu --profile-from-start off: capture the timed steps only
     if prof_range:
         torch.cuda.profiler.start()
+    t_begin = time.perf_counter()
     ev0.record()
     for i in range(a.steps):
         step(i)
     ev1.record()
     barrier()
+    t_end = time.perf_counter()
     if prof_range:
         torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = _cabi.launch_count() - l0 if graphed is None else graphed.launches_per_replay(*devb[0]) * a.steps
-    clocks = sampler.summary()
     # per-kernel durations: the same steps launched eagerly with a CUDA-event pair around every libcfpp launch (events cannot be
     # read back from inside a replayed graph); same kernels, same inputs, right after the timed region
     timer = ops.OpTimer(); ops.set_timer(timer)
@@ -243,6 +279,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
 
+    clocks = sampler.summary(t_begin, t_end)
     if saved_stdout is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
@@ -299,7 +336,10 @@ def main():
                 'e2e': {'value': world * B * a.steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': x0.numel() * 4 + c0.numel() * 8, 'd2h_bytes_per_step': B * world * M * 4},
                 'roofline': roof, 'roofline_coupling': roof_c, 'kernels': kernels}
         if world == 1 and not a.no_cpu_baseline:
-            base, _ = cpu_reference_run(workload, REF_BATCH[workload], 2, 1)
+            # bounded sample of the same workload on the host cores: ~10 s of CPU work (probe one step, then as many as fit)
+            probe, dt1 = cpu_reference_run(workload, REF_BATCH[workload], 1, 1)
+            nsteps = max(2, min(60, int(10.0 / max(dt1, 1e-3))))
+            base, _ = cpu_reference_run(workload, REF_BATCH[workload], nsteps, 0)
             line['cpu_baseline'] = base
         print(json.dumps(line))
     if world > 1:
