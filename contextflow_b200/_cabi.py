@@ -72,6 +72,9 @@ _SIGNATURES = {
     'cfpp_vit_tc_pack_bytes': (i64, [i32]),
     'cfpp_vit_tc_pack_chunk': (i32, [vp, i32, i32, i32, vp, vp]),
     'cfpp_vit_tc_fwd': (i32, [vp, i64, vp, C.POINTER(VitDesc), vp, i32, vp]),
+    'cfpp_vit_tc2_supported': (i32, [i32, i32, i32, i32]),
+    'cfpp_vit_tc2_chunks': (i64, [i32, i32, i32]),
+    'cfpp_vit_tc2_fwd': (i32, [vp, i64, vp, C.POINTER(VitDesc), vp, i32, vp]),
     'cfpp_gmm_logprob': (i32, [vp, i64, vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, vp]),
     'cfpp_gmm_logprob_ctxtab': (i32, [vp, i64, vp, vp, vp, vp, i32, C.POINTER(i32), C.POINTER(vp), i32, vp, f32, vp, vp, i64,
                                       i32, i32, i32, i32, i32, vp]),

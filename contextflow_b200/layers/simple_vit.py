@@ -102,19 +102,31 @@ class SimpleViT(nn.Module):
         return d
 
     def _tc_pack(self):
-        """fp16 hi/lo weight stream of the tensor-core kernel (chunk order of cfpp_vit_tc_fwd), or None when the shape has no plan."""
+        """(fp16 hi/lo weight stream, general) of the tensor-core kernels, or None when the shape has no plan.  general=False: one
+        64 x 64 chunk per matrix (cfpp_vit_tc_fwd, T <= 64 and tokens dividing 32); True: one chunk per (64-row output block, 64-column
+        input block), output block outer (cfpp_vit_tc2_fwd)."""
         g = self.geom
-        if not _cabi.lib().cfpp_vit_tc_supported(g['T'], g['patch_dim'], g['n_tok'], 0):
+        lib = _cabi.lib()
+        T, pd = g['T'], g['patch_dim']
+        small = bool(lib.cfpp_vit_tc_supported(T, pd, g['n_tok'], 0))
+        if not small and not lib.cfpp_vit_tc2_supported(T, pd, g['n_tok'], 0):
             return None
 
+        def blocks(w, n_out, k_in):
+            out = []
+            for n0 in range(0, n_out, 64):
+                for k0 in range(0, k_in, 64):
+                    out.append((w[n0: n0 + 64, k0: k0 + 64], min(64, n_out - n0), min(64, k_in - k0)))
+            return out
+
         def build():
-            T = g['T']
-            mats = [(self.to_patch_embedding[2].weight, T, g['patch_dim'])]
+            mats = blocks(self.to_patch_embedding[2].weight, T, pd)
             for attn, ff in self.transformer.layers:
-                wqkv = attn.to_qkv.weight
-                mats += [(wqkv[0:64], 64, T), (wqkv[64:128], 64, T), (wqkv[128:192], 64, T), (attn.to_out.weight, T, 64),
-                         (ff.net[1].weight, T, T), (ff.net[3].weight, T, T)]
-            return ops.vit_tc_pack(mats)
+                mats += blocks(attn.to_qkv.weight, 192, T) + blocks(attn.to_out.weight, T, 64)
+                mats += blocks(ff.net[1].weight, T, T) + blocks(ff.net[3].weight, T, T)
+            if not small:
+                assert len(mats) == int(lib.cfpp_vit_tc2_chunks(T, pd, g['depth']))
+            return ops.vit_tc_pack(mats), not small
         return self._packs.get('tc', self._sources(), build)
 
     def forward(self, img, extra=None):
@@ -123,7 +135,7 @@ class SimpleViT(nn.Module):
         cextra = 0 if extra is None else extra.shape[1]
         cout = g['T'] // (g['p1'] * g['p2'])
         if extra is None and img.is_cuda and ops.vit_tc_mode() != 'fma':
-            pack = self._tc_pack()
-            if pack is not None:
-                return ops.vit_cond_tc(img, self.descriptor(g['Cin']), pack, cout)
+            pk = self._tc_pack()
+            if pk is not None:
+                return ops.vit_cond_tc(img, self.descriptor(g['Cin']), pk[0], cout, general=pk[1])
         return ops.vit_cond(img, self.descriptor(g['Cin'] - cextra), cout, extra)

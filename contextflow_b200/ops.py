@@ -349,13 +349,14 @@ def vit_tc_pack(mats):
     return out
 
 
-def vit_cond_tc(x, desc: _cabi.VitDesc, wpack, cout):
+def vit_cond_tc(x, desc: _cabi.VitDesc, wpack, cout, general=False):
+    """general=False: cfpp_vit_tc_fwd (T <= 64, residual stream in registers); True: cfpp_vit_tc2_fwd (T <= 192, any token count)."""
     _need_cuda(x, wpack)
     xv, bstride = _half_view(x)
     B = x.shape[0]
     h = torch.empty((B, cout, desc.H, desc.W), device=x.device, dtype=torch.float32)
     _set_work(bytes=4.0 * B * desc.H * desc.W * (desc.Cin + cout), flops=2.0 * B * desc.n_tok * (desc.patch_dim * desc.T + desc.depth * (desc.T * 192 + 2 * desc.n_tok * 64 + 64 * desc.T + 2 * desc.T * desc.T)))
-    _call('vit_tc_fwd', (_p(xv), bstride, _p(h), C.byref(desc), _p(wpack), B, _stream()), 'vit_cond_tc_fwd')
+    _call('vit_tc2_fwd' if general else 'vit_tc_fwd', (_p(xv), bstride, _p(h), C.byref(desc), _p(wpack), B, _stream()), 'vit_cond_tc_fwd')
     return h
 
 
