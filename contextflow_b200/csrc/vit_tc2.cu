@@ -19,15 +19,15 @@ namespace vt2 {
 using namespace vtx;
 
 constexpr int kRows = 128, kPanels = 3;
-constexpr int kThreads = 192, kStages = 2;
+constexpr int kThreads = 192, kMaxStages = 8;       // ring slots: as many 16 KB weight chunks as the shared memory left by the tile allows
 constexpr int kChunkBytes = 2 * kW * 128;           // [hi image 64 rows x 128 B][lo image]
 constexpr int kPanelBytes = 2 * kRows * 128;        // hi rows + lo rows of one 64-channel operand panel
 
 struct Args {
-  const float* x; int64_t x_bstride; float* h; cfpp_vit_desc d; const uint8_t* wpack; int B, S, ntiles, NPT, P, PD, XS;
+  const float* x; int64_t x_bstride; float* h; cfpp_vit_desc d; const uint8_t* wpack; int B, S, ntiles, NPT, P, PD, XS, nstages, xrows;
 };
 
-enum { BAR_FULL = 0, BAR_EMPTY = kStages, BAR_AREADY = 2 * kStages, BAR_ACC, BAR_COUNT };
+enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_AREADY = 2 * kMaxStages, BAR_ACC, BAR_COUNT };
 
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 128 compute threads
 
@@ -75,9 +75,10 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc2_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t vt2_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(vt2_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* ops = base;                                        // kPanels x [hi 128 rows x 128 B][lo]
-  uint8_t* ring = ops + kPanels * kPanelBytes;                // kStages x kChunkBytes
-  float* X = reinterpret_cast<float*>(ring + kStages * kChunkBytes);       // [128][XS]
-  float* lprm = X + kRows * a.XS;                             // [6][P * 64]: lna_w lna_b lnf_w lnf_b b1 b2 of the current layer, zero padded
+  uint8_t* ring = ops + kPanels * kPanelBytes;                // nstages x kChunkBytes
+  const int kStages = a.nstages;
+  float* X = reinterpret_cast<float*>(ring + kStages * kChunkBytes);       // [xrows][XS]: only the rows that hold tokens
+  float* lprm = X + a.xrows * a.XS;                             // [6][P * 64]: lna_w lna_b lnf_w lnf_b b1 b2 of the current layer, zero padded
   const int PW = a.P * kW;
   const uint32_t bars = smem_u32(lprm + 6 * PW);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lprm + 6 * PW) + 2 * BAR_COUNT;
@@ -153,7 +154,8 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc2_kernel(const Args a) {
     const int HW = d.H * d.W, tw = d.W / d.p2, Cout = T / (d.p1 * d.p2);
     const int64_t lstride = 4 * (int64_t)T + (int64_t)T * 192 + 64 * (int64_t)a.NPT + 2 * (int64_t)T * a.NPT + 2 * (int64_t)a.NPT;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    float* xrow = X + r * XS;
+    const bool rowok = r < a.xrows;                                 // rows beyond the tile's tokens own no x row: they read row 0 and never write
+    float* xrow = X + (rowok ? r : 0) * XS;
     uint32_t nacc = 0;
     auto a_ready = [&]() { fence_async_smem(); mbar_arrive(bar(BAR_AREADY)); };
     auto acc_wait = [&]() { mbar_wait(bar(BAR_ACC), nacc & 1); ++nacc; tc_fence_after(); };
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc2_kernel(const Args a) {
           const int c = f % d.Cin, pp = f / d.Cin, i = pp / d.p2, j = pp - i * d.p2;
           v = __ldg(a.x + (int64_t)(b0 + s) * a.x_bstride + (int64_t)c * HW + (th * d.p1 + i) * d.W + (tww * d.p2 + j));
         }
-        xrow[f] = v;
+        if (rowok) xrow[f] = v;
       }
       ln_to_operands(d.patch_dim, PD, d.ln0_w, d.ln0_b, true);
       a_ready();
@@ -198,13 +200,13 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc2_kernel(const Args a) {
         load_acc_row(trow + c * 2 * kW, v);
 #pragma unroll
         for (int i = 0; i < kW; ++i) { const int col = 64 * c + i; v[i] += col < T ? __ldg(d.pe_b + col) : 0.f; }
-        store_x_chunk(xrow, c, T, v);
+        if (rowok) store_x_chunk(xrow, c, T, v);
       }
       tc_fence_before();
       {
         float mean, rstd;
         ln_stats(xrow, T, mean, rstd);
-        for (int i = 0; i < T; ++i) xrow[i] = fmaf((xrow[i] - mean) * rstd, __ldg(d.ln1_w + i), __ldg(d.ln1_b + i)) + __ldg(d.pos + tok * T + i);
+        if (rowok) for (int i = 0; i < T; ++i) xrow[i] = fmaf((xrow[i] - mean) * rstd, __ldg(d.ln1_w + i), __ldg(d.ln1_b + i)) + __ldg(d.pos + tok * T + i);
       }
 
       for (int l = 0; l < depth; ++l) {
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc2_kernel(const Args a) {
           load_x_chunk(xrow, c, T, xv);
 #pragma unroll
           for (int i = 0; i < kW; ++i) xv[i] += v[i];
-          store_x_chunk(xrow, c, T, xv);
+          if (rowok) store_x_chunk(xrow, c, T, xv);
         }
         tc_fence_before();
         // ---- MLP: x += W2 gelu(W1 LN(x) + b1) + b2 ----
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc2_kernel(const Args a) {
           const float* pb2 = lprm + 5 * PW + 64 * c;
 #pragma unroll
           for (int i = 0; i < kW; ++i) xv[i] += v[i] + pb2[i];
-          store_x_chunk(xrow, c, T, xv);
+          if (rowok) store_x_chunk(xrow, c, T, xv);
         }
         tc_fence_before();
       }
@@ -331,8 +333,13 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc2_kernel(const Args a) {
 }
 
 static int xs_of(int T) { int xs = (T + 3) & ~3; while ((xs & 7) != 4) xs += 4; return xs; }
-static size_t smem_bytes(int T, int P) {
-  return 1024 + (size_t)kPanels * kPanelBytes + (size_t)kStages * kChunkBytes + (size_t)kRows * xs_of(T) * 4 + (size_t)6 * P * kW * 4 + BAR_COUNT * 8 + 64;
+static size_t fixed_bytes(int T, int P, int xrows) {
+  return 1024 + (size_t)kPanels * kPanelBytes + (size_t)xrows * xs_of(T) * 4 + (size_t)6 * P * kW * 4 + BAR_COUNT * 8 + 64;
+}
+static int stages_for(int T, int P, int xrows) {
+  const long long left = 227LL * 1024 - (long long)fixed_bytes(T, P, xrows);
+  long long n = left / kChunkBytes;
+  return (int)(n > kMaxStages ? kMaxStages : n);
 }
 
 }  // namespace vt2
@@ -341,7 +348,7 @@ using namespace cfpp;
 
 extern "C" int cfpp_vit_tc2_supported(int T, int patch_dim, int n_tok, int Cextra) {
   if (!(T >= 4 && T % 4 == 0 && T <= 192 && patch_dim >= 1 && patch_dim <= T && Cextra == 0 && n_tok >= 1 && n_tok <= vt2::kRows)) return 0;
-  return vt2::smem_bytes(T, (T + 63) / 64) <= 227 * 1024 ? 1 : 0;
+  return vt2::stages_for(T, (T + 63) / 64, (vt2::kRows / n_tok) * n_tok) >= 2 ? 1 : 0;
 }
 
 /* chunks of the weight stream: embed (P x PD), then per layer qkv (3 x P), out (P x 1), mlp1 (P x P), mlp2 (P x P); P = ceil(T/64) */
@@ -357,9 +364,11 @@ extern "C" int cfpp_vit_tc2_fwd(const float* x, int64_t x_bstride, float* h, con
   CFPP_REQUIRE(d.n_tok == (d.H / d.p1) * (d.W / d.p2) && d.patch_dim == d.Cin * d.p1 * d.p2 && d.T % (d.p1 * d.p2) == 0, "vit_tc2: inconsistent descriptor");
   CFPP_REQUIRE((reinterpret_cast<uintptr_t>(wpack) & 15) == 0, "vit_tc2: wpack must be 16-byte aligned");
   if (B <= 0) return CFPP_OK;
-  vt2::Args a{x, x_bstride, h, d, (const uint8_t*)wpack, B, vt2::kRows / d.n_tok, 0, (d.T + 15) / 16 * 16, (d.T + 63) / 64, (d.patch_dim + 63) / 64, vt2::xs_of(d.T)};
+  vt2::Args a{x, x_bstride, h, d, (const uint8_t*)wpack, B, vt2::kRows / d.n_tok, 0, (d.T + 15) / 16 * 16, (d.T + 63) / 64, (d.patch_dim + 63) / 64, vt2::xs_of(d.T), 0, 0};
   a.ntiles = (B + a.S - 1) / a.S;
-  const size_t smem = vt2::smem_bytes(d.T, a.P);
+  a.xrows = a.S * d.n_tok;
+  a.nstages = vt2::stages_for(d.T, a.P, a.xrows);
+  const size_t smem = vt2::fixed_bytes(d.T, a.P, a.xrows) + (size_t)a.nstages * vt2::kChunkBytes;
   static size_t attr = 0;
   if (smem > attr) { cudaFuncSetAttribute(vt2::vit_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
   const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
