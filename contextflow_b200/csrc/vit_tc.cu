@@ -311,16 +311,22 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc_kernel(const Args a) {
               d0 = fmaf(y[4 * q], k4.x, d0); d1 = fmaf(y[4 * q + 1], k4.y, d1); d2 = fmaf(y[4 * q + 2], k4.z, d2); d3 = fmaf(y[4 * q + 3], k4.w, d3);
             }
             const float dot = ((d0 + d1) + (d2 + d3)) * 0.125f;    // dim_head ** -0.5
-            const float nm = fmaxf(mx, dot), corr = __expf(mx - nm), pj = __expf(dot - nm);
-            den = den * corr + pj;
+            if (dot > mx) {                                             // a new running maximum: rescale what was accumulated
+              const float corr = __expf(mx - dot);
+              den *= corr;
+#pragma unroll
+              for (int i = 0; i < kW; ++i) o[i] *= corr;
+              mx = dot;
+            }
+            const float pj = __expf(dot - mx);
+            den += pj;
             const float* vr = Vs + (r0 + j) * kKVStride;
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
               const float4 v4 = *reinterpret_cast<const float4*>(vr + 4 * q);
-              o[4 * q] = fmaf(o[4 * q], corr, pj * v4.x); o[4 * q + 1] = fmaf(o[4 * q + 1], corr, pj * v4.y);
-              o[4 * q + 2] = fmaf(o[4 * q + 2], corr, pj * v4.z); o[4 * q + 3] = fmaf(o[4 * q + 3], corr, pj * v4.w);
+              o[4 * q] = fmaf(pj, v4.x, o[4 * q]); o[4 * q + 1] = fmaf(pj, v4.y, o[4 * q + 1]);
+              o[4 * q + 2] = fmaf(pj, v4.z, o[4 * q + 2]); o[4 * q + 3] = fmaf(pj, v4.w, o[4 * q + 3]);
             }
-            mx = nm;
           }
           const float inv = 1.0f / den;
 #pragma unroll

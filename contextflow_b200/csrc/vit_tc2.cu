@@ -260,16 +260,22 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc2_kernel(const Args a) {
                 d0 = fmaf(q[4 * qq], k4.x, d0); d1 = fmaf(q[4 * qq + 1], k4.y, d1); d2 = fmaf(q[4 * qq + 2], k4.z, d2); d3 = fmaf(q[4 * qq + 3], k4.w, d3);
               }
               const float dot = ((d0 + d1) + (d2 + d3)) * 0.125f;
-              const float nm = fmaxf(mx, dot), corr = __expf(mx - nm), pj = __expf(dot - nm);
-              den = den * corr + pj;
+              if (dot > mx) {                                           // a new running maximum (rare after the first keys): rescale what was accumulated
+                const float corr = __expf(mx - dot);
+                den *= corr;
+#pragma unroll
+                for (int i = 0; i < kW; ++i) o[i] *= corr;
+                mx = dot;
+              }
+              const float pj = __expf(dot - mx);
+              den += pj;
               const float* vr = Vs + rj * kW;
 #pragma unroll
               for (int qq = 0; qq < 16; ++qq) {
                 const float4 v4 = *reinterpret_cast<const float4*>(vr + 4 * (qq ^ sw));
-                o[4 * qq] = fmaf(o[4 * qq], corr, pj * v4.x); o[4 * qq + 1] = fmaf(o[4 * qq + 1], corr, pj * v4.y);
-                o[4 * qq + 2] = fmaf(o[4 * qq + 2], corr, pj * v4.z); o[4 * qq + 3] = fmaf(o[4 * qq + 3], corr, pj * v4.w);
+                o[4 * qq] = fmaf(pj, v4.x, o[4 * qq]); o[4 * qq + 1] = fmaf(pj, v4.y, o[4 * qq + 1]);
+                o[4 * qq + 2] = fmaf(pj, v4.z, o[4 * qq + 2]); o[4 * qq + 3] = fmaf(pj, v4.w, o[4 * qq + 3]);
               }
-              mx = nm;
             }
             const float inv = 1.0f / den;
 #pragma unroll
