@@ -89,6 +89,16 @@ _SIGNATURES = {
     'cfpp_embed_lookup': (i32, [vp, C.POINTER(vp), i32, i32, vp, i32, vp]),
     'cfpp_linear_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     'cfpp_cn_batch': (i32, [C.POINTER(CnJob), i32, C.POINTER(vp), C.POINTER(vp), i32, vp]),
+    'cfpp_coupling_inv': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    'cfpp_actnorm_inv': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    'cfpp_mat_inverse': (i32, [vp, i32, vp, vp, vp]),
+    'cfpp_sigmoid_fwd': (i32, [vp, vp, i64, vp]),
+    'cfpp_normalize_inv': (i32, [vp, vp, i64, f32, f32, vp]),
+    'cfpp_floor_fwd': (i32, [vp, vp, i64, vp]),
+    'cfpp_prologue_inv': (i32, [vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32, i32, vp]),
+    'cfpp_gmm_sample': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    'cfpp_score_workspace_bytes': (i64, [i32]),
+    'cfpp_score_epilogue': (i32, [vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
     'cfpp_ldj_accumulate': (i32, [vp, vp, i32, i32, i32, vp]),
     'cfpp_ldj_sum': (i32, [vp, vp, vp, C.POINTER(vp), C.POINTER(i32), i32, i32, i32, vp]),
 }

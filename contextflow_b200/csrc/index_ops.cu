@@ -39,6 +39,22 @@ __global__ void __launch_bounds__(256) squeeze22_kernel(const float* __restrict_
   }
 }
 
+// The inverse: two 128-bit streaming loads from the planes j = 0 / 1, one interleaved 32-byte row segment out.
+__global__ void __launch_bounds__(256) unsqueeze22_kernel(const float* __restrict__ y, float* __restrict__ x, int64_t units, int H, int W) {
+  const int W8 = W >> 3, Ho = H >> 1, Wo = W >> 1;
+  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < units; u += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = u / W8; const int wq = (int)(u - r * W8);
+    const int64_t bc = r / H; const int hi = (int)(r - bc * H);
+    const int h = hi >> 1, i = hi & 1;
+    const float* src = y + ((bc * 4 + i * 2) * Ho + h) * (int64_t)Wo + wq * 4;
+    const float4 a = ldg_stream(reinterpret_cast<const float4*>(src));
+    const float4 b = ldg_stream(reinterpret_cast<const float4*>(src + (int64_t)Ho * Wo));
+    float4* dst = reinterpret_cast<float4*>(x + r * W + wq * 8);
+    stg_stream(dst, make_float4(a.x, b.x, a.y, b.y));
+    stg_stream(dst + 1, make_float4(a.z, b.z, a.w, b.w));
+  }
+}
+
 // ---- PermuteAxes (0,2,1,3): y[b,h,c,w] = x[b,c,h,w];  32x32 smem tile transpose over (c,h) per (b,w) ---------
 __global__ void permute_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int H, int W) {
   __shared__ float tile[32][33];
@@ -152,7 +168,10 @@ extern "C" int cfpp_squeeze_inv(const float* y, float* x, int B, int C, int H, i
   CFPP_REQUIRE(B >= 0 && C > 0 && p1 > 0 && p2 > 0 && H % p1 == 0 && W % p2 == 0, "squeeze_inv: bad dims");
   int64_t total = (int64_t)B * C * H * W;
   if (!total) return CFPP_OK;
-  squeeze_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(y, x, total, C, H, W, p1, p2, true);
+  if (p1 == 2 && p2 == 2 && W % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)
+    unsqueeze22_kernel<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(y, x, total / 8, H, W);
+  else
+    squeeze_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(y, x, total, C, H, W, p1, p2, true);
   return check_launch("squeeze_inv");
 }
 extern "C" int cfpp_permute_fwd(const float* x, float* y, int B, int C, int H, int W, void* stream) {

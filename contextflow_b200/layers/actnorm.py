@@ -71,7 +71,14 @@ class ActNorm(FlowActivationLayer):
         return ops.actnorm(x, self.NN_t.detach(), self.NN_logs.detach())
 
     def reverse(self, z, context=None):
-        raise NotImplementedError('inverse path is outside this round (SURVEY §8f-3)')
+        """actnorm.py:62-79: x = z * exp(logs) + t.  The reference's context branch calls rearrange on the (c, logp_c) tuple its
+        context_net returns (:65) and cannot run, so only the context-free form exists."""
+        inference_only(self.NN_t); inference_only(z)
+        if self.context_net:
+            raise NotImplementedError('ActNorm.reverse with a context_net is not executable in the reference (actnorm.py:65); '
+                                      'only context-free (generalist) layers invert')
+        assert self.is_initialized()                                  # actnorm.py:74
+        return ops.actnorm_inv(z, self.NN_t.detach(), self.NN_logs.detach())
 
     def logdet(self, x, context=None):
         return self.forward(x, context)[1]
@@ -84,6 +91,9 @@ class ActNormFC(ActNorm):
     def forward(self, x, context=None):
         out, ldj = super().forward(x.reshape(-1, self.D, 1, 1), context)
         return out.view(-1, self.D), ldj
+
+    def reverse(self, z, context=None):
+        return super().reverse(z.reshape(-1, self.D, 1, 1), context).view(-1, self.D)
 
     def logdet(self, x, context=None):
         return self.forward(x, context)[1]

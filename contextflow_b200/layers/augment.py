@@ -23,7 +23,10 @@ class Augment(FlowLayer):
         return y, ldj.unsqueeze(-1)
 
     def reverse(self, input, context=None):
-        return input[:, : input.shape[self.split_dim] - self.aug_size].contiguous()
+        keep = input.shape[self.split_dim] - self.aug_size             # augment.py:20-23: drop the noise channels
+        if input.dim() == 4 and self.split_dim == 1:
+            return ops.slice_channels(input, 0, keep)
+        return input[:, :keep].contiguous()
 
     def logdet(self, input, context=None):
         raise NotImplementedError

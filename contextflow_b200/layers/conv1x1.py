@@ -44,8 +44,23 @@ class Conv1x1(FlowLayer):
             return ops.conv1x1(x, self.NN.detach(), lad, cm, logp_c, self.contextflow)
         return ops.conv1x1(x, self.NN.detach(), lad)
 
+    def inverse_matrix(self):
+        """torch.inverse(NN) (conv1x1.py:70), recomputed only when NN changes; a singular NN raises like torch.inverse does."""
+        def build():
+            inv, flag = ops.mat_inverse(self.NN.detach())
+            if int(flag.item()):
+                raise RuntimeError('Conv1x1.reverse: NN is singular')
+            return inv
+        return self._packs.get('inverse', [self.NN], build)
+
     def reverse(self, z, context=None):
-        raise NotImplementedError('inverse path is outside this round (SURVEY §8f-3)')
+        """conv1x1.py:59-72.  Only the context-free branch is executable in the reference: its context branch reads
+        `w_ginv` before assigning it (:62) and multiplies by the nn.Linear module `self.CN`, so there is nothing to be on par with."""
+        inference_only(self.NN); inference_only(z)
+        if self.context_net:
+            raise NotImplementedError('Conv1x1.reverse with a context_net is not executable in the reference (conv1x1.py:62); '
+                                      'only context-free (generalist) layers invert')
+        return ops.conv1x1(z, self.inverse_matrix(), self.logabsdet())[0]
 
     def logdet(self, input, context=None):
         return self.forward(input, context)[1]
@@ -60,6 +75,9 @@ class FC(Conv1x1):
     def forward(self, x, context=None):
         out, ldj = super().forward(x.reshape(-1, self.D, 1, 1), context)
         return out.view(-1, self.D), ldj
+
+    def reverse(self, z, context=None):
+        return super().reverse(z.reshape(-1, self.D, 1, 1), context).view(-1, self.D)
 
     def logdet(self, x, context=None):
         return self.forward(x, context)[1]

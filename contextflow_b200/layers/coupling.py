@@ -36,9 +36,6 @@ class _CouplingBase(FlowLayer):
         h = ops.linear(h, packs[1], lin[1].bias.detach(), relu=True)
         return ops.linear(h, packs[2], lin[2].bias.detach()), logp_c
 
-    def reverse(self, z, context=None):
-        raise NotImplementedError('inverse path is outside this round (SURVEY §8f-3)')
-
     def logdet(self, input, context=None):
         return self.forward(input, context)[1]
 
@@ -113,6 +110,19 @@ class Coupling(_CouplingBase):
                 or ops.coupling(x, self._conditioner(x, pk, bias1_b=bias1), logp_c=logp_c, logp_scale=float(Hh * Ww)))
 
 
+    def reverse(self, z, context=None):
+        """coupling.py:68-73: the conditioner sees z0 = x0, so h is the forward pass's h; x1 = (z1 - t) / s."""
+        inference_only(z)
+        pk = self._packed_nn()
+        if not self.context_net:
+            return ops.coupling_inv(z, self._conditioner(z, pk))
+        cn, _ = self._context_terms(context)
+        if self.contextflow:
+            return ops.coupling_inv(z, self._conditioner(z, pk), add=cn)
+        bias1 = ops.linear(cn, pk['ctx_w'], self.NN[0].bias.detach())
+        return ops.coupling_inv(z, self._conditioner(z, pk, bias1_b=bias1))
+
+
 class CouplingFC(Coupling):
     def __init__(self, data_channels, kernel_size=(1, 1), padding=(0, 0), context_net=None, contextflow=False):
         super().__init__(data_channels, kernel_size=(1, 1), padding=(0, 0), context_net=None, contextflow=False)
@@ -121,6 +131,9 @@ class CouplingFC(Coupling):
     def forward(self, x, context=None):
         out, ldj = super().forward(x.reshape(-1, self.D, 1, 1), context)
         return out.view(-1, self.D), ldj
+
+    def reverse(self, z, context=None):
+        return super().reverse(z.reshape(-1, self.D, 1, 1), context).view(-1, self.D)
 
     def logdet(self, x, context=None):
         return self.forward(x, context)[1]
@@ -154,6 +167,17 @@ class TransCoupling(_CouplingBase):
         if self.contextflow:
             return ops.coupling(x, vit(x), add=cn, logp_c=logp_c, logp_scale=1.0)
         return ops.coupling(x, vit(x, extra=cn), logp_c=logp_c, logp_scale=1.0)
+
+    def reverse(self, z, context=None):
+        """coupling.py:150-155."""
+        inference_only(z)
+        vit = self.NN if isinstance(self.NN, SimpleViT) else self.NN[0]
+        if not self.context_net:
+            return ops.coupling_inv(z, vit(z))
+        cn, _ = self._context_terms(context)
+        if self.contextflow:
+            return ops.coupling_inv(z, vit(z), add=cn)
+        return ops.coupling_inv(z, vit(z, extra=cn))
 
 
 class MaskedCoupling(FlowLayer):

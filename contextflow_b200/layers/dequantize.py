@@ -22,7 +22,7 @@ class Dequantization(PreprocessingFlowLayer):
         return ops.add(input, noise), input.new_zeros(input.shape[0])
 
     def reverse(self, input, context=None):
-        return input.floor()
+        return ops.floor(input)                                     # dequantize.py:19-20
 
     def logdet(self, input, context=None):
         raise NotImplementedError

@@ -94,7 +94,19 @@ class GaussianMixtureDistribution(nn.Module):
         return ops.gmm_logprob(input, self.mG, self.sG, self.wG)
 
     def sample(self, n_samples, context=None):
-        raise NotImplementedError('sampling / inverse path is outside this round (SURVEY §8f-3)')
+        """gaussian.py:163-169: draw from the context-free MixtureSameFamily(Categorical(softmax wG), Normal(mG, softplus sG)),
+        keep mixture m = 1 (`x[:, 1]`, so M >= 2 is required exactly as in the reference), return (x, log_prob(x, context)).
+        Same distribution as the reference, different generator stream: the reference draws all M*K component samples and gathers;
+        here one component index per sample (rng.multinomial) and one standard normal per element (rng.randn) are drawn."""
+        inference_only(self.mG)
+        if self.M < 2:
+            raise IndexError('index 1 is out of bounds for dimension 1 with size 1')     # gaussian.py:167 `x[:,1,...]`
+        dev = self.mG.device
+        probs = self._tables.get('w1', [self.wG], lambda: torch.softmax(self.wG.detach()[1].double(), -1).float())
+        comp = rng.multinomial(probs, n_samples)
+        eps = rng.randn((n_samples, *self.size), dev, self.mG.dtype)
+        x = ops.gmm_sample(self.mG.detach(), self.sG.detach(), comp, eps, m=1)
+        return x, self.log_prob(x, context)
 
 
 class ConditionalGaussianDistribution(nn.Module):

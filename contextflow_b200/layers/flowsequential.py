@@ -103,8 +103,43 @@ class FlowSequential(nn.Module):
                 return g(input, context)
         return self.log_prob_eager(input, context)
 
+    def reverse(self, z, context=None):
+        """The layer loop of flowsequential.py:34-37 from a given latent z (what `sample` runs after drawing z).  The image
+        prologue's four reverses + Augment.reverse run as one kernel when the stack starts the way create_model builds it."""
+        mods = list(self.sequence_modules)
+        tail = self._prologue_tail()
+        out = z
+        for module in reversed(mods[tail:] if tail else mods):
+            out = module.reverse(out, context)
+        if tail:
+            n0, n1 = mods[1], mods[2]
+            s0, t0, _ = n0.host_constants(); s1, t1, _ = n1.host_constants()
+            aug = mods[4].aug_size if tail == 5 else 0
+            out = ops.prologue_inv(out, out.shape[1] - aug, s1, t1, s0, t0, do_floor=True)
+        return out
+
+    def _prologue_tail(self):
+        """Number of leading layers covered by the fused inverse prologue (0, 4 or 5): Dequantization, Normalization x2 (scalar),
+        LogitTransform [, Augment on channels] -- model.py:97-100,121-123."""
+        import os
+        from .augment import Augment
+        from .dequantize import Dequantization
+        from .normalize import Normalization
+        from .transforms import LogitTransform
+        mods = list(self.sequence_modules)
+        if os.environ.get('CFPP_FASTPATH', '1') == '0' or len(mods) < 4:
+            return 0
+        if not (isinstance(mods[0], Dequantization) and isinstance(mods[1], Normalization) and isinstance(mods[2], Normalization)
+                and isinstance(mods[3], LogitTransform) and mods[1].scale.numel() == 1 and mods[2].scale.numel() == 1):
+            return 0
+        if len(mods) > 4 and isinstance(mods[4], Augment) and mods[4].split_dim == 1:
+            return 5
+        return 4
+
     def sample(self, n_samples, context=None):
-        raise NotImplementedError('sampling / inverse path is outside this round (SURVEY §8f-3)')
+        """flowsequential.py:32-39: z ~ dist, then every layer's reverse from last to first."""
+        z, _ = self.dist.sample(n_samples, context)
+        return self.reverse(z, context)
 
 
 class FlowInvSequential(nn.Module):

@@ -42,7 +42,7 @@ class Normalization(PreprocessingFlowLayer):
 
     def reverse(self, input, context=None):
         s, t, _ = self.host_constants()
-        return ops.normalize(input, 1.0 / s, -t * s)                 # (x - t) * s
+        return ops.normalize_inv(input, s, t)                        # (x - t) * s   (normalize.py:37-41)
 
     def logdet_value(self, C, D):
         """The per-sample ldj as a python float: float32 arithmetic in the reference's order, C * (-1 * D * log(scale))

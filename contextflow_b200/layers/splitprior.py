@@ -15,7 +15,9 @@ class SplitPrior(FlowLayer):
         return ops.slice_channels(x, 0, half), ldj
 
     def reverse(self, z, context=None):
-        raise NotImplementedError('inverse path is outside this round (SURVEY §8f-3)')
+        # splitprior.py:17-21 calls self.dist.sample(self.C, context) but SplitPrior never defines `C`: the reference raises
+        # AttributeError here, so models with split priors (cfg2, cfg3) have no executable inverse to be on par with
+        raise AttributeError("'SplitPrior' object has no attribute 'C'")
 
     def logdet(self, input, context=None):
         return self.forward(input, context)[1]

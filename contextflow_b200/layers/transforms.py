@@ -8,7 +8,7 @@ class LogitTransform(PreprocessingFlowLayer):
         return ops.logit(input)
 
     def reverse(self, input, context=None):
-        raise NotImplementedError('inverse path is outside this round (SURVEY §8f-3)')
+        return ops.sigmoid(input)                                   # transforms.py:14-15
 
     def logdet(self, input, context=None):
         return ops.logit(input)[1]

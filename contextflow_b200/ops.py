@@ -102,6 +102,7 @@ def unsqueeze(y, p1, p2):
     B, Cs, Hs, Ws = y.shape
     Cc, H, W = Cs // (p1 * p2), Hs * p1, Ws * p2
     x = torch.empty((B, Cc, H, W), device=y.device, dtype=y.dtype)
+    _set_work(bytes=8.0 * y.numel())
     _call('squeeze_inv', (_p(y), _p(x), B, Cc, H, W, p1, p2, _stream()), 'squeeze_inv')
     return x
 
@@ -231,6 +232,108 @@ def coupling(x, h, add=None, logp_c=None, logp_scale=0.0):
     _call('coupling_fwd', (_p(x), _p(h), _p(None if add is None else _f32(add)), _p(logp_c), float(logp_scale),
                                   _p(z), _p(ldj), B, Cc, HW, _stream()), 'coupling_fwd')
     return z, ldj
+
+
+def coupling_inv(z, h, add=None):
+    """Coupling.reverse core (coupling.py:68-73): x = cat(z0, (z1 - t) / s)."""
+    _need_cuda(z, h); z = _f32(z); h = _f32(h)
+    B, Cc = z.shape[0], z.shape[1]
+    HW = z[0, 0].numel() if B else 1
+    x = torch.empty_like(z)
+    _set_work(bytes=12.0 * z.numel())
+    _call('coupling_inv', (_p(z), _p(h), _p(None if add is None else _f32(add)), _p(x), B, Cc, HW, _stream()), 'coupling_inv')
+    return x
+
+
+# ---------------------------------------------------------------------------------------------- inverse direction
+def actnorm_inv(z, t, logs):
+    _need_cuda(z, t, logs); z = _f32(z)
+    B, D = z.shape[0], z.shape[1]
+    HW = z[0, 0].numel() if B else 1
+    x = torch.empty_like(z)
+    _set_work(bytes=8.0 * z.numel())
+    _call('actnorm_inv', (_p(z), _p(x), _p(_f32(t)), _p(_f32(logs)), B, D, HW, _stream()), 'actnorm_inv')
+    return x
+
+
+def mat_inverse(A):
+    """torch.inverse(NN) (conv1x1.py:70): returns (Ainv, singular flag as a device int tensor)."""
+    _need_cuda(A); A = _f32(A)
+    out = torch.empty_like(A); flag = torch.empty(1, device=A.device, dtype=torch.int32)
+    _call('mat_inverse', (_p(A), A.shape[0], _p(out), _p(flag), _stream()), 'mat_inverse')
+    return out, flag
+
+
+def sigmoid(x):
+    _need_cuda(x); x = _f32(x)
+    y = torch.empty_like(x)
+    _call('sigmoid_fwd', (_p(x), _p(y), x.numel(), _stream()), 'sigmoid_fwd')
+    return y
+
+
+def normalize_inv(y, scale: float, translation: float):
+    _need_cuda(y); y = _f32(y)
+    x = torch.empty_like(y)
+    _call('normalize_inv', (_p(y), _p(x), y.numel(), float(scale), float(translation), _stream()), 'normalize_inv')
+    return x
+
+
+def floor(x):
+    _need_cuda(x); x = _f32(x)
+    y = torch.empty_like(x)
+    _call('floor_fwd', (_p(x), _p(y), x.numel(), _stream()), 'floor_fwd')
+    return y
+
+
+def prologue_inv(z, C, s1, t1, s0, t0, do_floor=True, keep_cont=False):
+    """Augment / Logit / Normalization x2 / Dequantization reverses in one pass; z is (B, C + A, H, W)."""
+    _need_cuda(z); z = _f32(z)
+    B, CA, H, W = z.shape
+    x = torch.empty((B, C, H, W), device=z.device, dtype=z.dtype)
+    cont = torch.empty_like(x) if keep_cont else None
+    _set_work(bytes=8.0 * x.numel())
+    _call('prologue_inv', (_p(z), _p(x), _p(cont), B, C, CA - C, H * W, float(s1), float(t1), float(s0), float(t0),
+                           int(bool(do_floor)), _stream()), 'prologue_inv')
+    return (x, cont) if keep_cont else x
+
+
+def gmm_sample(mG, sG, comp, eps, m=1):
+    """x[b] = mG[m, comp[b]] + softplus(sG[m, comp[b]]) * eps[b]  (gaussian.py:163-166 after its draws)."""
+    _need_cuda(mG, sG, comp, eps); eps = _f32(eps)
+    if comp.dtype != torch.int64:
+        raise TypeError('component indices must be int64')
+    M, K = mG.shape[0], mG.shape[1]
+    B = eps.shape[0]
+    n = mG[0, 0].numel()
+    x = torch.empty_like(eps)
+    _call('gmm_sample', (_p(_f32(mG)), _p(_f32(sG)), _p(comp.contiguous()), _p(eps), _p(x), B, M, K, n, int(m), _stream()), 'gmm_sample')
+    return x
+
+
+# ---------------------------------------------------------------------------------------------- loss / score epilogue
+def score_epilogue(logp, dim_inv, gt=None, class_w=None, want=('scaled', 'lse', 'softmax1', 'last', 'argmax')):
+    """experiment_ad.py:204-211,262-281 / experiment_cl.py:127-133,185-204 after log_prob, two launches.  Returns a dict with the
+    requested per-sample outputs and 'sums' (4,) = [sum logsigmoid(lse), sum logsigmoid(scaled), CE numerator, CE denominator]."""
+    _need_cuda(logp); logp = _f32(logp)
+    B, M = logp.shape
+    dev = logp.device
+    out = {}
+    if 'scaled' in want: out['scaled'] = torch.empty_like(logp)
+    for k in ('lse', 'softmax1', 'last'):
+        if k in want: out[k] = torch.empty(B, device=dev, dtype=torch.float32)
+    if 'argmax' in want: out['argmax'] = torch.empty(B, device=dev, dtype=torch.int64)
+    out['sums'] = torch.empty(4, device=dev, dtype=torch.float32)
+    ws = torch.empty(int(lib().cfpp_score_workspace_bytes(B)), device=dev, dtype=torch.uint8)
+    if gt is not None:
+        _need_cuda(gt)
+        if gt.dtype != torch.int64:
+            raise TypeError('gt must be int64 class indices')
+        gt = gt.contiguous()
+    _set_work(bytes=4.0 * logp.numel() * (2 if 'scaled' in want else 1))
+    _call('score_epilogue', (_p(logp), float(dim_inv), _p(gt), _p(None if class_w is None else _f32(class_w)),
+                             _p(out.get('scaled')), _p(out.get('lse')), _p(out.get('softmax1')), _p(out.get('last')),
+                             _p(out.get('argmax')), _p(out['sums']), _p(ws), B, M, _stream()), 'score_epilogue')
+    return out
 
 
 def pack_kmajor(w2d: torch.Tensor, pad_to: int = 16) -> torch.Tensor:

@@ -42,6 +42,13 @@ def rand(shape, device, dtype=torch.float32, host_draw=False):
     return torch.rand(tuple(shape), device=device, dtype=dtype)
 
 
+def multinomial(probs, n):
+    """n categorical draws (int64, on probs.device) with replacement."""
+    if _source is not None and hasattr(_source, 'multinomial'):
+        return _source.multinomial(probs, n)
+    return torch.multinomial(probs, n, replacement=True)
+
+
 def randn(shape, device, dtype=torch.float32):
     if _source is not None:
         return _source.randn(tuple(shape), device=device, dtype=dtype)

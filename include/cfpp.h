@@ -274,6 +274,45 @@ typedef struct cfpp_cn_job {
 int cfpp_cn_batch(const cfpp_cn_job* jobs, int n_jobs, const float* const* in, float* const* out, int B, void* stream);
 
 
+/* ---- inverse (sampling) direction: SURVEY §8(f)-3 ------------------------------------------------------------ */
+/* Coupling.reverse / TransCoupling.reverse, layers/coupling.py:68-73,150-155: t, r from h (+ add) as in cfpp_coupling_fwd;
+ * x = cat(z[:, :C/2], (z[:, C/2:] - t) / exp(2 tanh(r/2))).  One HBM pass, 12*C*HW bytes/sample. */
+int cfpp_coupling_inv(const float* z, const float* h, const float* add, float* x, int B, int C, int HW, void* stream);
+/* ActNorm.reverse without context, layers/actnorm.py:73-78: x = z * exp(logs[d]) + t[d]. */
+int cfpp_actnorm_inv(const float* z, float* x, const float* t, const float* logs, int B, int D, int HW, void* stream);
+/* torch.inverse(NN), layers/conv1x1.py:70 (Conv1x1.reverse = cfpp_conv1x1_fwd with this matrix): fp64 Gauss-Jordan with
+ * partial pivoting, D <= 128; singular[0] (optional, device int) = 1 when a zero pivot was met. */
+int cfpp_mat_inverse(const float* A, int D, float* Ainv, int* singular, void* stream);
+/* LogitTransform.reverse (layers/transforms.py:14-15): y = sigmoid(x). */
+int cfpp_sigmoid_fwd(const float* x, float* y, int64_t n, void* stream);
+/* Normalization.reverse (scalar scale), layers/normalize.py:37-41: x = (y - translation) * scale. */
+int cfpp_normalize_inv(const float* y, float* x, int64_t n, float scale, float translation, void* stream);
+/* Dequantization.reverse, layers/dequantize.py:19-20: y = floor(x). */
+int cfpp_floor_fwd(const float* x, float* y, int64_t n, void* stream);
+/* The image prologue backwards in one pass (model.py:97-100 right to left): Augment.reverse (keep the first C of C+A channels,
+ * layers/augment.py:20-23), sigmoid, (v - t1) * s1, (v - t0) * s0, floor (do_floor).  x_cont (optional) = value before the floor. */
+int cfpp_prologue_inv(const float* z, float* x, float* x_cont, int B, int C, int A, int HW,
+                      float s1, float t1, float s0, float t0, int do_floor, void* stream);
+/* GaussianMixtureDistribution.sample after its random draws (layers/distributions/gaussian.py:163-166: mixture m = 1 of
+ * MixtureSameFamily(Categorical(softmax wG), Normal(mG, softplus sG))): x[b] = mG[m, comp[b]] + softplus(sG[m, comp[b]]) * eps[b];
+ * comp (B) int64 component draws, eps (B, n_per_sample) standard-normal draws. */
+int cfpp_gmm_sample(const float* mG, const float* sG, const int64_t* comp, const float* eps, float* x,
+                    int B, int M, int K, int n_per_sample, int m, void* stream);
+
+/* ---- loss / score epilogue: SURVEY §8(f)-2 ------------------------------------------------------------------- */
+/* experiment_ad.py:204-211,262-281 / experiment_cl.py:127-133,185-204 after model.log_prob, in two launches:
+ *   scaled (B,M) = dim_inv * logp with NaN -> 0;  lse (B) = logsumexp_m;  softmax1 (B) = softmax(scaled)[:,1] (1 when M = 1);
+ *   last (B) = scaled[:, -1];  argmax (B) int64 (first maximum);
+ *   sums[0] = sum_b logsigmoid(lse_b), sums[1] = sum_{b,m} logsigmoid(scaled), sums[2], sums[3] = numerator, denominator of
+ *   nn.CrossEntropyLoss(weight=class_w)(scaled, gt) when gt != NULL (class_w NULL = unit weights).
+ * cost_uns = -alpha * sums[0] / B (criterion) or -alpha * sums[1] / (B*M) (none); cost_sup = sums[2] / sums[3].
+ * Every output but sums is optional (NULL).  Deterministic (fixed-order reductions, no atomics).
+ * workspace: cfpp_score_workspace_bytes(B) device bytes. */
+int64_t cfpp_score_workspace_bytes(int B);
+int cfpp_score_epilogue(const float* logp, float dim_inv, const int64_t* gt, const float* class_w,
+                        float* scaled, float* lse, float* softmax1, float* last, int64_t* argmax, float* sums,
+                        void* workspace, int B, int M, void* stream);
+
 /* ---- container ------------------------------------------------------------------------------------------------ */
 /* FlowSequential.forward, layers/flowsequential.py:23: logdet (B,M) += ldj (B,cols) with cols = 1 (broadcast) or M. */
 int cfpp_ldj_accumulate(float* logdet, const float* ldj, int B, int M, int cols, void* stream);

@@ -484,3 +484,126 @@ def log_prob(stack, state, x, ctx, noise, dtype=torch.float32):
 def bits_per_dim(logp, data_size):
     """-logsumexp_m(logp) / (ln2 * prod(data_size)) (experiment_cl.py:55,127,200 `dim_inv` convention)."""
     return -torch.logsumexp(logp, -1) / (math.log(2) * float(np.prod(data_size)))
+
+
+# =================================================================================================
+# inverse direction (SURVEY §8f-3): every layer's .reverse as the reference can execute it, and the loop of
+# FlowSequential.sample (flowsequential.py:32-39) from a given latent
+# =================================================================================================
+def unsqueeze(y, p):
+    """squeeze.py:13-14  'b (c p1 p2) h w -> b c (h p1) (w p2)'."""
+    B, Cs, Hs, Ws = y.shape
+    p1, p2 = p
+    x = y.reshape(B, Cs // (p1 * p2), p1, p2, Hs, Ws).permute(0, 1, 4, 2, 5, 3)
+    return x.reshape(B, Cs // (p1 * p2), Hs * p1, Ws * p2).contiguous()
+
+
+def coupling_reverse(P, state, lay, z, ctx, noise, dt, trans):
+    """Coupling.reverse / TransCoupling.reverse (coupling.py:68-73, 150-155): get_xs_logs_t on z0, x1 = (z1 - t) / s."""
+    k = lay['key']
+    B, C, H, W = z.shape
+    Ch = C // 2
+    z0 = z[:, :Ch]
+    if trans:
+        T = C * lay['p'][0] * lay['p'][1]
+        seq = lay['enc'] is None or lay['contextflow']
+        net = lambda inp: vit_conditioner(P, f'{k}.NN.0' if seq else f'{k}.NN', inp, lay['p'], T)
+    else:
+        net = lambda inp: conv_conditioner(P, f'{k}.NN', inp, lay['krn'], lay['pad'])
+    if lay['enc'] is None:
+        h = net(z0)
+    else:
+        c, _ = context_encode(P, state, f'{k}.context_net', lay['enc'], ctx, noise, dt)
+        cn = mlp3(P, f'{k}.CN', c)
+        if lay['contextflow']:
+            h = net(z0) + cn[:, :, None, None]
+        else:
+            h = net(torch.cat([z0, cn[:, :, None, None].expand(B, C, H, W)], 1))
+    t, r = h[:, :Ch], h[:, Ch:]
+    s = torch.exp(2.0 * torch.tanh(r / 2.0))
+    return torch.cat([z0, (z[:, Ch:] - t) / s], 1)
+
+
+def conv1x1_reverse(P, lay, z):
+    """Conv1x1.reverse, context-free branch (conv1x1.py:70): conv with torch.inverse(NN).  The context branch of the reference
+    is not executable (reads w_ginv before assignment, :62)."""
+    if lay['enc'] is not None:
+        raise NotImplementedError('Conv1x1.reverse with context is not executable in the reference')
+    return torch.einsum('ij,bjhw->bihw', torch.inverse(P(f"{lay['key']}.NN")), z)
+
+
+def actnorm_reverse(P, lay, z):
+    """ActNorm.reverse, context-free branch (actnorm.py:73-78): x = z * exp(logs) + t."""
+    if lay['enc'] is not None:
+        raise NotImplementedError('ActNorm.reverse with context is not executable in the reference (actnorm.py:65)')
+    k = lay['key']
+    return z * torch.exp(P(f'{k}.NN_logs'))[None, :, None, None] + P(f'{k}.NN_t')[None, :, None, None]
+
+
+def reverse_layer(P, state, lay, z, ctx, noise, dt):
+    op = lay['op']
+    if op == 'dequant':
+        return z.floor()                                                     # dequantize.py:19-20
+    if op == 'normalize':                                                    # normalize.py:37-41
+        s = torch.tensor([lay['s']], dtype=torch.float32).to(dt); t = torch.tensor([lay['t']], dtype=torch.float32).to(dt)
+        return (z - t) * s
+    if op == 'logit':
+        return torch.sigmoid(z)                                              # transforms.py:14-15
+    if op == 'augment':
+        return z[:, : z.shape[1] - lay['size'][0]].contiguous()              # augment.py:20-23
+    if op == 'squeeze':
+        return unsqueeze(z, lay['p'])
+    if op == 'permute':
+        return permute_chw(z)                                                # (0,2,1,3) is its own inverse
+    if op == 'conv1x1':
+        return conv1x1_reverse(P, lay, z)
+    if op == 'actnorm':
+        return actnorm_reverse(P, lay, z)
+    if op == 'coupling':
+        return coupling_reverse(P, state, lay, z, ctx, noise, dt, trans=False)
+    if op == 'transcoupling':
+        return coupling_reverse(P, state, lay, z, ctx, noise, dt, trans=True)
+    if op == 'splitprior':
+        raise AttributeError("'SplitPrior' object has no attribute 'C'")    # splitprior.py:18 in the reference
+    raise NotImplementedError(op)
+
+
+def reverse(stack, state, z, ctx, noise, dtype=torch.float32, trace: Optional[Callable] = None, stop_before: int = 0):
+    """The layer loop of FlowSequential.sample (flowsequential.py:34-37) from latent z; layers [stop_before:] are inverted."""
+    dt = dtype
+    P = _P(state, dt)
+    x = z.detach().to(DEVICE, dt)
+    if ctx is not None:
+        ctx = ctx.detach().to(DEVICE)
+    for lay in reversed(stack['layers'][stop_before:]):
+        x = reverse_layer(P, state, lay, x, ctx, noise, dt)
+        if trace is not None:
+            trace(lay, x)
+    return x
+
+
+def gmm_sample_given(P, lay, comp, eps, m=1):
+    """The deterministic part of GaussianMixtureDistribution.sample (gaussian.py:163-166): component comp[b] of mixture m = 1,
+    x = mG + softplus(sG) * eps."""
+    k = lay['key']
+    mean = P(f'{k}.mG')[m][comp]; scale = softplus(P(f'{k}.sG')[m][comp])
+    return mean + scale * eps
+
+
+# =================================================================================================
+# loss / score epilogue (SURVEY §8f-2): experiment_ad.py:204-211,262-281, experiment_cl.py:127-133,185-204
+# =================================================================================================
+def score_epilogue(logp, dim_inv, gt=None, class_w=None):
+    s = dim_inv * logp
+    s = s.clone(); s[s != s] = 0.0
+    lse = torch.logsumexp(s, -1)
+    out = dict(scaled=s, lse=lse, softmax1=torch.softmax(s, -1)[:, 1] if s.shape[1] > 1 else torch.ones_like(lse),
+               last=s[:, -1], argmax=torch.argmax(s, -1))
+    sums = [F.logsigmoid(lse).double().sum(), F.logsigmoid(s).double().sum(), torch.zeros((), dtype=torch.float64),
+            torch.zeros((), dtype=torch.float64)]
+    if gt is not None:
+        w = class_w[gt] if class_w is not None else torch.ones_like(lse)
+        sums[2] = (w * (lse - s.gather(1, gt[:, None])[:, 0])).double().sum()
+        sums[3] = w.double().sum()
+    out['sums'] = torch.stack(sums).float()
+    return out

@@ -34,3 +34,17 @@ CASES = {
     # MNIST at the literal 28x28 shape (BASELINE configs[0])
     'mnist28': dict(conf=variant('cfg1', data_size=(1, 28, 28)), B=2),
 }
+
+# ---- inverse direction (make_golden_inverse.py) ----
+# models whose every layer has an executable .reverse in the reference: generalists without split priors
+INVERSE_CHAIN = ['cfg1', 'cfg4', 'mnist28']
+# specialists: per-layer Coupling / TransCoupling .reverse with a context encoder (the other specialist reverses raise in the reference)
+INVERSE_COUPLING = ['cfg2', 'cifar_conventional', 'smap_conventional', 'atm_argmax2', 'msl_conv']
+
+# ---- loss / score epilogue ----
+SCORE_CASES = {
+    'ad_m2': dict(B=37, M=2, size=(25, 8, 1), spread=40.0, shift=-300.0, weight=[0.3, 1.7]),        # anomaly detection, criterion
+    'ad_m1': dict(B=9, M=1, size=(25, 8, 1), spread=40.0, shift=-300.0),                            # unsupervised (M = 1)
+    'cl_m10': dict(B=64, M=10, size=(3, 32, 32), spread=300.0, shift=-9000.0, weight=[1.0] * 10),   # classification
+    'cl_nan': dict(B=12, M=10, size=(1, 28, 28), spread=100.0, shift=-2000.0, nan=True),            # NaN -> 0 replacement
+}
