@@ -99,6 +99,19 @@ _SIGNATURES = {
     'cfpp_gmm_sample': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     'cfpp_score_workspace_bytes': (i64, [i32]),
     'cfpp_score_epilogue': (i32, [vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
+    'cfpp_coupling_bwd': (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    'cfpp_actnorm_bwd_workspace_floats': (i64, [i32, i32]),
+    'cfpp_actnorm_bwd': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    'cfpp_conv2d_fwd': (i32, [vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    'cfpp_conv2d_bwd_data': (i32, [vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    'cfpp_conv2d_bwd_weight': (i32, [vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+    'cfpp_relu_mask': (i32, [vp, vp, i64, vp]),
+    'cfpp_logdet_grad': (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    'cfpp_rowsum': (i32, [vp, vp, i32, i32, vp]),
+    'cfpp_gmm_train_prep': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    'cfpp_gmm_train_fwd': (i32, [vp, i64, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    'cfpp_gmm_train_bwd_workspace_floats': (i64, [i32, i32, i32, i32]),
+    'cfpp_gmm_train_bwd': (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     'cfpp_ldj_accumulate': (i32, [vp, vp, i32, i32, i32, vp]),
     'cfpp_ldj_sum': (i32, [vp, vp, vp, C.POINTER(vp), C.POINTER(i32), i32, i32, i32, vp]),
 }

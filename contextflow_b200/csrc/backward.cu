@@ -1,0 +1,556 @@
+// Training direction: the activation-saving conditioner forward and the backward kernels of the context-free
+// (generalist) conv stack -- Coupling (layers/coupling.py:39-66), its conv conditioner (:26-29), ActNorm (layers/actnorm.py:37-60),
+// Conv1x1 (layers/conv1x1.py:52-55), the mixture base (layers/distributions/gaussian.py:142-161) and the (B,M) log-det accumulation
+// (layers/flowsequential.py:20-27).  What the reference obtains from torch autograd over experiment_ad.py:204-213.
+// First correct version: FP32 CUDA cores, one CTA per sample with the sample resident in shared memory; weight gradients are
+// accumulated with fp32 atomics (sums over the batch are order dependent at the 1e-7 level).
+#include <math.h>
+#include "common.cuh"
+
+namespace cfpp {
+namespace bw {
+
+__device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Coupling backward.  Forward: t = h[:, :Ch], r = h[:, Ch:]; ls = 2 tanh(r/2); z1 = x1 e^{ls} + t; ldj = sum ls.
+//   dx0 = dz0 (the conditioner's contribution is added by its own backward); dx1 = dz1 e^{ls};
+//   dt = dz1; dr = (dz1 x1 e^{ls} + dldj[b]) (1 - tanh^2(r/2)).          20*C*HW bytes per sample.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) coupling_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
+                                                           const float* __restrict__ dz, const float* __restrict__ dldj,
+                                                           float* __restrict__ dx, float* __restrict__ dh, int B, int C, int HW, int G) {
+  const int spc = blockDim.x / G;
+  const int s = threadIdx.x / G, g = threadIdx.x % G;
+  const int64_t b = (int64_t)blockIdx.x * spc + s;
+  if (b >= B) return;
+  const int64_t n = (int64_t)(C / 2) * HW;
+  const float* xb = x + b * 2 * n; const float* hb = h + b * 2 * n; const float* gb = dz + b * 2 * n;
+  float* dxb = dx + b * 2 * n; float* dhb = dh + b * 2 * n;
+  const float gl = dldj ? dldj[b] : 0.f;
+  for (int64_t i = g; i < n; i += G) {
+    const float r = hb[n + i], x1 = xb[n + i], g0 = gb[i], g1 = gb[n + i];
+    const float th = tanhf(r * 0.5f);
+    const float sc = expf(2.0f * th);
+    dxb[i] = g0;
+    dxb[n + i] = g1 * sc;
+    dhb[i] = g1;
+    dhb[n + i] = (g1 * x1 * sc + gl) * (1.0f - th * th);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ActNorm backward (context-free).  Forward: z = (x - t) e^{-logs}; ldj[b] = sum_d logs.
+//   dx = dz e^{-logs};  dt[d] = -sum_{b,p} dz e^{-logs};  dlogs[d] = -sum_{b,p} dz z + sum_b dldj[b].
+// grid (D, chunks): a CTA walks channel d of a contiguous chunk of samples; partial[(chunk*D + d)*2 + {0,1}]; finish sums in order.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) actnorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                                          const float* __restrict__ t, const float* __restrict__ logs,
+                                                          float* __restrict__ dx, float* __restrict__ partial, int B, int D, int HW, int per_chunk) {
+  __shared__ float red[32];
+  const int d = blockIdx.x, chunk = blockIdx.y;
+  const int b0 = chunk * per_chunk, b1 = min(B, b0 + per_chunk);
+  const float e = expf(-logs[d]), tt = t[d];
+  float a0 = 0.f, a1 = 0.f;
+  const int64_t total = (int64_t)(b1 - b0) * HW;
+  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+    const int64_t b = b0 + i / HW; const int p = (int)(i % HW);
+    const int64_t o = (b * D + d) * HW + p;
+    const float g = dz[o], ge = g * e;
+    if (dx) dx[o] = ge;
+    a0 -= ge;
+    a1 -= g * ((x[o] - tt) * e);
+  }
+  a0 = group_sum(a0, blockDim.x, red);
+  a1 = group_sum(a1, blockDim.x, red);
+  if (threadIdx.x == 0) { partial[((int64_t)chunk * D + d) * 2] = a0; partial[((int64_t)chunk * D + d) * 2 + 1] = a1; }
+}
+
+__global__ void actnorm_bwd_finish_kernel(const float* __restrict__ partial, const float* __restrict__ dldj, float* __restrict__ dt,
+                                          float* __restrict__ dlogs, int B, int D, int chunks) {
+  __shared__ float red[32];
+  float s = 0.f;                                                    // sum_b dldj[b], fixed order per thread then tree
+  if (dldj) for (int b = threadIdx.x; b < B; b += blockDim.x) s += dldj[b];
+  s = group_sum(s, blockDim.x, red);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int c = 0; c < chunks; ++c) { a0 += partial[((int64_t)c * D + d) * 2]; a1 += partial[((int64_t)c * D + d) * 2 + 1]; }
+    dt[d] = a0; dlogs[d] = a1 + s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Generic small convolution family, NCHW, "same" reflect padding (KH, KW in {1,3}), torch weight layout (Cout, Cin, KH, KW).
+// One CTA per sample; the sample's input planes live in shared memory.  Used for the conditioner in training mode (the three
+// convolutions as separate launches so that the post-ReLU activations are saved) and, with 1x1 kernels, for Conv1x1's backward.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int CG = 4;        // output channels per thread
+
+__global__ void __launch_bounds__(256) conv2d_fwd_kernel(const float* __restrict__ in, int64_t in_bstride, const float* __restrict__ W,
+                                                         const float* __restrict__ bias, float* __restrict__ out,
+                                                         int Cin, int Cout, int H, int Wd, int KH, int KW, int relu) {
+  extern __shared__ float sin_[];                                    // Cin * HW
+  const int HW = H * Wd, KK = KH * KW;
+  const int64_t b = blockIdx.x;
+  for (int i = threadIdx.x; i < Cin * HW; i += blockDim.x) sin_[i] = in[b * in_bstride + i];
+  __syncthreads();
+  const int ncg = (Cout + CG - 1) / CG;
+  for (int item = threadIdx.x; item < HW * ncg; item += blockDim.x) {
+    const int p = item % HW, cg = item / HW;
+    const int y = p / Wd, xx = p - y * Wd;
+    const int co0 = cg * CG;
+    float acc[CG];
+#pragma unroll
+    for (int c = 0; c < CG; ++c) acc[c] = (bias && co0 + c < Cout) ? bias[co0 + c] : 0.f;
+    for (int kh = 0; kh < KH; ++kh) {
+      const int yy = reflect_idx(y + kh - KH / 2, H);
+      for (int kw = 0; kw < KW; ++kw) {
+        const int q = yy * Wd + reflect_idx(xx + kw - KW / 2, Wd);
+        const float* wp = W + (int64_t)co0 * Cin * KK + kh * KW + kw;
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float v = sin_[ci * HW + q];
+#pragma unroll
+          for (int c = 0; c < CG; ++c)
+            if (co0 + c < Cout) acc[c] = fmaf(__ldg(wp + ((int64_t)c * Cin + ci) * KK), v, acc[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CG; ++c)
+      if (co0 + c < Cout) out[(b * Cout + co0 + c) * HW + p] = relu ? fmaxf(acc[c], 0.f) : acc[c];
+  }
+}
+
+// din[b,ci,q] (= or +=) mask(act[b,ci,q] > 0) * sum_{u in U(q)} sum_{co,tap} W[co,ci,tap] dout[b,co,u - tap + pad]
+// U(q): q itself plus the padded positions that reflect onto q (the adjoint of reflect padding).
+__global__ void __launch_bounds__(256) conv2d_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict__ W,
+                                                              const float* __restrict__ act, int64_t act_bstride,
+                                                              float* __restrict__ din, int64_t din_bstride, int accumulate,
+                                                              int Cin, int Cout, int H, int Wd, int KH, int KW) {
+  extern __shared__ float sd[];                                      // Cout * HW
+  const int HW = H * Wd, KK = KH * KW, ph = KH / 2, pw = KW / 2;
+  const int64_t b = blockIdx.x;
+  for (int i = threadIdx.x; i < Cout * HW; i += blockDim.x) sd[i] = dout[b * Cout * HW + i];
+  __syncthreads();
+  const int ncg = (Cin + CG - 1) / CG;
+  for (int item = threadIdx.x; item < HW * ncg; item += blockDim.x) {
+    const int q = item % HW, cg = item / HW;
+    const int qy = q / Wd, qx = q - qy * Wd;
+    const int ci0 = cg * CG;
+    float acc[CG] = {0.f, 0.f, 0.f, 0.f};
+    int uys[3], uxs[3]; int ny = 0, nx = 0;
+    uys[ny++] = qy; if (ph == 1 && qy == 1) uys[ny++] = -1; if (ph == 1 && qy == H - 2) uys[ny++] = H;
+    uxs[nx++] = qx; if (pw == 1 && qx == 1) uxs[nx++] = -1; if (pw == 1 && qx == Wd - 2) uxs[nx++] = Wd;
+    for (int iy = 0; iy < ny; ++iy)
+      for (int kh = 0; kh < KH; ++kh) {
+        const int py = uys[iy] - kh + ph;
+        if (py < 0 || py >= H) continue;
+        for (int ix = 0; ix < nx; ++ix)
+          for (int kw = 0; kw < KW; ++kw) {
+            const int px = uxs[ix] - kw + pw;
+            if (px < 0 || px >= Wd) continue;
+            const int p = py * Wd + px;
+            const float* wp = W + (int64_t)ci0 * KK + kh * KW + kw;
+            for (int co = 0; co < Cout; ++co) {
+              const float g = sd[co * HW + p];
+#pragma unroll
+              for (int c = 0; c < CG; ++c)
+                if (ci0 + c < Cin) acc[c] = fmaf(__ldg(wp + ((int64_t)co * Cin + c) * KK), g, acc[c]);
+            }
+          }
+      }
+#pragma unroll
+    for (int c = 0; c < CG; ++c) {
+      if (ci0 + c >= Cin) continue;
+      float v = acc[c];
+      if (act && !(act[b * act_bstride + (int64_t)(ci0 + c) * HW + q] > 0.f)) v = 0.f;
+      float* o = din + b * din_bstride + (int64_t)(ci0 + c) * HW + q;
+      *o = accumulate ? *o + v : v;
+    }
+  }
+}
+
+// dW[co,ci,tap] += sum_{b in chunk, p} g[b,co,p] in[b,ci,nbr(p,tap)];  db[co] += sum g.   g = dout (masked by act_out > 0 when given).
+// grid (chunks, co blocks): a CTA owns NCO output channels x all input channels, PPT (co,ci) pairs per thread held in registers
+// across the samples of its chunk, then one fp32 atomicAdd per weight.
+constexpr int PPT = 2;
+
+template <int KK>
+__global__ void __launch_bounds__(256) conv2d_bwd_weight_kernel(const float* __restrict__ in, int64_t in_bstride, const float* __restrict__ dout,
+                                                                float* __restrict__ dW, float* __restrict__ db,
+                                                                int B, int Cin, int Cout, int H, int Wd, int KH, int KW, int NCO, int per_chunk) {
+  extern __shared__ float sm[];
+  const int HW = H * Wd;
+  float* sin_ = sm;                                   // Cin * HW
+  float* sd = sin_ + Cin * HW;                        // NCO * HW
+  int* nbr = reinterpret_cast<int*>(sd + NCO * HW);   // HW * KK
+  const int co0 = blockIdx.y * NCO;
+  const int nco = min(NCO, Cout - co0);
+  const int b0 = blockIdx.x * per_chunk, b1 = min(B, b0 + per_chunk);
+  for (int i = threadIdx.x; i < HW * KK; i += blockDim.x) {
+    const int p = i / KK, tap = i - p * KK;
+    const int y = p / Wd, xx = p - y * Wd, kh = tap / KW, kw = tap - kh * KW;
+    nbr[i] = reflect_idx(y + kh - KH / 2, H) * Wd + reflect_idx(xx + kw - KW / 2, Wd);
+  }
+  float acc[PPT][KK];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k)
+#pragma unroll
+    for (int t = 0; t < KK; ++t) acc[k][t] = 0.f;
+  float bsum = 0.f;
+  const int npairs = nco * Cin;
+  for (int b = b0; b < b1; ++b) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cin * HW; i += blockDim.x) sin_[i] = in[(int64_t)b * in_bstride + i];
+    for (int i = threadIdx.x; i < nco * HW; i += blockDim.x) sd[i] = dout[((int64_t)b * Cout + co0) * HW + i];
+    __syncthreads();
+    if ((int)threadIdx.x < nco) { float s = 0.f; for (int p = 0; p < HW; ++p) s += sd[threadIdx.x * HW + p]; bsum += s; }
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const int pair = threadIdx.x + k * 256;
+      if (pair >= npairs) continue;
+      const int co = pair / Cin, ci = pair - co * Cin;
+      const float* gp = sd + co * HW; const float* ip = sin_ + ci * HW;
+      for (int p = 0; p < HW; ++p) {
+        const float g = gp[p]; const int* nb = nbr + p * KK;
+#pragma unroll
+        for (int t = 0; t < KK; ++t) acc[k][t] = fmaf(g, ip[nb[t]], acc[k][t]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int pair = threadIdx.x + k * 256;
+    if (pair >= npairs) continue;
+    const int co = pair / Cin, ci = pair - co * Cin;
+#pragma unroll
+    for (int t = 0; t < KK; ++t) atomicAdd(dW + ((int64_t)(co0 + co) * Cin + ci) * KK + t, acc[k][t]);
+  }
+  if (db && (int)threadIdx.x < nco) atomicAdd(db + co0 + threadIdx.x, bsum);
+}
+
+// elementwise ReLU mask: g *= (act > 0)
+__global__ void relu_mask_kernel(float* __restrict__ g, const float* __restrict__ act, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (!(act[i] > 0.f)) g[i] = 0.f;
+}
+
+// Conv1x1's log-det term: dNN[i][j] += HW * (sum_b dldj[b]) * inv[j][i]     (d log|det A| / dA = A^-T), one CTA.
+__global__ void logdet_grad_kernel(float* __restrict__ dNN, const float* __restrict__ inv, const float* __restrict__ dldj, int B, int D, float HW) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) s += dldj[b];
+  s = group_sum(s, blockDim.x, red);
+  for (int e = threadIdx.x; e < D * D; e += blockDim.x) { const int i = e / D, j = e - i * D; dNN[e] += HW * s * inv[j * D + i]; }
+}
+
+// out[b] = sum_m g[b,m]: the gradient a (B,) or (B,1) log-det term receives from the (B,M) accumulation (flowsequential.py:23).
+__global__ void rowsum_kernel(const float* __restrict__ g, float* __restrict__ out, int B, int M) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) s += g[(int64_t)b * M + m];
+    out[b] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Mixture base, training direction (context-free).  prep: sigma = softplus(sG), a = 1/sigma^2, cst[m,k] = log_softmax-weights
+// - sum_e log sigma - n/2 log 2pi.  resp: comp[b,mk] = cst - 1/2 sum_e a (x-mu)^2; logp[b,m] = lse_k; r = softmax_k.
+// dx[b,e] = -sum_mk w a (x - mu), w[b,mk] = g[b,m] r[b,mk].   Parameter sums S0 = sum_b w, S1 = sum_b w x, S2 = sum_b w x^2:
+//   dmu = a (S1 - mu S0); dsigma = (S2 - 2 mu S1 + mu^2 S0) / sigma^3 - S0 / sigma; dsG = dsigma * sigmoid(sG);
+//   dmix = S0; dwG[m,j] = dmix[m,j] - softmax(wG)[m,j] sum_k dmix[m,k]   (the eps clamp of Categorical(probs) is inactive).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gmm_prep_kernel(const float* __restrict__ sG, const float* __restrict__ wG, float* __restrict__ inv_var,
+                                                       float* __restrict__ cst, int M, int K, int n) {
+  __shared__ float red[32];
+  const int mk = blockIdx.x, m = mk / K, k = mk - m * K;
+  float acc = 0.f;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const float s = softplus_f(sG[(int64_t)mk * n + e]);
+    inv_var[(int64_t)mk * n + e] = 1.0f / (s * s);
+    acc += logf(s);
+  }
+  acc = group_sum(acc, blockDim.x, red);
+  if (threadIdx.x == 0) {
+    float mx = -INFINITY;
+    for (int j = 0; j < K; ++j) mx = fmaxf(mx, wG[m * K + j]);
+    float se = 0.f;
+    for (int j = 0; j < K; ++j) se += expf(wG[m * K + j] - mx);
+    cst[mk] = (wG[mk] - mx - logf(se)) - acc - (float)n * kHalfLog2Pi;
+  }
+}
+
+constexpr int kMaxMK = 256;
+
+// one CTA per sample: warps loop over the (m,k) pairs, lanes over the elements of the sample held in shared memory
+__global__ void __launch_bounds__(256) gmm_resp_kernel(const float* __restrict__ x, int64_t x_bstride, const float* __restrict__ mG,
+                                                       const float* __restrict__ inv_var, const float* __restrict__ cst,
+                                                       float* __restrict__ logp, float* __restrict__ resp, int M, int K, int n) {
+  extern __shared__ float sx[];                        // n floats, then M*K comp values
+  float* comp = sx + n;
+  const int64_t b = blockIdx.x;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) sx[e] = x[b * x_bstride + e];
+  __syncthreads();
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int mk = w; mk < M * K; mk += nw) {
+    const float* mu = mG + (int64_t)mk * n; const float* a = inv_var + (int64_t)mk * n;
+    float acc = 0.f;
+    for (int e = l; e < n; e += 32) { const float d = sx[e] - __ldg(mu + e); acc = fmaf(d * d, __ldg(a + e), acc); }
+    acc = warp_sum(acc);
+    if (l == 0) comp[mk] = cst[mk] - 0.5f * acc;
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, comp[m * K + k]);
+    float se = 0.f;
+    for (int k = 0; k < K; ++k) se += expf(comp[m * K + k] - mx);
+    const float lp = mx + logf(se);
+    logp[b * M + m] = lp;
+    if (resp) for (int k = 0; k < K; ++k) resp[(b * M + m) * K + k] = expf(comp[m * K + k] - lp);
+  }
+}
+
+// w[b,mk] = g[b,m] * resp[b,mk] (in place into wbuf);  dx[b,e] = -sum_mk w a (x - mu).   One CTA per sample.
+__global__ void __launch_bounds__(256) gmm_dx_kernel(const float* __restrict__ x, int64_t x_bstride, const float* __restrict__ mG,
+                                                     const float* __restrict__ inv_var, const float* __restrict__ resp, const float* __restrict__ g,
+                                                     float* __restrict__ wbuf, float* __restrict__ dx, int64_t dx_bstride, int M, int K, int n) {
+  __shared__ float sw[kMaxMK];
+  const int64_t b = blockIdx.x;
+  const int MK = M * K;
+  for (int i = threadIdx.x; i < MK; i += blockDim.x) {
+    const float v = g[b * M + i / K] * resp[b * MK + i];
+    sw[i] = v; wbuf[b * MK + i] = v;
+  }
+  __syncthreads();
+  if (!dx) return;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const float xv = x[b * x_bstride + e];
+    float acc = 0.f;
+    for (int mk = 0; mk < MK; ++mk) acc = fmaf(sw[mk] * __ldg(inv_var + (int64_t)mk * n + e), __ldg(mG + (int64_t)mk * n + e) - xv, acc);
+    dx[b * dx_bstride + e] = acc;
+  }
+}
+
+// Partial sums over a chunk of samples: grid (n / 256, MK / MKT, chunks); thread = one element e, MKT pairs in registers.
+constexpr int MKT = 8;
+__global__ void __launch_bounds__(256) gmm_psum_kernel(const float* __restrict__ x, int64_t x_bstride, const float* __restrict__ wbuf,
+                                                       float* __restrict__ part, int B, int MK, int n, int per_chunk) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int mk0 = blockIdx.y * MKT;
+  const int chunk = blockIdx.z;
+  const int b0 = chunk * per_chunk, b1 = min(B, b0 + per_chunk);
+  float s1[MKT], s2[MKT];
+#pragma unroll
+  for (int j = 0; j < MKT; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  if (e < n) {
+    for (int b = b0; b < b1; ++b) {
+      const float xv = x[(int64_t)b * x_bstride + e], xx = xv * xv;
+      const float* wp = wbuf + (int64_t)b * MK + mk0;
+#pragma unroll
+      for (int j = 0; j < MKT; ++j) {
+        const float w = (mk0 + j < MK) ? __ldg(wp + j) : 0.f;
+        s1[j] = fmaf(w, xv, s1[j]); s2[j] = fmaf(w, xx, s2[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < MKT; ++j)
+      if (mk0 + j < MK) {
+        float* o = part + (((int64_t)chunk * MK + mk0 + j) * n + e) * 2;
+        o[0] = s1[j]; o[1] = s2[j];
+      }
+  }
+}
+
+// S0[mk] = sum_b w[b,mk] in fixed order (one CTA per mk), then dwG by the first thread of the last... kept separate for clarity.
+__global__ void __launch_bounds__(256) gmm_s0_kernel(const float* __restrict__ wbuf, float* __restrict__ S0, int B, int MK) {
+  __shared__ float red[32];
+  const int mk = blockIdx.x;
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) s += wbuf[(int64_t)b * MK + mk];
+  s = group_sum(s, blockDim.x, red);
+  if (threadIdx.x == 0) S0[mk] = s;
+}
+
+__global__ void __launch_bounds__(256) gmm_finish_kernel(const float* __restrict__ part, const float* __restrict__ S0, const float* __restrict__ mG,
+                                                         const float* __restrict__ sG, const float* __restrict__ wG,
+                                                         float* __restrict__ dmG, float* __restrict__ dsG, float* __restrict__ dwG,
+                                                         int M, int K, int n, int chunks) {
+  const int MK = M * K;
+  const int64_t total = (int64_t)MK * n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int mk = (int)(i / n);
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = 0; c < chunks; ++c) { const float* p = part + ((int64_t)c * total + i) * 2; s1 += p[0]; s2 += p[1]; }
+    const float s0 = S0[mk], mu = mG[i], raw = sG[i];
+    const float sg = softplus_f(raw);
+    const float a = 1.0f / (sg * sg);
+    dmG[i] = a * (s1 - mu * s0);
+    const float q = s2 - 2.0f * mu * s1 + mu * mu * s0;              // sum_b w (x - mu)^2
+    const float dsig = q * a / sg - s0 / sg;
+    dsG[i] = dsig * (1.0f / (1.0f + expf(-raw)));
+  }
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < MK; i += blockDim.x) {
+      const int m = i / K;
+      float mx = -INFINITY, tot = 0.f;
+      for (int k = 0; k < K; ++k) { mx = fmaxf(mx, wG[m * K + k]); tot += S0[m * K + k]; }
+      float se = 0.f;
+      for (int k = 0; k < K; ++k) se += expf(wG[m * K + k] - mx);
+      dwG[i] = S0[i] - expf(wG[i] - mx) / se * tot;
+    }
+}
+
+inline int grid1d(int64_t n, int per_thread = 1) {
+  int64_t blocks = (n + 256LL * per_thread - 1) / (256LL * per_thread);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+template <typename Kern>
+inline bool want_smem(Kern k, size_t bytes) {
+  if (bytes <= 48 * 1024) return true;
+  if (bytes > 200 * 1024) return false;
+  return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
+}
+
+}  // namespace bw
+}  // namespace cfpp
+using namespace cfpp;
+using namespace cfpp::bw;
+
+extern "C" int cfpp_coupling_bwd(const float* x, const float* h, const float* dz, const float* dldj, float* dx, float* dh,
+                                 int B, int C, int HW, void* stream) {
+  CFPP_REQUIRE(C >= 2 && C % 2 == 0 && HW >= 1, "coupling_bwd: C=%d must be even, HW=%d", C, HW);
+  if (B <= 0) return CFPP_OK;
+  const int64_t n = (int64_t)(C / 2) * HW;
+  int G = 32;
+  while (G < 256 && G * 4 < n) G <<= 1;
+  const int spc = 256 / G;
+  coupling_bwd_kernel<<<(B + spc - 1) / spc, 256, 0, (cudaStream_t)stream>>>(x, h, dz, dldj, dx, dh, B, C, HW, G);
+  return check_launch("coupling_bwd");
+}
+
+extern "C" int64_t cfpp_actnorm_bwd_workspace_floats(int B, int D) {
+  int chunks = (num_sms() * 4 + D - 1) / D; if (chunks < 1) chunks = 1; if (chunks > B) chunks = B > 0 ? B : 1;
+  return (int64_t)chunks * D * 2;
+}
+
+extern "C" int cfpp_actnorm_bwd(const float* x, const float* dz, const float* dldj, const float* t, const float* logs,
+                                float* dx, float* dt, float* dlogs, float* workspace, int B, int D, int HW, void* stream) {
+  CFPP_REQUIRE(D >= 1 && HW >= 1 && B >= 1, "actnorm_bwd: B=%d D=%d HW=%d", B, D, HW);
+  int chunks = (num_sms() * 4 + D - 1) / D; if (chunks < 1) chunks = 1; if (chunks > B) chunks = B;
+  const int per_chunk = (B + chunks - 1) / chunks;
+  chunks = (B + per_chunk - 1) / per_chunk;
+  actnorm_bwd_kernel<<<dim3(D, chunks), 256, 0, (cudaStream_t)stream>>>(x, dz, t, logs, dx, workspace, B, D, HW, per_chunk);
+  int rc = check_launch("actnorm_bwd");
+  if (rc != CFPP_OK) return rc;
+  actnorm_bwd_finish_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(workspace, dldj, dt, dlogs, B, D, chunks);
+  return check_launch("actnorm_bwd_finish");
+}
+
+extern "C" int cfpp_conv2d_fwd(const float* in, int64_t in_bstride, const float* W, const float* bias, float* out,
+                               int B, int Cin, int Cout, int H, int Wd, int KH, int KW, int relu, void* stream) {
+  CFPP_REQUIRE((KH == 1 || KH == 3) && (KW == 1 || KW == 3) && (KH == 1 || H >= 2) && (KW == 1 || Wd >= 2), "conv2d: kernel %dx%d on %dx%d", KH, KW, H, Wd);
+  if (B <= 0) return CFPP_OK;
+  const size_t smem = (size_t)Cin * H * Wd * sizeof(float);
+  CFPP_REQUIRE(want_smem(conv2d_fwd_kernel, smem), "conv2d_fwd: sample of %zu bytes exceeds shared memory", smem);
+  conv2d_fwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(in, in_bstride, W, bias, out, Cin, Cout, H, Wd, KH, KW, relu);
+  return check_launch("conv2d_fwd");
+}
+
+extern "C" int cfpp_conv2d_bwd_data(const float* dout, const float* W, const float* act, int64_t act_bstride, float* din, int64_t din_bstride,
+                                    int accumulate, int B, int Cin, int Cout, int H, int Wd, int KH, int KW, void* stream) {
+  CFPP_REQUIRE((KH == 1 || KH == 3) && (KW == 1 || KW == 3) && (KH == 1 || H >= 2) && (KW == 1 || Wd >= 2), "conv2d: kernel %dx%d on %dx%d", KH, KW, H, Wd);
+  if (B <= 0) return CFPP_OK;
+  const size_t smem = (size_t)Cout * H * Wd * sizeof(float);
+  CFPP_REQUIRE(want_smem(conv2d_bwd_data_kernel, smem), "conv2d_bwd_data: sample of %zu bytes exceeds shared memory", smem);
+  conv2d_bwd_data_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(dout, W, act, act_bstride, din, din_bstride, accumulate, Cin, Cout, H, Wd, KH, KW);
+  return check_launch("conv2d_bwd_data");
+}
+
+extern "C" int cfpp_conv2d_bwd_weight(const float* in, int64_t in_bstride, const float* dout, float* dW, float* db,
+                                      int B, int Cin, int Cout, int H, int Wd, int KH, int KW, void* stream) {
+  CFPP_REQUIRE((KH == 1 || KH == 3) && (KW == 1 || KW == 3) && (KH == 1 || H >= 2) && (KW == 1 || Wd >= 2), "conv2d: kernel %dx%d on %dx%d", KH, KW, H, Wd);
+  const int KK = KH * KW, HW = H * Wd;
+  cudaMemsetAsync(dW, 0, (size_t)Cout * Cin * KK * sizeof(float), (cudaStream_t)stream);
+  if (db) cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), (cudaStream_t)stream);
+  if (B <= 0) return CFPP_OK;
+  int NCO = (256 * PPT) / Cin; if (NCO < 1) NCO = 1; if (NCO > Cout) NCO = Cout;
+  CFPP_REQUIRE(NCO * Cin <= 256 * PPT, "conv2d_bwd_weight: Cin=%d too wide", Cin);
+  const int coblocks = (Cout + NCO - 1) / NCO;
+  int chunks = (num_sms() * 4 + coblocks - 1) / coblocks; if (chunks > B) chunks = B; if (chunks < 1) chunks = 1;
+  const int per_chunk = (B + chunks - 1) / chunks;
+  chunks = (B + per_chunk - 1) / per_chunk;
+  const size_t smem = ((size_t)(Cin + NCO) * HW) * sizeof(float) + (size_t)HW * KK * sizeof(int);
+  const dim3 grid(chunks, coblocks);
+#define CFPP_BWDW(KKV)                                                                                                          \
+  do {                                                                                                                          \
+    CFPP_REQUIRE(want_smem(conv2d_bwd_weight_kernel<KKV>, smem), "conv2d_bwd_weight: tile of %zu bytes exceeds shared memory", smem); \
+    conv2d_bwd_weight_kernel<KKV><<<grid, 256, smem, (cudaStream_t)stream>>>(in, in_bstride, dout, dW, db, B, Cin, Cout, H, Wd, KH, KW, NCO, per_chunk); \
+  } while (0)
+  if (KK == 9) CFPP_BWDW(9); else if (KK == 3) CFPP_BWDW(3); else CFPP_BWDW(1);
+#undef CFPP_BWDW
+  return check_launch("conv2d_bwd_weight");
+}
+
+extern "C" int cfpp_relu_mask(float* g, const float* act, int64_t n, void* stream) {
+  if (n <= 0) return CFPP_OK;
+  relu_mask_kernel<<<grid1d(n, 4), 256, 0, (cudaStream_t)stream>>>(g, act, n);
+  return check_launch("relu_mask");
+}
+
+extern "C" int cfpp_logdet_grad(float* dNN, const float* inv, const float* dldj, int B, int D, int HW, void* stream) {
+  CFPP_REQUIRE(D >= 1 && D <= 128 && dldj, "logdet_grad: D=%d", D);
+  logdet_grad_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dNN, inv, dldj, B, D, (float)HW);
+  return check_launch("logdet_grad");
+}
+
+extern "C" int cfpp_rowsum(const float* g, float* out, int B, int M, void* stream) {
+  if (B <= 0) return CFPP_OK;
+  rowsum_kernel<<<grid1d(B), 256, 0, (cudaStream_t)stream>>>(g, out, B, M);
+  return check_launch("rowsum");
+}
+
+extern "C" int cfpp_gmm_train_prep(const float* sG, const float* wG, float* inv_var, float* cst, int M, int K, int n, void* stream) {
+  CFPP_REQUIRE(M >= 1 && K >= 1 && M * K <= kMaxMK && n >= 1, "gmm_train: M*K=%d exceeds %d", M * K, kMaxMK);
+  gmm_prep_kernel<<<M * K, 256, 0, (cudaStream_t)stream>>>(sG, wG, inv_var, cst, M, K, n);
+  return check_launch("gmm_train_prep");
+}
+
+extern "C" int cfpp_gmm_train_fwd(const float* x, int64_t x_bstride, const float* mG, const float* inv_var, const float* cst,
+                                  float* logp, float* resp, int B, int M, int K, int n, void* stream) {
+  CFPP_REQUIRE(M >= 1 && K >= 1 && M * K <= kMaxMK && n >= 1, "gmm_train: M*K=%d exceeds %d", M * K, kMaxMK);
+  if (B <= 0) return CFPP_OK;
+  const size_t smem = ((size_t)n + M * K) * sizeof(float);
+  CFPP_REQUIRE(want_smem(gmm_resp_kernel, smem), "gmm_train_fwd: sample of %zu bytes exceeds shared memory", smem);
+  gmm_resp_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(x, x_bstride, mG, inv_var, cst, logp, resp, M, K, n);
+  return check_launch("gmm_train_fwd");
+}
+
+extern "C" int64_t cfpp_gmm_train_bwd_workspace_floats(int B, int M, int K, int n) {
+  int chunks = 8; if (chunks > B) chunks = B > 0 ? B : 1;
+  return (int64_t)B * M * K + (int64_t)M * K + (int64_t)chunks * M * K * n * 2;
+}
+
+extern "C" int cfpp_gmm_train_bwd(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* wG, const float* inv_var,
+                                  const float* resp, const float* g, float* dx, int64_t dx_bstride, float* dmG, float* dsG, float* dwG,
+                                  float* workspace, int B, int M, int K, int n, void* stream) {
+  CFPP_REQUIRE(M >= 1 && K >= 1 && M * K <= kMaxMK && n >= 1 && B >= 1, "gmm_train_bwd: B=%d M*K=%d", B, M * K);
+  const int MK = M * K;
+  int chunks = 8; if (chunks > B) chunks = B;
+  const int per_chunk = (B + chunks - 1) / chunks;
+  chunks = (B + per_chunk - 1) / per_chunk;
+  float* wbuf = workspace; float* S0 = wbuf + (int64_t)B * MK; float* part = S0 + MK;
+  cudaStream_t st = (cudaStream_t)stream;
+  gmm_dx_kernel<<<B, 256, 0, st>>>(x, x_bstride, mG, inv_var, resp, g, wbuf, dx, dx_bstride, M, K, n);
+  int rc = check_launch("gmm_train_dx");
+  if (rc != CFPP_OK || !dmG) return rc;
+  gmm_psum_kernel<<<dim3((n + 255) / 256, (MK + MKT - 1) / MKT, chunks), 256, 0, st>>>(x, x_bstride, wbuf, part, B, MK, n, per_chunk);
+  if ((rc = check_launch("gmm_train_psum")) != CFPP_OK) return rc;
+  gmm_s0_kernel<<<MK, 256, 0, st>>>(wbuf, S0, B, MK);
+  if ((rc = check_launch("gmm_train_s0")) != CFPP_OK) return rc;
+  gmm_finish_kernel<<<grid1d((int64_t)MK * n), 256, 0, st>>>(part, S0, mG, sG, wG, dmG, dsG, dwG, M, K, n, chunks);
+  return check_launch("gmm_train_finish");
+}

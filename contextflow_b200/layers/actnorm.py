@@ -4,7 +4,7 @@ parameters whenever `initialized == 0`, also in eval mode."""
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import ops, training
 from .activations import FlowActivationLayer
 from .context import ContextPlan
 from .flowlayer import PackCache, inference_only
@@ -57,7 +57,8 @@ class ActNorm(FlowActivationLayer):
         return ops.linear(c, wt, self.CN.bias.detach()), logp_c          # (B, 2D) 'b (p d)'
 
     def forward(self, x, context=None):
-        inference_only(self.NN_t); inference_only(x)
+        if self.context_net:
+            inference_only(self.NN_t); inference_only(x); inference_only(self.CN.weight)
         HW = x.shape[2] * x.shape[3]
         if self.context_net:
             cm, logp_c = self.context_affine(context)
@@ -68,6 +69,8 @@ class ActNorm(FlowActivationLayer):
             return ops.actnorm(x, None, None, cm, logp_c, float(HW), mode=2)
         if not self.is_initialized():
             self.initialize(x)
+        if training.wants_grad(x, self.NN_t, self.NN_logs):
+            return training.ActNormFn.apply(x, self.NN_t, self.NN_logs)
         return ops.actnorm(x, self.NN_t.detach(), self.NN_logs.detach())
 
     def reverse(self, z, context=None):

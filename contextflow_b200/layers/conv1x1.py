@@ -2,7 +2,7 @@
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import ops, training
 from .context import ContextPlan
 from .flowlayer import FlowLayer, PackCache, inference_only
 
@@ -37,6 +37,8 @@ class Conv1x1(FlowLayer):
         return ops.linear(c, wt, self.CN.bias.detach()), logp_c          # (B, D*D) 'b (d1 d2)'
 
     def forward(self, x, context=None):
+        if training.wants_grad(x, self.NN) and not self.context_net:
+            return training.Conv1x1Fn.apply(x, self.NN, self)          # autograd through libcfpp kernels
         inference_only(self.NN); inference_only(x)
         lad = self.logabsdet()
         if self.context_net:

@@ -3,7 +3,7 @@ TransCoupling (SimpleViT conditioner, :100-159).  Conditioner -> h in HBM -> fus
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import ops, training
 from .context import ContextPlan
 from .flowlayer import FlowLayer, PackCache, inference_only
 from .simple_vit import SimpleViT
@@ -94,7 +94,12 @@ class Coupling(_CouplingBase):
         return ops.conv_cond_tc_coupling(x, pk['tc'], b1, b2, b3, self._dims[1], self.krn[0], self.krn[1], **kw)
 
     def forward(self, x, context=None):
+        if not self.context_net and training.wants_grad(x, *self.NN.parameters()):
+            c1, c2, c3 = self.NN[0], self.NN[2], self.NN[4]
+            return training.CouplingConvFn.apply(x, c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias)
         inference_only(x)
+        if self.context_net:
+            inference_only(self.CN[0].weight)
         D, H, O = self._dims
         Hh, Ww = x.shape[2], x.shape[3]
         pk = self._packed_nn()

@@ -4,7 +4,7 @@ ConditionalGaussianDistribution (encoder base, :234-270)."""
 import torch
 import torch.nn as nn
 
-from ... import ops, rng
+from ... import ops, rng, training
 from ..context import ContextPlan
 from ..flowlayer import PackCache, inference_only
 
@@ -60,6 +60,8 @@ class GaussianMixtureDistribution(nn.Module):
         self._tables = PackCache()
 
     def log_prob(self, input, context=None):
+        if not self.context_net and training.wants_grad(input, self.mG, self.sG, self.wG):
+            return training.GmmFn.apply(input, self.mG, self.sG, self.wG, self)
         inference_only(self.mG); inference_only(input)
         H, W = input.shape[2], input.shape[3]
         if isinstance(context, list):

@@ -3,7 +3,7 @@ ldj into a (B, M) log-det and adds the base log-prob; FlowInvSequential.sample (
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import ops, training
 
 __all__ = ['FlowSequential', 'FlowInvSequential']
 
@@ -71,6 +71,8 @@ class FlowSequential(nn.Module):
             out, ldj = module(out, context)
             terms.append(ldj)                                   # (B,), (B,1) broadcast or (B,M)   (flowsequential.py:23)
         logprob = self.dist.log_prob(out, context)
+        if training.wants_grad(logprob, *terms):
+            return out, training.LdjSumFn.apply(logprob, self.mixtures, *terms)
         # logdet = ((0 + ldj_0) + ldj_1) + ...; logprob + logdet  (flowsequential.py:20-27), same order, one launch
         return out, ops.ldj_sum(terms, B, self.mixtures, input.device, last=logprob)
 

@@ -1,5 +1,5 @@
 """Squeeze / UnSqueeze: space-to-depth index permutation, bit exact (reference layers/squeeze.py)."""
-from .. import ops
+from .. import ops, training
 from .flowlayer import FlowLayer
 
 
@@ -9,6 +9,8 @@ class Squeeze(FlowLayer):
         self.p = patch_size
 
     def forward(self, input, context=None):
+        if training.wants_grad(input):
+            return training.SqueezeFn.apply(input, self.p[0], self.p[1]), self.logdet(input, context)
         return ops.squeeze(input, self.p[0], self.p[1]), self.logdet(input, context)
 
     def reverse(self, input, context=None):

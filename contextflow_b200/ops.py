@@ -647,3 +647,116 @@ def ldj_sum(terms, B, M, device, last=None):
         _call('ldj_sum', (_p(out), _p(first), _p(last if final else None), parr, carr, n, B, M, _stream()))
         first = out
     return out
+
+
+# ---------------------------------------------------------------------------------------------- training direction
+def coupling_bwd(x, h, dz, dldj=None):
+    _need_cuda(x, h, dz); x = _f32(x); h = _f32(h); dz = _f32(dz)
+    B, Cc = x.shape[0], x.shape[1]
+    HW = x[0, 0].numel() if B else 1
+    dx = torch.empty_like(x); dh = torch.empty_like(h)
+    _set_work(bytes=20.0 * x.numel())
+    _call('coupling_bwd', (_p(x), _p(h), _p(dz), _p(None if dldj is None else _f32(dldj)), _p(dx), _p(dh), B, Cc, HW, _stream()))
+    return dx, dh
+
+
+def actnorm_bwd(x, dz, dldj, t, logs, need_dx=True):
+    _need_cuda(x, dz); x = _f32(x); dz = _f32(dz)
+    B, D = x.shape[0], x.shape[1]
+    HW = x[0, 0].numel()
+    dx = torch.empty_like(x) if need_dx else None
+    dt = torch.empty(D, device=x.device, dtype=torch.float32); dlogs = torch.empty_like(dt)
+    ws = torch.empty(int(lib().cfpp_actnorm_bwd_workspace_floats(B, D)), device=x.device, dtype=torch.float32)
+    _set_work(bytes=(12.0 if need_dx else 8.0) * x.numel())
+    _call('actnorm_bwd', (_p(x), _p(dz), _p(None if dldj is None else _f32(dldj)), _p(_f32(t)), _p(_f32(logs)), _p(dx), _p(dt), _p(dlogs),
+                          _p(ws), B, D, HW, _stream()))
+    return dx, dt, dlogs
+
+
+def conv2d_fwd(x, cin, w, b, relu):
+    """out = [relu](conv(x[:, :cin]) + b), 'same' reflect padding; x may be wider than cin channels (read through its batch stride)."""
+    _need_cuda(x, w)
+    xv, bstride = _half_view(x[:, :cin])
+    B, H, W = x.shape[0], x.shape[2], x.shape[3]
+    cout, KH, KW = w.shape[0], w.shape[2], w.shape[3]
+    out = torch.empty((B, cout, H, W), device=x.device, dtype=torch.float32)
+    _set_work(flops=2.0 * B * cout * cin * KH * KW * H * W)
+    _call('conv2d_fwd', (_p(xv), bstride, _p(_f32(w)), _p(None if b is None else _f32(b)), _p(out), B, cin, cout, H, W, KH, KW, int(bool(relu)), _stream()))
+    return out
+
+
+def conv2d_bwd_data(dout, w, act=None, out=None, accumulate=False):
+    """Gradient w.r.t. the convolution's input; `out` (B, >=Cin, H, W) may be a wider tensor whose first Cin channels receive (+)= it."""
+    _need_cuda(dout, w); dout = _f32(dout)
+    B, cout, H, W = dout.shape
+    cin, KH, KW = w.shape[1], w.shape[2], w.shape[3]
+    if out is None:
+        out = torch.empty((B, cin, H, W), device=dout.device, dtype=torch.float32)
+    ov, ostride = _half_view(out[:, :cin])
+    assert ov.data_ptr() == out.data_ptr(), 'conv2d_bwd_data: output view must alias the given tensor'
+    av, astride = (None, 0) if act is None else _half_view(act[:, :cin])
+    _set_work(flops=2.0 * B * cout * cin * KH * KW * H * W)
+    _call('conv2d_bwd_data', (_p(dout), _p(_f32(w)), _p(av), astride, _p(ov), ostride, int(bool(accumulate)), B, cin, cout, H, W, KH, KW, _stream()))
+    return out
+
+
+def conv2d_bwd_weight(x, cin, dout, wshape, bias=True):
+    _need_cuda(x, dout); dout = _f32(dout)
+    xv, bstride = _half_view(x[:, :cin])
+    B, cout, H, W = dout.shape
+    KH, KW = wshape[2], wshape[3]
+    dW = torch.empty(tuple(wshape), device=dout.device, dtype=torch.float32)
+    db = torch.empty(cout, device=dout.device, dtype=torch.float32) if bias else None
+    _set_work(flops=2.0 * B * cout * cin * KH * KW * H * W)
+    _call('conv2d_bwd_weight', (_p(xv), bstride, _p(dout), _p(dW), _p(db), B, cin, cout, H, W, KH, KW, _stream()))
+    return dW, db
+
+
+def logdet_grad_(dNN, inv, dldj, HW):
+    _need_cuda(dNN, inv, dldj)
+    _call('logdet_grad', (_p(dNN), _p(_f32(inv)), _p(_f32(dldj)), dldj.shape[0], dNN.shape[0], int(HW), _stream()))
+    return dNN
+
+
+def rowsum(g):
+    _need_cuda(g); g = _f32(g)
+    B, M = g.shape
+    out = torch.empty(B, device=g.device, dtype=torch.float32)
+    _call('rowsum', (_p(g), _p(out), B, M, _stream()))
+    return out
+
+
+def gmm_train_prep(sG, wG):
+    _need_cuda(sG, wG)
+    M, K = wG.shape
+    n = sG[0, 0].numel()
+    inv_var = torch.empty((M, K, n), device=sG.device, dtype=torch.float32)
+    cst = torch.empty((M, K), device=sG.device, dtype=torch.float32)
+    _call('gmm_train_prep', (_p(_f32(sG)), _p(_f32(wG)), _p(inv_var), _p(cst), M, K, n, _stream()))
+    return inv_var, cst
+
+
+def gmm_train_fwd(x, mG, inv_var, cst):
+    _need_cuda(x, mG)
+    xv, bstride = _half_view(x)
+    B = x.shape[0]
+    M, K, n = inv_var.shape
+    logp = torch.empty((B, M), device=x.device, dtype=torch.float32)
+    resp = torch.empty((B, M, K), device=x.device, dtype=torch.float32)
+    _set_work(flops=3.0 * B * M * K * n)
+    _call('gmm_train_fwd', (_p(xv), bstride, _p(_f32(mG)), _p(inv_var), _p(cst), _p(logp), _p(resp), B, M, K, n, _stream()))
+    return logp, resp
+
+
+def gmm_train_bwd(x, mG, sG, wG, inv_var, resp, g, need_dx=True):
+    _need_cuda(x, mG, g); g = _f32(g)
+    xv, bstride = _half_view(x)
+    B = x.shape[0]
+    M, K, n = inv_var.shape
+    dx = torch.empty((B,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32) if need_dx else None
+    dmG = torch.empty_like(mG, memory_format=torch.contiguous_format); dsG = torch.empty_like(dmG); dwG = torch.empty((M, K), device=x.device, dtype=torch.float32)
+    ws = torch.empty(int(lib().cfpp_gmm_train_bwd_workspace_floats(B, M, K, n)), device=x.device, dtype=torch.float32)
+    _set_work(flops=8.0 * B * M * K * n)
+    _call('gmm_train_bwd', (_p(xv), bstride, _p(_f32(mG)), _p(_f32(sG)), _p(_f32(wG)), _p(inv_var), _p(resp), _p(g), _p(dx), n,
+                            _p(dmG), _p(dsG), _p(dwG), _p(ws), B, M, K, n, _stream()))
+    return dx, dmG, dsG, dwG

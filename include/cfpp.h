@@ -313,6 +313,50 @@ int cfpp_score_epilogue(const float* logp, float dim_inv, const int64_t* gt, con
                         float* scaled, float* lse, float* softmax1, float* last, int64_t* argmax, float* sums,
                         void* workspace, int B, int M, void* stream);
 
+/* ---- training direction, context-free conv stack: SURVEY §8(f)-1 ------------------------------------------------- */
+/* What torch autograd derives for the reference (experiment_ad.py:204-213).  All gradients fp32; weight gradients are OVERWRITTEN
+ * (zeroed inside, then accumulated with fp32 atomics over the batch).
+ * Coupling backward (layers/coupling.py:50-66): given x, h of the forward, dz and dldj (B, may be NULL):
+ *   dx = cat(dz0, dz1 * s); dh = cat(dz1, (dz1 * x1 * s + dldj[b]) * (1 - tanh^2(r/2))), s = exp(2 tanh(r/2)).
+ *   The conditioner's own gradient is then ADDED onto dx[:, :C/2] by cfpp_conv2d_bwd_data(accumulate = 1). */
+int cfpp_coupling_bwd(const float* x, const float* h, const float* dz, const float* dldj, float* dx, float* dh,
+                      int B, int C, int HW, void* stream);
+/* ActNorm backward without context (layers/actnorm.py:50-60): dx = dz * exp(-logs) (dx may be NULL);
+ * dt[d] = -sum dz * exp(-logs); dlogs[d] = -sum dz * z + sum_b dldj[b].  workspace: cfpp_actnorm_bwd_workspace_floats(B, D) floats. */
+int64_t cfpp_actnorm_bwd_workspace_floats(int B, int D);
+int cfpp_actnorm_bwd(const float* x, const float* dz, const float* dldj, const float* t, const float* logs,
+                     float* dx, float* dt, float* dlogs, float* workspace, int B, int D, int HW, void* stream);
+/* One convolution of the conditioner (layers/coupling.py:26-29) with saved output, "same" reflect padding, torch weight layout
+ * (Cout, Cin, KH, KW), KH, KW in {1, 3}: out = [relu](W * in + bias).  `in` is read through a batch stride (x0 is x[:, :C/2]). */
+int cfpp_conv2d_fwd(const float* in, int64_t in_bstride, const float* W, const float* bias, float* out,
+                    int B, int Cin, int Cout, int H, int Wd, int KH, int KW, int relu, void* stream);
+/* din (= or +=, `accumulate`) the gradient of that convolution w.r.t. its input, including the adjoint of the reflect padding,
+ * times (act > 0) when `act` (the input activation, post-ReLU) is given. */
+int cfpp_conv2d_bwd_data(const float* dout, const float* W, const float* act, int64_t act_bstride, float* din, int64_t din_bstride,
+                         int accumulate, int B, int Cin, int Cout, int H, int Wd, int KH, int KW, void* stream);
+/* dW (Cout, Cin, KH, KW) and db (Cout, may be NULL) of that convolution.  With 1x1 kernels and Cin = Cout = D this is also
+ * Conv1x1's dNN = sum_{b,p} dz x^T (layers/conv1x1.py:52-55). */
+int cfpp_conv2d_bwd_weight(const float* in, int64_t in_bstride, const float* dout, float* dW, float* db,
+                           int B, int Cin, int Cout, int H, int Wd, int KH, int KW, void* stream);
+/* g[i] = 0 where act[i] <= 0 (ReLU backward on a saved post-activation). */
+int cfpp_relu_mask(float* g, const float* act, int64_t n, void* stream);
+/* Conv1x1's log-det term: dNN[i][j] += HW * (sum_b dldj[b]) * inv[j][i], inv = cfpp_mat_inverse(NN). */
+int cfpp_logdet_grad(float* dNN, const float* inv, const float* dldj, int B, int D, int HW, void* stream);
+/* out[b] = sum_m g[b,m]: what a (B,) / (B,1) ldj term receives from the (B,M) accumulation (layers/flowsequential.py:23). */
+int cfpp_rowsum(const float* g, float* out, int B, int M, void* stream);
+/* Mixture base in training mode (layers/distributions/gaussian.py:142-161, context-free), M*K <= 256, n = D*H*W:
+ *   prep: inv_var (M,K,n) = 1/softplus(sG)^2, cst (M,K) = log_softmax(wG) - sum log sigma - n/2 log 2pi;
+ *   fwd : logp (B,M), resp (B,M,K) = component responsibilities (saved for the backward);
+ *   bwd : given g = dL/dlogp (B,M): dx (B,n; may be NULL), dmG, dsG (M,K,n), dwG (M,K).
+ *   workspace: cfpp_gmm_train_bwd_workspace_floats floats. */
+int cfpp_gmm_train_prep(const float* sG, const float* wG, float* inv_var, float* cst, int M, int K, int n, void* stream);
+int cfpp_gmm_train_fwd(const float* x, int64_t x_bstride, const float* mG, const float* inv_var, const float* cst,
+                       float* logp, float* resp, int B, int M, int K, int n, void* stream);
+int64_t cfpp_gmm_train_bwd_workspace_floats(int B, int M, int K, int n);
+int cfpp_gmm_train_bwd(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* wG, const float* inv_var,
+                       const float* resp, const float* g, float* dx, int64_t dx_bstride, float* dmG, float* dsG, float* dwG,
+                       float* workspace, int B, int M, int K, int n, void* stream);
+
 /* ---- container ------------------------------------------------------------------------------------------------ */
 /* FlowSequential.forward, layers/flowsequential.py:23: logdet (B,M) += ldj (B,cols) with cols = 1 (broadcast) or M. */
 int cfpp_ldj_accumulate(float* logdet, const float* ldj, int B, int M, int cols, void* stream);

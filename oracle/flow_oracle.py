@@ -129,6 +129,8 @@ class _P:
 
     def __call__(self, key):
         v = self.s[key]
+        if v.is_floating_point() and v.requires_grad and torch.is_grad_enabled():   # training direction: autograd over the op sequence
+            return v.to(DEVICE, self.dt)
         return v.detach().to(DEVICE, self.dt) if v.is_floating_point() else v.detach().to(DEVICE)
 
     def has(self, key):
@@ -607,3 +609,20 @@ def score_epilogue(logp, dim_inv, gt=None, class_w=None):
         sums[3] = w.double().sum()
     out['sums'] = torch.stack(sums).float()
     return out
+
+
+# =================================================================================================
+# training direction: the loss of experiment_ad.py:204-209 over `log_prob`; gradients by torch autograd over
+# the op sequence above (enable requires_grad on the float tensors of `state`)
+# =================================================================================================
+def training_loss(logp, gt, data_size, alpha, criterion=True, class_w=None):
+    dim_inv = 1.0 / float(np.prod(data_size))
+    s = dim_inv * logp
+    s = torch.where(s != s, torch.zeros_like(s), s)                          # experiment_ad.py:205
+    if criterion:
+        uns = -alpha * F.logsigmoid(torch.logsumexp(s, -1)).mean()           # :207
+        sup = F.cross_entropy(s, gt, weight=class_w)                         # :208, model.py:294
+    else:
+        uns = -alpha * F.logsigmoid(s).mean()
+        sup = torch.zeros_like(uns)
+    return sup + uns, sup, uns

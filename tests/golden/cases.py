@@ -33,6 +33,9 @@ CASES = {
                                   num_blocks=1, block_size=2), B=3),
     # MNIST at the literal 28x28 shape (BASELINE configs[0])
     'mnist28': dict(conf=variant('cfg1', data_size=(1, 28, 28)), B=2),
+    # generalist conv coupling on MSL-shaped windows ((3,1) kernels, 56 channels after Augment, M = 2): training-direction case
+    'msl_conv_gen': dict(conf=variant('cfg4', dataset='msl', coupling='conv', data_size=(55, 8, 1), contexts=[27], mixtures=2,
+                                      num_blocks=1, block_size=2), B=6),
 }
 
 # ---- inverse direction (make_golden_inverse.py) ----
@@ -47,4 +50,11 @@ SCORE_CASES = {
     'ad_m1': dict(B=9, M=1, size=(25, 8, 1), spread=40.0, shift=-300.0),                            # unsupervised (M = 1)
     'cl_m10': dict(B=64, M=10, size=(3, 32, 32), spread=300.0, shift=-9000.0, weight=[1.0] * 10),   # classification
     'cl_nan': dict(B=12, M=10, size=(1, 28, 28), spread=100.0, shift=-2000.0, nan=True),            # NaN -> 0 replacement
+}
+
+# ---- training direction (make_golden_training.py): context-free conv stacks; loss of experiment_ad.py:204-208 ----
+TRAINING_CASES = {
+    'cfg1': dict(alpha=1e-2, criterion=True, weight=[1.0, 0.5, 2.0, 1.0, 1.0, 1.5, 1.0, 0.7, 1.0, 1.2]),
+    'mnist28': dict(alpha=1e-2, criterion=True, weight=None),
+    'msl_conv_gen': dict(alpha=1e2, criterion=False, weight=None),
 }

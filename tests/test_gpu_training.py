@@ -1,0 +1,206 @@
+"""GPU parity of the training direction, context-free conv stacks: gradients of the reference's training loss
+(experiment_ad.py:204-209) through the libcfpp backward kernels, against gradients the unmodified reference produced with torch
+autograd (tests/golden/train_*.npz) and against autograd over the oracle on fresh inputs; one torch.optim.AdamW step (the optimizer
+model.py:289 builds) lands on the reference's updated parameters; op-level checks of every backward kernel."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from contextflow_b200 import builder, ops, rng, synth, training
+from oracle import flow_oracle as O
+from tests.golden.cases import CASES, TRAINING_CASES
+from tests.helpers import assert_close, case_inputs, golden_state, load_golden
+from tests.test_oracle_golden_training import check_grads, labels, load_train
+
+pytestmark = pytest.mark.gpu
+
+
+def build_cuda_model(case):
+    conf = case['conf']
+    model = builder.build_named(conf)
+    sd = model.state_dict(); synth.fill_state(sd, case.get('wseed', 'w0')); model.load_state_dict(sd)
+    return model.cuda()
+
+
+def reference_loss(model, x, ctx, gt, data_size, spec):
+    """experiment_ad.py:204-209 verbatim semantics, torch ops on the (B,M) result of the CUDA log_prob."""
+    dim_inv = 1.0 / torch.prod(torch.tensor(data_size))
+    log_theta = nn.LogSigmoid()
+    criterion = nn.CrossEntropyLoss(weight=None if spec['weight'] is None else torch.tensor(spec['weight']).cuda()) if spec['criterion'] else None
+    logp = dim_inv * model.log_prob(x, context=ctx)
+    logp[logp != logp] = 0.0
+    uns = -spec['alpha'] * log_theta(torch.logsumexp(logp, -1)).mean() if criterion else -spec['alpha'] * log_theta(logp).mean()
+    sup = criterion(logp, gt) if criterion else torch.zeros_like(uns)
+    return sup + uns, sup, uns
+
+
+@pytest.mark.parametrize('name', sorted(TRAINING_CASES))
+def test_gradients_match_reference_golden(name):
+    case, spec = CASES[name], TRAINING_CASES[name]
+    gold = load_train(name)
+    model = build_cuda_model(case).train()
+    x, ctx = case_inputs(case)
+    gt = labels(name, case['B'], case['conf']['mixtures']).cuda()
+    opt = torch.optim.AdamW(filter(lambda p: p.requires_grad, model.parameters()), lr=1e-3)
+    with rng.use_source(synth.NoiseTape(case.get('nseed', 'noise0'))):
+        cost, sup, uns = reference_loss(model, x.cuda(), ctx.cuda(), gt, case['conf']['data_size'], spec)
+    assert_close(np.array([cost.item(), sup.item(), uns.item()]), gold['loss'], 1e-4, 1e-5, f'{name} loss')
+    cost.backward()
+    named = dict(model.named_parameters())
+    assert sorted(gold['names']) == sorted(k for k, p in named.items() if p.requires_grad)
+    check_grads(name, {k: named[k].grad for k in gold['names']}, gold, rtol=2e-4)
+    opt.step()
+    for k in gold['names']:
+        pd = named[k].detach().double()
+        ref = gold[f'psum:{k}']
+        assert abs(pd.sum().item() - ref[0]) <= 1e-5 * ref[1] + 1e-5, f'{name} AdamW step {k}: sum'
+        assert abs(pd.abs().sum().item() - ref[1]) <= 1e-5 * ref[1] + 1e-5, f'{name} AdamW step {k}: abs sum'
+
+
+@pytest.mark.parametrize('name,B', [('cfg1', 37), ('msl_conv_gen', 50)])
+def test_gradients_match_oracle_autograd_fresh_inputs(name, B):
+    case = dict(CASES[name], B=B, iseed='in5', nseed='noise5')
+    spec = TRAINING_CASES[name]
+    stack, state = golden_state(load_golden(name), case)
+    model = build_cuda_model(case).train()
+    names = [k for k, p in model.named_parameters() if p.requires_grad]
+    for k in names:
+        state[k].requires_grad_(True)
+    x, ctx = case_inputs(case)
+    gt = labels(name + 'fresh', B, case['conf']['mixtures'])
+    w = None if spec['weight'] is None else torch.tensor(spec['weight'])
+    grads = {}
+    for dt in (torch.float32, torch.float64):
+        for k in names:
+            state[k].grad = None
+        _, logp = O.forward(stack, state, x, ctx, synth.NoiseTape('noise5'), dt)
+        cost_o, _, _ = O.training_loss(logp, gt, case['conf']['data_size'], spec['alpha'], spec['criterion'], None if w is None else w.to(dt))
+        cost_o.backward()
+        grads[dt] = {k: state[k].grad.double().clone() for k in names}
+    with rng.use_source(synth.NoiseTape('noise5')):
+        cost, _, _ = reference_loss(model, x.cuda(), ctx.cuda(), gt.cuda(), case['conf']['data_size'], spec)
+    cost.backward()
+    assert_close(cost.item(), cost_o.item(), 1e-4, 1e-5, 'loss')
+    named = dict(model.named_parameters())
+    for k in names:
+        # truth = autograd over the float64 oracle; the CUDA gradient must be within 2e-4 of the gradient's largest entry, or as close to
+        # the truth as the reference's own float32 arithmetic gets (Conv1x1's dNN is a difference of two large cancelling sums)
+        truth = grads[torch.float64][k]; got = named[k].grad.cpu().double()
+        scale = truth.abs().max().item() + 1e-12
+        err = (got - truth).abs().max().item()
+        ref_err = (grads[torch.float32][k] - truth).abs().max().item()
+        assert err <= 2e-4 * scale + 3.0 * ref_err + 1e-7, f'{name} grad {k}: max abs err {err:.3e}, fp32 reference err {ref_err:.3e}, scale {scale:.3e}'
+
+
+def test_training_loss_decreases_over_steps():
+    """Ten AdamW steps on one batch through the CUDA forward/backward: the loss goes down and stays finite."""
+    case = dict(CASES['cfg1'], B=64, iseed='in6')
+    spec = TRAINING_CASES['cfg1']
+    model = build_cuda_model(case).train()
+    x, ctx = case_inputs(case)
+    gt = labels('steps', 64, 10).cuda()
+    opt = torch.optim.AdamW(filter(lambda p: p.requires_grad, model.parameters()), lr=1e-3)
+    losses = []
+    for _ in range(10):
+        opt.zero_grad()
+        cost, _, _ = reference_loss(model, x.cuda(), ctx.cuda(), gt, case['conf']['data_size'], spec)
+        cost.backward(); opt.step()
+        losses.append(cost.item())
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+# ---- op-level: every backward kernel against torch autograd of the same op in float64 -------------------------------------------------
+@pytest.mark.parametrize('B,C,H,W', [(5, 8, 16, 16), (3, 32, 8, 8), (7, 56, 8, 1), (2, 4, 2, 2)])
+def test_coupling_bwd(B, C, H, W):
+    x = synth.normal('cbx', (B, C, H, W)); h = synth.normal('cbh', (B, C, H, W)) * 0.7
+    dz = synth.normal('cbdz', (B, C, H, W)); dl = synth.normal('cbdl', (B,))
+    xd, hd = x.double().requires_grad_(True), h.double().requires_grad_(True)
+    z, ldj = O.coupling_elementwise(xd, hd)
+    (z * dz.double()).sum().backward(retain_graph=True); (ldj * dl.double()).sum().backward()
+    dx, dh = ops.coupling_bwd(x.cuda(), h.cuda(), dz.cuda(), dl.cuda())
+    assert_close(dx.cpu().numpy(), xd.grad.numpy(), 1e-5, 1e-5, 'dx')
+    assert_close(dh.cpu().numpy(), hd.grad.numpy(), 1e-4, 1e-5, 'dh')
+
+
+@pytest.mark.parametrize('B,D,H,W', [(9, 8, 16, 16), (300, 32, 8, 8), (4, 56, 8, 1)])
+def test_actnorm_bwd(B, D, H, W):
+    x = synth.normal('abx', (B, D, H, W)); dz = synth.normal('abdz', (B, D, H, W)); dl = synth.normal('abdl', (B,))
+    t = synth.normal('abt', (D,)) * 0.3; logs = synth.normal('abl', (D,)) * 0.3
+    xd, td, ld = (v.double().requires_grad_(True) for v in (x, t, logs))
+    z = (xd - td[None, :, None, None]) * torch.exp(-ld)[None, :, None, None]
+    ((z * dz.double()).sum() + (ld.sum() * dl.double()).sum()).backward()
+    dx, dt, dlogs = ops.actnorm_bwd(x.cuda(), dz.cuda(), dl.cuda(), t.cuda(), logs.cuda())
+    assert_close(dx.cpu().numpy(), xd.grad.numpy(), 1e-5, 1e-6, 'dx')
+    assert_close(dt.cpu().numpy(), td.grad.numpy(), 1e-4, 1e-4 * float(td.grad.abs().max()), 'dt')
+    assert_close(dlogs.cpu().numpy(), ld.grad.numpy(), 1e-4, 1e-4 * float(ld.grad.abs().max()), 'dlogs')
+
+
+@pytest.mark.parametrize('B,Cin,Cout,H,W,KH,KW', [(3, 4, 16, 16, 16, 1, 1), (3, 16, 16, 16, 16, 3, 3), (5, 64, 64, 8, 8, 3, 3), (4, 112, 112, 8, 1, 3, 1),
+                                                   (2, 28, 112, 8, 1, 1, 1), (2, 6, 10, 2, 2, 3, 3), (3, 5, 7, 3, 4, 3, 3)])
+def test_conv2d_family(B, Cin, Cout, H, W, KH, KW):
+    x = synth.normal('cvx', (B, Cin + 3, H, W)); w = synth.normal('cvw', (Cout, Cin, KH, KW)) * 0.2; b = synth.normal('cvb', (Cout,)) * 0.1
+    dout = synth.normal('cvd', (B, Cout, H, W))
+    xd, wd, bd = x[:, :Cin].double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    pad = F.pad(xd, (KW // 2, KW // 2, KH // 2, KH // 2), mode='reflect') if (KH > 1 or KW > 1) else xd
+    out = torch.relu(F.conv2d(pad, wd, bd))
+    (out * dout.double()).sum().backward()
+    xc = x.cuda()
+    got = ops.conv2d_fwd(xc, Cin, w.cuda(), b.cuda(), relu=True)
+    assert_close(got.cpu().numpy(), out.detach().numpy(), 1e-4, 1e-5, 'conv fwd')
+    g = dout.cuda().clone(); ops._call('relu_mask', (ops._p(g), ops._p(got), g.numel(), ops._stream()))
+    dW, db = ops.conv2d_bwd_weight(xc, Cin, g, w.shape)
+    assert_close(dW.cpu().numpy(), wd.grad.numpy(), 1e-4, 1e-4 * float(wd.grad.abs().max()), 'dW')
+    assert_close(db.cpu().numpy(), bd.grad.numpy(), 1e-4, 1e-4 * float(bd.grad.abs().max()), 'db')
+    din = ops.conv2d_bwd_data(g, w.cuda())
+    assert_close(din.cpu().numpy(), xd.grad.numpy(), 1e-4, 1e-5 * float(xd.grad.abs().max()), 'din')
+    wide = torch.ones(B, Cin + 3, H, W, device='cuda')
+    ops.conv2d_bwd_data(g, w.cuda(), out=wide, accumulate=True)
+    assert_close(wide[:, :Cin].cpu().numpy(), xd.grad.numpy() + 1.0, 1e-4, 1e-5 * float(xd.grad.abs().max()) + 1e-6, 'din accumulate')
+    assert torch.equal(wide[:, Cin:], torch.ones_like(wide[:, Cin:]))
+
+
+@pytest.mark.parametrize('B,M,K,D,H,W', [(6, 10, 8, 32, 8, 8), (33, 2, 8, 56, 8, 1), (3, 1, 8, 4, 2, 2)])
+def test_gmm_training_kernels(B, M, K, D, H, W):
+    x = synth.normal('gx', (B, D, H, W)); mG = synth.normal('gm', (M, K, D, H, W)); sG = synth.normal('gs', (M, K, D, H, W)) * 0.5 + 1.0
+    wG = synth.normal('gw', (M, K)); g = synth.normal('gg', (B, M))
+    state = {'dist.mG': mG.double().requires_grad_(True), 'dist.sG': sG.double().requires_grad_(True), 'dist.wG': wG.double().requires_grad_(True)}
+    xd = x.double().requires_grad_(True)
+    lay = dict(key='dist', M=M, K=K, enc=None)
+    ref = O.gmm_log_prob(O._P(state, torch.float64), state, lay, xd, None, None, torch.float64)
+    (ref * g.double()).sum().backward()
+    inv_var, cst = ops.gmm_train_prep(sG.cuda(), wG.cuda())
+    logp, resp = ops.gmm_train_fwd(x.cuda(), mG.cuda(), inv_var, cst)
+    assert_close(logp.cpu().numpy(), ref.detach().numpy(), 1e-5, 1e-3, 'logp')
+    dx, dmG, dsG, dwG = ops.gmm_train_bwd(x.cuda(), mG.cuda(), sG.cuda(), wG.cuda(), inv_var, resp, g.cuda())
+    for got, want, what in ((dx, xd.grad, 'dx'), (dmG, state['dist.mG'].grad, 'dmG'), (dsG, state['dist.sG'].grad, 'dsG'), (dwG, state['dist.wG'].grad, 'dwG')):
+        assert_close(got.cpu().numpy(), want.numpy(), 1e-4, 1e-4 * float(want.abs().max()) + 1e-7, what)
+
+
+def test_conv1x1_and_ldj_sum_functions():
+    B, D, H, W, M = 6, 8, 4, 4, 3
+    x = synth.normal('c1x', (B, D, H, W)); NN = synth.normal('c1n', (D, D)) * 0.3 + torch.eye(D)
+    gz = synth.normal('c1g', (B, D, H, W)); gl = synth.normal('c1l', (B, M))
+    xd, Nd = x.double().requires_grad_(True), NN.double().requires_grad_(True)
+    z = torch.einsum('ij,bjhw->bihw', Nd, xd)
+    ldj = (torch.linalg.slogdet(Nd)[1] * H * W).expand(B)
+    out = torch.zeros(B, M, dtype=torch.float64) + ldj[:, None]
+    ((z * gz.double()).sum() + (out * gl.double()).sum()).backward()
+    from contextflow_b200.layers import Conv1x1
+    lay = Conv1x1((D, H, W)).cuda()
+    with torch.no_grad():
+        lay.NN.copy_(NN.cuda())
+    xc = x.cuda().requires_grad_(True)
+    zc, lc = lay(xc)
+    total = training.LdjSumFn.apply(torch.zeros(B, M, device='cuda'), M, lc)
+    ((zc * gz.cuda()).sum() + (total * gl.cuda()).sum()).backward()
+    assert_close(xc.grad.cpu().numpy(), xd.grad.numpy(), 1e-4, 1e-5, 'dx')
+    assert_close(lay.NN.grad.cpu().numpy(), Nd.grad.numpy(), 1e-4, 1e-4 * float(Nd.grad.abs().max()), 'dNN')
+
+
+def test_unsupported_layers_raise_under_autograd():
+    model = build_cuda_model(CASES['cfg4']).train()            # ViT conditioner: no backward kernels yet
+    x, ctx = case_inputs(CASES['cfg4'])
+    with pytest.raises(NotImplementedError):
+        model.log_prob(x.cuda(), ctx.cuda())
