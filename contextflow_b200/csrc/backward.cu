@@ -84,147 +84,234 @@ __global__ void actnorm_bwd_finish_kernel(const float* __restrict__ partial, con
 // One CTA per sample; the sample's input planes live in shared memory.  Used for the conditioner in training mode (the three
 // convolutions as separate launches so that the post-ReLU activations are saved) and, with 1x1 kernels, for Conv1x1's backward.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int CG = 4;        // output channels per thread
+constexpr int CG = 4;        // channels per thread
+constexpr int PXT = 4;       // pixels per thread
 
-__global__ void __launch_bounds__(256) conv2d_fwd_kernel(const float* __restrict__ in, int64_t in_bstride, const float* __restrict__ W,
-                                                         const float* __restrict__ bias, float* __restrict__ out,
-                                                         int Cin, int Cout, int H, int Wd, int KH, int KW, int relu) {
-  extern __shared__ float sin_[];                                    // Cin * HW
-  const int HW = H * Wd, KK = KH * KW;
-  const int64_t b = blockIdx.x;
-  for (int i = threadIdx.x; i < Cin * HW; i += blockDim.x) sin_[i] = in[b * in_bstride + i];
-  __syncthreads();
-  const int ncg = (Cout + CG - 1) / CG;
-  for (int item = threadIdx.x; item < HW * ncg; item += blockDim.x) {
-    const int p = item % HW, cg = item / HW;
-    const int y = p / Wd, xx = p - y * Wd;
-    const int co0 = cg * CG;
-    float acc[CG];
-#pragma unroll
-    for (int c = 0; c < CG; ++c) acc[c] = (bias && co0 + c < Cout) ? bias[co0 + c] : 0.f;
-    for (int kh = 0; kh < KH; ++kh) {
-      const int yy = reflect_idx(y + kh - KH / 2, H);
-      for (int kw = 0; kw < KW; ++kw) {
-        const int q = yy * Wd + reflect_idx(xx + kw - KW / 2, Wd);
-        const float* wp = W + (int64_t)co0 * Cin * KK + kh * KW + kw;
-        for (int ci = 0; ci < Cin; ++ci) {
-          const float v = sin_[ci * HW + q];
-#pragma unroll
-          for (int c = 0; c < CG; ++c)
-            if (co0 + c < Cout) acc[c] = fmaf(__ldg(wp + ((int64_t)c * Cin + ci) * KK), v, acc[c]);
-        }
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < CG; ++c)
-      if (co0 + c < Cout) out[(b * Cout + co0 + c) * HW + p] = relu ? fmaxf(acc[c], 0.f) : acc[c];
+__host__ __device__ inline int odd_stride(int n) { return n | 1; }   // odd row strides: channel rows start in different banks
+
+// Stage the first C channels of sample b with a reflect halo of (PH, PW): dst[c * S + (y + PH) * Wp + (x + PW)], Wp = W + 2 PW.
+template <int PH, int PW>
+__device__ __forceinline__ void stage_reflect(float* dst, const float* __restrict__ src, int C, int H, int Wd, int S) {
+  const int Hp = H + 2 * PH, Wp = Wd + 2 * PW, HW = H * Wd;
+  for (int i = threadIdx.x; i < C * Hp * Wp; i += blockDim.x) {
+    const int c = i / (Hp * Wp), r = i - c * (Hp * Wp);
+    const int yp = r / Wp, xp = r - yp * Wp;
+    dst[c * S + r] = src[c * HW + reflect_idx(yp - PH, H) * Wd + reflect_idx(xp - PW, Wd)];
   }
 }
 
-// din[b,ci,q] (= or +=) mask(act[b,ci,q] > 0) * sum_{u in U(q)} sum_{co,tap} W[co,ci,tap] dout[b,co,u - tap + pad]
-// U(q): q itself plus the padded positions that reflect onto q (the adjoint of reflect padding).
+// out[b,co,p] = [relu](bias[co] + sum_{ci,kh,kw} W[co,ci,kh,kw] in[b,ci,reflect(p + (kh,kw) - pad)]).
+// Thread = PXT pixels x CG output channels: per (ci, tap) 4 warp-uniform weight loads + 4 shared loads feed 16 FMAs.
+template <int KH, int KW>
+__global__ void __launch_bounds__(256) conv2d_fwd_kernel(const float* __restrict__ in, int64_t in_bstride, const float* __restrict__ W,
+                                                         const float* __restrict__ bias, float* __restrict__ out,
+                                                         int Cin, int Cout, int H, int Wd, int relu) {
+  constexpr int PH = KH / 2, PW = KW / 2, KK = KH * KW;
+  extern __shared__ float sm[];
+  const int HW = H * Wd, Wp = Wd + 2 * PW, S = odd_stride((H + 2 * PH) * Wp);
+  const int64_t b = blockIdx.x;
+  stage_reflect<PH, PW>(sm, in + b * in_bstride, Cin, H, Wd, S);
+  __syncthreads();
+  const int ncg = (Cout + CG - 1) / CG, nslot = (HW + PXT - 1) / PXT;
+  for (int item = threadIdx.x; item < nslot * ncg; item += blockDim.x) {
+    const int slot = item % nslot, co0 = (item / nslot) * CG;
+    int pb[PXT];
+#pragma unroll
+    for (int j = 0; j < PXT; ++j) { int p = slot + j * nslot; if (p >= HW) p = HW - 1; const int y = p / Wd; pb[j] = y * Wp + (p - y * Wd); }
+    float acc[PXT][CG];
+#pragma unroll
+    for (int c = 0; c < CG; ++c) {
+      const float bv = (bias && co0 + c < Cout) ? bias[co0 + c] : 0.f;
+#pragma unroll
+      for (int j = 0; j < PXT; ++j) acc[j][c] = bv;
+    }
+    const int nc = min(CG, Cout - co0);
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float* sp = sm + ci * S;
+      const float* wp = W + ((int64_t)co0 * Cin + ci) * KK;
+#pragma unroll
+      for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < KW; ++kw) {
+          float w[CG];
+#pragma unroll
+          for (int c = 0; c < CG; ++c) w[c] = c < nc ? __ldg(wp + (int64_t)c * Cin * KK + kh * KW + kw) : 0.f;
+#pragma unroll
+          for (int j = 0; j < PXT; ++j) {
+            const float v = sp[pb[j] + kh * Wp + kw];
+#pragma unroll
+            for (int c = 0; c < CG; ++c) acc[j][c] = fmaf(w[c], v, acc[j][c]);
+          }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < PXT; ++j) {
+      const int p = slot + j * nslot;
+      if (p >= HW) continue;
+#pragma unroll
+      for (int c = 0; c < CG; ++c)
+        if (c < nc) out[(b * Cout + co0 + c) * HW + p] = relu ? fmaxf(acc[j][c], 0.f) : acc[j][c];
+    }
+  }
+}
+
+// Gradient w.r.t. the convolution's input.  Phase 1: dpad[ci,u] = sum_{co,kh,kw} W[co,ci,kh,kw] dout0[co, u - (kh,kw)] over the PADDED
+// domain u (dout staged with a zero halo of (KH-1, KW-1), so no bounds checks), register tile PXT x CG, into shared memory.
+// Phase 2: fold the reflect halo back (the adjoint of reflect padding): din[q] = sum of dpad over the positions that read q,
+// times (act > 0), stored or accumulated.  With 1x1 kernels phase 1 writes straight to global memory.
+template <int KH, int KW>
 __global__ void __launch_bounds__(256) conv2d_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict__ W,
                                                               const float* __restrict__ act, int64_t act_bstride,
                                                               float* __restrict__ din, int64_t din_bstride, int accumulate,
-                                                              int Cin, int Cout, int H, int Wd, int KH, int KW) {
-  extern __shared__ float sd[];                                      // Cout * HW
-  const int HW = H * Wd, KK = KH * KW, ph = KH / 2, pw = KW / 2;
+                                                              int Cin, int Cout, int H, int Wd) {
+  constexpr int PH = KH / 2, PW = KW / 2, KK = KH * KW, ZH = KH - 1, ZW = KW - 1;
+  extern __shared__ float sm[];
+  const int HW = H * Wd;
+  const int Hp = H + 2 * PH, Wp = Wd + 2 * PW;                 // padded domain of the forward input
+  const int Hz = H + 2 * ZH, Wz = Wd + 2 * ZW;                 // dout with a zero halo
+  const int Sz = odd_stride(Hz * Wz), Sp = odd_stride(Hp * Wp);
+  float* sz = sm;                                              // Cout * Sz
+  float* spad = sm + Cout * Sz;                                // Cin * Sp (unused for 1x1)
   const int64_t b = blockIdx.x;
-  for (int i = threadIdx.x; i < Cout * HW; i += blockDim.x) sd[i] = dout[b * Cout * HW + i];
+  for (int i = threadIdx.x; i < Cout * Hz * Wz; i += blockDim.x) {
+    const int c = i / (Hz * Wz), r = i - c * (Hz * Wz);
+    const int y = r / Wz - ZH, x = r % Wz - ZW;
+    sz[c * Sz + r] = (y >= 0 && y < H && x >= 0 && x < Wd) ? dout[(b * Cout + c) * HW + y * Wd + x] : 0.f;
+  }
   __syncthreads();
-  const int ncg = (Cin + CG - 1) / CG;
-  for (int item = threadIdx.x; item < HW * ncg; item += blockDim.x) {
-    const int q = item % HW, cg = item / HW;
-    const int qy = q / Wd, qx = q - qy * Wd;
-    const int ci0 = cg * CG;
-    float acc[CG] = {0.f, 0.f, 0.f, 0.f};
-    int uys[3], uxs[3]; int ny = 0, nx = 0;
-    uys[ny++] = qy; if (ph == 1 && qy == 1) uys[ny++] = -1; if (ph == 1 && qy == H - 2) uys[ny++] = H;
-    uxs[nx++] = qx; if (pw == 1 && qx == 1) uxs[nx++] = -1; if (pw == 1 && qx == Wd - 2) uxs[nx++] = Wd;
-    for (int iy = 0; iy < ny; ++iy)
-      for (int kh = 0; kh < KH; ++kh) {
-        const int py = uys[iy] - kh + ph;
-        if (py < 0 || py >= H) continue;
-        for (int ix = 0; ix < nx; ++ix)
-          for (int kw = 0; kw < KW; ++kw) {
-            const int px = uxs[ix] - kw + pw;
-            if (px < 0 || px >= Wd) continue;
-            const int p = py * Wd + px;
-            const float* wp = W + (int64_t)ci0 * KK + kh * KW + kw;
-            for (int co = 0; co < Cout; ++co) {
-              const float g = sd[co * HW + p];
+  const int NP = Hp * Wp;
+  const int ncg = (Cin + CG - 1) / CG, nslot = (NP + PXT - 1) / PXT;
+  for (int item = threadIdx.x; item < nslot * ncg; item += blockDim.x) {
+    const int slot = item % nslot, ci0 = (item / nslot) * CG;
+    int ub[PXT];
 #pragma unroll
-              for (int c = 0; c < CG; ++c)
-                if (ci0 + c < Cin) acc[c] = fmaf(__ldg(wp + ((int64_t)co * Cin + c) * KK), g, acc[c]);
-            }
-          }
-      }
-#pragma unroll
-    for (int c = 0; c < CG; ++c) {
-      if (ci0 + c >= Cin) continue;
-      float v = acc[c];
-      if (act && !(act[b * act_bstride + (int64_t)(ci0 + c) * HW + q] > 0.f)) v = 0.f;
-      float* o = din + b * din_bstride + (int64_t)(ci0 + c) * HW + q;
-      *o = accumulate ? *o + v : v;
+    for (int j = 0; j < PXT; ++j) {
+      int u = slot + j * nslot; if (u >= NP) u = NP - 1;
+      const int uy = u / Wp, ux = u - uy * Wp;
+      ub[j] = (uy + ZH) * Wz + (ux + ZW);                      // dout0 index of tap (0,0); tap (kh,kw) reads ub - kh*Wz - kw
     }
+    float acc[PXT][CG];
+#pragma unroll
+    for (int j = 0; j < PXT; ++j)
+#pragma unroll
+      for (int c = 0; c < CG; ++c) acc[j][c] = 0.f;
+    const int nc = min(CG, Cin - ci0);
+    for (int co = 0; co < Cout; ++co) {
+      const float* gp = sz + co * Sz;
+      const float* wp = W + ((int64_t)co * Cin + ci0) * KK;
+#pragma unroll
+      for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < KW; ++kw) {
+          float w[CG];
+#pragma unroll
+          for (int c = 0; c < CG; ++c) w[c] = c < nc ? __ldg(wp + c * KK + kh * KW + kw) : 0.f;
+#pragma unroll
+          for (int j = 0; j < PXT; ++j) {
+            const float g = gp[ub[j] - kh * Wz - kw];
+#pragma unroll
+            for (int c = 0; c < CG; ++c) acc[j][c] = fmaf(w[c], g, acc[j][c]);
+          }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < PXT; ++j) {
+      const int u = slot + j * nslot;
+      if (u >= NP) continue;
+#pragma unroll
+      for (int c = 0; c < CG; ++c) {
+        if (c >= nc) continue;
+        if (KK == 1) {
+          float v = acc[j][c];
+          if (act && !(act[b * act_bstride + (int64_t)(ci0 + c) * HW + u] > 0.f)) v = 0.f;
+          float* o = din + b * din_bstride + (int64_t)(ci0 + c) * HW + u;
+          *o = accumulate ? *o + v : v;
+        } else {
+          spad[(ci0 + c) * Sp + u] = acc[j][c];
+        }
+      }
+    }
+  }
+  if (KK == 1) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cin * HW; i += blockDim.x) {
+    const int ci = i / HW, q = i - ci * HW;
+    const int qy = q / Wd, qx = q - qy * Wd;
+    int uy[3], ux[3]; int ny = 0, nx = 0;                      // padded rows / columns whose reflection is (qy, qx)
+    uy[ny++] = qy + PH; if (PH == 1 && qy == 1) uy[ny++] = 0; if (PH == 1 && qy == H - 2) uy[ny++] = H + 1;
+    ux[nx++] = qx + PW; if (PW == 1 && qx == 1) ux[nx++] = 0; if (PW == 1 && qx == Wd - 2) ux[nx++] = Wd + 1;
+    float v = 0.f;
+    for (int a = 0; a < ny; ++a)
+      for (int c = 0; c < nx; ++c) v += spad[ci * Sp + uy[a] * Wp + ux[c]];
+    if (act && !(act[b * act_bstride + (int64_t)ci * HW + q] > 0.f)) v = 0.f;
+    float* o = din + b * din_bstride + (int64_t)ci * HW + q;
+    *o = accumulate ? *o + v : v;
   }
 }
 
-// dW[co,ci,tap] += sum_{b in chunk, p} g[b,co,p] in[b,ci,nbr(p,tap)];  db[co] += sum g.   g = dout (masked by act_out > 0 when given).
-// grid (chunks, co blocks): a CTA owns NCO output channels x all input channels, PPT (co,ci) pairs per thread held in registers
-// across the samples of its chunk, then one fp32 atomicAdd per weight.
-constexpr int PPT = 2;
+// dW[co,ci,tap] += sum_{b in chunk, p} dout[b,co,p] in[b,ci,reflect(p + tap - pad)];  db[co] += sum dout.
+// grid (chunks, co blocks).  A CTA stages, per sample, the reflect-padded input planes and NCO rows of dout; thread = one input
+// channel x PPT output channels (the 3x3 input window is loaded once per pixel and reused by the PPT rows), accumulators live in
+// registers across the samples of the chunk, then one fp32 atomicAdd per weight.
+constexpr int PPT = 4;
 
-template <int KK>
+template <int KH, int KW>
 __global__ void __launch_bounds__(256) conv2d_bwd_weight_kernel(const float* __restrict__ in, int64_t in_bstride, const float* __restrict__ dout,
                                                                 float* __restrict__ dW, float* __restrict__ db,
-                                                                int B, int Cin, int Cout, int H, int Wd, int KH, int KW, int NCO, int per_chunk) {
+                                                                int B, int Cin, int Cout, int H, int Wd, int NCO, int per_chunk) {
+  constexpr int PH = KH / 2, PW = KW / 2, KK = KH * KW;
   extern __shared__ float sm[];
-  const int HW = H * Wd;
-  float* sin_ = sm;                                   // Cin * HW
-  float* sd = sin_ + Cin * HW;                        // NCO * HW
-  int* nbr = reinterpret_cast<int*>(sd + NCO * HW);   // HW * KK
+  const int HW = H * Wd, Wp = Wd + 2 * PW, S = odd_stride((H + 2 * PH) * Wp), Sg = odd_stride(HW);
+  float* sin_ = sm;                                   // Cin * S
+  float* sd = sm + Cin * S;                           // NCO * Sg
   const int co0 = blockIdx.y * NCO;
   const int nco = min(NCO, Cout - co0);
   const int b0 = blockIdx.x * per_chunk, b1 = min(B, b0 + per_chunk);
-  for (int i = threadIdx.x; i < HW * KK; i += blockDim.x) {
-    const int p = i / KK, tap = i - p * KK;
-    const int y = p / Wd, xx = p - y * Wd, kh = tap / KW, kw = tap - kh * KW;
-    nbr[i] = reflect_idx(y + kh - KH / 2, H) * Wd + reflect_idx(xx + kw - KW / 2, Wd);
-  }
+  const int cpp = 256 / Cin;                          // output channels covered per pass of the CTA (Cin <= 256)
+  const int ci = threadIdx.x % Cin, cog = threadIdx.x / Cin;
+  const bool live = cog < cpp;
   float acc[PPT][KK];
 #pragma unroll
   for (int k = 0; k < PPT; ++k)
 #pragma unroll
     for (int t = 0; t < KK; ++t) acc[k][t] = 0.f;
   float bsum = 0.f;
-  const int npairs = nco * Cin;
   for (int b = b0; b < b1; ++b) {
     __syncthreads();
-    for (int i = threadIdx.x; i < Cin * HW; i += blockDim.x) sin_[i] = in[(int64_t)b * in_bstride + i];
-    for (int i = threadIdx.x; i < nco * HW; i += blockDim.x) sd[i] = dout[((int64_t)b * Cout + co0) * HW + i];
+    stage_reflect<PH, PW>(sin_, in + (int64_t)b * in_bstride, Cin, H, Wd, S);
+    for (int i = threadIdx.x; i < nco * HW; i += blockDim.x) { const int c = i / HW; sd[c * Sg + (i - c * HW)] = dout[((int64_t)b * Cout + co0) * HW + i]; }
     __syncthreads();
-    if ((int)threadIdx.x < nco) { float s = 0.f; for (int p = 0; p < HW; ++p) s += sd[threadIdx.x * HW + p]; bsum += s; }
+    if ((int)threadIdx.x < nco) { float s = 0.f; for (int p = 0; p < HW; ++p) s += sd[threadIdx.x * Sg + p]; bsum += s; }
+    if (!live) continue;
+    const float* ip = sin_ + ci * S;
+    const float* gp[PPT];
+    bool on[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) { const int co = cog + k * cpp; on[k] = co < nco; gp[k] = sd + (on[k] ? co : 0) * Sg; }
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < Wd; ++x) {
+        float v[KK];
+#pragma unroll
+        for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < KW; ++kw) v[kh * KW + kw] = ip[(y + kh) * Wp + x + kw];
+        const int p = y * Wd + x;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          const float g = gp[k][p];
+#pragma unroll
+          for (int t = 0; t < KK; ++t) acc[k][t] = fmaf(g, v[t], acc[k][t]);
+        }
+      }
+  }
+  if (live) {
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
-      const int pair = threadIdx.x + k * 256;
-      if (pair >= npairs) continue;
-      const int co = pair / Cin, ci = pair - co * Cin;
-      const float* gp = sd + co * HW; const float* ip = sin_ + ci * HW;
-      for (int p = 0; p < HW; ++p) {
-        const float g = gp[p]; const int* nb = nbr + p * KK;
+      const int co = cog + k * cpp;
+      if (co >= nco) continue;
 #pragma unroll
-        for (int t = 0; t < KK; ++t) acc[k][t] = fmaf(g, ip[nb[t]], acc[k][t]);
-      }
+      for (int t = 0; t < KK; ++t) atomicAdd(dW + ((int64_t)(co0 + co) * Cin + ci) * KK + t, acc[k][t]);
     }
-  }
-#pragma unroll
-  for (int k = 0; k < PPT; ++k) {
-    const int pair = threadIdx.x + k * 256;
-    if (pair >= npairs) continue;
-    const int co = pair / Cin, ci = pair - co * Cin;
-#pragma unroll
-    for (int t = 0; t < KK; ++t) atomicAdd(dW + ((int64_t)(co0 + co) * Cin + ci) * KK + t, acc[k][t]);
   }
   if (db && (int)threadIdx.x < nco) atomicAdd(db + co0 + threadIdx.x, bsum);
 }
@@ -450,48 +537,62 @@ extern "C" int cfpp_actnorm_bwd(const float* x, const float* dz, const float* dl
   return check_launch("actnorm_bwd_finish");
 }
 
+#define CFPP_CONV_DISPATCH(KH, KW, ...)                                                   \
+  do {                                                                                    \
+    if (KH == 1 && KW == 1) { constexpr int kKH = 1, kKW = 1; __VA_ARGS__; }              \
+    else if (KH == 3 && KW == 3) { constexpr int kKH = 3, kKW = 3; __VA_ARGS__; }         \
+    else if (KH == 3 && KW == 1) { constexpr int kKH = 3, kKW = 1; __VA_ARGS__; }         \
+    else { constexpr int kKH = 1, kKW = 3; __VA_ARGS__; }                                 \
+  } while (0)
+
+static inline bool conv_shape_ok(int H, int Wd, int KH, int KW) {
+  return (KH == 1 || KH == 3) && (KW == 1 || KW == 3) && (KH == 1 || H >= 2) && (KW == 1 || Wd >= 2);
+}
+
 extern "C" int cfpp_conv2d_fwd(const float* in, int64_t in_bstride, const float* W, const float* bias, float* out,
                                int B, int Cin, int Cout, int H, int Wd, int KH, int KW, int relu, void* stream) {
-  CFPP_REQUIRE((KH == 1 || KH == 3) && (KW == 1 || KW == 3) && (KH == 1 || H >= 2) && (KW == 1 || Wd >= 2), "conv2d: kernel %dx%d on %dx%d", KH, KW, H, Wd);
+  CFPP_REQUIRE(conv_shape_ok(H, Wd, KH, KW), "conv2d: kernel %dx%d on %dx%d", KH, KW, H, Wd);
   if (B <= 0) return CFPP_OK;
-  const size_t smem = (size_t)Cin * H * Wd * sizeof(float);
-  CFPP_REQUIRE(want_smem(conv2d_fwd_kernel, smem), "conv2d_fwd: sample of %zu bytes exceeds shared memory", smem);
-  conv2d_fwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(in, in_bstride, W, bias, out, Cin, Cout, H, Wd, KH, KW, relu);
+  const size_t smem = (size_t)Cin * odd_stride((H + 2 * (KH / 2)) * (Wd + 2 * (KW / 2))) * sizeof(float);
+  CFPP_CONV_DISPATCH(KH, KW, {
+    CFPP_REQUIRE(want_smem(conv2d_fwd_kernel<kKH, kKW>, smem), "conv2d_fwd: sample of %zu bytes exceeds shared memory", smem);
+    conv2d_fwd_kernel<kKH, kKW><<<B, 256, smem, (cudaStream_t)stream>>>(in, in_bstride, W, bias, out, Cin, Cout, H, Wd, relu);
+  });
   return check_launch("conv2d_fwd");
 }
 
 extern "C" int cfpp_conv2d_bwd_data(const float* dout, const float* W, const float* act, int64_t act_bstride, float* din, int64_t din_bstride,
                                     int accumulate, int B, int Cin, int Cout, int H, int Wd, int KH, int KW, void* stream) {
-  CFPP_REQUIRE((KH == 1 || KH == 3) && (KW == 1 || KW == 3) && (KH == 1 || H >= 2) && (KW == 1 || Wd >= 2), "conv2d: kernel %dx%d on %dx%d", KH, KW, H, Wd);
+  CFPP_REQUIRE(conv_shape_ok(H, Wd, KH, KW), "conv2d: kernel %dx%d on %dx%d", KH, KW, H, Wd);
   if (B <= 0) return CFPP_OK;
-  const size_t smem = (size_t)Cout * H * Wd * sizeof(float);
-  CFPP_REQUIRE(want_smem(conv2d_bwd_data_kernel, smem), "conv2d_bwd_data: sample of %zu bytes exceeds shared memory", smem);
-  conv2d_bwd_data_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(dout, W, act, act_bstride, din, din_bstride, accumulate, Cin, Cout, H, Wd, KH, KW);
+  const size_t smem = ((size_t)Cout * odd_stride((H + 2 * (KH - 1)) * (Wd + 2 * (KW - 1))) +
+                       (KH * KW == 1 ? 0 : (size_t)Cin * odd_stride((H + 2 * (KH / 2)) * (Wd + 2 * (KW / 2))))) * sizeof(float);
+  CFPP_CONV_DISPATCH(KH, KW, {
+    CFPP_REQUIRE(want_smem(conv2d_bwd_data_kernel<kKH, kKW>, smem), "conv2d_bwd_data: sample of %zu bytes exceeds shared memory", smem);
+    conv2d_bwd_data_kernel<kKH, kKW><<<B, 256, smem, (cudaStream_t)stream>>>(dout, W, act, act_bstride, din, din_bstride, accumulate, Cin, Cout, H, Wd);
+  });
   return check_launch("conv2d_bwd_data");
 }
 
 extern "C" int cfpp_conv2d_bwd_weight(const float* in, int64_t in_bstride, const float* dout, float* dW, float* db,
                                       int B, int Cin, int Cout, int H, int Wd, int KH, int KW, void* stream) {
-  CFPP_REQUIRE((KH == 1 || KH == 3) && (KW == 1 || KW == 3) && (KH == 1 || H >= 2) && (KW == 1 || Wd >= 2), "conv2d: kernel %dx%d on %dx%d", KH, KW, H, Wd);
+  CFPP_REQUIRE(conv_shape_ok(H, Wd, KH, KW), "conv2d: kernel %dx%d on %dx%d", KH, KW, H, Wd);
+  CFPP_REQUIRE(Cin >= 1 && Cin <= 256, "conv2d_bwd_weight: Cin=%d outside [1,256]", Cin);
   const int KK = KH * KW, HW = H * Wd;
   cudaMemsetAsync(dW, 0, (size_t)Cout * Cin * KK * sizeof(float), (cudaStream_t)stream);
   if (db) cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), (cudaStream_t)stream);
   if (B <= 0) return CFPP_OK;
-  int NCO = (256 * PPT) / Cin; if (NCO < 1) NCO = 1; if (NCO > Cout) NCO = Cout;
-  CFPP_REQUIRE(NCO * Cin <= 256 * PPT, "conv2d_bwd_weight: Cin=%d too wide", Cin);
+  int NCO = (256 / Cin) * PPT; if (NCO > Cout) NCO = Cout;
   const int coblocks = (Cout + NCO - 1) / NCO;
   int chunks = (num_sms() * 4 + coblocks - 1) / coblocks; if (chunks > B) chunks = B; if (chunks < 1) chunks = 1;
   const int per_chunk = (B + chunks - 1) / chunks;
   chunks = (B + per_chunk - 1) / per_chunk;
-  const size_t smem = ((size_t)(Cin + NCO) * HW) * sizeof(float) + (size_t)HW * KK * sizeof(int);
+  const size_t smem = ((size_t)Cin * odd_stride((H + 2 * (KH / 2)) * (Wd + 2 * (KW / 2))) + (size_t)NCO * odd_stride(HW)) * sizeof(float);
   const dim3 grid(chunks, coblocks);
-#define CFPP_BWDW(KKV)                                                                                                          \
-  do {                                                                                                                          \
-    CFPP_REQUIRE(want_smem(conv2d_bwd_weight_kernel<KKV>, smem), "conv2d_bwd_weight: tile of %zu bytes exceeds shared memory", smem); \
-    conv2d_bwd_weight_kernel<KKV><<<grid, 256, smem, (cudaStream_t)stream>>>(in, in_bstride, dout, dW, db, B, Cin, Cout, H, Wd, KH, KW, NCO, per_chunk); \
-  } while (0)
-  if (KK == 9) CFPP_BWDW(9); else if (KK == 3) CFPP_BWDW(3); else CFPP_BWDW(1);
-#undef CFPP_BWDW
+  CFPP_CONV_DISPATCH(KH, KW, {
+    CFPP_REQUIRE(want_smem(conv2d_bwd_weight_kernel<kKH, kKW>, smem), "conv2d_bwd_weight: tile of %zu bytes exceeds shared memory", smem);
+    conv2d_bwd_weight_kernel<kKH, kKW><<<grid, 256, smem, (cudaStream_t)stream>>>(in, in_bstride, dout, dW, db, B, Cin, Cout, H, Wd, NCO, per_chunk);
+  });
   return check_launch("conv2d_bwd_weight");
 }
 

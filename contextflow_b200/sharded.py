@@ -53,3 +53,38 @@ class ShardedLogProb:
     def log_prob_local(self, x_local, ctx_local, total: int):
         """Each rank already holds only its slice (sharded loader)."""
         return self.gather(self.local_fn(x_local, ctx_local), total)
+
+
+class GradAllReduce:
+    """Training-mode exchange: after `loss.backward()` on each rank's slice, one all-reduce(sum) of the trainable
+    parameters' fp32 gradients, flattened into a single bucket (0.4-1.2 M floats for the BASELINE configs: one NCCL launch, sized for
+    launch latency rather than link count on NVSwitch).  The reference's loss is a batch MEAN (experiment_ad.py:207), so a rank that
+    averaged over b_r of the B global rows contributes with weight b_r / B."""
+
+    def __init__(self, params, group: Optional[dist.ProcessGroup] = None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._flat = None
+
+    def __call__(self, local_rows: int, total_rows: int):
+        if self.world == 1:
+            return
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        n = sum(g.numel() for g in grads)
+        if self._flat is None or self._flat.numel() != n or self._flat.device != grads[0].device:
+            self._flat = torch.empty(n, device=grads[0].device, dtype=torch.float32)
+        off = 0
+        scale = float(local_rows) / float(total_rows)
+        for g in grads:
+            self._flat[off: off + g.numel()].copy_(g.reshape(-1)).mul_(scale)
+            off += g.numel()
+        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
+        off = 0
+        for p, g in zip(self.params, grads):
+            new = self._flat[off: off + g.numel()].view_as(g)
+            if p.grad is None:
+                p.grad = new.clone()
+            else:
+                p.grad.copy_(new)
+            off += g.numel()

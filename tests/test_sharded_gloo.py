@@ -54,3 +54,52 @@ def test_shard_bounds_cover_batch():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def _grad_worker(rank, world, port, B, ret):
+    """Training exchange: each rank back-propagates the mean loss of ITS slice (autograd over the oracle stands in for the per-rank
+    CUDA backward), GradAllReduce combines; result must equal the single-process gradient of the global-batch mean loss."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from contextflow_b200 import synth
+    from contextflow_b200.sharded import GradAllReduce, shard_bounds
+    from oracle import flow_oracle as O
+    from tests.golden.cases import CASES
+    from tests.helpers import golden_state, load_golden
+    case = dict(CASES['msl_conv_gen'], B=B)
+    stack, state = golden_state(load_golden('msl_conv_gen'), case)
+    names = [k for k, v in state.items() if v.is_floating_point() and not k.endswith('initialized')]
+    params = [torch.nn.Parameter(state[k].clone()) for k in names]
+    x, ctx = synth.make_inputs(case['conf'], B, 'gshard')
+    eps = synth.normal('gshard:eps', (B, 1, 8, 1))
+
+    class RowNoise:
+        def __init__(self, lo, hi): self.lo, self.hi = lo, hi
+        def randn(self, shape): return eps[self.lo:self.hi]
+        def rand(self, shape): raise AssertionError
+
+    def loss_grads(lo, hi):
+        st = dict(state)
+        for k, p in zip(names, params):
+            p.grad = None; st[k] = p
+        logp = O.log_prob(stack, st, x[lo:hi], ctx[lo:hi], RowNoise(lo, hi))
+        cost, _, _ = O.training_loss(logp, None, case['conf']['data_size'], 1e2, criterion=False)
+        cost.backward()
+    lo, hi = shard_bounds(B, world, rank)
+    loss_grads(lo, hi)
+    GradAllReduce(params)(hi - lo, B)
+    got = [p.grad.clone() for p in params]
+    loss_grads(0, B)
+    ok = all((not g.any()) if p.grad is None else torch.allclose(g, p.grad, rtol=1e-4, atol=1e-5 * float(p.grad.abs().max()) + 1e-9)
+             for g, p in zip(got, params))
+    ret[rank] = bool(ok) and sum(p.grad is not None for p in params) >= 20
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('B', [8, 7])
+def test_world2_gloo_gradient_allreduce(B):
+    port = 31500 + (os.getpid() % 2000) + B
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_grad_worker, args=(2, port, B, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
