@@ -81,6 +81,14 @@ __global__ void slice_kernel(const float* __restrict__ x, float* __restrict__ y,
   }
 }
 
+__global__ void place_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t total, int C, int HW, int c0, int Cn) {
+  const int64_t per = (int64_t)Cn * HW;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = idx / per, r = idx % per;
+    dst[(b * C + c0) * HW + r] = src[idx];
+  }
+}
+
 __global__ void add_kernel(const float* __restrict__ x, const float* __restrict__ u, float* __restrict__ y, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = x[i] + u[i];
 }
@@ -188,6 +196,13 @@ extern "C" int cfpp_slice_channels(const float* x, float* y, int B, int C, int H
   if (!total) return CFPP_OK;
   slice_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, total, C, HW, c0, Cn);
   return check_launch("slice_channels");
+}
+extern "C" int cfpp_place_channels(const float* src, float* dst, int B, int C, int HW, int c0, int Cn, void* stream) {
+  CFPP_REQUIRE(c0 >= 0 && Cn > 0 && c0 + Cn <= C, "place: bad channel range");
+  int64_t total = (int64_t)B * Cn * HW;
+  if (!total) return CFPP_OK;
+  place_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, total, C, HW, c0, Cn);
+  return check_launch("place_channels");
 }
 extern "C" int cfpp_add_fwd(const float* x, const float* u, float* y, int64_t n, void* stream) {
   if (n <= 0) return CFPP_OK;

@@ -1,6 +1,6 @@
 """SplitPrior: factor out the second half of the channels under a (context-conditioned) mixture prior
 (reference layers/splitprior.py:7-15)."""
-from .. import ops
+from .. import ops, training
 from .flowlayer import FlowLayer
 
 
@@ -10,6 +10,9 @@ class SplitPrior(FlowLayer):
         self.dist = dist
 
     def forward(self, x, context=None):
+        d = self.dist
+        if not getattr(d, 'context_net', None) and hasattr(d, 'mG') and training.wants_grad(x, d.mG, d.sG, d.wG):
+            return training.SplitPriorFn.apply(x, d.mG, d.sG, d.wG, d)
         half = x.shape[1] // 2
         ldj = self.dist.log_prob(x[:, half:], context)         # read in place through the batch stride, (B, M)
         return ops.slice_channels(x, 0, half), ldj

@@ -748,15 +748,31 @@ def gmm_train_fwd(x, mG, inv_var, cst):
     return logp, resp
 
 
-def gmm_train_bwd(x, mG, sG, wG, inv_var, resp, g, need_dx=True):
+def place_channels(src, dst, c0):
+    """dst[:, c0:c0+Cn] = src (the adjoint of slice_channels)."""
+    _need_cuda(src, dst); src = _f32(src)
+    B, Cn, H, W = src.shape
+    assert dst.is_contiguous() and dst.dtype == torch.float32
+    _call('place_channels', (_p(src), _p(dst), B, dst.shape[1], H * W, int(c0), Cn, _stream()))
+    return dst
+
+
+def gmm_train_bwd(x, mG, sG, wG, inv_var, resp, g, need_dx=True, dx_out=None):
+    """dx_out: optional (B, D, H, W) channel-slice view of a wider contiguous tensor that receives dx in place."""
     _need_cuda(x, mG, g); g = _f32(g)
     xv, bstride = _half_view(x)
     B = x.shape[0]
     M, K, n = inv_var.shape
-    dx = torch.empty((B,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32) if need_dx else None
+    if dx_out is not None:
+        dv, dstride = _half_view(dx_out)
+        assert dv.data_ptr() == dx_out.data_ptr(), 'gmm_train_bwd: dx_out must be a channel slice of a contiguous tensor'
+        dx = dx_out
+    else:
+        dstride = n
+        dx = torch.empty((B,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32) if need_dx else None
     dmG = torch.empty_like(mG, memory_format=torch.contiguous_format); dsG = torch.empty_like(dmG); dwG = torch.empty((M, K), device=x.device, dtype=torch.float32)
     ws = torch.empty(int(lib().cfpp_gmm_train_bwd_workspace_floats(B, M, K, n)), device=x.device, dtype=torch.float32)
     _set_work(flops=8.0 * B * M * K * n)
-    _call('gmm_train_bwd', (_p(xv), bstride, _p(_f32(mG)), _p(_f32(sG)), _p(_f32(wG)), _p(inv_var), _p(resp), _p(g), _p(dx), n,
+    _call('gmm_train_bwd', (_p(xv), bstride, _p(_f32(mG)), _p(_f32(sG)), _p(_f32(wG)), _p(inv_var), _p(resp), _p(g), _p(dx), dstride,
                             _p(dmG), _p(dsG), _p(dwG), _p(ws), B, M, K, n, _stream()))
     return dx, dmG, dsG, dwG

@@ -136,6 +136,31 @@ class GmmFn(Function):
         return dx, dmG, dsG, dwG, None
 
 
+class SplitPriorFn(Function):
+    """SplitPrior.forward (splitprior.py:12-15) with a context-free mixture: x -> (x[:, :C/2], log_prob(x[:, C/2:]))."""
+
+    @staticmethod
+    def forward(ctx, x, mG, sG, wG, layer):
+        half = x.shape[1] // 2
+        inv_var, cst = layer._tables.get('train', [sG, wG], lambda: ops.gmm_train_prep(sG.detach(), wG.detach()))
+        logp, resp = ops.gmm_train_fwd(x[:, half:], mG.detach(), inv_var, cst)
+        ctx.save_for_backward(x, mG, sG, wG, inv_var, resp)
+        return ops.slice_channels(x, 0, half), logp
+
+    @staticmethod
+    def backward(ctx, dx0, g):
+        x, mG, sG, wG, inv_var, resp = ctx.saved_tensors
+        half = x.shape[1] // 2
+        g = torch.zeros((x.shape[0], mG.shape[0]), device=x.device) if g is None else g.contiguous()
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty_like(x) if need_dx else None
+        if need_dx:
+            ops.place_channels(_zeros_like_if_none(dx0, (x.shape[0], half) + tuple(x.shape[2:]), x.device).contiguous(), dx, 0)
+        _, dmG, dsG, dwG = ops.gmm_train_bwd(x[:, half:], mG.detach(), sG.detach(), wG.detach(), inv_var, resp, g, need_dx=need_dx,
+                                             dx_out=dx[:, half:] if need_dx else None)
+        return dx, dmG, dsG, dwG, None
+
+
 class LdjSumFn(Function):
     """logprob + ((0 + ldj_0) + ldj_1) + ...  (flowsequential.py:20-27); a (B,) / (B,1) term receives the row sum of the gradient."""
 

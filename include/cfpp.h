@@ -40,6 +40,9 @@ int cfpp_permute_fwd(const float* x, float* y, int B, int C, int H, int W, void*
 /* channel slice copy: y[b, 0:Cn, :] = x[b, c0:c0+Cn, :]  (SplitPrior's x[0], layers/splitprior.py:13-15). */
 int cfpp_slice_channels(const float* x, float* y, int B, int C, int HW, int c0, int Cn, void* stream);
 
+/* the adjoint of cfpp_slice_channels: dst[b, c0:c0+Cn, :] = src[b, 0:Cn, :] (SplitPrior backward); other channels untouched. */
+int cfpp_place_channels(const float* src, float* dst, int B, int C, int HW, int c0, int Cn, void* stream);
+
 /* ---- image prologue ----------------------------------------------------------------------------------- */
 /* Dequantization.forward, layers/dequantize.py:14-17: y = x + u. */
 int cfpp_add_fwd(const float* x, const float* u, float* y, int64_t n, void* stream);

@@ -34,6 +34,8 @@ CASES = {
     # MNIST at the literal 28x28 shape (BASELINE configs[0])
     'mnist28': dict(conf=variant('cfg1', data_size=(1, 28, 28)), B=2),
     # generalist conv coupling on MSL-shaped windows ((3,1) kernels, 56 channels after Augment, M = 2): training-direction case
+    # the CIFAR generalist (stage one of the paper's workflow): conv stack WITH split priors, no context
+    'cifar_gen': dict(conf=variant('cfg2', generalist=True, contextflow=False, num_blocks=2, block_size=1), B=3),
     'msl_conv_gen': dict(conf=variant('cfg4', dataset='msl', coupling='conv', data_size=(55, 8, 1), contexts=[27], mixtures=2,
                                       num_blocks=1, block_size=2), B=6),
 }
@@ -57,4 +59,5 @@ TRAINING_CASES = {
     'cfg1': dict(alpha=1e-2, criterion=True, weight=[1.0, 0.5, 2.0, 1.0, 1.0, 1.5, 1.0, 0.7, 1.0, 1.2]),
     'mnist28': dict(alpha=1e-2, criterion=True, weight=None),
     'msl_conv_gen': dict(alpha=1e2, criterion=False, weight=None),
+    'cifar_gen': dict(alpha=1e-3, criterion=True, weight=None),           # experiment_cl.py:56 alpha with a criterion
 }

@@ -66,6 +66,28 @@ def run(M_, name, spec):
         if p.requires_grad:
             pd = p.detach().double()
             rec[f'psum:{k}'] = np.array([pd.sum().item(), pd.abs().sum().item()])
+    # the same reference model and loss in float64: the yardstick for how far float32 summation order moves each gradient
+    torch.set_default_dtype(torch.float64)
+    try:
+        torch.manual_seed(0)
+        net64 = M_.create_model(conf['cfg'], data_size=conf['data_size'], mixtures=conf['mixtures'], contexts=conf['contexts'])
+        sd = net64.state_dict(); synth.fill_state(sd, case.get('wseed', 'w0')); net64.load_state_dict(sd)
+        net64 = net64.double().train()
+
+        class Tape64:
+            def __init__(self, t): self.t = t
+            def rand(self, shape, dtype=None, **kw): return self.t.rand(shape).double()
+            def randn(self, shape, dtype=None, **kw): return self.t.randn(shape).double()
+        with patched_rng(Tape64(synth.NoiseTape(case.get('nseed', 'noise0')))):
+            cost64, _, _ = training_loss(net64, x.double(), ctx, gt, conf['data_size'], spec)
+        cost64.backward()
+        for k, p in net64.named_parameters():
+            if p.requires_grad:
+                g = p.grad.detach()
+                rec[f'g64:{k}'] = g.numpy() if g.numel() <= FULL else g.flatten()[:512].numpy()
+        rec['loss64'] = np.array(cost64.item())
+    finally:
+        torch.set_default_dtype(torch.float32)
     rec['names'] = np.array(json.dumps(names))
     np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', f'train_{name}.npz'), **rec)
     print(f'train_{name}: loss={cost.item():.6f} (sup {sup.item():.6f}, uns {uns.item():.6f}) params={len(names)}')

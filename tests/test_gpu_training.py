@@ -50,7 +50,7 @@ def test_gradients_match_reference_golden(name):
     cost.backward()
     named = dict(model.named_parameters())
     assert sorted(gold['names']) == sorted(k for k, p in named.items() if p.requires_grad)
-    check_grads(name, {k: named[k].grad for k in gold['names']}, gold, rtol=1e-3)
+    check_grads(name, {k: named[k].grad for k in gold['names']}, gold, rtol=2e-4)
     opt.step()          # the torch optimizer the reference builds (model.py:289) consumes the CUDA-produced .grad tensors
     for k in gold['names']:
         # Adam's first step moves every entry by ~lr * g / (|g| + eps): entries with |g| ~ eps make the exact landing point
@@ -60,7 +60,7 @@ def test_gradients_match_reference_golden(name):
         assert abs(pd.abs().sum().item() - ref[1]) <= 2.5e-3 * pd.numel() + 1e-5 * ref[1], f'{name} AdamW step {k}'
 
 
-@pytest.mark.parametrize('name,B', [('cfg1', 37), ('msl_conv_gen', 50)])
+@pytest.mark.parametrize('name,B', [('cfg1', 37), ('msl_conv_gen', 50), ('cifar_gen', 21)])
 def test_gradients_match_oracle_autograd_fresh_inputs(name, B):
     case = dict(CASES[name], B=B, iseed='in5', nseed='noise5')
     spec = TRAINING_CASES[name]

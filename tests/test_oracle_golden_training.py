@@ -22,23 +22,24 @@ def labels(name, B, M):
 
 
 def check_grads(name, grads, gt_gold, rtol=2e-4):
-    """grads: {param name: tensor}.  Tolerance: rtol relative to the largest entry of that gradient (sums over the batch reorder)."""
+    """grads: {param name: tensor}.  Truth = the reference's own float64 gradients (g64); a gradient passes when it is within
+    rtol of the gradient's largest entry, or as close to the truth as the reference's float32 run (g) gets, times 3: every parameter
+    gradient is a signed sum over batch and pixels (Conv1x1's dNN and ActNorm's dlogs are differences of large cancelling sums), so
+    float32 summation order moves the reference itself by up to ~1e-3 of the largest entry."""
     for k in gt_gold['names']:
         g = grads[k].detach().cpu().double()
         ref_sum = gt_gold[f'gsum:{k}']
         scale = float(ref_sum[2]) + 1e-12
-        ref = torch.from_numpy(gt_gold[f'g:{k}']).double()
-        got = g if ref.shape == g.shape else g.flatten()[: ref.numel()]
-        err = (got - ref).abs().max().item()
-        # Every parameter gradient is a signed sum over the batch and the pixels; Conv1x1's dNN is in addition a difference of two large
-        # sums (data term and HW * NN^-T) that cancel at a likelihood optimum.  float32 reorderings of those sums move the reference's
-        # own result by up to ~1e-3 of the gradient's largest entry (measured against float64 autograd in
-        # tests/test_gpu_training.py::test_gradients_match_oracle_autograd_fresh_inputs, which holds the CUDA path to the principled
-        # bound: 2e-4 relative or 3x the reference's own float32 error).  Here: rtol for the same-order CPU oracle, 5x for CUDA sums.
-        tol = (10 * rtol if k.endswith('.NN') else rtol) * scale + 1e-7
-        assert err <= tol, f'{name} grad {k}: max abs err {err:.3e} vs scale {scale:.3e}'
-        assert abs(g.sum().item() - ref_sum[0]) <= tol * g.numel() ** 0.5 + rtol * ref_sum[1] + 1e-6, f'{name} grad {k}: sum'
-        assert abs(g.abs().sum().item() - ref_sum[1]) <= tol * g.numel() ** 0.5 + rtol * ref_sum[1] + 1e-6, f'{name} grad {k}: abs sum'
+        ref32 = torch.from_numpy(gt_gold[f'g:{k}']).double()
+        truth = torch.from_numpy(gt_gold[f'g64:{k}']).double()
+        got = g if truth.shape == g.shape else g.flatten()[: truth.numel()]
+        err = (got - truth).abs().max().item()
+        ref_err = (ref32 - truth).abs().max().item()
+        tol = rtol * scale + 3.0 * ref_err + 1e-7
+        assert err <= tol, f'{name} grad {k}: max abs err {err:.3e} (float32 reference err {ref_err:.3e}) vs scale {scale:.3e}'
+        if truth.shape != g.shape:              # large tensors store their first 512 values: the rest is covered by the checksums
+            assert abs(g.sum().item() - ref_sum[0]) <= tol * g.numel() ** 0.5 + rtol * ref_sum[1] + 1e-6, f'{name} grad {k}: sum'
+            assert abs(g.abs().sum().item() - ref_sum[1]) <= tol * g.numel() ** 0.5 + rtol * ref_sum[1] + 1e-6, f'{name} grad {k}: abs sum'
 
 
 @pytest.mark.parametrize('name', sorted(TRAINING_CASES))

@@ -11,11 +11,62 @@ from contextflow_b200 import _cabi, builder, ops, synth
 from contextflow_b200.sharded import GradAllReduce
 
 
+def reference_arm(a):
+    """The training step as the reference computes it: its eager torch op sequence (oracle/, pinned to the reference's gradients by
+    tests/test_oracle_golden_training.py), torch autograd, torch AdamW -- on the GPU (torch-on-CUDA baseline) or the host cores."""
+    import contextlib, time
+    from oracle import flow_oracle as O
+    conf = synth.CONFIGS[a.workload]
+    stack = O.build_stack(conf['cfg'], conf['data_size'], conf['mixtures'], conf['contexts'])
+    model = builder.build_named(conf)
+    state = model.state_dict(); synth.fill_state(state, 'bench')
+    dev = a.ref_device
+    O.DEVICE = dev
+    state = {k: v.to(dev) for k, v in state.items()}
+    names = [k for k, p in model.named_parameters() if p.requires_grad]
+    params = []
+    for k in names:
+        state[k] = torch.nn.Parameter(state[k]); params.append(state[k])
+    opt = torch.optim.AdamW(params, lr=1e-4)
+    B, M = a.batch, conf['mixtures']
+    C, H, W = conf['data_size']
+    torch.manual_seed(99)
+    x = (torch.randint(0, 256, (B, C, H, W)).float() if conf['image'] else torch.rand(B, C, H, W)).to(dev)
+    ctx = torch.stack([torch.randint(0, k, (B,)) for k in conf['contexts']], 1).to(dev); gt = torch.randint(0, M, (B,)).to(dev)
+
+    class TorchNoise:
+        def rand(self, shape): return torch.rand(shape, device=dev)
+        def randn(self, shape): return torch.randn(shape, device=dev)
+    sync = torch.cuda.synchronize if dev == 'cuda' else (lambda: None)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with (torch.device('cuda') if dev == 'cuda' else contextlib.nullcontext()):
+            logp = O.log_prob(stack, state, x, ctx, TorchNoise())
+            cost, _, _ = O.training_loss(logp, gt, conf['data_size'], 1e-2, True, None)
+        cost.backward(); opt.step()
+        return cost
+    for _ in range(max(1, min(a.warmup, 2))):
+        step()
+    sync(); t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cost = step()
+    sync(); dt = time.perf_counter() - t0
+    print(json.dumps({'metric': 'flow_training_step_samples_per_sec', 'impl': 'reference', 'value': B * a.steps / dt, 'unit': 'samples/s', 'n_gpus': 1,
+                      'workload': a.workload, 'batch_per_gpu': B, 'ms_per_step': 1e3 * dt / a.steps, 'loss': float(cost.item()),
+                      'how': f'oracle op sequence + torch autograd + AdamW, eager, device={dev}' + (f' ({torch.cuda.get_device_name(0)})' if dev == 'cuda' else f' ({torch.get_num_threads()} threads)')}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--workload', default='cfg1'); ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--steps', type=int, default=10); ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'],
+                    help="reference: the reference's torch op sequence (oracle restatement) + torch autograd + AdamW, eager, on --ref-device")
+    ap.add_argument('--ref-device', default='cuda', choices=['cpu', 'cuda'])
     a = ap.parse_args()
+    if a.impl == 'reference':
+        return reference_arm(a)
     rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1)); local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local); dev = torch.device('cuda', local)
     if world > 1:
