@@ -60,6 +60,8 @@ def main():
             def rev():
                 i[0] += 1
                 return model.reverse(zs[i[0] % 3], ctx)
+            if os.environ.get('CFPP_PROFILE_RANGE') == '1':
+                torch.cuda.profiler.start(); rev(); torch.cuda.synchronize(); torch.cuda.profiler.stop()
             ms_rev = timed(rev, a.steps)
             ms_fwd = timed(lambda: model.log_prob(x, ctx), a.steps)
             line = {'metric': 'flow_reverse_samples_per_sec', 'value': B / (ms_rev / 1e3), 'unit': 'samples/s', 'workload': name, 'batch': B,

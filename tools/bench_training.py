@@ -104,10 +104,15 @@ def main():
         dist.barrier()
     l0 = _cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof = os.environ.get('CFPP_PROFILE_RANGE') == '1'           # ncu --profile-from-start off: capture the timed steps only
+    if prof:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(a.steps):
         cost = step(i)
     e1.record(); torch.cuda.synchronize()
+    if prof:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1) / a.steps
     launches = (_cabi.launch_count() - l0) / a.steps
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
