@@ -33,10 +33,11 @@ def mark_expensive(func):
 
 
 def inference_only(t: torch.Tensor):
-    """The CUDA path is the log-density *forward*; autograd through it is the next scope row."""
+    """Layers without backward kernels (context-conditioned layers, encoders, the ViT conditioner) refuse autograd loudly; the
+    context-free conv stack trains through contextflow_b200/training.py."""
     if torch.is_grad_enabled() and t.requires_grad:
-        raise NotImplementedError('contextflow_b200 implements the forward log-density path; wrap the call in torch.no_grad() '
-                                  '(backward kernels are out of scope for this round, see DESIGN.md)')
+        raise NotImplementedError('this layer has no backward kernel yet (specialist / ViT layers): wrap the call in torch.no_grad(); '
+                                  'context-free conv stacks train through contextflow_b200.training (DESIGN.md §8 f-1)')
 
 
 class PackCache:
