@@ -47,6 +47,7 @@ _SIGNATURES = {
     'cfpp_permute_fwd': (i32, [vp, vp, i32, i32, i32, i32, vp]),
     'cfpp_slice_channels': (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     'cfpp_place_channels': (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
+    'cfpp_windows_fwd': (i32, [vp, i32, vp, i64, i64, vp, i32, i64, i32, i32, vp]),
     'cfpp_add_fwd': (i32, [vp, vp, vp, i64, vp]),
     'cfpp_normalize_fwd': (i32, [vp, vp, i64, f32, f32, vp]),
     'cfpp_logit_fwd': (i32, [vp, vp, vp, i32, i32, vp]),

@@ -89,6 +89,27 @@ __global__ void place_kernel(const float* __restrict__ src, float* __restrict__ 
   }
 }
 
+// Sliding windows with replication padding (datasets/mtad_data_preprocess.py:58-74) straight into the model layout of
+// datasets/mtad_dataloader.py:106-110: x[b, d, t, 0] = float(ts[max(0, end[b] - L + 1 + t), d]).  One CTA per window: the L rows are
+// read coalesced along d, transposed through shared memory, written coalesced along t.
+template <typename T>
+__global__ void __launch_bounds__(256) windows_kernel(const T* __restrict__ ts, const int64_t* __restrict__ end, int64_t end0, int64_t stride,
+                                                      float* __restrict__ x, int64_t n_rows, int D, int L) {
+  extern __shared__ float tile[];                     // L * (D + 1)
+  const int64_t b = blockIdx.x;
+  const int64_t e = end ? end[b] : end0 + b * stride;
+  for (int i = threadIdx.x; i < L * D; i += blockDim.x) {
+    const int t = i / D, d = i - t * D;
+    int64_t r = e - L + 1 + t; r = r < 0 ? 0 : (r >= n_rows ? n_rows - 1 : r);
+    tile[t * (D + 1) + d] = (float)ts[r * D + d];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L * D; i += blockDim.x) {
+    const int d = i / L, t = i - d * L;
+    x[b * (int64_t)L * D + i] = tile[t * (D + 1) + d];
+  }
+}
+
 __global__ void add_kernel(const float* __restrict__ x, const float* __restrict__ u, float* __restrict__ y, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = x[i] + u[i];
 }
@@ -203,6 +224,15 @@ extern "C" int cfpp_place_channels(const float* src, float* dst, int B, int C, i
   if (!total) return CFPP_OK;
   place_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, total, C, HW, c0, Cn);
   return check_launch("place_channels");
+}
+extern "C" int cfpp_windows_fwd(const void* ts, int ts_is_f64, const int64_t* end, int64_t end0, int64_t stride, float* x,
+                                int B, int64_t n_rows, int D, int L, void* stream) {
+  CFPP_REQUIRE(n_rows >= 1 && D >= 1 && L >= 1 && (size_t)L * (D + 1) * sizeof(float) <= 48 * 1024, "windows: rows=%lld D=%d L=%d", (long long)n_rows, D, L);
+  if (B <= 0) return CFPP_OK;
+  const size_t smem = (size_t)L * (D + 1) * sizeof(float);
+  if (ts_is_f64) windows_kernel<double><<<B, 256, smem, (cudaStream_t)stream>>>((const double*)ts, end, end0, stride, x, n_rows, D, L);
+  else windows_kernel<float><<<B, 256, smem, (cudaStream_t)stream>>>((const float*)ts, end, end0, stride, x, n_rows, D, L);
+  return check_launch("windows_fwd");
 }
 extern "C" int cfpp_add_fwd(const float* x, const float* u, float* y, int64_t n, void* stream) {
   if (n <= 0) return CFPP_OK;

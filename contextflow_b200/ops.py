@@ -128,6 +128,26 @@ def slice_channels(x, c0, cn):
     return y
 
 
+def windows(ts, L, end=None, end0=0, stride=1, count=None):
+    """Sliding windows of a device-resident series (n_rows, D) in the model layout (B, D, L, 1): get_windows + the dataset transpose
+    (mtad_data_preprocess.py:58-74, mtad_dataloader.py:106-110).  end: int64 (B,) window end rows, or the arithmetic run end0 + b*stride."""
+    _need_cuda(ts, end)
+    if ts.dtype not in (torch.float32, torch.float64) or ts.dim() != 2:
+        raise TypeError('series must be a (rows, D) float32 / float64 tensor')
+    ts = ts.contiguous()
+    n_rows, D = ts.shape
+    if end is not None:
+        if end.dtype != torch.int64:
+            raise TypeError('window end rows must be int64')
+        end = end.contiguous(); B = end.shape[0]
+    else:
+        B = int(count)
+    x = torch.empty((B, D, L, 1), device=ts.device, dtype=torch.float32)
+    _set_work(bytes=4.0 * x.numel() * 2)
+    _call('windows_fwd', (_p(ts), int(ts.dtype == torch.float64), _p(end), int(end0), int(stride), _p(x), B, n_rows, D, L, _stream()))
+    return x
+
+
 # ---------------------------------------------------------------------------------------------- prologue
 def add(x, u):
     _need_cuda(x, u); x = _f32(x); u = _f32(u)

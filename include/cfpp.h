@@ -43,6 +43,15 @@ int cfpp_slice_channels(const float* x, float* y, int B, int C, int HW, int c0, 
 /* the adjoint of cfpp_slice_channels: dst[b, c0:c0+Cn, :] = src[b, 0:Cn, :] (SplitPrior backward); other channels untouched. */
 int cfpp_place_channels(const float* src, float* dst, int B, int C, int HW, int c0, int Cn, void* stream);
 
+/* ---- data format in front of the path: SURVEY §8(f)-4 ----------------------------------------------------------- */
+/* Sliding windows over a raw multivariate series, generated on the device in the model's input layout: get_windows
+ * (datasets/mtad_data_preprocess.py:58-74: window ending at row e covers rows e-L+1..e, rows before 0 replicate row 0) followed by
+ * the transpose / float32 cast of sliding_window_dataset (datasets/mtad_dataloader.py:106-110):
+ *   x[b, d, t, 0] = (float) ts[max(0, e_b - L + 1 + t), d],  e_b = end[b] (int64, device) or end0 + b * stride when end == NULL.
+ * ts: (n_rows, D) row-major, float32 or float64 (ts_is_f64).  Bit exact (index work + the IEEE float64 -> float32 rounding torch applies). */
+int cfpp_windows_fwd(const void* ts, int ts_is_f64, const int64_t* end, int64_t end0, int64_t stride, float* x,
+                     int B, int64_t n_rows, int D, int L, void* stream);
+
 /* ---- image prologue ----------------------------------------------------------------------------------- */
 /* Dequantization.forward, layers/dequantize.py:14-17: y = x + u. */
 int cfpp_add_fwd(const float* x, const float* u, float* y, int64_t n, void* stream);

@@ -626,3 +626,15 @@ def training_loss(logp, gt, data_size, alpha, criterion=True, class_w=None):
         uns = -alpha * F.logsigmoid(s).mean()
         sup = torch.zeros_like(uns)
     return sup + uns, sup, uns
+
+
+# =================================================================================================
+# data format in front of the path: get_windows (datasets/mtad_data_preprocess.py:58-74) + the transpose / float32
+# cast of sliding_window_dataset (datasets/mtad_dataloader.py:106-110)
+# =================================================================================================
+def sliding_windows(ts: np.ndarray, window_size: int, stride: int = 1) -> torch.Tensor:
+    rows = ts.shape[0]
+    ends = np.arange(0, rows, stride)
+    idx = np.maximum(ends[:, None] - window_size + 1 + np.arange(window_size)[None, :], 0)     # replication padding with row 0
+    w = np.asarray(ts, dtype=float)[idx]                                                        # (N, L, D) float64
+    return torch.tensor(np.transpose(w, (0, 2, 1)), dtype=torch.float).unsqueeze(-1)            # N x D x L x 1
