@@ -13,6 +13,8 @@ __all__ = ['ActNorm', 'ActNormFC']
 
 
 class ActNorm(FlowActivationLayer):
+    stats_fn = None          # set by sharded.enable_sharded_actnorm_init: global-batch statistics over all ranks
+
     def __init__(self, data_size, context_net=None, contextflow=False):
         super().__init__()
         D, H, W = data_size if len(data_size) == 3 else (data_size[0], 1, 1)
@@ -45,7 +47,7 @@ class ActNorm(FlowActivationLayer):
     def initialize(self, x):
         """actnorm.py:28-35: t <- mean, logs <- log(unbiased std + 1e-8) over (B,H,W)."""
         with torch.no_grad():
-            mean, logstd = ops.actnorm_stats(x)
+            mean, logstd = (type(self).stats_fn or ops.actnorm_stats)(x)     # sharded first batch: contextflow_b200.sharded
             self.NN_t.data.copy_(mean)
             self.NN_logs.data.copy_(logstd)
             self.initialized.fill_(1)

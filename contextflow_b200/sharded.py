@@ -88,3 +88,39 @@ class GradAllReduce:
             else:
                 p.grad.copy_(new)
             off += g.numel()
+
+
+def sharded_actnorm_stats(x_local, group: Optional[dist.ProcessGroup] = None, local_stats: Optional[Callable] = None):
+    """ActNorm's data-dependent initialisation (actnorm.py:28-35: t <- mean, logs <- log(unbiased std + 1e-8) over (B,H,W)) when the
+    first batch is sharded over ranks: each rank computes its slice's (mean, logstd) with the same kernel as the
+    single-process path, one all-gather of (mean, M2, count) per channel, merged with the pairwise-variance formula in float64 -- the
+    result is the statistic of the GLOBAL batch, so a sharded run initialises exactly like the reference's single process."""
+    if local_stats is None:
+        from . import ops
+        local_stats = ops.actnorm_stats
+    mean_r, logstd_r = local_stats(x_local)
+    n_r = x_local.numel() // x_local.shape[1]
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return mean_r, logstd_r
+    std_r = (torch.exp(logstd_r.double()) - 1e-8).clamp_min(0.0) if n_r > 1 else torch.zeros_like(mean_r, dtype=torch.float64)
+    pack = torch.stack([mean_r.double(), std_r * std_r * max(n_r - 1, 0), torch.full_like(std_r, float(n_r))], 0).contiguous()   # (3, D)
+    world = dist.get_world_size(group)
+    flat = torch.empty(world * pack.numel(), device=pack.device, dtype=pack.dtype)
+    dist.all_gather_into_tensor(flat, pack.reshape(-1), group=group)
+    allp = flat.view((world,) + tuple(pack.shape))
+    n = allp[:, 2].sum(0)
+    mean = (allp[:, 0] * allp[:, 2]).sum(0) / n
+    m2 = (allp[:, 1] + allp[:, 2] * (allp[:, 0] - mean) ** 2).sum(0)
+    std = torch.sqrt(m2 / (n - 1))
+    return mean.float(), torch.log(std.float() + 1e-8)
+
+
+def enable_sharded_actnorm_init(group: Optional[dist.ProcessGroup] = None):
+    """Route every ActNorm's first-batch initialisation through `sharded_actnorm_stats` (all ranks must run the same model in lockstep)."""
+    from .layers.actnorm import ActNorm
+    ActNorm.stats_fn = staticmethod(lambda x: sharded_actnorm_stats(x, group))
+
+
+def disable_sharded_actnorm_init():
+    from .layers.actnorm import ActNorm
+    ActNorm.stats_fn = None

@@ -103,3 +103,27 @@ def test_world2_gloo_gradient_allreduce(B):
     mgr = mp.Manager(); ret = mgr.dict()
     mp.spawn(_grad_worker, args=(2, port, B, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def _actnorm_worker(rank, world, port, B, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from contextflow_b200 import synth
+    from contextflow_b200.sharded import shard_bounds, sharded_actnorm_stats
+    from oracle import flow_oracle as O
+    x = synth.normal('anshard', (B, 6, 4, 3)) * 2.5 + synth.uniform('anshard:m', (1, 6, 1, 1)) * 4
+    lo, hi = shard_bounds(B, world, rank)
+    mean, logstd = sharded_actnorm_stats(x[lo:hi], local_stats=O.actnorm_init)
+    ref_mean, ref_logstd = O.actnorm_init(x)
+    ret[rank] = bool(torch.allclose(mean, ref_mean, rtol=1e-5, atol=1e-6) and torch.allclose(logstd, ref_logstd, rtol=1e-5, atol=1e-6))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('B', [9, 2])
+def test_world2_gloo_actnorm_init_uses_global_batch_statistics(B):
+    """the sharded first batch initialises ActNorm with the statistics of the global batch (actnorm.py:28-35)."""
+    port = 33500 + (os.getpid() % 2000) + B
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_actnorm_worker, args=(2, port, B, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
