@@ -91,6 +91,7 @@ _SIGNATURES = {
     'cfpp_embed_lookup': (i32, [vp, C.POINTER(vp), i32, i32, vp, i32, vp]),
     'cfpp_linear_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     'cfpp_cn_batch': (i32, [C.POINTER(CnJob), i32, C.POINTER(vp), C.POINTER(vp), i32, vp]),
+    'cfpp_maf_coupling_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     'cfpp_coupling_inv': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     'cfpp_actnorm_inv': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     'cfpp_mat_inverse': (i32, [vp, i32, vp, vp, vp]),

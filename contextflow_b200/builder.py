@@ -115,7 +115,7 @@ def create_model(config, data_size=(1, 1, 1), mixtures=1, contexts=[-1]):
             elif config['coupling'] == 'conv':
                 stack.append(L.Coupling(sz[0], kernel_size=krn, padding=pad, context_net=ctx_net(sz[0]), contextflow=cf))
             elif config['coupling'] == 'maf':
-                raise NotImplementedError('--coupling maf is outside the accelerated path')
+                stack.append(L.MaskedCoupling(sz[0], kernel_size=krn, padding=pad, context_net=ctx_net(sz[0]), contextflow=cf))
             if dataset == 'atm':
                 stack.append(L.PermuteAxes((0, 2, 1, 3)))
                 sz = (sz[1], sz[0], sz[2])

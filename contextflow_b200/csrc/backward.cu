@@ -91,12 +91,13 @@ __host__ __device__ inline int odd_stride(int n) { return n | 1; }   // odd row 
 
 // Stage the first C channels of sample b with a reflect halo of (PH, PW): dst[c * S + (y + PH) * Wp + (x + PW)], Wp = W + 2 PW.
 template <int PH, int PW>
-__device__ __forceinline__ void stage_reflect(float* dst, const float* __restrict__ src, int C, int H, int Wd, int S) {
+__device__ __forceinline__ void stage_reflect(float* dst, const float* __restrict__ src, int C, int H, int Wd, int S, bool relu_in = false) {
   const int Hp = H + 2 * PH, Wp = Wd + 2 * PW, HW = H * Wd;
   for (int i = threadIdx.x; i < C * Hp * Wp; i += blockDim.x) {
     const int c = i / (Hp * Wp), r = i - c * (Hp * Wp);
     const int yp = r / Wp, xp = r - yp * Wp;
-    dst[c * S + r] = src[c * HW + reflect_idx(yp - PH, H) * Wd + reflect_idx(xp - PW, Wd)];
+    const float v = src[c * HW + reflect_idx(yp - PH, H) * Wd + reflect_idx(xp - PW, Wd)];
+    dst[c * S + r] = relu_in ? fmaxf(v, 0.f) : v;
   }
 }
 
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(256) conv2d_fwd_kernel(const float* __restrict
   extern __shared__ float sm[];
   const int HW = H * Wd, Wp = Wd + 2 * PW, S = odd_stride((H + 2 * PH) * Wp);
   const int64_t b = blockIdx.x;
-  stage_reflect<PH, PW>(sm, in + b * in_bstride, Cin, H, Wd, S);
+  stage_reflect<PH, PW>(sm, in + b * in_bstride, Cin, H, Wd, S, (relu & 2) != 0);     // relu bit 1: ReLU on the INPUT (pre-activation blocks)
+  relu &= 1;                                                                           // relu bit 0: ReLU on the output
   __syncthreads();
   const int ncg = (Cout + CG - 1) / CG, nslot = (HW + PXT - 1) / PXT;
   for (int item = threadIdx.x; item < nslot * ncg; item += blockDim.x) {

@@ -1,0 +1,70 @@
+"""Masked (autoregressive) convolution blocks of `--coupling maf` (reference layers/autoregressive/masked_conv_2d.py:7-99,
+layers/autoregressive/utils.py:25-92): the same module tree and buffer names (`conv{1,2,3}.weight/bias/mask`), so reference checkpoints
+load; the arithmetic runs in libcfpp (three conv launches with ReLU on the input over mask-multiplied weights)."""
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+__all__ = ['MaskedConv2d', 'MaskedResidualBlock2d', 'mask_channels', 'mask_conv2d']
+
+
+def mask_channels(mask_type, in_channels, out_channels, data_channels=3):
+    """utils.py:25-57: the (data_channels x data_channels) lower-triangular base ('A': strict) tiled over the feature maps."""
+    base = torch.ones(data_channels, data_channels).tril(-1 if mask_type == 'A' else 0)
+    rows = torch.cat([base] * (in_channels // data_channels + 1), dim=1)
+    full = torch.cat([rows] * (out_channels // data_channels + 1), dim=0)
+    return full[:out_channels, :in_channels]
+
+
+def mask_conv2d(mask_type, in_channels, out_channels, height, width, data_channels=3):
+    """utils.py:60-92: channel mask at the central tap, nothing to the right of or below the centre."""
+    mask = torch.ones(out_channels, in_channels, height, width)
+    mask[:, :, height // 2, width // 2] = mask_channels(mask_type, in_channels, out_channels, data_channels)
+    mask[:, :, height // 2, width // 2 + 1:] = 0
+    mask[:, :, height // 2 + 1:] = 0
+    return mask
+
+
+class MaskedConv2d(nn.Conv2d):
+    def __init__(self, *args, mask_type, data_channels=3, **kwargs):
+        super().__init__(*args, **kwargs)
+        assert mask_type in {'A', 'B'}
+        o, i, h, w = self.weight.size()
+        self.register_buffer('mask', mask_conv2d(mask_type, i, o, h, w, data_channels))
+        self._masked_version = None
+
+    def masked_weight(self):
+        """masked_conv_2d.py:21-23 multiplies `weight.data` by the mask in place on every forward; once per weight version is the
+        same state (the product is idempotent)."""
+        key = (self.weight.data_ptr(), self.weight._version)
+        if self._masked_version != key:
+            with torch.no_grad():
+                self.weight.data.mul_(self.mask)
+            self._masked_version = (self.weight.data_ptr(), self.weight._version)
+        return self.weight.detach()
+
+    def forward(self, x):
+        return ops.conv2d_fwd(x, x.shape[1], self.masked_weight(), self.bias.detach(), relu=False)
+
+
+class MaskedResidualBlock2d(nn.Module):
+    """masked_conv_2d.py:81-98: conv1(relu(x)) -> conv2(relu(.)) -> conv3(relu(.)) + cat(x, x).  `forward(x, identity=False)` returns the
+    conv output without the identity: the fused coupling kernel adds x itself."""
+
+    def __init__(self, I, O, kernel_size=(1, 1), padding=(0, 0), D=0, mask_type='B'):
+        super().__init__()
+        self.conv1 = MaskedConv2d(1 * I, 2 * I, 1, mask_type=mask_type, data_channels=D)
+        self.conv2 = MaskedConv2d(2 * I, 2 * I, kernel_size, padding=padding, padding_mode='reflect', mask_type=mask_type, data_channels=D)
+        self.conv3 = MaskedConv2d(2 * I, 2 * O, 1, mask_type=mask_type, data_channels=D)
+        ks, pd = tuple(self.conv2.kernel_size), tuple(self.conv2.padding)
+        if pd != (ks[0] // 2, ks[1] // 2) or any(k not in (1, 3) for k in ks):
+            raise NotImplementedError('the conv kernels assume "same" reflect padding with 1/3-wide kernels (model.py:114)')
+
+    def forward(self, x, identity=True):
+        h = x
+        for conv in (self.conv1, self.conv2, self.conv3):
+            h = ops.conv2d_fwd(h, h.shape[1], conv.masked_weight(), conv.bias.detach(), relu=False, relu_in=True)
+        if identity:
+            raise NotImplementedError('use MaskedCoupling: the identity is added inside the fused coupling kernel')
+        return h

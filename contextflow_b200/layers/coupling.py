@@ -186,11 +186,25 @@ class TransCoupling(_CouplingBase):
 
 
 class MaskedCoupling(FlowLayer):
-    """--coupling maf: outside the accelerated path."""
+    """`--coupling maf` (reference layers/ar.py:15-69), context-free form: h = MaskedResidualBlock2d(x); t, r = halves of h;
+    z = x * exp(2 tanh(r/2)) + t over all channels; ldj = sum log_s.  With a context_net the reference adds a masked linear block
+    (ar.py:28,41): not built."""
 
-    def __init__(self, *a, **kw):
-        raise NotImplementedError('MaskedCoupling (--coupling maf) is outside the accelerated path')
+    def __init__(self, data_channels, kernel_size=(1, 1), padding=(0, 0), context_net=None, contextflow=False, mask_type='B'):
+        super().__init__()
+        if context_net:
+            raise NotImplementedError('MaskedCoupling with a context_net (MaskedResidualBlockLinear, ar.py:28) is outside the accelerated path')
+        from .autoregressive import MaskedResidualBlock2d
+        D = data_channels
+        self.context_net, self.contextflow = context_net, contextflow
+        self.NN = MaskedResidualBlock2d(D, D, kernel_size=kernel_size, padding=padding, D=D, mask_type=mask_type)
 
-    def forward(self, input, context=None): ...
-    def reverse(self, input, context=None): ...
-    def logdet(self, input, context=None): ...
+    def forward(self, x, context=None):
+        inference_only(x); inference_only(self.NN.conv1.weight)
+        return ops.maf_coupling(x, self.NN(x, identity=False))
+
+    def reverse(self, z, context=None):
+        return torch.zeros_like(z)                     # ar.py:59-66: the reference's reverse is a stub returning zeros
+
+    def logdet(self, input, context=None):
+        return self.forward(input, context)[1]

@@ -693,15 +693,27 @@ def actnorm_bwd(x, dz, dldj, t, logs, need_dx=True):
     return dx, dt, dlogs
 
 
-def conv2d_fwd(x, cin, w, b, relu):
-    """out = [relu](conv(x[:, :cin]) + b), 'same' reflect padding; x may be wider than cin channels (read through its batch stride)."""
+def maf_coupling(x, h):
+    """MaskedCoupling elementwise part (ar.py:35-57): h (B, 2C, H, W) without the identity."""
+    _need_cuda(x, h); x = _f32(x); h = _f32(h)
+    B, Cc = x.shape[0], x.shape[1]
+    HW = x[0, 0].numel() if B else 1
+    z = torch.empty_like(x); ldj = torch.empty(B, device=x.device, dtype=x.dtype)
+    _set_work(bytes=16.0 * x.numel())
+    _call('maf_coupling_fwd', (_p(x), _p(h), _p(z), _p(ldj), B, Cc, HW, _stream()))
+    return z, ldj
+
+
+def conv2d_fwd(x, cin, w, b, relu, relu_in=False):
+    """out = [relu](conv([relu_in](x[:, :cin])) + b), 'same' reflect padding; x may be wider than cin channels (read through its batch stride)."""
     _need_cuda(x, w)
     xv, bstride = _half_view(x[:, :cin])
     B, H, W = x.shape[0], x.shape[2], x.shape[3]
     cout, KH, KW = w.shape[0], w.shape[2], w.shape[3]
     out = torch.empty((B, cout, H, W), device=x.device, dtype=torch.float32)
     _set_work(flops=2.0 * B * cout * cin * KH * KW * H * W)
-    _call('conv2d_fwd', (_p(xv), bstride, _p(_f32(w)), _p(None if b is None else _f32(b)), _p(out), B, cin, cout, H, W, KH, KW, int(bool(relu)), _stream()))
+    _call('conv2d_fwd', (_p(xv), bstride, _p(_f32(w)), _p(None if b is None else _f32(b)), _p(out), B, cin, cout, H, W, KH, KW,
+                         int(bool(relu)) | (2 if relu_in else 0), _stream()))
     return out
 
 

@@ -99,7 +99,7 @@ def fill_state(state: dict, seed: str = 'w0') -> dict:
         shape = tuple(v.shape)
         if leaf == 'initialized':
             v.fill_(1)
-        elif leaf in ('qbins', 'ldj_per_dim', 'cardinalities', 'temperature', 'translation', 'scale', 'empty', 'buffer'):
+        elif leaf in ('qbins', 'ldj_per_dim', 'cardinalities', 'temperature', 'translation', 'scale', 'empty', 'buffer', 'mask'):
             continue
         elif leaf == 'NN' and v.dim() == 2:                      # invertible 1x1 / FC matrix
             d = shape[0]
@@ -125,6 +125,8 @@ def fill_state(state: dict, seed: str = 'w0') -> dict:
                 scale *= 0.5 / float(shape[0]) ** 0.25
             if key.endswith('NN.4.weight') or key.endswith('CN.4.weight'):   # conditioner output layer: keep |h| ~ 0.3
                 scale *= 0.4
+            if '.NN.conv' in key:                                            # masked residual block (--coupling maf): h rides on the identity x
+                scale *= 0.15 if key.endswith('conv3.weight') else 0.5
             v.copy_(uniform(tag, shape) * scale)
         elif leaf == 'bias':
             v.copy_(uniform(tag, shape) * (0.03 if key.endswith('transformer.norm.bias') else 0.1))

@@ -286,6 +286,11 @@ typedef struct cfpp_cn_job {
 int cfpp_cn_batch(const cfpp_cn_job* jobs, int n_jobs, const float* const* in, float* const* out, int B, void* stream);
 
 
+/* MaskedCoupling.forward (`--coupling maf`, layers/ar.py:35-57) after its masked residual block: h (B, 2C, HW) is the block's conv
+ * output WITHOUT the identity; t = h[:, :C] + x, r = h[:, C:] + x (masked_conv_2d.py:92,98); z = x * exp(2 tanh(r/2)) + t;
+ * ldj[b] = sum 2 tanh(r/2).  The block itself = three cfpp_conv2d_fwd launches (ReLU on the input) over mask-multiplied weights. */
+int cfpp_maf_coupling_fwd(const float* x, const float* h, float* z, float* ldj, int B, int C, int HW, void* stream);
+
 /* ---- inverse (sampling) direction: SURVEY §8(f)-3 ------------------------------------------------------------ */
 /* Coupling.reverse / TransCoupling.reverse, layers/coupling.py:68-73,150-155: t, r from h (+ add) as in cfpp_coupling_fwd;
  * x = cat(z[:, :C/2], (z[:, C/2:] - t) / exp(2 tanh(r/2))).  One HBM pass, 12*C*HW bytes/sample. */
@@ -339,7 +344,9 @@ int64_t cfpp_actnorm_bwd_workspace_floats(int B, int D);
 int cfpp_actnorm_bwd(const float* x, const float* dz, const float* dldj, const float* t, const float* logs,
                      float* dx, float* dt, float* dlogs, float* workspace, int B, int D, int HW, void* stream);
 /* One convolution of the conditioner (layers/coupling.py:26-29) with saved output, "same" reflect padding, torch weight layout
- * (Cout, Cin, KH, KW), KH, KW in {1, 3}: out = [relu](W * in + bias).  `in` is read through a batch stride (x0 is x[:, :C/2]). */
+ * (Cout, Cin, KH, KW), KH, KW in {1, 3}: out = [relu](W * [relu](in) + bias); `relu` bit 0 = ReLU on the output, bit 1 = ReLU on the
+ * input (the pre-activation order of MaskedResidualBlock2d, layers/autoregressive/masked_conv_2d.py:93-98).  `in` is read through a
+ * batch stride (x0 is x[:, :C/2]). */
 int cfpp_conv2d_fwd(const float* in, int64_t in_bstride, const float* W, const float* bias, float* out,
                     int B, int Cin, int Cout, int H, int Wd, int KH, int KW, int relu, void* stream);
 /* din (= or +=, `accumulate`) the gradient of that convolution w.r.t. its input, including the adjoint of the reflect padding,

@@ -103,8 +103,10 @@ def build_stack(cfg: dict, data_size, mixtures: int, contexts) -> dict:
                 L.append(dict(op='transcoupling', size=sz, p=p, enc=enc(sz[0]), contextflow=cf))
             elif cfg['coupling'] == 'conv':
                 L.append(dict(op='coupling', C=sz[0], krn=krn, pad=pad, enc=enc(sz[0]), contextflow=cf))
-            elif cfg['coupling'] == 'maf':
-                raise NotImplementedError('--coupling maf is outside the hot path (SURVEY §8f)')
+            elif cfg['coupling'] == 'maf':                                   # model.py:145-147
+                if special:
+                    raise NotImplementedError('MaskedCoupling with a context_net is outside the restated path')
+                L.append(dict(op='maf', C=sz[0], krn=krn, pad=pad, enc=None, contextflow=cf))
             if cfg['dataset'] == 'atm':                                      # model.py:149-151
                 L.append(dict(op='permute')); sz = (sz[1], sz[0], sz[2])
         if cfg['split_prior'] and l < cfg['num_blocks'] - 1:                 # model.py:153-158
@@ -397,6 +399,37 @@ def coupling(P, state, lay, x, ctx, noise, dt, trans):
     return z, ls + logp_c
 
 
+def maf_mask(out_c, in_c, kh, kw, data_channels):
+    """mask_conv2d(mask_type='B') (layers/autoregressive/utils.py:25-92)."""
+    base = torch.ones(data_channels, data_channels).tril(0)
+    rows = torch.cat([base] * (in_c // data_channels + 1), 1)
+    chan = torch.cat([rows] * (out_c // data_channels + 1), 0)[:out_c, :in_c]
+    m = torch.ones(out_c, in_c, kh, kw)
+    m[:, :, kh // 2, kw // 2] = chan
+    m[:, :, kh // 2, kw // 2 + 1:] = 0
+    m[:, :, kh // 2 + 1:] = 0
+    return m
+
+
+def masked_coupling(P, lay, x):
+    """MaskedCoupling.forward (ar.py:35-57) over MaskedResidualBlock2d (masked_conv_2d.py:81-98): pre-activation convs with
+    mask-multiplied weights (:21-23), identity on both halves; z = x * s + t on all channels."""
+    k, D = lay['key'], lay['C']
+    pad = lay['pad']
+    h = x
+    for name in ('conv1', 'conv2', 'conv3'):
+        w = P(f'{k}.NN.{name}.weight')
+        w = w * maf_mask(w.shape[0], w.shape[1], w.shape[2], w.shape[3], D).to(w)
+        h = torch.relu(h)
+        if name == 'conv2' and (pad[0] or pad[1]):
+            h = F.pad(h, (pad[1], pad[1], pad[0], pad[0]), mode='reflect')
+        h = F.conv2d(h, w, P(f'{k}.NN.{name}.bias'))
+    h = h + x.repeat(1, 2, 1, 1)
+    t, r = h[:, :D], h[:, D:]
+    log_s = 2.0 * torch.tanh(r / 2.0)
+    return x * torch.exp(log_s) + t, log_s.flatten(1).sum(-1)
+
+
 def gmm_log_prob(P, state, lay, x, ctx, noise, dt):
     """GaussianMixtureDistribution.log_prob (gaussian.py:142-161) via torch.distributions semantics:
     Categorical(probs) -> logits = log(clamp(p/sum p, eps, 1-eps)); MixtureSameFamily: logsumexp_k(
@@ -466,6 +499,8 @@ def forward(stack: dict, state: Dict[str, torch.Tensor], x: torch.Tensor, ctx: O
             x, ldj = coupling(P, state, lay, x, ctx, noise, dt, trans=False)
         elif op == 'transcoupling':
             x, ldj = coupling(P, state, lay, x, ctx, noise, dt, trans=True)
+        elif op == 'maf':
+            x, ldj = masked_coupling(P, lay, x)
         elif op == 'splitprior':                                             # splitprior.py:12-15
             Ch = x.shape[1] // 2
             ldj = gmm_log_prob(P, state, dict(lay, key=f"{lay['key']}.dist"), x[:, Ch:], ctx, noise, dt)

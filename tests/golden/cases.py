@@ -34,6 +34,10 @@ CASES = {
     # MNIST at the literal 28x28 shape (BASELINE configs[0])
     'mnist28': dict(conf=variant('cfg1', data_size=(1, 28, 28)), B=2),
     # generalist conv coupling on MSL-shaped windows ((3,1) kernels, 56 channels after Augment, M = 2): training-direction case
+    # --coupling maf (MaskedCoupling over masked residual conv blocks), generalists: images (3x3) and MSL-shaped windows (3x1)
+    'mnist_maf': dict(conf=variant('cfg1', coupling='maf', num_blocks=2, block_size=1), B=3),
+    'msl_maf': dict(conf=variant('cfg4', dataset='msl', coupling='maf', data_size=(55, 8, 1), contexts=[27], mixtures=2,
+                                 num_blocks=1, block_size=2), B=4),
     # the CIFAR generalist (stage one of the paper's workflow): conv stack WITH split priors, no context
     'cifar_gen': dict(conf=variant('cfg2', generalist=True, contextflow=False, num_blocks=2, block_size=1), B=3),
     'msl_conv_gen': dict(conf=variant('cfg4', dataset='msl', coupling='conv', data_size=(55, 8, 1), contexts=[27], mixtures=2,

@@ -13,6 +13,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 Z_RTOL, Z_ATOL = 1e-4, 1e-5
 L_RTOL, L_ATOL = 1e-4, 1e-3
 BPD_ATOL = 1e-3
+BPD_RTOL = 2e-6      # only matters where |bpd| >> 1 (the maf stacks reach ~2e3: one float32 ulp of their log-prob is already 2e-4 bpd)
 
 
 def load_golden(name):
@@ -49,6 +50,12 @@ def golden_state(g, case):
         if f'{pre}.qbins' in state:
             q = torch.tensor(enc['num_cats'], dtype=torch.float32)
             state[f'{pre}.qbins'].copy_(q); state[f'{pre}.ldj_per_dim'].copy_(-torch.log(q))
+    for lay in stack['layers']:
+        if lay['op'] == 'maf':                                      # buffers of MaskedConv2d (masked_conv_2d.py:77-78)
+            for name in ('conv1', 'conv2', 'conv3'):
+                mk = f"{lay['key']}.NN.{name}.mask"
+                o, i, kh, kw = state[mk].shape
+                state[mk].copy_(O.maf_mask(o, i, kh, kw, lay['C']))
     synth.fill_state(state, case.get('wseed', 'w0'))
     if case.get('fresh_actnorm'):
         for k in state:
