@@ -208,3 +208,26 @@ def test_score_epilogue_large_batch_deterministic(B, M):
     assert torch.equal(a['argmax'].cpu(), ref['argmax'])
     assert_close(a['lse'].cpu().numpy(), ref['lse'].numpy(), 1e-5, 1e-6, 'lse')
     assert_close(a['sums'].cpu().numpy(), ref['sums'].numpy(), 1e-5, 1e-3, 'sums')
+
+
+def test_empty_and_single_sample_batches():
+    """Edge cases the reference's ops accept: B = 0 (empty tensors flow through) and B = 1, for the inverse / training / window ops."""
+    from contextflow_b200.windows import WindowedScorer
+    for B in (0, 1):
+        z = torch.zeros(B, 8, 4, 4, device='cuda'); h = torch.zeros(B, 8, 4, 4, device='cuda')
+        assert ops.coupling_inv(z, h).shape == (B, 8, 4, 4)
+        assert ops.actnorm_inv(z, torch.zeros(8, device='cuda'), torch.zeros(8, device='cuda')).shape == (B, 8, 4, 4)
+        assert ops.unsqueeze(z, 2, 2).shape == (B, 2, 8, 8)
+        assert ops.prologue_inv(z, 7, 1.0, 0.0, 256.0, 0.0).shape == (B, 7, 4, 4)
+        dx, dh = ops.coupling_bwd(z, h, z)
+        assert dx.shape == z.shape and dh.shape == h.shape
+        assert ops.maf_coupling(z, torch.zeros(B, 16, 4, 4, device='cuda'))[1].shape == (B,)
+        assert ops.conv2d_fwd(z, 8, torch.zeros(5, 8, 3, 3, device='cuda'), torch.zeros(5, device='cuda'), relu=True).shape == (B, 5, 4, 4)
+        dW, db = ops.conv2d_bwd_weight(z, 8, torch.zeros(B, 5, 4, 4, device='cuda'), (5, 8, 3, 3))
+        assert not dW.any() and not db.any()
+    sc = WindowedScorer(torch.rand(1, 3, dtype=torch.float64), 4)
+    assert torch.equal(sc.windows(0, 1).cpu(), torch.from_numpy(np.broadcast_to(sc.ts.cpu().float().numpy().T[None, :, :, None], (1, 3, 4, 1)).copy()))
+    with pytest.raises(RuntimeError):
+        ops.score_epilogue(torch.zeros(0, 3, device='cuda'), 1.0)          # the reference's .mean() over an empty batch is NaN: refused loudly
+    one = ops.score_epilogue(torch.tensor([[-3.0, -1.0]], device='cuda'), 0.5)
+    assert one['argmax'].item() == 1 and abs(one['lse'].item() - float(torch.logsumexp(torch.tensor([-1.5, -0.5]), 0))) < 1e-6
