@@ -91,6 +91,7 @@ _SIGNATURES = {
     'cfpp_embed_lookup': (i32, [vp, C.POINTER(vp), i32, i32, vp, i32, vp]),
     'cfpp_linear_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     'cfpp_cn_batch': (i32, [C.POINTER(CnJob), i32, C.POINTER(vp), C.POINTER(vp), i32, vp]),
+    'cfpp_relu_fwd': (i32, [vp, vp, i64, vp]),
     'cfpp_maf_coupling_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     'cfpp_coupling_inv': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     'cfpp_actnorm_inv': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
@@ -107,7 +108,8 @@ _SIGNATURES = {
     'cfpp_actnorm_bwd': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     'cfpp_conv2d_fwd': (i32, [vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'cfpp_conv2d_bwd_data': (i32, [vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
-    'cfpp_conv2d_bwd_weight': (i32, [vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+    'cfpp_conv2d_bwd_weight_workspace_floats': (i64, [i32, i32, i32, i32, i32]),
+    'cfpp_conv2d_bwd_weight': (i32, [vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     'cfpp_relu_mask': (i32, [vp, vp, i64, vp]),
     'cfpp_logdet_grad': (i32, [vp, vp, vp, i32, i32, i32, vp]),
     'cfpp_rowsum': (i32, [vp, vp, i32, i32, vp]),

@@ -2,8 +2,8 @@
 // (generalist) conv stack -- Coupling (layers/coupling.py:39-66), its conv conditioner (:26-29), ActNorm (layers/actnorm.py:37-60),
 // Conv1x1 (layers/conv1x1.py:52-55), the mixture base (layers/distributions/gaussian.py:142-161) and the (B,M) log-det accumulation
 // (layers/flowsequential.py:20-27).  What the reference obtains from torch autograd over experiment_ad.py:204-213.
-// First correct version: FP32 CUDA cores, one CTA per sample with the sample resident in shared memory; weight gradients are
-// accumulated with fp32 atomics (sums over the batch are order dependent at the 1e-7 level).
+// First version: FP32 CUDA cores, one CTA per sample with the sample resident in shared memory; every reduction over the batch is
+// two-stage with a fixed order (no atomics): gradients are bit-identical run to run.
 #include <math.h>
 #include "common.cuh"
 
@@ -254,14 +254,18 @@ __global__ void __launch_bounds__(256) conv2d_bwd_data_kernel(const float* __res
 // dW[co,ci,tap] += sum_{b in chunk, p} dout[b,co,p] in[b,ci,reflect(p + tap - pad)];  db[co] += sum dout.
 // grid (chunks, co blocks).  A CTA stages, per sample, the reflect-padded input planes and NCO rows of dout; thread = one input
 // channel x PPT output channels (the 3x3 input window is loaded once per pixel and reused by the PPT rows), accumulators live in
-// registers across the samples of the chunk, then one fp32 atomicAdd per weight.
+// registers across the samples of the chunk, then one store per weight into the chunk's slice of the workspace; a finishing kernel adds
+// the chunks in order, so the gradient is bit-identical run to run (no atomics).
 constexpr int PPT = 4;
 
 template <int KH, int KW>
 __global__ void __launch_bounds__(256) conv2d_bwd_weight_kernel(const float* __restrict__ in, int64_t in_bstride, const float* __restrict__ dout,
                                                                 float* __restrict__ dW, float* __restrict__ db,
                                                                 int B, int Cin, int Cout, int H, int Wd, int NCO, int per_chunk) {
+  // dW / db here are the workspace slices: [chunk][Cout*Cin*KK] and [chunk][Cout]
   constexpr int PH = KH / 2, PW = KW / 2, KK = KH * KW;
+  dW += (int64_t)blockIdx.x * Cout * Cin * KK;
+  if (db) db += (int64_t)blockIdx.x * Cout;
   extern __shared__ float sm[];
   const int HW = H * Wd, Wp = Wd + 2 * PW, S = odd_stride((H + 2 * PH) * Wp), Sg = odd_stride(HW);
   float* sin_ = sm;                                   // Cin * S
@@ -312,10 +316,18 @@ __global__ void __launch_bounds__(256) conv2d_bwd_weight_kernel(const float* __r
       const int co = cog + k * cpp;
       if (co >= nco) continue;
 #pragma unroll
-      for (int t = 0; t < KK; ++t) atomicAdd(dW + ((int64_t)(co0 + co) * Cin + ci) * KK + t, acc[k][t]);
+      for (int t = 0; t < KK; ++t) dW[((int64_t)(co0 + co) * Cin + ci) * KK + t] = acc[k][t];
     }
   }
-  if (db && (int)threadIdx.x < nco) atomicAdd(db + co0 + threadIdx.x, bsum);
+  if (db && (int)threadIdx.x < nco) db[co0 + threadIdx.x] = bsum;
+}
+
+__global__ void chunk_sum_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int chunks) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += part[(int64_t)c * n + i];
+    out[i] = s;
+  }
 }
 
 // elementwise ReLU mask: g *= (act > 0)
@@ -576,26 +588,50 @@ extern "C" int cfpp_conv2d_bwd_data(const float* dout, const float* W, const flo
   return check_launch("conv2d_bwd_data");
 }
 
-extern "C" int cfpp_conv2d_bwd_weight(const float* in, int64_t in_bstride, const float* dout, float* dW, float* db,
+static inline void bwd_weight_plan(int B, int Cin, int Cout, int& NCO, int& coblocks, int& chunks, int& per_chunk) {
+  NCO = (256 / (Cin > 0 ? Cin : 1)) * PPT; if (NCO > Cout) NCO = Cout; if (NCO < 1) NCO = 1;
+  coblocks = (Cout + NCO - 1) / NCO;
+  chunks = (num_sms() * 4 + coblocks - 1) / coblocks; if (chunks > B) chunks = B; if (chunks < 1) chunks = 1;
+  per_chunk = (B + chunks - 1) / chunks; if (per_chunk < 1) per_chunk = 1;
+  chunks = B > 0 ? (B + per_chunk - 1) / per_chunk : 1;
+}
+
+extern "C" int64_t cfpp_conv2d_bwd_weight_workspace_floats(int B, int Cin, int Cout, int KH, int KW) {
+  int NCO, coblocks, chunks, per_chunk;
+  bwd_weight_plan(B, Cin, Cout, NCO, coblocks, chunks, per_chunk);
+  return (int64_t)chunks * ((int64_t)Cout * Cin * KH * KW + Cout);
+}
+
+extern "C" int cfpp_conv2d_bwd_weight(const float* in, int64_t in_bstride, const float* dout, float* dW, float* db, float* workspace,
                                       int B, int Cin, int Cout, int H, int Wd, int KH, int KW, void* stream) {
   CFPP_REQUIRE(conv_shape_ok(H, Wd, KH, KW), "conv2d: kernel %dx%d on %dx%d", KH, KW, H, Wd);
   CFPP_REQUIRE(Cin >= 1 && Cin <= 256, "conv2d_bwd_weight: Cin=%d outside [1,256]", Cin);
   const int KK = KH * KW, HW = H * Wd;
-  cudaMemsetAsync(dW, 0, (size_t)Cout * Cin * KK * sizeof(float), (cudaStream_t)stream);
-  if (db) cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), (cudaStream_t)stream);
-  if (B <= 0) return CFPP_OK;
-  int NCO = (256 / Cin) * PPT; if (NCO > Cout) NCO = Cout;
-  const int coblocks = (Cout + NCO - 1) / NCO;
-  int chunks = (num_sms() * 4 + coblocks - 1) / coblocks; if (chunks > B) chunks = B; if (chunks < 1) chunks = 1;
-  const int per_chunk = (B + chunks - 1) / chunks;
-  chunks = (B + per_chunk - 1) / per_chunk;
+  const int64_t nW = (int64_t)Cout * Cin * KK;
+  if (B <= 0) {
+    cudaMemsetAsync(dW, 0, (size_t)nW * sizeof(float), (cudaStream_t)stream);
+    if (db) cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), (cudaStream_t)stream);
+    return CFPP_OK;
+  }
+  CFPP_REQUIRE(workspace != nullptr, "conv2d_bwd_weight: workspace required (cfpp_conv2d_bwd_weight_workspace_floats)");
+  int NCO, coblocks, chunks, per_chunk;
+  bwd_weight_plan(B, Cin, Cout, NCO, coblocks, chunks, per_chunk);
+  float* partW = workspace; float* partb = workspace + (int64_t)chunks * nW;
   const size_t smem = ((size_t)Cin * odd_stride((H + 2 * (KH / 2)) * (Wd + 2 * (KW / 2))) + (size_t)NCO * odd_stride(HW)) * sizeof(float);
   const dim3 grid(chunks, coblocks);
   CFPP_CONV_DISPATCH(KH, KW, {
     CFPP_REQUIRE(want_smem(conv2d_bwd_weight_kernel<kKH, kKW>, smem), "conv2d_bwd_weight: tile of %zu bytes exceeds shared memory", smem);
-    conv2d_bwd_weight_kernel<kKH, kKW><<<grid, 256, smem, (cudaStream_t)stream>>>(in, in_bstride, dout, dW, db, B, Cin, Cout, H, Wd, NCO, per_chunk);
+    conv2d_bwd_weight_kernel<kKH, kKW><<<grid, 256, smem, (cudaStream_t)stream>>>(in, in_bstride, dout, partW, db ? partb : nullptr, B, Cin, Cout, H, Wd, NCO, per_chunk);
   });
-  return check_launch("conv2d_bwd_weight");
+  int rc = check_launch("conv2d_bwd_weight");
+  if (rc != CFPP_OK) return rc;
+  chunk_sum_kernel<<<grid1d(nW), 256, 0, (cudaStream_t)stream>>>(partW, dW, nW, chunks);
+  if ((rc = check_launch("conv2d_bwd_weight_sum")) != CFPP_OK) return rc;
+  if (db) {
+    chunk_sum_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partb, db, Cout, chunks);
+    rc = check_launch("conv2d_bwd_bias_sum");
+  }
+  return rc;
 }
 
 extern "C" int cfpp_relu_mask(float* g, const float* act, int64_t n, void* stream) {

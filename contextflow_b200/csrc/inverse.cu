@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ in
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float v = in[i];
-    out[i] = op == 0 ? sigmoid_f(v) : op == 1 ? __fmul_rn(__fsub_rn(v, b), a) : floorf(v);
+    out[i] = op == 0 ? sigmoid_f(v) : op == 1 ? __fmul_rn(__fsub_rn(v, b), a) : op == 2 ? floorf(v) : fmaxf(v, 0.f);
   }
 }
 
@@ -401,6 +401,12 @@ extern "C" int cfpp_floor_fwd(const float* x, float* y, int64_t n, void* stream)
   if (n <= 0) return CFPP_OK;
   unary_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, y, n, 2, 0.f, 0.f);
   return check_launch("floor_fwd");
+}
+
+extern "C" int cfpp_relu_fwd(const float* x, float* y, int64_t n, void* stream) {
+  if (n <= 0) return CFPP_OK;
+  unary_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, y, n, 3, 0.f, 0.f);
+  return check_launch("relu_fwd");
 }
 
 extern "C" int cfpp_gmm_sample(const float* mG, const float* sG, const int64_t* comp, const float* eps, float* x,

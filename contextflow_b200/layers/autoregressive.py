@@ -60,11 +60,31 @@ class MaskedResidualBlock2d(nn.Module):
         ks, pd = tuple(self.conv2.kernel_size), tuple(self.conv2.padding)
         if pd != (ks[0] // 2, ks[1] // 2) or any(k not in (1, 3) for k in ks):
             raise NotImplementedError('the conv kernels assume "same" reflect padding with 1/3-wide kernels (model.py:114)')
+        from .flowlayer import PackCache
+        self._packs = PackCache()
+
+    def _tc_pack(self):
+        """The block is the conditioner's 1x1 -> ReLU -> kxk reflect -> ReLU -> 1x1 chain applied to relu(x): same tcgen05 kernel, weights
+        packed from the mask-multiplied tensors (once per weight version)."""
+        convs = (self.conv1, self.conv2, self.conv3)
+        ws = [c.masked_weight() for c in convs]
+        if not ws[0].is_cuda:
+            return None
+        key = [c.weight for c in convs] + [c.bias for c in convs]
+        return self._packs.get('tc', key, lambda: (ops.conv_cond_tc_pack(ws[0], ws[1], ws[2], ws[0].shape[1]),
+                                                   ops.pad_vec(self.conv1.bias), ops.pad_vec(self.conv2.bias), ops.pad_vec(self.conv3.bias)))
 
     def forward(self, x, identity=True):
-        h = x
-        for conv in (self.conv1, self.conv2, self.conv3):
-            h = ops.conv2d_fwd(h, h.shape[1], conv.masked_weight(), conv.bias.detach(), relu=False, relu_in=True)
         if identity:
             raise NotImplementedError('use MaskedCoupling: the identity is added inside the fused coupling kernel')
+        pk = self._tc_pack()
+        if pk is not None and pk[0] is not None and ops.conv_cond_tc_mode() != 'fma':
+            ks = self.conv2.kernel_size
+            h = ops.conv_cond_tc(ops.relu(x), x.shape[1], pk[0], pk[1], pk[2], pk[3], self.conv2.out_channels, x.shape[2], x.shape[3],
+                                 ks[0], ks[1], self.conv3.out_channels)
+            if h is not None:
+                return h
+        h = x
+        for conv in (self.conv1, self.conv2, self.conv3):                  # FP32 kernels: shapes without a tensor-core plan
+            h = ops.conv2d_fwd(h, h.shape[1], conv.masked_weight(), conv.bias.detach(), relu=False, relu_in=True)
         return h

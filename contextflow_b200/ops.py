@@ -693,6 +693,14 @@ def actnorm_bwd(x, dz, dldj, t, logs, need_dx=True):
     return dx, dt, dlogs
 
 
+def relu(x):
+    _need_cuda(x); x = _f32(x)
+    y = torch.empty_like(x)
+    _set_work(bytes=8.0 * x.numel())
+    _call('relu_fwd', (_p(x), _p(y), x.numel(), _stream()))
+    return y
+
+
 def maf_coupling(x, h):
     """MaskedCoupling elementwise part (ar.py:35-57): h (B, 2C, H, W) without the identity."""
     _need_cuda(x, h); x = _f32(x); h = _f32(h)
@@ -740,7 +748,8 @@ def conv2d_bwd_weight(x, cin, dout, wshape, bias=True):
     dW = torch.empty(tuple(wshape), device=dout.device, dtype=torch.float32)
     db = torch.empty(cout, device=dout.device, dtype=torch.float32) if bias else None
     _set_work(flops=2.0 * B * cout * cin * KH * KW * H * W)
-    _call('conv2d_bwd_weight', (_p(xv), bstride, _p(dout), _p(dW), _p(db), B, cin, cout, H, W, KH, KW, _stream()))
+    ws = torch.empty(max(1, int(lib().cfpp_conv2d_bwd_weight_workspace_floats(B, cin, cout, KH, KW))), device=dout.device, dtype=torch.float32)
+    _call('conv2d_bwd_weight', (_p(xv), bstride, _p(dout), _p(dW), _p(db), _p(ws), B, cin, cout, H, W, KH, KW, _stream()))
     return dW, db
 
 

@@ -289,6 +289,8 @@ int cfpp_cn_batch(const cfpp_cn_job* jobs, int n_jobs, const float* const* in, f
 /* MaskedCoupling.forward (`--coupling maf`, layers/ar.py:35-57) after its masked residual block: h (B, 2C, HW) is the block's conv
  * output WITHOUT the identity; t = h[:, :C] + x, r = h[:, C:] + x (masked_conv_2d.py:92,98); z = x * exp(2 tanh(r/2)) + t;
  * ldj[b] = sum 2 tanh(r/2).  The block itself = three cfpp_conv2d_fwd launches (ReLU on the input) over mask-multiplied weights. */
+/* y = max(x, 0): the pre-activation of MaskedResidualBlock2d (masked_conv_2d.py:94) in front of cfpp_conv_cond_tc_fwd. */
+int cfpp_relu_fwd(const float* x, float* y, int64_t n, void* stream);
 int cfpp_maf_coupling_fwd(const float* x, const float* h, float* z, float* ldj, int B, int C, int HW, void* stream);
 
 /* ---- inverse (sampling) direction: SURVEY §8(f)-3 ------------------------------------------------------------ */
@@ -331,8 +333,8 @@ int cfpp_score_epilogue(const float* logp, float dim_inv, const int64_t* gt, con
                         void* workspace, int B, int M, void* stream);
 
 /* ---- training direction, context-free conv stack: SURVEY §8(f)-1 ------------------------------------------------- */
-/* What torch autograd derives for the reference (experiment_ad.py:204-213).  All gradients fp32; weight gradients are OVERWRITTEN
- * (zeroed inside, then accumulated with fp32 atomics over the batch).
+/* What torch autograd derives for the reference (experiment_ad.py:204-213).  All gradients fp32; weight gradients are OVERWRITTEN;
+ * every reduction over the batch has a fixed order (bit-identical run to run).
  * Coupling backward (layers/coupling.py:50-66): given x, h of the forward, dz and dldj (B, may be NULL):
  *   dx = cat(dz0, dz1 * s); dh = cat(dz1, (dz1 * x1 * s + dldj[b]) * (1 - tanh^2(r/2))), s = exp(2 tanh(r/2)).
  *   The conditioner's own gradient is then ADDED onto dx[:, :C/2] by cfpp_conv2d_bwd_data(accumulate = 1). */
@@ -354,8 +356,10 @@ int cfpp_conv2d_fwd(const float* in, int64_t in_bstride, const float* W, const f
 int cfpp_conv2d_bwd_data(const float* dout, const float* W, const float* act, int64_t act_bstride, float* din, int64_t din_bstride,
                          int accumulate, int B, int Cin, int Cout, int H, int Wd, int KH, int KW, void* stream);
 /* dW (Cout, Cin, KH, KW) and db (Cout, may be NULL) of that convolution.  With 1x1 kernels and Cin = Cout = D this is also
- * Conv1x1's dNN = sum_{b,p} dz x^T (layers/conv1x1.py:52-55). */
-int cfpp_conv2d_bwd_weight(const float* in, int64_t in_bstride, const float* dout, float* dW, float* db,
+ * Conv1x1's dNN = sum_{b,p} dz x^T (layers/conv1x1.py:52-55).  Per-chunk partial sums go to `workspace`
+ * (cfpp_conv2d_bwd_weight_workspace_floats floats) and are added in chunk order: deterministic, no atomics. */
+int64_t cfpp_conv2d_bwd_weight_workspace_floats(int B, int Cin, int Cout, int KH, int KW);
+int cfpp_conv2d_bwd_weight(const float* in, int64_t in_bstride, const float* dout, float* dW, float* db, float* workspace,
                            int B, int Cin, int Cout, int H, int Wd, int KH, int KW, void* stream);
 /* g[i] = 0 where act[i] <= 0 (ReLU backward on a saved post-activation). */
 int cfpp_relu_mask(float* g, const float* act, int64_t n, void* stream);

@@ -200,6 +200,24 @@ def test_conv1x1_and_ldj_sum_functions():
     assert_close(lay.NN.grad.cpu().numpy(), Nd.grad.numpy(), 1e-4, 1e-4 * float(Nd.grad.abs().max()), 'dNN')
 
 
+def test_backward_is_deterministic():
+    """Two backward passes over the same batch give bit-identical gradients (fixed-order reductions, no atomics)."""
+    case = dict(CASES['cifar_gen'], B=300, iseed='in7')
+    spec = TRAINING_CASES['cifar_gen']
+    model = build_cuda_model(case).train()
+    x, ctx = case_inputs(case)
+    gt = labels('det', 300, 10).cuda()
+    grads = []
+    for _ in range(2):
+        model.zero_grad(set_to_none=True)
+        with rng.use_source(synth.NoiseTape('noise7')):
+            cost, _, _ = reference_loss(model, x.cuda(), ctx.cuda(), gt, case['conf']['data_size'], spec)
+        cost.backward()
+        grads.append({k: p.grad.clone() for k, p in model.named_parameters() if p.requires_grad})
+    for k in grads[0]:
+        assert torch.equal(grads[0][k], grads[1][k]), k
+
+
 def test_unsupported_layers_raise_under_autograd():
     model = build_cuda_model(CASES['cfg4']).train()            # ViT conditioner: no backward kernels yet
     x, ctx = case_inputs(CASES['cfg4'])
