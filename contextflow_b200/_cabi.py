@@ -117,6 +117,20 @@ _SIGNATURES = {
     'cfpp_gmm_train_fwd': (i32, [vp, i64, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     'cfpp_gmm_train_bwd_workspace_floats': (i64, [i32, i32, i32, i32]),
     'cfpp_gmm_train_bwd': (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    'cfpp_patchify_fwd': (i32, [vp, i64, vp, i32, i32, i32, i32, i32, i32, vp]),
+    'cfpp_patchify_inv': (i32, [vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp]),
+    'cfpp_layernorm_fwd': (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp]),
+    'cfpp_layernorm_bwd_workspace_floats': (i64, [i64, i32]),
+    'cfpp_layernorm_bwd': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp]),
+    'cfpp_rows_linear_fwd': (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
+    'cfpp_rows_linear_bwd_data': (i32, [vp, vp, vp, i32, i64, i32, i32, vp]),
+    'cfpp_rows_linear_bwd_weight_workspace_floats': (i64, [i64, i32, i32]),
+    'cfpp_rows_linear_bwd_weight': (i32, [vp, vp, vp, vp, vp, i64, i32, i32, vp]),
+    'cfpp_gelu_fwd': (i32, [vp, vp, i64, vp]),
+    'cfpp_gelu_bwd': (i32, [vp, vp, vp, i64, vp]),
+    'cfpp_add_pos': (i32, [vp, vp, i64, i32, i32, vp]),
+    'cfpp_attention_fwd': (i32, [vp, vp, vp, i32, i32, vp]),
+    'cfpp_attention_bwd': (i32, [vp, vp, vp, vp, i32, i32, vp]),
     'cfpp_ldj_accumulate': (i32, [vp, vp, i32, i32, i32, vp]),
     'cfpp_ldj_sum': (i32, [vp, vp, vp, C.POINTER(vp), C.POINTER(i32), i32, i32, i32, vp]),
 }

@@ -40,6 +40,8 @@ class Conv1x1(FlowLayer):
         if training.wants_grad(x, self.NN) and not self.context_net:
             return training.Conv1x1Fn.apply(x, self.NN, self)          # autograd through libcfpp kernels
         inference_only(self.NN); inference_only(x)
+        if self.context_net:
+            inference_only(self.CN.weight)
         lad = self.logabsdet()
         if self.context_net:
             cm, logp_c = self.context_matrix(context)

@@ -164,8 +164,10 @@ class TransCoupling(_CouplingBase):
         self._plan, self._packs = ContextPlan(), PackCache()
 
     def forward(self, x, context=None):
-        inference_only(x)
         vit = self.NN if isinstance(self.NN, SimpleViT) else self.NN[0]
+        if not self.context_net and training.wants_grad(x, *vit.parameters()):
+            return training.CouplingVitFn.apply(x, vit, *vit._sources())   # autograd through libcfpp kernels
+        inference_only(x)
         if not self.context_net:
             return ops.coupling(x, vit(x))
         cn, logp_c = self._context_terms(context)                   # note: logp_c is NOT scaled by H*W here (coupling.py:126)

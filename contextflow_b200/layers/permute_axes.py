@@ -1,7 +1,7 @@
 """PermuteAxes: the ATM stack swaps channel and time axes (reference layers/permute_axes.py:5-21, model.py:149-151)."""
 from collections.abc import Iterable
 
-from .. import ops
+from .. import ops, training
 from .flowlayer import FlowLayer
 
 
@@ -18,6 +18,8 @@ class PermuteAxes(FlowLayer):
             return x.clone()
         if tuple(perm) != (0, 2, 1, 3):
             raise NotImplementedError(f'only the (0,2,1,3) axis swap has a kernel; got {tuple(perm)}')
+        if training.wants_grad(x):
+            return training.PermuteFn.apply(x)
         return ops.permute_chw(x)
 
     def forward(self, input, context=None):

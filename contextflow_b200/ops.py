@@ -817,3 +817,114 @@ def gmm_train_bwd(x, mG, sG, wG, inv_var, resp, g, need_dx=True, dx_out=None):
     _call('gmm_train_bwd', (_p(xv), bstride, _p(_f32(mG)), _p(_f32(sG)), _p(_f32(wG)), _p(inv_var), _p(resp), _p(g), _p(dx), dstride,
                             _p(dmG), _p(dsG), _p(dwG), _p(ws), B, M, K, n, _stream()))
     return dx, dmG, dsG, dwG
+
+
+# ---------------------------------------------------------------------------------------------- ViT conditioner, training direction
+def patchify(x, c, p1, p2):
+    """(B, >=c, H, W) -> token rows (B * n_tok, p1*p2*c)  (simple_vit.py:102)."""
+    _need_cuda(x)
+    xv, bstride = _half_view(x[:, :c])
+    B, H, W = x.shape[0], x.shape[2], x.shape[3]
+    tok = torch.empty((B * (H // p1) * (W // p2), p1 * p2 * c), device=x.device, dtype=torch.float32)
+    _call('patchify_fwd', (_p(xv), bstride, _p(tok), B, c, H, W, p1, p2, _stream()))
+    return tok
+
+
+def patchify_inv(tok, c, H, W, p1, p2, out=None, accumulate=False):
+    """Token rows -> (B, c, H, W); with `out` (B, >=c, H, W) the first c channels receive (+)= it."""
+    _need_cuda(tok); tok = _f32(tok)
+    B = tok.shape[0] // ((H // p1) * (W // p2))
+    if out is None:
+        out = torch.empty((B, c, H, W), device=tok.device, dtype=torch.float32)
+    ov, ostride = _half_view(out[:, :c])
+    assert ov.data_ptr() == out.data_ptr()
+    _call('patchify_inv', (_p(tok), _p(ov), ostride, int(bool(accumulate)), B, c, H, W, p1, p2, _stream()))
+    return out
+
+
+def layernorm_fwd(x, gamma, beta):
+    _need_cuda(x); x = _f32(x)
+    R, F = x.shape
+    y = torch.empty_like(x); mean = torch.empty(R, device=x.device, dtype=torch.float32); rstd = torch.empty_like(mean)
+    _set_work(bytes=8.0 * x.numel())
+    _call('layernorm_fwd', (_p(x), _p(_f32(gamma)), _p(_f32(beta)), _p(y), _p(mean), _p(rstd), R, F, _stream()))
+    return y, mean, rstd
+
+
+def layernorm_bwd(x, dy, gamma, mean, rstd):
+    _need_cuda(x, dy); x = _f32(x); dy = _f32(dy)
+    R, F = x.shape
+    dx = torch.empty_like(x); dg = torch.empty(F, device=x.device, dtype=torch.float32); db = torch.empty_like(dg)
+    ws = torch.empty(int(lib().cfpp_layernorm_bwd_workspace_floats(R, F)), device=x.device, dtype=torch.float32)
+    _set_work(bytes=12.0 * x.numel())
+    _call('layernorm_bwd', (_p(x), _p(dy), _p(_f32(gamma)), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db), _p(ws), R, F, _stream()))
+    return dx, dg, db
+
+
+def rows_linear(x, w, b=None):
+    _need_cuda(x, w); x = _f32(x)
+    R, I = x.shape
+    J = w.shape[0]
+    y = torch.empty((R, J), device=x.device, dtype=torch.float32)
+    _set_work(flops=2.0 * R * I * J)
+    _call('rows_linear_fwd', (_p(x), _p(_f32(w)), _p(None if b is None else _f32(b)), _p(y), R, I, J, _stream()))
+    return y
+
+
+def rows_linear_bwd_data(dy, w):
+    _need_cuda(dy, w); dy = _f32(dy)
+    R, J = dy.shape
+    I = w.shape[1]
+    dx = torch.empty((R, I), device=dy.device, dtype=torch.float32)
+    _set_work(flops=2.0 * R * I * J)
+    _call('rows_linear_bwd_data', (_p(dy), _p(_f32(w)), _p(dx), 0, R, I, J, _stream()))
+    return dx
+
+
+def rows_linear_bwd_weight(x, dy, bias=True):
+    _need_cuda(x, dy); x = _f32(x); dy = _f32(dy)
+    R, I = x.shape
+    J = dy.shape[1]
+    dW = torch.empty((J, I), device=x.device, dtype=torch.float32)
+    db = torch.empty(J, device=x.device, dtype=torch.float32) if bias else None
+    ws = torch.empty(int(lib().cfpp_rows_linear_bwd_weight_workspace_floats(R, I, J)), device=x.device, dtype=torch.float32)
+    _set_work(flops=2.0 * R * I * J)
+    _call('rows_linear_bwd_weight', (_p(x), _p(dy), _p(dW), _p(db), _p(ws), R, I, J, _stream()))
+    return dW, db
+
+
+def gelu_fwd(x):
+    _need_cuda(x); x = _f32(x)
+    y = torch.empty_like(x)
+    _call('gelu_fwd', (_p(x), _p(y), x.numel(), _stream()))
+    return y
+
+
+def gelu_bwd(x, dy):
+    _need_cuda(x, dy); x = _f32(x); dy = _f32(dy)
+    dx = torch.empty_like(x)
+    _call('gelu_bwd', (_p(x), _p(dy), _p(dx), x.numel(), _stream()))
+    return dx
+
+
+def add_pos_(x, pos, n_tok):
+    _need_cuda(x, pos)
+    _call('add_pos', (_p(x), _p(_f32(pos)), x.shape[0], n_tok, x.shape[1], _stream()))
+    return x
+
+
+def attention_fwd(qkv, B, n_tok):
+    _need_cuda(qkv); qkv = _f32(qkv)
+    O = torch.empty((B * n_tok, 64), device=qkv.device, dtype=torch.float32)
+    P = torch.empty((B, n_tok, n_tok), device=qkv.device, dtype=torch.float32)
+    _set_work(flops=4.0 * B * n_tok * n_tok * 64)
+    _call('attention_fwd', (_p(qkv), _p(O), _p(P), B, n_tok, _stream()))
+    return O, P
+
+
+def attention_bwd(qkv, P, dO, B, n_tok):
+    _need_cuda(qkv, P, dO); dO = _f32(dO)
+    dqkv = torch.empty_like(qkv)
+    _set_work(flops=8.0 * B * n_tok * n_tok * 64)
+    _call('attention_bwd', (_p(qkv), _p(P), _p(dO), _p(dqkv), B, n_tok, _stream()))
+    return dqkv

@@ -44,6 +44,18 @@ class UnSqueezeFn(Function):
         return ops.squeeze(dx.contiguous(), *ctx.p), None, None
 
 
+class PermuteFn(Function):
+    """PermuteAxes((0,2,1,3)) (permute_axes.py:13-14): the swap is its own inverse."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.permute_chw(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.permute_chw(dy.contiguous())
+
+
 class Conv1x1Fn(Function):
     """z = NN x per pixel, ldj = HW log|det NN| (conv1x1.py:52-55)."""
 
@@ -186,3 +198,76 @@ class LdjSumFn(Function):
                     rs = ops.rowsum(g)
                 grads.append(rs.view(shp))
         return (g, None, *grads)
+
+
+class CouplingVitFn(Function):
+    """TransCoupling with the SimpleViT conditioner (coupling.py:100-148, simple_vit.py:30-127), context-free.  The training forward is
+    the reference's module stack op by op on token rows (LayerNorm, Linear, single-head attention, GELU, residuals) with the
+    activations saved; the backward walks it in reverse.  Parameter order = SimpleViT._sources()."""
+
+    @staticmethod
+    def forward(ctx, x, vit, *params):
+        g = vit.geom
+        c, p1, p2, T, n, depth = g['Cin'], g['p1'], g['p2'], g['T'], g['n_tok'], g['depth']
+        B, C, H, W = x.shape
+        P = [p.detach() for p in params]
+        ln0w, ln0b, pew, peb, ln1w, ln1b, lnfw, lnfb = P[:8]
+        tok = ops.patchify(x, c, p1, p2)
+        y0, m0, r0 = ops.layernorm_fwd(tok, ln0w, ln0b)
+        e = ops.rows_linear(y0, pew, peb)
+        X, m1, r1 = ops.layernorm_fwd(e, ln1w, ln1b)
+        ops.add_pos_(X, vit.pos_embedding.to(x.device, torch.float32).contiguous(), n)
+        saved = [tok, m0, r0, y0, e, m1, r1]
+        for l in range(depth):
+            anw, anb, qkvw, outw, f0w, f0b, f1w, f1b, f3w, f3b = P[8 + 10 * l: 18 + 10 * l]
+            y, ma, ra = ops.layernorm_fwd(X, anw, anb)
+            qkv = ops.rows_linear(y, qkvw)
+            O, Pm = ops.attention_fwd(qkv, B, n)
+            X1 = ops.add(ops.rows_linear(O, outw), X)
+            y2, mf, rf = ops.layernorm_fwd(X1, f0w, f0b)
+            hpre = ops.rows_linear(y2, f1w, f1b)
+            gact = ops.gelu_fwd(hpre)
+            X2 = ops.add(ops.rows_linear(gact, f3w, f3b), X1)
+            saved += [X, ma, ra, y, qkv, Pm, O, X1, mf, rf, y2, hpre, gact]
+            X = X2
+        Xf, mz, rz = ops.layernorm_fwd(X, lnfw, lnfb)
+        cc = T // (p1 * p2)
+        h = ops.patchify_inv(Xf, cc, H, W, p1, p2)
+        z, ldj = ops.coupling(x, h)
+        saved += [X, mz, rz, x, h]
+        ctx.save_for_backward(*saved, *params)
+        ctx.meta = (c, p1, p2, T, n, depth, B, H, W, cc, len(saved))
+        return z, ldj
+
+    @staticmethod
+    def backward(ctx, dz, dldj):
+        c, p1, p2, T, n, depth, B, H, W, cc, ns = ctx.meta
+        S = ctx.saved_tensors[:ns]
+        P = [p.detach() for p in ctx.saved_tensors[ns:]]
+        ln0w, ln0b, pew, peb, ln1w, ln1b, lnfw, lnfb = P[:8]
+        Xlast, mz, rz, x, h = S[-5:]
+        dz = _zeros_like_if_none(dz, x.shape, x.device).contiguous()
+        dx, dh = ops.coupling_bwd(x, h, dz, None if dldj is None else dldj.contiguous())
+        grads = [None] * len(P)
+        dXf = ops.patchify(dh, cc, p1, p2)
+        dX, grads[6], grads[7] = ops.layernorm_bwd(Xlast, dXf, lnfw, mz, rz)
+        for l in reversed(range(depth)):
+            X, ma, ra, y, qkv, Pm, O, X1, mf, rf, y2, hpre, gact = S[7 + 13 * l: 20 + 13 * l]
+            o = 8 + 10 * l
+            anw, anb, qkvw, outw, f0w, f0b, f1w, f1b, f3w, f3b = P[o: o + 10]
+            grads[o + 8], grads[o + 9] = ops.rows_linear_bwd_weight(gact, dX)
+            dhpre = ops.gelu_bwd(hpre, ops.rows_linear_bwd_data(dX, f3w))
+            grads[o + 6], grads[o + 7] = ops.rows_linear_bwd_weight(y2, dhpre)
+            d1, grads[o + 4], grads[o + 5] = ops.layernorm_bwd(X1, ops.rows_linear_bwd_data(dhpre, f1w), f0w, mf, rf)
+            dX1 = ops.add(dX, d1)
+            grads[o + 3], _ = ops.rows_linear_bwd_weight(O, dX1, bias=False)
+            dqkv = ops.attention_bwd(qkv, Pm, ops.rows_linear_bwd_data(dX1, outw), B, n)
+            grads[o + 2], _ = ops.rows_linear_bwd_weight(y, dqkv, bias=False)
+            d0, grads[o], grads[o + 1] = ops.layernorm_bwd(X, ops.rows_linear_bwd_data(dqkv, qkvw), anw, ma, ra)
+            dX = ops.add(dX1, d0)
+        tok, m0, r0, y0, e, m1, r1 = S[:7]
+        de, grads[4], grads[5] = ops.layernorm_bwd(e, dX, ln1w, m1, r1)
+        grads[2], grads[3] = ops.rows_linear_bwd_weight(y0, de)
+        dtok, grads[0], grads[1] = ops.layernorm_bwd(tok, ops.rows_linear_bwd_data(de, pew), ln0w, m0, r0)
+        ops.patchify_inv(dtok, c, H, W, p1, p2, out=dx, accumulate=True)          # dx[:, :c] += the conditioner's input gradient
+        return (dx if ctx.needs_input_grad[0] else None, None, *grads)

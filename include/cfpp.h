@@ -380,6 +380,33 @@ int cfpp_gmm_train_bwd(const float* x, int64_t x_bstride, const float* mG, const
                        const float* resp, const float* g, float* dx, int64_t dx_bstride, float* dmG, float* dsG, float* dwG,
                        float* workspace, int B, int M, int K, int n, void* stream);
 
+/* ---- training direction of the SimpleViT conditioner (layers/simple_vit.py:30-127): SURVEY §8(f)-1 --------------------- */
+/* Row-major token rows X (R = B * n_tok, F features).  Each entry is one op of the reference's module stack, forward with the
+ * activations its backward needs, and the backward torch autograd would derive.  Reductions over rows are deterministic.
+ * patchify: 'b c (h p1) (w p2) -> (b h w) (p1 p2 c)' (simple_vit.py:102); x read through a batch stride.  _inv: the inverse
+ * permutation (the un-patchify of TransCoupling / the adjoint of patchify), stored or accumulated through a batch stride. */
+int cfpp_patchify_fwd(const float* x, int64_t x_bstride, float* tok, int B, int c, int H, int W, int p1, int p2, void* stream);
+int cfpp_patchify_inv(const float* tok, float* x, int64_t x_bstride, int accumulate, int B, int c, int H, int W, int p1, int p2, void* stream);
+/* nn.LayerNorm(F) (eps 1e-5, biased variance): y, and mean / rstd per row for the backward.  F <= 256. */
+int cfpp_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int64_t R, int F, void* stream);
+int64_t cfpp_layernorm_bwd_workspace_floats(int64_t R, int F);
+int cfpp_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* mean, const float* rstd,
+                       float* dx, float* dgamma, float* dbeta, float* workspace, int64_t R, int F, void* stream);
+/* nn.Linear(I -> J): y = x W^T (+ bias), W (J, I) torch layout; its input gradient dx = dy W (stored or accumulated); dW = dy^T x, db. */
+int cfpp_rows_linear_fwd(const float* x, const float* W, const float* bias, float* y, int64_t R, int I, int J, void* stream);
+int cfpp_rows_linear_bwd_data(const float* dy, const float* W, float* dx, int accumulate, int64_t R, int I, int J, void* stream);
+int64_t cfpp_rows_linear_bwd_weight_workspace_floats(int64_t R, int I, int J);
+int cfpp_rows_linear_bwd_weight(const float* x, const float* dy, float* dW, float* db, float* workspace, int64_t R, int I, int J, void* stream);
+/* nn.GELU() (erf form) and its derivative on the saved pre-activation. */
+int cfpp_gelu_fwd(const float* x, float* y, int64_t n, void* stream);
+int cfpp_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);
+/* x[r] += pos[r mod n_tok]  (the sincos position table, simple_vit.py:121). */
+int cfpp_add_pos(float* x, const float* pos, int64_t R, int n_tok, int F, void* stream);
+/* Single-head attention per sample (simple_vit.py:45-60, heads = 1, dim_head = 64): qkv rows (n_tok, 192) = [q | k | v];
+ * P (B, n, n) = softmax(q k^T / 8) is saved; O = P v.  bwd: dqkv from dO. */
+int cfpp_attention_fwd(const float* qkv, float* O, float* P, int B, int n_tok, void* stream);
+int cfpp_attention_bwd(const float* qkv, const float* P, const float* dO, float* dqkv, int B, int n_tok, void* stream);
+
 /* ---- container ------------------------------------------------------------------------------------------------ */
 /* FlowSequential.forward, layers/flowsequential.py:23: logdet (B,M) += ldj (B,cols) with cols = 1 (broadcast) or M. */
 int cfpp_ldj_accumulate(float* logdet, const float* ldj, int B, int M, int cols, void* stream);

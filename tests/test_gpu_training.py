@@ -7,6 +7,7 @@ import pytest
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+import torch.nn.functional as F_
 
 from contextflow_b200 import builder, ops, rng, synth, training
 from oracle import flow_oracle as O
@@ -60,7 +61,7 @@ def test_gradients_match_reference_golden(name):
         assert abs(pd.abs().sum().item() - ref[1]) <= 2.5e-3 * pd.numel() + 1e-5 * ref[1], f'{name} AdamW step {k}'
 
 
-@pytest.mark.parametrize('name,B', [('cfg1', 37), ('msl_conv_gen', 50), ('cifar_gen', 21)])
+@pytest.mark.parametrize('name,B', [('cfg1', 37), ('msl_conv_gen', 50), ('cifar_gen', 21), ('cfg4', 50), ('atm_gen', 17)])
 def test_gradients_match_oracle_autograd_fresh_inputs(name, B):
     case = dict(CASES[name], B=B, iseed='in5', nseed='noise5')
     spec = TRAINING_CASES[name]
@@ -219,7 +220,65 @@ def test_backward_is_deterministic():
 
 
 def test_unsupported_layers_raise_under_autograd():
-    model = build_cuda_model(CASES['cfg4']).train()            # ViT conditioner: no backward kernels yet
-    x, ctx = case_inputs(CASES['cfg4'])
+    model = build_cuda_model(CASES['cfg2_init']).train()       # context-conditioned (specialist) layers: no backward kernels yet
+    x, ctx = case_inputs(CASES['cfg2_init'])
     with pytest.raises(NotImplementedError):
         model.log_prob(x.cuda(), ctx.cuda())
+
+
+# ---- op-level: the ViT training kernels against torch float64 autograd ------------------------------------------------------------------
+@pytest.mark.parametrize('R,F', [(37, 52), (300, 152), (5, 26), (2048, 192)])
+def test_layernorm_kernels(R, F):
+    x = synth.normal('lnx', (R, F)) * 1.5 + 0.3; g = 1.0 + 0.2 * synth.normal('lng', (F,)); b = 0.1 * synth.normal('lnb', (F,)); dy = synth.normal('lnd', (R, F))
+    xd, gd, bd = (t.double().requires_grad_(True) for t in (x, g, b))
+    ref = F_.layer_norm(xd, (F,), gd, bd, 1e-5)
+    (ref * dy.double()).sum().backward()
+    y, m, r = ops.layernorm_fwd(x.cuda(), g.cuda(), b.cuda())
+    assert_close(y.cpu().numpy(), ref.detach().numpy(), 1e-5, 1e-5, 'ln fwd')
+    dx, dg, db = ops.layernorm_bwd(x.cuda(), dy.cuda(), g.cuda(), m, r)
+    assert_close(dx.cpu().numpy(), xd.grad.numpy(), 1e-4, 1e-5, 'ln dx')
+    assert_close(dg.cpu().numpy(), gd.grad.numpy(), 1e-4, 1e-4 * float(gd.grad.abs().max()), 'ln dgamma')
+    assert_close(db.cpu().numpy(), bd.grad.numpy(), 1e-4, 1e-4 * float(bd.grad.abs().max()), 'ln dbeta')
+
+
+@pytest.mark.parametrize('R,I,J', [(37, 26, 52), (1000, 152, 192), (70, 64, 152), (3, 7, 5)])
+def test_rows_linear_kernels(R, I, J):
+    x = synth.normal('rlx', (R, I)); w = synth.normal('rlw', (J, I)) * 0.2; b = synth.normal('rlb', (J,)) * 0.1; dy = synth.normal('rld', (R, J))
+    xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
+    ref = xd @ wd.t() + bd
+    (ref * dy.double()).sum().backward()
+    assert_close(ops.rows_linear(x.cuda(), w.cuda(), b.cuda()).cpu().numpy(), ref.detach().numpy(), 1e-5, 1e-5, 'linear fwd')
+    assert_close(ops.rows_linear_bwd_data(dy.cuda(), w.cuda()).cpu().numpy(), xd.grad.numpy(), 1e-5, 1e-5, 'linear dx')
+    dW, db = ops.rows_linear_bwd_weight(x.cuda(), dy.cuda())
+    assert_close(dW.cpu().numpy(), wd.grad.numpy(), 1e-4, 1e-4 * float(wd.grad.abs().max()), 'linear dW')
+    assert_close(db.cpu().numpy(), bd.grad.numpy(), 1e-4, 1e-4 * float(bd.grad.abs().max()), 'linear db')
+
+
+@pytest.mark.parametrize('B,n', [(5, 4), (3, 38), (2, 1), (7, 9)])
+def test_attention_kernels(B, n):
+    qkv = synth.normal('atq', (B * n, 192)); dO = synth.normal('atd', (B * n, 64))
+    qd = qkv.double().requires_grad_(True)
+    t = qd.view(B, n, 192)
+    q, k, v = t[..., :64], t[..., 64:128], t[..., 128:]
+    ref = torch.softmax(q @ k.transpose(-1, -2) * 64 ** -0.5, -1) @ v
+    (ref * dO.double().view(B, n, 64)).sum().backward()
+    O, P = ops.attention_fwd(qkv.cuda(), B, n)
+    assert_close(O.cpu().numpy(), ref.detach().reshape(B * n, 64).numpy(), 1e-4, 1e-5, 'attention fwd')
+    dqkv = ops.attention_bwd(qkv.cuda(), P, dO.cuda(), B, n)
+    assert_close(dqkv.cpu().numpy(), qd.grad.numpy(), 1e-4, 1e-5, 'attention bwd')
+
+
+def test_gelu_and_patchify_kernels():
+    x = synth.normal('gex', (1000,)) * 2; dy = synth.normal('ged', (1000,))
+    xd = x.double().requires_grad_(True)
+    ref = F_.gelu(xd); (ref * dy.double()).sum().backward()
+    assert_close(ops.gelu_fwd(x.cuda()).cpu().numpy(), ref.detach().numpy(), 1e-5, 1e-6, 'gelu')
+    assert_close(ops.gelu_bwd(x.cuda(), dy.cuda()).cpu().numpy(), xd.grad.numpy(), 1e-4, 1e-6, 'gelu bwd')
+    img = synth.normal('pax', (3, 7, 8, 2))
+    tok = ops.patchify(img.cuda(), 5, 2, 1)                                   # first 5 of 7 channels, read in place
+    ref = img[:, :5].reshape(3, 5, 4, 2, 2, 1).permute(0, 2, 4, 3, 5, 1).reshape(3 * 8, 10)
+    assert torch.equal(tok.cpu(), ref)
+    assert torch.equal(ops.patchify_inv(tok, 5, 8, 2, 2, 1).cpu(), img[:, :5])
+    wide = torch.ones(3, 7, 8, 2, device='cuda')
+    ops.patchify_inv(tok, 5, 8, 2, 2, 1, out=wide, accumulate=True)
+    assert torch.equal(wide[:, :5].cpu(), img[:, :5] + 1) and torch.equal(wide[:, 5:].cpu(), torch.ones(3, 2, 8, 2))
