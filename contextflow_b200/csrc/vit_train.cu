@@ -97,6 +97,7 @@ __global__ void ln_finish_kernel(const float* __restrict__ part, float* __restri
   for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) {
     const int which = i / F, f = i - which * F;
     float s = 0.f;
+#pragma unroll 8
     for (int c = 0; c < ctas; ++c) s += part[((int64_t)c * 2 + which) * F + f];
     (which ? dbeta : dgamma)[f] = s;
   }
@@ -105,6 +106,7 @@ __global__ void ln_finish_kernel(const float* __restrict__ part, float* __restri
 __global__ void chunk_sum_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int chunks) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
+#pragma unroll 8
     for (int c = 0; c < chunks; ++c) s += part[(int64_t)c * n + i];
     out[i] = s;
   }
@@ -112,68 +114,102 @@ __global__ void chunk_sum_kernel(const float* __restrict__ part, float* __restri
 
 // ---- row GEMMs.  TRANS = 0: OUT[r][j] = sum_i IN[r][i] W[j][i] (+ b[j])   (nn.Linear forward, W is (J, I))
 //                  TRANS = 1: OUT[r][j] = sum_i IN[r][i] W[i][j]            (its input gradient, W is (I, J))
-// CTA = 64 rows staged in shared memory (odd stride); thread = one row x 4 output columns per pass, weights by warp-uniform loads.
+// CTA = 64 rows x 64 output columns; IN rows and the weight tile (i-major) live in shared memory; thread = 4 rows x 4 columns:
+// per i, four broadcast loads of x and one 128-bit load of four weights feed 16 FMAs.
+constexpr int kWS = 68;             // padded width of the weight tile rows (floats): 16-byte aligned, conflict-free 128-bit reads
 template <int TRANS>
 __global__ void __launch_bounds__(256) rows_linear_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
                                                           float* __restrict__ out, int64_t R, int I, int J, int accumulate) {
-  extern __shared__ float sin_[];
+  extern __shared__ float4 sm4[];
+  float* ws = reinterpret_cast<float*>(sm4);          // [I][kWS]
+  float* xs = ws + (size_t)I * kWS;                   // [64][I | 1]
   const int S = I | 1;
   const int64_t r0 = (int64_t)blockIdx.x * 64;
-  const int rows = (int)min((int64_t)64, R - r0);
-  for (int i = threadIdx.x; i < rows * I; i += blockDim.x) { const int r = i / I, k = i - r * I; sin_[r * S + k] = in[(r0 + r) * I + k]; }
+  const int j0 = blockIdx.y * 64;
+  const int rows = (int)min((int64_t)64, R - r0), cols = min(64, J - j0);
+  for (int i = threadIdx.x; i < 64 * I; i += blockDim.x) { const int r = i / I, k = i - r * I; xs[r * S + k] = r < rows ? in[(r0 + r) * I + k] : 0.f; }
+  if (TRANS) {
+    for (int e = threadIdx.x; e < I * 64; e += blockDim.x) { const int i = e >> 6, jj = e & 63; ws[i * kWS + jj] = jj < cols ? W[(int64_t)i * J + j0 + jj] : 0.f; }
+  } else {
+    for (int e = threadIdx.x; e < I * 64; e += blockDim.x) { const int jj = e / I, i = e - jj * I; ws[i * kWS + jj] = jj < cols ? W[(int64_t)(j0 + jj) * I + i] : 0.f; }
+  }
   __syncthreads();
-  const int r = threadIdx.x & 63, jq = threadIdx.x >> 6;
-  if (r >= rows) return;
-  const float* xr = sin_ + r * S;
-  for (int j0 = jq * 4; j0 < J; j0 += 16) {
-    float acc[4];
+  const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
+  float acc[4][4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[c] = (bias && j0 + c < J) ? bias[j0 + c] : 0.f;
-    const int nc = min(4, J - j0);
-    for (int i = 0; i < I; ++i) {
-      const float xv = xr[i];
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < nc) acc[c] = fmaf(xv, TRANS ? __ldg(W + (int64_t)i * J + j0 + c) : __ldg(W + (int64_t)(j0 + c) * I + i), acc[c]);
-      }
+    for (int c = 0; c < 4; ++c) acc[a][c] = (bias && 4 * tc + c < cols) ? bias[j0 + 4 * tc + c] : 0.f;
+  const float* x0 = xs + (4 * tr) * S;
+#pragma unroll 4
+  for (int i = 0; i < I; ++i) {
+    const float4 w = *reinterpret_cast<const float4*>(ws + i * kWS + 4 * tc);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const float xv = x0[a * S + i];
+      acc[a][0] = fmaf(xv, w.x, acc[a][0]); acc[a][1] = fmaf(xv, w.y, acc[a][1]);
+      acc[a][2] = fmaf(xv, w.z, acc[a][2]); acc[a][3] = fmaf(xv, w.w, acc[a][3]);
     }
+  }
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (c < nc) { float* o = out + (r0 + r) * J + j0 + c; *o = accumulate ? *o + acc[c] : acc[c]; }
+  for (int a = 0; a < 4; ++a) {
+    const int r = 4 * tr + a;
+    if (r >= rows) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = 4 * tc + c;
+      if (j < cols) { float* o = out + (r0 + r) * J + j0 + j; *o = accumulate ? *o + acc[a][c] : acc[a][c]; }
+    }
   }
 }
 
 // dW[j][i] = sum_r dY[r][j] X[r][i], db[j] = sum_r dY[r][j] over a chunk of rows -> part[chunk][J*I], partb[chunk][J].
-// grid (chunks, ceil(J / 16)); thread = output row j (16 per CTA) x input columns {kq, kq + 16, ...}.
-constexpr int kWI = 16;             // up to 16 * 16 = 256 input columns
+// grid (chunks, J tiles x I tiles of 64 x 64); thread = 4 output rows j x 4 input columns i; per row of the chunk two 128-bit shared
+// loads feed 16 FMAs.
 __global__ void __launch_bounds__(256) rows_wgrad_kernel(const float* __restrict__ X, const float* __restrict__ dY, float* __restrict__ part,
-                                                         float* __restrict__ partb, int64_t R, int I, int J, int64_t per_chunk) {
-  __shared__ float sx[32][kMaxF + 1];
-  __shared__ float sdy[32][17];
-  const int jn = threadIdx.x >> 4, kq = threadIdx.x & 15;
-  const int j0 = blockIdx.y * 16, j = j0 + jn;
+                                                         float* __restrict__ partb, int64_t R, int I, int J, int64_t per_chunk, int itiles) {
+  __shared__ float4 sx4[32 * kWS / 4];
+  __shared__ float4 sd4[32 * kWS / 4];
+  float* sx = reinterpret_cast<float*>(sx4); float* sd = reinterpret_cast<float*>(sd4);
+  const int jt = blockIdx.y / itiles, it = blockIdx.y - jt * itiles;
+  const int j0 = jt * 64, i0 = it * 64;
+  const int tj = threadIdx.x >> 4, ti = threadIdx.x & 15;
   const int64_t rbeg = (int64_t)blockIdx.x * per_chunk, rend = min(R, rbeg + per_chunk);
-  float acc[kWI];
+  float acc[4][4];
 #pragma unroll
-  for (int t = 0; t < kWI; ++t) acc[t] = 0.f;
-  float bacc = 0.f;
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int64_t rt = rbeg; rt < rend; rt += 32) {
     const int rows = (int)min((int64_t)32, rend - rt);
     __syncthreads();
-    for (int i = threadIdx.x; i < rows * I; i += blockDim.x) { const int r = i / I, k = i - r * I; sx[r][k] = X[(rt + r) * I + k]; }
-    for (int i = threadIdx.x; i < rows * 16; i += blockDim.x) { const int r = i >> 4, c = i & 15; sdy[r][c] = j0 + c < J ? dY[(rt + r) * J + j0 + c] : 0.f; }
+    for (int e = threadIdx.x; e < 32 * 64; e += blockDim.x) {
+      const int r = e >> 6, c = e & 63;
+      sx[r * kWS + c] = (r < rows && i0 + c < I) ? X[(rt + r) * I + i0 + c] : 0.f;
+      sd[r * kWS + c] = (r < rows && j0 + c < J) ? dY[(rt + r) * J + j0 + c] : 0.f;
+    }
     __syncthreads();
-    for (int r = 0; r < rows; ++r) {
-      const float g = sdy[r][jn];
-      if (kq == 0) bacc += g;
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      const float4 g = *reinterpret_cast<const float4*>(sd + r * kWS + 4 * tj);
+      const float4 x = *reinterpret_cast<const float4*>(sx + r * kWS + 4 * ti);
+      const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-      for (int t = 0; t < kWI; ++t) { const int k = kq + 16 * t; if (k < I) acc[t] = fmaf(g, sx[r][k], acc[t]); }
+      for (int a = 0; a < 4; ++a) {
+        acc[a][0] = fmaf(gv[a], x.x, acc[a][0]); acc[a][1] = fmaf(gv[a], x.y, acc[a][1]);
+        acc[a][2] = fmaf(gv[a], x.z, acc[a][2]); acc[a][3] = fmaf(gv[a], x.w, acc[a][3]);
+        bacc[a] += gv[a];
+      }
     }
   }
-  if (j < J) {
 #pragma unroll
-    for (int t = 0; t < kWI; ++t) { const int k = kq + 16 * t; if (k < I) part[((int64_t)blockIdx.x * J + j) * I + k] = acc[t]; }
-    if (kq == 0 && partb) partb[(int64_t)blockIdx.x * J + j] = bacc;
+  for (int a = 0; a < 4; ++a) {
+    const int j = j0 + 4 * tj + a;
+    if (j >= J) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { const int i = i0 + 4 * ti + c; if (i < I) part[((int64_t)blockIdx.x * J + j) * I + i] = acc[a][c]; }
+    if (ti == 0 && it == 0 && partb) partb[(int64_t)blockIdx.x * J + j] = bacc[a];
   }
 }
 
@@ -285,10 +321,10 @@ inline int grid1d(int64_t n, int per_thread = 1) {
   if (blocks > cap) blocks = cap;
   return (int)(blocks < 1 ? 1 : blocks);
 }
-inline int ln_bwd_ctas(int64_t R) { int64_t c = (R + 7) / 8; const int64_t cap = (int64_t)num_sms() * 4; return (int)(c > cap ? cap : (c < 1 ? 1 : c)); }
-inline void wgrad_plan(int64_t R, int J, int& chunks, int64_t& per_chunk) {
-  const int jb = (J + 15) / 16;
-  int64_t c = ((int64_t)num_sms() * 4 + jb - 1) / jb;
+inline int ln_bwd_ctas(int64_t R) { int64_t c = (R + 7) / 8; const int64_t cap = (int64_t)num_sms(); return (int)(c > cap ? cap : (c < 1 ? 1 : c)); }
+inline void wgrad_plan(int64_t R, int I, int J, int& chunks, int64_t& per_chunk) {
+  const int jb = ((J + 63) / 64) * ((I + 63) / 64);
+  int64_t c = ((int64_t)num_sms() * 2 + jb - 1) / jb;
   const int64_t maxc = (R + 31) / 32;
   if (c > maxc) c = maxc; if (c < 1) c = 1;
   per_chunk = ((R + c - 1) / c + 31) / 32 * 32;
@@ -340,10 +376,10 @@ extern "C" int cfpp_layernorm_bwd(const float* x, const float* dy, const float* 
 extern "C" int cfpp_rows_linear_fwd(const float* x, const float* W, const float* bias, float* y, int64_t R, int I, int J, void* stream) {
   CFPP_REQUIRE(I >= 1 && I <= kMaxF && J >= 1, "rows_linear: I=%d J=%d", I, J);
   if (R <= 0) return CFPP_OK;
-  const size_t smem = (size_t)64 * (I | 1) * sizeof(float);
+  const size_t smem = ((size_t)64 * (I | 1) + (size_t)I * kWS) * sizeof(float);
   static bool a = false;
-  if (!a) { cudaFuncSetAttribute(rows_linear_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * (kMaxF + 1) * 4); a = true; }
-  rows_linear_kernel<0><<<(unsigned)((R + 63) / 64), 256, smem, (cudaStream_t)stream>>>(x, W, bias, y, R, I, J, 0);
+  if (!a) { cudaFuncSetAttribute(rows_linear_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * (kMaxF + 1) + kMaxF * kWS) * 4); a = true; }
+  rows_linear_kernel<0><<<dim3((unsigned)((R + 63) / 64), (J + 63) / 64), 256, smem, (cudaStream_t)stream>>>(x, W, bias, y, R, I, J, 0);
   return check_launch("rows_linear_fwd");
 }
 
@@ -351,16 +387,16 @@ extern "C" int cfpp_rows_linear_bwd_data(const float* dy, const float* W, float*
   // W is the forward weight (J, I); dx[r][i] = sum_j dy[r][j] W[j][i]
   CFPP_REQUIRE(J >= 1 && J <= kMaxF && I >= 1, "rows_linear_bwd_data: I=%d J=%d", I, J);
   if (R <= 0) return CFPP_OK;
-  const size_t smem = (size_t)64 * (J | 1) * sizeof(float);
+  const size_t smem = ((size_t)64 * (J | 1) + (size_t)J * kWS) * sizeof(float);
   static bool a = false;
-  if (!a) { cudaFuncSetAttribute(rows_linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * (kMaxF + 1) * 4); a = true; }
-  rows_linear_kernel<1><<<(unsigned)((R + 63) / 64), 256, smem, (cudaStream_t)stream>>>(dy, W, nullptr, dx, R, J, I, accumulate);
+  if (!a) { cudaFuncSetAttribute(rows_linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * (kMaxF + 1) + kMaxF * kWS) * 4); a = true; }
+  rows_linear_kernel<1><<<dim3((unsigned)((R + 63) / 64), (I + 63) / 64), 256, smem, (cudaStream_t)stream>>>(dy, W, nullptr, dx, R, J, I, accumulate);
   return check_launch("rows_linear_bwd_data");
 }
 
 extern "C" int64_t cfpp_rows_linear_bwd_weight_workspace_floats(int64_t R, int I, int J) {
   int chunks; int64_t per_chunk;
-  wgrad_plan(R, J, chunks, per_chunk);
+  wgrad_plan(R, I, J, chunks, per_chunk);
   return (int64_t)chunks * ((int64_t)J * I + J);
 }
 
@@ -368,9 +404,10 @@ extern "C" int cfpp_rows_linear_bwd_weight(const float* x, const float* dy, floa
                                            int64_t R, int I, int J, void* stream) {
   CFPP_REQUIRE(I >= 1 && I <= kMaxF && J >= 1 && R >= 1 && workspace, "rows_linear_bwd_weight: R=%lld I=%d J=%d", (long long)R, I, J);
   int chunks; int64_t per_chunk;
-  wgrad_plan(R, J, chunks, per_chunk);
+  wgrad_plan(R, I, J, chunks, per_chunk);
   float* part = workspace; float* partb = workspace + (int64_t)chunks * J * I;
-  rows_wgrad_kernel<<<dim3(chunks, (J + 15) / 16), 256, 0, (cudaStream_t)stream>>>(x, dy, part, db ? partb : nullptr, R, I, J, per_chunk);
+  const int itiles = (I + 63) / 64;
+  rows_wgrad_kernel<<<dim3(chunks, ((J + 63) / 64) * itiles), 256, 0, (cudaStream_t)stream>>>(x, dy, part, db ? partb : nullptr, R, I, J, per_chunk, itiles);
   int rc = check_launch("rows_linear_bwd_weight");
   if (rc != CFPP_OK) return rc;
   chunk_sum_kernel<<<grid1d((int64_t)J * I), 256, 0, (cudaStream_t)stream>>>(part, dW, (int64_t)J * I, chunks);
