@@ -294,21 +294,40 @@ __global__ void __launch_bounds__(256) conv2d_bwd_weight_kernel(const float* __r
     bool on[PPT];
 #pragma unroll
     for (int k = 0; k < PPT; ++k) { const int co = cog + k * cpp; on[k] = co < nco; gp[k] = sd + (on[k] ? co : 0) * Sg; }
-    for (int y = 0; y < H; ++y)
-      for (int x = 0; x < Wd; ++x) {
-        float v[KK];
+    if (on[PPT - 1]) {                                   // all PPT output channels of this thread exist
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < Wd; ++x) {
+          float v[KK];
 #pragma unroll
-        for (int kh = 0; kh < KH; ++kh)
+          for (int kh = 0; kh < KH; ++kh)
 #pragma unroll
-          for (int kw = 0; kw < KW; ++kw) v[kh * KW + kw] = ip[(y + kh) * Wp + x + kw];
-        const int p = y * Wd + x;
+            for (int kw = 0; kw < KW; ++kw) v[kh * KW + kw] = ip[(y + kh) * Wp + x + kw];
+          const int p = y * Wd + x;
 #pragma unroll
-        for (int k = 0; k < PPT; ++k) {
-          const float g = gp[k][p];
+          for (int k = 0; k < PPT; ++k) {
+            const float g = gp[k][p];
 #pragma unroll
-          for (int t = 0; t < KK; ++t) acc[k][t] = fmaf(g, v[t], acc[k][t]);
+            for (int t = 0; t < KK; ++t) acc[k][t] = fmaf(g, v[t], acc[k][t]);
+          }
         }
-      }
+    } else {                                             // narrow layers (Cout < channels per pass x PPT): only the live ones
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < Wd; ++x) {
+          float v[KK];
+#pragma unroll
+          for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < KW; ++kw) v[kh * KW + kw] = ip[(y + kh) * Wp + x + kw];
+          const int p = y * Wd + x;
+#pragma unroll
+          for (int k = 0; k < PPT; ++k) {
+            if (!on[k]) break;
+            const float g = gp[k][p];
+#pragma unroll
+            for (int t = 0; t < KK; ++t) acc[k][t] = fmaf(g, v[t], acc[k][t]);
+          }
+        }
+    }
   }
   if (live) {
 #pragma unroll

@@ -48,14 +48,16 @@ class Conv1x1(FlowLayer):
             return ops.conv1x1(x, self.NN.detach(), lad, cm, logp_c, self.contextflow)
         return ops.conv1x1(x, self.NN.detach(), lad)
 
-    def inverse_matrix(self):
-        """torch.inverse(NN) (conv1x1.py:70), recomputed only when NN changes; a singular NN raises like torch.inverse does."""
-        def build():
-            inv, flag = ops.mat_inverse(self.NN.detach())
+    def inverse_matrix(self, check=True):
+        """torch.inverse(NN) (conv1x1.py:70), recomputed only when NN changes.  check=True (the sampling direction): a singular NN raises
+        like torch.inverse does -- one device read per weight version; check=False (the training backward, every step a new version):
+        no host synchronisation, a singular NN shows up as inf/nan gradients exactly as in torch."""
+        inv, flag = self._packs.get('inverse', [self.NN], lambda: ops.mat_inverse(self.NN.detach()))
+        if check and not getattr(self, '_inv_checked', None) == self.NN._version:
             if int(flag.item()):
                 raise RuntimeError('Conv1x1.reverse: NN is singular')
-            return inv
-        return self._packs.get('inverse', [self.NN], build)
+            self._inv_checked = self.NN._version
+        return inv
 
     def reverse(self, z, context=None):
         """conv1x1.py:59-72.  Only the context-free branch is executable in the reference: its context branch reads

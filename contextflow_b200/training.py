@@ -77,7 +77,7 @@ class Conv1x1Fn(Function):
             dNN, _ = ops.conv2d_bwd_weight(x, D, dz, (D, D, 1, 1), bias=False)
             dNN = dNN.view(D, D)
             if dldj is not None:
-                ops.logdet_grad_(dNN, ctx.layer.inverse_matrix(), dldj.contiguous(), H * W)
+                ops.logdet_grad_(dNN, ctx.layer.inverse_matrix(check=False), dldj.contiguous(), H * W)
         dx = ops.conv2d_bwd_data(dz, w4) if ctx.needs_input_grad[0] else None
         return dx, dNN, None
 
