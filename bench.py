@@ -32,6 +32,9 @@ def parse():
     ap.add_argument('--ref-device', default='cpu', choices=['cpu', 'cuda'],
                     help='--impl reference only: cpu (the contract: host cores) or cuda (the same torch op sequence run eagerly on the GPU, '
                          'the "reference torch-on-CUDA" figure of the north star; informative)')
+    ap.add_argument('--path', default='log_prob', choices=['log_prob', 'train', 'reverse'],
+                    help='log_prob (default): the headline forward log-density path; train / reverse: the SURVEY §8(f) rows, measured by '
+                         'tools/bench_training.py / tools/bench_inverse.py (their own JSON lines)')
     ap.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying the captured CUDA graph')
     return ap.parse_args()
 
@@ -146,6 +149,19 @@ def cpu_reference_run(workload, batch, steps, warmup, device='cpu'):
 
 def main():
     a = parse()
+    if a.path != 'log_prob':                       # the "next" rows have their own measurement tools; same launch conventions (torchrun for N > 1)
+        import runpy
+        tool = 'bench_training.py' if a.path == 'train' else 'bench_inverse.py'
+        argv = [tool, '--steps', str(a.steps)]
+        if a.path == 'train':
+            argv += ['--warmup', str(a.warmup), '--impl', a.impl, '--workload', a.workload if a.workload in ('cfg1', 'cfg4') else 'cfg1']
+            if a.batch:
+                argv += ['--batch', str(a.batch)]
+            if a.impl == 'reference':
+                argv += ['--ref-device', a.ref_device]
+        sys.argv = argv
+        runpy.run_path(os.path.join(ROOT, 'tools', tool), run_name='__main__')
+        return
     rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1)); local = int(os.environ.get('LOCAL_RANK', 0))
     workload = a.workload
 

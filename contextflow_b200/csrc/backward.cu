@@ -341,11 +341,19 @@ __global__ void __launch_bounds__(256) conv2d_bwd_weight_kernel(const float* __r
   if (db && (int)threadIdx.x < nco) db[co0 + threadIdx.x] = bsum;
 }
 
-__global__ void chunk_sum_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int chunks) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+// out[i] = sum_c part[c][i]: a CTA covers 32 consecutive outputs; warp w sums chunks w, w+8, ..., the eight warp partials are added
+// in warp order -- a fixed order, so the result is deterministic
+__global__ void __launch_bounds__(256) chunk_sum_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int chunks) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int64_t i0 = (int64_t)blockIdx.x * 32; i0 < n; i0 += (int64_t)gridDim.x * 32) {
+    const int64_t i = i0 + lane;
     float s = 0.f;
-    for (int c = 0; c < chunks; ++c) s += part[(int64_t)c * n + i];
-    out[i] = s;
+    if (i < n) for (int c = w; c < chunks; c += 8) s += part[(int64_t)c * n + i];
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && i < n) { float t = 0.f; for (int q = 0; q < 8; ++q) t += red[q][lane]; out[i] = t; }
+    __syncthreads();
   }
 }
 
@@ -644,10 +652,10 @@ extern "C" int cfpp_conv2d_bwd_weight(const float* in, int64_t in_bstride, const
   });
   int rc = check_launch("conv2d_bwd_weight");
   if (rc != CFPP_OK) return rc;
-  chunk_sum_kernel<<<grid1d(nW), 256, 0, (cudaStream_t)stream>>>(partW, dW, nW, chunks);
+  chunk_sum_kernel<<<(unsigned)((nW + 31) / 32), 256, 0, (cudaStream_t)stream>>>(partW, dW, nW, chunks);
   if ((rc = check_launch("conv2d_bwd_weight_sum")) != CFPP_OK) return rc;
   if (db) {
-    chunk_sum_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partb, db, Cout, chunks);
+    chunk_sum_kernel<<<(Cout + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partb, db, Cout, chunks);
     rc = check_launch("conv2d_bwd_bias_sum");
   }
   return rc;

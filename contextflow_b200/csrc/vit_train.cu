@@ -93,22 +93,31 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x
   }
 }
 
-__global__ void ln_finish_kernel(const float* __restrict__ part, float* __restrict__ dgamma, float* __restrict__ dbeta, int F, int ctas) {
-  for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) {
+// one warp per output: lane-strided partial sums, then the shuffle tree -- a fixed order, so still deterministic
+__global__ void __launch_bounds__(256) ln_finish_kernel(const float* __restrict__ part, float* __restrict__ dgamma, float* __restrict__ dbeta, int F, int ctas) {
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < 2 * F; i += gridDim.x * 8) {
     const int which = i / F, f = i - which * F;
     float s = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < ctas; ++c) s += part[((int64_t)c * 2 + which) * F + f];
-    (which ? dbeta : dgamma)[f] = s;
+    for (int c = lane; c < ctas; c += 32) s += part[((int64_t)c * 2 + which) * F + f];
+    s = warp_sum(s);
+    if (lane == 0) (which ? dbeta : dgamma)[f] = s;
   }
 }
 
-__global__ void chunk_sum_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int chunks) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+// out[i] = sum_c part[c][i]: a CTA covers 32 consecutive outputs; warp w sums chunks w, w+8, ... (coalesced rows of 32 floats), the
+// eight warp partials are added in warp order -- a fixed order, so still deterministic
+__global__ void __launch_bounds__(256) chunk_sum_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int chunks) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int64_t i0 = (int64_t)blockIdx.x * 32; i0 < n; i0 += (int64_t)gridDim.x * 32) {
+    const int64_t i = i0 + lane;
     float s = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < chunks; ++c) s += part[(int64_t)c * n + i];
-    out[i] = s;
+    if (i < n) for (int c = w; c < chunks; c += 8) s += part[(int64_t)c * n + i];
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && i < n) { float t = 0.f; for (int q = 0; q < 8; ++q) t += red[q][lane]; out[i] = t; }
+    __syncthreads();
   }
 }
 
@@ -369,7 +378,7 @@ extern "C" int cfpp_layernorm_bwd(const float* x, const float* dy, const float* 
   ln_bwd_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(x, dy, gamma, mean, rstd, dx, workspace, R, F);
   int rc = check_launch("layernorm_bwd");
   if (rc != CFPP_OK) return rc;
-  ln_finish_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(workspace, dgamma, dbeta, F, ctas);
+  ln_finish_kernel<<<(2 * F + 7) / 8, 256, 0, (cudaStream_t)stream>>>(workspace, dgamma, dbeta, F, ctas);
   return check_launch("layernorm_bwd_finish");
 }
 
@@ -410,10 +419,10 @@ extern "C" int cfpp_rows_linear_bwd_weight(const float* x, const float* dy, floa
   rows_wgrad_kernel<<<dim3(chunks, ((J + 63) / 64) * itiles), 256, 0, (cudaStream_t)stream>>>(x, dy, part, db ? partb : nullptr, R, I, J, per_chunk, itiles);
   int rc = check_launch("rows_linear_bwd_weight");
   if (rc != CFPP_OK) return rc;
-  chunk_sum_kernel<<<grid1d((int64_t)J * I), 256, 0, (cudaStream_t)stream>>>(part, dW, (int64_t)J * I, chunks);
+  chunk_sum_kernel<<<(unsigned)(((int64_t)J * I + 31) / 32), 256, 0, (cudaStream_t)stream>>>(part, dW, (int64_t)J * I, chunks);
   if ((rc = check_launch("rows_linear_bwd_weight_sum")) != CFPP_OK) return rc;
   if (db) {
-    chunk_sum_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partb, db, J, chunks);
+    chunk_sum_kernel<<<(J + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partb, db, J, chunks);
     rc = check_launch("rows_linear_bwd_bias_sum");
   }
   return rc;
