@@ -103,7 +103,9 @@ _SIGNATURES = {
     'cfpp_gmm_sample': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     'cfpp_score_workspace_bytes': (i64, [i32]),
     'cfpp_score_epilogue': (i32, [vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
-    'cfpp_coupling_bwd': (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    'cfpp_coupling_bwd': (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    'cfpp_conv1x1_ctx_bwd': (i32, [vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, vp]),
+    'cfpp_actnorm_ctx_bwd': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     'cfpp_actnorm_bwd_workspace_floats': (i64, [i32, i32]),
     'cfpp_actnorm_bwd': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     'cfpp_conv2d_fwd': (i32, [vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
@@ -117,6 +119,9 @@ _SIGNATURES = {
     'cfpp_gmm_train_fwd': (i32, [vp, i64, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     'cfpp_gmm_train_bwd_workspace_floats': (i64, [i32, i32, i32, i32]),
     'cfpp_gmm_train_bwd': (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    'cfpp_gmm_ctx_train_fwd': (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    'cfpp_gmm_ctx_train_bwd': (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp]),
+    'cfpp_embed_scatter': (i32, [vp, i64, i32, vp, vp, vp, i32, i32, vp]),
     'cfpp_patchify_fwd': (i32, [vp, i64, vp, i32, i32, i32, i32, i32, i32, vp]),
     'cfpp_patchify_inv': (i32, [vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp]),
     'cfpp_layernorm_fwd': (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp]),

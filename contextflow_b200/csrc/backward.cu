@@ -17,7 +17,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (
 //   dx0 = dz0 (the conditioner's contribution is added by its own backward); dx1 = dz1 e^{ls};
 //   dt = dz1; dr = (dz1 x1 e^{ls} + dldj[b]) (1 - tanh^2(r/2)).          20*C*HW bytes per sample.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) coupling_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
+__global__ void __launch_bounds__(256) coupling_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h, const float* __restrict__ add,
                                                            const float* __restrict__ dz, const float* __restrict__ dldj,
                                                            float* __restrict__ dx, float* __restrict__ dh, int B, int C, int HW, int G) {
   const int spc = blockDim.x / G;
@@ -28,8 +28,9 @@ __global__ void __launch_bounds__(256) coupling_bwd_kernel(const float* __restri
   const float* xb = x + b * 2 * n; const float* hb = h + b * 2 * n; const float* gb = dz + b * 2 * n;
   float* dxb = dx + b * 2 * n; float* dhb = dh + b * 2 * n;
   const float gl = dldj ? dldj[b] : 0.f;
+  const float* ab = add ? add + b * C + C / 2 : nullptr;        // additive context term of the scale half (coupling.py:45)
   for (int64_t i = g; i < n; i += G) {
-    const float r = hb[n + i], x1 = xb[n + i], g0 = gb[i], g1 = gb[n + i];
+    const float r = hb[n + i] + (ab ? ab[i / HW] : 0.f), x1 = xb[n + i], g0 = gb[i], g1 = gb[n + i];
     const float th = tanhf(r * 0.5f);
     const float sc = expf(2.0f * th);
     dxb[i] = g0;
@@ -357,6 +358,78 @@ __global__ void __launch_bounds__(256) chunk_sum_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Context-conditioned (specialist) layers, backward w.r.t. the input and the raw context-network output (conv1x1.py:31-50,
+// actnorm.py:42-58).  The frozen generalist parameters get no gradient in --contextflow mode (requires_grad False in the reference).
+// Conv1x1: W_b = tril(c,-1) + diag(exp(diag c)) [- I + NN];  z = W_b x;  ldj = HW (sum diag c [+ logabsdet NN]) + HW logp_c.
+//   dx = W_b^T dz;  G = dz x^T;  dc[i][j] = G[i][j] (j < i),  exp(c_ii) G[i][i] + HW dldj[b] (j == i),  0 (j > i).
+// One CTA per sample: x, dz (D x HW, odd row stride) and W_b in shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv1x1_ctx_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, const float* __restrict__ c,
+                                                              const float* __restrict__ NN, int contextflow, const float* __restrict__ dldj,
+                                                              float* __restrict__ dx, float* __restrict__ dc, int D, int HW) {
+  extern __shared__ float sm[];
+  const int S = HW | 1, SW = D | 1;
+  float* xs = sm; float* gs = xs + D * S; float* Wb = gs + D * S;          // Wb[i * SW + j]
+  const int64_t b = blockIdx.x;
+  const float* cb = c + b * D * D;
+  for (int i = threadIdx.x; i < D * HW; i += blockDim.x) {
+    const int d = i / HW, p = i - d * HW;
+    xs[d * S + p] = x[b * D * HW + i]; gs[d * S + p] = dz[b * D * HW + i];
+  }
+  for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+    const int i = e / D, j = e - i * D;
+    float v = j < i ? cb[e] : (j == i ? expf(cb[e]) : 0.f);
+    if (contextflow) v = (v - (i == j ? 1.f : 0.f)) + NN[e];
+    Wb[i * SW + j] = v;
+  }
+  __syncthreads();
+  if (dx)
+    for (int e = threadIdx.x; e < D * HW; e += blockDim.x) {
+      const int j = e / HW, p = e - j * HW;
+      float acc = 0.f;
+      for (int i = 0; i < D; ++i) acc = fmaf(Wb[i * SW + j], gs[i * S + p], acc);
+      dx[b * D * HW + e] = acc;
+    }
+  const float gl = dldj ? dldj[b] * (float)HW : 0.f;
+  for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+    const int i = e / D, j = e - i * D;
+    float v = 0.f;
+    if (j <= i) {
+      float acc = 0.f;
+      for (int p = 0; p < HW; ++p) acc = fmaf(gs[i * S + p], xs[j * S + p], acc);
+      v = j < i ? acc : expf(cb[e]) * acc + gl;
+    }
+    dc[b * D * D + e] = v;
+  }
+}
+
+// ActNorm with per-sample context terms: t_b = [NN_t +] c[b,:D], logs_b = [NN_logs +] c[b,D:];  z = (x - t_b) e^{-logs_b};
+// ldj[b] = sum_d logs_b + HW logp_c.   dx = dz e^{-logs_b};  dc[b,d] = -sum_p dz e^{-logs_b};  dc[b,D+d] = -sum_p dz z + dldj[b].
+// One CTA per sample, one warp per channel.
+__global__ void __launch_bounds__(256) actnorm_ctx_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, const float* __restrict__ c,
+                                                              const float* __restrict__ base_t, const float* __restrict__ base_logs,
+                                                              const float* __restrict__ dldj, float* __restrict__ dx, float* __restrict__ dc,
+                                                              int D, int HW) {
+  const int64_t b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float gl = dldj ? dldj[b] : 0.f;
+  for (int d = warp; d < D; d += nw) {
+    const float t = c[b * 2 * D + d] + (base_t ? base_t[d] : 0.f);
+    const float e = expf(-(c[b * 2 * D + D + d] + (base_logs ? base_logs[d] : 0.f)));
+    const int64_t o = (b * D + d) * HW;
+    float a0 = 0.f, a1 = 0.f;
+    for (int p = lane; p < HW; p += 32) {
+      const float g = dz[o + p], ge = g * e;
+      if (dx) dx[o + p] = ge;
+      a0 -= ge;
+      a1 -= g * ((x[o + p] - t) * e);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1);
+    if (lane == 0) { dc[b * 2 * D + d] = a0; dc[b * 2 * D + D + d] = a1 + gl; }
+  }
+}
+
 // elementwise ReLU mask: g *= (act > 0)
 __global__ void relu_mask_kernel(float* __restrict__ g, const float* __restrict__ act, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -529,6 +602,109 @@ __global__ void __launch_bounds__(256) gmm_finish_kernel(const float* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Mixture with per-sample context offsets (gaussian.py:146-155: c = context_net(ctx), 'b (p m k d)': mean + c[0], softplus(sG + c[1])),
+// training direction.  General in the context structure: c (B, 2*M*K*D) is the materialised lookup; the table gradients are a
+// scatter of dc by context value (embed_scatter below).  One CTA per sample; sigma is recomputed where it is needed.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gmm_ctx_fwd_kernel(const float* __restrict__ x, int64_t x_bstride, const float* __restrict__ mG,
+                                                          const float* __restrict__ sG, const float* __restrict__ wG, const float* __restrict__ c,
+                                                          float* __restrict__ logp, float* __restrict__ resp, int M, int K, int D, int HW) {
+  extern __shared__ float sx[];                        // n floats, then M*K comp values
+  const int n = D * HW, MK = M * K;
+  float* comp = sx + n;
+  const int64_t b = blockIdx.x;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) sx[e] = x[b * x_bstride + e];
+  __syncthreads();
+  const float* cm = c + b * 2 * MK * D; const float* cs = cm + (int64_t)MK * D;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int mk = w; mk < MK; mk += nw) {
+    float acc = 0.f;
+    for (int e = l; e < n; e += 32) {
+      const int d = e / HW;
+      const float mu = mG[(int64_t)mk * n + e] + cm[mk * D + d];
+      const float s = softplus_f(sG[(int64_t)mk * n + e] + cs[mk * D + d]);
+      const float df = sx[e] - mu;
+      acc += -0.5f * df * df / (s * s) - logf(s);
+    }
+    acc = warp_sum(acc);
+    if (l == 0) {
+      const int m = mk / K;
+      float mx = -INFINITY;
+      for (int j = 0; j < K; ++j) mx = fmaxf(mx, wG[m * K + j]);
+      float se = 0.f;
+      for (int j = 0; j < K; ++j) se += expf(wG[m * K + j] - mx);
+      comp[mk] = acc + (wG[mk] - mx - logf(se)) - (float)n * kHalfLog2Pi;
+    }
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, comp[m * K + k]);
+    float se = 0.f;
+    for (int k = 0; k < K; ++k) se += expf(comp[m * K + k] - mx);
+    const float lp = mx + logf(se);
+    logp[b * M + m] = lp;
+    for (int k = 0; k < K; ++k) resp[(b * M + m) * K + k] = expf(comp[m * K + k] - lp);
+  }
+}
+
+// w[b,mk] = g[b,m] resp[b,mk];  dx[b,e] = sum_mk w (mu - x) / s^2;  dc_mean[b,mk,d] = sum_hw w (x - mu) / s^2;
+// dc_scale[b,mk,d] = sum_hw w ((x - mu)^2 / s^3 - 1/s) sigmoid(sG + cs).   Warp per (mk, d): lanes over hw, shuffle-tree sums.
+__global__ void __launch_bounds__(256) gmm_ctx_bwd_kernel(const float* __restrict__ x, int64_t x_bstride, const float* __restrict__ mG,
+                                                          const float* __restrict__ sG, const float* __restrict__ c, const float* __restrict__ resp,
+                                                          const float* __restrict__ g, float* __restrict__ dx, int64_t dx_bstride,
+                                                          float* __restrict__ dc, int M, int K, int D, int HW) {
+  extern __shared__ float sx[];                        // n floats x, then M*K weights
+  const int n = D * HW, MK = M * K;
+  float* sw = sx + n;
+  const int64_t b = blockIdx.x;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) sx[e] = x[b * x_bstride + e];
+  for (int i = threadIdx.x; i < MK; i += blockDim.x) sw[i] = g[b * M + i / K] * resp[b * MK + i];
+  __syncthreads();
+  const float* cm = c + b * 2 * MK * D; const float* cs = cm + (int64_t)MK * D;
+  float* dcm = dc + b * 2 * MK * D; float* dcs = dcm + (int64_t)MK * D;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int pair = w; pair < MK * D; pair += nw) {
+    const int mk = pair / D, d = pair - mk * D;
+    const float wt = sw[mk], om = cm[pair], os = cs[pair];
+    float a0 = 0.f, a1 = 0.f;
+    for (int hw = l; hw < HW; hw += 32) {
+      const int e = d * HW + hw;
+      const float raw = sG[(int64_t)mk * n + e] + os;
+      const float s = softplus_f(raw);
+      const float df = sx[e] - (mG[(int64_t)mk * n + e] + om);
+      const float is2 = 1.0f / (s * s);
+      a0 += df * is2;
+      a1 += (df * df * is2 / s - 1.0f / s) * (1.0f / (1.0f + expf(-raw)));
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1);
+    if (l == 0) { dcm[pair] = wt * a0; dcs[pair] = wt * a1; }
+  }
+  if (!dx) return;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int d = e / HW;
+    const float xv = sx[e];
+    float acc = 0.f;
+    for (int mk = 0; mk < MK; ++mk) {
+      const float s = softplus_f(sG[(int64_t)mk * n + e] + cs[mk * D + d]);
+      acc = fmaf(sw[mk] / (s * s), mG[(int64_t)mk * n + e] + cm[mk * D + d] - xv, acc);
+    }
+    dx[b * dx_bstride + e] = acc;
+  }
+}
+
+// dTable[v][col] = sum over the samples whose context feature equals v (bucket order given by a stable sort), of dc[b][col0 + col]
+__global__ void __launch_bounds__(256) embed_scatter_kernel(const float* __restrict__ dc, int64_t dc_stride, int col0, const int64_t* __restrict__ perm,
+                                                            const int64_t* __restrict__ offsets, float* __restrict__ dtable, int width) {
+  const int v = blockIdx.x;
+  const int col = blockIdx.y * blockDim.x + threadIdx.x;
+  if (col >= width) return;
+  float s = 0.f;
+  for (int64_t i = offsets[v]; i < offsets[v + 1]; ++i) s += dc[perm[i] * dc_stride + col0 + col];
+  dtable[(int64_t)v * width + col] = s;
+}
+
 inline int grid1d(int64_t n, int per_thread = 1) {
   int64_t blocks = (n + 256LL * per_thread - 1) / (256LL * per_thread);
   const int64_t cap = (int64_t)num_sms() * 16;
@@ -548,7 +724,7 @@ inline bool want_smem(Kern k, size_t bytes) {
 using namespace cfpp;
 using namespace cfpp::bw;
 
-extern "C" int cfpp_coupling_bwd(const float* x, const float* h, const float* dz, const float* dldj, float* dx, float* dh,
+extern "C" int cfpp_coupling_bwd(const float* x, const float* h, const float* add, const float* dz, const float* dldj, float* dx, float* dh,
                                  int B, int C, int HW, void* stream) {
   CFPP_REQUIRE(C >= 2 && C % 2 == 0 && HW >= 1, "coupling_bwd: C=%d must be even, HW=%d", C, HW);
   if (B <= 0) return CFPP_OK;
@@ -556,7 +732,7 @@ extern "C" int cfpp_coupling_bwd(const float* x, const float* h, const float* dz
   int G = 32;
   while (G < 256 && G * 4 < n) G <<= 1;
   const int spc = 256 / G;
-  coupling_bwd_kernel<<<(B + spc - 1) / spc, 256, 0, (cudaStream_t)stream>>>(x, h, dz, dldj, dx, dh, B, C, HW, G);
+  coupling_bwd_kernel<<<(B + spc - 1) / spc, 256, 0, (cudaStream_t)stream>>>(x, h, add, dz, dldj, dx, dh, B, C, HW, G);
   return check_launch("coupling_bwd");
 }
 
@@ -659,6 +835,51 @@ extern "C" int cfpp_conv2d_bwd_weight(const float* in, int64_t in_bstride, const
     rc = check_launch("conv2d_bwd_bias_sum");
   }
   return rc;
+}
+
+extern "C" int cfpp_conv1x1_ctx_bwd(const float* x, const float* dz, const float* c, const float* NN, int contextflow, const float* dldj,
+                                    float* dx, float* dc, int B, int D, int HW, void* stream) {
+  CFPP_REQUIRE(D >= 1 && HW >= 1 && c && dc && (!contextflow || NN), "conv1x1_ctx_bwd: D=%d HW=%d", D, HW);
+  if (B <= 0) return CFPP_OK;
+  const size_t smem = ((size_t)2 * D * (HW | 1) + (size_t)D * (D | 1)) * sizeof(float);
+  CFPP_REQUIRE(want_smem(conv1x1_ctx_bwd_kernel, smem), "conv1x1_ctx_bwd: sample of %zu bytes exceeds shared memory", smem);
+  conv1x1_ctx_bwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(x, dz, c, NN, contextflow, dldj, dx, dc, D, HW);
+  return check_launch("conv1x1_ctx_bwd");
+}
+
+extern "C" int cfpp_actnorm_ctx_bwd(const float* x, const float* dz, const float* c, const float* base_t, const float* base_logs,
+                                    const float* dldj, float* dx, float* dc, int B, int D, int HW, void* stream) {
+  CFPP_REQUIRE(D >= 1 && HW >= 1 && c && dc, "actnorm_ctx_bwd: D=%d HW=%d", D, HW);
+  if (B <= 0) return CFPP_OK;
+  actnorm_ctx_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, dz, c, base_t, base_logs, dldj, dx, dc, D, HW);
+  return check_launch("actnorm_ctx_bwd");
+}
+
+extern "C" int cfpp_gmm_ctx_train_fwd(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* wG, const float* c,
+                                      float* logp, float* resp, int B, int M, int K, int D, int HW, void* stream) {
+  CFPP_REQUIRE(M >= 1 && K >= 1 && M * K <= kMaxMK && D >= 1 && HW >= 1 && c, "gmm_ctx_train: M*K=%d exceeds %d", M * K, kMaxMK);
+  if (B <= 0) return CFPP_OK;
+  const size_t smem = ((size_t)D * HW + M * K) * sizeof(float);
+  CFPP_REQUIRE(want_smem(gmm_ctx_fwd_kernel, smem), "gmm_ctx_train_fwd: sample of %zu bytes exceeds shared memory", smem);
+  gmm_ctx_fwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(x, x_bstride, mG, sG, wG, c, logp, resp, M, K, D, HW);
+  return check_launch("gmm_ctx_train_fwd");
+}
+
+extern "C" int cfpp_gmm_ctx_train_bwd(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* c, const float* resp,
+                                      const float* g, float* dx, int64_t dx_bstride, float* dc, int B, int M, int K, int D, int HW, void* stream) {
+  CFPP_REQUIRE(M >= 1 && K >= 1 && M * K <= kMaxMK && D >= 1 && HW >= 1 && c && dc, "gmm_ctx_train_bwd: M*K=%d", M * K);
+  if (B <= 0) return CFPP_OK;
+  const size_t smem = ((size_t)D * HW + M * K) * sizeof(float);
+  CFPP_REQUIRE(want_smem(gmm_ctx_bwd_kernel, smem), "gmm_ctx_train_bwd: sample of %zu bytes exceeds shared memory", smem);
+  gmm_ctx_bwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(x, x_bstride, mG, sG, c, resp, g, dx, dx_bstride, dc, M, K, D, HW);
+  return check_launch("gmm_ctx_train_bwd");
+}
+
+extern "C" int cfpp_embed_scatter(const float* dc, int64_t dc_stride, int col0, const int64_t* perm, const int64_t* offsets, float* dtable,
+                                  int cardinality, int width, void* stream) {
+  CFPP_REQUIRE(cardinality >= 1 && width >= 1 && perm && offsets, "embed_scatter: card=%d width=%d", cardinality, width);
+  embed_scatter_kernel<<<dim3(cardinality, (width + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dc, dc_stride, col0, perm, offsets, dtable, width);
+  return check_launch("embed_scatter");
 }
 
 extern "C" int cfpp_relu_mask(float* g, const float* act, int64_t n, void* stream) {

@@ -97,9 +97,18 @@ class Coupling(_CouplingBase):
         if not self.context_net and training.wants_grad(x, *self.NN.parameters()):
             c1, c2, c3 = self.NN[0], self.NN[2], self.NN[4]
             return training.CouplingConvFn.apply(x, c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias)
+        if self.context_net and training.wants_grad(x, *self.CN.parameters()):
+            if not self.contextflow:
+                raise NotImplementedError('training the conventional (concatenated-context) coupling has no backward kernel yet')
+            training.require_constant_encoder(self.context_net)
+            if max(self._dims) > 256:
+                raise NotImplementedError('CN wider than 256 features has no training kernel yet')
+            c, logp_c = self._plan.run(self.context_net, context)
+            lin = [self.CN[0], self.CN[2], self.CN[4]]
+            cn = training.Mlp3RowsFn.apply(c, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias)
+            c1, c2, c3 = self.NN[0], self.NN[2], self.NN[4]
+            return training.CouplingCtxConvFn.apply(x, cn, logp_c, c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias)
         inference_only(x)
-        if self.context_net:
-            inference_only(self.CN[0].weight)
         D, H, O = self._dims
         Hh, Ww = x.shape[2], x.shape[3]
         pk = self._packed_nn()
@@ -166,7 +175,17 @@ class TransCoupling(_CouplingBase):
     def forward(self, x, context=None):
         vit = self.NN if isinstance(self.NN, SimpleViT) else self.NN[0]
         if not self.context_net and training.wants_grad(x, *vit.parameters()):
-            return training.CouplingVitFn.apply(x, vit, *vit._sources())   # autograd through libcfpp kernels
+            return training.CouplingVitFn.apply(x, None, None, vit, *vit._sources())   # autograd through libcfpp kernels
+        if self.context_net and training.wants_grad(x, *self.CN.parameters()):
+            if not self.contextflow:
+                raise NotImplementedError('training the conventional (concatenated-context) coupling has no backward kernel yet')
+            training.require_constant_encoder(self.context_net)
+            if max(self._dims) > 256:
+                raise NotImplementedError('CN wider than 256 features has no training kernel yet')
+            c, logp_c = self._plan.run(self.context_net, context)
+            lin = [self.CN[0], self.CN[2], self.CN[4]]
+            cn = training.Mlp3RowsFn.apply(c, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias)
+            return training.CouplingVitFn.apply(x, cn, logp_c, vit, *vit._sources())
         inference_only(x)
         if not self.context_net:
             return ops.coupling(x, vit(x))

@@ -670,13 +670,14 @@ def ldj_sum(terms, B, M, device, last=None):
 
 
 # ---------------------------------------------------------------------------------------------- training direction
-def coupling_bwd(x, h, dz, dldj=None):
+def coupling_bwd(x, h, dz, dldj=None, add=None):
     _need_cuda(x, h, dz); x = _f32(x); h = _f32(h); dz = _f32(dz)
     B, Cc = x.shape[0], x.shape[1]
     HW = x[0, 0].numel() if B else 1
     dx = torch.empty_like(x); dh = torch.empty_like(h)
     _set_work(bytes=20.0 * x.numel())
-    _call('coupling_bwd', (_p(x), _p(h), _p(dz), _p(None if dldj is None else _f32(dldj)), _p(dx), _p(dh), B, Cc, HW, _stream()))
+    _call('coupling_bwd', (_p(x), _p(h), _p(None if add is None else _f32(add)), _p(dz), _p(None if dldj is None else _f32(dldj)), _p(dx), _p(dh),
+                           B, Cc, HW, _stream()))
     return dx, dh
 
 
@@ -710,6 +711,13 @@ def maf_coupling(x, h):
     _set_work(bytes=16.0 * x.numel())
     _call('maf_coupling_fwd', (_p(x), _p(h), _p(z), _p(ldj), B, Cc, HW, _stream()))
     return z, ldj
+
+
+def relu_mask_(g, act):
+    """g[i] = 0 where act[i] <= 0, in place (ReLU backward on the saved post-activation)."""
+    _need_cuda(g, act)
+    _call('relu_mask', (_p(g), _p(_f32(act)), g.numel(), _stream()))
+    return g
 
 
 def conv2d_fwd(x, cin, w, b, relu, relu_in=False):
@@ -928,3 +936,76 @@ def attention_bwd(qkv, P, dO, B, n_tok):
     _set_work(flops=8.0 * B * n_tok * n_tok * 64)
     _call('attention_bwd', (_p(qkv), _p(P), _p(dO), _p(dqkv), B, n_tok, _stream()))
     return dqkv
+
+
+# ---------------------------------------------------------------------------------------------- specialist layers, training direction
+def conv1x1_ctx_bwd(x, dz, cmat, NN, contextflow, dldj=None, need_dx=True):
+    _need_cuda(x, dz, cmat); x = _f32(x); dz = _f32(dz); cmat = _f32(cmat)
+    B, D = x.shape[0], x.shape[1]
+    HW = x[0, 0].numel()
+    dx = torch.empty_like(x) if need_dx else None
+    dc = torch.empty_like(cmat)
+    _set_work(flops=4.0 * B * D * D * HW)
+    _call('conv1x1_ctx_bwd', (_p(x), _p(dz), _p(cmat), _p(None if NN is None else _f32(NN)), int(bool(contextflow)),
+                              _p(None if dldj is None else _f32(dldj)), _p(dx), _p(dc), B, D, HW, _stream()))
+    return dx, dc
+
+
+def actnorm_ctx_bwd(x, dz, cm, base_t, base_logs, dldj=None, need_dx=True):
+    _need_cuda(x, dz, cm); x = _f32(x); dz = _f32(dz); cm = _f32(cm)
+    B, D = x.shape[0], x.shape[1]
+    HW = x[0, 0].numel()
+    dx = torch.empty_like(x) if need_dx else None
+    dc = torch.empty_like(cm)
+    _set_work(bytes=(12.0 if need_dx else 8.0) * x.numel())
+    _call('actnorm_ctx_bwd', (_p(x), _p(dz), _p(cm), _p(base_t), _p(base_logs), _p(None if dldj is None else _f32(dldj)), _p(dx), _p(dc),
+                              B, D, HW, _stream()))
+    return dx, dc
+
+
+def gmm_ctx_train_fwd(x, mG, sG, wG, c):
+    _need_cuda(x, mG, c); c = _f32(c)
+    xv, bstride = _half_view(x)
+    B, D, HW = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+    M, K = wG.shape
+    logp = torch.empty((B, M), device=x.device, dtype=torch.float32)
+    resp = torch.empty((B, M, K), device=x.device, dtype=torch.float32)
+    _set_work(flops=8.0 * B * M * K * D * HW)
+    _call('gmm_ctx_train_fwd', (_p(xv), bstride, _p(_f32(mG)), _p(_f32(sG)), _p(_f32(wG)), _p(c), _p(logp), _p(resp), B, M, K, D, HW, _stream()))
+    return logp, resp
+
+
+def gmm_ctx_train_bwd(x, mG, sG, c, resp, g, need_dx=True, dx_out=None):
+    _need_cuda(x, mG, c, g); c = _f32(c); g = _f32(g)
+    xv, bstride = _half_view(x)
+    B, D, HW = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+    M, K = resp.shape[1], resp.shape[2]
+    if dx_out is not None:
+        dv, dstride = _half_view(dx_out)
+        assert dv.data_ptr() == dx_out.data_ptr()
+        dx = dx_out
+    else:
+        dstride = D * HW
+        dx = torch.empty((B, D) + tuple(x.shape[2:]), device=x.device, dtype=torch.float32) if need_dx else None
+    dc = torch.empty_like(c)
+    _set_work(flops=24.0 * B * M * K * D * HW)
+    _call('gmm_ctx_train_bwd', (_p(xv), bstride, _p(_f32(mG)), _p(_f32(sG)), _p(c), _p(resp), _p(g), _p(dx), dstride, _p(dc), B, M, K, D, HW, _stream()))
+    return dx, dc
+
+
+def embed_scatter(dc, ctx, tables):
+    """Gradients of the embedding tables from dc (B, n_ctx * width): per feature a stable sort of the batch by context value (torch,
+    index preparation only) and one deterministic bucket-sum kernel."""
+    _need_cuda(dc, ctx); dc = _f32(dc)
+    width = tables[0].shape[1]
+    out = []
+    for i, t in enumerate(tables):
+        card = t.shape[0]
+        col = ctx[:, i].contiguous()
+        perm = torch.sort(col, stable=True)[1].contiguous()
+        offsets = torch.zeros(card + 1, device=dc.device, dtype=torch.int64)
+        offsets[1:] = torch.cumsum(torch.bincount(col, minlength=card), 0)
+        dt = torch.empty((card, width), device=dc.device, dtype=torch.float32)
+        _call('embed_scatter', (_p(dc), dc.shape[1], i * width, _p(perm), _p(offsets), _p(dt), card, width, _stream()))
+        out.append(dt)
+    return out

@@ -206,7 +206,9 @@ class CouplingVitFn(Function):
     activations saved; the backward walks it in reverse.  Parameter order = SimpleViT._sources()."""
 
     @staticmethod
-    def forward(ctx, x, vit, *params):
+    def forward(ctx, x, add, logp_c, vit, *params):
+        # add (B, C) / logp_c (B): the additive context term CN(c) and the encoder's log-density of a --contextflow specialist
+        # (coupling.py:126-133; note logp_c is NOT scaled by H*W in TransCoupling); None for a generalist
         g = vit.geom
         c, p1, p2, T, n, depth = g['Cin'], g['p1'], g['p2'], g['T'], g['n_tok'], g['depth']
         B, C, H, W = x.shape
@@ -233,9 +235,10 @@ class CouplingVitFn(Function):
         Xf, mz, rz = ops.layernorm_fwd(X, lnfw, lnfb)
         cc = T // (p1 * p2)
         h = ops.patchify_inv(Xf, cc, H, W, p1, p2)
-        z, ldj = ops.coupling(x, h)
+        z, ldj = ops.coupling(x, h, add=add, logp_c=logp_c, logp_scale=1.0)
         saved += [X, mz, rz, x, h]
         ctx.save_for_backward(*saved, *params)
+        ctx.add = add
         ctx.meta = (c, p1, p2, T, n, depth, B, H, W, cc, len(saved))
         return z, ldj
 
@@ -247,7 +250,8 @@ class CouplingVitFn(Function):
         ln0w, ln0b, pew, peb, ln1w, ln1b, lnfw, lnfb = P[:8]
         Xlast, mz, rz, x, h = S[-5:]
         dz = _zeros_like_if_none(dz, x.shape, x.device).contiguous()
-        dx, dh = ops.coupling_bwd(x, h, dz, None if dldj is None else dldj.contiguous())
+        dx, dh = ops.coupling_bwd(x, h, dz, None if dldj is None else dldj.contiguous(), add=ctx.add)
+        dadd = ops.rowsum(dh.view(B * dh.shape[1], -1)).view(B, dh.shape[1]) if ctx.add is not None else None
         grads = [None] * len(P)
         dXf = ops.patchify(dh, cc, p1, p2)
         dX, grads[6], grads[7] = ops.layernorm_bwd(Xlast, dXf, lnfw, mz, rz)
@@ -270,4 +274,187 @@ class CouplingVitFn(Function):
         grads[2], grads[3] = ops.rows_linear_bwd_weight(y0, de)
         dtok, grads[0], grads[1] = ops.layernorm_bwd(tok, ops.rows_linear_bwd_data(de, pew), ln0w, m0, r0)
         ops.patchify_inv(dtok, c, H, W, p1, p2, out=dx, accumulate=True)          # dx[:, :c] += the conditioner's input gradient
-        return (dx if ctx.needs_input_grad[0] else None, None, *grads)
+        ng = ctx.needs_input_grad
+        grads = [gr if ng[4 + i] else None for i, gr in enumerate(grads)]          # frozen ViT parameters (--contextflow) take none
+        return (dx if ng[0] else None, dadd, None, None, *grads)
+
+
+# ---------------------------------------------------------------------------------------------- specialist (--contextflow) layers
+def encoder_is_constant(context_net) -> bool:
+    """True when the layer's context encoder has no trainable parameter (onehot / eye embeddings with the uniform surjection -- the
+    reference's default `--enc-emb onehot --enc-type uniform`): its output (c, logp_c) is then a constant of the graph.  Encoders with
+    inner flows (vardeq, argmax, probsample) or trainable embeddings have no backward kernels yet."""
+    return not any(p.requires_grad for p in context_net.parameters())
+
+
+def require_constant_encoder(context_net):
+    if not encoder_is_constant(context_net):
+        raise NotImplementedError('training through a context encoder with trainable parameters (vardeq / argmax / probsample flows, embed '
+                                  'tables) has no backward kernel yet; onehot|eye + uniform encoders train (DESIGN.md §8 f-1)')
+
+
+class LinearRowsFn(Function):
+    """nn.Linear on (B, K) rows: the CN of Conv1x1 / ActNorm (conv1x1.py:22, actnorm.py:21)."""
+
+    @staticmethod
+    def forward(ctx, c, W, b):
+        ctx.save_for_backward(c, W)
+        return ops.rows_linear(c, W.detach(), b.detach())
+
+    @staticmethod
+    def backward(ctx, dy):
+        c, W = ctx.saved_tensors
+        dy = dy.contiguous()
+        dW, db = ops.rows_linear_bwd_weight(c, dy)
+        dc = ops.rows_linear_bwd_data(dy, W.detach()) if ctx.needs_input_grad[0] else None
+        return dc, dW, db
+
+
+class Mlp3RowsFn(Function):
+    """Linear-ReLU-Linear-ReLU-Linear on (B, K) rows: the CN of the couplings (coupling.py:37,121)."""
+
+    @staticmethod
+    def forward(ctx, c, w1, b1, w2, b2, w3, b3):
+        h1 = ops.relu(ops.rows_linear(c, w1.detach(), b1.detach()))
+        h2 = ops.relu(ops.rows_linear(h1, w2.detach(), b2.detach()))
+        ctx.save_for_backward(c, h1, h2, w1, w2, w3)
+        return ops.rows_linear(h2, w3.detach(), b3.detach())
+
+    @staticmethod
+    def backward(ctx, dout):
+        c, h1, h2, w1, w2, w3 = ctx.saved_tensors
+        dout = dout.contiguous()
+        dw3, db3 = ops.rows_linear_bwd_weight(h2, dout)
+        dh2 = ops.relu_mask_(ops.rows_linear_bwd_data(dout, w3.detach()), h2)
+        dw2, db2 = ops.rows_linear_bwd_weight(h1, dh2)
+        dh1 = ops.relu_mask_(ops.rows_linear_bwd_data(dh2, w2.detach()), h1)
+        dw1, db1 = ops.rows_linear_bwd_weight(c, dh1)
+        dc = ops.rows_linear_bwd_data(dh1, w1.detach()) if ctx.needs_input_grad[0] else None
+        return dc, dw1, db1, dw2, db2, dw3, db3
+
+
+class Conv1x1CtxFn(Function):
+    """Conv1x1 with a per-sample context matrix (conv1x1.py:31-50); `cmat` = CN(c) (B, D*D); NN is frozen under --contextflow."""
+
+    @staticmethod
+    def forward(ctx, x, cmat, logp_c, layer):
+        z, ldj = ops.conv1x1(x, layer.NN.detach(), layer.logabsdet(), cmat, logp_c, layer.contextflow)
+        ctx.save_for_backward(x, cmat)
+        ctx.layer = layer
+        return z, ldj
+
+    @staticmethod
+    def backward(ctx, dz, dldj):
+        x, cmat = ctx.saved_tensors
+        lay = ctx.layer
+        dz = _zeros_like_if_none(dz, x.shape, x.device).contiguous()
+        dx, dc = ops.conv1x1_ctx_bwd(x, dz, cmat, lay.NN.detach() if lay.contextflow else None, lay.contextflow,
+                                     None if dldj is None else dldj.contiguous(), need_dx=ctx.needs_input_grad[0])
+        return dx, dc, None, None
+
+
+class ActNormCtxFn(Function):
+    """ActNorm with per-sample context shift / log-scale (actnorm.py:42-58); `cm` = CN(c) (B, 2D)."""
+
+    @staticmethod
+    def forward(ctx, x, cm, logp_c, layer):
+        HW = x.shape[2] * x.shape[3]
+        if layer.contextflow:
+            z, ldj = ops.actnorm(x, layer.NN_t.detach(), layer.NN_logs.detach(), cm, logp_c, float(HW), mode=1)
+        else:
+            z, ldj = ops.actnorm(x, None, None, cm, logp_c, float(HW), mode=2)
+        ctx.save_for_backward(x, cm)
+        ctx.layer = layer
+        return z, ldj
+
+    @staticmethod
+    def backward(ctx, dz, dldj):
+        x, cm = ctx.saved_tensors
+        lay = ctx.layer
+        dz = _zeros_like_if_none(dz, x.shape, x.device).contiguous()
+        bt, bl = (lay.NN_t.detach(), lay.NN_logs.detach()) if lay.contextflow else (None, None)
+        dx, dc = ops.actnorm_ctx_bwd(x, dz, cm, bt, bl, None if dldj is None else dldj.contiguous(), need_dx=ctx.needs_input_grad[0])
+        return dx, dc, None, None
+
+
+class CouplingCtxConvFn(Function):
+    """Coupling with the conv conditioner and the ADDITIVE context term of --contextflow (coupling.py:45): h = NN(x0) + CN(c).  NN is
+    frozen in that mode (its weight gradients are skipped unless they require grad); `add` = CN(c) (B, C)."""
+
+    @staticmethod
+    def forward(ctx, x, add, logp_c, w1, b1, w2, b2, w3, b3):
+        Ch = x.shape[1] // 2
+        HW = x.shape[2] * x.shape[3]
+        a1 = ops.conv2d_fwd(x, Ch, w1.detach(), b1.detach(), relu=True)
+        a2 = ops.conv2d_fwd(a1, a1.shape[1], w2.detach(), b2.detach(), relu=True)
+        h = ops.conv2d_fwd(a2, a2.shape[1], w3.detach(), b3.detach(), relu=False)
+        z, ldj = ops.coupling(x, h, add=add, logp_c=logp_c, logp_scale=float(HW))
+        ctx.save_for_backward(x, add, a1, a2, h, w1, w2, w3)
+        return z, ldj
+
+    @staticmethod
+    def backward(ctx, dz, dldj):
+        x, add, a1, a2, h, w1, w2, w3 = ctx.saved_tensors
+        B, C = x.shape[0], x.shape[1]
+        Ch = C // 2
+        dz = _zeros_like_if_none(dz, x.shape, x.device).contiguous()
+        dx, dh = ops.coupling_bwd(x, h, dz, None if dldj is None else dldj.contiguous(), add=add)
+        dadd = ops.rowsum(dh.view(B * C, -1)).view(B, C)
+        ng = ctx.needs_input_grad
+        dw3 = db3 = dw2 = db2 = dw1 = db1 = None
+        if ng[7] or ng[8]:
+            dw3, db3 = ops.conv2d_bwd_weight(a2, a2.shape[1], dh, w3.shape)
+        da2 = ops.conv2d_bwd_data(dh, w3.detach(), act=a2)
+        if ng[5] or ng[6]:
+            dw2, db2 = ops.conv2d_bwd_weight(a1, a1.shape[1], da2, w2.shape)
+        da1 = ops.conv2d_bwd_data(da2, w2.detach(), act=a1)
+        if ng[3] or ng[4]:
+            dw1, db1 = ops.conv2d_bwd_weight(x, Ch, da1, w1.shape)
+        ops.conv2d_bwd_data(da1, w1.detach(), out=dx, accumulate=True)
+        return (dx if ng[0] else None), dadd, None, dw1, db1, dw2, db2, dw3, db3
+
+
+def _lookup_tables(dist):
+    """The embedding tables of a mixture's context_net when it is the embed + eyesample lookup create_model gives every prior
+    (model.py:157,162); None otherwise."""
+    from .layers._encoder_desc import EncoderBatch
+    fused = dist._plan.fused_for(dist.context_net)
+    if fused is None or not EncoderBatch.is_lookup(fused):
+        return None
+    return fused.emb.tables()
+
+
+class GmmCtxFn(Function):
+    """GaussianMixtureDistribution.log_prob with context offsets from an embedding lookup (gaussian.py:146-155), --contextflow: mG, sG,
+    wG frozen, the tables train.  `split` > 0: the SplitPrior form -- x is the full tensor, the mixture scores x[:, split:] and the
+    Function also returns x[:, :split] (splitprior.py:12-15)."""
+
+    @staticmethod
+    def forward(ctx, x, context, dist, split, *tables):
+        c = ops.embed_lookup(context, [t.detach() for t in tables])
+        xs = x[:, split:] if split else x
+        logp, resp = ops.gmm_ctx_train_fwd(xs, dist.mG.detach(), dist.sG.detach(), dist.wG.detach(), c)
+        ctx.save_for_backward(x, context, c, resp, *tables)
+        ctx.dist, ctx.split = dist, split
+        if split:
+            return ops.slice_channels(x, 0, split), logp
+        return logp
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x, context, c, resp = ctx.saved_tensors[:4]
+        tables = ctx.saved_tensors[4:]
+        dist, split = ctx.dist, ctx.split
+        dx0, g = (grads if split else (None, grads[0]))
+        g = torch.zeros((x.shape[0], dist.M), device=x.device) if g is None else g.contiguous()
+        need_dx = ctx.needs_input_grad[0]
+        if split:
+            dx = torch.empty_like(x) if need_dx else None
+            if need_dx:
+                ops.place_channels(_zeros_like_if_none(dx0, (x.shape[0], split) + tuple(x.shape[2:]), x.device).contiguous(), dx, 0)
+            _, dc = ops.gmm_ctx_train_bwd(x[:, split:], dist.mG.detach(), dist.sG.detach(), c, resp, g, need_dx=need_dx,
+                                          dx_out=dx[:, split:] if need_dx else None)
+        else:
+            dx, dc = ops.gmm_ctx_train_bwd(x, dist.mG.detach(), dist.sG.detach(), c, resp, g, need_dx=need_dx)
+        dtables = ops.embed_scatter(dc, context, tables)
+        return (dx, None, None, None, *dtables)

@@ -336,10 +336,20 @@ int cfpp_score_epilogue(const float* logp, float dim_inv, const int64_t* gt, con
 /* What torch autograd derives for the reference (experiment_ad.py:204-213).  All gradients fp32; weight gradients are OVERWRITTEN;
  * every reduction over the batch has a fixed order (bit-identical run to run).
  * Coupling backward (layers/coupling.py:50-66): given x, h of the forward, dz and dldj (B, may be NULL):
- *   dx = cat(dz0, dz1 * s); dh = cat(dz1, (dz1 * x1 * s + dldj[b]) * (1 - tanh^2(r/2))), s = exp(2 tanh(r/2)).
+ *   dx = cat(dz0, dz1 * s); dh = cat(dz1, (dz1 * x1 * s + dldj[b]) * (1 - tanh^2(r/2))), s = exp(2 tanh(r/2)), r = h_r (+ add_r: the
+ *   additive context term `add` (B,C) of coupling.py:45, NULL without; its gradient is the sum of dh over the pixels: cfpp_rowsum).
  *   The conditioner's own gradient is then ADDED onto dx[:, :C/2] by cfpp_conv2d_bwd_data(accumulate = 1). */
-int cfpp_coupling_bwd(const float* x, const float* h, const float* dz, const float* dldj, float* dx, float* dh,
+int cfpp_coupling_bwd(const float* x, const float* h, const float* add, const float* dz, const float* dldj, float* dx, float* dh,
                       int B, int C, int HW, void* stream);
+/* Context-conditioned (specialist) Conv1x1 / ActNorm, backward w.r.t. the input and the raw context-network output c
+ * (layers/conv1x1.py:31-50, layers/actnorm.py:42-58; the frozen generalist parameters get no gradient under --contextflow).
+ * Conv1x1: c (B,D,D): dx = W_b^T dz; dc = lower triangle of dz x^T, diagonal exp(c_ii) (dz x^T)_ii + HW dldj[b], zero above.
+ * ActNorm: c (B,2D) 'b (p d)', base_t / base_logs (D) or NULL (conventional): dx = dz exp(-logs_b); dc = [-sum dz exp(-logs_b) |
+ * -sum dz z + dldj[b]].  dx may be NULL. */
+int cfpp_conv1x1_ctx_bwd(const float* x, const float* dz, const float* c, const float* NN, int contextflow, const float* dldj,
+                         float* dx, float* dc, int B, int D, int HW, void* stream);
+int cfpp_actnorm_ctx_bwd(const float* x, const float* dz, const float* c, const float* base_t, const float* base_logs,
+                         const float* dldj, float* dx, float* dc, int B, int D, int HW, void* stream);
 /* ActNorm backward without context (layers/actnorm.py:50-60): dx = dz * exp(-logs) (dx may be NULL);
  * dt[d] = -sum dz * exp(-logs); dlogs[d] = -sum dz * z + sum_b dldj[b].  workspace: cfpp_actnorm_bwd_workspace_floats(B, D) floats. */
 int64_t cfpp_actnorm_bwd_workspace_floats(int B, int D);
@@ -379,6 +389,19 @@ int64_t cfpp_gmm_train_bwd_workspace_floats(int B, int M, int K, int n);
 int cfpp_gmm_train_bwd(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* wG, const float* inv_var,
                        const float* resp, const float* g, float* dx, int64_t dx_bstride, float* dmG, float* dsG, float* dwG,
                        float* workspace, int B, int M, int K, int n, void* stream);
+
+/* Mixture with per-sample context offsets (layers/distributions/gaussian.py:146-155), training direction: c (B, 2*M*K*D) 'b (p m k d)'
+ * is the materialised context_net output (mean offsets | pre-softplus scale offsets).  fwd: logp (B,M) and the responsibilities resp
+ * (B,M,K); bwd: dx (B, D*HW; may be NULL) and dc (B, 2*M*K*D).  The frozen mG / sG / wG get no gradient under --contextflow. */
+int cfpp_gmm_ctx_train_fwd(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* wG, const float* c,
+                           float* logp, float* resp, int B, int M, int K, int D, int HW, void* stream);
+int cfpp_gmm_ctx_train_bwd(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* c, const float* resp,
+                           const float* g, float* dx, int64_t dx_bstride, float* dc, int B, int M, int K, int D, int HW, void* stream);
+/* Gradient of an embedding table (rtdl CatEmbeddings, _embeddings.py:265-283): dtable[v] = sum of dc[b, col0:col0+width] over the
+ * samples b whose context feature equals v; perm (B) = sample indices stably sorted by that feature, offsets (cardinality + 1) the
+ * bucket boundaries -- a fixed summation order, deterministic. */
+int cfpp_embed_scatter(const float* dc, int64_t dc_stride, int col0, const int64_t* perm, const int64_t* offsets, float* dtable,
+                       int cardinality, int width, void* stream);
 
 /* ---- training direction of the SimpleViT conditioner (layers/simple_vit.py:30-127): SURVEY §8(f)-1 --------------------- */
 /* Row-major token rows X (R = B * n_tok, F features).  Each entry is one op of the reference's module stack, forward with the

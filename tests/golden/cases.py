@@ -40,6 +40,11 @@ CASES = {
                                  num_blocks=1, block_size=2), B=4),
     # ATM-shaped generalist with the ViT conditioner and PermuteAxes (training-direction case for TransCoupling)
     'atm_gen': dict(conf=variant('cfg3', generalist=True, contextflow=False, num_blocks=1, block_size=2, contexts=[9], data_size=(6, 16, 1)), B=4),
+    # --contextflow specialists with the reference's DEFAULT encoder (--enc-emb onehot --enc-type uniform, config.py:18-19): the
+    # training-direction cases of the context-conditioned layers (conv with split priors and two context features; ViT)
+    'cifar_onehot_uniform': dict(conf=variant('cfg2', enc_type='uniform', num_blocks=2, block_size=1), B=3),
+    'atm_onehot_uniform': dict(conf=variant('cfg3', enc_emb='onehot', enc_type='uniform', num_blocks=2, block_size=1, contexts=[9, 5],
+                                            data_size=(6, 16, 1)), B=4),
     # the CIFAR generalist (stage one of the paper's workflow): conv stack WITH split priors, no context
     'cifar_gen': dict(conf=variant('cfg2', generalist=True, contextflow=False, num_blocks=2, block_size=1), B=3),
     'msl_conv_gen': dict(conf=variant('cfg4', dataset='msl', coupling='conv', data_size=(55, 8, 1), contexts=[27], mixtures=2,
@@ -68,4 +73,8 @@ TRAINING_CASES = {
     'cifar_gen': dict(alpha=1e-3, criterion=True, weight=None),           # experiment_cl.py:56 alpha with a criterion
     'cfg4': dict(alpha=1e2, criterion=False, weight=None),                # SMAP generalist, ViT conditioner, M = 1 (experiment_ad.py:61)
     'atm_gen': dict(alpha=1e-2, criterion=True, weight=[0.4, 1.6]),       # ViT conditioner with 8 / 3 tokens, PermuteAxes, M = 2
+    # --contextflow specialists, default (parameter-free) encoders: CN networks and the priors' embedding tables train
+    'mnist_onehot_uniform': dict(alpha=1e-2, criterion=True, weight=None),
+    'cifar_onehot_uniform': dict(alpha=1e-3, criterion=True, weight=None),
+    'atm_onehot_uniform': dict(alpha=1e-2, criterion=True, weight=[0.4, 1.6]),
 }

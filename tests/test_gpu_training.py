@@ -61,7 +61,8 @@ def test_gradients_match_reference_golden(name):
         assert abs(pd.abs().sum().item() - ref[1]) <= 2.5e-3 * pd.numel() + 1e-5 * ref[1], f'{name} AdamW step {k}'
 
 
-@pytest.mark.parametrize('name,B', [('cfg1', 37), ('msl_conv_gen', 50), ('cifar_gen', 21), ('cfg4', 50), ('atm_gen', 17)])
+@pytest.mark.parametrize('name,B', [('cfg1', 37), ('msl_conv_gen', 50), ('cifar_gen', 21), ('cfg4', 50), ('atm_gen', 17),
+                                    ('mnist_onehot_uniform', 21), ('cifar_onehot_uniform', 9), ('atm_onehot_uniform', 13)])
 def test_gradients_match_oracle_autograd_fresh_inputs(name, B):
     case = dict(CASES[name], B=B, iseed='in5', nseed='noise5')
     spec = TRAINING_CASES[name]
