@@ -16,7 +16,7 @@ def reference_arm(a):
     tests/test_oracle_golden_training.py), torch autograd, torch AdamW -- on the GPU (torch-on-CUDA baseline) or the host cores."""
     import contextlib, time
     from oracle import flow_oracle as O
-    conf = synth.CONFIGS[a.workload]
+    conf = synth.variant(a.workload, enc_type=a.enc_type) if a.enc_type else synth.CONFIGS[a.workload]
     stack = O.build_stack(conf['cfg'], conf['data_size'], conf['mixtures'], conf['contexts'])
     model = builder.build_named(conf)
     state = model.state_dict(); synth.fill_state(state, 'bench')
@@ -53,7 +53,7 @@ def reference_arm(a):
         cost = step()
     sync(); dt = time.perf_counter() - t0
     print(json.dumps({'metric': 'flow_training_step_samples_per_sec', 'impl': 'reference', 'value': B * a.steps / dt, 'unit': 'samples/s', 'n_gpus': 1,
-                      'workload': a.workload, 'batch_per_gpu': B, 'ms_per_step': 1e3 * dt / a.steps, 'loss': float(cost.item()),
+                      'workload': a.workload + (f' (enc_type={a.enc_type})' if a.enc_type else ''), 'batch_per_gpu': B, 'ms_per_step': 1e3 * dt / a.steps, 'loss': float(cost.item()),
                       'how': f'oracle op sequence + torch autograd + AdamW, eager, device={dev}' + (f' ({torch.cuda.get_device_name(0)})' if dev == 'cuda' else f' ({torch.get_num_threads()} threads)')}))
 
 
@@ -61,6 +61,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--workload', default='cfg1'); ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--steps', type=int, default=10); ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--enc-type', default=None, help='override the workload encoder type, e.g. uniform (the reference default): '
+                                                     'cfg2 with --enc-type uniform is the specialist whose training kernels exist')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'],
                     help="reference: the reference's torch op sequence (oracle restatement) + torch autograd + AdamW, eager, on --ref-device")
     ap.add_argument('--ref-device', default='cuda', choices=['cpu', 'cuda'])
@@ -71,7 +73,7 @@ def main():
     torch.cuda.set_device(local); dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    conf = synth.CONFIGS[a.workload]
+    conf = synth.variant(a.workload, enc_type=a.enc_type) if a.enc_type else synth.CONFIGS[a.workload]
     model = builder.build_named(conf)
     sd = model.state_dict(); synth.fill_state(sd, 'bench'); model.load_state_dict(sd)
     model = model.to(dev).train()
@@ -129,7 +131,7 @@ def main():
                     'GBps': round(v['bytes'] / (v['ms'] / 1e3) / 1e9, 1) if v['bytes'] else None}
                 for k, v in sorted(summ.items(), key=lambda kv: -kv[1]['ms'])}
         print(json.dumps({'metric': 'flow_training_step_samples_per_sec', 'value': world * B / (float(t.item()) / 1e3), 'unit': 'samples/s',
-                          'n_gpus': world, 'workload': a.workload, 'batch_per_gpu': B, 'ms_per_step': float(t.item()), 'loss': float(cost.item()),
+                          'n_gpus': world, 'workload': a.workload + (f' (enc_type={a.enc_type})' if a.enc_type else ''), 'batch_per_gpu': B, 'ms_per_step': float(t.item()), 'loss': float(cost.item()),
                           'libcfpp_launches_per_step': launches, 'libcfpp_kernel_ms_per_step': round(sum(v['ms'] for v in summ.values()) / a.steps, 3),
                           'optimizer': 'torch.optim.AdamW (the reference builds it, model.py:289)', 'kernels': kern}))
     if world > 1:
