@@ -694,6 +694,59 @@ __global__ void __launch_bounds__(256) gmm_ctx_bwd_kernel(const float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Encoder flows, training direction: the base draw and the variational-dequantisation epilogue as elementwise (B, C) kernels.
+// ConditionalGaussianDistribution.sample (gaussian.py:263-270): c = [mean | log_scale] (B, 2C); x = mean + exp(ls) eps;
+//   logq[b] = sum_d (-1/2 log 2pi - ls - 1/2 eps^2)   (the reference evaluates -1/2 exp(-2 ls) (x - mean)^2, which is eps^2).
+//   backward: dc_mean = dx; dc_ls = dx eps exp(ls) - dlogq[b].
+// VariationalCatDequantization.forward (dequantize.py:107-116) with Sigmoid (activations.py:231-235, temperature 1):
+//   z = (x + sigmoid(u)) / qbins;  ldj[b] = ldj_const + sum_d (-softplus(-u) - softplus(u)) - qu[b].
+//   backward: du = dz / qbins * s (1 - s) + dldj[b] (1 - 2 s);  dqu = -dldj.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void cond_gauss_fwd_kernel(const float* __restrict__ c, const float* __restrict__ eps, float* __restrict__ x, float* __restrict__ logq, int B, int C) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int d = 0; d < C; ++d) {
+      const float ls = c[(int64_t)b * 2 * C + C + d], e = eps[(int64_t)b * C + d];
+      x[(int64_t)b * C + d] = c[(int64_t)b * 2 * C + d] + expf(ls) * e;
+      acc += -kHalfLog2Pi - ls - 0.5f * e * e;
+    }
+    logq[b] = acc;
+  }
+}
+__global__ void cond_gauss_bwd_kernel(const float* __restrict__ c, const float* __restrict__ eps, const float* __restrict__ dx,
+                                      const float* __restrict__ dlogq, float* __restrict__ dc, int B, int C) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)B * C; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / C; const int d = (int)(i - b * C);
+    const float g = dx ? dx[i] : 0.f;
+    dc[b * 2 * C + d] = g;
+    dc[b * 2 * C + C + d] = g * eps[i] * expf(c[b * 2 * C + C + d]) - (dlogq ? dlogq[b] : 0.f);
+  }
+}
+__global__ void vardeq_fwd_kernel(const float* __restrict__ u, const float* __restrict__ qu, const int64_t* __restrict__ xcat, const float* __restrict__ qbins,
+                                  float ldj_const, float* __restrict__ z, float* __restrict__ ldj, int B, int C) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int d = 0; d < C; ++d) {
+      const float v = u[(int64_t)b * C + d];
+      const float s = 1.0f / (1.0f + expf(-v));
+      z[(int64_t)b * C + d] = ((float)xcat[(int64_t)b * C + d] + s) / qbins[d];
+      acc += -softplus_f(-v) - softplus_f(v);
+    }
+    ldj[b] = (ldj_const + acc) - qu[b];
+  }
+}
+__global__ void vardeq_bwd_kernel(const float* __restrict__ u, const float* __restrict__ qbins, const float* __restrict__ dz, const float* __restrict__ dldj,
+                                  float* __restrict__ du, float* __restrict__ dqu, int B, int C) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)B * C; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / C; const int d = (int)(i - b * C);
+    const float s = 1.0f / (1.0f + expf(-u[i]));
+    const float gl = dldj ? dldj[b] : 0.f;
+    du[i] = (dz ? dz[i] / qbins[d] * s * (1.0f - s) : 0.f) + gl * (1.0f - 2.0f * s);
+    if (d == 0) dqu[b] = -gl;
+  }
+}
+
 // dTable[v][col] = sum over the samples whose context feature equals v (bucket order given by a stable sort), of dc[b][col0 + col]
 __global__ void __launch_bounds__(256) embed_scatter_kernel(const float* __restrict__ dc, int64_t dc_stride, int col0, const int64_t* __restrict__ perm,
                                                             const int64_t* __restrict__ offsets, float* __restrict__ dtable, int width) {
@@ -873,6 +926,32 @@ extern "C" int cfpp_gmm_ctx_train_bwd(const float* x, int64_t x_bstride, const f
   CFPP_REQUIRE(want_smem(gmm_ctx_bwd_kernel, smem), "gmm_ctx_train_bwd: sample of %zu bytes exceeds shared memory", smem);
   gmm_ctx_bwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(x, x_bstride, mG, sG, c, resp, g, dx, dx_bstride, dc, M, K, D, HW);
   return check_launch("gmm_ctx_train_bwd");
+}
+
+extern "C" int cfpp_cond_gauss_fwd(const float* c, const float* eps, float* x, float* logq, int B, int C, void* stream) {
+  CFPP_REQUIRE(C >= 1, "cond_gauss: C=%d", C);
+  if (B <= 0) return CFPP_OK;
+  cond_gauss_fwd_kernel<<<grid1d(B), 256, 0, (cudaStream_t)stream>>>(c, eps, x, logq, B, C);
+  return check_launch("cond_gauss_fwd");
+}
+extern "C" int cfpp_cond_gauss_bwd(const float* c, const float* eps, const float* dx, const float* dlogq, float* dc, int B, int C, void* stream) {
+  CFPP_REQUIRE(C >= 1, "cond_gauss: C=%d", C);
+  if (B <= 0) return CFPP_OK;
+  cond_gauss_bwd_kernel<<<grid1d((int64_t)B * C), 256, 0, (cudaStream_t)stream>>>(c, eps, dx, dlogq, dc, B, C);
+  return check_launch("cond_gauss_bwd");
+}
+extern "C" int cfpp_vardeq_fwd(const float* u, const float* qu, const int64_t* xcat, const float* qbins, float ldj_const, float* z, float* ldj,
+                               int B, int C, void* stream) {
+  CFPP_REQUIRE(C >= 1, "vardeq: C=%d", C);
+  if (B <= 0) return CFPP_OK;
+  vardeq_fwd_kernel<<<grid1d(B), 256, 0, (cudaStream_t)stream>>>(u, qu, xcat, qbins, ldj_const, z, ldj, B, C);
+  return check_launch("vardeq_fwd");
+}
+extern "C" int cfpp_vardeq_bwd(const float* u, const float* qbins, const float* dz, const float* dldj, float* du, float* dqu, int B, int C, void* stream) {
+  CFPP_REQUIRE(C >= 1, "vardeq: C=%d", C);
+  if (B <= 0) return CFPP_OK;
+  vardeq_bwd_kernel<<<grid1d((int64_t)B * C), 256, 0, (cudaStream_t)stream>>>(u, qbins, dz, dldj, du, dqu, B, C);
+  return check_launch("vardeq_bwd");
 }
 
 extern "C" int cfpp_embed_scatter(const float* dc, int64_t dc_stride, int col0, const int64_t* perm, const int64_t* offsets, float* dtable,

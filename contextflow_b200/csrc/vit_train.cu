@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) chunk_sum_kernel(const float* __restrict_
 constexpr int kWS = 68;             // padded width of the weight tile rows (floats): 16-byte aligned, conflict-free 128-bit reads
 template <int TRANS>
 __global__ void __launch_bounds__(256) rows_linear_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
-                                                          float* __restrict__ out, int64_t R, int I, int J, int accumulate) {
+                                                          float* __restrict__ out, int64_t R, int I, int J, int accumulate, int64_t in_stride) {
   extern __shared__ float4 sm4[];
   float* ws = reinterpret_cast<float*>(sm4);          // [I][kWS]
   float* xs = ws + (size_t)I * kWS;                   // [64][I | 1]
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) rows_linear_kernel(const float* __restric
   const int64_t r0 = (int64_t)blockIdx.x * 64;
   const int j0 = blockIdx.y * 64;
   const int rows = (int)min((int64_t)64, R - r0), cols = min(64, J - j0);
-  for (int i = threadIdx.x; i < 64 * I; i += blockDim.x) { const int r = i / I, k = i - r * I; xs[r * S + k] = r < rows ? in[(r0 + r) * I + k] : 0.f; }
+  for (int i = threadIdx.x; i < 64 * I; i += blockDim.x) { const int r = i / I, k = i - r * I; xs[r * S + k] = r < rows ? in[(r0 + r) * in_stride + k] : 0.f; }
   if (TRANS) {
     for (int e = threadIdx.x; e < I * 64; e += blockDim.x) { const int i = e >> 6, jj = e & 63; ws[i * kWS + jj] = jj < cols ? W[(int64_t)i * J + j0 + jj] : 0.f; }
   } else {
@@ -388,19 +388,25 @@ extern "C" int cfpp_rows_linear_fwd(const float* x, const float* W, const float*
   const size_t smem = ((size_t)64 * (I | 1) + (size_t)I * kWS) * sizeof(float);
   static bool a = false;
   if (!a) { cudaFuncSetAttribute(rows_linear_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * (kMaxF + 1) + kMaxF * kWS) * 4); a = true; }
-  rows_linear_kernel<0><<<dim3((unsigned)((R + 63) / 64), (J + 63) / 64), 256, smem, (cudaStream_t)stream>>>(x, W, bias, y, R, I, J, 0);
+  rows_linear_kernel<0><<<dim3((unsigned)((R + 63) / 64), (J + 63) / 64), 256, smem, (cudaStream_t)stream>>>(x, W, bias, y, R, I, J, 0, I);
   return check_launch("rows_linear_fwd");
 }
 
 extern "C" int cfpp_rows_linear_bwd_data(const float* dy, const float* W, float* dx, int accumulate, int64_t R, int I, int J, void* stream) {
   // W is the forward weight (J, I); dx[r][i] = sum_j dy[r][j] W[j][i]
-  CFPP_REQUIRE(J >= 1 && J <= kMaxF && I >= 1, "rows_linear_bwd_data: I=%d J=%d", I, J);
+  CFPP_REQUIRE(J >= 1 && I >= 1, "rows_linear_bwd_data: I=%d J=%d", I, J);
   if (R <= 0) return CFPP_OK;
-  const size_t smem = ((size_t)64 * (J | 1) + (size_t)J * kWS) * sizeof(float);
   static bool a = false;
   if (!a) { cudaFuncSetAttribute(rows_linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * (kMaxF + 1) + kMaxF * kWS) * 4); a = true; }
-  rows_linear_kernel<1><<<dim3((unsigned)((R + 63) / 64), (I + 63) / 64), 256, smem, (cudaStream_t)stream>>>(dy, W, nullptr, dx, R, J, I, accumulate);
-  return check_launch("rows_linear_bwd_data");
+  for (int j0 = 0; j0 < J; j0 += kMaxF) {             // wide outputs (Conv1x1's CN: D*D columns): reduce in slices of 256, accumulating
+    const int len = J - j0 < kMaxF ? J - j0 : kMaxF;
+    const size_t smem = ((size_t)64 * (len | 1) + (size_t)len * kWS) * sizeof(float);
+    rows_linear_kernel<1><<<dim3((unsigned)((R + 63) / 64), (I + 63) / 64), 256, smem, (cudaStream_t)stream>>>(
+        dy + j0, W + (int64_t)j0 * I, nullptr, dx, R, len, I, accumulate || j0 > 0, J);
+    const int rc = check_launch("rows_linear_bwd_data");
+    if (rc != CFPP_OK) return rc;
+  }
+  return CFPP_OK;
 }
 
 extern "C" int64_t cfpp_rows_linear_bwd_weight_workspace_floats(int64_t R, int I, int J) {

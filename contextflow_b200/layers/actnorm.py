@@ -60,11 +60,10 @@ class ActNorm(FlowActivationLayer):
 
     def forward(self, x, context=None):
         if self.context_net and training.wants_grad(x, self.CN.weight, self.CN.bias):
-            training.require_constant_encoder(self.context_net)
             inference_only(self.NN_t)
             if self.contextflow and not self.is_initialized():
                 self.initialize(x)
-            c, logp_c = self._plan.run(self.context_net, context)
+            c, logp_c = training.encode(self, context)
             cm = training.LinearRowsFn.apply(c, self.CN.weight, self.CN.bias)
             return training.ActNormCtxFn.apply(x, cm, logp_c, self)
         HW = x.shape[2] * x.shape[3]

@@ -40,9 +40,8 @@ class Conv1x1(FlowLayer):
         if training.wants_grad(x, self.NN) and not self.context_net:
             return training.Conv1x1Fn.apply(x, self.NN, self)          # autograd through libcfpp kernels
         if self.context_net and training.wants_grad(x, self.CN.weight, self.CN.bias):
-            training.require_constant_encoder(self.context_net)       # specialist: gradients w.r.t. CN and the input
-            inference_only(self.NN)
-            c, logp_c = self._plan.run(self.context_net, context)
+            inference_only(self.NN)                                   # specialist: gradients w.r.t. CN, the encoder and the input
+            c, logp_c = training.encode(self, context)
             cmat = training.LinearRowsFn.apply(c, self.CN.weight, self.CN.bias)
             return training.Conv1x1CtxFn.apply(x, cmat, logp_c, self)
         inference_only(self.NN); inference_only(x)

@@ -100,10 +100,9 @@ class Coupling(_CouplingBase):
         if self.context_net and training.wants_grad(x, *self.CN.parameters()):
             if not self.contextflow:
                 raise NotImplementedError('training the conventional (concatenated-context) coupling has no backward kernel yet')
-            training.require_constant_encoder(self.context_net)
             if max(self._dims) > 256:
                 raise NotImplementedError('CN wider than 256 features has no training kernel yet')
-            c, logp_c = self._plan.run(self.context_net, context)
+            c, logp_c = training.encode(self, context)
             lin = [self.CN[0], self.CN[2], self.CN[4]]
             cn = training.Mlp3RowsFn.apply(c, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias)
             c1, c2, c3 = self.NN[0], self.NN[2], self.NN[4]
@@ -179,10 +178,9 @@ class TransCoupling(_CouplingBase):
         if self.context_net and training.wants_grad(x, *self.CN.parameters()):
             if not self.contextflow:
                 raise NotImplementedError('training the conventional (concatenated-context) coupling has no backward kernel yet')
-            training.require_constant_encoder(self.context_net)
             if max(self._dims) > 256:
                 raise NotImplementedError('CN wider than 256 features has no training kernel yet')
-            c, logp_c = self._plan.run(self.context_net, context)
+            c, logp_c = training.encode(self, context)
             lin = [self.CN[0], self.CN[2], self.CN[4]]
             cn = training.Mlp3RowsFn.apply(c, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias)
             return training.CouplingVitFn.apply(x, cn, logp_c, vit, *vit._sources())

@@ -63,7 +63,8 @@ class FlowSequential(nn.Module):
         B = input.shape[0]
         out = input
         terms = []
-        groups = self._encoder_groups() if context is not None else {}
+        # under autograd every layer evaluates its own encoder (trainable encoders run their module tree: training.encode), in layer order
+        groups = self._encoder_groups() if (context is not None and not torch.is_grad_enabled()) else {}
         for i, module in enumerate(self.sequence_modules):
             batch = groups.get(i)
             if batch is not None and batch.ready():

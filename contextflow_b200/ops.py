@@ -1009,3 +1009,35 @@ def embed_scatter(dc, ctx, tables):
         _call('embed_scatter', (_p(dc), dc.shape[1], i * width, _p(perm), _p(offsets), _p(dt), card, width, _stream()))
         out.append(dt)
     return out
+
+
+def cond_gauss_fwd(c, eps):
+    _need_cuda(c, eps); c = _f32(c); eps = _f32(eps)
+    B, C_ = eps.shape
+    x = torch.empty_like(eps); logq = torch.empty(B, device=eps.device, dtype=torch.float32)
+    _call('cond_gauss_fwd', (_p(c), _p(eps), _p(x), _p(logq), B, C_, _stream()))
+    return x, logq
+
+
+def cond_gauss_bwd(c, eps, dx, dlogq):
+    _need_cuda(c, eps)
+    B, C_ = eps.shape
+    dc = torch.empty_like(c)
+    _call('cond_gauss_bwd', (_p(c), _p(eps), _p(None if dx is None else _f32(dx)), _p(None if dlogq is None else _f32(dlogq)), _p(dc), B, C_, _stream()))
+    return dc
+
+
+def vardeq_fwd(u, qu, xcat, qbins, ldj_const):
+    _need_cuda(u, qu, xcat, qbins); u = _f32(u); qu = _f32(qu)
+    B, C_ = u.shape
+    z = torch.empty_like(u); ldj = torch.empty(B, device=u.device, dtype=torch.float32)
+    _call('vardeq_fwd', (_p(u), _p(qu), _p(xcat.contiguous()), _p(_f32(qbins)), float(ldj_const), _p(z), _p(ldj), B, C_, _stream()))
+    return z, ldj
+
+
+def vardeq_bwd(u, qbins, dz, dldj):
+    _need_cuda(u, qbins)
+    B, C_ = u.shape
+    du = torch.empty_like(u); dqu = torch.empty(B, device=u.device, dtype=torch.float32)
+    _call('vardeq_bwd', (_p(u), _p(_f32(qbins)), _p(None if dz is None else _f32(dz)), _p(None if dldj is None else _f32(dldj)), _p(du), _p(dqu), B, C_, _stream()))
+    return du, dqu

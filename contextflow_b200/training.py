@@ -276,7 +276,8 @@ class CouplingVitFn(Function):
         ops.patchify_inv(dtok, c, H, W, p1, p2, out=dx, accumulate=True)          # dx[:, :c] += the conditioner's input gradient
         ng = ctx.needs_input_grad
         grads = [gr if ng[4 + i] else None for i, gr in enumerate(grads)]          # frozen ViT parameters (--contextflow) take none
-        return (dx if ng[0] else None, dadd, None, None, *grads)
+        dlogp = dldj if (ng[2] and dldj is not None) else None                                      # TransCoupling: logp_c unscaled (coupling.py:126)
+        return (dx if ng[0] else None, dadd, dlogp, None, *grads)
 
 
 # ---------------------------------------------------------------------------------------------- specialist (--contextflow) layers
@@ -350,7 +351,9 @@ class Conv1x1CtxFn(Function):
         dz = _zeros_like_if_none(dz, x.shape, x.device).contiguous()
         dx, dc = ops.conv1x1_ctx_bwd(x, dz, cmat, lay.NN.detach() if lay.contextflow else None, lay.contextflow,
                                      None if dldj is None else dldj.contiguous(), need_dx=ctx.needs_input_grad[0])
-        return dx, dc, None, None
+        HW = x.shape[2] * x.shape[3]
+        dlogp = dldj * float(HW) if (ctx.needs_input_grad[2] and dldj is not None) else None      # ldj += HW * logp_c (conv1x1.py:50)
+        return dx, dc, dlogp, None
 
 
 class ActNormCtxFn(Function):
@@ -374,7 +377,9 @@ class ActNormCtxFn(Function):
         dz = _zeros_like_if_none(dz, x.shape, x.device).contiguous()
         bt, bl = (lay.NN_t.detach(), lay.NN_logs.detach()) if lay.contextflow else (None, None)
         dx, dc = ops.actnorm_ctx_bwd(x, dz, cm, bt, bl, None if dldj is None else dldj.contiguous(), need_dx=ctx.needs_input_grad[0])
-        return dx, dc, None, None
+        HW = x.shape[2] * x.shape[3]
+        dlogp = dldj * float(HW) if (ctx.needs_input_grad[2] and dldj is not None) else None      # ldj += HW * logp_c (actnorm.py:44,60)
+        return dx, dc, dlogp, None
 
 
 class CouplingCtxConvFn(Function):
@@ -411,7 +416,9 @@ class CouplingCtxConvFn(Function):
         if ng[3] or ng[4]:
             dw1, db1 = ops.conv2d_bwd_weight(x, Ch, da1, w1.shape)
         ops.conv2d_bwd_data(da1, w1.detach(), out=dx, accumulate=True)
-        return (dx if ng[0] else None), dadd, None, dw1, db1, dw2, db2, dw3, db3
+        HW = x.shape[2] * x.shape[3]
+        dlogp = dldj * float(HW) if (ng[2] and dldj is not None) else None                          # ldj += HW * logp_c (coupling.py:43)
+        return (dx if ng[0] else None), dadd, dlogp, dw1, db1, dw2, db2, dw3, db3
 
 
 def _lookup_tables(dist):
@@ -458,3 +465,80 @@ class GmmCtxFn(Function):
             dx, dc = ops.gmm_ctx_train_bwd(x, dist.mG.detach(), dist.sG.detach(), c, resp, g, need_dx=need_dx)
         dtables = ops.embed_scatter(dc, context, tables)
         return (dx, None, None, None, *dtables)
+
+
+# ---------------------------------------------------------------------------------------------- encoders with trainable parameters
+class EmbedLookupFn(Function):
+    """CatEmbeddings.forward (rtdl/nn/_embeddings.py:265-283): concatenated table rows; backward = deterministic bucket sums."""
+
+    @staticmethod
+    def forward(ctx, context, *tables):
+        ctx.save_for_backward(context, *tables)
+        return ops.embed_lookup(context, [t.detach() for t in tables])
+
+    @staticmethod
+    def backward(ctx, dc):
+        context, tables = ctx.saved_tensors[0], ctx.saved_tensors[1:]
+        return (None, *ops.embed_scatter(dc.contiguous(), context, tables))
+
+
+class CondGaussFn(Function):
+    """ConditionalGaussianDistribution.sample given its parameters c = [mean | log_scale] and the draw eps (gaussian.py:263-270)."""
+
+    @staticmethod
+    def forward(ctx, c, eps):
+        ctx.save_for_backward(c, eps)
+        return ops.cond_gauss_fwd(c, eps)
+
+    @staticmethod
+    def backward(ctx, dx, dlogq):
+        c, eps = ctx.saved_tensors
+        return ops.cond_gauss_bwd(c, eps, None if dx is None else dx.contiguous(), None if dlogq is None else dlogq.contiguous()), None
+
+
+class VardeqFn(Function):
+    """The epilogue of VariationalCatDequantization.forward (dequantize.py:107-116)."""
+
+    @staticmethod
+    def forward(ctx, u, qu, xcat, qbins, ldj_const):
+        ctx.save_for_backward(u, qbins)
+        return ops.vardeq_fwd(u, qu, xcat, qbins, ldj_const)
+
+    @staticmethod
+    def backward(ctx, dz, dldj):
+        u, qbins = ctx.saved_tensors
+        du, dqu = ops.vardeq_bwd(u, qbins, None if dz is None else dz.contiguous(), None if dldj is None else dldj.contiguous())
+        return du, dqu, None, None, None
+
+
+def encode(owner, context):
+    """(c, logp_c) of a layer's context encoder under autograd.  Parameter-free encoders (onehot|eye + uniform) are constants of the graph
+    and keep the fused kernel; the variational dequantiser (BASELINE cfg2) runs its module tree -- embedding lookup, conditional-Gaussian
+    draw, the inner flow on the FC / ActNormFC / CouplingFC training kernels, the dequantisation epilogue -- in the reference's order
+    (model.py:30-90, dequantize.py:107-116, flowsequential.py:60-69), drawing the same noise shapes as the fused path."""
+    from . import rng
+    from .layers.augment import Augment
+    net = owner.context_net
+    if encoder_is_constant(net):
+        return owner._plan.run(net, context)
+    emb, surj = net[0], net[1]
+    if getattr(surj, 'kind', None) != 'vardeq':
+        raise NotImplementedError(f'training through a {getattr(surj, "kind", type(surj).__name__)} context encoder has no backward kernel yet; '
+                                  'onehot|eye + uniform and vardeq encoders train (DESIGN.md §8 f-1)')
+    if context.dim() != 2:
+        raise ValueError('context must be (B, n)')
+    x, ctx_i = emb(context)
+    flow = surj.encoder
+    dist = flow.dist
+    cemb = EmbedLookupFn.apply(ctx_i, *dist.context_net.tables())
+    eps = rng.randn((context.shape[0], dist.D), context.device)
+    u, qu = CondGaussFn.apply(cemb, eps)
+    for module in flow.sequence_modules:
+        if isinstance(module, Augment):
+            raise NotImplementedError('encoder flows with an Augment step (odd context width) have no backward kernel yet')
+        u, ldj = module(u, ctx_i)
+        qu = qu - ldj                                                   # flowsequential.py:66
+    const = getattr(surj, '_ldj_const', None)
+    if const is None:
+        const = surj._ldj_const = float((surj.ldj_per_dim.detach().float().cpu() * x.shape[1:].numel()).sum())
+    return VardeqFn.apply(u, qu, x, surj.qbins, const)

@@ -397,6 +397,16 @@ int cfpp_gmm_ctx_train_fwd(const float* x, int64_t x_bstride, const float* mG, c
                            float* logp, float* resp, int B, int M, int K, int D, int HW, void* stream);
 int cfpp_gmm_ctx_train_bwd(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* c, const float* resp,
                            const float* g, float* dx, int64_t dx_bstride, float* dc, int B, int M, int K, int D, int HW, void* stream);
+/* Encoder flows in training mode: the base draw of ConditionalGaussianDistribution.sample (gaussian.py:263-270; c = [mean | log_scale]
+ * (B, 2C), eps (B, C) standard normal: x = mean + exp(ls) eps, logq = sum(-1/2 log 2pi - ls - 1/2 eps^2)) and the epilogue of
+ * VariationalCatDequantization.forward (dequantize.py:107-116: z = (xcat + sigmoid(u)) / qbins, ldj = ldj_const + sum(-softplus(-u) -
+ * softplus(u)) - qu), each with the backward torch autograd derives.  The inner flow between them (FC, ActNormFC, CouplingFC) runs on
+ * the Conv1x1 / ActNorm / Coupling training kernels with H = W = 1. */
+int cfpp_cond_gauss_fwd(const float* c, const float* eps, float* x, float* logq, int B, int C, void* stream);
+int cfpp_cond_gauss_bwd(const float* c, const float* eps, const float* dx, const float* dlogq, float* dc, int B, int C, void* stream);
+int cfpp_vardeq_fwd(const float* u, const float* qu, const int64_t* xcat, const float* qbins, float ldj_const, float* z, float* ldj,
+                    int B, int C, void* stream);
+int cfpp_vardeq_bwd(const float* u, const float* qbins, const float* dz, const float* dldj, float* du, float* dqu, int B, int C, void* stream);
 /* Gradient of an embedding table (rtdl CatEmbeddings, _embeddings.py:265-283): dtable[v] = sum of dc[b, col0:col0+width] over the
  * samples b whose context feature equals v; perm (B) = sample indices stably sorted by that feature, offsets (cardinality + 1) the
  * bucket boundaries -- a fixed summation order, deterministic. */

@@ -43,6 +43,8 @@ CASES = {
     # --contextflow specialists with the reference's DEFAULT encoder (--enc-emb onehot --enc-type uniform, config.py:18-19): the
     # training-direction cases of the context-conditioned layers (conv with split priors and two context features; ViT)
     'cifar_onehot_uniform': dict(conf=variant('cfg2', enc_type='uniform', num_blocks=2, block_size=1), B=3),
+    # the BASELINE cfg2 encoder (onehot + vardeq: trainable inner flows), reduced depth, ActNorms initialised
+    'cifar_vardeq': dict(conf=variant('cfg2', num_blocks=2, block_size=1), B=3),
     'atm_onehot_uniform': dict(conf=variant('cfg3', enc_emb='onehot', enc_type='uniform', num_blocks=2, block_size=1, contexts=[9, 5],
                                             data_size=(6, 16, 1)), B=4),
     # the CIFAR generalist (stage one of the paper's workflow): conv stack WITH split priors, no context
@@ -77,4 +79,6 @@ TRAINING_CASES = {
     'mnist_onehot_uniform': dict(alpha=1e-2, criterion=True, weight=None),
     'cifar_onehot_uniform': dict(alpha=1e-3, criterion=True, weight=None),
     'atm_onehot_uniform': dict(alpha=1e-2, criterion=True, weight=[0.4, 1.6]),
+    # --contextflow specialist with the BASELINE cfg2 encoder (variational dequantisation): the encoder flows train too
+    'cifar_vardeq': dict(alpha=1e-3, criterion=True, weight=None),
 }

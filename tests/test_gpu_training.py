@@ -62,7 +62,7 @@ def test_gradients_match_reference_golden(name):
 
 
 @pytest.mark.parametrize('name,B', [('cfg1', 37), ('msl_conv_gen', 50), ('cifar_gen', 21), ('cfg4', 50), ('atm_gen', 17),
-                                    ('mnist_onehot_uniform', 21), ('cifar_onehot_uniform', 9), ('atm_onehot_uniform', 13)])
+                                    ('mnist_onehot_uniform', 21), ('cifar_onehot_uniform', 9), ('atm_onehot_uniform', 13), ('cifar_vardeq', 7)])
 def test_gradients_match_oracle_autograd_fresh_inputs(name, B):
     case = dict(CASES[name], B=B, iseed='in5', nseed='noise5')
     spec = TRAINING_CASES[name]
@@ -221,8 +221,8 @@ def test_backward_is_deterministic():
 
 
 def test_unsupported_layers_raise_under_autograd():
-    model = build_cuda_model(CASES['cfg2_init']).train()       # context-conditioned (specialist) layers: no backward kernels yet
-    x, ctx = case_inputs(CASES['cfg2_init'])
+    model = build_cuda_model(CASES['atm_argmax2']).train()     # argmax encoders: no backward kernels yet
+    x, ctx = case_inputs(CASES['atm_argmax2'])
     with pytest.raises(NotImplementedError):
         model.log_prob(x.cuda(), ctx.cuda())
 
