@@ -123,8 +123,8 @@ _SIGNATURES = {
     'cfpp_gmm_ctx_train_bwd': (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp]),
     'cfpp_cond_gauss_fwd': (i32, [vp, vp, vp, vp, i32, i32, vp]),
     'cfpp_cond_gauss_bwd': (i32, [vp, vp, vp, vp, vp, i32, i32, vp]),
-    'cfpp_vardeq_fwd': (i32, [vp, vp, vp, vp, f32, vp, vp, i32, i32, vp]),
-    'cfpp_vardeq_bwd': (i32, [vp, vp, vp, vp, vp, vp, i32, i32, vp]),
+    'cfpp_vardeq_fwd': (i32, [vp, vp, vp, vp, f32, i32, vp, vp, i32, i32, vp]),
+    'cfpp_vardeq_bwd': (i32, [vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, vp]),
     'cfpp_embed_scatter': (i32, [vp, i64, i32, vp, vp, vp, i32, i32, vp]),
     'cfpp_patchify_fwd': (i32, [vp, i64, vp, i32, i32, i32, i32, i32, i32, vp]),
     'cfpp_patchify_inv': (i32, [vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp]),

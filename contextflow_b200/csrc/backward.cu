@@ -723,27 +723,31 @@ __global__ void cond_gauss_bwd_kernel(const float* __restrict__ c, const float* 
     dc[b * 2 * C + C + d] = g * eps[i] * expf(c[b * 2 * C + C + d]) - (dlogq ? dlogq[b] : 0.f);
   }
 }
+// mode 0 vardeq: z = (xcat + s) / qbins, ldj = const + act - qu;  mode 1 argmax (dequantize.py:239-268): z = s * sign (sign = 2 bit - 1,
+// passed in xcat as +-1), ldj = act - qu;  mode 2 probsample (:152-160): z = s, ldj = act + qu.   s = sigmoid(u), act = sum(-softplus(-u) - softplus(u)).
 __global__ void vardeq_fwd_kernel(const float* __restrict__ u, const float* __restrict__ qu, const int64_t* __restrict__ xcat, const float* __restrict__ qbins,
-                                  float ldj_const, float* __restrict__ z, float* __restrict__ ldj, int B, int C) {
+                                  float ldj_const, int mode, float* __restrict__ z, float* __restrict__ ldj, int B, int C) {
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
     float acc = 0.f;
     for (int d = 0; d < C; ++d) {
       const float v = u[(int64_t)b * C + d];
       const float s = 1.0f / (1.0f + expf(-v));
-      z[(int64_t)b * C + d] = ((float)xcat[(int64_t)b * C + d] + s) / qbins[d];
+      z[(int64_t)b * C + d] = mode == 0 ? ((float)xcat[(int64_t)b * C + d] + s) / qbins[d] : mode == 1 ? s * (float)xcat[(int64_t)b * C + d] : s;
       acc += -softplus_f(-v) - softplus_f(v);
     }
-    ldj[b] = (ldj_const + acc) - qu[b];
+    ldj[b] = mode == 2 ? (ldj_const + acc) + qu[b] : (ldj_const + acc) - qu[b];
   }
 }
-__global__ void vardeq_bwd_kernel(const float* __restrict__ u, const float* __restrict__ qbins, const float* __restrict__ dz, const float* __restrict__ dldj,
+__global__ void vardeq_bwd_kernel(const float* __restrict__ u, const int64_t* __restrict__ xcat, const float* __restrict__ qbins, int mode,
+                                  const float* __restrict__ dz, const float* __restrict__ dldj,
                                   float* __restrict__ du, float* __restrict__ dqu, int B, int C) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)B * C; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = i / C; const int d = (int)(i - b * C);
     const float s = 1.0f / (1.0f + expf(-u[i]));
     const float gl = dldj ? dldj[b] : 0.f;
-    du[i] = (dz ? dz[i] / qbins[d] * s * (1.0f - s) : 0.f) + gl * (1.0f - 2.0f * s);
-    if (d == 0) dqu[b] = -gl;
+    const float mul = mode == 0 ? 1.0f / qbins[d] : mode == 1 ? (float)xcat[i] : 1.0f;
+    du[i] = (dz ? dz[i] * mul * s * (1.0f - s) : 0.f) + gl * (1.0f - 2.0f * s);
+    if (d == 0) dqu[b] = mode == 2 ? gl : -gl;
   }
 }
 
@@ -940,17 +944,18 @@ extern "C" int cfpp_cond_gauss_bwd(const float* c, const float* eps, const float
   cond_gauss_bwd_kernel<<<grid1d((int64_t)B * C), 256, 0, (cudaStream_t)stream>>>(c, eps, dx, dlogq, dc, B, C);
   return check_launch("cond_gauss_bwd");
 }
-extern "C" int cfpp_vardeq_fwd(const float* u, const float* qu, const int64_t* xcat, const float* qbins, float ldj_const, float* z, float* ldj,
+extern "C" int cfpp_vardeq_fwd(const float* u, const float* qu, const int64_t* xcat, const float* qbins, float ldj_const, int mode, float* z, float* ldj,
                                int B, int C, void* stream) {
-  CFPP_REQUIRE(C >= 1, "vardeq: C=%d", C);
+  CFPP_REQUIRE(C >= 1 && mode >= 0 && mode <= 2 && (mode == 2 || xcat) && (mode != 0 || qbins), "vardeq: C=%d mode=%d", C, mode);
   if (B <= 0) return CFPP_OK;
-  vardeq_fwd_kernel<<<grid1d(B), 256, 0, (cudaStream_t)stream>>>(u, qu, xcat, qbins, ldj_const, z, ldj, B, C);
+  vardeq_fwd_kernel<<<grid1d(B), 256, 0, (cudaStream_t)stream>>>(u, qu, xcat, qbins, ldj_const, mode, z, ldj, B, C);
   return check_launch("vardeq_fwd");
 }
-extern "C" int cfpp_vardeq_bwd(const float* u, const float* qbins, const float* dz, const float* dldj, float* du, float* dqu, int B, int C, void* stream) {
-  CFPP_REQUIRE(C >= 1, "vardeq: C=%d", C);
+extern "C" int cfpp_vardeq_bwd(const float* u, const int64_t* xcat, const float* qbins, int mode, const float* dz, const float* dldj, float* du, float* dqu,
+                               int B, int C, void* stream) {
+  CFPP_REQUIRE(C >= 1 && mode >= 0 && mode <= 2 && (mode == 2 || xcat) && (mode != 0 || qbins), "vardeq: C=%d mode=%d", C, mode);
   if (B <= 0) return CFPP_OK;
-  vardeq_bwd_kernel<<<grid1d((int64_t)B * C), 256, 0, (cudaStream_t)stream>>>(u, qbins, dz, dldj, du, dqu, B, C);
+  vardeq_bwd_kernel<<<grid1d((int64_t)B * C), 256, 0, (cudaStream_t)stream>>>(u, xcat, qbins, mode, dz, dldj, du, dqu, B, C);
   return check_launch("vardeq_bwd");
 }
 

@@ -8,7 +8,7 @@
 namespace cfpp {
 namespace vt {
 
-constexpr int kMaxF = 256;          // widest row a warp keeps in registers (8 values per lane)
+constexpr int kMaxF = 320;          // widest row a warp keeps in registers (10 values per lane): 2C of the widest ATM coupling
 constexpr int kDh = 64;             // attention head width (simple_vit.py: dim_head = 64, heads = 1)
 
 // ---- patchify 'b c (h p1) (w p2) -> (b h w) (p1 p2 c)' and its inverse (simple_vit.py:102,115 / coupling un-patchify) ----------

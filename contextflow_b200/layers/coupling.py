@@ -100,8 +100,8 @@ class Coupling(_CouplingBase):
         if self.context_net and training.wants_grad(x, *self.CN.parameters()):
             if not self.contextflow:
                 raise NotImplementedError('training the conventional (concatenated-context) coupling has no backward kernel yet')
-            if max(self._dims) > 256:
-                raise NotImplementedError('CN wider than 256 features has no training kernel yet')
+            if max(self._dims) > 320:
+                raise NotImplementedError('CN wider than 320 features has no training kernel yet')
             c, logp_c = training.encode(self, context)
             lin = [self.CN[0], self.CN[2], self.CN[4]]
             cn = training.Mlp3RowsFn.apply(c, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias)
@@ -178,8 +178,8 @@ class TransCoupling(_CouplingBase):
         if self.context_net and training.wants_grad(x, *self.CN.parameters()):
             if not self.contextflow:
                 raise NotImplementedError('training the conventional (concatenated-context) coupling has no backward kernel yet')
-            if max(self._dims) > 256:
-                raise NotImplementedError('CN wider than 256 features has no training kernel yet')
+            if max(self._dims) > 320:
+                raise NotImplementedError('CN wider than 320 features has no training kernel yet')
             c, logp_c = training.encode(self, context)
             lin = [self.CN[0], self.CN[2], self.CN[4]]
             cn = training.Mlp3RowsFn.apply(c, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias)

@@ -1027,17 +1027,20 @@ def cond_gauss_bwd(c, eps, dx, dlogq):
     return dc
 
 
-def vardeq_fwd(u, qu, xcat, qbins, ldj_const):
+def vardeq_fwd(u, qu, xcat, qbins, ldj_const, mode=0):
+    """mode 0 vardeq, 1 argmax (xcat = +-1 signs), 2 probsample."""
     _need_cuda(u, qu, xcat, qbins); u = _f32(u); qu = _f32(qu)
     B, C_ = u.shape
     z = torch.empty_like(u); ldj = torch.empty(B, device=u.device, dtype=torch.float32)
-    _call('vardeq_fwd', (_p(u), _p(qu), _p(xcat.contiguous()), _p(_f32(qbins)), float(ldj_const), _p(z), _p(ldj), B, C_, _stream()))
+    _call('vardeq_fwd', (_p(u), _p(qu), _p(None if xcat is None else xcat.contiguous()), _p(None if qbins is None else _f32(qbins)), float(ldj_const),
+                         int(mode), _p(z), _p(ldj), B, C_, _stream()))
     return z, ldj
 
 
-def vardeq_bwd(u, qbins, dz, dldj):
-    _need_cuda(u, qbins)
+def vardeq_bwd(u, xcat, qbins, dz, dldj, mode=0):
+    _need_cuda(u, xcat, qbins)
     B, C_ = u.shape
     du = torch.empty_like(u); dqu = torch.empty(B, device=u.device, dtype=torch.float32)
-    _call('vardeq_bwd', (_p(u), _p(_f32(qbins)), _p(None if dz is None else _f32(dz)), _p(None if dldj is None else _f32(dldj)), _p(du), _p(dqu), B, C_, _stream()))
+    _call('vardeq_bwd', (_p(u), _p(None if xcat is None else xcat.contiguous()), _p(None if qbins is None else _f32(qbins)), int(mode),
+                         _p(None if dz is None else _f32(dz)), _p(None if dldj is None else _f32(dldj)), _p(du), _p(dqu), B, C_, _stream()))
     return du, dqu

@@ -500,15 +500,17 @@ class VardeqFn(Function):
     """The epilogue of VariationalCatDequantization.forward (dequantize.py:107-116)."""
 
     @staticmethod
-    def forward(ctx, u, qu, xcat, qbins, ldj_const):
-        ctx.save_for_backward(u, qbins)
-        return ops.vardeq_fwd(u, qu, xcat, qbins, ldj_const)
+    def forward(ctx, u, qu, xcat, qbins, ldj_const, mode):
+        ctx.save_for_backward(u)
+        ctx.aux = (xcat, qbins, mode)
+        return ops.vardeq_fwd(u, qu, xcat, qbins, ldj_const, mode)
 
     @staticmethod
     def backward(ctx, dz, dldj):
-        u, qbins = ctx.saved_tensors
-        du, dqu = ops.vardeq_bwd(u, qbins, None if dz is None else dz.contiguous(), None if dldj is None else dldj.contiguous())
-        return du, dqu, None, None, None
+        (u,) = ctx.saved_tensors
+        xcat, qbins, mode = ctx.aux
+        du, dqu = ops.vardeq_bwd(u, xcat, qbins, None if dz is None else dz.contiguous(), None if dldj is None else dldj.contiguous(), mode)
+        return du, dqu, None, None, None, None
 
 
 def encode(owner, context):
@@ -522,12 +524,19 @@ def encode(owner, context):
     if encoder_is_constant(net):
         return owner._plan.run(net, context)
     emb, surj = net[0], net[1]
-    if getattr(surj, 'kind', None) != 'vardeq':
-        raise NotImplementedError(f'training through a {getattr(surj, "kind", type(surj).__name__)} context encoder has no backward kernel yet; '
-                                  'onehot|eye + uniform and vardeq encoders train (DESIGN.md §8 f-1)')
+    kind = getattr(surj, 'kind', None)
     if context.dim() != 2:
         raise ValueError('context must be (B, n)')
-    x, ctx_i = emb(context)
+    trainable_emb = any(p.requires_grad for p in emb.parameters())
+    if kind == 'eyesample' and trainable_emb and hasattr(emb, 'tables'):      # embed + eyesample: c is the table lookup itself, ldj = 0
+        return EmbedLookupFn.apply(context, *emb.tables()), torch.zeros(context.shape[0], device=context.device)
+    # probsample ignores the embedding's values (dequantize.py:152-160 uses x for nothing but the batch size), so a trainable `embed`
+    # table in front of it receives no gradient in the reference either
+    if kind not in ('vardeq', 'argmax', 'probsample') or (trainable_emb and kind != 'probsample'):
+        raise NotImplementedError(f'training through a {kind or type(surj).__name__} context encoder over {type(emb).__name__} has no backward '
+                                  'kernel yet (DESIGN.md §8 f-1)')
+    with torch.no_grad():
+        x, ctx_i = emb(context)
     flow = surj.encoder
     dist = flow.dist
     cemb = EmbedLookupFn.apply(ctx_i, *dist.context_net.tables())
@@ -538,7 +547,19 @@ def encode(owner, context):
             raise NotImplementedError('encoder flows with an Augment step (odd context width) have no backward kernel yet')
         u, ldj = module(u, ctx_i)
         qu = qu - ldj                                                   # flowsequential.py:66
+    if kind == 'argmax':                                 # dequantize.py:244-256: bits MSB first per feature, one zero column if odd, sign = 2 bit - 1
+        nb = surj.num_bits if isinstance(surj.num_bits, (list, tuple)) else [surj.num_bits] * context.shape[1]
+        cols = []
+        for i, bits in enumerate(nb):                    # integer index preparation (torch integer ops, no arithmetic of the path)
+            shifts = torch.arange(bits - 1, -1, -1, device=context.device, dtype=torch.int64)
+            cols.append((context[:, i:i + 1] >> shifts) & 1)
+        bits_all = torch.cat(cols, 1)
+        if bits_all.shape[1] % 2:
+            bits_all = torch.cat([bits_all, torch.zeros_like(bits_all[:, :1])], 1)
+        return VardeqFn.apply(u, qu, bits_all * 2 - 1, None, 0.0, 1)
+    if kind == 'probsample':
+        return VardeqFn.apply(u, qu, None, None, 0.0, 2)
     const = getattr(surj, '_ldj_const', None)
     if const is None:
         const = surj._ldj_const = float((surj.ldj_per_dim.detach().float().cpu() * x.shape[1:].numel()).sum())
-    return VardeqFn.apply(u, qu, x, surj.qbins, const)
+    return VardeqFn.apply(u, qu, x, surj.qbins, const, 0)

@@ -404,9 +404,12 @@ int cfpp_gmm_ctx_train_bwd(const float* x, int64_t x_bstride, const float* mG, c
  * the Conv1x1 / ActNorm / Coupling training kernels with H = W = 1. */
 int cfpp_cond_gauss_fwd(const float* c, const float* eps, float* x, float* logq, int B, int C, void* stream);
 int cfpp_cond_gauss_bwd(const float* c, const float* eps, const float* dx, const float* dlogq, float* dc, int B, int C, void* stream);
-int cfpp_vardeq_fwd(const float* u, const float* qu, const int64_t* xcat, const float* qbins, float ldj_const, float* z, float* ldj,
+/* mode 0: the vardeq form above; mode 1: ArgmaxCatDequantization (dequantize.py:239-268): z = sigmoid(u) * sign with sign = +-1 passed
+ * in xcat, ldj = act - qu; mode 2: ProbSampling (:152-160): z = sigmoid(u), ldj = act + qu. */
+int cfpp_vardeq_fwd(const float* u, const float* qu, const int64_t* xcat, const float* qbins, float ldj_const, int mode, float* z, float* ldj,
                     int B, int C, void* stream);
-int cfpp_vardeq_bwd(const float* u, const float* qbins, const float* dz, const float* dldj, float* du, float* dqu, int B, int C, void* stream);
+int cfpp_vardeq_bwd(const float* u, const int64_t* xcat, const float* qbins, int mode, const float* dz, const float* dldj, float* du, float* dqu,
+                    int B, int C, void* stream);
 /* Gradient of an embedding table (rtdl CatEmbeddings, _embeddings.py:265-283): dtable[v] = sum of dc[b, col0:col0+width] over the
  * samples b whose context feature equals v; perm (B) = sample indices stably sorted by that feature, offsets (cardinality + 1) the
  * bucket boundaries -- a fixed summation order, deterministic. */
@@ -420,7 +423,7 @@ int cfpp_embed_scatter(const float* dc, int64_t dc_stride, int col0, const int64
  * permutation (the un-patchify of TransCoupling / the adjoint of patchify), stored or accumulated through a batch stride. */
 int cfpp_patchify_fwd(const float* x, int64_t x_bstride, float* tok, int B, int c, int H, int W, int p1, int p2, void* stream);
 int cfpp_patchify_inv(const float* tok, float* x, int64_t x_bstride, int accumulate, int B, int c, int H, int W, int p1, int p2, void* stream);
-/* nn.LayerNorm(F) (eps 1e-5, biased variance): y, and mean / rstd per row for the backward.  F <= 256. */
+/* nn.LayerNorm(F) (eps 1e-5, biased variance): y, and mean / rstd per row for the backward.  F <= 320. */
 int cfpp_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int64_t R, int F, void* stream);
 int64_t cfpp_layernorm_bwd_workspace_floats(int64_t R, int F);
 int cfpp_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* mean, const float* rstd,

@@ -81,4 +81,10 @@ TRAINING_CASES = {
     'atm_onehot_uniform': dict(alpha=1e-2, criterion=True, weight=[0.4, 1.6]),
     # --contextflow specialist with the BASELINE cfg2 encoder (variational dequantisation): the encoder flows train too
     'cifar_vardeq': dict(alpha=1e-3, criterion=True, weight=None),
+    # the other valid (embedding x surjection) pairs: eye + argmax over the ViT stack (BASELINE cfg3's encoder), eye + vardeq,
+    # embed + probsample, embed + eyesample
+    'atm_argmax2': dict(alpha=1e-2, criterion=True, weight=None),
+    'mnist_eye_vardeq2': dict(alpha=1e-2, criterion=True, weight=None),
+    'mnist_embed_probsample': dict(alpha=1e-2, criterion=True, weight=None),
+    'mnist_embed_eyesample': dict(alpha=1e-2, criterion=True, weight=None),
 }

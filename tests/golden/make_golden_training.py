@@ -54,7 +54,7 @@ def run(M_, name, spec):
     rec = dict(loss=np.array([cost.item(), sup.item(), uns.item()]))
     names = []
     for k, p in net.named_parameters():
-        if not p.requires_grad:
+        if not p.requires_grad or p.grad is None:        # e.g. the embed table in front of probsample: unused by the reference's forward
             continue
         g = p.grad.detach()
         names.append(k)
@@ -63,7 +63,7 @@ def run(M_, name, spec):
         rec[f'g:{k}'] = g.numpy() if g.numel() <= FULL else g.flatten()[:512].numpy()
     opt.step()
     for k, p in net.named_parameters():
-        if p.requires_grad:
+        if p.requires_grad and p.grad is not None:
             pd = p.detach().double()
             rec[f'psum:{k}'] = np.array([pd.sum().item(), pd.abs().sum().item()])
     # the same reference model and loss in float64: the yardstick for how far float32 summation order moves each gradient
@@ -82,7 +82,7 @@ def run(M_, name, spec):
             cost64, _, _ = training_loss(net64, x.double(), ctx, gt, conf['data_size'], spec)
         cost64.backward()
         for k, p in net64.named_parameters():
-            if p.requires_grad:
+            if p.requires_grad and p.grad is not None:
                 g = p.grad.detach()
                 rec[f'g64:{k}'] = g.numpy() if g.numel() <= FULL else g.flatten()[:512].numpy()
         rec['loss64'] = np.array(cost64.item())

@@ -50,7 +50,7 @@ def test_gradients_match_reference_golden(name):
     assert_close(np.array([cost.item(), sup.item(), uns.item()]), gold['loss'], 1e-4, 1e-5, f'{name} loss')
     cost.backward()
     named = dict(model.named_parameters())
-    assert sorted(gold['names']) == sorted(k for k, p in named.items() if p.requires_grad)
+    assert sorted(gold['names']) == sorted(k for k, p in named.items() if p.requires_grad and p.grad is not None)
     check_grads(name, {k: named[k].grad for k in gold['names']}, gold, rtol=2e-4)
     opt.step()          # the torch optimizer the reference builds (model.py:289) consumes the CUDA-produced .grad tensors
     for k in gold['names']:
@@ -62,13 +62,14 @@ def test_gradients_match_reference_golden(name):
 
 
 @pytest.mark.parametrize('name,B', [('cfg1', 37), ('msl_conv_gen', 50), ('cifar_gen', 21), ('cfg4', 50), ('atm_gen', 17),
-                                    ('mnist_onehot_uniform', 21), ('cifar_onehot_uniform', 9), ('atm_onehot_uniform', 13), ('cifar_vardeq', 7)])
+                                    ('mnist_onehot_uniform', 21), ('cifar_onehot_uniform', 9), ('atm_onehot_uniform', 13), ('cifar_vardeq', 7),
+                                    ('atm_argmax2', 11), ('mnist_embed_probsample', 6), ('mnist_embed_eyesample', 10)])
 def test_gradients_match_oracle_autograd_fresh_inputs(name, B):
     case = dict(CASES[name], B=B, iseed='in5', nseed='noise5')
     spec = TRAINING_CASES[name]
     stack, state = golden_state(load_golden(name), case)
     model = build_cuda_model(case).train()
-    names = [k for k, p in model.named_parameters() if p.requires_grad]
+    names = [k for k in load_train(name)['names']]            # the parameters the reference's backward reaches
     for k in names:
         state[k].requires_grad_(True)
     x, ctx = case_inputs(case)
@@ -221,8 +222,8 @@ def test_backward_is_deterministic():
 
 
 def test_unsupported_layers_raise_under_autograd():
-    model = build_cuda_model(CASES['atm_argmax2']).train()     # argmax encoders: no backward kernels yet
-    x, ctx = case_inputs(CASES['atm_argmax2'])
+    model = build_cuda_model(CASES['cifar_conventional']).train()     # conventional (concatenated-context) specialists: no backward kernels yet
+    x, ctx = case_inputs(CASES['cifar_conventional'])
     with pytest.raises(NotImplementedError):
         model.log_prob(x.cuda(), ctx.cuda())
 
