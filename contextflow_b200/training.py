@@ -253,28 +253,33 @@ class CouplingVitFn(Function):
         dx, dh = ops.coupling_bwd(x, h, dz, None if dldj is None else dldj.contiguous(), add=ctx.add)
         dadd = ops.rowsum(dh.view(B * dh.shape[1], -1)).view(B, dh.shape[1]) if ctx.add is not None else None
         grads = [None] * len(P)
+        ng = ctx.needs_input_grad
+
+        def wgrad(idx, xin, dy, bias=True):              # frozen ViT parameters (--contextflow specialists): no weight gradient launches
+            if not ng[4 + idx]:
+                return None, None
+            return ops.rows_linear_bwd_weight(xin, dy, bias=bias)
         dXf = ops.patchify(dh, cc, p1, p2)
         dX, grads[6], grads[7] = ops.layernorm_bwd(Xlast, dXf, lnfw, mz, rz)
         for l in reversed(range(depth)):
             X, ma, ra, y, qkv, Pm, O, X1, mf, rf, y2, hpre, gact = S[7 + 13 * l: 20 + 13 * l]
             o = 8 + 10 * l
             anw, anb, qkvw, outw, f0w, f0b, f1w, f1b, f3w, f3b = P[o: o + 10]
-            grads[o + 8], grads[o + 9] = ops.rows_linear_bwd_weight(gact, dX)
+            grads[o + 8], grads[o + 9] = wgrad(o + 8, gact, dX)
             dhpre = ops.gelu_bwd(hpre, ops.rows_linear_bwd_data(dX, f3w))
-            grads[o + 6], grads[o + 7] = ops.rows_linear_bwd_weight(y2, dhpre)
+            grads[o + 6], grads[o + 7] = wgrad(o + 6, y2, dhpre)
             d1, grads[o + 4], grads[o + 5] = ops.layernorm_bwd(X1, ops.rows_linear_bwd_data(dhpre, f1w), f0w, mf, rf)
             dX1 = ops.add(dX, d1)
-            grads[o + 3], _ = ops.rows_linear_bwd_weight(O, dX1, bias=False)
+            grads[o + 3], _ = wgrad(o + 3, O, dX1, bias=False)
             dqkv = ops.attention_bwd(qkv, Pm, ops.rows_linear_bwd_data(dX1, outw), B, n)
-            grads[o + 2], _ = ops.rows_linear_bwd_weight(y, dqkv, bias=False)
+            grads[o + 2], _ = wgrad(o + 2, y, dqkv, bias=False)
             d0, grads[o], grads[o + 1] = ops.layernorm_bwd(X, ops.rows_linear_bwd_data(dqkv, qkvw), anw, ma, ra)
             dX = ops.add(dX1, d0)
         tok, m0, r0, y0, e, m1, r1 = S[:7]
         de, grads[4], grads[5] = ops.layernorm_bwd(e, dX, ln1w, m1, r1)
-        grads[2], grads[3] = ops.rows_linear_bwd_weight(y0, de)
+        grads[2], grads[3] = wgrad(2, y0, de)
         dtok, grads[0], grads[1] = ops.layernorm_bwd(tok, ops.rows_linear_bwd_data(de, pew), ln0w, m0, r0)
         ops.patchify_inv(dtok, c, H, W, p1, p2, out=dx, accumulate=True)          # dx[:, :c] += the conditioner's input gradient
-        ng = ctx.needs_input_grad
         grads = [gr if ng[4 + i] else None for i, gr in enumerate(grads)]          # frozen ViT parameters (--contextflow) take none
         dlogp = dldj if (ng[2] and dldj is not None) else None                                      # TransCoupling: logp_c unscaled (coupling.py:126)
         return (dx if ng[0] else None, dadd, dlogp, None, *grads)
