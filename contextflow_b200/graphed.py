@@ -121,3 +121,38 @@ class GraphedLogProb:
         comp.synchronize()
         return outs
 
+
+
+class GraphedTrainStep:
+    """forward + loss + backward of a training step captured in ONE CUDA graph (torch.cuda.graph around the libcfpp launches, which go to
+    torch's current stream): removes the host launch overhead of the 10^3 kernels of a specialist step.  The optimizer stays eager -- the
+    reference builds a plain torch.optim.AdamW (model.py:289), which is not capturable -- and reads the static .grad tensors the replay
+    overwrites, so do NOT call zero_grad(set_to_none=True) between steps.  Inputs are copied into static buffers; shapes are fixed.
+    `loss_fn(model, x, ctx, gt) -> scalar loss`."""
+
+    def __init__(self, model, loss_fn, x, ctx, gt, warmup: int = 2):
+        self.model, self.loss_fn = model, loss_fn
+        self.static = (x.clone(), ctx.clone(), None if gt is None else gt.clone())
+        params = [p for p in model.parameters() if p.requires_grad]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                     # allocator warm-up, lazy initialisations (ActNorm flags, cached constants)
+                for p in params:
+                    p.grad = None
+                loss_fn(model, *self.static).backward()
+        torch.cuda.current_stream().wait_stream(side)
+        for p in params:
+            p.grad = None                                # the captured backward allocates the static .grad tensors in the graph's pool
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = loss_fn(model, *self.static)
+            self.loss.backward()
+
+    def __call__(self, x, ctx, gt=None):
+        self.static[0].copy_(x, non_blocking=True)
+        self.static[1].copy_(ctx, non_blocking=True)
+        if gt is not None:
+            self.static[2].copy_(gt, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -1002,9 +1002,10 @@ def embed_scatter(dc, ctx, tables):
     for i, t in enumerate(tables):
         card = t.shape[0]
         col = ctx[:, i].contiguous()
-        perm = torch.sort(col, stable=True)[1].contiguous()
-        offsets = torch.zeros(card + 1, device=dc.device, dtype=torch.int64)
-        offsets[1:] = torch.cumsum(torch.bincount(col, minlength=card), 0)
+        srt, perm = torch.sort(col, stable=True)
+        perm = perm.contiguous()
+        # bucket boundaries without a host synchronisation (torch.bincount sizes its output from the data): capturable in a CUDA graph
+        offsets = torch.searchsorted(srt, torch.arange(card + 1, device=dc.device, dtype=col.dtype)).contiguous()
         dt = torch.empty((card, width), device=dc.device, dtype=torch.float32)
         _call('embed_scatter', (_p(dc), dc.shape[1], i * width, _p(perm), _p(offsets), _p(dt), card, width, _stream()))
         out.append(dt)

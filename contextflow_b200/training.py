@@ -218,7 +218,10 @@ class CouplingVitFn(Function):
         y0, m0, r0 = ops.layernorm_fwd(tok, ln0w, ln0b)
         e = ops.rows_linear(y0, pew, peb)
         X, m1, r1 = ops.layernorm_fwd(e, ln1w, ln1b)
-        ops.add_pos_(X, vit.pos_embedding.to(x.device, torch.float32).contiguous(), n)
+        pos = getattr(vit, '_pos_dev', None)                 # the sincos table on the device, uploaded once (not per step: no H2D in a captured step)
+        if pos is None or pos.device != x.device:
+            pos = vit._pos_dev = vit.pos_embedding.to(x.device, torch.float32).contiguous()
+        ops.add_pos_(X, pos, n)
         saved = [tok, m0, r0, y0, e, m1, r1]
         for l in range(depth):
             anw, anb, qkvw, outw, f0w, f0b, f1w, f1b, f3w, f3b = P[8 + 10 * l: 18 + 10 * l]

@@ -221,6 +221,28 @@ def test_backward_is_deterministic():
         assert torch.equal(grads[0][k], grads[1][k]), k
 
 
+def test_graphed_train_step_matches_eager():
+    """GraphedTrainStep (forward + loss + backward replayed from one CUDA graph) produces the eager gradients bit for bit, on fresh
+    inputs copied into its static buffers (ATM-shaped ViT generalist: no random draws on the path)."""
+    from contextflow_b200.graphed import GraphedTrainStep
+    case = dict(CASES['atm_gen'], B=24)
+    spec = TRAINING_CASES['atm_gen']
+    model = build_cuda_model(case).train()
+    loss_fn = lambda m, x, c, gt: reference_loss(m, x, c, gt, case['conf']['data_size'], spec)[0]
+    xa, ca = case_inputs(dict(case, iseed='g0')); xb, cb = case_inputs(dict(case, iseed='g1'))
+    gta, gtb = labels('ga', 24, 2).cuda(), labels('gb', 24, 2).cuda()
+    step = GraphedTrainStep(model, loss_fn, xa.cuda(), ca.cuda(), gta)
+    loss_g = step(xb.cuda(), cb.cuda(), gtb).item()
+    got = {k: p.grad.clone() for k, p in model.named_parameters() if p.requires_grad}
+    model.zero_grad(set_to_none=True)
+    loss_e = loss_fn(model, xb.cuda(), cb.cuda(), gtb)
+    loss_e.backward()
+    assert loss_g == loss_e.item()
+    for k, p in model.named_parameters():
+        if p.requires_grad:
+            assert torch.equal(got[k], p.grad), k
+
+
 def test_unsupported_layers_raise_under_autograd():
     model = build_cuda_model(CASES['cifar_conventional']).train()     # conventional (concatenated-context) specialists: no backward kernels yet
     x, ctx = case_inputs(CASES['cifar_conventional'])

@@ -63,6 +63,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10); ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--enc-type', default=None, help='override the workload encoder type, e.g. uniform (the reference default): '
                                                      'cfg2 with --enc-type uniform is the specialist whose training kernels exist')
+    ap.add_argument('--graph', action='store_true', help='capture forward + loss + backward in one CUDA graph (GraphedTrainStep)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'],
                     help="reference: the reference's torch op sequence (oracle restatement) + torch autograd + AdamW, eager, on --ref-device")
     ap.add_argument('--ref-device', default='cuda', choices=['cpu', 'cuda'])
@@ -88,13 +89,24 @@ def main():
     dim_inv = 1.0 / float(C * H * W)
     crit = nn.CrossEntropyLoss(); log_theta = nn.LogSigmoid()
 
+    def loss_fn(m, x, c, gt):
+        logp = dim_inv * m.log_prob(x, context=c)
+        logp[logp != logp] = 0.0
+        return crit(logp, gt) - 1e-2 * log_theta(torch.logsumexp(logp, -1)).mean()
+
+    graphed = None
+    if a.graph:
+        from contextflow_b200.graphed import GraphedTrainStep
+        graphed = GraphedTrainStep(model, loss_fn, *batches[0])
+
     def step(i):
         x, c, gt = batches[i % 3]
-        opt.zero_grad(set_to_none=True)
-        logp = dim_inv * model.log_prob(x, context=c)
-        logp[logp != logp] = 0.0
-        cost = crit(logp, gt) - 1e-2 * log_theta(torch.logsumexp(logp, -1)).mean()
-        cost.backward()
+        if graphed is not None:
+            cost = graphed(x, c, gt)
+        else:
+            opt.zero_grad(set_to_none=True)
+            cost = loss_fn(model, x, c, gt)
+            cost.backward()
         sync(B, B * world)
         opt.step()
         return cost
@@ -121,9 +133,11 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     timer = ops.OpTimer(); ops.set_timer(timer)
+    graphed_keep, graphed = graphed, None               # per-kernel events need eager launches
     for i in range(a.steps):
         step(i)
     torch.cuda.synchronize(); ops.set_timer(None)
+    graphed = graphed_keep
     if rank == 0:
         summ = timer.summary()
         kern = {k: {'ms_per_step': round(v['ms'] / a.steps, 4), 'launches_per_step': v['n'] / a.steps,
@@ -132,7 +146,7 @@ def main():
                 for k, v in sorted(summ.items(), key=lambda kv: -kv[1]['ms'])}
         print(json.dumps({'metric': 'flow_training_step_samples_per_sec', 'value': world * B / (float(t.item()) / 1e3), 'unit': 'samples/s',
                           'n_gpus': world, 'workload': a.workload + (f' (enc_type={a.enc_type})' if a.enc_type else ''), 'batch_per_gpu': B, 'ms_per_step': float(t.item()), 'loss': float(cost.item()),
-                          'libcfpp_launches_per_step': launches, 'libcfpp_kernel_ms_per_step': round(sum(v['ms'] for v in summ.values()) / a.steps, 3),
+                          'libcfpp_launches_per_step': launches if not a.graph else 'captured in one CUDA graph (forward + loss + backward)', 'libcfpp_kernel_ms_per_step': round(sum(v['ms'] for v in summ.values()) / a.steps, 3),
                           'optimizer': 'torch.optim.AdamW (the reference builds it, model.py:289)', 'kernels': kern}))
     if world > 1:
         dist.destroy_process_group()
