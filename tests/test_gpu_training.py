@@ -228,7 +228,13 @@ def test_graphed_train_step_matches_eager():
     case = dict(CASES['atm_gen'], B=24)
     spec = TRAINING_CASES['atm_gen']
     model = build_cuda_model(case).train()
-    loss_fn = lambda m, x, c, gt: reference_loss(m, x, c, gt, case['conf']['data_size'], spec)[0]
+    crit = nn.CrossEntropyLoss(weight=torch.tensor(spec['weight']).cuda()); log_theta = nn.LogSigmoid()
+    dim_inv = 1.0 / float(np.prod(case['conf']['data_size']))
+
+    def loss_fn(m, x, c, gt):                            # experiment_ad.py:204-209; every tensor it touches already lives on the device
+        logp = dim_inv * m.log_prob(x, context=c)
+        logp[logp != logp] = 0.0
+        return crit(logp, gt) - spec['alpha'] * log_theta(torch.logsumexp(logp, -1)).mean()
     xa, ca = case_inputs(dict(case, iseed='g0')); xb, cb = case_inputs(dict(case, iseed='g1'))
     gta, gtb = labels('ga', 24, 2).cuda(), labels('gb', 24, 2).cuda()
     step = GraphedTrainStep(model, loss_fn, xa.cuda(), ca.cuda(), gta)
