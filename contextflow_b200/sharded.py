@@ -70,24 +70,20 @@ class GradAllReduce:
     def __call__(self, local_rows: int, total_rows: int):
         if self.world == 1:
             return
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-        n = sum(g.numel() for g in grads)
+        for p in self.params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        grads = [p.grad for p in self.params]
+        sizes = [g.numel() for g in grads]
+        n = sum(sizes)
         if self._flat is None or self._flat.numel() != n or self._flat.device != grads[0].device:
             self._flat = torch.empty(n, device=grads[0].device, dtype=torch.float32)
-        off = 0
-        scale = float(local_rows) / float(total_rows)
-        for g in grads:
-            self._flat[off: off + g.numel()].copy_(g.reshape(-1)).mul_(scale)
-            off += g.numel()
+            self._views = [c.view_as(g) for c, g in zip(self._flat.split(sizes), grads)]
+        # two fused multi-tensor launches around ONE collective instead of a copy per parameter
+        torch._foreach_copy_(self._views, grads)
+        self._flat.mul_(float(local_rows) / float(total_rows))
         dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
-        off = 0
-        for p, g in zip(self.params, grads):
-            new = self._flat[off: off + g.numel()].view_as(g)
-            if p.grad is None:
-                p.grad = new.clone()
-            else:
-                p.grad.copy_(new)
-            off += g.numel()
+        torch._foreach_copy_(grads, self._views)
 
 
 def sharded_actnorm_stats(x_local, group: Optional[dist.ProcessGroup] = None, local_stats: Optional[Callable] = None):
