@@ -552,7 +552,9 @@ def encode(owner, context):
     u, qu = CondGaussFn.apply(cemb, eps)
     for module in flow.sequence_modules:
         if isinstance(module, Augment):
-            raise NotImplementedError('encoder flows with an Augment step (odd context width) have no backward kernel yet')
+            # the reference itself cannot run this configuration: Augment's (B,1) ldj is subtracted in place from the (B,) log-density
+            # (flowsequential.py:66 -> "output with shape [B] doesn't match the broadcast shape [B, B]")
+            raise RuntimeError('encoder flows with an Augment step (odd context width) fail in the reference (flowsequential.py:66)')
         u, ldj = module(u, ctx_i)
         qu = qu - ldj                                                   # flowsequential.py:66
     if kind == 'argmax':                                 # dequantize.py:244-256: bits MSB first per feature, one zero column if odd, sign = 2 bit - 1
