@@ -331,6 +331,7 @@ def main():
             except Exception:
                 pass
             roof = {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak, 'traffic': traffic,
+                    **({'issued_tensor_TFLOPps': 3.0 * ach, 'frac_issued': 3.0 * ach / tf_peak} if top == 'conv_cond_tc_fwd' else {}),
                     'peak_source': 'measured bf16 sustained (MEASURED_PEAKS.json); ' +
                                    ('achieved counts ALGORITHMIC flops: the fp32-faithful fp16-pair arithmetic issues 3 tensor products per algorithmic one, so its ceiling is 1/3 of this peak'
                                     if top == 'conv_cond_tc_fwd' else 'this kernel is an FP32-FMA path')}
