@@ -93,6 +93,7 @@ _SIGNATURES = {
     'cfpp_cn_batch': (i32, [C.POINTER(CnJob), i32, C.POINTER(vp), C.POINTER(vp), i32, vp]),
     'cfpp_relu_fwd': (i32, [vp, vp, i64, vp]),
     'cfpp_maf_coupling_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    'cfpp_maf_coupling_bwd': (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     'cfpp_coupling_inv': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     'cfpp_actnorm_inv': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     'cfpp_mat_inverse': (i32, [vp, i32, vp, vp, vp]),

@@ -89,6 +89,23 @@ __global__ void __launch_bounds__(256) maf_coupling_kernel(const float* __restri
   if (valid && g == 0) ldj[b] = acc;
 }
 
+// MaskedCoupling backward: z = x s + t with t = h_t + x, r = h_r + x, s = exp(2 tanh(r/2)), ldj = sum 2 tanh(r/2).
+//   dr = (dz x s + dldj[b]) (1 - tanh^2(r/2));  dh = cat(dz, dr);  dx = dz s + dz + dr   (the conditioner's part is added by its own backward).
+__global__ void __launch_bounds__(256) maf_coupling_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h, const float* __restrict__ dz,
+                                                               const float* __restrict__ dldj, float* __restrict__ dx, float* __restrict__ dh,
+                                                               int64_t total, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / n, e = i - b * n;
+    const float xv = x[i], g = dz[i];
+    const float th = tanhf((h[b * 2 * n + n + e] + xv) * 0.5f);
+    const float sc = expf(2.0f * th);
+    const float dr = (g * xv * sc + (dldj ? dldj[b] : 0.f)) * (1.0f - th * th);
+    dh[b * 2 * n + e] = g;
+    dh[b * 2 * n + n + e] = dr;
+    dx[i] = g * sc + g + dr;
+  }
+}
+
 }  // namespace cfpp
 using namespace cfpp;
 
@@ -118,4 +135,14 @@ extern "C" int cfpp_maf_coupling_fwd(const float* x, const float* h, float* z, f
   const int spc = 256 / G;
   maf_coupling_kernel<<<(B + spc - 1) / spc, 256, 0, (cudaStream_t)stream>>>(x, h, z, ldj, B, C, HW, G);
   return check_launch("maf_coupling_fwd");
+}
+
+extern "C" int cfpp_maf_coupling_bwd(const float* x, const float* h, const float* dz, const float* dldj, float* dx, float* dh,
+                                     int B, int C, int HW, void* stream) {
+  CFPP_REQUIRE(C >= 1 && HW >= 1, "maf_coupling_bwd: C=%d HW=%d", C, HW);
+  if (B <= 0) return CFPP_OK;
+  const int64_t n = (int64_t)C * HW, total = (int64_t)B * n;
+  int64_t blocks = (total + 255) / 256; const int64_t cap = (int64_t)num_sms() * 16; if (blocks > cap) blocks = cap;
+  maf_coupling_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, h, dz, dldj, dx, dh, total, n);
+  return check_launch("maf_coupling_bwd");
 }

@@ -219,8 +219,13 @@ class MaskedCoupling(FlowLayer):
         self.NN = MaskedResidualBlock2d(D, D, kernel_size=kernel_size, padding=padding, D=D, mask_type=mask_type)
 
     def forward(self, x, context=None):
-        inference_only(x); inference_only(self.NN.conv1.weight)
-        return ops.maf_coupling(x, self.NN(x, identity=False))
+        nn_ = self.NN
+        if training.wants_grad(x, *nn_.parameters()):
+            for c in (nn_.conv1, nn_.conv2, nn_.conv3):
+                c.masked_weight()                                                                  # mask in place first (masked_conv_2d.py:21-23)
+            ws = [nn_.conv1.weight, nn_.conv2.weight, nn_.conv3.weight]
+            return training.MaskedCouplingFn.apply(x, ws[0], nn_.conv1.bias, ws[1], nn_.conv2.bias, ws[2], nn_.conv3.bias)
+        return ops.maf_coupling(x, nn_(x, identity=False))
 
     def reverse(self, z, context=None):
         return torch.zeros_like(z)                     # ar.py:59-66: the reference's reverse is a stub returning zeros

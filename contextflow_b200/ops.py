@@ -720,6 +720,16 @@ def relu_mask_(g, act):
     return g
 
 
+def maf_coupling_bwd(x, h, dz, dldj=None):
+    _need_cuda(x, h, dz); x = _f32(x); h = _f32(h); dz = _f32(dz)
+    B, Cc = x.shape[0], x.shape[1]
+    HW = x[0, 0].numel() if B else 1
+    dx = torch.empty_like(x); dh = torch.empty_like(h)
+    _set_work(bytes=24.0 * x.numel())
+    _call('maf_coupling_bwd', (_p(x), _p(h), _p(dz), _p(None if dldj is None else _f32(dldj)), _p(dx), _p(dh), B, Cc, HW, _stream()))
+    return dx, dh
+
+
 def conv2d_fwd(x, cin, w, b, relu, relu_in=False):
     """out = [relu](conv([relu_in](x[:, :cin])) + b), 'same' reflect padding; x may be wider than cin channels (read through its batch stride)."""
     _need_cuda(x, w)

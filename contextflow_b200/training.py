@@ -130,6 +130,35 @@ class CouplingConvFn(Function):
         return (dx if ctx.needs_input_grad[0] else None), dw1, db1, dw2, db2, dw3, db3
 
 
+class MaskedCouplingFn(Function):
+    """MaskedCoupling (`--coupling maf`, ar.py:35-57) over MaskedResidualBlock2d (masked_conv_2d.py:81-98), context-free.  The weights the
+    Function receives are already mask-multiplied in place (the reference's `weight.data *= mask` on every forward, :21-23); exactly like
+    autograd in the reference, the weight gradients are the dense ones (the mask is applied to the data, not inside the graph)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3):
+        r0 = ops.relu(x)
+        a1 = ops.conv2d_fwd(r0, r0.shape[1], w1.detach(), b1.detach(), relu=True)
+        a2 = ops.conv2d_fwd(a1, a1.shape[1], w2.detach(), b2.detach(), relu=True)
+        h = ops.conv2d_fwd(a2, a2.shape[1], w3.detach(), b3.detach(), relu=False)
+        z, ldj = ops.maf_coupling(x, h)
+        ctx.save_for_backward(x, r0, a1, a2, h, w1, w2, w3)
+        return z, ldj
+
+    @staticmethod
+    def backward(ctx, dz, dldj):
+        x, r0, a1, a2, h, w1, w2, w3 = ctx.saved_tensors
+        dz = _zeros_like_if_none(dz, x.shape, x.device).contiguous()
+        dx, dh = ops.maf_coupling_bwd(x, h, dz, None if dldj is None else dldj.contiguous())
+        dw3, db3 = ops.conv2d_bwd_weight(a2, a2.shape[1], dh, w3.shape)
+        da2 = ops.conv2d_bwd_data(dh, w3.detach(), act=a2)
+        dw2, db2 = ops.conv2d_bwd_weight(a1, a1.shape[1], da2, w2.shape)
+        da1 = ops.conv2d_bwd_data(da2, w2.detach(), act=a1)
+        dw1, db1 = ops.conv2d_bwd_weight(r0, r0.shape[1], da1, w1.shape)
+        ops.conv2d_bwd_data(da1, w1.detach(), act=x, out=dx, accumulate=True)      # through relu(x): masked by x > 0
+        return (dx if ctx.needs_input_grad[0] else None), dw1, db1, dw2, db2, dw3, db3
+
+
 class GmmFn(Function):
     """GaussianMixtureDistribution.log_prob (gaussian.py:142-161), context-free."""
 

@@ -293,6 +293,11 @@ int cfpp_cn_batch(const cfpp_cn_job* jobs, int n_jobs, const float* const* in, f
 int cfpp_relu_fwd(const float* x, float* y, int64_t n, void* stream);
 int cfpp_maf_coupling_fwd(const float* x, const float* h, float* z, float* ldj, int B, int C, int HW, void* stream);
 
+/* Its backward: dh (B, 2C, HW) = cat(dz, dr), dr = (dz x s + dldj[b]) (1 - tanh^2(r/2)); dx = dz s + dz + dr (the identity feeds both halves);
+ * the masked block's own input gradient is then accumulated onto dx by cfpp_conv2d_bwd_data(act = x, accumulate = 1). */
+int cfpp_maf_coupling_bwd(const float* x, const float* h, const float* dz, const float* dldj, float* dx, float* dh,
+                          int B, int C, int HW, void* stream);
+
 /* ---- inverse (sampling) direction: SURVEY §8(f)-3 ------------------------------------------------------------ */
 /* Coupling.reverse / TransCoupling.reverse, layers/coupling.py:68-73,150-155: t, r from h (+ add) as in cfpp_coupling_fwd;
  * x = cat(z[:, :C/2], (z[:, C/2:] - t) / exp(2 tanh(r/2))).  One HBM pass, 12*C*HW bytes/sample. */

@@ -1,7 +1,7 @@
 """CPU oracle for the ContextFlow++ flow log-density path  --  TEST INFRASTRUCTURE, NOT PRODUCT.
 
-Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline / `--impl reference` legs may import
-this module.  The product (contextflow_b200/) never does: it fails loudly without its CUDA library.
+Only tests/, __graft_entry__.smoke() and the CPU-baseline / `--impl reference` legs of bench.py and of its per-row companions
+(tools/bench_training.py --impl reference) may import this module.  The product (contextflow_b200/) never does: it fails loudly without its CUDA library.
 
 What it is: a from-scratch restatement of the reference's algorithm for `FlowSequential.log_prob`
 as flat functions over a `{state_dict key: tensor}` mapping -- no nn.Module, no einops, no
@@ -419,7 +419,9 @@ def masked_coupling(P, lay, x):
     h = x
     for name in ('conv1', 'conv2', 'conv3'):
         w = P(f'{k}.NN.{name}.weight')
-        w = w * maf_mask(w.shape[0], w.shape[1], w.shape[2], w.shape[3], D).to(w)
+        # masked_conv_2d.py:21-23 multiplies weight.DATA by the mask (outside the autograd graph): the forward sees masked weights, the
+        # gradient w.r.t. the parameter is the dense one
+        w = w + (w * maf_mask(w.shape[0], w.shape[1], w.shape[2], w.shape[3], D).to(w) - w).detach()
         h = torch.relu(h)
         if name == 'conv2' and (pad[0] or pad[1]):
             h = F.pad(h, (pad[1], pad[1], pad[0], pad[0]), mode='reflect')

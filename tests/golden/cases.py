@@ -87,4 +87,7 @@ TRAINING_CASES = {
     'mnist_eye_vardeq2': dict(alpha=1e-2, criterion=True, weight=None),
     'mnist_embed_probsample': dict(alpha=1e-2, criterion=True, weight=None),
     'mnist_embed_eyesample': dict(alpha=1e-2, criterion=True, weight=None),
+    # --coupling maf generalists (masked residual conv blocks)
+    'mnist_maf': dict(alpha=1e-2, criterion=True, weight=None),
+    'msl_maf': dict(alpha=1e-2, criterion=True, weight=[0.4, 1.6]),
 }

@@ -63,7 +63,7 @@ def test_gradients_match_reference_golden(name):
 
 @pytest.mark.parametrize('name,B', [('cfg1', 37), ('msl_conv_gen', 50), ('cifar_gen', 21), ('cfg4', 50), ('atm_gen', 17),
                                     ('mnist_onehot_uniform', 21), ('cifar_onehot_uniform', 9), ('atm_onehot_uniform', 13), ('cifar_vardeq', 7),
-                                    ('atm_argmax2', 11), ('mnist_embed_probsample', 6), ('mnist_embed_eyesample', 10)])
+                                    ('atm_argmax2', 11), ('mnist_embed_probsample', 6), ('mnist_embed_eyesample', 10), ('mnist_maf', 9), ('msl_maf', 14)])
 def test_gradients_match_oracle_autograd_fresh_inputs(name, B):
     case = dict(CASES[name], B=B, iseed='in5', nseed='noise5')
     spec = TRAINING_CASES[name]
