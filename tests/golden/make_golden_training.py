@@ -3,7 +3,7 @@
 Run in the build container only:   python tests/golden/make_golden_training.py
 Training direction.  For each case the reference model (hash-derived weights, inputs and noise, as in make_golden.py)
 evaluates the training loss exactly as experiment_ad.py:204-209 writes it and calls .backward(); stored: the loss terms and the
-gradient of every trainable parameter (full tensor up to 8192 elements, else (sum, sum|.|) and the first 512 values), plus the
+gradient of every trainable parameter (full tensor up to 2048 elements, else (sum, sum|.|) and the first 512 values), plus the
 parameters after ONE torch.optim.AdamW step with the settings of model.py:289 (lr 1e-3 here).
 """
 import sys, os, argparse, json
@@ -17,7 +17,7 @@ from contextflow_b200 import synth  # noqa: E402
 from tests.golden.cases import CASES, TRAINING_CASES  # noqa: E402
 from tests.golden.make_golden import import_reference, patched_rng  # noqa: E402
 
-FULL = 8192
+FULL = 2048
 
 
 def training_loss(net, x, ctx, gt, data_size, spec):
