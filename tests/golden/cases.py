@@ -31,6 +31,8 @@ CASES = {
     # time-series conv coupling (3,1) reflect kernels; MSL-shaped windows
     'msl_conv': dict(conf=variant('cfg4', dataset='msl', coupling='conv', data_size=(55, 8, 1), contexts=[27],
                                   num_blocks=1, block_size=2), B=3),
+    # SMD-shaped windows (38 x 8 x 1, model.py:216-218), ViT generalist
+    'smd_trans': dict(conf=variant('cfg4', dataset='smd', data_size=(38, 8, 1), contexts=[28]), B=4),
     # MNIST at the literal 28x28 shape (BASELINE configs[0])
     'mnist28': dict(conf=variant('cfg1', data_size=(1, 28, 28)), B=2),
     # generalist conv coupling on MSL-shaped windows ((3,1) kernels, 56 channels after Augment, M = 2): training-direction case

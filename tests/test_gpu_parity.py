@@ -68,7 +68,7 @@ def test_cuda_matches_reference_golden(name):
 
 
 @pytest.mark.parametrize('name,B', [('cfg1', 9), ('cfg2', 11), ('cfg3', 5), ('cfg4', 67), ('cifar_conventional', 6), ('msl_conv', 19),
-                                    ('mnist_maf', 7), ('msl_maf', 33), ('cifar_gen', 5)])
+                                    ('mnist_maf', 7), ('msl_maf', 33), ('cifar_gen', 5), ('smd_trans', 21)])
 def test_cuda_matches_oracle_per_layer(name, B):
     """Fresh seeded inputs (not in the goldens), ragged batch sizes; every layer's full z and ldj against the oracle."""
     case = dict(CASES[name], B=B, iseed='in1', nseed='noise1')
