@@ -154,7 +154,7 @@ def main():
         tool = 'bench_training.py' if a.path == 'train' else 'bench_inverse.py'
         argv = [tool, '--steps', str(a.steps)]
         if a.path == 'train':
-            argv += ['--warmup', str(a.warmup), '--impl', a.impl, '--workload', a.workload if a.workload in ('cfg1', 'cfg4') else 'cfg1']
+            argv += ['--warmup', str(a.warmup), '--impl', a.impl, '--workload', a.workload]
             if a.batch:
                 argv += ['--batch', str(a.batch)]
             if a.impl == 'reference':
