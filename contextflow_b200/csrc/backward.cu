@@ -754,19 +754,24 @@ __global__ void vardeq_bwd_kernel(const float* __restrict__ u, const int64_t* __
 // dTable[v][col] = sum over the samples whose context feature equals v (bucket order given by a stable sort), of dc[b][col0 + col]
 __global__ void __launch_bounds__(256) embed_scatter_kernel(const float* __restrict__ dc, int64_t dc_stride, int col0, const int64_t* __restrict__ perm,
                                                             const int64_t* __restrict__ offsets, float* __restrict__ dtable, int width) {
+  // CTA = one table row v x 32 columns; the 8 warps take the bucket's samples round-robin (8 rows in flight per column), their partial
+  // sums are added in warp order: a fixed summation order, so the result is deterministic
+  __shared__ float red[8][32];
   const int v = blockIdx.x;
-  const int col = blockIdx.y * blockDim.x + threadIdx.x;
-  if (col >= width) return;
-  float s = 0.f;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.y * 32 + lane;
   const int64_t i1 = offsets[v + 1];
-  int64_t i = offsets[v];
-  for (; i + 4 <= i1; i += 4) {                       // four independent loads in flight, added in bucket order (same sum as the plain loop)
-    const float v0 = dc[perm[i] * dc_stride + col0 + col], v1 = dc[perm[i + 1] * dc_stride + col0 + col];
-    const float v2 = dc[perm[i + 2] * dc_stride + col0 + col], v3 = dc[perm[i + 3] * dc_stride + col0 + col];
-    s = (((s + v0) + v1) + v2) + v3;
+  float s = 0.f;
+  if (col < width)
+    for (int64_t i = offsets[v] + w; i < i1; i += 8) s += dc[perm[i] * dc_stride + col0 + col];
+  red[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && col < width) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][lane];
+    dtable[(int64_t)v * width + col] = t;
   }
-  for (; i < i1; ++i) s += dc[perm[i] * dc_stride + col0 + col];
-  dtable[(int64_t)v * width + col] = s;
 }
 
 inline int grid1d(int64_t n, int per_thread = 1) {
@@ -969,7 +974,7 @@ extern "C" int cfpp_vardeq_bwd(const float* u, const int64_t* xcat, const float*
 extern "C" int cfpp_embed_scatter(const float* dc, int64_t dc_stride, int col0, const int64_t* perm, const int64_t* offsets, float* dtable,
                                   int cardinality, int width, void* stream) {
   CFPP_REQUIRE(cardinality >= 1 && width >= 1 && perm && offsets, "embed_scatter: card=%d width=%d", cardinality, width);
-  embed_scatter_kernel<<<dim3(cardinality, (width + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dc, dc_stride, col0, perm, offsets, dtable, width);
+  embed_scatter_kernel<<<dim3(cardinality, (width + 31) / 32), 256, 0, (cudaStream_t)stream>>>(dc, dc_stride, col0, perm, offsets, dtable, width);
   return check_launch("embed_scatter");
 }
 
