@@ -654,15 +654,16 @@ __global__ void __launch_bounds__(256) gmm_ctx_fwd_kernel(const float* __restric
 __global__ void __launch_bounds__(256) gmm_ctx_bwd_kernel(const float* __restrict__ x, int64_t x_bstride, const float* __restrict__ mG,
                                                           const float* __restrict__ sG, const float* __restrict__ c, const float* __restrict__ resp,
                                                           const float* __restrict__ g, float* __restrict__ dx, int64_t dx_bstride,
-                                                          float* __restrict__ dc, int M, int K, int D, int HW) {
-  extern __shared__ float sx[];                        // n floats x, M*K weights, then (dx wanted) one partial dx row of n floats per warp
+                                                          float* __restrict__ dc, int M, int K, int D, int HW, int dx_partials) {
+  extern __shared__ float sx[];                        // n floats x, M*K weights, then (dx_partials) one partial dx row of n floats per warp
   const int n = D * HW, MK = M * K;
   float* sw = sx + n;
   float* dxp = sw + MK;                                // [8][n]
   const int64_t b = blockIdx.x;
   for (int e = threadIdx.x; e < n; e += blockDim.x) sx[e] = x[b * x_bstride + e];
   for (int i = threadIdx.x; i < MK; i += blockDim.x) sw[i] = g[b * M + i / K] * resp[b * MK + i];
-  if (dx) for (int i = threadIdx.x; i < 8 * n; i += blockDim.x) dxp[i] = 0.f;
+  const bool part = dx && dx_partials;
+  if (part) for (int i = threadIdx.x; i < 8 * n; i += blockDim.x) dxp[i] = 0.f;
   __syncthreads();
   const float* cm = c + b * 2 * MK * D; const float* cs = cm + (int64_t)MK * D;
   float* dcm = dc + b * 2 * MK * D; float* dcs = dcm + (int64_t)MK * D;
@@ -679,12 +680,24 @@ __global__ void __launch_bounds__(256) gmm_ctx_bwd_kernel(const float* __restric
       const float is2 = 1.0f / (s * s);
       a0 += df * is2;
       a1 += (df * df * is2 / s - 1.0f / s) * (1.0f / (1.0f + expf(-raw)));
-      if (dx) dxp[w * n + e] -= wt * df * is2;         // this warp's share of dx[e] = sum_mk w (mu - x) / s^2 (one lane per e: no race)
+      if (part) dxp[w * n + e] -= wt * df * is2;       // this warp's share of dx[e] = sum_mk w (mu - x) / s^2 (one lane per e: no race)
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1);
     if (l == 0) { dcm[pair] = wt * a0; dcs[pair] = wt * a1; }
   }
   if (!dx) return;
+  if (!part) {                                         // samples too large for eight partial rows: second pass, sigma recomputed per element
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      const int d = e / HW;
+      float acc = 0.f;
+      for (int mk = 0; mk < MK; ++mk) {
+        const float s = softplus_f(sG[(int64_t)mk * n + e] + cs[mk * D + d]);
+        acc -= sw[mk] * (sx[e] - (mG[(int64_t)mk * n + e] + cm[mk * D + d])) / (s * s);
+      }
+      dx[b * dx_bstride + e] = acc;
+    }
+    return;
+  }
   __syncthreads();
   for (int e = threadIdx.x; e < n; e += blockDim.x) {  // the eight warp partials in warp order: deterministic
     float acc = 0.f;
@@ -938,9 +951,14 @@ extern "C" int cfpp_gmm_ctx_train_bwd(const float* x, int64_t x_bstride, const f
                                       const float* g, float* dx, int64_t dx_bstride, float* dc, int B, int M, int K, int D, int HW, void* stream) {
   CFPP_REQUIRE(M >= 1 && K >= 1 && M * K <= kMaxMK && D >= 1 && HW >= 1 && c && dc, "gmm_ctx_train_bwd: M*K=%d", M * K);
   if (B <= 0) return CFPP_OK;
-  const size_t smem = ((size_t)D * HW * (dx ? 9 : 1) + M * K) * sizeof(float);
+  size_t smem = ((size_t)D * HW * (dx ? 9 : 1) + M * K) * sizeof(float);
+  int partials = dx ? 1 : 0;
+  if (dx && !want_smem(gmm_ctx_bwd_kernel, smem)) {    // eight partial dx rows do not fit: keep the sample only and recompute sigma for dx
+    partials = 0;
+    smem = ((size_t)D * HW + M * K) * sizeof(float);
+  }
   CFPP_REQUIRE(want_smem(gmm_ctx_bwd_kernel, smem), "gmm_ctx_train_bwd: sample of %zu bytes exceeds shared memory", smem);
-  gmm_ctx_bwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(x, x_bstride, mG, sG, c, resp, g, dx, dx_bstride, dc, M, K, D, HW);
+  gmm_ctx_bwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(x, x_bstride, mG, sG, c, resp, g, dx, dx_bstride, dc, M, K, D, HW, partials);
   return check_launch("gmm_ctx_train_bwd");
 }
 

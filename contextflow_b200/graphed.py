@@ -15,11 +15,15 @@ from __future__ import annotations
 
 import torch
 
+import operator
+
 from . import _cabi
+
+_version_of = operator.attrgetter('_version')
 
 
 class _Entry:
-    __slots__ = ('graph', 'x', 'ctx', 'out', 'launches', 'signature')
+    __slots__ = ('graph', 'x', 'ctx', 'out', 'launches', 'signature', 'device')
 
 
 class GraphedLogProb:
@@ -27,17 +31,39 @@ class GraphedLogProb:
         self.model, self.warmup = model, max(1, warmup)
         self._entries = {}
         self._pool = None
+        self._tensors = None
+
+    def _device(self):
+        """The model's device (the reference places it with .to('cuda:{gpu}') and never calls set_device, model.py:170,285)."""
+        for p in self.model.parameters():
+            if p.is_cuda:
+                return p.device
+        return torch.device('cuda', torch.cuda.current_device())
 
     def _signature(self):
-        """Changes whenever a parameter / buffer is written in place or replaced: the layers repack weights on the host side keyed on
-        these versions, so a captured graph is only valid for the signature it was captured under."""
-        sig = 0
-        for t in self.model.state_dict(keep_vars=True).values():
-            sig = (sig * 1000003 + t._version + (t.data_ptr() & 0xFFFFF)) & 0xFFFFFFFFFFFF
-        return sig
+        """Changes whenever a parameter / buffer is written in place (optimizer step, load_state_dict, ActNorm initialisation) or moved
+        (.to(), .double()): the layers repack weights on the host side keyed on these versions, so a captured graph is only valid for
+        the signature it was captured under.  Cost matters at small batches (reference default B = 256: a replay is ~0.5 ms of device
+        time): the tensor list is cached (rebuilt when the module tree is re-applied, see FlowSequential._apply) and only the version
+        counters are read per call -- ~0.1 ms for the ~1200 tensors of cfg2 instead of 7 ms for a state_dict() walk."""
+        ts = self._tensors
+        if ts is None:
+            ts = self._tensors = list(self.model.parameters()) + list(self.model.buffers())
+            self._ptrs = hash(tuple(t.data_ptr() for t in ts))
+        return hash(tuple(map(_version_of, ts))) ^ self._ptrs
+
+    def invalidate(self):
+        """Forget the cached tensor list and every captured graph (the module tree was moved / cast / restructured)."""
+        self._tensors = None
+        self._entries.clear()
 
     def _capture(self, x, ctx, device):
+        with torch.cuda.device(device):
+            return self._capture_on(x, ctx, device)
+
+    def _capture_on(self, x, ctx, device):
         e = _Entry()
+        e.device = device
         e.x = torch.empty(x.shape, device=device, dtype=x.dtype)
         e.ctx = None if ctx is None else torch.empty(ctx.shape, device=device, dtype=ctx.dtype)
         e.x.copy_(x)
@@ -67,7 +93,7 @@ class GraphedLogProb:
         if e is not None and e.signature != self._signature():    # weights changed since capture (training step, load_state_dict)
             e = None
         if e is None:
-            dev = x.device if x.is_cuda else torch.device('cuda', torch.cuda.current_device())
+            dev = x.device if x.is_cuda else self._device()
             e = self._entries[key] = self._capture(x, ctx, dev)
         return e
 
@@ -77,6 +103,13 @@ class GraphedLogProb:
     def __call__(self, x, ctx=None, clone: bool = True):
         """x / ctx may live on the device or in (pinned) host memory; returns the (B, M) log-probabilities."""
         e = self.entry(x, ctx)
+        if e.device.index != torch.cuda.current_device():
+            with torch.cuda.device(e.device):
+                return self._replay(e, x, ctx, clone)
+        return self._replay(e, x, ctx, clone)
+
+    @staticmethod
+    def _replay(e, x, ctx, clone):
         e.x.copy_(x, non_blocking=True)
         if ctx is not None:
             e.ctx.copy_(ctx, non_blocking=True)
@@ -89,7 +122,11 @@ class GraphedLogProb:
         stream while the captured graph of batch i replays (two device staging buffers); the device-to-host copy of each result
         is queued right behind its replay.  Returns after everything has completed.  `post(logp)` (optional) maps the replay's
         output to the tensor that is copied out (e.g. the all-gather of a sharded batch)."""
-        dev = torch.device('cuda', torch.cuda.current_device())
+        with torch.cuda.device(self._device()):
+            return self._stream_on(batches, outs, post)
+
+    def _stream_on(self, batches, outs, post):
+        dev = self._device()
         comp = torch.cuda.current_stream(dev)
         copy_stream = getattr(self, '_copy_stream', None)
         if copy_stream is None:
@@ -132,7 +169,7 @@ class GraphedTrainStep:
 
     def __init__(self, model, loss_fn, x, ctx, gt, warmup: int = 2):
         self.model, self.loss_fn = model, loss_fn
-        self.static = (x.clone(), ctx.clone(), None if gt is None else gt.clone())
+        self.static = (x.clone(), None if ctx is None else ctx.clone(), None if gt is None else gt.clone())
         params = [p for p in model.parameters() if p.requires_grad]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -145,13 +182,17 @@ class GraphedTrainStep:
         for p in params:
             p.grad = None                                # the captured backward allocates the static .grad tensors in the graph's pool
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        from .layers.flowlayer import live_capture
+        # live_capture: everything derived from a trainable parameter (log|det NN|, NN^-1, mixture tables, masked weights) is recomputed by
+        # kernels recorded in the graph instead of being served from the version-keyed host caches the warm-up filled
+        with live_capture(), torch.cuda.graph(self.graph):
             self.loss = loss_fn(model, *self.static)
             self.loss.backward()
 
     def __call__(self, x, ctx, gt=None):
         self.static[0].copy_(x, non_blocking=True)
-        self.static[1].copy_(ctx, non_blocking=True)
+        if ctx is not None:
+            self.static[1].copy_(ctx, non_blocking=True)
         if gt is not None:
             self.static[2].copy_(gt, non_blocking=True)
         self.graph.replay()

@@ -210,10 +210,13 @@ class EncoderBatch:
         """Noise of every member in layer order.  With a replayed tape (tests) each member draws on its own, with the reference's
         shapes; from torch's generator the normal and the uniform draws are each ONE call cut into per-member (B, width) blocks
         (same distribution, ~40 launches fewer per forward)."""
-        if rng._source is not None:
+        if rng._source is not None or not rng._encoder_draws_batched:
             return [f._draw(B, w, device) for (_, f), w in zip(self.members, widths)]
         kinds = ['none' if f.surj.kind == 'eyesample' else ('rand' if f.surj.kind == 'uniform' else 'randn') for _, f in self.members]
         out = [None] * len(kinds)
+        rec = rng._recorder
+        if rec is not None:
+            rec.paused = True                         # the flat draws are recorded below as the per-member blocks, in layer order
         for kind, fn in (('rand', rng.rand), ('randn', rng.randn)):
             idx = [i for i, k in enumerate(kinds) if k == kind]
             if not idx:
@@ -222,6 +225,11 @@ class EncoderBatch:
             flat, off = fn((total,), device), 0
             for i in idx:
                 out[i] = flat[off: off + B * widths[i]].view(B, widths[i]); off += B * widths[i]
+        if rec is not None:
+            rec.paused = False
+            for k, t in zip(kinds, out):
+                if t is not None:
+                    rec.add(k, t)
         return out
 
     def run(self, context):

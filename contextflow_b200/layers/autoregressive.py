@@ -37,8 +37,9 @@ class MaskedConv2d(nn.Conv2d):
     def masked_weight(self):
         """masked_conv_2d.py:21-23 multiplies `weight.data` by the mask in place on every forward; once per weight version is the
         same state (the product is idempotent)."""
+        from .flowlayer import derived_is_live
         key = (self.weight.data_ptr(), self.weight._version)
-        if self._masked_version != key:
+        if self._masked_version != key or derived_is_live([self.weight]):
             with torch.no_grad():
                 self.weight.data.mul_(self.mask)
             self._masked_version = (self.weight.data_ptr(), self.weight._version)

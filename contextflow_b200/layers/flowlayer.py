@@ -40,6 +40,27 @@ def inference_only(t: torch.Tensor):
                                   'context-free conv stacks train through contextflow_b200.training (DESIGN.md §8 f-1)')
 
 
+LIVE_CAPTURE = False     # set by graphed.GraphedTrainStep while it captures a training step (see PackCache.get)
+
+
+class live_capture:
+    """While a TRAINING step is being captured into a CUDA graph, quantities derived from trainable parameters (log|det NN|, NN^-1,
+    mixture tables, masked weights, repacked operands) must be recomputed by kernels recorded IN the graph: the optimizer rewrites the
+    parameters between replays, and a cache hit at capture time would bake the warm-up's values into every replay."""
+
+    def __enter__(self):
+        global LIVE_CAPTURE
+        self._prev, LIVE_CAPTURE = LIVE_CAPTURE, True
+
+    def __exit__(self, *exc):
+        global LIVE_CAPTURE
+        LIVE_CAPTURE = self._prev
+
+
+def derived_is_live(tensors):
+    return LIVE_CAPTURE and any(getattr(t, 'requires_grad', False) for t in tensors)
+
+
 class PackCache:
     """One-time weight repacking (K-major, padded) keyed on the source tensors' version counters and storage."""
 
@@ -47,6 +68,9 @@ class PackCache:
         self._store = {}
 
     def get(self, name, tensors, build):
+        if derived_is_live(tensors):                 # recorded in the graph, reads the live parameters on every replay; never cached
+            with torch.no_grad():
+                return build()
         key = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
         hit = self._store.get(name)
         if hit is None or hit[0] != key:

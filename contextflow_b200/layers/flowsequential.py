@@ -24,6 +24,14 @@ class FlowSequential(nn.Module):
     def __iter__(self):
         yield from self.sequence_modules
 
+    def _apply(self, fn, *args, **kwargs):
+        """.to() / .cuda() / .double(): parameters may be re-created, so captured graphs and their cached tensor list are dropped."""
+        out = super()._apply(fn, *args, **kwargs)
+        g = getattr(self, '_graphed', None)
+        if g is not None:
+            g.invalidate()
+        return out
+
     def _encoder_groups(self):
         """{index of first member layer: EncoderBatch}: runs of layers whose context encoders can share one launch.  A run
         ends at any layer that draws noise itself (Augment, Dequantization) or whose context_net is an opaque callable."""
@@ -102,7 +110,7 @@ class FlowSequential(nn.Module):
         g = getattr(self, '_graphed', None)
         if g is not None and input.is_cuda and not torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing():
             from .. import rng
-            if rng._source is None:                            # replayed noise tapes (tests) are host-driven: stay eager
+            if rng._source is None and rng._recorder is None:  # replayed noise tapes / draw recording (tests) are host-driven: stay eager
                 return g(input, context)
         return self.log_prob_eager(input, context)
 

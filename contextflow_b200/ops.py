@@ -35,7 +35,19 @@ def set_timer(t):
     _timer = t
 
 
+_dev = None            # device of the current op's tensors (set by _need_cuda): launches go to ITS current stream under ITS context
+
+
 def _call(name, args, label=None):
+    global _work
+    if _dev is not None and _dev.index != torch.cuda.current_device():
+        # the reference builds torch.device('cuda:{gpu}') and never calls set_device (model.py:170): launch under the tensors' device
+        with torch.cuda.device(_dev):
+            return _call_on_device(name, args)
+    return _call_on_device(name, args)
+
+
+def _call_on_device(name, args):
     global _work
     fn = getattr(lib(), 'cfpp_' + name)
     if _timer is None:
@@ -56,13 +68,23 @@ def _set_work(**kw):
 
 
 def _stream():
-    return vp(torch.cuda.current_stream().cuda_stream)
+    return vp(torch.cuda.current_stream(_dev).cuda_stream)
 
 
 def _need_cuda(*ts):
+    global _dev
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError('contextflow_b200 kernels run on CUDA tensors only (no CPU fallback); got a CPU tensor')
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f'contextflow_b200: tensor arguments live on different devices ({dev} and {t.device})')
+    if dev is not None:
+        _dev = dev
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:
@@ -463,6 +485,7 @@ def vit_tc_mode() -> str:
 
 def vit_tc_pack(mats):
     """mats: [(weight (out, in) row-major, n_rows, k_cols)] in chunk order -> packed fp16 hi/lo weight stream of cfpp_vit_tc_fwd."""
+    _need_cuda(*[m[0] for m in mats])
     chunk = int(lib().cfpp_vit_tc_pack_bytes(0))
     out = torch.empty(chunk * len(mats), device=mats[0][0].device, dtype=torch.uint8)
     keep = []

@@ -12,7 +12,19 @@ import contextlib
 import torch
 
 _source = None            # object with rand(shape, device=, dtype=) / randn(...), or None for torch's generators
+_recorder = None          # DrawRecorder: keeps every draw of a forward, in the reference's order (parity checks at large batches)
 _dequant_on_host = False  # True reproduces uniform.py:32 literally (CPU generator + H2D copy every batch)
+_encoder_draws_batched = True   # False: every context encoder draws its own (B, width) block, i.e. the reference's generator stream
+
+
+def set_reference_streams(flag: bool = True):
+    """flag=True: consume torch's generators EXACTLY as the reference does -- image dequantisation noise from the CPU generator
+    (uniform.py:32) and one device draw per context encoder in layer order (gaussian.py:265, dequantize.py:57) -- so that, under the
+    same torch.manual_seed, this path and the reference's torch layers on the same GPU see identical noise (tests/test_gpu_boundary.py
+    compares the unmodified experiment loops that way).  Default (False): dequantisation noise drawn on the device and all encoder
+    noise of a forward cut from one draw -- same distributions, fewer launches, no per-batch host RNG.  Env: CFPP_RNG=reference."""
+    global _dequant_on_host, _encoder_draws_batched
+    _dequant_on_host, _encoder_draws_batched = bool(flag), not flag
 
 
 def set_dequant_mode(mode: str):
@@ -22,6 +34,11 @@ def set_dequant_mode(mode: str):
     if mode not in ('device', 'host'):
         raise ValueError(mode)
     _dequant_on_host = mode == 'host'
+
+
+import os as _os
+if _os.environ.get('CFPP_RNG') == 'reference':
+    set_reference_streams(True)
 
 
 @contextlib.contextmanager
@@ -34,12 +51,61 @@ def use_source(src):
         _source = prev
 
 
+class DrawRecorder:
+    """Records the draws torch's own generators produce during a forward, as [(kind, tensor)] in the reference's draw order (SURVEY
+    App. C-7), WITHOUT changing how they are drawn: the recorded forward consumes exactly the Philox stream an unrecorded one (or a
+    CUDA-graph replay under the same seed) does.  `rows(idx)` replays a row subsample into the CPU oracle, which is how a batch of
+    8192 or 131072 samples is compared with the reference arithmetic at the sizes bench.py measures."""
+
+    def __init__(self):
+        self.log = []
+        self.paused = False
+
+    def add(self, kind, t):
+        if not self.paused:
+            self.log.append((kind, t))
+
+    def rows(self, idx):
+        return _RowReplay(self.log, idx)
+
+
+class _RowReplay:
+    def __init__(self, log, idx):
+        self.log, self.idx, self.pos = log, idx, 0
+
+    def _next(self, kind, shape):
+        k, t = self.log[self.pos]; self.pos += 1
+        out = t.detach()[self.idx.to(t.device)].cpu()
+        assert k == kind and tuple(out.shape) == tuple(shape), f'draw {self.pos - 1}: recorded {k}{tuple(out.shape)}, requested {kind}{tuple(shape)}'
+        return out
+
+    def rand(self, shape, device=None, dtype=None):
+        return self._next('rand', shape)
+
+    def randn(self, shape, device=None, dtype=None):
+        return self._next('randn', shape)
+
+
+@contextlib.contextmanager
+def record_draws():
+    global _recorder
+    prev, _recorder = _recorder, DrawRecorder()
+    try:
+        yield _recorder
+    finally:
+        _recorder = prev
+
+
 def rand(shape, device, dtype=torch.float32, host_draw=False):
     if _source is not None:
         return _source.rand(tuple(shape), device=device, dtype=dtype)
     if host_draw and _dequant_on_host:
-        return torch.rand(tuple(shape)).to(device=device, dtype=dtype)
-    return torch.rand(tuple(shape), device=device, dtype=dtype)
+        out = torch.rand(tuple(shape)).to(device=device, dtype=dtype)
+    else:
+        out = torch.rand(tuple(shape), device=device, dtype=dtype)
+    if _recorder is not None:
+        _recorder.add('rand', out)
+    return out
 
 
 def multinomial(probs, n):
@@ -52,4 +118,7 @@ def multinomial(probs, n):
 def randn(shape, device, dtype=torch.float32):
     if _source is not None:
         return _source.randn(tuple(shape), device=device, dtype=dtype)
-    return torch.randn(tuple(shape), device=device, dtype=dtype)
+    out = torch.randn(tuple(shape), device=device, dtype=dtype)
+    if _recorder is not None:
+        _recorder.add('randn', out)
+    return out

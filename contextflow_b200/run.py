@@ -33,6 +33,9 @@ def main(argv=None):
     if not argv:
         raise SystemExit(__doc__)
     script = os.path.abspath(argv[0])
+    # inference calls of model.log_prob (eval_epoch, experiment_ad.py:262 / experiment_cl.py:185) replay a captured CUDA graph per input
+    # shape; training calls (autograd on) always launch eagerly.  CFPP_CUDA_GRAPHS=0 in the environment keeps everything eager.
+    os.environ.setdefault('CFPP_CUDA_GRAPHS', '1')
     install_layers()
     sys.argv = [script] + argv[1:]
     sys.path.insert(0, os.path.dirname(script))

@@ -70,10 +70,11 @@ class GradAllReduce:
     def __call__(self, local_rows: int, total_rows: int):
         if self.world == 1:
             return
-        for p in self.params:
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
-        grads = [p.grad for p in self.params]
+        # parameters that received no gradient (e.g. an embedding table in front of probsample) stay at grad=None: which ones those are is
+        # structural, hence identical on every rank, and AdamW must skip them exactly as a single-process run does (no weight decay / moments)
+        grads = [p.grad for p in self.params if p.grad is not None]
+        if not grads:
+            return
         sizes = [g.numel() for g in grads]
         n = sum(sizes)
         if self._flat is None or self._flat.numel() != n or self._flat.device != grads[0].device:

@@ -158,17 +158,114 @@ def test_fused_plan_matches_oracle_ragged_batch():
 
 
 def test_cuda_graph_replay_matches_eager():
+    """The thing bench.py times is the CUDA-graph replay: with the same generator seed before the eager call and before the replay the
+    Philox draws are identical, so the log-probs must be identical BIT FOR BIT (same kernels, same inputs, same noise)."""
     case = CASES['cfg2']
     model = build_cuda_model(case)
     x, ctx = synth.make_inputs(case['conf'], 16, 'in4')
     xc, cc = x.cuda(), ctx.cuda()
     with torch.no_grad():
+        model.log_prob(xc, cc)                                    # ActNorm initialisation, weight packing
         torch.manual_seed(5); a = model.log_prob(xc, cc)
         model.enable_cuda_graphs()
-        b = model.log_prob(xc, cc)                                # different noise draws: compare statistically tight quantities only
+        model.log_prob(xc, cc)                                    # captures (its warm-up consumes draws)
+        torch.manual_seed(5); b = model.log_prob(xc, cc)
         b2 = model.log_prob(xc, cc)
+        torch.manual_seed(5); b3 = model.log_prob(xc, cc)
     assert a.shape == b.shape == (16, case['conf']['mixtures']) and torch.isfinite(b).all() and torch.isfinite(b2).all()
-    # the dequantisation / augment / encoder noise differs per call: same images, same model -> the same log-probs up to noise
-    rel = ((a - b).abs() / a.abs()).max().item()
-    assert rel < 0.5 and abs((a.mean() - b.mean()).item()) < 0.1 * abs(a.mean().item()), f'graph replay vs eager: max rel diff {rel:.3f}'
+    assert torch.equal(a, b), f'graph replay differs from the eager launch sequence: max abs diff {(a - b).abs().max().item():.3e}'
+    assert torch.equal(b, b3)
     assert not torch.equal(b, b2)                                 # replays advance the Philox offset: fresh noise every batch
+
+
+# ---- parity at the batch sizes bench.py measures (VERDICT r1 "what's weak" 1-3) ------------------------------------------------------
+def _bench_like_inputs(conf, B, seed):
+    gen = torch.Generator().manual_seed(seed)
+    C, H, W = conf['data_size']
+    x = torch.randint(0, 256, (B, C, H, W), generator=gen).float() if conf['image'] else torch.rand(B, C, H, W, generator=gen)
+    ctx = torch.stack([torch.randint(0, k, (B,), generator=gen) for k in conf['contexts']], 1)
+    return x, ctx
+
+
+@pytest.mark.parametrize('name,B', [('cfg2', 8192), ('cfg4', 131072), ('cfg1', 8192), ('cfg3', 1024)])
+def test_bench_batch_matches_oracle_and_graph_replay(name, B):
+    """The configuration bench.py times: a full default batch through (1) the eager fused plan with recorded draws, (2) the CUDA-graph
+    replay under the same seed -- bit-identical to (1) -- and (3) the CPU oracle on a 256-row subsample replaying the recorded noise rows.
+    At these sizes the context-bucketed mixture kernel (B >= 32 x context tuples), multi-tile persistent CTAs and the single batched
+    encoder-noise draw are what runs; none of them is reached by the small-batch golden cases."""
+    from oracle import check
+    case = CASES[name]
+    conf = case['conf']
+    model = build_cuda_model(case)
+    x, ctx = _bench_like_inputs(conf, B, 77)
+    xc, cc = x.cuda(), ctx.cuda()
+    with torch.no_grad():
+        model.log_prob(xc[:64], cc[:64])                          # packing / lazy state
+    logp, rec = check.recorded_log_prob(model, xc, cc, seed=11)
+    assert model._fastpath.usable(xc, cc)
+    res = check.rows_parity(model, conf, xc, cc, seed=11, n_rows=256, logp=logp, rec=rec)
+    assert res['ok'], f'{name} B={B}: {res}'
+    model.enable_cuda_graphs()
+    with torch.no_grad():
+        model.log_prob(xc, cc)                                    # capture
+        torch.manual_seed(11); rep = model.log_prob(xc, cc)
+    assert torch.equal(rep, logp), f'{name} B={B}: graph replay differs from eager, max abs {(rep - logp).abs().max().item():.3e}'
+
+
+def _encoder_outputs(model, ctx, tape):
+    """{layer index: (c, logp_c)} of every flow layer's context encoder, evaluated by the batched encoder launch the fused plan uses."""
+    out = {}
+    with torch.no_grad(), rng.use_source(tape):
+        groups = model._encoder_groups()
+        assert len(groups) == 1
+        batch = next(iter(groups.values()))
+        batch.run(ctx)
+        plans = {id(p): (p, f) for p, f in batch.members}
+        for i, m in enumerate(model.sequence_modules):
+            p = getattr(m, '_plan', None)
+            if p is not None and id(p) in plans:
+                out[i] = (p.preset[0].clone(), p.preset[1].clone()); p.preset = None
+    return out
+
+
+@pytest.mark.parametrize('name', ['cfg3', 'cfg2', 'atm_argmax2', 'mnist_eye_vardeq2', 'mnist_onehot_uniform'])
+def test_every_context_value_is_encoded_exactly(name):
+    """Exhaustive sweep of the context space (all 68 ATM entities, all 15 x 5 CIFAR corruption tuples, ...): the integer part of every
+    encoder's output -- argmax sign bits MSB first with the zero pad column (dequantize.py:196-211,239-268), the one-hot / eye code under
+    the dequantisation noise (dequantize.py:55-63,107-116) -- is BIT EXACT against the oracle for every context value and every layer;
+    the full (c, logp_c) agrees within the z / ldj gates."""
+    case = CASES[name]
+    conf = case['conf']
+    model = build_cuda_model(case)
+    cards = conf['contexts']
+    grids = torch.cartesian_prod(*[torch.arange(k) for k in cards]).reshape(-1, len(cards))
+    ctx = torch.cat([grids, grids.flip(0)], 0)                    # every tuple twice, different noise rows
+    B = ctx.shape[0]
+    assert B == 2 * int(np.prod(cards))
+    g = load_golden(name)
+    stack, state = golden_state(g, case)
+    got = _encoder_outputs(model, ctx.cuda(), synth.NoiseTape('sweep'))
+    assert len(got) >= 3
+    tape = synth.NoiseTape('sweep')
+    P = O._P(state, torch.float32)
+    n_checked = 0
+    for lay in stack['layers']:
+        if lay.get('enc') is None or lay['op'] == 'splitprior':
+            continue
+        i = int(lay['key'])
+        spec = lay['enc']
+        c_ref, lp_ref = O.context_encode(P, state, f'{i}.context_net', spec, ctx, tape, torch.float32)
+        c, lp = got[i][0].cpu(), got[i][1].cpu()
+        assert_close(c.numpy(), c_ref.numpy(), Z_RTOL, Z_ATOL, f'{name} layer {i} encoder c')
+        assert_close(lp.numpy(), lp_ref.numpy(), L_RTOL, L_ATOL, f'{name} layer {i} encoder logp_c')
+        if spec['type'] == 'argmax':
+            bits = torch.cat([O.int_to_bits(ctx[:, j], b) for j, b in enumerate(spec['bits'])], -1)
+            if bits.shape[-1] % 2:
+                bits = torch.cat([bits, torch.zeros(B, 1, dtype=bits.dtype)], -1)
+            assert torch.equal(torch.sign(c), (bits * 2 - 1).float()), f'{name} layer {i}: argmax sign bits'
+        else:                                                     # uniform / vardeq: c * qbins = code + noise in [0, 1)
+            q = state[f'{i}.context_net.1.qbins']
+            code = torch.cat([torch.nn.functional.one_hot(ctx[:, j], k) for j, k in enumerate(cards)], 1) if spec['emb'] == 'onehot' else ctx
+            assert torch.equal(torch.floor(c * q).long(), code.long()), f'{name} layer {i}: integer code under the dequantisation noise'
+        n_checked += 1
+    assert n_checked == len(got)

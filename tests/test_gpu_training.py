@@ -249,6 +249,88 @@ def test_graphed_train_step_matches_eager():
             assert torch.equal(got[k], p.grad), k
 
 
+@pytest.mark.parametrize('name,B', [('cfg1', 32), ('cifar_vardeq', 12), ('mnist_maf', 16), ('cifar_gen', 16)])
+def test_graphed_train_steps_with_optimizer_match_eager(name, B):
+    """Three AdamW steps driven by GraphedTrainStep replays land on the parameters three eager steps produce, bit for bit.  The
+    optimizer rewrites the parameters between replays, so everything derived from them (log|det NN| and NN^-1 of Conv1x1 / FC, the
+    mixture tables, mask-multiplied MAF weights) must be recomputed INSIDE the captured graph (layers/flowlayer.py:live_capture);
+    a graph that served them from the host caches filled by the warm-up would diverge from step 2 on."""
+    import copy
+    from contextflow_b200.graphed import GraphedTrainStep
+    case = dict(CASES[name], B=B)
+    spec = TRAINING_CASES[name]
+    ds = case['conf']['data_size']
+    M = case['conf']['mixtures']
+    m_eager = build_cuda_model(case).train()
+    xw, cw = case_inputs(dict(case, iseed='gw'))
+    with torch.no_grad():                                        # ActNorm data-dependent initialisation before the copy: both arms start equal
+        m_eager.log_prob(xw.cuda(), None if cw is None else cw.cuda())
+    m_graph = copy.deepcopy(m_eager)
+    batches = [case_inputs(dict(case, iseed=f'gs{i}')) for i in range(3)]
+    gts = [labels(f'gt{i}', B, M).cuda() for i in range(3)]
+
+    def loss_fn(m, x, c, gt):
+        return reference_loss(m, x, c, gt, ds, spec)[0]
+    opt_e = torch.optim.AdamW([p for p in m_eager.parameters() if p.requires_grad], lr=1e-3)
+    opt_g = torch.optim.AdamW([p for p in m_graph.parameters() if p.requires_grad], lr=1e-3)
+    x0, c0 = batches[0]
+    step = GraphedTrainStep(m_graph, loss_fn, x0.cuda(), None if c0 is None else c0.cuda(), gts[0])
+    for i, ((x, c), gt) in enumerate(zip(batches, gts)):
+        xc, cc = x.cuda(), None if c is None else c.cuda()
+        torch.manual_seed(100 + i)
+        opt_e.zero_grad(set_to_none=True)
+        le = loss_fn(m_eager, xc, cc, gt); le.backward(); opt_e.step()
+        torch.manual_seed(100 + i)
+        lg = step(xc, cc, gt); opt_g.step()
+        assert le.item() == lg.item(), f'{name} step {i}: loss {le.item()} (eager) vs {lg.item()} (graph replay)'
+        for (k, pe), (_, pg) in zip(m_eager.named_parameters(), m_graph.named_parameters()):
+            assert torch.equal(pe, pg), f'{name} step {i}: parameter {k} differs after the optimizer step'
+
+
+def test_graphed_train_step_without_context():
+    """A generalist trained with context=None (model.log_prob(x)) goes through GraphedTrainStep too."""
+    from contextflow_b200.graphed import GraphedTrainStep
+    case = dict(CASES['cfg4'], B=16)
+    spec = TRAINING_CASES['cfg4']
+    model = build_cuda_model(case).train()
+    x, _ = case_inputs(case)
+
+    def loss_fn(m, x, c, gt):
+        return reference_loss(m, x, c, gt, case['conf']['data_size'], spec)[0]
+    torch.manual_seed(3)
+    step = GraphedTrainStep(model, loss_fn, x.cuda(), None, None)
+    torch.manual_seed(4); lg = step(x.cuda(), None).item()
+    got = {k: p.grad.clone() for k, p in model.named_parameters() if p.requires_grad}
+    model.zero_grad(set_to_none=True)
+    torch.manual_seed(4); le = loss_fn(model, x.cuda(), None, None); le.backward()
+    assert lg == le.item()
+    for k, p in model.named_parameters():
+        if p.requires_grad:
+            assert torch.equal(got[k], p.grad), k
+
+
+def test_context_mixture_backward_large_sample_fallback():
+    """cfpp_gmm_ctx_train_bwd keeps eight partial dx rows in shared memory; a sample too large for that (9 x D*HW floats > 200 KB)
+    takes the recompute-sigma path instead of failing.  Both paths against float64 autograd."""
+    for D, H, W in ((6, 8, 8), (40, 16, 12)):                   # 384 elements (partials) / 7680 elements (fallback)
+        B, M, K = 3, 2, 4
+        n = D * H * W
+        x = synth.normal('gf:x', (B, D, H, W)); mG = synth.normal('gf:m', (M, K, D, H, W)); sG = synth.normal('gf:s', (M, K, D, H, W))
+        wG = synth.normal('gf:w', (M, K)); c = 0.3 * synth.normal('gf:c', (B, 2 * M * K * D)); g = synth.normal('gf:g', (B, M))
+        xd, cd = x.double().requires_grad_(True), c.double().requires_grad_(True)
+        cm, cs = cd.view(B, 2, M, K, D, 1, 1)[:, 0], cd.view(B, 2, M, K, D, 1, 1)[:, 1]
+        mu = mG.double()[None] + cm; sig = F.softplus(sG.double()[None] + cs)
+        comp = (-0.5 * ((xd[:, None, None] - mu) / sig) ** 2 - sig.log() - 0.5 * np.log(2 * np.pi)).flatten(3).sum(-1)
+        logw = torch.log_softmax(torch.log(torch.softmax(wG.double(), -1).clamp(1.19e-7, 1 - 1.19e-7)), -1)
+        ref = torch.logsumexp(comp + logw[None], -1)
+        (ref * g.double()).sum().backward()
+        logp, resp = ops.gmm_ctx_train_fwd(x.cuda(), mG.cuda(), sG.cuda(), wG.cuda(), c.cuda())
+        assert_close(logp.cpu().numpy(), ref.detach().numpy(), 1e-4, 1e-3, 'ctx mixture fwd')
+        dx, dc = ops.gmm_ctx_train_bwd(x.cuda(), mG.cuda(), sG.cuda(), c.cuda(), resp, g.cuda())
+        assert_close(dx.cpu().numpy(), xd.grad.numpy(), 1e-3, 1e-4 * float(xd.grad.abs().max()), f'dx n={n}')
+        assert_close(dc.cpu().numpy(), cd.grad.numpy(), 1e-3, 1e-4 * float(cd.grad.abs().max()), f'dc n={n}')
+
+
 def test_unsupported_layers_raise_under_autograd():
     model = build_cuda_model(CASES['cifar_conventional']).train()     # conventional (concatenated-context) specialists: no backward kernels yet
     x, ctx = case_inputs(CASES['cifar_conventional'])

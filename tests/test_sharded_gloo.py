@@ -88,12 +88,13 @@ def _grad_worker(rank, world, port, B, ret):
         cost.backward()
     lo, hi = shard_bounds(B, world, rank)
     loss_grads(lo, hi)
-    GradAllReduce(params)(hi - lo, B)
-    got = [p.grad.clone() for p in params]
+    unused = torch.nn.Parameter(torch.ones(3))                 # receives no gradient on any rank: must stay grad=None (AdamW skips it)
+    GradAllReduce(params + [unused])(hi - lo, B)
+    got = [None if p.grad is None else p.grad.clone() for p in params]
     loss_grads(0, B)
-    ok = all((not g.any()) if p.grad is None else torch.allclose(g, p.grad, rtol=1e-4, atol=1e-5 * float(p.grad.abs().max()) + 1e-9)
+    ok = all((g is None) if p.grad is None else torch.allclose(g, p.grad, rtol=1e-4, atol=1e-5 * float(p.grad.abs().max()) + 1e-9)
              for g, p in zip(got, params))
-    ret[rank] = bool(ok) and sum(p.grad is not None for p in params) >= 20
+    ret[rank] = bool(ok) and unused.grad is None and sum(p.grad is not None for p in params) >= 20
     dist.destroy_process_group()
 
 
