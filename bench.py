@@ -37,6 +37,7 @@ def parse():
                     help='log_prob (default): the headline forward log-density path; train / reverse: the SURVEY §8(f) rows, measured by '
                          'tools/bench_training.py / tools/bench_inverse.py (their own JSON lines)')
     ap.add_argument('--secondary', default='cfg4', choices=sorted(WORKLOADS) + [''], help='second workload measured in the same run ("" = none)')
+    ap.add_argument('--no-parity', action='store_true', help='skip the oracle parity check of the timed batch (profiling runs)')
     ap.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying the captured CUDA graph')
     return ap.parse_args()
 
@@ -350,6 +351,10 @@ def measure(a, workload, B, rank, world, dev, with_e2e=True, parity=True):
         sec = v['ms'] / 1e3
         kernels[name] = {'share': round(v['ms'] / total_ms, 4), 'ms_per_step': round(v['ms'] / a.steps, 4), 'launches_per_step': v['n'] / a.steps,
                          'GBps': round(v['bytes'] / sec / 1e9, 1) if sec > 0 else None, 'TFLOPps': round(v['flops'] / sec / 1e12, 3) if sec > 0 else None}
+        if v.get('shapes'):
+            kernels[name]['by_shape'] = {k: {'ms_per_launch': round(w['ms'] / w['n'], 4), 'launches_per_step': w['n'] / a.steps,
+                                             'GBps': round(w['bytes'] / (w['ms'] / 1e3) / 1e9, 1), 'TFLOPps': round(w['flops'] / (w['ms'] / 1e3) / 1e12, 3)}
+                                         for k, w in v['shapes'].items() if w['ms'] > 0}
 
     def traffic_of(name):
         try:                                                   # DRAM bytes of one launch from the committed ncu --set full capture
@@ -439,12 +444,12 @@ def main():
         os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=dev)
     B = a.batch or DEFAULT_BATCH[workload]
-    res = measure(a, workload, B, rank, world, dev)
+    res = measure(a, workload, B, rank, world, dev, parity=not a.no_parity)
     sec = None
     if a.secondary and a.secondary != workload:
         # BASELINE configs[4] names two shapes for the throughput sweep (CIFAR-shape conv AND SMAP-shape trans): the second one rides
         # along in the same line so that it is seen at every N the driver runs
-        sec = measure(a, a.secondary, DEFAULT_BATCH[a.secondary], rank, world, dev, with_e2e=False, parity=True)
+        sec = measure(a, a.secondary, DEFAULT_BATCH[a.secondary], rank, world, dev, with_e2e=False, parity=not a.no_parity)
     if saved_stdout is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

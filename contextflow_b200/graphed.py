@@ -23,7 +23,7 @@ _version_of = operator.attrgetter('_version')
 
 
 class _Entry:
-    __slots__ = ('graph', 'x', 'ctx', 'out', 'launches', 'signature', 'device')
+    __slots__ = ('graph', 'x', 'ctx', 'out', 'launches', 'signature', 'device', 'host_draws')
 
 
 class GraphedLogProb:
@@ -69,6 +69,10 @@ class GraphedLogProb:
         e.x.copy_(x)
         if ctx is not None:
             e.ctx.copy_(ctx)
+        # the eager warm-up and the capture consume random numbers; the generators are put back afterwards so that the FIRST replay sees
+        # exactly the draws an eager call at this point would have seen (same seed => same noise as the eager path / the reference)
+        from . import rng
+        cpu_state, cuda_state = torch.get_rng_state(), torch.cuda.get_rng_state(device)
         cur = torch.cuda.current_stream(device)
         side = torch.cuda.Stream(device)
         side.wait_stream(cur)
@@ -79,9 +83,13 @@ class GraphedLogProb:
         torch.cuda.synchronize(device)
         e.graph = torch.cuda.CUDAGraph()
         l0 = _cabi.launch_count()
+        del rng._capture_host_draws[:]
         with torch.no_grad(), torch.cuda.graph(e.graph, pool=self._pool):
             e.out = self.model.log_prob_eager(e.x, e.ctx)
         e.launches = _cabi.launch_count() - l0
+        e.host_draws = list(rng._capture_host_draws)
+        del rng._capture_host_draws[:]
+        torch.set_rng_state(cpu_state); torch.cuda.set_rng_state(cuda_state, device)
         if self._pool is None:
             self._pool = e.graph.pool()
         e.signature = self._signature()
@@ -113,6 +121,8 @@ class GraphedLogProb:
         e.x.copy_(x, non_blocking=True)
         if ctx is not None:
             e.ctx.copy_(ctx, non_blocking=True)
+        for buf in e.host_draws:                               # rng 'host' mode: the CPU-generator draws of this forward (uniform.py:32)
+            buf.copy_(torch.rand(buf.shape, dtype=buf.dtype))
         e.graph.replay()
         return e.out.clone() if clone else e.out
 
@@ -152,6 +162,8 @@ class GraphedLogProb:
             if hc is not None:
                 e.ctx.copy_(stage[k][1], non_blocking=True)
             consumed[k].record(comp)
+            for buf in e.host_draws:
+                buf.copy_(torch.rand(buf.shape, dtype=buf.dtype))
             e.graph.replay()
             res = e.out if post is None else post(e.out)
             outs[i].copy_(res[:outs[i].shape[0]], non_blocking=True)

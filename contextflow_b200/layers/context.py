@@ -12,6 +12,9 @@ class ContextPlan:
         self._owner = None
         self.preset = None          # (c, logp_c) computed ahead by an EncoderBatch launch of the enclosing FlowSequential
 
+    def __deepcopy__(self, memo):                    # copy.deepcopy(model): the copy re-recognises its own encoder lazily
+        return ContextPlan()
+
     def fused_for(self, context_net):
         from ._encoder_desc import FusedEncoder
         if self._owner is not context_net:

@@ -67,6 +67,9 @@ class PackCache:
     def __init__(self):
         self._store = {}
 
+    def __deepcopy__(self, memo):                    # packed operands / ctypes descriptors belong to the tensors they were built from
+        return PackCache()
+
     def get(self, name, tensors, build):
         if derived_is_live(tensors):                 # recorded in the graph, reads the live parameters on every replay; never cached
             with torch.no_grad():

@@ -24,6 +24,22 @@ class FlowSequential(nn.Module):
     def __iter__(self):
         yield from self.sequence_modules
 
+    def __deepcopy__(self, memo):
+        """copy.deepcopy(model) (EMA / best-model snapshots): the execution plan, encoder batches and captured graphs hold ctypes
+        descriptors and device pointers of THIS module tree, so the copy starts without them and rebuilds them lazily."""
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ('_fastpath', '_graphed', '_groups'):
+                continue
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        new.__dict__['_groups'] = None
+        new.__dict__['_graphed'] = None
+        if self._graphed is not None:
+            new.enable_cuda_graphs()
+        return new
+
     def _apply(self, fn, *args, **kwargs):
         """.to() / .cuda() / .double(): parameters may be re-created, so captured graphs and their cached tensor list are dropped."""
         out = super()._apply(fn, *args, **kwargs)

@@ -20,9 +20,13 @@ class OpTimer:
     def summary(self):
         out = {}
         for name, s, e, work in self.records:
-            d = out.setdefault(name, dict(ms=0.0, n=0, bytes=0.0, flops=0.0))
-            d['ms'] += s.elapsed_time(e); d['n'] += 1
+            d = out.setdefault(name, dict(ms=0.0, n=0, bytes=0.0, flops=0.0, shapes={}))
+            ms = s.elapsed_time(e)
+            d['ms'] += ms; d['n'] += 1
             d['bytes'] += work.get('bytes', 0.0); d['flops'] += work.get('flops', 0.0)
+            if 'shape' in work:
+                sh = d['shapes'].setdefault(work['shape'], dict(ms=0.0, n=0, bytes=0.0, flops=0.0))
+                sh['ms'] += ms; sh['n'] += 1; sh['bytes'] += work.get('bytes', 0.0); sh['flops'] += work.get('flops', 0.0)
         return out
 
 
@@ -237,7 +241,7 @@ def conv1x1(x, NN, logabsdet, c=None, logp_c=None, contextflow=False, an_t=None,
         per_sample, an_logs = 2, an_t[:, D:]
     else:
         per_sample = int(an_t is not None and an_t.dim() == 2)
-    _set_work(bytes=8.0 * x.numel() + (0 if c is None else 4.0 * c.numel()), flops=2.0 * D * x.numel())
+    _set_work(bytes=8.0 * x.numel() + (0 if c is None else 4.0 * c.numel()), flops=2.0 * D * x.numel(), shape=f'D{D}xHW{HW}')
     _call('conv1x1_fwd', (_p(x), _p(z), _p(ldj), _p(_f32(NN)), _p(logabsdet), _p(None if c is None else _f32(c)),
                                  _p(logp_c), int(bool(contextflow)), _p(an_t), _p(an_logs), per_sample, _p(an_logp_c),
                                  float(an_logp_scale), B, D, HW, _stream()), 'conv1x1_fwd')
@@ -270,7 +274,7 @@ def coupling(x, h, add=None, logp_c=None, logp_scale=0.0):
     B, Cc = x.shape[0], x.shape[1]
     HW = x[0, 0].numel() if B else 1
     z = torch.empty_like(x); ldj = torch.empty(B, device=x.device, dtype=x.dtype)
-    _set_work(bytes=12.0 * x.numel())
+    _set_work(bytes=12.0 * x.numel(), shape=f'C{Cc}xHW{HW}')
     _call('coupling_fwd', (_p(x), _p(h), _p(None if add is None else _f32(add)), _p(logp_c), float(logp_scale),
                                   _p(z), _p(ldj), B, Cc, HW, _stream()), 'coupling_fwd')
     return z, ldj
@@ -437,7 +441,7 @@ def conv_cond_tc(x, cin, wpack, b1, b2, b3, ch, H, W, KH, KW, cout, bias1_b=None
     if not lib().cfpp_conv_cond_tc_supported(B, cin, ch, cout, H, W, KH, KW, bstride) or xv.data_ptr() % 16:
         return None
     h = torch.empty((B, cout, H, W), device=x.device, dtype=torch.float32)
-    _set_work(bytes=4.0 * B * H * W * (cin + cout), flops=2.0 * B * H * W * (cin * ch + ch * ch * KH * KW + ch * cout))
+    _set_work(bytes=4.0 * B * H * W * (cin + cout), flops=2.0 * B * H * W * (cin * ch + ch * ch * KH * KW + ch * cout), shape=f'Ch{ch}x{H}x{W}')
     _call('conv_cond_tc_fwd', (_p(xv), bstride, _p(h), _p(wpack), _p(b1), _p(None if bias1_b is None else _f32(bias1_b)), _p(b2), _p(b3),
                                B, cin, ch, cout, H, W, KH, KW, _stream()))
     return h
@@ -453,7 +457,7 @@ def conv_cond_tc_coupling(x, wpack, b1, b2, b3, ch, KH, KW, add=None, logp_c=Non
         return None
     z = torch.empty_like(x); ldj = torch.empty(B, device=x.device, dtype=torch.float32)
     cin = Cc // 2
-    _set_work(bytes=8.0 * x.numel(), flops=2.0 * B * H * W * (cin * ch + ch * ch * KH * KW + ch * Cc))
+    _set_work(bytes=8.0 * x.numel(), flops=2.0 * B * H * W * (cin * ch + ch * ch * KH * KW + ch * Cc), shape=f'Ch{ch}x{H}x{W}')
     _call('conv_cond_tc_coupling_fwd', (_p(x), _p(z), _p(ldj), _p(wpack), _p(b1), _p(None if bias1_b is None else _f32(bias1_b)), _p(b2), _p(b3),
                                         _p(None if add is None else _f32(add)), _p(logp_c), float(logp_scale), B, Cc, ch, H, W, KH, KW, _stream()))
     return z, ldj
@@ -574,7 +578,7 @@ def gmm_tile_logprob(x, table, M, K, ctx=None, cards=(), mean_table=None, mean_o
     ws = torch.empty(max(need, 1), device=x.device, dtype=torch.uint8)
     mt = None if mean_table is None else _f32(mean_table)
     carr = (_cabi.i32 * max(n, 1))(*[int(c) for c in cards])
-    _set_work(bytes=4.0 * B * D * HW + 4.0 * B * M, flops=3.0 * B * M * K * D * HW)
+    _set_work(bytes=4.0 * B * D * HW + 4.0 * B * M, flops=3.0 * B * M * K * D * HW, shape=f'D{D}xHW{HW}xK{n_keys}')
     _call('gmm_tile_logprob', (_p(xv), bstride, _p(table), _p(None if ctx is None else ctx.contiguous()), n, carr,
                                _p(mt), 0 if mt is None else mt.shape[1], int(mean_off), _p(logp_c), float(logp_scale),
                                _p(out), _p(ws), need, B, M, K, D, HW, _stream()))

@@ -14,6 +14,7 @@ import torch
 _source = None            # object with rand(shape, device=, dtype=) / randn(...), or None for torch's generators
 _recorder = None          # DrawRecorder: keeps every draw of a forward, in the reference's order (parity checks at large batches)
 _dequant_on_host = False  # True reproduces uniform.py:32 literally (CPU generator + H2D copy every batch)
+_capture_host_draws = []   # device buffers standing in for host draws inside the graph being captured (see rand)
 _encoder_draws_batched = True   # False: every context encoder draws its own (B, width) block, i.e. the reference's generator stream
 
 
@@ -100,6 +101,12 @@ def rand(shape, device, dtype=torch.float32, host_draw=False):
     if _source is not None:
         return _source.rand(tuple(shape), device=device, dtype=dtype)
     if host_draw and _dequant_on_host:
+        if torch.cuda.is_current_stream_capturing():
+            # a CPU draw cannot live inside a CUDA graph: the capture records a persistent device buffer that GraphedLogProb refills
+            # from the CPU generator before every replay (same stream of numbers as the reference's uniform.py:32)
+            out = torch.empty(tuple(shape), device=device, dtype=dtype)
+            _capture_host_draws.append(out)
+            return out
         out = torch.rand(tuple(shape)).to(device=device, dtype=dtype)
     else:
         out = torch.rand(tuple(shape), device=device, dtype=dtype)

@@ -202,7 +202,8 @@ def test_bench_batch_matches_oracle_and_graph_replay(name, B):
     with torch.no_grad():
         model.log_prob(xc[:64], cc[:64])                          # packing / lazy state
     logp, rec = check.recorded_log_prob(model, xc, cc, seed=11)
-    assert model._fastpath.usable(xc, cc)
+    with torch.no_grad():
+        assert model._fastpath.usable(xc, cc)
     res = check.rows_parity(model, conf, xc, cc, seed=11, n_rows=256, logp=logp, rec=rec)
     assert res['ok'], f'{name} B={B}: {res}'
     model.enable_cuda_graphs()

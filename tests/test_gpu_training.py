@@ -37,6 +37,22 @@ def reference_loss(model, x, ctx, gt, data_size, spec):
     return sup + uns, sup, uns
 
 
+def device_loss(data_size, spec):
+    """The same loss with every constant created up front on the device: nothing inside may touch host memory while a CUDA graph is
+    being captured (reference_loss builds torch.tensor(...) on the CPU per call, as experiment_ad.py does)."""
+    dim_inv = 1.0 / float(np.prod(data_size))
+    log_theta = nn.LogSigmoid()
+    crit = nn.CrossEntropyLoss(weight=None if spec['weight'] is None else torch.tensor(spec['weight']).cuda()) if spec['criterion'] else None
+
+    def loss_fn(m, x, c, gt):
+        logp = dim_inv * m.log_prob(x, context=c)
+        logp = torch.where(logp != logp, torch.zeros_like(logp), logp)
+        if crit is None:
+            return -spec['alpha'] * log_theta(logp).mean()
+        return crit(logp, gt) - spec['alpha'] * log_theta(torch.logsumexp(logp, -1)).mean()
+    return loss_fn
+
+
 @pytest.mark.parametrize('name', sorted(TRAINING_CASES))
 def test_gradients_match_reference_golden(name):
     case, spec = CASES[name], TRAINING_CASES[name]
@@ -269,8 +285,7 @@ def test_graphed_train_steps_with_optimizer_match_eager(name, B):
     batches = [case_inputs(dict(case, iseed=f'gs{i}')) for i in range(3)]
     gts = [labels(f'gt{i}', B, M).cuda() for i in range(3)]
 
-    def loss_fn(m, x, c, gt):
-        return reference_loss(m, x, c, gt, ds, spec)[0]
+    loss_fn = device_loss(ds, spec)
     opt_e = torch.optim.AdamW([p for p in m_eager.parameters() if p.requires_grad], lr=1e-3)
     opt_g = torch.optim.AdamW([p for p in m_graph.parameters() if p.requires_grad], lr=1e-3)
     x0, c0 = batches[0]
@@ -295,8 +310,7 @@ def test_graphed_train_step_without_context():
     model = build_cuda_model(case).train()
     x, _ = case_inputs(case)
 
-    def loss_fn(m, x, c, gt):
-        return reference_loss(m, x, c, gt, case['conf']['data_size'], spec)[0]
+    loss_fn = device_loss(case['conf']['data_size'], spec)
     torch.manual_seed(3)
     step = GraphedTrainStep(model, loss_fn, x.cuda(), None, None)
     torch.manual_seed(4); lg = step(x.cuda(), None).item()

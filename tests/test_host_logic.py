@@ -52,13 +52,21 @@ def test_fused_plan_is_not_used_on_cpu_tensors():
             model.log_prob(x, ctx)
 
 
-def test_reference_arm_prints_one_json_line():
+@pytest.mark.parametrize('force_port', ['1', '0'])
+def test_reference_arm_prints_one_json_line(force_port):
+    """--impl reference: the unmodified reference when a complete checkout exists (baseline/_ref or /root/reference), else the port."""
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', 'cfg4', '--batch', '64',
-                          '--steps', '1', '--warmup', '1'], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                          '--steps', '1', '--warmup', '1'], capture_output=True, text=True, timeout=300, cwd=ROOT,
+                         env=dict(os.environ, CFPP_BENCH_FORCE_PORT=force_port))
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['metric'] == 'flow_log_prob_samples_per_sec' and d['value'] > 0
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import refshim
+    want = 'port' if force_port == '1' or refshim.find_reference() is None else 'reference'
+    assert d['cpu_baseline']['kind'] == want and d['cpu_baseline']['cores'] >= 1
+    assert d['config']['batch_per_gpu'] == 131072                   # the reference arm reports this repo's arm's config; the bounded sample is described apart
+    assert '64-sample' in d['cpu_baseline']['sample']
     assert d['e2e'] == {'value': d['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
