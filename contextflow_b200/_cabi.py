@@ -55,6 +55,8 @@ _SIGNATURES = {
     'cfpp_prologue_fwd': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32, f32, vp]),
     'cfpp_slogdet': (i32, [vp, i32, vp, vp]),
     'cfpp_conv1x1_fwd': (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, f32, i32, i32, i32, vp]),
+    'cfpp_conv1x1_ctx_supported': (i32, [i32, i32, i32, i32]),
+    'cfpp_conv1x1_ctx_fwd': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, f32, i32, i32, i32, i32, vp]),
     'cfpp_actnorm_fwd': (i32, [vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp]),
     'cfpp_actnorm_stats': (i32, [vp, vp, vp, i32, i32, i32, vp]),
     'cfpp_coupling_fwd': (i32, [vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, vp]),
@@ -88,6 +90,8 @@ _SIGNATURES = {
     'cfpp_gmm_tile_logprob': (i32, [vp, i64, vp, vp, i32, C.POINTER(i32), vp, i32, i32, vp, f32, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
     'cfpp_ctx_encode': (i32, [vp, vp, vp, vp, C.POINTER(EncDesc), i32, i32, vp]),
     'cfpp_ctx_encode_batch': (i32, [vp, vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i32, vp]),
+    'cfpp_ctx_encode_flow_supported': (i32, [i32]),
+    'cfpp_ctx_encode_batch_flow': (i32, [vp, vp, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i32, vp]),
     'cfpp_embed_lookup': (i32, [vp, C.POINTER(vp), i32, i32, vp, i32, vp]),
     'cfpp_linear_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     'cfpp_cn_batch': (i32, [C.POINTER(CnJob), i32, C.POINTER(vp), C.POINTER(vp), i32, vp]),

@@ -200,6 +200,179 @@ __global__ void __launch_bounds__(128) ctx_encode_batch_kernel(const int64_t* __
   if (b < B) encode_sample(ctx, p.noise[e], p.c[e], p.logp[e], d, -1, b);
 }
 
+// ---- tiled form of the inner-flow encoders (vardeq / argmax / probsample) for a compile-time width C ------------------------------
+// The one-thread-per-sample walk above keeps x, y, h1, h2 in local memory (runtime C) and reads every weight from global memory at
+// dependent-load latency: ncu (r1u) showed 10 long-scoreboard stall cycles per issued instruction.  Here a CTA = 128 samples of ONE encoder:
+// the encoder's 2 x (FC, ActNormFC, CouplingFC) parameters are staged once in shared memory (FC transposed to K-major), every layer is
+//   out[o..o+3] = bias + sum_k W[k][o..o+3] * in[k]        k unrolled at compile time: `in` lives in registers,
+// the four weights arrive as one 128-bit warp-broadcast shared load per 4 FMAs, and the outputs bounce through the thread's own column of a
+// shared buffer ([feature][129]: conflict free) so that the next layer reads them back with static register indices.  Noise rows come in
+// and c rows go out through the same buffer, coalesced.
+constexpr int kEncTile = 128, kEncStride = kEncTile + 1;
+
+template <int C> struct EncFlowLayout {
+  static constexpr int Ch = C / 2, H2 = 2 * C;
+  static constexpr int fcT = 0, ant = fcT + C * C, ansc = ant + C, w1 = ansc + C, b1 = w1 + Ch * H2, w2 = b1 + H2, b2 = w2 + H2 * H2,
+                       w3 = b2 + H2, b3 = w3 + H2 * C, per_layer = b3 + C;
+  static constexpr int floats = 2 * per_layer + H2 * kEncStride + 4;          // + {fc_logabsdet[2], sum an_logs[2]}
+};
+
+template <int KIN, int NOUT, bool BIAS, bool RELU>
+__device__ __forceinline__ void enc_matvec(const float* __restrict__ W, const float* __restrict__ bias, const float (&in)[KIN], float* __restrict__ col) {
+#pragma unroll 2
+  for (int o = 0; o < NOUT; o += 4) {
+    float4 acc = BIAS ? *reinterpret_cast<const float4*>(bias + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < KIN; ++k) {
+      const float4 w = *reinterpret_cast<const float4*>(W + k * NOUT + o);
+      acc.x = fmaf(in[k], w.x, acc.x); acc.y = fmaf(in[k], w.y, acc.y); acc.z = fmaf(in[k], w.z, acc.z); acc.w = fmaf(in[k], w.w, acc.w);
+    }
+    if (RELU) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+    col[(o + 0) * kEncStride] = acc.x; col[(o + 1) * kEncStride] = acc.y; col[(o + 2) * kEncStride] = acc.z; col[(o + 3) * kEncStride] = acc.w;
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kEncTile) ctx_encode_flow_kernel(const int64_t* __restrict__ ctx, const cfpp_enc_desc* __restrict__ descs,
+                                                                   const EncBatchPtrs p, int B) {
+  using Lo = EncFlowLayout<C>;
+  constexpr int Ch = Lo::Ch, H2 = Lo::H2;
+  extern __shared__ float4 enc_smem4[];
+  __shared__ cfpp_enc_desc d;
+  float* sm = reinterpret_cast<float*>(enc_smem4);
+  float* bounce = sm + 2 * Lo::per_layer;                   // [H2][kEncStride]
+  float* scal = bounce + H2 * kEncStride;                   // fc_logabsdet[0..1], sum an_logs[0..1]
+  const int e = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < (int)(sizeof(cfpp_enc_desc) / 4); i += kEncTile)
+    reinterpret_cast<uint32_t*>(&d)[i] = reinterpret_cast<const uint32_t*>(descs + e)[i];
+  __syncthreads();
+  const float* noise = p.noise[e];
+  // ---- stage the encoder's parameters and this tile's noise rows ----
+  for (int L = 0; L < 2; ++L) {
+    float* w = sm + L * Lo::per_layer;
+    for (int i = tid; i < C * C; i += kEncTile) { const int r = i / C, c = i - r * C; w[Lo::fcT + c * C + r] = __ldg(d.fc[L] + i); }   // FC: y = NN x (conv1x1.py:80-96)
+    for (int i = tid; i < C; i += kEncTile) { w[Lo::ant + i] = __ldg(d.an_t[L] + i); w[Lo::ansc + i] = expf(-__ldg(d.an_logs[L] + i)); w[Lo::b3 + i] = __ldg(d.cb3[L] + i); }
+    for (int i = tid; i < Ch * H2; i += kEncTile) w[Lo::w1 + i] = __ldg(d.cw1t[L] + i);
+    for (int i = tid; i < H2; i += kEncTile) { w[Lo::b1 + i] = __ldg(d.cb1[L] + i); w[Lo::b2 + i] = __ldg(d.cb2[L] + i); }
+    for (int i = tid; i < H2 * H2; i += kEncTile) w[Lo::w2 + i] = __ldg(d.cw2t[L] + i);
+    for (int i = tid; i < H2 * C; i += kEncTile) w[Lo::w3 + i] = __ldg(d.cw3t[L] + i);
+    if (tid == 32 * L) {                                     // ActNormFC ldj = sum logs (actnorm.py:86-102), in index order like the per-sample walk
+      float sl = 0.f;
+      for (int i = 0; i < C; ++i) sl += d.an_logs[L][i];
+      scal[2 + L] = sl; scal[L] = d.fc_logabsdet[L][0];
+    }
+  }
+  // a CTA walks several 128-sample tiles of its encoder: the parameters are staged once
+  const int ntiles = (B + kEncTile - 1) / kEncTile;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const int b0 = tile * kEncTile, b = b0 + tid;
+  const bool live = b < B;
+  for (int idx = tid; idx < kEncTile * C; idx += kEncTile) {
+    const int s = idx / C, j = idx - s * C;
+    bounce[j * kEncStride + s] = (b0 + s < B) ? __ldg(noise + (int64_t)b0 * C + idx) : 0.f;
+  }
+  __syncthreads();
+  float* col = bounce + tid;
+  const int n = d.n_ctx;
+  const int64_t* cb = ctx + (int64_t)(live ? b : 0) * n;
+  auto x_in = [&](int j) -> float {                          // the embedded input value at output column j (as in encode_sample)
+    if (d.emb == CFPP_EMB_ONEHOT) {
+      int start = 0;
+      for (int f = 0; f < n; ++f) { if (j < start + d.card[f]) return (cb[f] == (int64_t)(j - start)) ? 1.f : 0.f; start += d.card[f]; }
+      return 0.f;
+    } else if (d.emb == CFPP_EMB_EYE) {
+      return (float)cb[j < n ? j : n - 1];
+    } else if (d.emb == CFPP_EMB_DENSE) {
+      return d.dense[(int64_t)(live ? b : 0) * C + j];
+    } else {
+      const int f = j / d.emb_dim;
+      return d.emb_w[f][cb[f] * d.emb_dim + j % d.emb_dim];
+    }
+  };
+  // ---- ConditionalGaussianDistribution.sample (gaussian.py:263-270) ----
+  float x[C], y[C], h[H2];
+  float logq = 0.f;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    const int f0 = j / d.inner_dim, f1 = (C + j) / d.inner_dim;
+    const float mean = d.inner_w[f0][cb[f0] * d.inner_dim + j % d.inner_dim], ls = d.inner_w[f1][cb[f1] * d.inner_dim + (C + j) % d.inner_dim];
+    const float v = mean + expf(ls) * col[j * kEncStride];
+    x[j] = v;
+    const float df = v - mean;
+    logq += (-kHalfLog2Pi - ls) + (-0.5f * expf(-2.f * ls) * (df * df));
+  }
+  // ---- 2 x (FC, ActNormFC, CouplingFC)  (flowsequential.py:60-69) ----
+#pragma unroll 1
+  for (int L = 0; L < 2; ++L) {
+    const float* w = sm + L * Lo::per_layer;
+    enc_matvec<C, C, false, false>(w + Lo::fcT, nullptr, x, col);
+#pragma unroll
+    for (int i = 0; i < C; ++i) x[i] = (col[i * kEncStride] - w[Lo::ant + i]) * w[Lo::ansc + i];
+    logq -= scal[L];
+    logq -= scal[2 + L];
+    float xa[Ch];
+#pragma unroll
+    for (int i = 0; i < Ch; ++i) xa[i] = x[i];
+    enc_matvec<Ch, H2, true, true>(w + Lo::w1, w + Lo::b1, xa, col);            // coupling.py:80-97
+#pragma unroll
+    for (int i = 0; i < H2; ++i) h[i] = col[i * kEncStride];
+    enc_matvec<H2, H2, true, true>(w + Lo::w2, w + Lo::b2, h, col);
+#pragma unroll
+    for (int i = 0; i < H2; ++i) h[i] = col[i * kEncStride];
+    enc_matvec<H2, C, true, false>(w + Lo::w3, w + Lo::b3, h, col);
+#pragma unroll
+    for (int i = 0; i < C; ++i) y[i] = col[i * kEncStride];
+    float ssum = 0.f;
+#pragma unroll
+    for (int o = 0; o < Ch; ++o) {
+      const float ls = 2.0f * tanhf(y[Ch + o] * 0.5f);
+      x[Ch + o] = fmaf(x[Ch + o], expf(ls), y[o]);
+      ssum += ls;
+    }
+    logq -= ssum;
+  }
+  // ---- sigmoid flow (activations.py:234-238) and the surjection ----
+  // softplus(-v) + softplus(v) = |v| + 2 log1p(e^-|v|) and sigmoid(v) = {1, e^-|v|} / (1 + e^-|v|): one exponential per element
+  const float T = d.temperature[0], logT = logf(T);
+  float act = 0.f;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    const float v = T * x[j], av = fabsf(v);
+    const float ev = expf(-av);
+    act += logT - (av + 2.f * log1pf(ev));
+    x[j] = (v >= 0.f ? 1.f : ev) / (1.f + ev);
+  }
+  float lp;
+  if (d.type == CFPP_ENC_VARDEQ) {                          // dequantize.py:107-116
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) { col[j * kEncStride] = (x_in(j) + x[j]) / d.qbins[j]; l += d.ldj_per_dim[j] * (float)C; }
+    lp = (l + act) - logq;
+  } else if (d.type == CFPP_ENC_ARGMAX) {                   // dequantize.py:239-268: bits MSB first, zero-padded to even
+    int f = 0, k = d.bits[0] - 1;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      while (f < n && k < 0) { ++f; k = f < n ? d.bits[f] - 1 : -1; }
+      if (f < n) { const int bit = (int)((cb[f] >> k) & 1); col[j * kEncStride] = x[j] * (float)(2 * bit - 1); --k; }
+      else col[j * kEncStride] = -x[j];
+    }
+    lp = act - logq;
+  } else {                                                  // prob sampling, dequantize.py:152-161
+#pragma unroll
+    for (int j = 0; j < C; ++j) col[j * kEncStride] = x[j];
+    lp = act + logq;
+  }
+  if (live) p.logp[e][b] = lp;
+  __syncthreads();
+  float* c_out = p.c[e];
+  for (int idx = tid; idx < kEncTile * C; idx += kEncTile) {
+    const int s = idx / C, j = idx - s * C;
+    if (b0 + s < B) c_out[(int64_t)b0 * C + idx] = bounce[j * kEncStride + s];
+  }
+  __syncthreads();
+  }
+}
+
 // y (B,N) = act(x (B,K) @ wt (K,N) + bias): 64x64 tile, 4x4 per thread, K chunks of 16.
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
                                                      float* __restrict__ y, int B, int K, int N, int relu) {
@@ -279,6 +452,32 @@ extern "C" int cfpp_ctx_encode_batch(const int64_t* ctx, const cfpp_enc_desc* de
   for (int i = 0; i < n_enc; ++i) { p.noise[i] = noise[i]; p.c[i] = c_out[i]; p.logp[i] = logp_out[i]; }
   dim3 grid((B + 127) / 128, n_enc);
   ctx_encode_batch_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(ctx, descs_device, p, B);
+  return check_launch("ctx_encode_batch");
+}
+
+extern "C" int cfpp_ctx_encode_flow_supported(int C) { return (C == 8 || C == 20) ? 1 : 0; }
+
+extern "C" int cfpp_ctx_encode_batch_flow(const int64_t* ctx, const cfpp_enc_desc* descs_device, int n_enc, int C, const float* const* noise,
+                                          float* const* c_out, float* const* logp_out, int B, void* stream) {
+  CFPP_REQUIRE(n_enc >= 1 && n_enc <= CFPP_MAX_ENC_BATCH, "ctx_encode_batch_flow: n_enc=%d outside [1,%d]", n_enc, CFPP_MAX_ENC_BATCH);
+  CFPP_REQUIRE(descs_device && noise && c_out && logp_out, "ctx_encode_batch_flow: null argument");
+  CFPP_REQUIRE(cfpp_ctx_encode_flow_supported(C), "ctx_encode_batch_flow: width C=%d has no tiled kernel", C);
+  for (int i = 0; i < n_enc; ++i) CFPP_REQUIRE(noise[i] && c_out[i] && logp_out[i], "ctx_encode_batch_flow: encoder %d: null noise / output", i);
+  if (B <= 0) return CFPP_OK;
+  EncBatchPtrs p;
+  for (int i = 0; i < n_enc; ++i) { p.noise[i] = noise[i]; p.c[i] = c_out[i]; p.logp[i] = logp_out[i]; }
+  // about four resident CTAs per SM in one wave; each CTA stages its encoder's parameters once and walks its share of the sample tiles
+  const int ntiles = (B + kEncTile - 1) / kEncTile;
+  int per_enc = (4 * num_sms()) / n_enc;
+  if (per_enc > ntiles) per_enc = ntiles;
+  if (per_enc < 1) per_enc = 1;
+  dim3 grid(per_enc, n_enc);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CFPP_ENCF(C_) do { const int smem = EncFlowLayout<C_>::floats * 4; static bool set_ = false; \
+    if (!set_) { cudaFuncSetAttribute(ctx_encode_flow_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set_ = true; } \
+    ctx_encode_flow_kernel<C_><<<grid, kEncTile, smem, st>>>(ctx, descs_device, p, B); } while (0)
+  if (C == 8) CFPP_ENCF(8); else CFPP_ENCF(20);
+#undef CFPP_ENCF
   return check_launch("ctx_encode_batch");
 }
 

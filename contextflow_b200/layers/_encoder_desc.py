@@ -248,7 +248,8 @@ class EncoderBatch:
         dsize = ctypes.sizeof(_cabi.EncDesc)
         for i0 in range(0, len(descs), step):
             sl = slice(i0, i0 + step)
-            cs, lps = ops.ctx_encode_batch(context, self._dev[i0 * dsize:], noises[sl], widths[sl])
+            flow = all(f.surj.kind in ('vardeq', 'argmax', 'probsample') for _, f in self.members[sl]) and len(set(widths[sl])) == 1
+            cs, lps = ops.ctx_encode_batch(context, self._dev[i0 * dsize:], noises[sl], widths[sl], flow_width=widths[i0] if flow else 0)
             for (plan, _), c, lp in zip(self.members[sl], cs, lps):
                 plan.preset = (c, lp)
 

@@ -17,6 +17,8 @@ other case `log_prob` runs the layer-by-layer forward, which is the same CUDA co
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import ops
@@ -57,11 +59,25 @@ class _ConvAct:
         self.mods = [conv, an]
         self.conv, self.an = conv, an
         self.c_conv = self.c_an = None          # (cn_out, logp_c) filled by the context pre-pass
+        self._fused_key = self._fused = None
+
+    def fused_cn(self):
+        """True when the layer's own context network runs inside the conv kernel (cfpp_conv1x1_ctx_fwd): no (B, D, D) matrix in HBM."""
+        conv = self.conv
+        if not conv.context_net or not self.an.context_net or os.environ.get('CFPP_C1X1_CTX', '1') == '0':
+            return False
+        key = (conv.D, conv.H * conv.W, conv.C)
+        if self._fused_key != key:
+            self._fused_key, self._fused = key, ops.conv1x1_ctx_supported(8, *key)
+        return self._fused
+
+    def ctx_plans(self):
+        return [m._plan for m in (self.conv, self.an) if m.context_net]
 
     def cn_jobs(self):
         conv, an = self.conv, self.an
         jobs = []
-        if conv.context_net:
+        if conv.context_net and not self.fused_cn():
             wt = conv._packs.get('cn', [conv.CN.weight], lambda: ops.pack_kmajor(conv.CN.weight, 1))
             jobs.append((conv._plan, [(wt, conv.CN.bias.detach())], conv.D, self, 'c_conv'))
         if an.context_net:
@@ -83,7 +99,15 @@ class _ConvAct:
             kw = dict(an_t=tl, an_logs=None, an_logp_c=lp, an_logp_scale=float(HW))
         else:
             kw = dict(an_t=an.NN_t.detach(), an_logs=an.NN_logs.detach())
-        if conv.context_net:
+        if conv.context_net and self.fused_cn() and HW == conv.H * conv.W:
+            e, lp = conv._plan.preset; conv._plan.preset = None
+            wt, bt = conv._packs.get('cn_tril', [conv.CN.weight, conv.CN.bias], lambda: ops.pack_cn_tril(conv.CN.weight, conv.CN.bias, conv.D))
+            z, ldj = ops.conv1x1_ctx(x, e, wt, bt, conv.NN.detach(), conv.logabsdet(), lp, conv.contextflow, **kw)
+        elif conv.context_net:
+            if self.c_conv is None:                  # fused plan chosen for another spatial size than the one that arrived: the two-kernel route
+                e, lp = conv._plan.preset; conv._plan.preset = None
+                wk = conv._packs.get('cn', [conv.CN.weight], lambda: ops.pack_kmajor(conv.CN.weight, 1))
+                self.c_conv = (ops.linear(e, wk, conv.CN.bias.detach()), lp)
             cm, lp = self.c_conv
             z, ldj = ops.conv1x1(x, conv.NN.detach(), conv.logabsdet(), cm, lp, conv.contextflow, **kw)
         else:
@@ -98,6 +122,9 @@ class _Coup:
         self.mods = [m]
         self.m = m
         self.c_cn = None
+
+    def ctx_plans(self):
+        return [self.m._plan] if self.m.context_net else []
 
     def cn_jobs(self):
         m = self.m
@@ -165,7 +192,7 @@ class FastLogProb:
             return False
         for s in self.segs:
             if isinstance(s, (_ConvAct, _Coup)):
-                for plan, *_ in s.cn_jobs():
+                for plan in s.ctx_plans():
                     if context is None or context.dim() != 2:
                         return False
                     if not any(any(p is plan for p, _ in b.members) for b in groups.values()):

@@ -3,6 +3,7 @@ computation below is a libcfpp kernel.  CPU tensors are rejected: there is no fa
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -245,6 +246,38 @@ def conv1x1(x, NN, logabsdet, c=None, logp_c=None, contextflow=False, an_t=None,
     _call('conv1x1_fwd', (_p(x), _p(z), _p(ldj), _p(_f32(NN)), _p(logabsdet), _p(None if c is None else _f32(c)),
                                  _p(logp_c), int(bool(contextflow)), _p(an_t), _p(an_logs), per_sample, _p(an_logp_c),
                                  float(an_logp_scale), B, D, HW, _stream()), 'conv1x1_fwd')
+    return z, ldj
+
+
+def conv1x1_ctx_supported(B, D, HW, K) -> bool:
+    return bool(lib().cfpp_conv1x1_ctx_supported(int(B), int(D), int(HW), int(K)))
+
+
+def pack_cn_tril(weight, bias, D):
+    """Conv1x1.CN (nn.Linear(C, D*D), conv1x1.py:22) restricted to the entries torch.tril keeps, K-major over the packed triangle:
+    -> (cnw_tri (K, T), cnb_tri (T)), T = D(D+1)/2, entry t = i(i+1)/2 + j <-> output row i*D + j (one-time weight prep)."""
+    ii, jj = torch.tril_indices(D, D, device=weight.device)
+    rows = ii * D + jj                                               # row-major lower triangle: i ascending, j <= i ascending
+    return weight.detach().to(torch.float32)[rows].t().contiguous(), bias.detach().to(torch.float32)[rows].contiguous()
+
+
+def conv1x1_ctx(x, e, cnw_tri, cnb_tri, NN, logabsdet, logp_c=None, contextflow=False, an_t=None, an_logs=None, an_logp_c=None, an_logp_scale=0.0):
+    """Conv1x1 with its context network and the ActNorm epilogue in one kernel (cfpp_conv1x1_ctx_fwd)."""
+    _need_cuda(x, e, cnw_tri); x = _f32(x); e = _f32(e)
+    B, D = x.shape[0], x.shape[1]
+    HW = x[0, 0].numel() if B else 1
+    z = torch.empty_like(x); ldj = torch.empty(B, device=x.device, dtype=x.dtype)
+    per_sample = 0
+    if an_t is not None:
+        if an_logs is None:
+            per_sample, an_logs = 2, an_t[:, D:]
+        else:
+            per_sample = 1
+    K, T = cnw_tri.shape
+    _set_work(bytes=8.0 * x.numel() + 4.0 * e.numel(), flops=2.0 * D * x.numel() + 2.0 * B * K * T, shape=f'D{D}xHW{HW}')
+    _call('conv1x1_ctx_fwd', (_p(x), _p(z), _p(ldj), _p(e), _p(cnw_tri), _p(cnb_tri), _p(_f32(NN)), _p(logabsdet), _p(logp_c),
+                              int(bool(contextflow)), _p(an_t), _p(an_logs), per_sample, _p(an_logp_c), float(an_logp_scale),
+                              B, D, HW, K, _stream()), 'conv1x1_fwd')
     return z, ldj
 
 
@@ -616,15 +649,19 @@ def _carve(B, widths, device, align=64):
     return outs
 
 
-def ctx_encode_batch(ctx, descs_dev, noises, widths):
-    """n encoders over one context batch in a single launch; returns ([c_i (B, width_i)], [logp_i (B,)])."""
+def ctx_encode_batch(ctx, descs_dev, noises, widths, flow_width=0):
+    """n encoders over one context batch in a single launch; returns ([c_i (B, width_i)], [logp_i (B,)]).
+    flow_width = C when every encoder carries the inner flow at that width (the tiled kernel is used where it exists)."""
     _need_cuda(ctx, descs_dev)
     B, n = ctx.shape[0], len(widths)
     logp_all = torch.empty((n, B), device=ctx.device, dtype=torch.float32)
     cs = _carve(B, widths, ctx.device)
     arr = lambda ts: (vp * n)(*[vp(0 if t is None else t.data_ptr()) for t in ts])
     noises = [None if t is None else _f32(t) for t in noises]
-    _call('ctx_encode_batch', (_p(ctx.contiguous()), _p(descs_dev), n, arr(noises), arr(cs), arr(list(logp_all)), B, _stream()))
+    if flow_width and os.environ.get('CFPP_ENC_FLOW', '1') != '0' and lib().cfpp_ctx_encode_flow_supported(int(flow_width)):
+        _call('ctx_encode_batch_flow', (_p(ctx.contiguous()), _p(descs_dev), n, int(flow_width), arr(noises), arr(cs), arr(list(logp_all)), B, _stream()))
+    else:
+        _call('ctx_encode_batch', (_p(ctx.contiguous()), _p(descs_dev), n, arr(noises), arr(cs), arr(list(logp_all)), B, _stream()))
     return cs, list(logp_all)
 
 

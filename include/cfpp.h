@@ -82,6 +82,20 @@ int cfpp_conv1x1_fwd(const float* x, float* z, float* ldj, const float* NN, cons
                      const float* c, const float* logp_c, int contextflow,
                      const float* an_t, const float* an_logs, int an_per_sample, const float* an_logp_c, float an_logp_scale,
                      int B, int D, int HW, void* stream);
+/* Conv1x1.forward with a context_net, layers/conv1x1.py:31-50, INCLUDING its context network `c = self.CN(c)` (:33) and the optional
+ * ActNorm epilogue (layers/actnorm.py:37-60) in one persistent kernel: the (B,D,D) matrix c never exists in HBM.
+ *   e        (B,K)  encoder output of the layer's context_net (K = context_net.C <= 64);
+ *   cnw_tri  (K,T)  CN.weight restricted to the lower triangle + diagonal, K-major: cnw_tri[k][i(i+1)/2 + j] = CN.weight[i*D + j][k], j <= i,
+ *                   T = D(D+1)/2 (the strictly upper entries of c are discarded by torch.tril, conv1x1.py:36,40,46);
+ *   cnb_tri  (T)    CN.bias in the same order.
+ * W_b, ldj and the epilogue exactly as cfpp_conv1x1_fwd with c != NULL; an_per_sample must be 1 or 2 when an_t is given.
+ * cfpp_conv1x1_ctx_supported: 1 when (D, HW, K) has a plan (D <= 128, HW % 4 == 0, the tiles fit shared memory); otherwise callers use
+ * cfpp_cn_batch + cfpp_conv1x1_fwd. */
+int cfpp_conv1x1_ctx_supported(int B, int D, int HW, int K);
+int cfpp_conv1x1_ctx_fwd(const float* x, float* z, float* ldj, const float* e, const float* cnw_tri, const float* cnb_tri,
+                         const float* NN, const float* logabsdet, const float* logp_c, int contextflow,
+                         const float* an_t, const float* an_logs, int an_per_sample, const float* an_logp_c, float an_logp_scale,
+                         int B, int D, int HW, int K, void* stream);
 /* ActNorm.forward, layers/actnorm.py:37-60: t,logs = base (D) [+ c (B,2D) 'b (p d)'] per mode:
  *   mode 0: base only; mode 1: base + c (contextflow); mode 2: c only (conventional).
  * z = (x - t) * exp(-logs); ldj[b] = sum_d logs[b,d] + logp_scale * logp_c[b]   (note: no H*W factor, App. C-1). */
@@ -263,6 +277,14 @@ int cfpp_ctx_encode(const int64_t* ctx, const float* noise, float* c, float* log
 #define CFPP_MAX_ENC_BATCH 64
 int cfpp_ctx_encode_batch(const int64_t* ctx, const cfpp_enc_desc* descs_device, int n_enc, const float* const* noise,
                           float* const* c_out, float* const* logp_out, int B, void* stream);
+/* The same launch for encoders that all carry the inner flow (type vardeq / argmax / probsample) and share one width C with a tiled
+ * kernel (cfpp_ctx_encode_flow_supported(C) == 1: C = 8 -- eye + argmax over 68 ATM contexts --, C = 20 -- onehot [15, 5] + vardeq, the
+ * CIFAR-10C stack): 128 samples of one encoder per CTA, the flow's parameters staged in shared memory, layer inputs in registers
+ * (model.py:30-90, flowsequential.py:60-69, conv1x1.py:80-96, actnorm.py:86-102, coupling.py:80-97).  Same results as
+ * cfpp_ctx_encode_batch up to fp32 summation order. */
+int cfpp_ctx_encode_flow_supported(int C);
+int cfpp_ctx_encode_batch_flow(const int64_t* ctx, const cfpp_enc_desc* descs_device, int n_enc, int C, const float* const* noise,
+                               float* const* c_out, float* const* logp_out, int B, void* stream);
 /* CatEmbeddings.forward (stack=False), layers/rtdl/nn/_embeddings.py:265-283: out[b] = cat_i tables[i][ctx[b,i]], each `width` wide.
  * `tables` is a HOST array of n_ctx device pointers. */
 int cfpp_embed_lookup(const int64_t* ctx, const float* const* tables, int n_ctx, int width, float* out, int B, void* stream);

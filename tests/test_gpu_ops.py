@@ -55,6 +55,53 @@ def test_conv1x1_shapes(B, D, HW, ctx, contextflow):
     assert_close(ldj.cpu().numpy(), want_l.numpy(), L_RTOL, L_ATOL, 'conv1x1 ldj')
 
 
+@pytest.mark.parametrize('B,D,HW,K', [(37, 16, 256, 20), (300, 64, 16, 20), (1000, 32, 64, 20), (9, 76, 72, 8), (5, 72, 76, 8), (13, 36, 76, 8), (21, 12, 16, 3),
+                                      (1, 64, 16, 20), (70, 128, 4, 64)])
+@pytest.mark.parametrize('contextflow', [True, False])
+@pytest.mark.parametrize('an_mode', [2, 1, 0])
+def test_conv1x1_with_fused_context_network(B, D, HW, K, contextflow, an_mode):
+    """cfpp_conv1x1_ctx_fwd (the CN linear layer + W_b assembly + 1x1 conv + ActNorm in one kernel) against the fp64 restatement of
+    conv1x1.py:31-50 / actnorm.py:37-60, on ragged batches that leave partial sample groups."""
+    assert ops.conv1x1_ctx_supported(B, D, HW, K)
+    x = synth.uniform('f1x', (B, D, HW, 1)) * 2
+    NN = torch.eye(D) + synth.uniform('f1w', (D, D)) * 0.2 / math.sqrt(D)
+    e = synth.uniform('f1e', (B, K)) * 2
+    cw = synth.uniform('f1cw', (D * D, K)) * 0.1
+    cb = synth.uniform('f1cb', (D * D,)) * 0.1
+    lp = synth.uniform('f1l', (B,))
+    tl = synth.uniform('f1t', (B, 2 * D)) * 0.5
+    alp = synth.uniform('f1al', (B,))
+    lad = ops.slogdet(NN.to(dev))
+    wt, bt = ops.pack_cn_tril(cw.to(dev), cb.to(dev), D)
+    kw = {}
+    if an_mode == 2:
+        kw = dict(an_t=tl.to(dev), an_logs=None, an_logp_c=alp.to(dev), an_logp_scale=float(HW))
+    elif an_mode == 1:
+        kw = dict(an_t=tl[:, :D].contiguous().to(dev), an_logs=tl[:, D:].contiguous().to(dev))
+    z, ldj = ops.conv1x1_ctx(x.to(dev), e.to(dev), wt, bt, NN.to(dev), lad, lp.to(dev), contextflow, **kw)
+    xd, ed = x.double(), e.double()
+    cm = (ed @ cw.double().t() + cb.double()).reshape(B, D, D)
+    diag = torch.diagonal(cm, dim1=-2, dim2=-1)
+    Wb = torch.tril(cm, -1) + torch.diag_embed(torch.exp(diag))
+    want_l = HW * diag.sum(-1)
+    if contextflow:
+        Wb = Wb - torch.eye(D, dtype=torch.float64) + NN.double()
+        want_l = HW * (torch.linalg.slogdet(NN.double())[1] + diag.sum(-1))
+    want_l = want_l + lp.double() * HW
+    want = torch.einsum('bij,bjhw->bihw', Wb, xd)
+    if an_mode:
+        t, logs = tl[:, :D].double(), tl[:, D:].double()
+        want = (want - t[:, :, None, None]) * torch.exp(-logs)[:, :, None, None]
+        want_l = want_l + logs.sum(-1) + (HW * alp.double() if an_mode == 2 else 0)
+    assert_close(z.cpu().numpy(), want.float().numpy(), Z_RTOL, Z_ATOL * 4, 'conv1x1_ctx z')
+    assert_close(ldj.cpu().numpy(), want_l.float().numpy(), L_RTOL, L_ATOL, 'conv1x1_ctx ldj')
+    # and the two-kernel route (cn_batch-style linear + cfpp_conv1x1_fwd) gives the same layer
+    c2 = ops.linear(e.to(dev), ops.pack_kmajor(cw.to(dev), 1), cb.to(dev))
+    z2, l2 = ops.conv1x1(x.to(dev), NN.to(dev), lad, c2, lp.to(dev), contextflow, **kw)
+    assert_close(z.cpu().numpy(), z2.cpu().numpy(), Z_RTOL, Z_ATOL * 4, 'fused vs two-kernel z')
+    assert_close(ldj.cpu().numpy(), l2.cpu().numpy(), L_RTOL, L_ATOL, 'fused vs two-kernel ldj')
+
+
 @pytest.mark.parametrize('B,C,HW', [(3, 16, 256), (5, 26, 8), (2, 8, 49), (1, 76, 72), (70, 2, 1)])
 @pytest.mark.parametrize('with_ctx', [False, True])
 def test_coupling_elementwise(B, C, HW, with_ctx):
