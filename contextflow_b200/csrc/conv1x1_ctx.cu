@@ -6,7 +6,7 @@
 // per sample -- at D = 64 more than the activations themselves -- and the consumer then spends most of its instructions re-assembling
 // W_b from it.  Here persistent CTAs (two per SM where shared memory allows) loop over groups of NS <= 4 samples:
 //   stage   : the activations of the NEXT group arrive by one bulk-TMA copy per sample (contiguous D*HW floats) behind an mbarrier while
-//             the current group is computed (two activation buffers);
+//             the current groups are computed (two to four activation stages);
 //   phase A : every thread owns entries t of the packed lower triangle: 1 coalesced weight load per k (cnw is K-major over the packed
 //             triangle: (K, T), L2 resident), reused for the group's samples whose encoder rows e sit in shared memory as [k][s] (one 128-bit
 //             broadcast load = four samples; ten weight loads in flight per entry); exp on the diagonal, - I + NN, written into the group's W_b tiles; the strictly upper triangle
@@ -24,7 +24,7 @@ struct Args {
   const float* e; const float* cnw; const float* cnb;
   const float* NN; const float* logabsdet; const float* logp_c; int contextflow;
   const float* an_t; const float* an_logs; int an_stride; const float* an_logp_c; float an_logp_scale;
-  int B, D, DR, G, HW, K, T, PG, TPS, NS, WS, ngroups;
+  int B, D, DR, G, HW, K, T, PG, TPS, NS, WS, ngroups, NSTG;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -52,25 +52,26 @@ __global__ void __launch_bounds__(kThreads, 2) conv1x1_ctx_kernel(const Args a) 
   const int D = a.D, DR = a.DR, HW = a.HW, WS = a.WS, NS = a.NS, K = a.K, T = a.T;
   const int KP = (K + kKB - 1) / kKB * kKB;                    // encoder rows padded with zeros to whole blocks of kKB
   float* Ws = reinterpret_cast<float*>(c1f_smem4);             // [NS][DR][WS]; rows >= D and columns >= D stay zero
-  float* Xs = Ws + (size_t)NS * DR * WS;                       // [2][NS][DR][HW]; rows >= D stay zero
-  float* Es = Xs + (size_t)2 * NS * DR * HW;                   // [KP][SL]
+  const int NSTG = a.NSTG;                                     // activation stages (2..4): NSTG - 1 groups in flight behind mbarriers
+  float* Xs = Ws + (size_t)NS * DR * WS;                       // [NSTG][NS][DR][HW]; rows >= D stay zero
+  float* Es = Xs + (size_t)NSTG * NS * DR * HW;                // [KP][SL]
   float* dg = Es + (size_t)KP * SL;                            // [NS][DR] raw diagonal of c
   float* sh = dg + (size_t)NS * DR;                            // [NS][DR] ActNorm shift
   float* sc = sh + (size_t)NS * DR;                            // [NS][DR] ActNorm exp(-logs)
   float* lg = sc + (size_t)NS * DR;                            // [NS][DR] ActNorm logs
   uint32_t* tab = reinterpret_cast<uint32_t*>(lg + (size_t)NS * DR);   // [T] (i << 16) | j of packed entry t
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tab + ((T + 1) & ~1));  // two mbarriers (8-byte aligned: every block above is a multiple of 8 bytes)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tab + ((T + 1) & ~1));  // NSTG mbarriers (8-byte aligned: every block above is a multiple of 8 bytes)
   const int tid = threadIdx.x;
   const uint32_t bar0 = smem_u32(bars);
 
   // ---- once per CTA: barriers, zero padding, the triangle index table, the context-free part of W ----
-  if (tid == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (tid == 0) { for (int q = 0; q < NSTG; ++q) mbar_init(bar0 + 8 * q, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   for (int idx = tid; idx < DR * WS; idx += kThreads) {         // the same context-free entries in every sample slot
     const int i = idx / WS, j = idx - i * WS;
     const float v = (a.contextflow && i < D && j < D && j > i) ? __ldg(a.NN + i * D + j) : 0.f;
     for (int s = 0; s < NS; ++s) Ws[(size_t)s * DR * WS + idx] = v;
   }
-  if (DR != D) for (int idx = tid; idx < 2 * NS * (DR - D) * HW; idx += kThreads) {
+  if (DR != D) for (int idx = tid; idx < NSTG * NS * (DR - D) * HW; idx += kThreads) {
     const int blk = idx / ((DR - D) * HW), rem = idx - blk * (DR - D) * HW;
     Xs[((size_t)blk * DR + D) * HW + rem] = 0.f;
   }
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1x1_ctx_kernel(const Args a) 
     for (int m = 0; m < nS; ++m)
       bulk_g2s(smem_u32(Xs + ((size_t)buf * NS + m) * DR * HW), a.x + (b0 + m) * (int64_t)D * HW, xbytes, bar0 + 8 * buf);
   };
-  if (tid == 0 && (int)blockIdx.x < a.ngroups) prefetch(blockIdx.x, 0);
+  if (tid == 0) for (int q = 0; q < NSTG - 1; ++q) if ((int)(blockIdx.x + q * gridDim.x) < a.ngroups) prefetch(blockIdx.x + q * gridDim.x, q);
 
   // the small per-sample rows of a group (encoder output, ActNorm parameters) are fetched one group ahead into registers
   const int es = tid / K, ek = tid - es * K;                  // this thread's element of the (SL, K) encoder tile (tid < SL * K)
@@ -110,14 +111,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv1x1_ctx_kernel(const Args a) 
   const int p0 = pg * 4, pstep = a.PG * 4;
   const float4* Es4 = reinterpret_cast<const float4*>(Es);
   const float lad = a.contextflow ? __ldg(a.logabsdet) : 0.f;
+  const bool teven = (T & 1) == 0 && (reinterpret_cast<uintptr_t>(a.cnw) & 7) == 0;
 
-  int it = 0;
+  int it = 0, buf = 0, use = 0;                                // stage of this iteration, how often the stages have wrapped
   for (int grp = blockIdx.x; grp < a.ngroups; grp += gridDim.x, ++it) {
-    const int buf = it & 1;
     const int64_t b0 = (int64_t)grp * NS;
     const int nS = (int)min((int64_t)NS, (int64_t)a.B - b0);
     const bool more = grp + (int)gridDim.x < a.ngroups;
-    if (tid == 0 && more) prefetch(grp + gridDim.x, buf ^ 1);  // buffer buf^1 was last read before the previous iteration's closing barrier
+    {   // the stage consumed by the previous iteration (released by its closing barrier) receives the group NSTG - 1 iterations ahead
+      const int far = grp + (NSTG - 1) * (int)gridDim.x;
+      if (tid == 0 && far < a.ngroups) prefetch(far, buf == 0 ? NSTG - 1 : buf - 1);
+    }
     // ---- this group's encoder rows [k][slot] and ActNorm parameters: registers -> shared; then the next group's fetch goes in flight ----
     if (tid < SL * K) Es[ek * SL + es] = e_next;
     if (a.an_logs) {
@@ -144,8 +148,15 @@ __global__ void __launch_bounds__(kThreads, 2) conv1x1_ctx_kernel(const Args a) 
       const float* wp1 = a.cnw + t1;
       if (KT > 0) {
         float w0[KT > 0 ? KT : 1], w1[KT > 0 ? KT : 1];
+        if (teven) {                                             // entries t0, t0 + 1 of one weight row: one 64-bit load (k T + t0 is even)
+          const float2* wq = reinterpret_cast<const float2*>(wp0);
+          const int T2 = T >> 1;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) { w0[k] = __ldg(wp0); w1[k] = __ldg(wp1); wp0 += T; wp1 += T; }
+          for (int k = 0; k < KT; ++k) { const float2 w = __ldg(wq + k * T2); w0[k] = w.x; w1[k] = w.y; }
+        } else {
+#pragma unroll
+          for (int k = 0; k < KT; ++k) { w0[k] = __ldg(wp0); w1[k] = __ldg(wp1); wp0 += T; wp1 += T; }
+        }
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
           const float4 e0 = Es4[k];
@@ -175,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1x1_ctx_kernel(const Args a) 
         }
       }
     }
-    mbar_wait(bar0 + 8 * buf, (it >> 1) & 1);
+    mbar_wait(bar0 + 8 * buf, use & 1);
     __syncthreads();
     // ---- per-sample ldj: one warp per sample, fixed order ----
     {
@@ -246,10 +257,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv1x1_ctx_kernel(const Args a) 
       }
     }
     __syncthreads();
+    if (++buf == NSTG) { buf = 0; ++use; }
   }
 }
 
-struct Geo { int PT, G, PG, TPS, NS, DR, WS, occ; size_t smem; };
+struct Geo { int PT, G, PG, TPS, NS, DR, WS, occ, nstg; size_t smem; };
 
 // Geometry for (D, HW, K); false when the shape has no plan (the caller keeps the two-kernel route).
 static bool plan(int B, int D, int HW, int K, Geo& o) {
@@ -263,16 +275,20 @@ static bool plan(int B, int D, int HW, int K, Geo& o) {
     const int TPS = o.G * PG;
     if (TPS > kThreads) continue;
     const int ns_max = kThreads / TPS > kSlots ? kSlots : kThreads / TPS;
-    auto bytes = [&](int ns) {
-      return ((size_t)ns * o.DR * o.WS + (size_t)2 * ns * o.DR * HW + (size_t)KP * kSlots + (size_t)4 * ns * o.DR + (size_t)((T + 1) & ~1)) * 4 + 16;
+    auto bytes = [&](int ns, int nstg) {
+      return ((size_t)ns * o.DR * o.WS + (size_t)nstg * ns * o.DR * HW + (size_t)KP * kSlots + (size_t)4 * ns * o.DR + (size_t)((T + 1) & ~1)) * 4 + 64;
     };
     for (int NS = ns_max; NS >= 1; --NS) {
-      const size_t sm = bytes(NS);
+      size_t sm = bytes(NS, 2);
       if (sm > 222 * 1024) continue;
       const int occ = sm + 1024 <= 113 * 1024 ? 2 : 1;            // registers (up to 128 x 256 threads) allow two CTAs per SM
+      const size_t cap = occ == 2 ? 113 * 1024 - 1024 : 222 * 1024;
+      int nstg = 2;                                               // deeper activation prefetch where it is free: HBM latency under load needs ~64 KB in flight per SM
+      while (nstg < 4 && bytes(NS, nstg + 1) <= cap && (size_t)(nstg - 1) * NS * D * HW * 4 * occ < 96 * 1024) ++nstg;
+      sm = bytes(NS, nstg);
       // busy phase-B threads per SM; 8 pixels per thread = fewer shared loads per FMA; a lone CTA cannot hide its own load latencies
       const double util = (double)NS * TPS / kThreads * (PT == 8 ? 1.15 : 1.0) * (occ == 1 ? 0.5 : 1.0);
-      if (!found || util > best) { found = true; best = util; o.PT = PT; o.PG = PG; o.TPS = TPS; o.NS = NS > B ? B : NS; o.smem = sm; o.occ = occ; }
+      if (!found || util > best) { found = true; best = util; o.PT = PT; o.PG = PG; o.TPS = TPS; o.NS = NS > B ? B : NS; o.smem = sm; o.occ = occ; o.nstg = nstg; }
     }
   }
   return found;
@@ -299,7 +315,7 @@ extern "C" int cfpp_conv1x1_ctx_fwd(const float* x, float* z, float* ldj, const 
   c1f::Geo g;
   if (!c1f::plan(B, D, HW, K, g)) { set_error("conv1x1_ctx: shape (D %d, HW %d, K %d) has no plan", D, HW, K); return CFPP_ERR_UNSUPPORTED; }
   c1f::Args a{x, z, ldj, e, cnw_tri, cnb_tri, NN, logabsdet, logp_c, contextflow, an_t, an_logs, an_per_sample == 2 ? 2 * D : D, an_logp_c, an_logp_scale,
-              B, D, g.DR, g.G, HW, K, D * (D + 1) / 2, g.PG, g.TPS, g.NS, g.WS, (B + g.NS - 1) / g.NS};
+              B, D, g.DR, g.G, HW, K, D * (D + 1) / 2, g.PG, g.TPS, g.NS, g.WS, (B + g.NS - 1) / g.NS, g.nstg};
   const int slots = num_sms() * g.occ;
   const int grid = a.ngroups < slots ? a.ngroups : slots;
   cudaStream_t st = (cudaStream_t)stream;

@@ -35,6 +35,10 @@
 #include <cuda_fp16.h>
 #include "common.cuh"
 
+#ifndef CFPP_TC_WIDE
+#define CFPP_TC_WIDE 0   // 1: 32-column epilogue items in the one-CTA-per-SM kernels (spills under the 144-register cap since the packed-math epilogue)
+#endif
+
 namespace cfpp {
 namespace tc {
 
@@ -48,6 +52,7 @@ struct Plan {
   int P, KS1, N2, N3;                // channel panels, k-steps of stage 1, N of stages 1-2, N of stage 3 (padded to 16)
   int stage_bytes, nstages, ntiles;
   int resident;                      // 1: nstages == chunks per tile, the weight chunks are loaded once per CTA and never recycled
+  int pipe;                          // 1: software-pipelined tiles (two operand sets, disjoint accumulator column blocks), see the kernel
   int region_bytes;                  // bytes of one (hi|lo, panel) operand region
   int off_ring, off_stage_x, off_bias, off_tab, off_ls, off_bar, smem_bytes;   // off_tab: R + T2*128 packed row-decode words; off_ls: per-row log-scale partials
   long long x_bstride;
@@ -185,6 +190,7 @@ struct Args {
   // fused affine coupling (coupling.py:50-66), z != NULL: h is not written; x must be the full (B, 2 Cin, H, W) tensor
   float* z; float* ldj; const float* add; const float* logp_c; float logp_scale;
   long long wrepl_stride; int nrepl;   // experiment: weight stream replicas (CTA uses replica blockIdx % nrepl)
+  int dbg;           // debug (profile kernels only): bit 0 = epilogue warps skip their TMEM loads / operand stores, bit 1 = skip the x0 transform
   long long* prof;   // optional (debug): 12 phase-cycle counters of CTA 0's epilogue thread 0, see cfpp_conv_cond_tc_set_profile
 };
 
@@ -220,6 +226,14 @@ __device__ __forceinline__ bool decode_out(const Plan& p, int m, int& s, int& y,
   }
 }
 
+// Packed fp32 pairs (Blackwell add / mul / fma .f32x2: two IEEE round-to-nearest operations per issue slot; results identical to the scalar forms)
+__device__ __forceinline__ uint64_t pack2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 // One epilogue item: 32 accumulator columns [c0, c0+32) (16 when only 16 remain) of one row, two column blocks of N each ->
 // + bias -> ReLU -> (v, lo) -> operand row `row`.  All four TMEM loads are in flight before the single wait.  All 32 lanes
 // must call (tcgen05.ld is warp-collective); `write` only guards the stores.
@@ -228,20 +242,37 @@ __device__ __forceinline__ void store_split16(const float (&v)[16], const float 
                                               int row, int col, int rb) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
-    float o[8];
+    if (F16) {
+      // per pair of channels: (v + b) and the rescaled cross block in packed fp32, ReLU, hi = 11-bit truncation, lo' = (r - hi) * 2^11
+      uint32_t h[4], l[4];
+      const uint64_t kinv = pack2(kLoInv, kLoInv), ksc = pack2(kLoScale, kLoScale);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const float4 b = *reinterpret_cast<const float4*>(bias + 8 * g + 4 * q);
-      const int i = 8 * g + 4 * q;
-      if (F16) {
-        o[4 * q + 0] = fmaxf(fmaf(u[i + 0], kLoInv, v[i + 0] + b.x), 0.f); o[4 * q + 1] = fmaxf(fmaf(u[i + 1], kLoInv, v[i + 1] + b.y), 0.f);
-        o[4 * q + 2] = fmaxf(fmaf(u[i + 2], kLoInv, v[i + 2] + b.z), 0.f); o[4 * q + 3] = fmaxf(fmaf(u[i + 3], kLoInv, v[i + 3] + b.w), 0.f);
-      } else {
+      for (int q = 0; q < 4; ++q) {
+        const int i = 8 * g + 2 * q;
+        const float2 b = *reinterpret_cast<const float2*>(bias + i);
+        float r0, r1;
+        unpack2(ffma2(pack2(u[i], u[i + 1]), kinv, fadd2(pack2(v[i], v[i + 1]), pack2(b.x, b.y))), r0, r1);
+        r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f);
+        const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
+        float l0, l1;
+        unpack2(fmul2(fsub2(pack2(r0, r1), pack2(h0, h1)), ksc), l0, l1);
+        h[q] = pack_f16x2_sat(h0, h1);
+        l[q] = pack_f16x2_sat(l0, l1);
+      }
+      const uint32_t off = row_off(row, (col + 8 * g) >> 3, rb);
+      *reinterpret_cast<uint4*>(ph + off) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(pl + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    } else {
+      float o[8];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + 8 * g + 4 * q);
+        const int i = 8 * g + 4 * q;
         o[4 * q + 0] = fmaxf(v[i + 0] + u[i + 0] + b.x, 0.f); o[4 * q + 1] = fmaxf(v[i + 1] + u[i + 1] + b.y, 0.f);
         o[4 * q + 2] = fmaxf(v[i + 2] + u[i + 2] + b.z, 0.f); o[4 * q + 3] = fmaxf(v[i + 3] + u[i + 3] + b.w, 0.f);
       }
+      store_group8<F16, true>(ph, pl, row, col + 8 * g, o, rb);
     }
-    store_group8<F16, true>(ph, pl, row, col + 8 * g, o, rb);
   }
 }
 template <bool F16, bool WIDE>
@@ -263,16 +294,26 @@ __device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, int c
   }
 }
 
-template <bool SEG, bool PROF, bool F16, int OCC>
+// PIPE (software-pipelined tiles, one CTA per SM).  A tile's stages are a dependent chain  x0 -> MMA 1 -> epilogue 1 -> MMA 2 -> epilogue 2 ->
+// MMA 3 -> epilogue 3: run back to back, the epilogue warps idle through every MMA stage and the tensor pipe idles through every epilogue
+// (ncu r1: tensor pipe 21 %, issue slots 47 % with two such CTAs per SM).  With PIPE the epilogue warps interleave two tiles,
+//     X(i+1)  E2(i)  E1(i+1)  E3(i)        and the issuer     S1(i+1)  S3(i)  S2(i+1),
+// so that every MMA stage runs under epilogue work of the other tile: S1(i+1) under E2(i), S3(i) under E1(i+1), S2(i+1) -- the 94 % --
+// under E3(i) and X(i+2).  This takes two operand sets in shared memory (tile parity) and three disjoint accumulator column blocks in TMEM
+// (stage 1 | stage 2 | stage 3: T1*2*N2 + T2*2*N2 + T2*2*N3 <= 512), and a weight stream in consumption order (W1, W3.., W2..).
+template <bool SEG, bool PROF, bool F16, int OCC, bool PIPE>
 __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(const Plan p, const Args a) {
   constexpr int kEpiWarps = epi_warps(OCC), kEpiGroups = kEpiWarps / 4, kEpiThreads = kEpiWarps * 32;
   constexpr int kMmaWarp = kEpiWarps, kProdWarp = kEpiWarps + 1, kThreads = cta_threads(OCC), kTmemCols = 512 / OCC;
   constexpr int KE = F16 ? 16 : 8;                          // channels per MMA k-step
   const int rb = p.rb, CPR = F16 ? rb >> 1 : 32;            // operand row bytes, channels per operand row (panel)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* a_hi = base;                                     // [P][region]
-  uint8_t* a_lo = base + (size_t)p.P * p.region_bytes;      // [P][region]
+  // pointer arithmetic on the shared array (not an integer round trip) keeps the address space visible to the compiler: LDS / STS, 32-bit addressing
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_hi0 = base;                                    // [P][region]; PIPE: a second (hi | lo) set follows for the odd tiles
+  uint8_t* a_lo0 = base + (size_t)p.P * p.region_bytes;     // [P][region]
+  const uint32_t set_bytes = 2u * (uint32_t)p.P * (uint32_t)p.region_bytes;
+  const uint32_t col1 = 0, col2 = PIPE ? (uint32_t)(p.T1 * 2 * p.N2) : 0u, col3 = PIPE ? col2 + (uint32_t)(p.T2 * 2 * p.N2) : 0u;   // accumulator column blocks
   uint8_t* ring = base + p.off_ring;
   float* xstage = reinterpret_cast<float*>(base + p.off_stage_x);
   float* sb1 = reinterpret_cast<float*>(base + p.off_bias);
@@ -323,20 +364,44 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
     // ===================== producer: weight chunks through the ring, next tile's x0 into the staging buffer ==========
     if (elect_one()) {
       uint32_t st = 0, rphase = 0;
-      for (int it = 0; it < my_tiles; ++it) {
+      auto load_x = [&](int it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int b0 = tile * p.S, nS = min(p.S, p.B - b0);
         mbar_wait(bar(BAR_XEMPTY), (it & 1) ^ 1);
         mbar_expect_tx(bar(BAR_XFULL), (uint32_t)(nS * xfloats * 4));
         for (int s = 0; s < nS; ++s)
           bulk_g2s(smem_u32(xstage + (size_t)s * xfloats), a.x + (size_t)(b0 + s) * p.x_bstride, (uint32_t)(xfloats * 4), bar(BAR_XFULL));
-        for (int c = 0; c < nchunks_tile; ++c) {
-          if (p.resident && it > 0) break;                       // resident weights: loaded for the first tile only
-          mbar_wait(bar(BAR_EMPTY + st), rphase ^ 1);
-          const uint32_t bytes = (c < nchunks_tile - p.P) ? (uint32_t)(2 * p.N2 * rb) : (uint32_t)(2 * p.N3 * rb);
-          mbar_expect_tx(bar(BAR_FULL + st), bytes);
-          bulk_g2s(smem_u32(ring + (size_t)st * p.stage_bytes), a.wpack + (size_t)(blockIdx.x % a.nrepl) * a.wrepl_stride + (size_t)c * p.stage_bytes, bytes, bar(BAR_FULL + st));
-          if (++st == (uint32_t)p.nstages) { st = 0; rphase ^= 1; }
+      };
+      auto load_chunk = [&](int c) {
+        mbar_wait(bar(BAR_EMPTY + st), rphase ^ 1);
+        const uint32_t bytes = (c < nchunks_tile - p.P) ? (uint32_t)(2 * p.N2 * rb) : (uint32_t)(2 * p.N3 * rb);
+        mbar_expect_tx(bar(BAR_FULL + st), bytes);
+        bulk_g2s(smem_u32(ring + (size_t)st * p.stage_bytes), a.wpack + (size_t)(blockIdx.x % a.nrepl) * a.wrepl_stride + (size_t)c * p.stage_bytes, bytes, bar(BAR_FULL + st));
+        if (++st == (uint32_t)p.nstages) { st = 0; rphase ^= 1; }
+      };
+      if (!PIPE) {
+        for (int it = 0; it < my_tiles; ++it) {
+          load_x(it);
+          if (!(p.resident && it > 0))                             // resident weights: loaded for the first tile only
+            for (int c = 0; c < nchunks_tile; ++c) load_chunk(c);
+        }
+      } else if (my_tiles > 0) {
+        const int cW3 = nchunks_tile - p.P;                        // chunks: 0 = W1, [1, cW3) = W2 (tap, panel), [cW3, nchunks) = W3 (panel)
+        load_x(0);
+        if (p.resident) {
+          for (int c = 0; c < nchunks_tile; ++c) load_chunk(c);
+          for (int it = 1; it < my_tiles; ++it) load_x(it);
+        } else {
+          // consumption order of the issuer: S1(0) S2(0) | S1(i+1) S3(i) S2(i+1) ...; the x0 of a tile is requested one iteration early
+          if (my_tiles > 1) load_x(1);
+          load_chunk(0);
+          for (int c = 1; c < cW3; ++c) load_chunk(c);
+          for (int it = 0; it < my_tiles; ++it) {
+            if (it + 2 < my_tiles) load_x(it + 2);
+            if (it + 1 < my_tiles) load_chunk(0);
+            for (int c = cW3; c < nchunks_tile; ++c) load_chunk(c);
+            if (it + 1 < my_tiles) for (int c = 1; c < cW3; ++c) load_chunk(c);
+          }
         }
       }
     }
@@ -350,8 +415,11 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
       const uint32_t idN2 = make_idesc(p.N2, F16), id2N2 = make_idesc(2 * p.N2, F16), idN3 = make_idesc(p.N3, F16), id2N3 = make_idesc(2 * p.N3, F16);
       const uint32_t sbo2 = (uint32_t)(p.GS * rb), sbo1 = (uint32_t)(8 * rb), lin_u = (uint32_t)(8 * rb), row_u1 = (uint32_t)rb >> 4;   // lin_u: 128 rows / 16
       const uint32_t tile_cols2 = 2 * p.N2, tile_cols3 = 2 * p.N3;
-      const uint64_t ahi_lin = make_desc(smem_u32(a_hi), sbo1, rb), alo_lin = make_desc(smem_u32(a_lo), sbo1, rb);   // stages 1 / 3: plain 128-row tiles
-      const uint64_t ahi_seg = make_desc(smem_u32(a_hi), sbo2, rb), alo_seg = make_desc(smem_u32(a_lo), sbo2, rb);   // stage 2: group stride GS rows
+      const uint64_t ahi_lin0 = make_desc(smem_u32(a_hi0), sbo1, rb), alo_lin0 = make_desc(smem_u32(a_lo0), sbo1, rb);   // stages 1 / 3: plain 128-row tiles
+      const uint64_t ahi_seg0 = make_desc(smem_u32(a_hi0), sbo2, rb), alo_seg0 = make_desc(smem_u32(a_lo0), sbo2, rb);   // stage 2: group stride GS rows
+      const uint32_t set_u = set_bytes >> 4;                                                                             // operand set of the odd tiles (PIPE)
+      uint64_t ahi_lin = ahi_lin0, alo_lin = alo_lin0, ahi_seg = ahi_seg0, alo_seg = alo_seg0;                           // descriptors of the tile being issued
+      uint32_t acc_base = tmem;                                                                                          // accumulator column block of the stage being issued
       const uint64_t bdesc0 = make_desc(smem_u32(ring), sbo1, rb);
       const uint32_t stage_u = (uint32_t)p.stage_bytes >> 4, region_u = (uint32_t)p.region_bytes >> 4;        // descriptor address units (16 B)
       const uint32_t tile_u2 = sbo2, ys_u = (uint32_t)p.YS * row_u1;                                                 // 16 groups * sbo2 / 16; image-row stride
@@ -379,7 +447,7 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
       auto issue_chunk = [&](uint64_t ah, uint64_t al, uint32_t tile_u, uint32_t dcols, int T, int ksn, uint32_t id2, uint32_t id1,
                              uint32_t first_acc, bool has_next) {
         const uint64_t bd = bdesc0 + st * stage_u;
-        uint32_t d = tmem;
+        uint32_t d = acc_base;
         // Straight-line blocks: the issuing thread's operands live in vector registers and every distinct value costs an R2UR move
         // per use inside a loop body, so k-steps are unrolled at compile time (descriptor + immediate) and M-tiles go two per
         // iteration; the next chunk's barrier is polled before the last block so its latency hides behind queued MMAs.
@@ -434,13 +502,13 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
         const uint64_t bd = bdesc0 + st * stage_u;
         if constexpr (T == 1) {
           constexpr int H = (KS + 1) / 2;
-          mma_tiles<F16, H, 1>(tmem, dcols, ah, al, tile_u, bd, id2, id1, first_acc);
+          mma_tiles<F16, H, 1>(acc_base, dcols, ah, al, tile_u, bd, id2, id1, first_acc);
           wait_next(has_next);
-          if constexpr (H < KS) mma_tiles<F16, KS, 1, H>(tmem, dcols, ah, al, tile_u, bd, id2, id1, first_acc);
+          if constexpr (H < KS) mma_tiles<F16, KS, 1, H>(acc_base, dcols, ah, al, tile_u, bd, id2, id1, first_acc);
         } else {
-          mma_tiles<F16, KS, T - 1>(tmem, dcols, ah, al, tile_u, bd, id2, id1, first_acc);
+          mma_tiles<F16, KS, T - 1>(acc_base, dcols, ah, al, tile_u, bd, id2, id1, first_acc);
           wait_next(has_next);
-          mma_tiles<F16, KS, 1>(tmem + (T - 1) * dcols, dcols, ah + (uint64_t)((T - 1) * tile_u), al + (uint64_t)((T - 1) * tile_u), tile_u, bd, id2, id1, first_acc);
+          mma_tiles<F16, KS, 1>(acc_base + (T - 1) * dcols, dcols, ah + (uint64_t)((T - 1) * tile_u), al + (uint64_t)((T - 1) * tile_u), tile_u, bd, id2, id1, first_acc);
         }
         if (!resident) tc_commit(bar(BAR_EMPTY) + 8u * st);
         if (++st == (uint32_t)nst) { st = 0; rphase ^= 1; }
@@ -462,20 +530,27 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
       const int s2class = (ks_last != ks_full) ? 0 : (T2 == 1 && ks_full == 4) ? 1 : (T2 == 2 && ks_full == 4) ? 2 : (T2 == 2 && ks_full == 2) ? 3
                           : (T2 == 4 && ks_full == 2) ? 4 : (T2 == 4 && ks_full == 4) ? 5 : 0;
 
-      if (my_tiles > 0) { mbar_wait(bar(BAR_FULL), 0); tc_fence_after(); }   // first chunk of the first tile; every later chunk is pre-waited
-      for (int it = 0; it < my_tiles; ++it) {
-        const uint32_t ph = it & 1;
-        const bool last_tile = it == my_tiles - 1;
-        wskip = resident && it > 0;
-        // ---- stage 1: H1 = W1 x0 over every stored row ----
-        mbar_wait(bar(BAR_AREADY), ph);
+      const int cW3 = nchunks_tile - P;                          // first W3 chunk
+      auto use_tile = [&](int it) {                              // operand set of tile `it`
+        const uint32_t o = (PIPE && (it & 1)) ? set_u : 0u;
+        ahi_lin = ahi_lin0 + o; alo_lin = alo_lin0 + o; ahi_seg = ahi_seg0 + o; alo_seg = alo_seg0 + o;
+      };
+      // ---- stage 1: H1 = W1 x0 over every stored row ----
+      auto stage1 = [&](int it) {
+        use_tile(it); acc_base = tmem + col1;
+        if (PIPE && resident) st = 0;                            // resident weights sit at their chunk index
+        mbar_wait(bar(BAR_AREADY), it & 1);
         tc_fence_after();
         tick(10);
         issue_chunk(ahi_lin, alo_lin, lin_u, tile_cols2, T1, KS1, id2N2, idN2, 0, true);
         tc_commit(bar(BAR_ACC1));
         tick(9);
-        // ---- stage 2: KH x KW taps as shifted operand views ----
-        mbar_wait(bar(BAR_H1), ph);
+      };
+      // ---- stage 2: KH x KW taps as shifted operand views ----
+      auto stage2 = [&](int it) {
+        use_tile(it); acc_base = tmem + col2;
+        if (PIPE && resident) st = 1;
+        mbar_wait(bar(BAR_H1), it & 1);
         tc_fence_after();
         tick(10);
         uint32_t first_acc = 0;
@@ -498,8 +573,13 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
         }
         tc_commit(bar(BAR_ACC2));
         tick(9);
-        // ---- stage 3: h = W3 H2 ----
-        mbar_wait(bar(BAR_H2), ph);
+      };
+      // ---- stage 3: h = W3 H2 ----
+      auto stage3 = [&](int it) {
+        const bool last_tile = it == my_tiles - 1;
+        use_tile(it); acc_base = tmem + col3;
+        if (PIPE && resident) st = (uint32_t)cW3;
+        mbar_wait(bar(BAR_H2), it & 1);
         tc_fence_after();
         tick(10);
         uint32_t pan_u = 0;
@@ -508,6 +588,25 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
                       !(last_tile && pn == P - 1));
         tc_commit(bar(BAR_ACC3));
         tick(9);
+      };
+      if (!PIPE) {
+        if (my_tiles > 0) { mbar_wait(bar(BAR_FULL), 0); tc_fence_after(); }   // first chunk of the first tile; every later chunk is pre-waited
+        for (int it = 0; it < my_tiles; ++it) {
+          wskip = resident && it > 0;
+          stage1(it); stage2(it); stage3(it);
+        }
+      } else if (my_tiles > 0) {
+        if (resident) {                                          // every chunk is loaded once, up front: wait for all of them here, never again
+          for (int c = 0; c < nchunks_tile; ++c) mbar_wait(bar(BAR_FULL) + 8u * c, 0);
+          tc_fence_after();
+          wskip = true;
+        } else { mbar_wait(bar(BAR_FULL), 0); tc_fence_after(); }
+        stage1(0); stage2(0);
+        for (int it = 0; it < my_tiles; ++it) {
+          if (it + 1 < my_tiles) stage1(it + 1);
+          stage3(it);
+          if (it + 1 < my_tiles) stage2(it + 1);
+        }
       }
       if (PROF && prof) { a.prof[8] = acc8; a.prof[9] = acc9; a.prof[10] = acc10; }
     }
@@ -518,16 +617,19 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const int row_in_tile = quad * 32 + lane;
     const int ng1 = p.KS1 * KE / 8;                           // groups of 8 channels of x0 per stored row (K zero-padded to whole k-steps)
-    constexpr bool kWide = OCC == 1;                          // epilogue item width of stages 1-2: 32 columns, 16 under the two-CTA register budget
+    constexpr bool kWide = CFPP_TC_WIDE && OCC == 1;                          // epilogue item width of stages 1-2: 32 columns, 16 under the two-CTA register budget
     constexpr int kIW = kWide ? 32 : 16;
     const int nc2 = (p.N2 + kIW - 1) / kIW, nc3 = p.N3 >> 4;  // items per M-tile (stage 3 items are 16 columns)
     const bool prof = PROF && a.prof != nullptr && blockIdx.x == 0 && tid == 0;
     long long tp = 0, pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     auto tick = [&](int slot) { if (PROF && prof) { const long long now = clock64(); pacc[slot] += now - tp; tp = now; } };
-    for (int it = 0; it < my_tiles; ++it) {
+    auto stepX = [&](int it) {
       const uint32_t ph = it & 1;
       const int tile = blockIdx.x + it * gridDim.x;
       const int b0 = tile * p.S, nS = min(p.S, p.B - b0);
+      uint8_t* a_hi = a_hi0 + ((PIPE && (it & 1)) ? set_bytes : 0u);   // operand set of this tile
+      uint8_t* a_lo = a_lo0 + ((PIPE && (it & 1)) ? set_bytes : 0u);
+      (void)ph; (void)b0; (void)nS; (void)a_hi; (void)a_lo;
       // ---- x0 staging -> operand rows (reflect halo / segment overlap applied here) ----
       if (PROF && prof) tp = clock64();
       mbar_wait(bar(BAR_XFULL), ph);
@@ -537,6 +639,7 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
           bulk_s2g(a.z + (size_t)(b0 + s) * p.Cout * HW, smem_u32(xstage + (size_t)s * xfloats), (uint32_t)(xfloats * 4));
         bulk_commit();
       }
+      if (!(PROF && (a.dbg & 2)))
       for (int r = tid; r < p.R; r += kEpiThreads) {
         const uint32_t w = tab_in[r];
         const int s = w >> 24, y = (w >> 12) & 0xFFF, x = w & 0xFFF;
@@ -554,36 +657,64 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
       mbar_arrive(bar(BAR_XEMPTY));
       mbar_arrive(bar(BAR_AREADY));
       tick(1);
+    };
+    auto stepE1 = [&](int it) {
+      const uint32_t ph = it & 1;
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b0 = tile * p.S, nS = min(p.S, p.B - b0);
+      uint8_t* a_hi = a_hi0 + ((PIPE && (it & 1)) ? set_bytes : 0u);   // operand set of this tile
+      uint8_t* a_lo = a_lo0 + ((PIPE && (it & 1)) ? set_bytes : 0u);
+      (void)ph; (void)b0; (void)nS; (void)a_hi; (void)a_lo;
       // ---- epilogue 1: H1 = relu(acc + b1) for every stored row ----
       mbar_wait(bar(BAR_ACC1), ph);
       tc_fence_after();
       tick(2);
+      if (!(PROF && (a.dbg & 1)))
       for (int item = grp, t = 0, ci = grp; item < p.T1 * nc2; item += kEpiGroups, ci += kEpiGroups) {
         while (ci >= nc2) { ci -= nc2; ++t; }                  // item -> (M-tile t, column item ci) without a division
         const int c0 = ci * kIW;
         const int r = t * 128 + row_in_tile;
-        const float* bias = sb1;
-        if (a.bias1_b != nullptr && r < p.R) bias = a.bias1_b + (size_t)min(b0 + (int)(tab_in[r] >> 24), p.B - 1) * p.Ch;
-        epilogue_to_operand<F16, kWide>(tmem + lane_base + t * 2 * p.N2, p.N2, c0, bias, a_hi, a_lo, p.region_bytes, r, r < p.R, rb);
+        if (a.bias1_b == nullptr)                                // two call sites: the shared-memory bias keeps LDS addressing
+          epilogue_to_operand<F16, kWide>(tmem + col1 + lane_base + t * 2 * p.N2, p.N2, c0, sb1, a_hi, a_lo, p.region_bytes, r, r < p.R, rb);
+        else
+          epilogue_to_operand<F16, kWide>(tmem + col1 + lane_base + t * 2 * p.N2, p.N2, c0,
+                                          a.bias1_b + (size_t)min(b0 + (r < p.R ? (int)(tab_in[r] >> 24) : 0), p.B - 1) * p.Ch, a_hi, a_lo, p.region_bytes, r, r < p.R, rb);
       }
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(bar(BAR_H1));
       tick(3);
+    };
+    auto stepE2 = [&](int it) {
+      const uint32_t ph = it & 1;
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b0 = tile * p.S, nS = min(p.S, p.B - b0);
+      uint8_t* a_hi = a_hi0 + ((PIPE && (it & 1)) ? set_bytes : 0u);   // operand set of this tile
+      uint8_t* a_lo = a_lo0 + ((PIPE && (it & 1)) ? set_bytes : 0u);
+      (void)ph; (void)b0; (void)nS; (void)a_hi; (void)a_lo;
       // ---- epilogue 2: H2 = relu(acc + b2) at the accumulator's own row index ----
       mbar_wait(bar(BAR_ACC2), ph);
       tc_fence_after();
       tick(4);
+      if (!(PROF && (a.dbg & 1)))
       for (int item = grp, t = 0, ci = grp; item < p.T2 * nc2; item += kEpiGroups, ci += kEpiGroups) {
         while (ci >= nc2) { ci -= nc2; ++t; }
         const int c0 = ci * kIW;
         const int m = t * 128 + row_in_tile;
-        epilogue_to_operand<F16, kWide>(tmem + lane_base + t * 2 * p.N2, p.N2, c0, sb2, a_hi, a_lo, p.region_bytes, m, (tab_out[m] >> 31) != 0, rb);
+        epilogue_to_operand<F16, kWide>(tmem + col2 + lane_base + t * 2 * p.N2, p.N2, c0, sb2, a_hi, a_lo, p.region_bytes, m, (tab_out[m] >> 31) != 0, rb);
       }
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(bar(BAR_H2));
       tick(5);
+    };
+    auto stepE3 = [&](int it) {
+      const uint32_t ph = it & 1;
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b0 = tile * p.S, nS = min(p.S, p.B - b0);
+      uint8_t* a_hi = a_hi0 + ((PIPE && (it & 1)) ? set_bytes : 0u);   // operand set of this tile
+      uint8_t* a_lo = a_lo0 + ((PIPE && (it & 1)) ? set_bytes : 0u);
+      (void)ph; (void)b0; (void)nS; (void)a_hi; (void)a_lo;
       // ---- epilogue 3: h = acc + b3 -> HBM (NCHW) ----
       mbar_wait(bar(BAR_ACC3), ph);
       tc_fence_after();
@@ -601,7 +732,7 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
           const bool valid = (w >> 31) != 0 && s < nS;
           const size_t bb = (size_t)(b0 + (valid ? s : 0));
           const int pix = y * p.W + x;
-          const uint32_t taddr = tmem + lane_base + t * 2 * p.N3;
+          const uint32_t taddr = tmem + col3 + lane_base + t * 2 * p.N3;
           float vt[8], ut[8], vr[8], ur[8];
           tmem_ld8(taddr + k0, vt); tmem_ld8(taddr + p.N3 + k0, ut);
           tmem_ld8(taddr + half + k0, vr); tmem_ld8(taddr + p.N3 + half + k0, ur);
@@ -649,7 +780,7 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         for (int i = tid; i < kEpiGroups * p.T2 * 128; i += kEpiThreads) reinterpret_cast<float*>(base + p.off_ls)[i] = 0.f;
-      } else
+      } else if (!(PROF && (a.dbg & 1)))
       for (int item = grp, t = 0, ci = grp; item < p.T2 * nc3; item += kEpiGroups, ci += kEpiGroups) {
         while (ci >= nc3) { ci -= nc3; ++t; }
         const int c0 = ci << 4;
@@ -658,7 +789,7 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
         const int s = (w >> 24) & 0x7F, y = (w >> 12) & 0xFFF, x = w & 0xFFF;
         const bool valid = (w >> 31) != 0 && s < nS;
         float* dst = a.h + ((size_t)(b0 + (valid ? s : 0)) * p.Cout) * HW + y * p.W + x;
-        const uint32_t taddr = tmem + lane_base + t * 2 * p.N3;
+        const uint32_t taddr = tmem + col3 + lane_base + t * 2 * p.N3;
         float v[16], u[16];
         tmem_ld16(taddr + c0, v);
         tmem_ld16(taddr + p.N3 + c0, u);
@@ -671,6 +802,18 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
       }
       tc_fence_before();
       tick(7);
+    };
+    if (!PIPE) {
+      for (int it = 0; it < my_tiles; ++it) { stepX(it); stepE1(it); stepE2(it); stepE3(it); }
+    } else if (my_tiles > 0) {
+      // two tiles interleaved: the MMA stage an epilogue step waits for was issued two steps earlier (see the kernel's header comment)
+      stepX(0); stepE1(0);
+      for (int it = 0; it < my_tiles; ++it) {
+        if (it + 1 < my_tiles) stepX(it + 1);
+        stepE2(it);
+        if (it + 1 < my_tiles) stepE1(it + 1);
+        stepE3(it);
+      }
     }
     if (PROF && prof) {
 #pragma unroll
@@ -734,7 +877,7 @@ static int tc_kind() {
 // operand row bytes: the fp16 kind stores <= 32 channels in 64-byte rows (SWIZZLE_64B) -- half the shared memory of a padded 128-byte row
 static int row_bytes(int kind, int Cin, int Ch) { return (kind == 1 && Ch <= 32 && Cin <= 32 && env_int("CFPP_TC_RB64", 1)) ? 64 : 128; }
 
-static bool make_plan_occ(Plan& p, double& waste_out, int occ, int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, long long x_bstride, int sms) {
+static bool make_plan_occ(Plan& p, double& waste_out, int occ, int pipe, int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, long long x_bstride, int sms) {
   const int max_s = env_int("CFPP_TC_MAXS", 32);
   const int kind = tc_kind(), rb = row_bytes(kind, Cin, Ch), CPR = kind ? rb >> 1 : 32, KE = kind ? 16 : 8;
   if (!((KH == 1 || KH == 3) && (KW == 1 || KW == 3))) return false;
@@ -743,7 +886,7 @@ static bool make_plan_occ(Plan& p, double& waste_out, int occ, int B, int Cin, i
   if ((Cin * H * W) % 4 != 0 || x_bstride % 4 != 0) return false;      // 16-byte bulk copies of x0
   p = Plan{};
   p.B = B; p.Cin = Cin; p.Ch = Ch; p.Cout = Cout; p.H = H; p.W = W; p.KH = KH; p.KW = KW; p.x_bstride = x_bstride;
-  p.kind = kind; p.rb = rb; p.occ = occ;
+  p.kind = kind; p.rb = rb; p.occ = occ; p.pipe = pipe;
   sms *= occ;                                                            // resident CTA slots
   const int tmem_cols = 512 / occ;
   p.P = (Ch + CPR - 1) / CPR; p.KS1 = (Cin + KE - 1) / KE; p.N2 = Ch; p.N3 = (Cout + 15) / 16 * 16;
@@ -769,9 +912,11 @@ static bool make_plan_occ(Plan& p, double& waste_out, int occ, int B, int Cin, i
       }
       q.T1 = (q.R + 127) / 128;
       if (q.T1 * 2 * q.N2 > tmem_cols || q.T2 * 2 * q.N2 > tmem_cols || q.T2 * 2 * q.N3 > tmem_cols) break;
+      if (pipe && q.T1 * 2 * q.N2 + q.T2 * 2 * q.N2 + q.T2 * 2 * q.N3 > tmem_cols) break;   // three disjoint accumulator column blocks
       q.region_bytes = ((q.R + 15) / 16 * 16) * rb;          // multiple of 1024 bytes: every region starts on a swizzle-atom boundary
       // operand rows the MMAs may touch (garbage rows included) must stay inside this CTA's shared memory
-      q.off_ring = 2 * q.P * q.region_bytes;
+      const int set_bytes = 2 * q.P * q.region_bytes;           // one (hi | lo) operand set; PIPE keeps two (tile parity)
+      q.off_ring = (pipe ? 2 : 1) * set_bytes;
       const int xbytes = (S * Cin * HW * 4 + 127) / 128 * 128;
       const int tab_bytes = (q.R + q.T2 * 128) * 4;
       const int ls_bytes = epi_warps(occ) / 4 * q.T2 * 128 * 4;          // per (epilogue group, accumulator row) log-scale partials of the fused coupling
@@ -785,7 +930,7 @@ static bool make_plan_occ(Plan& p, double& waste_out, int occ, int B, int Cin, i
       q.nstages = nst;
       const int reach1 = q.T1 * 128 * rb;                                                     // stage 1 / 3 tiles
       const int reach2 = ((q.T2 * 16 - 1) * q.GS + (KH - 1) * q.YS + (KW - 1) + 8) * rb;       // last group of the last tap
-      const int reach = (reach1 > reach2 ? reach1 : reach2) + (2 * q.P - 1) * q.region_bytes;
+      const int reach = (reach1 > reach2 ? reach1 : reach2) + (2 * q.P - 1) * q.region_bytes + (pipe ? set_bytes : 0);
       if (reach > q.off_ring + nst * q.stage_bytes) continue;
       q.off_stage_x = q.off_ring + nst * q.stage_bytes;
       q.off_bias = q.off_stage_x + xbytes;
@@ -806,12 +951,19 @@ static bool make_plan_occ(Plan& p, double& waste_out, int occ, int B, int Cin, i
   return found;
 }
 
-// CFPP_TC_OCC = 1 / 2 forces the residency; default: two CTAs per SM when such a plan exists and wastes at most 30 % more MMA rows
+// CFPP_TC_OCC = 1 / 2 forces the residency; default: two CTAs per SM when such a plan exists and wastes at most 30 % more MMA rows.
+// CFPP_TC_PIPE = 1 turns the software-pipelined form on (one CTA per SM) whenever the shape has such a plan (fp16 kind)
+// and it wastes at most 30 % more MMA rows than the best unpipelined plan.
 static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, long long x_bstride, int sms) {
   const int force = env_int("CFPP_TC_OCC", 0);
-  Plan p1, p2; double w1 = 0, w2 = 0;
-  const bool ok1 = force != 2 && make_plan_occ(p1, w1, 1, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, sms);
-  const bool ok2 = force != 1 && make_plan_occ(p2, w2, 2, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, sms);
+  Plan p1, p2, pp; double w1 = 0, w2 = 0, wp = 0;
+  const bool ok1 = force != 2 && make_plan_occ(p1, w1, 1, 0, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, sms);
+  const bool ok2 = force != 1 && make_plan_occ(p2, w2, 2, 0, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, sms);
+  const bool okp = force != 2 && tc_kind() == 1 && env_int("CFPP_TC_PIPE", 0) && make_plan_occ(pp, wp, 1, 1, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, sms);
+  if (okp) {
+    const double wbest = ok1 && ok2 ? (w1 < w2 ? w1 : w2) : ok1 ? w1 : ok2 ? w2 : wp;
+    if (wp <= 1.3 * wbest) { p = pp; return true; }
+  }
   if (ok2 && (!ok1 || w2 <= 1.3 * w1)) { p = p2; return true; }
   if (ok1) { p = p1; return true; }
   return false;
@@ -861,29 +1013,34 @@ static int conv_cond_tc_launch(const float* x, int64_t x_bstride, float* h, cons
   tc::g_last_plan = p;
   const int P_ = p.P;
   const long long pack_bytes = (long long)(1 + KH * KW * P_ + P_) * (2 * Ch * p.rb);
-  tc::Args a{x, h, (const uint8_t*)wpack, b1, b2, b3, bias1_b, z, ldj, add, logp_c, logp_scale, pack_bytes, tc::env_int("CFPP_TC_REPL", 1), tc::g_prof};
+  tc::Args a{x, h, (const uint8_t*)wpack, b1, b2, b3, bias1_b, z, ldj, add, logp_c, logp_scale, pack_bytes, tc::env_int("CFPP_TC_REPL", 1), tc::env_int("CFPP_TC_DBG", 0), tc::g_prof};
   const int slots = num_sms() * p.occ;
   const int grid = p.ntiles < slots ? p.ntiles : slots;
   cudaStream_t st = (cudaStream_t)stream;
   using KernelFn = void (*)(const tc::Plan, const tc::Args);
-  static const KernelFn kernels[16] = {
-      tc::conv_cond_tc_kernel<false, false, false, 1>, tc::conv_cond_tc_kernel<false, false, true, 1>,
-      tc::conv_cond_tc_kernel<false, true, false, 1>,  tc::conv_cond_tc_kernel<false, true, true, 1>,
-      tc::conv_cond_tc_kernel<true, false, false, 1>,  tc::conv_cond_tc_kernel<true, false, true, 1>,
-      tc::conv_cond_tc_kernel<true, true, false, 1>,   tc::conv_cond_tc_kernel<true, true, true, 1>,
-      tc::conv_cond_tc_kernel<false, false, false, 2>, tc::conv_cond_tc_kernel<false, false, true, 2>,
-      tc::conv_cond_tc_kernel<false, true, false, 2>,  tc::conv_cond_tc_kernel<false, true, true, 2>,
-      tc::conv_cond_tc_kernel<true, false, false, 2>,  tc::conv_cond_tc_kernel<true, false, true, 2>,
-      tc::conv_cond_tc_kernel<true, true, false, 2>,   tc::conv_cond_tc_kernel<true, true, true, 2>};
+  static const KernelFn kernels[20] = {
+      tc::conv_cond_tc_kernel<false, false, false, 1, false>, tc::conv_cond_tc_kernel<false, false, true, 1, false>,
+      tc::conv_cond_tc_kernel<false, true, false, 1, false>,  tc::conv_cond_tc_kernel<false, true, true, 1, false>,
+      tc::conv_cond_tc_kernel<true, false, false, 1, false>,  tc::conv_cond_tc_kernel<true, false, true, 1, false>,
+      tc::conv_cond_tc_kernel<true, true, false, 1, false>,   tc::conv_cond_tc_kernel<true, true, true, 1, false>,
+      tc::conv_cond_tc_kernel<false, false, false, 2, false>, tc::conv_cond_tc_kernel<false, false, true, 2, false>,
+      tc::conv_cond_tc_kernel<false, true, false, 2, false>,  tc::conv_cond_tc_kernel<false, true, true, 2, false>,
+      tc::conv_cond_tc_kernel<true, false, false, 2, false>,  tc::conv_cond_tc_kernel<true, false, true, 2, false>,
+      tc::conv_cond_tc_kernel<true, true, false, 2, false>,   tc::conv_cond_tc_kernel<true, true, true, 2, false>,
+      // software-pipelined tiles: fp16 kind, one CTA per SM; index 16 + (seg ? 2 : 0) + (profile ? 1 : 0)
+      tc::conv_cond_tc_kernel<false, false, true, 1, true>,   tc::conv_cond_tc_kernel<false, true, true, 1, true>,
+      tc::conv_cond_tc_kernel<true, false, true, 1, true>,    tc::conv_cond_tc_kernel<true, true, true, 1, true>};
   static bool attr_set = false;
   if (!attr_set) {
-    for (int i = 0; i < 16; ++i) {
-      cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, i < 8 ? 227 * 1024 : (228 * 1024) / 2 - 1024);
+    for (int i = 0; i < 20; ++i) {
+      cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (i < 8 || i >= 16) ? 227 * 1024 : (228 * 1024) / 2 - 1024);
       cudaFuncSetAttribute(kernels[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
     attr_set = true;
   }
-  kernels[(p.occ == 2 ? 8 : 0) | (p.seg ? 4 : 0) | (a.prof != nullptr ? 2 : 0) | (p.kind ? 1 : 0)]<<<grid, tc::cta_threads(p.occ), p.smem_bytes, st>>>(p, a);
+  const int ki = p.pipe ? 16 + (p.seg ? 2 : 0) + (a.prof != nullptr ? 1 : 0)
+                        : (p.occ == 2 ? 8 : 0) | (p.seg ? 4 : 0) | (a.prof != nullptr ? 2 : 0) | (p.kind ? 1 : 0);
+  kernels[ki]<<<grid, tc::cta_threads(p.occ), p.smem_bytes, st>>>(p, a);
   return check_launch("conv_cond_tc_fwd");
 }
 
@@ -910,9 +1067,9 @@ extern "C" int cfpp_conv_cond_tc_coupling_fwd(const float* x, float* z, float* l
 extern "C" int cfpp_conv_cond_tc_kind(void) { return tc::tc_kind(); }
 
 /* geometry of the last launch, for tests / bench reporting: {seg, S, R, T1, T2, nstages, smem_bytes, ntiles, CTAs per SM, row bytes} */
-extern "C" void cfpp_conv_cond_tc_last_plan(int* out8) {
+extern "C" void cfpp_conv_cond_tc_last_plan(int* out8) {   /* 11 values, see cfpp.h */
   const tc::Plan& p = tc::g_last_plan;
-  out8[8] = p.occ; out8[9] = p.rb;
+  out8[8] = p.occ; out8[9] = p.rb; out8[10] = p.pipe;
   out8[0] = p.seg; out8[1] = p.S; out8[2] = p.R; out8[3] = p.T1; out8[4] = p.T2; out8[5] = p.nstages; out8[6] = p.smem_bytes; out8[7] = p.ntiles;
 }
 

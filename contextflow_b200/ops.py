@@ -497,9 +497,9 @@ def conv_cond_tc_coupling(x, wpack, b1, b2, b3, ch, KH, KW, add=None, logp_c=Non
 
 
 def conv_cond_tc_last_plan():
-    out = (_cabi.i32 * 10)()
+    out = (_cabi.i32 * 12)()
     lib().cfpp_conv_cond_tc_last_plan(out)
-    return dict(zip(('seg', 'S', 'R', 'T1', 'T2', 'nstages', 'smem_bytes', 'ntiles', 'occ', 'row_bytes'), list(out)))
+    return dict(zip(('seg', 'S', 'R', 'T1', 'T2', 'nstages', 'smem_bytes', 'ntiles', 'occ', 'row_bytes', 'pipe'), list(out)))
 
 
 def vit_cond(x, desc: _cabi.VitDesc, cout, extra=None):

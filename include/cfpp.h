@@ -147,8 +147,9 @@ int cfpp_conv_cond_tc_coupling_fwd(const float* x, float* z, float* ldj, const v
  * CFPP_TC_KIND=tf32).  Packed weights are specific to the kind they were packed under. */
 int cfpp_conv_cond_tc_kind(void);
 /* geometry of the last cfpp_conv_cond_tc_fwd launch (tests / bench): {segment layout, samples per tile, stored rows, M-tiles of
- * stage 1, M-tiles of stages 2-3, ring stages, shared-memory bytes, tiles, CTAs resident per SM, operand row bytes} (10 ints) */
-void cfpp_conv_cond_tc_last_plan(int* out10);
+ * stage 1, M-tiles of stages 2-3, ring stages, shared-memory bytes, tiles, CTAs resident per SM, operand row bytes, software-pipelined
+ * tiles (1/0)} (11 ints; pass room for 12) */
+void cfpp_conv_cond_tc_last_plan(int* out12);
 /* debug instrumentation: device array of 12 int64 cycle counters that CTA 0 accumulates over its tiles; NULL = off.
  * epilogue thread 0: {wait x0, x0 transform, wait stage-1 MMAs, epilogue 1, wait stage-2 MMAs, epilogue 2, wait stage-3 MMAs,
  * epilogue 3}; MMA thread: {wait weight chunk, issue, wait operands, spare} */
