@@ -54,7 +54,7 @@ struct Plan {
   int resident;                      // 1: nstages == chunks per tile, the weight chunks are loaded once per CTA and never recycled
   int pipe;                          // 1: software-pipelined tiles (two operand sets, disjoint accumulator column blocks), see the kernel
   int region_bytes;                  // bytes of one (hi|lo, panel) operand region
-  int off_ring, off_stage_x, off_bias, off_tab, off_ls, off_bar, smem_bytes;   // off_tab: R + T2*128 packed row-decode words; off_ls: per-row log-scale partials
+  int off_ring, off_stage_x, off_bias, off_tab, off_ls, off_add, off_bar, smem_bytes;   // off_tab: R + T2*128 packed row-decode words; off_ls: per-row log-scale partials; off_add: S x N3 per-sample output bias (b3 + CN(c)) of the fused coupling
   long long x_bstride;
 };
 
@@ -652,6 +652,13 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
           store_group8<F16>(a_hi, a_lo, r, 8 * j, o, rb);
         }
       }
+      if (a.z != nullptr && a.add != nullptr) {                // fused coupling: b3 + CN(c) of this tile's samples (read by epilogue 3, ordered by the barrier chain)
+        float* sadd = reinterpret_cast<float*>(base + p.off_add);
+        for (int i = tid; i < nS * p.N3; i += kEpiThreads) {
+          const int s_ = i / p.N3, c_ = i - s_ * p.N3;
+          sadd[i] = c_ < p.Cout ? sb3[c_] + __ldg(a.add + (size_t)(b0 + s_) * p.Cout + c_) : 0.f;
+        }
+      }
       fence_async_smem();
       if (a.z != nullptr && tid == 0) bulk_wait_read();        // the staging buffer may be refilled once the bulk store has read it
       mbar_arrive(bar(BAR_XEMPTY));
@@ -716,12 +723,25 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
       uint8_t* a_lo = a_lo0 + ((PIPE && (it & 1)) ? set_bytes : 0u);
       (void)ph; (void)b0; (void)nS; (void)a_hi; (void)a_lo;
       // ---- epilogue 3: h = acc + b3 -> HBM (NCHW) ----
+      // fused coupling: the x1 values of an item are fetched one item ahead, the first item's before the wait for the stage-3 MMAs, so the
+      // HBM latency of these loads hides behind the tensor pipe instead of sitting between the accumulator load and the transform
+      const int half = p.Cout >> 1, nck = half >> 3;             // items of 8 (t, r) channel pairs; half % 8 == 0 (host)
+      float x1c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      auto fetch_x1 = [&](int t, int ci, float (&dst)[8]) {
+        const uint32_t w = tab_out[t * 128 + row_in_tile];
+        const int s = (w >> 24) & 0x7F;
+        if ((w >> 31) != 0 && s < nS) {
+          const float* xs1 = a.x + (size_t)(b0 + s) * p.x_bstride + (size_t)(half + (ci << 3)) * HW + ((w >> 12) & 0xFFF) * p.W + (w & 0xFFF);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[i] = __ldg(xs1 + (size_t)i * HW);
+        }
+      };
+      if (a.z != nullptr && grp < p.T2 * nck) { int t = 0, ci = grp; while (ci >= nck) { ci -= nck; ++t; } fetch_x1(t, ci, x1c); }
       mbar_wait(bar(BAR_ACC3), ph);
       tc_fence_after();
       tick(6);
       if (a.z != nullptr) {
         // ---- fused affine coupling: (t | r) = acc + b3 (+ CN(c)); z0 = x0, z1 = x1 * exp(2 tanh(r / 2)) + t; ldj = sum log-scale ----
-        const int half = p.Cout >> 1, nck = half >> 3;           // items of 8 (t, r) channel pairs; half % 8 == 0 (host)
         float* lsp = reinterpret_cast<float*>(base + p.off_ls) + grp * (p.T2 * 128);
         for (int item = grp, t = 0, ci = grp; item < p.T2 * nck; item += kEpiGroups, ci += kEpiGroups) {
           while (ci >= nck) { ci -= nck; ++t; }
@@ -736,22 +756,22 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
           float vt[8], ut[8], vr[8], ur[8];
           tmem_ld8(taddr + k0, vt); tmem_ld8(taddr + p.N3 + k0, ut);
           tmem_ld8(taddr + half + k0, vr); tmem_ld8(taddr + p.N3 + half + k0, ur);
-          float x1v[8];
-          if (valid) {
-            const float* xs1 = a.x + bb * p.x_bstride + (size_t)(half + k0) * HW + pix;
+          float x1v[8], x1n[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x1v[i] = __ldg(xs1 + (size_t)i * HW);
+          for (int i = 0; i < 8; ++i) x1v[i] = x1c[i];
+          if (item + kEpiGroups < p.T2 * nck) {                  // the next item's x1 goes in flight under this item's transform
+            int t2 = t, c2 = ci + kEpiGroups; while (c2 >= nck) { c2 -= nck; ++t2; }
+            fetch_x1(t2, c2, x1n);
           }
           tmem_ld_wait();
           if (valid) {
             float* zd = a.z + (bb * p.Cout + k0) * HW + pix;
-            const float* addb = a.add ? a.add + bb * p.Cout : nullptr;
+            const float* ob = a.add ? reinterpret_cast<const float*>(base + p.off_add) + s * p.N3 : sb3;   // output bias: b3 (+ CN(c) of the sample)
             float lsum = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float tt = (F16 ? fmaf(ut[i], kLoInv, vt[i]) : vt[i] + ut[i]) + sb3[k0 + i];
-              float rr = (F16 ? fmaf(ur[i], kLoInv, vr[i]) : vr[i] + ur[i]) + sb3[half + k0 + i];
-              if (addb) { tt += __ldg(addb + k0 + i); rr += __ldg(addb + half + k0 + i); }
+              const float tt = (F16 ? fmaf(ut[i], kLoInv, vt[i]) : vt[i] + ut[i]) + ob[k0 + i];
+              const float rr = (F16 ? fmaf(ur[i], kLoInv, vr[i]) : vr[i] + ur[i]) + ob[half + k0 + i];
               // log_s = 2 tanh(r/2) = 2 (1 - e^-r) / (1 + e^-r) with the SFU exponential (relative error ~2^-21; tanh saturates in fp32 beyond
               // |r| = 18, the clamp keeps e^-r finite): ~12 instructions instead of ~60 for tanhf + expf on the epilogue warps' critical path
               const float e = __expf(-fminf(fmaxf(rr, -30.f), 30.f));
@@ -761,6 +781,8 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
             }
             lsp[m] += lsum;
           }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x1c[i] = x1n[i];
         }
         tc_fence_before();
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
@@ -920,7 +942,8 @@ static bool make_plan_occ(Plan& p, double& waste_out, int occ, int pipe, int B, 
       const int xbytes = (S * Cin * HW * 4 + 127) / 128 * 128;
       const int tab_bytes = (q.R + q.T2 * 128) * 4;
       const int ls_bytes = epi_warps(occ) / 4 * q.T2 * 128 * 4;          // per (epilogue group, accumulator row) log-scale partials of the fused coupling
-      const int fixed = q.off_ring + xbytes + bias_bytes + tab_bytes + ls_bytes + bar_bytes + 256;
+      const int add_bytes = S * q.N3 * 4;
+      const int fixed = q.off_ring + xbytes + bias_bytes + tab_bytes + ls_bytes + add_bytes + bar_bytes + 256;
       int nst = (kSmemMax - fixed) / q.stage_bytes;
       if (nst < 2) break;
       const int nchunks = 1 + KH * KW * q.P + q.P;
@@ -936,7 +959,8 @@ static bool make_plan_occ(Plan& p, double& waste_out, int occ, int pipe, int B, 
       q.off_bias = q.off_stage_x + xbytes;
       q.off_tab = (q.off_bias + bias_bytes + 15) / 16 * 16;
       q.off_ls = (q.off_tab + tab_bytes + 15) / 16 * 16;
-      q.off_bar = (q.off_ls + ls_bytes + 15) / 16 * 16;
+      q.off_add = (q.off_ls + ls_bytes + 15) / 16 * 16;
+      q.off_bar = (q.off_add + add_bytes + 15) / 16 * 16;
       q.smem_bytes = q.off_bar + bar_bytes + 1024;
       q.ntiles = (B + S - 1) / S;
       // cost: MMA row-slots per real pixel, plus a penalty when the batch no longer fills the SMs evenly
