@@ -42,6 +42,15 @@ _SIGNATURES = {
     'cfpp_version': (i32, []),
     'cfpp_last_error': (C.c_char_p, []),
     'cfpp_launch_count': (i64, []),
+    'cfpp_maf_coupling_ctx_fwd': (i32, [vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, vp]),
+    'cfpp_activation_fwd': (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
+    'cfpp_activation_inv': (i32, [vp, vp, vp, i64, f32, i32, vp]),
+    'cfpp_activation_bwd': (i32, [vp, vp, vp, vp, vp, i64, i32, i32, vp]),
+    'cfpp_student_table_floats': (i64, [i32, i32, i32]),
+    'cfpp_student_prep': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    'cfpp_student_logprob': (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    'cfpp_bias_rows_relu': (i32, [vp, vp, i32, i32, i32, vp]),
+    'cfpp_gmm_ctx_param_bwd': (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     'cfpp_squeeze_fwd': (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     'cfpp_squeeze_inv': (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     'cfpp_permute_fwd': (i32, [vp, vp, i32, i32, i32, i32, vp]),

@@ -67,7 +67,9 @@ __global__ void __launch_bounds__(256) coupling_kernel(const float* __restrict__
 // MaskedCoupling.forward (layers/ar.py:35-57): the block output carries the identity x on both halves (masked_conv_2d.py:92,98), so
 // t = h[:, :C] + x, r = h[:, C:] + x; log_s = 2 tanh(r/2); z = x e^{log_s} + t over ALL C channels; ldj[b] = sum log_s.
 // h is (B, 2C, HW).  16*C*HW bytes per sample.
-__global__ void __launch_bounds__(256) maf_coupling_kernel(const float* __restrict__ x, const float* __restrict__ h, float* __restrict__ z,
+// --contextflow specialist (ar.py:39-42): h += CN(c) (`add`, (B, 2C), broadcast over the pixels), ldj += logp_scale * logp_c[b].
+__global__ void __launch_bounds__(256) maf_coupling_kernel(const float* __restrict__ x, const float* __restrict__ h, const float* __restrict__ add,
+                                                           const float* __restrict__ logp_c, float logp_scale, float* __restrict__ z,
                                                            float* __restrict__ ldj, int B, int C, int HW, int G) {
   __shared__ float red[32];
   const int spc = blockDim.x / G;
@@ -78,15 +80,18 @@ __global__ void __launch_bounds__(256) maf_coupling_kernel(const float* __restri
   float acc = 0.f;
   if (valid) {
     const float* xb = x + b * n; const float* hb = h + b * 2 * n; float* zb = z + b * n;
+    const float* ab = add ? add + b * 2 * C : nullptr;
     for (int64_t i = g; i < n; i += G) {
       const float xv = xb[i];
+      float at = 0.f, ar = 0.f;
+      if (ab) { const int ch = (int)(i / HW); at = ab[ch]; ar = ab[C + ch]; }
       float o;
-      couple1(xv, hb[i] + xv, hb[n + i] + xv, o, acc);
+      couple1(xv, hb[i] + at + xv, hb[n + i] + ar + xv, o, acc);
       zb[i] = o;
     }
   }
   acc = group_sum(acc, G, red);
-  if (valid && g == 0) ldj[b] = acc;
+  if (valid && g == 0) ldj[b] = acc + (logp_c ? logp_scale * logp_c[b] : 0.f);
 }
 
 // MaskedCoupling backward: z = x s + t with t = h_t + x, r = h_r + x, s = exp(2 tanh(r/2)), ldj = sum 2 tanh(r/2).
@@ -126,15 +131,20 @@ extern "C" int cfpp_coupling_fwd(const float* x, const float* h, const float* ad
   return check_launch("coupling_fwd");
 }
 
-extern "C" int cfpp_maf_coupling_fwd(const float* x, const float* h, float* z, float* ldj, int B, int C, int HW, void* stream) {
+extern "C" int cfpp_maf_coupling_ctx_fwd(const float* x, const float* h, const float* add, const float* logp_c, float logp_scale,
+                                         float* z, float* ldj, int B, int C, int HW, void* stream) {
   CFPP_REQUIRE(C >= 1 && HW >= 1, "maf_coupling: C=%d HW=%d", C, HW);
   if (B <= 0) return CFPP_OK;
   const int64_t n = (int64_t)C * HW;
   int G = 32;
   while (G < 256 && G * 4 < n) G <<= 1;
   const int spc = 256 / G;
-  maf_coupling_kernel<<<(B + spc - 1) / spc, 256, 0, (cudaStream_t)stream>>>(x, h, z, ldj, B, C, HW, G);
+  maf_coupling_kernel<<<(B + spc - 1) / spc, 256, 0, (cudaStream_t)stream>>>(x, h, add, logp_c, logp_scale, z, ldj, B, C, HW, G);
   return check_launch("maf_coupling_fwd");
+}
+
+extern "C" int cfpp_maf_coupling_fwd(const float* x, const float* h, float* z, float* ldj, int B, int C, int HW, void* stream) {
+  return cfpp_maf_coupling_ctx_fwd(x, h, nullptr, nullptr, 0.f, z, ldj, B, C, HW, stream);
 }
 
 extern "C" int cfpp_maf_coupling_bwd(const float* x, const float* h, const float* dz, const float* dldj, float* dx, float* dh,

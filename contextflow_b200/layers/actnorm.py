@@ -60,7 +60,8 @@ class ActNorm(FlowActivationLayer):
 
     def forward(self, x, context=None):
         if self.context_net and training.wants_grad(x, self.CN.weight, self.CN.bias):
-            inference_only(self.NN_t)
+            if self.contextflow:                                       # conventional: NN_t / NN_logs are unused (actnorm.py:53-54) and get no gradient
+                inference_only(self.NN_t)
             if self.contextflow and not self.is_initialized():
                 self.initialize(x)
             c, logp_c = training.encode(self, context)

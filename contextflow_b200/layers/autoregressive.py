@@ -6,7 +6,7 @@ import torch.nn as nn
 
 from .. import ops
 
-__all__ = ['MaskedConv2d', 'MaskedResidualBlock2d', 'mask_channels', 'mask_conv2d']
+__all__ = ['MaskedConv2d', 'MaskedResidualBlock2d', 'MaskedLinear', 'MaskedResidualBlockLinear', 'mask_channels', 'mask_conv2d']
 
 
 def mask_channels(mask_type, in_channels, out_channels, data_channels=3):
@@ -89,3 +89,48 @@ class MaskedResidualBlock2d(nn.Module):
         for conv in (self.conv1, self.conv2, self.conv3):                  # FP32 kernels: shapes without a tensor-core plan
             h = ops.conv2d_fwd(h, h.shape[1], conv.masked_weight(), conv.bias.detach(), relu=False, relu_in=True)
         return h
+
+
+class MaskedLinear(nn.Linear):
+    """masked_linear.py:17-102, the hidden-layer form MaskedResidualBlockLinear uses (is_output = False, no random mask): out degrees
+    cycle over 1 .. data_features - 1, mask[o, i] = out_degree[o] >= in_degree[i]; forward = F.linear(x, weight * mask, bias).  Buffers
+    `mask` and `degrees` as in the reference, so checkpoints load."""
+
+    def __init__(self, in_degrees, out_features, data_features, bias=True):
+        super().__init__(in_features=len(in_degrees), out_features=out_features, bias=bias)
+        self.data_features = data_features
+        max_, min_ = max(1, data_features - 1), min(1, data_features - 1)
+        out_degrees = torch.arange(out_features) % max_ + min_
+        self.register_buffer('mask', (out_degrees[..., None] >= in_degrees).float())
+        self.register_buffer('degrees', out_degrees)
+
+    @staticmethod
+    def get_data_degrees(in_features):
+        return torch.arange(1, in_features + 1)
+
+    def masked_weight(self):
+        return (self.weight * self.mask).detach()
+
+    def forward(self, x):
+        return ops.rows_linear(x, self.masked_weight(), self.bias.detach())
+
+
+class MaskedResidualBlockLinear(nn.Module):
+    """masked_linear.py:104-128: linear1(relu(x)) -> linear2(relu(.)) -> linear3(relu(.)) + x.  The output is 2*O wide and the identity I
+    wide: like the reference's `x + identity`, this only works when I == 2*O or I == 1."""
+
+    def __init__(self, I, O, D):
+        super().__init__()
+        self.linear1 = MaskedLinear(MaskedLinear.get_data_degrees(1 * I), 2 * I, D)
+        self.linear2 = MaskedLinear(MaskedLinear.get_data_degrees(2 * I), 2 * I, D)
+        self.linear3 = MaskedLinear(MaskedLinear.get_data_degrees(2 * I), 2 * O, D)
+        self.I, self.O = I, O
+
+    def forward(self, c):
+        if self.I not in (1, 2 * self.O):
+            raise RuntimeError(f'The size of tensor a ({2 * self.O}) must match the size of tensor b ({self.I}) at non-singleton dimension 1')   # masked_linear.py:128
+        h = c
+        for lin in (self.linear1, self.linear2, self.linear3):
+            h = lin(ops.relu(h))
+        ident = c if self.I == 2 * self.O else c.expand(c.shape[0], 2 * self.O).contiguous()
+        return ops.add(h, ident)

@@ -40,7 +40,8 @@ class Conv1x1(FlowLayer):
         if training.wants_grad(x, self.NN) and not self.context_net:
             return training.Conv1x1Fn.apply(x, self.NN, self)          # autograd through libcfpp kernels
         if self.context_net and training.wants_grad(x, self.CN.weight, self.CN.bias):
-            inference_only(self.NN)                                   # specialist: gradients w.r.t. CN, the encoder and the input
+            if self.contextflow:                                       # specialist: gradients w.r.t. CN, the encoder and the input;
+                inference_only(self.NN)                               # a conventional specialist never reads NN (conv1x1.py:46-49): it gets no gradient, as in the reference
             c, logp_c = training.encode(self, context)
             cmat = training.LinearRowsFn.apply(c, self.CN.weight, self.CN.bias)
             return training.Conv1x1CtxFn.apply(x, cmat, logp_c, self)

@@ -97,16 +97,15 @@ class Coupling(_CouplingBase):
         if not self.context_net and training.wants_grad(x, *self.NN.parameters()):
             c1, c2, c3 = self.NN[0], self.NN[2], self.NN[4]
             return training.CouplingConvFn.apply(x, c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias)
-        if self.context_net and training.wants_grad(x, *self.CN.parameters()):
-            if not self.contextflow:
-                raise NotImplementedError('training the conventional (concatenated-context) coupling has no backward kernel yet')
+        if self.context_net and training.wants_grad(x, *self.CN.parameters(), *self.NN.parameters()):
             if max(self._dims) > 320:
                 raise NotImplementedError('CN wider than 320 features has no training kernel yet')
             c, logp_c = training.encode(self, context)
             lin = [self.CN[0], self.CN[2], self.CN[4]]
             cn = training.Mlp3RowsFn.apply(c, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias)
             c1, c2, c3 = self.NN[0], self.NN[2], self.NN[4]
-            return training.CouplingCtxConvFn.apply(x, cn, logp_c, c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias)
+            fn = training.CouplingCtxConvFn if self.contextflow else training.CouplingConcatConvFn     # additive (coupling.py:45) / concatenated (:47)
+            return fn.apply(x, cn, logp_c, c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias)
         inference_only(x)
         D, H, O = self._dims
         Hh, Ww = x.shape[2], x.shape[3]
@@ -175,15 +174,13 @@ class TransCoupling(_CouplingBase):
         vit = self.NN if isinstance(self.NN, SimpleViT) else self.NN[0]
         if not self.context_net and training.wants_grad(x, *vit.parameters()):
             return training.CouplingVitFn.apply(x, None, None, vit, *vit._sources())   # autograd through libcfpp kernels
-        if self.context_net and training.wants_grad(x, *self.CN.parameters()):
-            if not self.contextflow:
-                raise NotImplementedError('training the conventional (concatenated-context) coupling has no backward kernel yet')
+        if self.context_net and training.wants_grad(x, *self.CN.parameters(), *vit.parameters()):
             if max(self._dims) > 320:
                 raise NotImplementedError('CN wider than 320 features has no training kernel yet')
             c, logp_c = training.encode(self, context)
             lin = [self.CN[0], self.CN[2], self.CN[4]]
             cn = training.Mlp3RowsFn.apply(c, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias)
-            return training.CouplingVitFn.apply(x, cn, logp_c, vit, *vit._sources())
+            return training.CouplingVitFn.apply(x, cn, logp_c, vit, *vit._sources())       # additive (--contextflow) or concatenated by the ViT's width
         inference_only(x)
         if not self.context_net:
             return ops.coupling(x, vit(x))
@@ -205,21 +202,37 @@ class TransCoupling(_CouplingBase):
 
 
 class MaskedCoupling(FlowLayer):
-    """`--coupling maf` (reference layers/ar.py:15-69), context-free form: h = MaskedResidualBlock2d(x); t, r = halves of h;
-    z = x * exp(2 tanh(r/2)) + t over all channels; ldj = sum log_s.  With a context_net the reference adds a masked linear block
-    (ar.py:28,41): not built."""
+    """`--coupling maf` (reference layers/ar.py:15-69): h = MaskedResidualBlock2d(x); t, r = halves of h; z = x * exp(2 tanh(r/2)) + t over
+    all channels; ldj = sum log_s.  --contextflow specialist (ar.py:23-28,39-42): NN frozen, h += CN(c) with CN the masked residual linear
+    block (which the reference can only evaluate when the encoder width is 1 or 2 * channels), ldj += H W logp_c.  The conventional
+    specialist is not executable in the reference (its 3D-channel concatenation meets a 2D-channel conv1, ar.py:26,44) and raises here too."""
 
     def __init__(self, data_channels, kernel_size=(1, 1), padding=(0, 0), context_net=None, contextflow=False, mask_type='B'):
         super().__init__()
-        if context_net:
-            raise NotImplementedError('MaskedCoupling with a context_net (MaskedResidualBlockLinear, ar.py:28) is outside the accelerated path')
-        from .autoregressive import MaskedResidualBlock2d
+        from .autoregressive import MaskedResidualBlock2d, MaskedResidualBlockLinear
         D = data_channels
         self.context_net, self.contextflow = context_net, contextflow
         self.NN = MaskedResidualBlock2d(D, D, kernel_size=kernel_size, padding=padding, D=D, mask_type=mask_type)
+        if self.context_net:
+            if not self.contextflow:
+                self.NN = MaskedResidualBlock2d(2 * D, D, kernel_size=kernel_size, padding=padding, D=D, mask_type=mask_type)
+            else:
+                _freeze(self.NN)
+            self.C = self.context_net.C
+            self.CN = MaskedResidualBlockLinear(self.C, D, D)
+            self._plan = ContextPlan()
 
     def forward(self, x, context=None):
         nn_ = self.NN
+        if self.context_net:
+            if not self.contextflow:
+                raise RuntimeError('MaskedCoupling without --contextflow concatenates 2D context channels to the D data channels and feeds a '
+                                   '2D-channel masked conv (ar.py:26,44): the reference raises a channel mismatch here as well')
+            if training.wants_grad(x, *self.CN.parameters()):
+                raise NotImplementedError('training a MaskedCoupling specialist has no backward kernel (only the forward is built)')
+            inference_only(x)
+            c, logp_c = self._plan.run(self.context_net, context)
+            return ops.maf_coupling(x, nn_(x, identity=False), add=self.CN(c), logp_c=logp_c, logp_scale=float(x.shape[2] * x.shape[3]))
         if training.wants_grad(x, *nn_.parameters()):
             for c in (nn_.conv1, nn_.conv2, nn_.conv3):
                 c.masked_weight()                                                                  # mask in place first (masked_conv_2d.py:21-23)

@@ -64,12 +64,12 @@ class GaussianMixtureDistribution(nn.Module):
             return training.GmmFn.apply(input, self.mG, self.sG, self.wG, self)
         if self.context_net and training.wants_grad(input, *self.context_net.parameters()):
             tables = training._lookup_tables(self)                 # specialist prior: embedding tables train
-            if tables is None or not self.contextflow:
+            if tables is None:
                 raise NotImplementedError('training a mixture whose context_net is not the embed + eyesample lookup of create_model '
-                                          '(or without --contextflow) has no backward kernel yet')
+                                          'has no backward kernel yet')
             if isinstance(context, list):
                 context = context[0]
-            return training.GmmCtxFn.apply(input, context, self, 0, *tables)
+            return training.GmmCtxFn.apply(input, context, self, 0, self.mG, self.sG, self.wG, *tables)
         inference_only(self.mG); inference_only(input)
         H, W = input.shape[2], input.shape[3]
         if isinstance(context, list):

@@ -15,11 +15,11 @@ class SplitPrior(FlowLayer):
             return training.SplitPriorFn.apply(x, d.mG, d.sG, d.wG, d)
         if getattr(d, 'context_net', None) and hasattr(d, 'mG') and training.wants_grad(x, *d.context_net.parameters()):
             tables = training._lookup_tables(d)
-            if tables is None or not d.contextflow:
-                raise NotImplementedError('training a split prior whose context_net is not the embed + eyesample lookup (or without '
-                                          '--contextflow) has no backward kernel yet')
+            if tables is None:
+                raise NotImplementedError('training a split prior whose context_net is not the embed + eyesample lookup has no backward '
+                                          'kernel yet')
             ctx2 = context[0] if isinstance(context, list) else context
-            return training.GmmCtxFn.apply(x, ctx2, d, x.shape[1] // 2, *tables)
+            return training.GmmCtxFn.apply(x, ctx2, d, x.shape[1] // 2, d.mG, d.sG, d.wG, *tables)
         half = x.shape[1] // 2
         ldj = self.dist.log_prob(x[:, half:], context)         # read in place through the batch stride, (B, M)
         return ops.slice_channels(x, 0, half), ldj

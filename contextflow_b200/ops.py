@@ -766,14 +766,16 @@ def relu(x):
     return y
 
 
-def maf_coupling(x, h):
-    """MaskedCoupling elementwise part (ar.py:35-57): h (B, 2C, H, W) without the identity."""
-    _need_cuda(x, h); x = _f32(x); h = _f32(h)
+def maf_coupling(x, h, add=None, logp_c=None, logp_scale=0.0):
+    """MaskedCoupling elementwise part (ar.py:35-57): h (B, 2C, H, W) without the identity; add (B, 2C) = CN(c) of a --contextflow
+    specialist, ldj += logp_scale * logp_c."""
+    _need_cuda(x, h, add, logp_c); x = _f32(x); h = _f32(h)
     B, Cc = x.shape[0], x.shape[1]
     HW = x[0, 0].numel() if B else 1
     z = torch.empty_like(x); ldj = torch.empty(B, device=x.device, dtype=x.dtype)
     _set_work(bytes=16.0 * x.numel())
-    _call('maf_coupling_fwd', (_p(x), _p(h), _p(z), _p(ldj), B, Cc, HW, _stream()))
+    _call('maf_coupling_ctx_fwd', (_p(x), _p(h), _p(None if add is None else _f32(add)), _p(None if logp_c is None else _f32(logp_c)), float(logp_scale),
+                                   _p(z), _p(ldj), B, Cc, HW, _stream()))
     return z, ldj
 
 
@@ -1119,3 +1121,76 @@ def vardeq_bwd(u, xcat, qbins, dz, dldj, mode=0):
     _call('vardeq_bwd', (_p(u), _p(None if xcat is None else xcat.contiguous()), _p(None if qbins is None else _f32(qbins)), int(mode),
                          _p(None if dz is None else _f32(dz)), _p(None if dldj is None else _f32(dldj)), _p(du), _p(dqu), B, C_, _stream()))
     return du, dqu
+
+
+# ---------------------------------------------------------------------------------------------- rows beside the headline path
+_ACT_KIND = dict(sigmoid=0, softplus=1)
+
+
+def activation_fwd(x, kind, temperature=None):
+    """Standalone Sigmoid / Softplus flow layer (activations.py:228-264) on (..., D): (z, ldj over the last axis)."""
+    _need_cuda(x, temperature); x = _f32(x)
+    D = x.shape[-1]
+    rows = x.numel() // D if D else 0
+    z = torch.empty_like(x); ldj = torch.empty(x.shape[:-1], device=x.device, dtype=torch.float32)
+    _set_work(bytes=8.0 * x.numel())
+    _call('activation_fwd', (_p(x), _p(z), _p(ldj), _p(temperature), rows, D, _ACT_KIND[kind], _stream()))
+    return z, ldj
+
+
+def activation_inv(z, kind, eps, temperature=None):
+    _need_cuda(z, temperature); z = _f32(z)
+    x = torch.empty_like(z)
+    _set_work(bytes=8.0 * z.numel())
+    _call('activation_inv', (_p(z), _p(x), _p(temperature), z.numel(), float(eps), _ACT_KIND[kind], _stream()))
+    return x
+
+
+def activation_bwd(x, dz, dldj, kind, temperature=None):
+    _need_cuda(x, dz, dldj, temperature); x = _f32(x)
+    D = x.shape[-1]
+    dx = torch.empty_like(x)
+    _call('activation_bwd', (_p(x), _p(None if dz is None else _f32(dz)), _p(None if dldj is None else _f32(dldj)), _p(dx), _p(temperature),
+                             x.numel() // D if D else 0, D, _ACT_KIND[kind], _stream()))
+    return dx
+
+
+def student_table(mG, sG, wG, mS, sS, wS, vS):
+    """Per-element constants of StudentMixtureDistribution (student.py:76-82) for student_logprob; rebuild when parameters change."""
+    _need_cuda(mG, sG, wG, mS, sS, wS, vS)
+    M, K = wG.shape
+    n = mG[0, 0].numel()
+    tab = torch.empty(int(lib().cfpp_student_table_floats(M, K, n)), device=mG.device, dtype=torch.float32)
+    _call('student_prep', (_p(_f32(mG)), _p(_f32(sG)), _p(_f32(wG)), _p(_f32(mS)), _p(_f32(sS)), _p(_f32(wS)), _p(_f32(vS)), _p(tab), M, K, n, _stream()))
+    return tab
+
+
+def student_logprob(x, table, M, K):
+    _need_cuda(x, table); x = _f32(x)
+    B = x.shape[0]
+    n = x[0].numel() if B else 1
+    logp = torch.empty((B, M), device=x.device, dtype=torch.float32)
+    _set_work(flops=12.0 * B * M * K * n)
+    _call('student_logprob', (_p(x), _p(table), _p(logp), B, M, K, n, _stream()))
+    return logp
+
+
+def bias_rows_relu_(a, bias):
+    """a (B, C, H, W) <- relu(a + bias[b, c]) in place (conventional coupling's first convolution, coupling.py:47)."""
+    _need_cuda(a, bias)
+    B, Cc = a.shape[0], a.shape[1]
+    _call('bias_rows_relu', (_p(a), _p(_f32(bias)), B, Cc, a[0, 0].numel() if B else 1, _stream()))
+    return a
+
+
+def gmm_ctx_param_bwd(x, mG, sG, wG, c, resp, g):
+    """Gradients of the mixture's own parameters beside per-sample context offsets (gaussian.py:131-155, contextflow = False)."""
+    _need_cuda(x, mG, c, g); c = _f32(c); g = _f32(g)
+    xv, bstride = _half_view(x)
+    B, D, HW = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+    M, K = resp.shape[1], resp.shape[2]
+    dmG = torch.empty_like(mG, dtype=torch.float32); dsG = torch.empty_like(sG, dtype=torch.float32); dwG = torch.empty_like(wG, dtype=torch.float32)
+    _set_work(flops=24.0 * B * M * K * D * HW)
+    _call('gmm_ctx_param_bwd', (_p(xv), bstride, _p(_f32(mG)), _p(_f32(sG)), _p(_f32(wG)), _p(c), _p(_f32(resp)), _p(g), _p(dmG), _p(dsG), _p(dwG),
+                                B, M, K, D, HW, _stream()))
+    return dmG, dsG, dwG

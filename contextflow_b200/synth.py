@@ -99,19 +99,21 @@ def fill_state(state: dict, seed: str = 'w0') -> dict:
         shape = tuple(v.shape)
         if leaf == 'initialized':
             v.fill_(1)
-        elif leaf in ('qbins', 'ldj_per_dim', 'cardinalities', 'temperature', 'translation', 'scale', 'empty', 'buffer', 'mask'):
+        elif leaf in ('qbins', 'ldj_per_dim', 'cardinalities', 'temperature', 'translation', 'scale', 'empty', 'buffer', 'mask', 'degrees'):
             continue
         elif leaf == 'NN' and v.dim() == 2:                      # invertible 1x1 / FC matrix
             d = shape[0]
             v.copy_(torch.eye(d) + uniform(tag, shape) * (0.25 / np.sqrt(d)))
         elif leaf in ('NN_t', 'NN_logs'):
             v.copy_(uniform(tag, shape) * 0.2)
-        elif leaf == 'mG':
+        elif leaf in ('mG', 'mS'):
             v.copy_(uniform(tag, shape))
-        elif leaf == 'sG':
+        elif leaf in ('sG', 'sS'):
             v.copy_(1.0 + 0.3 * uniform(tag, shape))
-        elif leaf == 'wG':
+        elif leaf in ('wG', 'wS'):
             v.copy_(uniform(tag, shape))
+        elif leaf == 'vS':                                       # Student-t degrees of freedom (pre-softplus): keeps the linspace(1, 10) initialisation
+            continue
         elif '_embeddings.' in key:
             v.copy_(uniform(tag, shape) * 0.1)
         elif leaf == 'weight' and v.dim() == 1:                  # LayerNorm gain (the ViT's output norm is kept small)

@@ -236,14 +236,21 @@ class CouplingVitFn(Function):
 
     @staticmethod
     def forward(ctx, x, add, logp_c, vit, *params):
-        # add (B, C) / logp_c (B): the additive context term CN(c) and the encoder's log-density of a --contextflow specialist
-        # (coupling.py:126-133; note logp_c is NOT scaled by H*W in TransCoupling); None for a generalist
+        # add (B, C) / logp_c (B): the context term CN(c) and the encoder's log-density of a specialist (coupling.py:126-133; note logp_c
+        # is NOT scaled by H*W in TransCoupling); None for a generalist.  --contextflow adds CN(c) to h; a conventional specialist
+        # (vit.geom['Cin'] = C/2 + C input channels) concatenates CN(c), broadcast over the pixels, to x0 (coupling.py:129).
         g = vit.geom
         c, p1, p2, T, n, depth = g['Cin'], g['p1'], g['p2'], g['T'], g['n_tok'], g['depth']
         B, C, H, W = x.shape
         P = [p.detach() for p in params]
         ln0w, ln0b, pew, peb, ln1w, ln1b, lnfw, lnfb = P[:8]
-        tok = ops.patchify(x, c, p1, p2)
+        concat = add is not None and c > C // 2
+        if concat:
+            xin = torch.cat([x.detach()[:, :C // 2], add.detach()[:, :, None, None].expand(B, add.shape[1], H, W)], dim=1).contiguous()
+            tok = ops.patchify(xin, c, p1, p2)
+            add = None
+        else:
+            tok = ops.patchify(x, c, p1, p2)
         y0, m0, r0 = ops.layernorm_fwd(tok, ln0w, ln0b)
         e = ops.rows_linear(y0, pew, peb)
         X, m1, r1 = ops.layernorm_fwd(e, ln1w, ln1b)
@@ -270,7 +277,7 @@ class CouplingVitFn(Function):
         z, ldj = ops.coupling(x, h, add=add, logp_c=logp_c, logp_scale=1.0)
         saved += [X, mz, rz, x, h]
         ctx.save_for_backward(*saved, *params)
-        ctx.add = add
+        ctx.add, ctx.concat = add, concat
         ctx.meta = (c, p1, p2, T, n, depth, B, H, W, cc, len(saved))
         return z, ldj
 
@@ -311,7 +318,13 @@ class CouplingVitFn(Function):
         de, grads[4], grads[5] = ops.layernorm_bwd(e, dX, ln1w, m1, r1)
         grads[2], grads[3] = wgrad(2, y0, de)
         dtok, grads[0], grads[1] = ops.layernorm_bwd(tok, ops.rows_linear_bwd_data(de, pew), ln0w, m0, r0)
-        ops.patchify_inv(dtok, c, H, W, p1, p2, out=dx, accumulate=True)          # dx[:, :c] += the conditioner's input gradient
+        if ctx.concat:                                                             # input gradient of cat(x0, CN(c)): x0 part onto dx, the rest summed over pixels
+            Ch = x.shape[1] // 2
+            dxin = ops.patchify_inv(dtok, c, H, W, p1, p2)
+            ops.place_channels(ops.add(ops.slice_channels(dx, 0, Ch), ops.slice_channels(dxin, 0, Ch)), dx, 0)
+            dadd = ops.rowsum(ops.slice_channels(dxin, Ch, c - Ch).view(B * (c - Ch), -1)).view(B, c - Ch)
+        else:
+            ops.patchify_inv(dtok, c, H, W, p1, p2, out=dx, accumulate=True)      # dx[:, :c] += the conditioner's input gradient
         grads = [gr if ng[4 + i] else None for i, gr in enumerate(grads)]          # frozen ViT parameters (--contextflow) take none
         dlogp = dldj if (ng[2] and dldj is not None) else None                                      # TransCoupling: logp_c unscaled (coupling.py:126)
         return (dx if ng[0] else None, dadd, dlogp, None, *grads)
@@ -458,6 +471,48 @@ class CouplingCtxConvFn(Function):
         return (dx if ng[0] else None), dadd, dlogp, dw1, db1, dw2, db2, dw3, db3
 
 
+class CouplingConcatConvFn(Function):
+    """Coupling with the conv conditioner over the CONCATENATED context of a conventional specialist (coupling.py:47):
+    h = NN(cat(x0, CN(c) broadcast)).  The first convolution is 1x1, so it equals W1[:, :D] x0 plus the per-sample bias
+    b1 + W1[:, D:] CN(c); every weight trains (contextflow = False).  `cn` = CN(c) (B, O)."""
+
+    @staticmethod
+    def forward(ctx, x, cn, logp_c, w1, b1, w2, b2, w3, b3):
+        Ch = x.shape[1] // 2
+        HW = x.shape[2] * x.shape[3]
+        w1d = w1.detach().reshape(w1.shape[0], -1)
+        w1a, w1b = w1d[:, :Ch].contiguous(), w1d[:, Ch:].contiguous()
+        bias1 = ops.rows_linear(cn.detach(), w1b, b1.detach())                                   # (B, H): b1 + W1[:, D:] CN(c)
+        a1 = ops.bias_rows_relu_(ops.conv2d_fwd(x, Ch, w1a.view(-1, Ch, 1, 1), None, relu=False), bias1)
+        a2 = ops.conv2d_fwd(a1, a1.shape[1], w2.detach(), b2.detach(), relu=True)
+        h = ops.conv2d_fwd(a2, a2.shape[1], w3.detach(), b3.detach(), relu=False)
+        z, ldj = ops.coupling(x, h, logp_c=logp_c, logp_scale=float(HW))
+        ctx.save_for_backward(x, cn, a1, a2, h, w1a, w1b, w2, w3)
+        ctx.w1_shape = tuple(w1.shape)
+        return z, ldj
+
+    @staticmethod
+    def backward(ctx, dz, dldj):
+        x, cn, a1, a2, h, w1a, w1b, w2, w3 = ctx.saved_tensors
+        B, C = x.shape[0], x.shape[1]
+        Ch, Hd = C // 2, a1.shape[1]
+        dz = _zeros_like_if_none(dz, x.shape, x.device).contiguous()
+        dx, dh = ops.coupling_bwd(x, h, dz, None if dldj is None else dldj.contiguous())
+        dw3, db3 = ops.conv2d_bwd_weight(a2, a2.shape[1], dh, w3.shape)
+        da2 = ops.conv2d_bwd_data(dh, w3.detach(), act=a2)
+        dw2, db2 = ops.conv2d_bwd_weight(a1, a1.shape[1], da2, w2.shape)
+        da1 = ops.conv2d_bwd_data(da2, w2.detach(), act=a1)
+        dw1a, _ = ops.conv2d_bwd_weight(x, Ch, da1, (Hd, Ch, 1, 1), bias=False)
+        dbias = ops.rowsum(da1.view(B * Hd, -1)).view(B, Hd)                                    # gradient of the per-sample bias
+        dw1b, db1 = ops.rows_linear_bwd_weight(cn, dbias)                                       # W1[:, D:] and b1
+        dcn = ops.rows_linear_bwd_data(dbias, w1b) if ctx.needs_input_grad[1] else None
+        dw1 = torch.cat([dw1a.view(Hd, Ch), dw1b], dim=1).view(ctx.w1_shape)
+        ops.conv2d_bwd_data(da1, w1a.view(Hd, Ch, 1, 1), out=dx, accumulate=True)                # dx[:, :Ch] += W1[:, :D]^T da1
+        HW = x.shape[2] * x.shape[3]
+        dlogp = dldj * float(HW) if (ctx.needs_input_grad[2] and dldj is not None) else None      # ldj += HW * logp_c (coupling.py:43)
+        return (dx if ctx.needs_input_grad[0] else None), dcn, dlogp, dw1, db1, dw2, db2, dw3, db3
+
+
 def _lookup_tables(dist):
     """The embedding tables of a mixture's context_net when it is the embed + eyesample lookup create_model gives every prior
     (model.py:157,162); None otherwise."""
@@ -469,16 +524,17 @@ def _lookup_tables(dist):
 
 
 class GmmCtxFn(Function):
-    """GaussianMixtureDistribution.log_prob with context offsets from an embedding lookup (gaussian.py:146-155), --contextflow: mG, sG,
-    wG frozen, the tables train.  `split` > 0: the SplitPrior form -- x is the full tensor, the mixture scores x[:, split:] and the
-    Function also returns x[:, :split] (splitprior.py:12-15)."""
+    """GaussianMixtureDistribution.log_prob with context offsets from an embedding lookup (gaussian.py:146-155).  The tables always
+    train; mG, sG, wG are frozen under --contextflow and train beside the tables in a conventional specialist (gaussian.py:137-141).
+    `split` > 0: the SplitPrior form -- x is the full tensor, the mixture scores x[:, split:] and the Function also returns
+    x[:, :split] (splitprior.py:12-15)."""
 
     @staticmethod
-    def forward(ctx, x, context, dist, split, *tables):
+    def forward(ctx, x, context, dist, split, mG, sG, wG, *tables):
         c = ops.embed_lookup(context, [t.detach() for t in tables])
         xs = x[:, split:] if split else x
-        logp, resp = ops.gmm_ctx_train_fwd(xs, dist.mG.detach(), dist.sG.detach(), dist.wG.detach(), c)
-        ctx.save_for_backward(x, context, c, resp, *tables)
+        logp, resp = ops.gmm_ctx_train_fwd(xs, mG.detach(), sG.detach(), wG.detach(), c)
+        ctx.save_for_backward(x, context, c, resp, mG, sG, wG, *tables)
         ctx.dist, ctx.split = dist, split
         if split:
             return ops.slice_channels(x, 0, split), logp
@@ -486,9 +542,10 @@ class GmmCtxFn(Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        x, context, c, resp = ctx.saved_tensors[:4]
-        tables = ctx.saved_tensors[4:]
+        x, context, c, resp, mG, sG, wG = ctx.saved_tensors[:7]
+        tables = ctx.saved_tensors[7:]
         dist, split = ctx.dist, ctx.split
+        mG, sG, wG = mG.detach(), sG.detach(), wG.detach()
         dx0, g = (grads if split else (None, grads[0]))
         g = torch.zeros((x.shape[0], dist.M), device=x.device) if g is None else g.contiguous()
         need_dx = ctx.needs_input_grad[0]
@@ -496,12 +553,14 @@ class GmmCtxFn(Function):
             dx = torch.empty_like(x) if need_dx else None
             if need_dx:
                 ops.place_channels(_zeros_like_if_none(dx0, (x.shape[0], split) + tuple(x.shape[2:]), x.device).contiguous(), dx, 0)
-            _, dc = ops.gmm_ctx_train_bwd(x[:, split:], dist.mG.detach(), dist.sG.detach(), c, resp, g, need_dx=need_dx,
-                                          dx_out=dx[:, split:] if need_dx else None)
+            _, dc = ops.gmm_ctx_train_bwd(x[:, split:], mG, sG, c, resp, g, need_dx=need_dx, dx_out=dx[:, split:] if need_dx else None)
         else:
-            dx, dc = ops.gmm_ctx_train_bwd(x, dist.mG.detach(), dist.sG.detach(), c, resp, g, need_dx=need_dx)
+            dx, dc = ops.gmm_ctx_train_bwd(x, mG, sG, c, resp, g, need_dx=need_dx)
         dtables = ops.embed_scatter(dc, context, tables)
-        return (dx, None, None, None, *dtables)
+        dmG = dsG = dwG = None
+        if any(ctx.needs_input_grad[4:7]):                       # conventional specialist: the mixture itself trains too
+            dmG, dsG, dwG = ops.gmm_ctx_param_bwd(x[:, split:] if split else x, mG, sG, wG, c, resp, g)
+        return (dx, None, None, None, dmG, dsG, dwG, *dtables)
 
 
 # ---------------------------------------------------------------------------------------------- encoders with trainable parameters

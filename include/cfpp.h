@@ -315,6 +315,10 @@ int cfpp_cn_batch(const cfpp_cn_job* jobs, int n_jobs, const float* const* in, f
 /* y = max(x, 0): the pre-activation of MaskedResidualBlock2d (masked_conv_2d.py:94) in front of cfpp_conv_cond_tc_fwd. */
 int cfpp_relu_fwd(const float* x, float* y, int64_t n, void* stream);
 int cfpp_maf_coupling_fwd(const float* x, const float* h, float* z, float* ldj, int B, int C, int HW, void* stream);
+/* the same for a --contextflow specialist (ar.py:39-42): h += add[b] ((B, 2C), broadcast over the pixels; may be NULL),
+ * ldj[b] += logp_scale * logp_c[b] (logp_c may be NULL) */
+int cfpp_maf_coupling_ctx_fwd(const float* x, const float* h, const float* add, const float* logp_c, float logp_scale,
+                              float* z, float* ldj, int B, int C, int HW, void* stream);
 
 /* Its backward: dh (B, 2C, HW) = cat(dz, dr), dr = (dz x s + dldj[b]) (1 - tanh^2(r/2)); dx = dz s + dz + dr (the identity feeds both halves);
  * the masked block's own input gradient is then accumulated onto dx by cfpp_conv2d_bwd_data(act = x, accumulate = 1). */
@@ -470,6 +474,31 @@ int cfpp_add_pos(float* x, const float* pos, int64_t R, int n_tok, int F, void* 
  * P (B, n, n) = softmax(q k^T / 8) is saved; O = P v.  bwd: dqkv from dO. */
 int cfpp_attention_fwd(const float* qkv, float* O, float* P, int B, int n_tok, void* stream);
 int cfpp_attention_bwd(const float* qkv, const float* P, const float* dO, float* dqkv, int B, int n_tok, void* stream);
+
+/* ---- rows beside the headline path ------------------------------------------------------------------- */
+/* Standalone invertible activations on rows of D values (reference layers/activations.py:228-264).  kind 0 = Sigmoid(temperature):
+ * z = sigmoid(T x), ldj[row] = sum_i log T - softplus(-T x_i) - softplus(T x_i); kind 1 = Softplus: z = softplus(x), ldj[row] = sum_i
+ * logsigmoid(x_i).  inv: Sigmoid clamps z to [eps, 1 - eps] (the [0,1] assertion of :241 is the caller's), x = (log z - log1p(-z)) / T;
+ * Softplus x = z + log1p(-exp(-max(z, eps))).  bwd: dx from dz (may be NULL) and dldj (rows; may be NULL).  temperature: device scalar. */
+int cfpp_activation_fwd(const float* x, float* z, float* ldj, const float* temperature, int64_t rows, int D, int kind, void* stream);
+int cfpp_activation_inv(const float* z, float* x, const float* temperature, int64_t n, float eps, int kind, void* stream);
+int cfpp_activation_bwd(const float* x, const float* dz, const float* dldj, float* dx, const float* temperature, int64_t rows, int D,
+                        int kind, void* stream);
+/* StudentMixtureDistribution.log_prob (layers/distributions/student.py:44-111): logp (B, M) = Gaussian-mixture log-density + Student-t
+ * mixture log-density of x (B, n = D*H*W) under parameters (M, K, n) / weights (M, K) (softmax over dim 0, renormalised along K by
+ * Categorical).  prep fills `table` (cfpp_student_table_floats floats) from the parameters; redo it when they change. */
+int64_t cfpp_student_table_floats(int M, int K, int n);
+int cfpp_student_prep(const float* mG, const float* sG, const float* wG, const float* mS, const float* sS, const float* wS,
+                      const float* vS, float* table, int M, int K, int n, void* stream);
+int cfpp_student_logprob(const float* x, const float* table, float* logp, int B, int M, int K, int n, void* stream);
+/* Training of the conventional (concatenated-context, contextflow = False) specialists.
+ * bias_rows_relu: a (B, C, HW) <- relu(a + bias[b, c]) in place: conv1 of coupling.py:47 = W1[:, :D] x0 + (b1 + W1[:, D:] CN(c)).
+ * gmm_ctx_param_bwd: gradients of the mixture's own mG, sG (M, K, D, HW) and wG (M, K) when they train beside the context offsets c
+ * (B, 2*M*K*D) (distributions/gaussian.py:131-155); resp (B, M, K) from cfpp_gmm_ctx_train_fwd, g (B, M) = dL/dlogp. */
+int cfpp_bias_rows_relu(float* a, const float* bias, int B, int C, int HW, void* stream);
+int cfpp_gmm_ctx_param_bwd(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* wG, const float* c,
+                           const float* resp, const float* g, float* dmG, float* dsG, float* dwG, int B, int M, int K, int D, int HW,
+                           void* stream);
 
 /* ---- container ------------------------------------------------------------------------------------------------ */
 /* FlowSequential.forward, layers/flowsequential.py:23: logdet (B,M) += ldj (B,cols) with cols = 1 (broadcast) or M. */

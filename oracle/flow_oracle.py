@@ -104,9 +104,9 @@ def build_stack(cfg: dict, data_size, mixtures: int, contexts) -> dict:
             elif cfg['coupling'] == 'conv':
                 L.append(dict(op='coupling', C=sz[0], krn=krn, pad=pad, enc=enc(sz[0]), contextflow=cf))
             elif cfg['coupling'] == 'maf':                                   # model.py:145-147
-                if special:
-                    raise NotImplementedError('MaskedCoupling with a context_net is outside the restated path')
-                L.append(dict(op='maf', C=sz[0], krn=krn, pad=pad, enc=None, contextflow=cf))
+                if special and not cf:                                       # ar.py:26,44: the 3D-channel concatenation meets a 2D-channel conv1
+                    raise RuntimeError('the reference cannot execute a conventional MaskedCoupling specialist (ar.py:26,44)')
+                L.append(dict(op='maf', C=sz[0], krn=krn, pad=pad, enc=enc(sz[0]), contextflow=cf))
             if cfg['dataset'] == 'atm':                                      # model.py:149-151
                 L.append(dict(op='permute')); sz = (sz[1], sz[0], sz[2])
         if cfg['split_prior'] and l < cfg['num_blocks'] - 1:                 # model.py:153-158
@@ -411,9 +411,29 @@ def maf_mask(out_c, in_c, kh, kw, data_channels):
     return m
 
 
-def masked_coupling(P, lay, x):
+def made_degrees(in_degrees, out_features, data_features):
+    """MaskedLinear.get_mask_and_degrees, hidden-layer form (masked_linear.py:77-79): mask (out, in), out degrees."""
+    max_, min_ = max(1, data_features - 1), min(1, data_features - 1)
+    out_degrees = torch.arange(out_features) % max_ + min_
+    return (out_degrees[..., None] >= in_degrees).float(), out_degrees
+
+
+def masked_residual_linear(P, prefix, c, D):
+    """MaskedResidualBlockLinear(C, D, D).forward (masked_linear.py:104-128): three pre-activation masked linear layers (none of them
+    built with is_output=True, so all use the hidden-layer mask over get_data_degrees = 1..n) plus the identity c, which broadcasts
+    only when C == 2 D or C == 1."""
+    h = c
+    for name in ('linear1', 'linear2', 'linear3'):
+        w = P(f'{prefix}.{name}.weight')
+        mask, _ = made_degrees(torch.arange(1, w.shape[1] + 1), w.shape[0], D)
+        h = F.linear(torch.relu(h), w * mask.to(w), P(f'{prefix}.{name}.bias'))
+    return h + c
+
+
+def masked_coupling(P, lay, x, state=None, ctx=None, noise=None, dt=torch.float32):
     """MaskedCoupling.forward (ar.py:35-57) over MaskedResidualBlock2d (masked_conv_2d.py:81-98): pre-activation convs with
-    mask-multiplied weights (:21-23), identity on both halves; z = x * s + t on all channels."""
+    mask-multiplied weights (:21-23), identity on both halves; z = x * s + t on all channels.  --contextflow specialist (ar.py:39-42):
+    h += CN(c) with CN the masked residual linear block, ldj += H W logp_c."""
     k, D = lay['key'], lay['C']
     pad = lay['pad']
     h = x
@@ -427,9 +447,14 @@ def masked_coupling(P, lay, x):
             h = F.pad(h, (pad[1], pad[1], pad[0], pad[0]), mode='reflect')
         h = F.conv2d(h, w, P(f'{k}.NN.{name}.bias'))
     h = h + x.repeat(1, 2, 1, 1)
+    logp_c = 0.0
+    if lay.get('enc') is not None:
+        c, logp_c = context_encode(P, state, f'{k}.context_net', lay['enc'], ctx, noise, dt)
+        logp_c = logp_c * x.shape[2] * x.shape[3]                           # ar.py:39
+        h = h + masked_residual_linear(P, f'{k}.CN', c, D)[:, :, None, None]
     t, r = h[:, :D], h[:, D:]
     log_s = 2.0 * torch.tanh(r / 2.0)
-    return x * torch.exp(log_s) + t, log_s.flatten(1).sum(-1)
+    return x * torch.exp(log_s) + t, log_s.flatten(1).sum(-1) + logp_c
 
 
 def gmm_log_prob(P, state, lay, x, ctx, noise, dt):
@@ -502,7 +527,7 @@ def forward(stack: dict, state: Dict[str, torch.Tensor], x: torch.Tensor, ctx: O
         elif op == 'transcoupling':
             x, ldj = coupling(P, state, lay, x, ctx, noise, dt, trans=True)
         elif op == 'maf':
-            x, ldj = masked_coupling(P, lay, x)
+            x, ldj = masked_coupling(P, lay, x, state, ctx, noise, dt)
         elif op == 'splitprior':                                             # splitprior.py:12-15
             Ch = x.shape[1] // 2
             ldj = gmm_log_prob(P, state, dict(lay, key=f"{lay['key']}.dist"), x[:, Ch:], ctx, noise, dt)
@@ -675,3 +700,46 @@ def sliding_windows(ts: np.ndarray, window_size: int, stride: int = 1) -> torch.
     idx = np.maximum(ends[:, None] - window_size + 1 + np.arange(window_size)[None, :], 0)     # replication padding with row 0
     w = np.asarray(ts, dtype=float)[idx]                                                        # (N, L, D) float64
     return torch.tensor(np.transpose(w, (0, 2, 1)), dtype=torch.float).unsqueeze(-1)            # N x D x L x 1
+
+
+# ---------------------------------------------------------------------------------------------- rows beside the headline path
+def sigmoid_layer(x, temperature=1.0):
+    """Standalone Sigmoid flow layer, activations.py:234-238: z = sigmoid(T x), ldj = sum_last(log T - softplus(-T x) - softplus(T x))."""
+    t = torch.as_tensor(temperature, dtype=x.dtype)
+    tx = t * x
+    return torch.sigmoid(tx), (torch.log(t) - softplus(-tx) - softplus(tx)).sum(-1)
+
+
+def sigmoid_layer_reverse(z, temperature=1.0, eps=0.0):
+    """activations.py:240-244."""
+    zc = torch.clamp(z, eps, 1 - eps)
+    return (1.0 / temperature) * (torch.log(zc) - torch.log1p(-zc))
+
+
+def softplus_layer(x):
+    """Standalone Softplus flow layer, activations.py:252-259: z = softplus(x), ldj = sum_last logsigmoid(x)."""
+    return softplus(x), (torch.clamp(x, max=0) - torch.log1p(torch.exp(-x.abs()))).sum(-1)
+
+
+def softplus_layer_reverse(z, eps=1e-7):
+    """activations.py:261-264: x = z + log(1 - exp(-max(z, eps)))."""
+    return z + torch.log1p(-torch.exp(-z.clamp(eps)))
+
+
+def student_mixture_log_prob(P, x):
+    """StudentMixtureDistribution.log_prob, distributions/student.py:76-98, written out: for both families the mixture weights are
+    softmax over dim 0 of w (M, K), renormalised along K by Categorical(probs); component log-densities are summed over (D, H, W);
+    log_prob (B, M) = logsumexp_k(Gaussian) + logsumexp_k(Student-t).  StudentT.log_prob as torch.distributions writes it."""
+    M, K = P['wG'].shape
+    xb = x[:, None, None]                                               # (B, 1, 1, D, H, W) against (M, K, D, H, W)
+
+    def logw(w):
+        p = torch.softmax(w, dim=0)
+        return torch.log(p / p.sum(-1, keepdim=True))
+    sg = softplus(P['sG'])
+    lg = (-0.5 * ((xb - P['mG']) / sg) ** 2 - torch.log(sg) - 0.5 * math.log(2 * math.pi)).sum((-1, -2, -3))
+    ss, df = softplus(P['sS']), softplus(P['vS'])
+    y = (xb - P['mS']) / ss
+    Z = torch.log(ss) + 0.5 * torch.log(df) + 0.5 * math.log(math.pi) + torch.lgamma(0.5 * df) - torch.lgamma(0.5 * (df + 1.0))
+    ls = (-0.5 * (df + 1.0) * torch.log1p(y ** 2 / df) - Z).sum((-1, -2, -3))
+    return torch.logsumexp(lg + logw(P['wG']), -1) + torch.logsumexp(ls + logw(P['wS']), -1)

@@ -40,6 +40,12 @@ CASES = {
     'mnist_maf': dict(conf=variant('cfg1', coupling='maf', num_blocks=2, block_size=1), B=3),
     'msl_maf': dict(conf=variant('cfg4', dataset='msl', coupling='maf', data_size=(55, 8, 1), contexts=[27], mixtures=2,
                                  num_blocks=1, block_size=2), B=4),
+    # --coupling maf --contextflow specialists: CN = MaskedResidualBlockLinear (ar.py:28, masked_linear.py:104-128), executable in the
+    # reference only when the encoder width is 1 (eye over two classes) or 2 x channels (onehot over 16 classes at 8 channels)
+    'mnist_maf_eye2': dict(conf=variant('cfg1', coupling='maf', generalist=False, contextflow=True, enc_emb='eye', enc_type='uniform',
+                                        num_blocks=1, block_size=2, contexts=[2]), B=4),
+    'mnist_maf_onehot16': dict(conf=variant('cfg1', coupling='maf', generalist=False, contextflow=True, enc_emb='onehot', enc_type='uniform',
+                                            num_blocks=1, block_size=1, contexts=[16]), B=5),
     # ATM-shaped generalist with the ViT conditioner and PermuteAxes (training-direction case for TransCoupling)
     'atm_gen': dict(conf=variant('cfg3', generalist=True, contextflow=False, num_blocks=1, block_size=2, contexts=[9], data_size=(6, 16, 1)), B=4),
     # --contextflow specialists with the reference's DEFAULT encoder (--enc-emb onehot --enc-type uniform, config.py:18-19): the
@@ -89,6 +95,9 @@ TRAINING_CASES = {
     'mnist_eye_vardeq2': dict(alpha=1e-2, criterion=True, weight=None),
     'mnist_embed_probsample': dict(alpha=1e-2, criterion=True, weight=None),
     'mnist_embed_eyesample': dict(alpha=1e-2, criterion=True, weight=None),
+    # conventional (concatenated-context, contextflow=False) specialists: every layer trains, the context enters by concatenation
+    'cifar_conventional': dict(alpha=1e-3, criterion=True, weight=None),
+    'smap_conventional': dict(alpha=1e2, criterion=False, weight=None),
     # --coupling maf generalists (masked residual conv blocks)
     'mnist_maf': dict(alpha=1e-2, criterion=True, weight=None),
     'msl_maf': dict(alpha=1e-2, criterion=True, weight=[0.4, 1.6]),

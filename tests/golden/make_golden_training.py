@@ -95,5 +95,7 @@ def run(M_, name, spec):
 
 if __name__ == '__main__':
     M_ = import_reference()
+    only = set(sys.argv[1:])                       # optional: case names to (re)generate
     for n, spec in TRAINING_CASES.items():
-        run(M_, n, spec)
+        if not only or n in only:
+            run(M_, n, spec)

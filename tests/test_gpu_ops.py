@@ -265,3 +265,75 @@ def test_ldj_sum_is_the_ordered_chain():
         want += t.unsqueeze(-1)
     assert torch.equal(ops.ldj_sum([t.to(dev) for t in many], B, M, dev).cpu(), want)
     assert torch.equal(ops.ldj_sum([], B, M, dev).cpu(), torch.zeros(B, M))
+
+
+# ---- rows beside the headline path: standalone activations, Student-t mixture -------------------------------------------------------
+def _extras():
+    import os
+    import numpy as np
+    from tests.helpers import GOLD
+    return dict(np.load(os.path.join(GOLD, 'extras.npz'), allow_pickle=False))
+
+
+def test_activation_layers_match_reference_fixture():
+    g = _extras()
+    x = torch.from_numpy(g['act_x']).to(dev)
+    for T in (1.0, 2.5):
+        lay = L.Sigmoid(temperature=T, eps=1e-6).to(dev)
+        z, ldj = lay(x)
+        assert_close(z.cpu().numpy(), g[f'sig_z_{T}'], 1e-6, 1e-6, f'sigmoid z T={T}')
+        assert_close(ldj.cpu().numpy(), g[f'sig_ldj_{T}'], 1e-5, 1e-4, f'sigmoid ldj T={T}')
+        # the reverse is ill-conditioned where z rounds to 1 (x = 25): compare where the reference's own z is away from the clamp
+        rev, ref = lay.reverse(z).cpu(), torch.from_numpy(g[f'sig_rev_{T}'])
+        ok = (torch.from_numpy(g[f'sig_z_{T}']) < 1 - 1e-4) & (torch.from_numpy(g[f'sig_z_{T}']) > 1e-4)
+        assert_close(rev[ok].numpy(), ref[ok].numpy(), 2e-3, 2e-3, f'sigmoid reverse T={T}')
+    lay = L.Softplus()
+    z, ldj = lay(x)
+    assert_close(z.cpu().numpy(), g['sp_z'], 1e-6, 1e-6, 'softplus z')
+    assert_close(ldj.cpu().numpy(), g['sp_ldj'], 1e-5, 1e-4, 'softplus ldj')
+    zr = torch.from_numpy(g['sp_z'])
+    ok = zr > 1e-3
+    assert_close(lay.reverse(z).cpu()[ok].numpy(), torch.from_numpy(g['sp_rev'])[ok].numpy(), 1e-4, 1e-4, 'softplus reverse')
+    # gradients of sum(z * a) + sum(ldj * b) through the backward kernels
+    a, b = torch.from_numpy(g['act_a']).to(dev), torch.from_numpy(g['act_b']).to(dev)
+    for lay, key in ((L.Sigmoid(temperature=2.5).to(dev), 'sig_dx_2.5'), (L.Softplus(), 'sp_dx')):
+        xg = x.clone().requires_grad_(True)
+        z, ldj = lay(xg)
+        ((z * a).sum() + (ldj * b).sum()).backward()
+        assert_close(xg.grad.cpu().numpy(), g[key], 1e-5, 1e-5, key)
+
+
+@pytest.mark.parametrize('shape', [(3, 1), (1025, 33), (4, 5, 64)])
+def test_activation_layers_match_oracle(shape):
+    x = synth.uniform('actx', shape) * 12.0
+    for T in (1.0, 0.7):
+        z, ldj = L.Sigmoid(temperature=T).to(dev)(x.to(dev))
+        zo, lo = O.sigmoid_layer(x, T)
+        assert_close(z.cpu().numpy(), zo.numpy(), 1e-6, 1e-6, 'sigmoid z'); assert_close(ldj.cpu().numpy(), lo.numpy(), 1e-5, 1e-4, 'sigmoid ldj')
+    z, ldj = L.Softplus()(x.to(dev))
+    zo, lo = O.softplus_layer(x)
+    assert_close(z.cpu().numpy(), zo.numpy(), 1e-6, 1e-6, 'softplus z'); assert_close(ldj.cpu().numpy(), lo.numpy(), 1e-5, 1e-4, 'softplus ldj')
+    ok = zo > 1e-2                                         # log(1 - exp(-z)) amplifies one ulp of exp(-z) by 1 / z: compare on the same z, away from 0
+    assert_close(L.Softplus().reverse(zo.to(dev)).cpu()[ok].numpy(), O.softplus_layer_reverse(zo)[ok].numpy(), 1e-4, 1e-4, 'softplus reverse')
+
+
+def test_student_mixture_matches_reference_fixture():
+    from tests.golden.make_golden_extras import STUDENT
+    g = _extras()
+    dist = L.StudentMixtureDistribution(STUDENT['size'], mixtures=STUDENT['mixtures'])
+    sd = dist.state_dict(); synth.fill_state(sd, 'student'); dist.load_state_dict(sd)
+    dist = dist.to(dev)
+    with torch.no_grad():
+        logp = dist.log_prob(torch.from_numpy(g['stu_x']).to(dev))
+    assert_close(logp.cpu().numpy(), g['stu_logp64'].astype('float32'), 1e-5, 1e-3, 'student log_prob vs the float64 reference')
+
+
+@pytest.mark.parametrize('B,M,size', [(9, 2, (8, 16, 16)), (300, 10, (4, 3, 2)), (1, 1, (1, 1, 1))])
+def test_student_mixture_matches_oracle(B, M, size):
+    dist = L.StudentMixtureDistribution(size, mixtures=M)
+    sd = dist.state_dict(); synth.fill_state(sd, f'stu{B}'); dist.load_state_dict(sd)
+    x = synth.uniform('stux', (B,) + tuple(size)) * 2.0
+    ref = O.student_mixture_log_prob({k: v.double() for k, v in dist.state_dict().items() if k in ('mG', 'sG', 'wG', 'mS', 'sS', 'wS', 'vS')}, x.double())
+    with torch.no_grad():
+        logp = dist.to(dev).log_prob(x.to(dev))
+    assert_close(logp.cpu().numpy(), ref.float().numpy(), 2e-5, 1e-3, 'student log_prob')

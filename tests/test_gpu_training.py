@@ -346,8 +346,8 @@ def test_context_mixture_backward_large_sample_fallback():
 
 
 def test_unsupported_layers_raise_under_autograd():
-    model = build_cuda_model(CASES['cifar_conventional']).train()     # conventional (concatenated-context) specialists: no backward kernels yet
-    x, ctx = case_inputs(CASES['cifar_conventional'])
+    model = build_cuda_model(CASES['mnist_maf_onehot16']).train()     # --coupling maf specialists: the masked linear context block has no backward kernel
+    x, ctx = case_inputs(CASES['mnist_maf_onehot16'])
     with pytest.raises(NotImplementedError):
         model.log_prob(x.cuda(), ctx.cuda())
 

@@ -28,6 +28,15 @@ def test_fused_plan_segments_cfg2():
     flat = [m for s in segs for m in s.mods]
     assert all(a is b for a, b in zip(flat, model.sequence_modules))
     # context pre-pass: one CN job per contextual Conv1x1 / ActNorm / Coupling, the Conv1x1 ones flagged lower-triangular
+    # (the Conv1x1 ones are absent when the persistent Conv1x1 + context-network kernel has a plan for the level: its CN runs in-kernel)
+    jobs = [j for s in segs if isinstance(s, (_ConvAct, _Coup)) for j in s.cn_jobs()]
+    assert len(jobs) == 24
+    assert sorted({tril for _, _, tril, _, _ in jobs}) == [0]
+
+
+def test_fused_plan_segments_cfg2_two_kernel_conv1x1(monkeypatch):
+    monkeypatch.setenv('CFPP_C1X1_CTX', '0')                                        # the two-kernel route: CN pre-pass + per-sample-matrix kernel
+    _, segs = _segments('cfg2')
     jobs = [j for s in segs if isinstance(s, (_ConvAct, _Coup)) for j in s.cn_jobs()]
     assert len(jobs) == 36
     assert sorted({tril for _, _, tril, _, _ in jobs}) == [0, 16, 32, 64]
