@@ -42,6 +42,7 @@ _SIGNATURES = {
     'cfpp_version': (i32, []),
     'cfpp_last_error': (C.c_char_p, []),
     'cfpp_launch_count': (i64, []),
+    'cfpp_copy_peer_async': (i32, [vp, i32, vp, i32, i64, vp]),
     'cfpp_maf_coupling_ctx_fwd': (i32, [vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, vp]),
     'cfpp_activation_fwd': (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
     'cfpp_activation_inv': (i32, [vp, vp, vp, i64, f32, i32, vp]),

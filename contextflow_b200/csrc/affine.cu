@@ -322,8 +322,8 @@ int cfpp_conv1x1_rt_launch(const float* x, float* z, float* ldj, const float* NN
 
 extern "C" int cfpp_slogdet(const float* A, int D, float* logabsdet, void* stream) {
   CFPP_REQUIRE(D >= 1 && D <= 128, "slogdet: D=%d outside [1,128]", D);
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(slogdet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8); attr_set = true; }
+  static DeviceOnce attr_set;
+  if (attr_set.first()) { cudaFuncSetAttribute(slogdet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8); }
   slogdet_kernel<<<1, 128, (size_t)D * D * sizeof(double), (cudaStream_t)stream>>>(A, D, logabsdet);
   return check_launch("slogdet");
 }
@@ -373,7 +373,7 @@ extern "C" int cfpp_conv1x1_fwd(const float* x, float* z, float* ldj, const floa
   CFPP_REQUIRE(threads <= 256 && smem <= 200 * 1024, "conv1x1: tile does not fit (D=%d)", D);
   const int64_t blocks = (int64_t)((B + ns - 1) / ns) * a.tiles_per_sample;
   cudaStream_t st = (cudaStream_t)stream;
-#define CFPP_C1(DT_, PX_) do { static bool set_ = false; if (!set_) { cudaFuncSetAttribute(conv1x1_kernel<DT_, PX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set_ = true; } \
+#define CFPP_C1(DT_, PX_) do { static DeviceOnce set_; if (set_.first()) { cudaFuncSetAttribute(conv1x1_kernel<DT_, PX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); } \
     conv1x1_kernel<DT_, PX_><<<(unsigned)blocks, threads, smem, st>>>(a); } while (0)
   if (DT == 16) { if (PX == 4) CFPP_C1(16, 4); else if (PX == 2) CFPP_C1(16, 2); else CFPP_C1(16, 1); }
   else if (DT == 32) { if (PX == 2) CFPP_C1(32, 2); else CFPP_C1(32, 1); }

@@ -153,11 +153,10 @@ extern "C" int cfpp_cn_batch(const cfpp_cn_job* jobs, int n_jobs, const float* c
   for (int j = 0; j < n_jobs; ++j) { a.job[j] = jobs[order[j]]; a.in[j] = in[order[j]]; a.out[j] = out[order[j]]; }
   a.stride = (width + 3) & ~3;
   const size_t smem = 2ull * CN_SPB * a.stride * sizeof(float);
-  static size_t smem_set = 48 * 1024;
-  if (smem > smem_set) {
+  static DeviceHighWater smem_set;                              // per device: one process may drive several GPUs
+  if (smem > 48 * 1024 && smem_set.raise((long long)smem)) {
     cudaError_t e = cudaFuncSetAttribute(cn_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("cn_batch: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return CFPP_ERR_CUDA; }
-    smem_set = smem;
   }
   const int64_t tiles = ((int64_t)B + CN_SPB - 1) / CN_SPB;
   CFPP_REQUIRE(tiles <= 0x7fffffff, "cn_batch: batch too large");

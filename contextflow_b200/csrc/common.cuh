@@ -20,6 +20,29 @@ inline int check_launch(const char* what) {
 
 #define CFPP_REQUIRE(cond, ...) do { if (!(cond)) { ::cfpp::set_error(__VA_ARGS__); return CFPP_ERR_ARG; } } while (0)
 
+// Function attributes (dynamic shared-memory limit, carve-out) are per DEVICE: `static DeviceOnce once; if (once.first()) { cudaFuncSetAttribute... }`
+// runs its body once for every device a kernel is launched on (one process may drive several GPUs: contextflow_b200/multigpu.py).
+struct DeviceOnce {
+  std::atomic<unsigned long long> seen{0};
+  bool first() {
+    int dev = 0; cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    return (seen.fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+  }
+};
+// per-device high-water mark for attributes that grow with the request (`if (hw.raise(bytes)) cudaFuncSetAttribute(..., bytes)`)
+struct DeviceHighWater {
+  std::atomic<long long> v[64];
+  DeviceHighWater() { for (auto& x : v) x.store(0); }
+  bool raise(long long want) {
+    int dev = 0; cudaGetDevice(&dev);
+    std::atomic<long long>& a = v[dev & 63];
+    if (want <= a.load(std::memory_order_relaxed)) return false;
+    a.store(want, std::memory_order_relaxed);
+    return true;
+  }
+};
+
 inline int num_sms() {
   static int n = 0;
   if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }

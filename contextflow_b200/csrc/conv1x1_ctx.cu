@@ -319,8 +319,8 @@ extern "C" int cfpp_conv1x1_ctx_fwd(const float* x, float* z, float* ldj, const 
   const int slots = num_sms() * g.occ;
   const int grid = a.ngroups < slots ? a.ngroups : slots;
   cudaStream_t st = (cudaStream_t)stream;
-#define CFPP_C1F(PT_, KT_) do { static bool set_ = false; if (!set_) { cudaFuncSetAttribute(c1f::conv1x1_ctx_kernel<PT_, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
-    cudaFuncSetAttribute(c1f::conv1x1_ctx_kernel<PT_, KT_>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); set_ = true; } \
+#define CFPP_C1F(PT_, KT_) do { static DeviceOnce set_; if (set_.first()) { cudaFuncSetAttribute(c1f::conv1x1_ctx_kernel<PT_, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+    cudaFuncSetAttribute(c1f::conv1x1_ctx_kernel<PT_, KT_>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); } \
     c1f::conv1x1_ctx_kernel<PT_, KT_><<<grid, c1f::kThreads, g.smem, st>>>(a); } while (0)
   if (g.PT == 8) { if (K == 20) CFPP_C1F(8, 20); else if (K == 8) CFPP_C1F(8, 8); else CFPP_C1F(8, 0); }
   else { if (K == 20) CFPP_C1F(4, 20); else if (K == 8) CFPP_C1F(4, 8); else CFPP_C1F(4, 0); }

@@ -243,8 +243,8 @@ int cfpp_conv1x1_rt_launch(const float* x, float* z, float* ldj, const float* NN
   const size_t smem = fixed + ns * per_sample;
   const int64_t blocks = (int64_t)((B + ns - 1) / ns) * a.tiles_per_sample;
   if (blocks > 0x7fffffff) return CFPP_ERR_UNSUPPORTED;
-#define CFPP_C1RT(PT_, DC_) do { static bool set_ = false; if (!set_) { cudaFuncSetAttribute(c1::conv1x1_rt_kernel<PT_, DC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-    cudaFuncSetAttribute(c1::conv1x1_rt_kernel<PT_, DC_>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); set_ = true; } \
+#define CFPP_C1RT(PT_, DC_) do { static DeviceOnce set_; if (set_.first()) { cudaFuncSetAttribute(c1::conv1x1_rt_kernel<PT_, DC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+    cudaFuncSetAttribute(c1::conv1x1_rt_kernel<PT_, DC_>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); } \
     c1::conv1x1_rt_kernel<PT_, DC_><<<(unsigned)blocks, threads, smem, st>>>(a); } while (0)
   const int DC = (D == 16 || D == 32 || D == 64) ? D : 0;
   if (PT == 8) { if (DC == 16) CFPP_C1RT(8, 16); else if (DC == 32) CFPP_C1RT(8, 32); else if (DC == 64) CFPP_C1RT(8, 64); else CFPP_C1RT(8, 0); }

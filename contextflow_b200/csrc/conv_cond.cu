@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(256) conv_cond_kernel(const ConvCondArgs a) {
 
 template <int KH, int KW, int TP>
 static int launch_conv_cond(const ConvCondArgs& a, int nwarps, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(conv_cond_kernel<KH, KW, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  static DeviceOnce attr_set;
+  if (attr_set.first()) { cudaFuncSetAttribute(conv_cond_kernel<KH, KW, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }
   const int blocks = (a.B + a.S - 1) / a.S;
   conv_cond_kernel<KH, KW, TP><<<blocks, nwarps * 32, smem, st>>>(a);
   return check_launch("conv_cond_fwd");

@@ -1054,13 +1054,12 @@ static int conv_cond_tc_launch(const float* x, int64_t x_bstride, float* h, cons
       // software-pipelined tiles: fp16 kind, one CTA per SM; index 16 + (seg ? 2 : 0) + (profile ? 1 : 0)
       tc::conv_cond_tc_kernel<false, false, true, 1, true>,   tc::conv_cond_tc_kernel<false, true, true, 1, true>,
       tc::conv_cond_tc_kernel<true, false, true, 1, true>,    tc::conv_cond_tc_kernel<true, true, true, 1, true>};
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
     for (int i = 0; i < 20; ++i) {
       cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (i < 8 || i >= 16) ? 227 * 1024 : (228 * 1024) / 2 - 1024);
       cudaFuncSetAttribute(kernels[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
-    attr_set = true;
   }
   const int ki = p.pipe ? 16 + (p.seg ? 2 : 0) + (a.prof != nullptr ? 1 : 0)
                         : (p.occ == 2 ? 8 : 0) | (p.seg ? 4 : 0) | (a.prof != nullptr ? 2 : 0) | (p.kind ? 1 : 0);

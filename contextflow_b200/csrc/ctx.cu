@@ -473,8 +473,8 @@ extern "C" int cfpp_ctx_encode_batch_flow(const int64_t* ctx, const cfpp_enc_des
   if (per_enc < 1) per_enc = 1;
   dim3 grid(per_enc, n_enc);
   cudaStream_t st = (cudaStream_t)stream;
-#define CFPP_ENCF(C_) do { const int smem = EncFlowLayout<C_>::floats * 4; static bool set_ = false; \
-    if (!set_) { cudaFuncSetAttribute(ctx_encode_flow_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set_ = true; } \
+#define CFPP_ENCF(C_) do { const int smem = EncFlowLayout<C_>::floats * 4; static DeviceOnce set_; \
+    if (set_.first()) { cudaFuncSetAttribute(ctx_encode_flow_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); } \
     ctx_encode_flow_kernel<C_><<<grid, kEncTile, smem, st>>>(ctx, descs_device, p, B); } while (0)
   if (C == 8) CFPP_ENCF(8); else CFPP_ENCF(20);
 #undef CFPP_ENCF

@@ -128,8 +128,8 @@ static int launch_gmm(const float* x, int64_t bs, const float* mG, const float* 
                       float lps, float* out, int B, int M, int K, int D, int HW, cudaStream_t st) {
   const int E = D * HW, MK = M * K;
   const size_t smem = ((size_t)S * E + (size_t)S * MK) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(gmm_kernel<CTX, S, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  static DeviceOnce attr_set;
+  if (attr_set.first()) { cudaFuncSetAttribute(gmm_kernel<CTX, S, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }
   const int ngroups = (MK + PK - 1) / PK;
   const int nwarps = ngroups < 8 ? ngroups : 8;
   gmm_kernel<CTX, S, PK><<<(B + S - 1) / S, nwarps * 32, smem, st>>>(x, bs, mG, sG, ws, co, lp, lps, out, B, M, K, D, HW);
@@ -326,13 +326,13 @@ extern "C" int cfpp_gmm_logprob_ctxtab(const float* x, int64_t x_bstride, const 
   const int ngroups = (MK + 3) / 4;
   const int nwarps = ngroups < 8 ? ngroups : 8;
   if (S == 8) {
-    static bool a8 = false;
-    if (!a8) { cudaFuncSetAttribute(gmm_tab_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); a8 = true; }
+    static DeviceOnce a8;
+    if (a8.first()) { cudaFuncSetAttribute(gmm_tab_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); }
     gmm_tab_kernel<8, 4><<<(int)max_tiles, nwarps * 32, smem, st>>>(x, x_bstride, mG, w.A, w.LB, w.perm, w.tile_key, w.n_tiles, mtab, width, moff,
                                                                   n_ctx, n_ctx == 2 ? cards[1] : 1, logp_c, logp_scale, out, M, K, D, HW);
   } else {
-    static bool a2 = false;
-    if (!a2) { cudaFuncSetAttribute(gmm_tab_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); a2 = true; }
+    static DeviceOnce a2;
+    if (a2.first()) { cudaFuncSetAttribute(gmm_tab_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); }
     gmm_tab_kernel<2, 4><<<(int)max_tiles, nwarps * 32, smem, st>>>(x, x_bstride, mG, w.A, w.LB, w.perm, w.tile_key, w.n_tiles, mtab, width, moff,
                                                                   n_ctx, n_ctx == 2 ? cards[1] : 1, logp_c, logp_scale, out, M, K, D, HW);
   }

@@ -359,11 +359,10 @@ extern "C" int cfpp_gmm_tile_logprob(const float* x, int64_t x_bstride, const vo
   const bool offs = mean_table != nullptr;
 #define CFPP_GT_LAUNCH(TMV, OFFV)                                                                                          \
   do {                                                                                                                     \
-    static bool attr = false;                                                                                              \
-    if (!attr) {                                                                                                           \
+    static DeviceOnce attr;                                                                                              \
+    if (attr.first()) {                                                                                                           \
       cudaFuncSetAttribute(gt::tile_kernel<TMV, OFFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);           \
       cudaFuncSetAttribute(gt::tile_kernel<TMV, OFFV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
-      attr = true;                                                                                                         \
     }                                                                                                                      \
     gt::tile_kernel<TMV, OFFV><<<grid, threads, smem, st>>>(a);                                                            \
   } while (0)

@@ -369,9 +369,9 @@ extern "C" int cfpp_actnorm_inv(const float* z, float* x, const float* t, const 
 
 extern "C" int cfpp_mat_inverse(const float* A, int D, float* Ainv, int* singular, void* stream) {
   CFPP_REQUIRE(D >= 1 && D <= 128, "mat_inverse: D=%d outside [1,128]", D);
-  static bool attr_set = false;
+  static DeviceOnce attr_set;
   const size_t full = ((size_t)128 * 128 + 2 * 128) * sizeof(double);
-  if (!attr_set) { cudaFuncSetAttribute(mat_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)full); attr_set = true; }
+  if (attr_set.first()) { cudaFuncSetAttribute(mat_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)full); }
   mat_inverse_kernel<<<1, 256, ((size_t)D * D + 2 * D) * sizeof(double), (cudaStream_t)stream>>>(A, D, Ainv, singular);
   return check_launch("mat_inverse");
 }

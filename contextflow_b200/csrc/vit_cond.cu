@@ -169,8 +169,8 @@ __global__ void __launch_bounds__(512) vit_cond_kernel(const VitArgs a) {
 
 template <int TP>
 static int launch_vit(const VitArgs& a, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(vit_cond_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  static DeviceOnce attr_set;
+  if (attr_set.first()) { cudaFuncSetAttribute(vit_cond_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }
   vit_cond_kernel<TP><<<(a.B + a.S - 1) / a.S, 512, smem, st>>>(a);
   return check_launch("vit_cond_fwd");
 }

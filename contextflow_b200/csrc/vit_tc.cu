@@ -427,8 +427,8 @@ extern "C" int cfpp_vit_tc_fwd(const float* x, int64_t x_bstride, float* h, cons
   a.ntiles = (B + a.S - 1) / a.S;
   const size_t smem = vt::smem_bytes(d.n_tok, d.depth);
   CFPP_REQUIRE(smem <= 227 * 1024, "vit_tc: depth %d does not fit the shared-memory parameter table", d.depth);
-  static size_t attr = 0;
-  if (smem > attr) { cudaFuncSetAttribute(vt::vit_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+  static DeviceHighWater attr;                                  // per device: one process may drive several GPUs
+  if (attr.raise((long long)smem)) cudaFuncSetAttribute(vt::vit_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
   vt::vit_tc_kernel<<<grid, vt::kThreads, smem, (cudaStream_t)stream>>>(a);
   return check_launch("vit_cond_tc_fwd");

@@ -375,8 +375,8 @@ extern "C" int cfpp_vit_tc2_fwd(const float* x, int64_t x_bstride, float* h, con
   a.xrows = a.S * d.n_tok;
   a.nstages = vt2::stages_for(d.T, a.P, a.xrows);
   const size_t smem = vt2::fixed_bytes(d.T, a.P, a.xrows) + (size_t)a.nstages * vt2::kChunkBytes;
-  static size_t attr = 0;
-  if (smem > attr) { cudaFuncSetAttribute(vt2::vit_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+  static DeviceHighWater attr;                                  // per device: one process may drive several GPUs
+  if (attr.raise((long long)smem)) cudaFuncSetAttribute(vt2::vit_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
   vt2::vit_tc2_kernel<<<grid, vt2::kThreads, smem, (cudaStream_t)stream>>>(a);
   return check_launch("vit_cond_tc_fwd");

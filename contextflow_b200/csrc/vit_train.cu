@@ -386,8 +386,8 @@ extern "C" int cfpp_rows_linear_fwd(const float* x, const float* W, const float*
   CFPP_REQUIRE(I >= 1 && I <= kMaxF && J >= 1, "rows_linear: I=%d J=%d", I, J);
   if (R <= 0) return CFPP_OK;
   const size_t smem = ((size_t)64 * (I | 1) + (size_t)I * kWS) * sizeof(float);
-  static bool a = false;
-  if (!a) { cudaFuncSetAttribute(rows_linear_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * (kMaxF + 1) + kMaxF * kWS) * 4); a = true; }
+  static DeviceOnce a;
+  if (a.first()) { cudaFuncSetAttribute(rows_linear_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * (kMaxF + 1) + kMaxF * kWS) * 4); }
   rows_linear_kernel<0><<<dim3((unsigned)((R + 63) / 64), (J + 63) / 64), 256, smem, (cudaStream_t)stream>>>(x, W, bias, y, R, I, J, 0, I);
   return check_launch("rows_linear_fwd");
 }
@@ -396,8 +396,8 @@ extern "C" int cfpp_rows_linear_bwd_data(const float* dy, const float* W, float*
   // W is the forward weight (J, I); dx[r][i] = sum_j dy[r][j] W[j][i]
   CFPP_REQUIRE(J >= 1 && I >= 1, "rows_linear_bwd_data: I=%d J=%d", I, J);
   if (R <= 0) return CFPP_OK;
-  static bool a = false;
-  if (!a) { cudaFuncSetAttribute(rows_linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * (kMaxF + 1) + kMaxF * kWS) * 4); a = true; }
+  static DeviceOnce a;
+  if (a.first()) { cudaFuncSetAttribute(rows_linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * (kMaxF + 1) + kMaxF * kWS) * 4); }
   for (int j0 = 0; j0 < J; j0 += kMaxF) {             // wide outputs (Conv1x1's CN: D*D columns): reduce in slices of 256, accumulating
     const int len = J - j0 < kMaxF ? J - j0 : kMaxF;
     const size_t smem = ((size_t)64 * (len | 1) + (size_t)len * kWS) * sizeof(float);

@@ -84,7 +84,9 @@ class GraphedLogProb:
         e.graph = torch.cuda.CUDAGraph()
         l0 = _cabi.launch_count()
         del rng._capture_host_draws[:]
-        with torch.no_grad(), torch.cuda.graph(e.graph, pool=self._pool):
+        # explicit capture stream on THIS device: torch.cuda.graph's default capture stream is created once per process, on whichever
+        # device was current at the first capture, and would drag captures of replicas on other GPUs (multigpu.py) onto that device
+        with torch.no_grad(), torch.cuda.graph(e.graph, pool=self._pool, stream=side):
             e.out = self.model.log_prob_eager(e.x, e.ctx)
         e.launches = _cabi.launch_count() - l0
         e.host_draws = list(rng._capture_host_draws)

@@ -31,7 +31,7 @@ class FlowSequential(nn.Module):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ('_fastpath', '_graphed', '_groups'):
+            if k in ('_fastpath', '_graphed', '_groups', '_replicated'):
                 continue
             new.__dict__[k] = copy.deepcopy(v, memo)
         new.__dict__['_groups'] = None
@@ -122,7 +122,32 @@ class FlowSequential(nn.Module):
                 return fp(input, context)
         return self.forward(input, context)[1]
 
+    def enable_multi_gpu(self, flag: bool = True, devices=None, min_rows: int = 512):
+        """Single-process N-GPU log_prob (SURVEY §8e process model, contextflow_b200/multigpu.py): batches of at least 2 * min_rows rows that
+        arrive on the model's device under no_grad are cut into contiguous slices, scored by weight replicas on every visible device and
+        concatenated back in order on the caller's device.  Also turned on by CFPP_MULTI_GPU=1."""
+        from ..multigpu import ReplicatedLogProb
+        object.__setattr__(self, '_replicated', ReplicatedLogProb(self, devices, min_rows) if flag else None)
+        return self
+
     def log_prob(self, input, context=None):
+        rep = self.__dict__.get('_replicated', False)
+        if rep is False:                                         # first call: the environment decides (a replica carries None)
+            import os
+            rep = None
+            if os.environ.get('CFPP_MULTI_GPU', '0') == '1' and not self.__dict__.get('_is_replica'):
+                self.enable_multi_gpu()
+                rep = self.__dict__['_replicated']
+            else:
+                object.__setattr__(self, '_replicated', None)
+        if (rep is not None and input.is_cuda and not torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing()
+                and torch.cuda.device_count() > 1):
+            from .. import rng
+            if rng._source is None and rng._recorder is None:
+                return rep(input, context)
+        return self._log_prob_single(input, context)
+
+    def _log_prob_single(self, input, context=None):
         g = getattr(self, '_graphed', None)
         if g is not None and input.is_cuda and not torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing():
             from .. import rng

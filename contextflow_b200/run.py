@@ -1,6 +1,6 @@
 """Launcher: run the reference's UNMODIFIED model.py over this package's layers.
 
-    cd <reference>/contextflow && python -m contextflow_b200.run model.py --gpu 0 --dataset smap --action-type test ...
+    cd <reference>/contextflow && python -m contextflow_b200.run [--multi-gpu] model.py --gpu 0 --dataset smap --action-type test ...
 
 model.py does `from layers import *` and `from layers.rtdl.nn._embeddings import *` (model.py:14-15) and is started from
 the reference directory, whose own `layers/` package would win on sys.path.  The replacement is therefore registered in
@@ -30,6 +30,9 @@ def install_layers():
 
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
+    if argv and argv[0] == '--multi-gpu':                     # score large inference batches on every visible GPU from this one process
+        os.environ['CFPP_MULTI_GPU'] = '1'                    # (contextflow_b200/multigpu.py; model.py itself stays unchanged)
+        argv = argv[1:]
     if not argv:
         raise SystemExit(__doc__)
     script = os.path.abspath(argv[0])

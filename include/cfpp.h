@@ -29,6 +29,9 @@ int cfpp_version(void);
 const char* cfpp_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches claim) */
 int64_t cfpp_launch_count(void);
+/* asynchronous copy of `bytes` between devices of this process on `stream` (a stream of the CURRENT device): single-process N-GPU
+ * log_prob pulls a batch slice to / pushes its (b, M) result from the device that scores it (contextflow_b200/multigpu.py) */
+int cfpp_copy_peer_async(void* dst, int dst_device, const void* src, int src_device, int64_t bytes, void* stream);
 
 /* ---- index-only layers (bit exact) ------------------------------------------------------------------ */
 /* Squeeze.forward, layers/squeeze.py:10-11: y[b,(c p1 p2),h,w] = x[b,c,h*p1+i,w*p2+j]; (H,W) are INPUT dims. */
