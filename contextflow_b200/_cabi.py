@@ -44,6 +44,8 @@ _SIGNATURES = {
     'cfpp_launch_count': (i64, []),
     'cfpp_copy_peer_async': (i32, [vp, i32, vp, i32, i64, vp]),
     'cfpp_maf_coupling_ctx_fwd': (i32, [vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, vp]),
+    'cfpp_adamw_chunk': (i32, []),
+    'cfpp_adamw_step': (i32, [vp, vp, i32, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp]),
     'cfpp_activation_fwd': (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
     'cfpp_activation_inv': (i32, [vp, vp, vp, i64, f32, i32, vp]),
     'cfpp_activation_bwd': (i32, [vp, vp, vp, vp, vp, i64, i32, i32, vp]),

@@ -176,9 +176,10 @@ class GraphedLogProb:
 
 class GraphedTrainStep:
     """forward + loss + backward of a training step captured in ONE CUDA graph (torch.cuda.graph around the libcfpp launches, which go to
-    torch's current stream): removes the host launch overhead of the 10^3 kernels of a specialist step.  The optimizer stays eager -- the
-    reference builds a plain torch.optim.AdamW (model.py:289), which is not capturable -- and reads the static .grad tensors the replay
-    overwrites, so do NOT call zero_grad(set_to_none=True) between steps.  Inputs are copied into static buffers; shapes are fixed.
+    torch's current stream): removes the host launch overhead of the 10^3 kernels of a specialist step.  A plain torch.optim.AdamW (what model.py:289
+    builds) is not capturable and stays eager; contextflow_b200.optim.FusedAdamW is captured by attach_optimizer() and replayed by
+    step().  Either way the optimizer reads the static .grad tensors the replay overwrites, so do NOT call zero_grad(set_to_none=True)
+    between steps.  Inputs are copied into static buffers; shapes are fixed.
     `loss_fn(model, x, ctx, gt) -> scalar loss`."""
 
     def __init__(self, model, loss_fn, x, ctx, gt, warmup: int = 2):
@@ -202,6 +203,26 @@ class GraphedTrainStep:
         with live_capture(), torch.cuda.graph(self.graph):
             self.loss = loss_fn(model, *self.static)
             self.loss.backward()
+
+    def attach_optimizer(self, opt):
+        """Capture `opt.step()` (contextflow_b200.optim.FusedAdamW: one multi-tensor kernel, step counter and bias corrections on the
+        device) in a second graph over the static .grad tensors of the captured backward; `step()` then replays it.  Kept apart from the
+        forward/backward graph so that a multi-GPU caller can all-reduce the gradients in between (sharded.GradAllReduce)."""
+        from .optim import FusedAdamW
+        if not isinstance(opt, FusedAdamW):
+            raise TypeError('attach_optimizer needs a contextflow_b200.optim.FusedAdamW (a plain torch.optim.AdamW is not capturable)')
+        for gi, group in enumerate(opt.param_groups):
+            opt._plan(gi, group)                           # pointer tables and state buffers are built eagerly (host -> device copies)
+        self.opt = opt
+        self.opt_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.opt_graph):
+            opt.step()
+        return self
+
+    def step(self):
+        """Optimizer update from the gradients of the last replay (after an optional gradient all-reduce)."""
+        self.opt.sync_learning_rate()
+        self.opt_graph.replay()
 
     def __call__(self, x, ctx, gt=None):
         self.static[0].copy_(x, non_blocking=True)

@@ -40,6 +40,9 @@ def main(argv=None):
     # shape; training calls (autograd on) always launch eagerly.  CFPP_CUDA_GRAPHS=0 in the environment keeps everything eager.
     os.environ.setdefault('CFPP_CUDA_GRAPHS', '1')
     install_layers()
+    if os.environ.get('CFPP_FUSED_ADAMW', '1') != '0':          # model.py:289 `optim.AdamW(...)` then builds the one-kernel optimizer
+        from contextflow_b200 import optim as _optim
+        _optim.install()
     sys.argv = [script] + argv[1:]
     sys.path.insert(0, os.path.dirname(script))
     os.chdir(os.path.dirname(script))

@@ -503,6 +503,15 @@ int cfpp_gmm_ctx_param_bwd(const float* x, int64_t x_bstride, const float* mG, c
                            const float* resp, const float* g, float* dmG, float* dsG, float* dwG, int B, int M, int K, int D, int HW,
                            void* stream);
 
+/* Fused multi-tensor AdamW (torch.optim.AdamW's update rule, model.py:289), capturable in a CUDA graph.  tensors: device array of
+ * 4 pointers per tensor {param, grad, exp_avg, exp_avg_sq} (float32); chunks: device array of {tensor index, first element, count}
+ * triples, count <= cfpp_adamw_chunk(); state: device float[3] {step count, 1 - b1^t, sqrt(1 - b2^t)} -- the call increments the
+ * step count first; lr: device scalar.  Hyper-parameters arrive as doubles: 1 - beta and the bias corrections are formed in double, as
+ * torch forms them from python floats, before rounding to float32. */
+int cfpp_adamw_chunk(void);
+int cfpp_adamw_step(const void* tensors, const int* chunks, int n_chunks, float* state, const float* lr, double beta1, double beta2,
+                    double eps, double weight_decay, void* stream);
+
 /* ---- container ------------------------------------------------------------------------------------------------ */
 /* FlowSequential.forward, layers/flowsequential.py:23: logdet (B,M) += ldj (B,cols) with cols = 1 (broadcast) or M. */
 int cfpp_ldj_accumulate(float* logdet, const float* ldj, int B, int M, int cols, void* stream);

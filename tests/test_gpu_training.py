@@ -408,3 +408,73 @@ def test_gelu_and_patchify_kernels():
     wide = torch.ones(3, 7, 8, 2, device='cuda')
     ops.patchify_inv(tok, 5, 8, 2, 2, 1, out=wide, accumulate=True)
     assert torch.equal(wide[:, :5].cpu(), img[:, :5] + 1) and torch.equal(wide[:, 5:].cpu(), torch.ones(3, 2, 8, 2))
+
+
+# ---- fused AdamW (contextflow_b200/optim.py) against torch.optim.AdamW ---------------------------------------------------------------
+def test_fused_adamw_matches_torch_adamw():
+    from contextflow_b200.optim import FusedAdamW, _TorchAdamW
+    shapes = [(5,), (3, 7), (4100,), (2, 3, 3, 3), (1,), (64, 65)]
+    ref = [torch.nn.Parameter(synth.normal(f'aw{i}', s).cuda()) for i, s in enumerate(shapes)]
+    got = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    o_ref = _TorchAdamW(ref + [torch.nn.Parameter(torch.ones(3).cuda())], lr=3e-3, weight_decay=0.05)   # the extra parameter never gets a gradient:
+    o_got = FusedAdamW(got + [torch.nn.Parameter(torch.ones(3).cuda())], lr=3e-3, weight_decay=0.05)    # skipped, as in torch
+    def grads(tag):
+        for i, (a, b) in enumerate(zip(ref, got)):
+            g = synth.normal(f'awg{tag}_{i}', tuple(a.shape)).cuda() * (10.0 ** (i - 2))
+            a.grad, b.grad = g.clone(), g.clone()
+    for step in range(6):
+        if step == 3:                                                                    # a scheduler moves the learning rate (model.py:290)
+            for o in (o_ref, o_got):
+                for g in o.param_groups:
+                    g['lr'] = 7e-4
+        grads(step)
+        o_ref.step(); o_got.step()
+        for i, (a, b) in enumerate(zip(ref, got)):
+            assert_close(b.detach().cpu().numpy(), a.detach().cpu().numpy(), 2e-6, 1e-7, f'step {step} param {i}')
+    sd = o_got.state_dict()
+    assert float(sd['state'][0]['step']) == 6.0
+    assert_close(sd['state'][2]['exp_avg_sq'].cpu().numpy(), o_ref.state_dict()['state'][2]['exp_avg_sq'].cpu().numpy(), 1e-5, 1e-12, 'exp_avg_sq')
+    o2 = FusedAdamW(got + [torch.nn.Parameter(torch.ones(3).cuda())], lr=7e-4, weight_decay=0.05)
+    o2.load_state_dict(sd)                                                               # resume (experiment_ad.py:319): the step count carries over
+    grads(9)
+    o_ref.step(); o2.step()
+    for i, (a, b) in enumerate(zip(ref, got)):
+        assert_close(b.detach().cpu().numpy(), a.detach().cpu().numpy(), 2e-6, 1e-7, f'resumed param {i}')
+
+
+@pytest.mark.parametrize('name,B', [('cfg1', 32), ('cifar_vardeq', 12)])
+def test_graphed_train_step_with_captured_optimizer(name, B):
+    """forward + backward in one graph, FusedAdamW in a second one (attach_optimizer), three steps: the parameters follow three eager
+    steps with torch.optim.AdamW (same gradients bit for bit; the fused update differs from torch's by float32 rounding only)."""
+    import copy
+    from contextflow_b200.graphed import GraphedTrainStep
+    from contextflow_b200.optim import FusedAdamW, _TorchAdamW
+    case = dict(CASES[name], B=B)
+    spec = TRAINING_CASES[name]
+    m_eager = build_cuda_model(case).train()
+    xw, cw = case_inputs(dict(case, iseed='gw'))
+    with torch.no_grad():
+        m_eager.log_prob(xw.cuda(), None if cw is None else cw.cuda())
+    m_graph = copy.deepcopy(m_eager)
+    batches = [case_inputs(dict(case, iseed=f'gs{i}')) for i in range(3)]
+    gts = [labels(f'gt{i}', B, case['conf']['mixtures']).cuda() for i in range(3)]
+    loss_fn = device_loss(case['conf']['data_size'], spec)
+    opt_e = _TorchAdamW([p for p in m_eager.parameters() if p.requires_grad], lr=1e-3)
+    opt_g = FusedAdamW([p for p in m_graph.parameters() if p.requires_grad], lr=1e-3)
+    x0, c0 = batches[0]
+    step = GraphedTrainStep(m_graph, loss_fn, x0.cuda(), None if c0 is None else c0.cuda(), gts[0]).attach_optimizer(opt_g)
+    for i, ((x, c), gt) in enumerate(zip(batches, gts)):
+        xc, cc = x.cuda(), None if c is None else c.cuda()
+        torch.manual_seed(100 + i)
+        opt_e.zero_grad(set_to_none=True)
+        le = loss_fn(m_eager, xc, cc, gt); le.backward(); opt_e.step()
+        torch.manual_seed(100 + i)
+        lg = step(xc, cc, gt); step.step()
+        assert abs(le.item() - lg.item()) <= 1e-5 * abs(le.item()), f'{name} step {i}: loss {le.item()} (eager) vs {lg.item()} (graph replay)'
+    for (k, pe), (_, pg) in zip(m_eager.named_parameters(), m_graph.named_parameters()):
+        if pe.requires_grad:
+            # Adam's update is lr * m / (sqrt(v) + eps): for an entry whose gradient is within rounding of zero the ratio is a coin flip, so
+            # float32-rounding differences of step 1 can move single entries by a fraction of lr; the bulk must agree to rounding
+            d = (pg.detach() - pe.detach()).abs()
+            assert d.max().item() <= 1.2e-3, f'{name}: {k} moved by {d.max().item():.3e} (more than 1.2 lr over three steps)'
+            assert d.mean().item() <= 2e-7 + 1e-5 * pe.detach().abs().mean().item(), f'{name}: {k} mean deviation {d.mean().item():.3e}'
