@@ -10,6 +10,7 @@
 // the stacked [B_hi; B_lo'] weight image); weights stream through a bulk-TMA mbarrier ring, one 16 KB chunk per 64 x 64 matrix.
 // Attention (n_tok <= 32 keys, all inside the thread's own warp) runs on the CUDA cores from k / v rows staged in shared memory.
 // Roles: warps 0-3 compute (thread = row), warp 4 = MMA issuer, warp 5 = weight producer.
+#include <stdlib.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
 
@@ -381,6 +382,328 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc_kernel(const Args a) {
   if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// Four threads per token row.  The kernel above keeps a whole 64-wide row in ONE thread: 4 compute warps per SM, one per scheduler, every
+// LayerNorm / GELU / operand split a 64-step serial instruction stream with nothing to switch to while a TMEM load, a shared-memory store
+// or the MMA round trip is outstanding (ncu r1u: issue slots 19 %, tensor pipe 4 %).  Here 16 compute warps share the tile: warp w serves
+// TMEM lane quadrant w % 4 (rows 32 (w % 4) .. +31, the hardware's warp -> lane rule) and column group g = w / 4 (columns 16 g .. +15): the
+// row state per thread shrinks to 16 registers, each scheduler holds 4 compute warps, and row-wide quantities cross the four column groups
+// through shared memory with a named barrier per quadrant:
+//   * LayerNorm: two reductions (sum, centred sum of squares), partials in a double-buffered [4][128] table, combined in a fixed order;
+//   * attention: q, k, v rows are staged in shared memory; thread (row, g) computes the FULL 64-wide dot products for the keys j = g, g + 4, ..
+//     and publishes the scores; after the quadrant barrier every thread forms the softmax (n_tok <= 32 exponentials, redundantly) and its
+//     own 16 columns of sum_j p_j v_j.
+// Everything else (operand rows, weight ring, the single MMA issuer, fp16 hi / scaled-lo arithmetic) is the kernel above.
+constexpr int kCG = 4, kCW = kW / kCG;              // column groups per row, columns per thread
+constexpr int kThreads4 = (4 * kCG + 2) * 32;       // 16 compute warps + MMA issuer + weight producer
+constexpr int kStages4 = 3;
+constexpr int kSStride = 33;                        // floats per row of the score table (n_tok <= 32)
+
+__device__ __forceinline__ void quad_sync(int quad) { asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(kCG * 32) : "memory"); }
+
+// sum of `v` over the four column-group threads of a row; `red` = this call's [kCG][kRows] table (callers alternate two tables)
+__device__ __forceinline__ float row_sum4(float v, float* red, int r, int g, int quad) {
+  red[g * kRows + r] = v;
+  quad_sync(quad);
+  return (red[r] + red[kRows + r]) + (red[2 * kRows + r] + red[3 * kRows + r]);
+}
+
+// LayerNorm over the first T entries of a row spread over four threads (16 columns each, zero beyond T): same padding algebra as above
+__device__ __forceinline__ void layer_norm4(const float (&x)[kCW], float (&out)[kCW], int T, const float* w, const float* b, float* red2, int& flip,
+                                            int r, int g, int quad) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kCW; i += 2) { s0 += x[i]; s1 += x[i + 1]; }
+  const float mean = row_sum4(s0 + s1, red2 + (flip & 1) * kCG * kRows, r, g, quad) / (float)T; ++flip;
+  float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kCW; i += 2) { const float d0 = x[i] - mean, d1 = x[i + 1] - mean; v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); }
+  const float ss = row_sum4(v0 + v1, red2 + (flip & 1) * kCG * kRows, r, g, quad); ++flip;
+  const float var = fmaxf(ss - (float)(kW - T) * mean * mean, 0.f) / (float)T;
+  const float rstd = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < kCW; i += 4) {
+    const float4 w4 = *reinterpret_cast<const float4*>(w + i), b4 = *reinterpret_cast<const float4*>(b + i);
+    out[i] = fmaf((x[i] - mean) * rstd, w4.x, b4.x); out[i + 1] = fmaf((x[i + 1] - mean) * rstd, w4.y, b4.y);
+    out[i + 2] = fmaf((x[i + 2] - mean) * rstd, w4.z, b4.z); out[i + 3] = fmaf((x[i + 3] - mean) * rstd, w4.w, b4.w);
+  }
+}
+// the thread's 16 channels of operand row `row` (two 16-byte chunks of the hi / lo regions)
+__device__ __forceinline__ void store_operand16(uint8_t* a_hi, uint8_t* a_lo, int row, int g, const float (&v)[kCW]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f16_split2(v[8 * c + 2 * q], v[8 * c + 2 * q + 1], h[q], l[q]);
+    const uint32_t off = (uint32_t)row * 128u + (uint32_t)((((2 * g + c) ^ row) & 7) << 4);
+    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+// the thread's 16 columns of its accumulator row: main block + 2^-11 * cross block
+__device__ __forceinline__ void load_acc16(uint32_t taddr, int g, float (&o)[kCW]) {
+  float v[16], u[16];
+  tmem_ld16(taddr + kCW * g, v);
+  tmem_ld16(taddr + kW + kCW * g, u);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < kCW; ++i) o[i] = fmaf(u[i], kLoInv, v[i]);
+}
+
+enum { B4_FULL = 0, B4_EMPTY = kStages4, B4_AREADY = 2 * kStages4, B4_ACC, B4_COUNT };
+
+__global__ void __launch_bounds__(kThreads4, 1) vit_tc4_kernel(const Args a) {
+  extern __shared__ __align__(1024) uint8_t vt_smem_raw[];
+  uint8_t* base = vt_smem_raw + ((1024u - (smem_u32(vt_smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_hi = base;                                       // 128 rows x 128 B
+  uint8_t* a_lo = base + kRows * 128;
+  uint8_t* ring = base + 2 * kRows * 128;                     // kStages4 x kChunkBytes
+  float* Ks = reinterpret_cast<float*>(ring + kStages4 * kChunkBytes);   // [128][kKVStride]
+  float* Vs = Ks + kRows * kKVStride;
+  float* Qs = Vs + kRows * kKVStride;
+  float* Sc = Qs + kRows * kKVStride;                         // [128][kSStride] attention scores
+  float* red2 = Sc + kRows * kSStride;                        // [2][kCG][128] row-reduction partials
+  float* prm = red2 + 2 * kCG * kRows;                        // parameter rows of 64 floats, zero padded
+  const int prm_rows = 7 + a.d.n_tok + 6 * a.d.depth;
+  const uint32_t bars = smem_u32(prm + prm_rows * kW);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(prm + prm_rows * kW) + 2 * B4_COUNT;
+  auto bar = [&](int i) { return bars + 8u * i; };
+  const cfpp_vit_desc& d = a.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = d.T, ntok = d.n_tok, depth = d.depth;
+  constexpr int kMmaWarp = 4 * kCG, kProdWarp = 4 * kCG + 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages4; ++i) { mbar_init(bar(B4_FULL + i), 1); mbar_init(bar(B4_EMPTY + i), 1); }
+    mbar_init(bar(B4_AREADY), kRows * kCG); mbar_init(bar(B4_ACC), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {   // parameter rows, as in the kernel above
+    const int64_t lstride = 4 * (int64_t)T + (int64_t)T * 192 + 64 * (int64_t)a.NPT + 2 * (int64_t)T * a.NPT + 2 * (int64_t)a.NPT;
+    for (int idx = tid; idx < prm_rows * kW; idx += kThreads4) {
+      const int row = idx / kW, i = idx - row * kW;
+      const float* src = nullptr; int n = T;
+      if (row == 0) { src = d.ln0_w; n = d.patch_dim; } else if (row == 1) { src = d.ln0_b; n = d.patch_dim; }
+      else if (row == 2) src = d.pe_b; else if (row == 3) src = d.ln1_w; else if (row == 4) src = d.ln1_b;
+      else if (row == 5) src = d.lnf_w; else if (row == 6) src = d.lnf_b;
+      else if (row < 7 + ntok) src = d.pos + (row - 7) * T;
+      else {
+        const int l = (row - 7 - ntok) / 6, k = (row - 7 - ntok) % 6;
+        const float* Lp = d.layers + l * lstride;
+        const float* lnf = Lp + 2 * T + (int64_t)T * 192 + 64 * (int64_t)a.NPT;
+        const float* b1 = lnf + 2 * T + (int64_t)T * a.NPT;
+        src = k == 0 ? Lp : k == 1 ? Lp + T : k == 2 ? lnf : k == 3 ? lnf + T : k == 4 ? b1 : b1 + a.NPT + (int64_t)T * a.NPT;
+      }
+      prm[idx] = i < n ? __ldg(src + i) : 0.f;
+    }
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int chunks_per_tile = 1 + 6 * depth;
+  const int my_tiles = (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == kProdWarp) {
+    if (elect_one()) {
+      uint32_t st = 0, ph = 0;
+      for (int it = 0; it < my_tiles; ++it)
+        for (int c = 0; c < chunks_per_tile; ++c) {
+          mbar_wait(bar(B4_EMPTY + st), ph ^ 1);
+          mbar_expect_tx(bar(B4_FULL + st), kChunkBytes);
+          bulk_g2s(smem_u32(ring + (size_t)st * kChunkBytes), a.wpack + (size_t)c * kChunkBytes, kChunkBytes, bar(B4_FULL + st));
+          if (++st == kStages4) { st = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == kMmaWarp) {
+    if (elect_one()) {
+      const uint32_t id128 = make_idesc(2 * kW), id64 = make_idesc(kW);
+      const uint64_t ah = make_desc(smem_u32(a_hi)), al = make_desc(smem_u32(a_lo)), b0 = make_desc(smem_u32(ring));
+      uint32_t st = 0, ph = 0, na = 0;
+      auto group = [&](int nchunks) {
+        mbar_wait(bar(B4_AREADY), na & 1); ++na;
+        tc_fence_after();
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(bar(B4_FULL + st), ph);
+          tc_fence_after();
+          const uint64_t bd = b0 + (uint64_t)(st * (kChunkBytes >> 4));
+          const uint32_t dd = tmem + c * 2 * kW;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            mma_f16(dd, ah + 2 * ks, bd + 2 * ks, id128, ks ? 1u : 0u);
+            mma_f16(dd + kW, al + 2 * ks, bd + 2 * ks, id64, 1u);
+          }
+          tc_commit(bar(B4_EMPTY + st));
+          if (++st == kStages4) { st = 0; ph ^= 1; }
+        }
+        tc_commit(bar(B4_ACC));
+      };
+      for (int it = 0; it < my_tiles; ++it) {
+        group(1);
+        for (int l = 0; l < depth; ++l) { group(3); group(1); group(1); group(1); }
+      }
+    }
+  } else {
+    // ===================== compute threads: (row, column group) =====================
+    const int quad = warp & 3, g = warp >> 2;
+    const int r = quad * 32 + lane, c0 = kCW * g;
+    const int HW = d.H * d.W, tw = d.W / d.p2, Cout = T / (d.p1 * d.p2);
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
+    uint32_t nacc = 0;
+    int flip = 0;
+    auto a_ready = [&]() { fence_async_smem(); mbar_arrive(bar(B4_AREADY)); };
+    auto acc_wait = [&]() { mbar_wait(bar(B4_ACC), nacc & 1); ++nacc; tc_fence_after(); };
+    auto prow = [&](int row) { return prm + row * kW + c0; };
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b0 = tile * a.S;
+      const int s = r / ntok, tok = r - s * ntok;
+      const bool live = r < a.S * ntok && b0 + s < a.B;
+      const int th = tok / tw, tww = tok - th * tw;
+      float x[kCW], y[kCW];                                      // invariant: entries beyond the live width are zero
+#pragma unroll
+      for (int i = 0; i < kCW; ++i) {
+        const int f = c0 + i;
+        float v = 0.f;
+        if (live && f < d.patch_dim) {
+          const int c = f % d.Cin, pp = f / d.Cin, ii = pp / d.p2, j = pp - ii * d.p2;
+          v = __ldg(a.x + (int64_t)(b0 + s) * a.x_bstride + (int64_t)c * HW + (th * d.p1 + ii) * d.W + (tww * d.p2 + j));
+        }
+        x[i] = v;
+      }
+      layer_norm4(x, y, d.patch_dim, prow(0), prow(1), red2, flip, r, g, quad);
+      store_operand16(a_hi, a_lo, r, g, y);
+      a_ready();
+      acc_wait();
+      load_acc16(trow, g, x);
+      tc_fence_before();
+      {
+        const float* pb = prow(2);
+#pragma unroll
+        for (int i = 0; i < kCW; ++i) x[i] += pb[i];
+      }
+      layer_norm4(x, x, T, prow(3), prow(4), red2, flip, r, g, quad);
+      {
+        const float* pp = prow(7 + tok);
+#pragma unroll
+        for (int i = 0; i < kCW; ++i) x[i] += pp[i];
+      }
+
+      for (int l = 0; l < depth; ++l) {
+        const int lrow = 7 + ntok + 6 * l;                         // lna_w lna_b lnf_w lnf_b b1 b2
+        // ---- attention: x += Wo softmax(q k^T / 8) v ----
+        layer_norm4(x, y, T, prow(lrow), prow(lrow + 1), red2, flip, r, g, quad);
+        store_operand16(a_hi, a_lo, r, g, y);
+        a_ready();
+        acc_wait();
+        {
+          float t16[kCW];
+          load_acc16(trow + 2 * kW, g, t16);                       // k
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(Ks + r * kKVStride + c0 + 4 * q) = make_float4(t16[4 * q], t16[4 * q + 1], t16[4 * q + 2], t16[4 * q + 3]);
+          load_acc16(trow + 4 * kW, g, t16);                       // v
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(Vs + r * kKVStride + c0 + 4 * q) = make_float4(t16[4 * q], t16[4 * q + 1], t16[4 * q + 2], t16[4 * q + 3]);
+          load_acc16(trow, g, t16);                                // q
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(Qs + r * kKVStride + c0 + 4 * q) = make_float4(t16[4 * q], t16[4 * q + 1], t16[4 * q + 2], t16[4 * q + 3]);
+        }
+        tc_fence_before();
+        quad_sync(quad);                                           // the keys / values of a sample are rows of this quadrant (n_tok divides 32)
+        const int r0 = r - tok;
+        for (int j = g; j < ntok; j += kCG) {                      // full-width scores of the keys this column group owns
+          const float* qr = Qs + r * kKVStride;
+          const float* kr = Ks + (r0 + j) * kKVStride;
+          float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float4 q4 = *reinterpret_cast<const float4*>(qr + 4 * q), k4 = *reinterpret_cast<const float4*>(kr + 4 * q);
+            d0 = fmaf(q4.x, k4.x, d0); d1 = fmaf(q4.y, k4.y, d1); d2 = fmaf(q4.z, k4.z, d2); d3 = fmaf(q4.w, k4.w, d3);
+          }
+          Sc[r * kSStride + j] = ((d0 + d1) + (d2 + d3)) * 0.125f;   // dim_head ** -0.5
+        }
+        quad_sync(quad);
+        {
+          float o[kCW];
+#pragma unroll
+          for (int i = 0; i < kCW; ++i) o[i] = 0.f;
+          float mx = -INFINITY;
+          for (int j = 0; j < ntok; ++j) mx = fmaxf(mx, Sc[r * kSStride + j]);
+          float den = 0.f;
+          for (int j = 0; j < ntok; ++j) {
+            const float pj = __expf(Sc[r * kSStride + j] - mx);
+            den += pj;
+            const float* vr = Vs + (r0 + j) * kKVStride + c0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 v4 = *reinterpret_cast<const float4*>(vr + 4 * q);
+              o[4 * q] = fmaf(pj, v4.x, o[4 * q]); o[4 * q + 1] = fmaf(pj, v4.y, o[4 * q + 1]);
+              o[4 * q + 2] = fmaf(pj, v4.z, o[4 * q + 2]); o[4 * q + 3] = fmaf(pj, v4.w, o[4 * q + 3]);
+            }
+          }
+          const float inv = 1.0f / den;
+#pragma unroll
+          for (int i = 0; i < kCW; ++i) o[i] *= inv;
+          store_operand16(a_hi, a_lo, r, g, o);
+        }
+        a_ready();                                                 // (the MMA group starts only when every thread is past its k / v / score reads)
+        acc_wait();
+        load_acc16(trow, g, y);
+        tc_fence_before();
+#pragma unroll
+        for (int i = 0; i < kCW; ++i) x[i] += y[i];
+        // ---- MLP: x += W2 gelu(W1 LN(x) + b1) + b2 ----
+        layer_norm4(x, y, T, prow(lrow + 2), prow(lrow + 3), red2, flip, r, g, quad);
+        store_operand16(a_hi, a_lo, r, g, y);
+        a_ready();
+        acc_wait();
+        load_acc16(trow, g, y);
+        tc_fence_before();
+        {
+          const float* pb1 = prow(lrow + 4);
+#pragma unroll
+          for (int i = 0; i < kCW; ++i) { const float u = y[i] + pb1[i]; y[i] = 0.5f * u * (1.0f + erf_as(u * 0.70710678118654752440f)); }
+        }
+        store_operand16(a_hi, a_lo, r, g, y);
+        a_ready();
+        acc_wait();
+        load_acc16(trow, g, y);
+        tc_fence_before();
+        {
+          const float* pb2 = prow(lrow + 5);
+#pragma unroll
+          for (int i = 0; i < kCW; ++i) x[i] += y[i] + pb2[i];
+        }
+      }
+      layer_norm4(x, x, T, prow(5), prow(6), red2, flip, r, g, quad);
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < kCW; ++i) {
+          const int f = c0 + i;
+          if (f < T) {
+            const int c = f % Cout, pp = f / Cout, ii = pp / d.p2, j = pp - ii * d.p2;
+            a.h[((int64_t)(b0 + s) * Cout + c) * HW + (th * d.p1 + ii) * d.W + (tww * d.p2 + j)] = x[i];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+static size_t smem_bytes4(int n_tok, int depth) {
+  return 1024 + 2 * kRows * 128 + (size_t)kStages4 * kChunkBytes + 3 * (size_t)kRows * kKVStride * 4 + (size_t)kRows * kSStride * 4 +
+         (size_t)2 * kCG * kRows * 4 + (size_t)(7 + n_tok + 6 * depth) * kW * 4 + B4_COUNT * 8 + 64;
+}
+
 // One 64 x 64 weight matrix -> one chunk: [hi image][lo image], rows = output features (zero beyond n_rows), 64 input channels per
 // 128-byte row (zero beyond k_cols), SWIZZLE_128B.  w is row-major (out, in) with leading dimension ld (nn.Linear.weight).
 __global__ void pack_chunk_kernel(const float* __restrict__ w, int ld, int n_rows, int k_cols, uint8_t* __restrict__ out) {
@@ -425,11 +748,19 @@ extern "C" int cfpp_vit_tc_fwd(const float* x, int64_t x_bstride, float* h, cons
   if (B <= 0) return CFPP_OK;
   vt::Args a{x, x_bstride, h, d, (const uint8_t*)wpack, B, vt::kRows / d.n_tok, 0, (d.T + 15) / 16 * 16};
   a.ntiles = (B + a.S - 1) / a.S;
+  const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
+  static const bool v1 = [] { const char* e = getenv("CFPP_VIT_TC_V1"); return e && *e == '1'; }();   // the one-thread-per-row kernel, kept for A/B timing
+  const size_t smem4 = vt::smem_bytes4(d.n_tok, d.depth);
+  if (!v1 && smem4 <= 227 * 1024) {
+    static DeviceHighWater attr4;                               // per device: one process may drive several GPUs
+    if (attr4.raise((long long)smem4)) cudaFuncSetAttribute(vt::vit_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+    vt::vit_tc4_kernel<<<grid, vt::kThreads4, smem4, (cudaStream_t)stream>>>(a);
+    return check_launch("vit_cond_tc_fwd");
+  }
   const size_t smem = vt::smem_bytes(d.n_tok, d.depth);
   CFPP_REQUIRE(smem <= 227 * 1024, "vit_tc: depth %d does not fit the shared-memory parameter table", d.depth);
-  static DeviceHighWater attr;                                  // per device: one process may drive several GPUs
+  static DeviceHighWater attr;
   if (attr.raise((long long)smem)) cudaFuncSetAttribute(vt::vit_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
   vt::vit_tc_kernel<<<grid, vt::kThreads, smem, (cudaStream_t)stream>>>(a);
   return check_launch("vit_cond_tc_fwd");
 }
