@@ -383,6 +383,39 @@ __global__ void __launch_bounds__(kThreads, 1) vit_tc_kernel(const Args a) {
 }
 
 
+
+// Packed fp32 pairs (Blackwell add / mul / fma .f32x2: two IEEE round-to-nearest operations per issue slot, results identical to scalar code)
+__device__ __forceinline__ uint64_t pack2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ uint64_t splat2(float a) { return pack2(a, a); }
+// GELU (erf form) of a pair: the Abramowitz & Stegun erf of erf_as above with the polynomial in packed arithmetic
+__device__ __forceinline__ void gelu2(float u0, float u1, float& o0, float& o1) {
+  const uint64_t u = pack2(u0, u1);
+  float t0, t1;
+  unpack2(fmul2(u, splat2(0.70710678118654752440f)), t0, t1);
+  const float a0 = fabsf(t0), a1 = fabsf(t1);
+  const uint64_t ax = pack2(a0, a1);
+  float d0, d1;
+  unpack2(ffma2(splat2(0.3275911f), ax, splat2(1.0f)), d0, d1);
+  const uint64_t t = pack2(__fdividef(1.0f, d0), __fdividef(1.0f, d1));
+  uint64_t p = ffma2(t, splat2(1.061405429f), splat2(-1.453152027f));
+  p = ffma2(t, p, splat2(1.421413741f));
+  p = ffma2(t, p, splat2(-0.284496736f));
+  p = ffma2(t, p, splat2(0.254829592f));
+  p = fmul2(t, p);
+  float e0, e1;
+  unpack2(fmul2(ax, ax), e0, e1);
+  float r0, r1;
+  unpack2(fsub2(splat2(1.0f), fmul2(p, pack2(__expf(-e0), __expf(-e1)))), r0, r1);
+  r0 = copysignf(r0, t0); r1 = copysignf(r1, t1);
+  const uint64_t hu = fmul2(u, splat2(0.5f));
+  unpack2(ffma2(hu, pack2(r0, r1), hu), o0, o1);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------------------
 // Four threads per token row.  The kernel above keeps a whole 64-wide row in ONE thread: 4 compute warps per SM, one per scheduler, every
 // LayerNorm / GELU / operand split a 64-step serial instruction stream with nothing to switch to while a TMEM load, a shared-memory store
@@ -421,13 +454,22 @@ __device__ __forceinline__ void layer_norm4(const float (&x)[kCW], float (&out)[
   for (int i = 0; i < kCW; i += 2) { const float d0 = x[i] - mean, d1 = x[i + 1] - mean; v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); }
   const float ss = row_sum4(v0 + v1, red2 + (flip & 1) * kCG * kRows, r, g, quad); ++flip;
   const float var = fmaxf(ss - (float)(kW - T) * mean * mean, 0.f) / (float)T;
-  const float rstd = 1.0f / sqrtf(var + 1e-5f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  const uint64_t m2 = splat2(mean), r2 = splat2(rstd);
 #pragma unroll
   for (int i = 0; i < kCW; i += 4) {
     const float4 w4 = *reinterpret_cast<const float4*>(w + i), b4 = *reinterpret_cast<const float4*>(b + i);
-    out[i] = fmaf((x[i] - mean) * rstd, w4.x, b4.x); out[i + 1] = fmaf((x[i + 1] - mean) * rstd, w4.y, b4.y);
-    out[i + 2] = fmaf((x[i + 2] - mean) * rstd, w4.z, b4.z); out[i + 3] = fmaf((x[i + 3] - mean) * rstd, w4.w, b4.w);
+    unpack2(ffma2(fmul2(fsub2(pack2(x[i], x[i + 1]), m2), r2), pack2(w4.x, w4.y), pack2(b4.x, b4.y)), out[i], out[i + 1]);
+    unpack2(ffma2(fmul2(fsub2(pack2(x[i + 2], x[i + 3]), m2), r2), pack2(w4.z, w4.w), pack2(b4.z, b4.w)), out[i + 2], out[i + 3]);
   }
+}
+// (hi, lo') fp16 pairs of two values in packed arithmetic: 3 instructions per element
+__device__ __forceinline__ void f16_split2p(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const float ha = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), hb = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+  float la, lb;
+  unpack2(fmul2(fsub2(pack2(a, b), pack2(ha, hb)), splat2(kLoScale)), la, lb);
+  hi = pack_f16x2_sat(ha, hb);
+  lo = pack_f16x2_sat(la, lb);
 }
 // the thread's 16 channels of operand row `row` (two 16-byte chunks of the hi / lo regions)
 __device__ __forceinline__ void store_operand16(uint8_t* a_hi, uint8_t* a_lo, int row, int g, const float (&v)[kCW]) {
@@ -435,7 +477,7 @@ __device__ __forceinline__ void store_operand16(uint8_t* a_hi, uint8_t* a_lo, in
   for (int c = 0; c < 2; ++c) {
     uint32_t h[4], l[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) f16_split2(v[8 * c + 2 * q], v[8 * c + 2 * q + 1], h[q], l[q]);
+    for (int q = 0; q < 4; ++q) f16_split2p(v[8 * c + 2 * q], v[8 * c + 2 * q + 1], h[q], l[q]);
     const uint32_t off = (uint32_t)row * 128u + (uint32_t)((((2 * g + c) ^ row) & 7) << 4);
     *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -447,8 +489,9 @@ __device__ __forceinline__ void load_acc16(uint32_t taddr, int g, float (&o)[kCW
   tmem_ld16(taddr + kCW * g, v);
   tmem_ld16(taddr + kW + kCW * g, u);
   tmem_ld_wait();
+  const uint64_t k2 = splat2(kLoInv);
 #pragma unroll
-  for (int i = 0; i < kCW; ++i) o[i] = fmaf(u[i], kLoInv, v[i]);
+  for (int i = 0; i < kCW; i += 2) unpack2(ffma2(pack2(u[i], u[i + 1]), k2, pack2(v[i], v[i + 1])), o[i], o[i + 1]);
 }
 
 enum { B4_FULL = 0, B4_EMPTY = kStages4, B4_AREADY = 2 * kStages4, B4_ACC, B4_COUNT };
@@ -466,8 +509,10 @@ __global__ void __launch_bounds__(kThreads4, 1) vit_tc4_kernel(const Args a) {
   float* red2 = Sc + kRows * kSStride;                        // [2][kCG][128] row-reduction partials
   float* prm = red2 + 2 * kCG * kRows;                        // parameter rows of 64 floats, zero padded
   const int prm_rows = 7 + a.d.n_tok + 6 * a.d.depth;
-  const uint32_t bars = smem_u32(prm + prm_rows * kW);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(prm + prm_rows * kW) + 2 * B4_COUNT;
+  int* idx_in = reinterpret_cast<int*>(prm + prm_rows * kW);  // [n_tok][64] element offset of (token, feature) inside a sample of x; -1 beyond patch_dim
+  int* idx_out = idx_in + a.d.n_tok * kW;                     // [n_tok][64] the same for the output h; -1 beyond T
+  const uint32_t bars = smem_u32(idx_out + a.d.n_tok * kW);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(idx_out + a.d.n_tok * kW) + 2 * B4_COUNT;
   auto bar = [&](int i) { return bars + 8u * i; };
   const cfpp_vit_desc& d = a.d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -496,6 +541,17 @@ __global__ void __launch_bounds__(kThreads4, 1) vit_tc4_kernel(const Args a) {
         src = k == 0 ? Lp : k == 1 ? Lp + T : k == 2 ? lnf : k == 3 ? lnf + T : k == 4 ? b1 : b1 + a.NPT + (int64_t)T * a.NPT;
       }
       prm[idx] = i < n ? __ldg(src + i) : 0.f;
+    }
+  }
+  {   // 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' and its inverse as offset tables: the runtime divisions are paid once per CTA, not per tile
+    const int HW_ = d.H * d.W, tw_ = d.W / d.p2, Cout_ = T / (d.p1 * d.p2);
+    for (int idx = tid; idx < ntok * kW; idx += kThreads4) {
+      const int tok = idx / kW, f = idx - tok * kW;
+      const int th = tok / tw_, tww = tok - th * tw_;
+      int oi = -1, oo = -1;
+      if (f < d.patch_dim) { const int c = f % d.Cin, pp = f / d.Cin, ii = pp / d.p2, j = pp - ii * d.p2; oi = c * HW_ + (th * d.p1 + ii) * d.W + (tww * d.p2 + j); }
+      if (f < T) { const int c = f % Cout_, pp = f / Cout_, ii = pp / d.p2, j = pp - ii * d.p2; oo = c * HW_ + (th * d.p1 + ii) * d.W + (tww * d.p2 + j); }
+      idx_in[idx] = oi; idx_out[idx] = oo;
     }
   }
   if (warp == kMmaWarp) {
@@ -553,7 +609,7 @@ __global__ void __launch_bounds__(kThreads4, 1) vit_tc4_kernel(const Args a) {
     // ===================== compute threads: (row, column group) =====================
     const int quad = warp & 3, g = warp >> 2;
     const int r = quad * 32 + lane, c0 = kCW * g;
-    const int HW = d.H * d.W, tw = d.W / d.p2, Cout = T / (d.p1 * d.p2);
+    const int HW = d.H * d.W, Cout = T / (d.p1 * d.p2);
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
     uint32_t nacc = 0;
     int flip = 0;
@@ -565,17 +621,12 @@ __global__ void __launch_bounds__(kThreads4, 1) vit_tc4_kernel(const Args a) {
       const int b0 = tile * a.S;
       const int s = r / ntok, tok = r - s * ntok;
       const bool live = r < a.S * ntok && b0 + s < a.B;
-      const int th = tok / tw, tww = tok - th * tw;
       float x[kCW], y[kCW];                                      // invariant: entries beyond the live width are zero
+      {
+        const float* xs = a.x + (int64_t)(b0 + s) * a.x_bstride;
+        const int* oi = idx_in + tok * kW + c0;
 #pragma unroll
-      for (int i = 0; i < kCW; ++i) {
-        const int f = c0 + i;
-        float v = 0.f;
-        if (live && f < d.patch_dim) {
-          const int c = f % d.Cin, pp = f / d.Cin, ii = pp / d.p2, j = pp - ii * d.p2;
-          v = __ldg(a.x + (int64_t)(b0 + s) * a.x_bstride + (int64_t)c * HW + (th * d.p1 + ii) * d.W + (tww * d.p2 + j));
-        }
-        x[i] = v;
+        for (int i = 0; i < kCW; ++i) { const int o = oi[i]; x[i] = (live && o >= 0) ? __ldg(xs + o) : 0.f; }
       }
       layer_norm4(x, y, d.patch_dim, prow(0), prow(1), red2, flip, r, g, quad);
       store_operand16(a_hi, a_lo, r, g, y);
@@ -657,7 +708,7 @@ __global__ void __launch_bounds__(kThreads4, 1) vit_tc4_kernel(const Args a) {
         load_acc16(trow, g, y);
         tc_fence_before();
 #pragma unroll
-        for (int i = 0; i < kCW; ++i) x[i] += y[i];
+        for (int i = 0; i < kCW; i += 2) unpack2(fadd2(pack2(x[i], x[i + 1]), pack2(y[i], y[i + 1])), x[i], x[i + 1]);
         // ---- MLP: x += W2 gelu(W1 LN(x) + b1) + b2 ----
         layer_norm4(x, y, T, prow(lrow + 2), prow(lrow + 3), red2, flip, r, g, quad);
         store_operand16(a_hi, a_lo, r, g, y);
@@ -668,7 +719,7 @@ __global__ void __launch_bounds__(kThreads4, 1) vit_tc4_kernel(const Args a) {
         {
           const float* pb1 = prow(lrow + 4);
 #pragma unroll
-          for (int i = 0; i < kCW; ++i) { const float u = y[i] + pb1[i]; y[i] = 0.5f * u * (1.0f + erf_as(u * 0.70710678118654752440f)); }
+          for (int i = 0; i < kCW; i += 2) gelu2(y[i] + pb1[i], y[i + 1] + pb1[i + 1], y[i], y[i + 1]);
         }
         store_operand16(a_hi, a_lo, r, g, y);
         a_ready();
@@ -678,19 +729,15 @@ __global__ void __launch_bounds__(kThreads4, 1) vit_tc4_kernel(const Args a) {
         {
           const float* pb2 = prow(lrow + 5);
 #pragma unroll
-          for (int i = 0; i < kCW; ++i) x[i] += y[i] + pb2[i];
+          for (int i = 0; i < kCW; i += 2) unpack2(fadd2(pack2(x[i], x[i + 1]), fadd2(pack2(y[i], y[i + 1]), pack2(pb2[i], pb2[i + 1]))), x[i], x[i + 1]);
         }
       }
       layer_norm4(x, x, T, prow(5), prow(6), red2, flip, r, g, quad);
       if (live) {
+        float* hs = a.h + (int64_t)(b0 + s) * Cout * HW;
+        const int* oo = idx_out + tok * kW + c0;
 #pragma unroll
-        for (int i = 0; i < kCW; ++i) {
-          const int f = c0 + i;
-          if (f < T) {
-            const int c = f % Cout, pp = f / Cout, ii = pp / d.p2, j = pp - ii * d.p2;
-            a.h[((int64_t)(b0 + s) * Cout + c) * HW + (th * d.p1 + ii) * d.W + (tww * d.p2 + j)] = x[i];
-          }
-        }
+        for (int i = 0; i < kCW; ++i) { const int o = oo[i]; if (o >= 0) hs[o] = x[i]; }
       }
     }
   }
@@ -701,7 +748,7 @@ __global__ void __launch_bounds__(kThreads4, 1) vit_tc4_kernel(const Args a) {
 
 static size_t smem_bytes4(int n_tok, int depth) {
   return 1024 + 2 * kRows * 128 + (size_t)kStages4 * kChunkBytes + 3 * (size_t)kRows * kKVStride * 4 + (size_t)kRows * kSStride * 4 +
-         (size_t)2 * kCG * kRows * 4 + (size_t)(7 + n_tok + 6 * depth) * kW * 4 + B4_COUNT * 8 + 64;
+         (size_t)2 * kCG * kRows * 4 + (size_t)(7 + n_tok + 6 * depth) * kW * 4 + (size_t)2 * n_tok * kW * 4 + B4_COUNT * 8 + 64;
 }
 
 // One 64 x 64 weight matrix -> one chunk: [hi image][lo image], rows = output features (zero beyond n_rows), 64 input channels per
