@@ -195,8 +195,10 @@ __global__ void __launch_bounds__(1024) gmm_bucket_kernel(const int64_t* __restr
   }
 }
 
+// Up to 20 warps per tile: at small batches (the reference's default B = 256 gives ~10^2 tiles of 8 samples) the tile's latency is the
+// kernel's, so every group of PK components gets its own warp instead of taking turns on 8.
 template <int S, int PK>
-__global__ void __launch_bounds__(256) gmm_tab_kernel(const float* __restrict__ x, int64_t x_bstride, const float* __restrict__ mG,
+__global__ void __launch_bounds__(640) gmm_tab_kernel(const float* __restrict__ x, int64_t x_bstride, const float* __restrict__ mG,
                                                       const float* __restrict__ A, const float* __restrict__ LB,
                                                       const int* __restrict__ perm, const int* __restrict__ tile_key,
                                                       const int* __restrict__ n_tiles, const float* __restrict__ mtab, int width, int moff,
@@ -324,7 +326,7 @@ extern "C" int cfpp_gmm_logprob_ctxtab(const float* x, int64_t x_bstride, const 
   if (rc) return rc;
   const size_t smem = ((size_t)S * E + (size_t)S * MK) * sizeof(float);
   const int ngroups = (MK + 3) / 4;
-  const int nwarps = ngroups < 8 ? ngroups : 8;
+  const int nwarps = ngroups < 20 ? ngroups : 20;
   if (S == 8) {
     static DeviceOnce a8;
     if (a8.first()) { cudaFuncSetAttribute(gmm_tab_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); }
