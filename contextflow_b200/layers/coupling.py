@@ -85,10 +85,12 @@ class Coupling(_CouplingBase):
 
     def _fused(self, x, pk, **kw):
         """Conditioner + coupling transform as one tensor-core kernel (h never reaches HBM); None when the shape has no fused plan."""
-        # measured (B200, cfg2, B = 8192): fused 3.75 ms / step against 2.98 + 0.46 ms for conditioner + coupling kernel -- the epilogue
-        # warps are the conditioner's bottleneck and the coupling kernel already runs at 94 % of HBM bandwidth, so the fused form is
-        # opt-in (CFPP_CONV_COND=fused) until the epilogue has headroom
-        if pk['tc'] is None or ops.conv_cond_tc_mode() != 'fused':
+        # measured (B200, cfg2): round 1 the fused form lost (3.75 ms / step against 2.98 + 0.46 ms at B = 8192); with x1 prefetched ahead of
+        # the stage-3 wait and the per-sample output bias staged in shared memory it ties at B = 8192 (3.20 vs 2.78 + 0.47 ms) and wins at
+        # small batches, where every launch's fixed latency counts (B = 256: 0.682 vs 0.706 ms / step) -- 'auto' takes it below
+        # ops.CONV_COND_FUSED_MAX_BATCH samples; CFPP_CONV_COND=fused / split force either route
+        mode = ops.conv_cond_tc_mode()
+        if pk['tc'] is None or not (mode == 'fused' or (mode == 'auto' and x.shape[0] < ops.CONV_COND_FUSED_MAX_BATCH)):
             return None
         b1, b2, b3 = pk['main'][1], pk['main'][3], pk['main'][5]
         return ops.conv_cond_tc_coupling(x, pk['tc'], b1, b2, b3, self._dims[1], self.krn[0], self.krn[1], **kw)

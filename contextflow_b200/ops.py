@@ -446,9 +446,13 @@ def conv_cond(x, cin, packed, H, W, KH, KW, cout, bias1_b=None):
     return h
 
 
+CONV_COND_FUSED_MAX_BATCH = 4096     # B200, cfg2: fused 0.682 / 1.207 / 1.811 ms per step at B = 256 / 1024 / 2048 against 0.706 / 1.230 / 1.818 split; 5.73 against 5.66 at 8192
+
+
 def conv_cond_tc_mode() -> str:
-    """'auto' (tensor cores whenever the shape has a plan), 'fused' (conditioner + coupling transform in one kernel),
-    'fma' (force the FP32-FMA kernel) -- env CFPP_CONV_COND."""
+    """'auto' (tensor cores whenever the shape has a plan; below CONV_COND_FUSED_MAX_BATCH samples the conditioner and the coupling transform
+    run as ONE kernel, so h never reaches HBM and a launch is saved -- measured faster there; above it the two-kernel route is ~1 % ahead),
+    'fused' / 'split' (force either), 'fma' (force the FP32-FMA conditioner) -- env CFPP_CONV_COND."""
     import os
     return os.environ.get('CFPP_CONV_COND', 'auto')
 
