@@ -55,6 +55,7 @@ _SIGNATURES = {
     'cfpp_bias_rows_relu': (i32, [vp, vp, i32, i32, i32, vp]),
     'cfpp_gmm_ctx_param_bwd': (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     'cfpp_squeeze_fwd': (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    'cfpp_squeeze_strided_fwd': (i32, [vp, i64, vp, i32, i32, i32, i32, i32, i32, vp]),
     'cfpp_squeeze_inv': (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     'cfpp_permute_fwd': (i32, [vp, vp, i32, i32, i32, i32, vp]),
     'cfpp_slice_channels': (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),

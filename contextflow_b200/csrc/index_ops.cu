@@ -25,13 +25,16 @@ __global__ void squeeze_kernel(const float* __restrict__ x, float* __restrict__ 
 
 // Squeeze with a (2,2) patch and W % 8 == 0 (the image stacks): a thread moves 8 consecutive input floats of one input row
 // (two 128-bit streaming loads) to the two output planes j = 0 / 1 (one 128-bit streaming store each); no per-element index math.
-__global__ void __launch_bounds__(256) squeeze22_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t units, int H, int W) {
+// x_gap = floats between the end of one sample's C channels and the start of the next sample (0 for a contiguous tensor; C*H*W when x is
+// the first half of the channels of a SplitPrior input, so that the split needs no copy of its own)
+__global__ void __launch_bounds__(256) squeeze22_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t units, int H, int W,
+                                                        int C, int64_t x_gap) {
   const int W8 = W >> 3, Ho = H >> 1, Wo = W >> 1;
   for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < units; u += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = u / W8; const int wq = (int)(u - r * W8);
     const int64_t bc = r / H; const int hi = (int)(r - bc * H);
     const int h = hi >> 1, i = hi & 1;
-    const float4* src = reinterpret_cast<const float4*>(x + r * W + wq * 8);
+    const float4* src = reinterpret_cast<const float4*>(x + r * W + wq * 8 + (x_gap ? (bc / C) * x_gap : 0));
     const float4 a = ldg_stream(src), b = ldg_stream(src + 1);
     float* dst = y + ((bc * 4 + i * 2) * Ho + h) * (int64_t)Wo + wq * 4;
     stg_stream(reinterpret_cast<float4*>(dst), make_float4(a.x, a.z, b.x, b.z));
@@ -188,9 +191,23 @@ extern "C" int cfpp_squeeze_fwd(const float* x, float* y, int B, int C, int H, i
   int64_t total = (int64_t)B * C * H * W;
   if (!total) return CFPP_OK;
   if (p1 == 2 && p2 == 2 && W % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)
-    squeeze22_kernel<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(x, y, total / 8, H, W);
+    squeeze22_kernel<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(x, y, total / 8, H, W, C, 0);
   else
     squeeze_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, total, C, H, W, p1, p2, false);
+  return check_launch("squeeze_fwd");
+}
+// Squeeze of the first C channels of every sample of a wider tensor (batch stride x_bstride floats >= C*H*W): SplitPrior's z = x[:, :C]
+// (splitprior.py:13) followed by the next block's Squeeze (model.py:125-127) without the copy in between.  2x2 squeezes of 16-byte aligned
+// rows only (the BASELINE image stacks); CFPP_ERR_UNSUPPORTED otherwise (the caller slices first).
+extern "C" int cfpp_squeeze_strided_fwd(const float* x, int64_t x_bstride, float* y, int B, int C, int H, int W, int p1, int p2, void* stream) {
+  CFPP_REQUIRE(B >= 0 && C > 0 && p1 > 0 && p2 > 0 && H % p1 == 0 && W % p2 == 0 && x_bstride >= (int64_t)C * H * W, "squeeze_strided: bad dims");
+  int64_t total = (int64_t)B * C * H * W;
+  if (!total) return CFPP_OK;
+  if (!(p1 == 2 && p2 == 2 && W % 8 == 0 && x_bstride % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)) {
+    set_error("squeeze_strided: only 2x2 squeezes of 16-byte aligned rows (W %% 8 == 0) read through a batch stride");
+    return CFPP_ERR_UNSUPPORTED;
+  }
+  squeeze22_kernel<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(x, y, total / 8, H, W, C, x_bstride - (int64_t)C * H * W);
   return check_launch("squeeze_fwd");
 }
 extern "C" int cfpp_squeeze_inv(const float* y, float* x, int B, int C, int H, int W, int p1, int p2, void* stream) {

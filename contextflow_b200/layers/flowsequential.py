@@ -16,6 +16,11 @@ class FlowSequential(nn.Module):
         for i, module in enumerate(modules):
             self.add_module(str(i), module)
         self.sequence_modules = modules
+        from .splitprior import SplitPrior
+        from .squeeze import Squeeze
+        for m, nxt in zip(modules, modules[1:]):                 # SplitPrior -> Squeeze (model.py:153-158, 125-127): the kept half is handed over
+            if isinstance(m, SplitPrior) and isinstance(nxt, Squeeze) and tuple(getattr(nxt, 'p', getattr(nxt, 'factor', (0, 0)))) == (2, 2):
+                m._view_ok = True                                # as a view; the squeeze kernel reads it through the batch stride (no copy)
         import os
         self._graphed = None
         if os.environ.get('CFPP_CUDA_GRAPHS', '0') == '1':

@@ -22,6 +22,8 @@ class SplitPrior(FlowLayer):
             return training.GmmCtxFn.apply(x, ctx2, d, x.shape[1] // 2, d.mG, d.sG, d.wG, *tables)
         half = x.shape[1] // 2
         ldj = self.dist.log_prob(x[:, half:], context)         # read in place through the batch stride, (B, M)
+        if getattr(self, '_view_ok', False) and x.is_contiguous() and x.shape[3] % 8 == 0 and (half * x.shape[2] * x.shape[3]) % 4 == 0:
+            return x[:, :half], ldj                             # the next layer is a 2x2 Squeeze that reads this view in place (ops.squeeze)
         return ops.slice_channels(x, 0, half), ldj
 
     def reverse(self, z, context=None):

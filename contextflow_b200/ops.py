@@ -116,7 +116,16 @@ def _half_view(x: torch.Tensor):
 
 # ---------------------------------------------------------------------------------------------- index ops
 def squeeze(x, p1, p2):
-    _need_cuda(x); x = _f32(x)
+    _need_cuda(x)
+    if not x.is_contiguous() and x.dtype == torch.float32 and x.dim() == 4 and p1 == 2 and p2 == 2 and x.shape[3] % 8 == 0:
+        st = x.stride()                                          # a leading-channels view of a wider tensor (SplitPrior's z): read it in place
+        B, Cc, H, W = x.shape
+        if st[3] == 1 and st[2] == W and st[1] == H * W and st[0] % 4 == 0 and st[0] >= Cc * H * W and x.data_ptr() % 16 == 0:
+            y = torch.empty((B, Cc * 4, H // 2, W // 2), device=x.device, dtype=x.dtype)
+            _set_work(bytes=8.0 * x.numel())
+            _call('squeeze_strided_fwd', (_p(x), st[0], _p(y), B, Cc, H, W, p1, p2, _stream()), 'squeeze_fwd')
+            return y
+    x = _f32(x)
     B, Cc, H, W = x.shape
     y = torch.empty((B, Cc * p1 * p2, H // p1, W // p2), device=x.device, dtype=x.dtype)
     _set_work(bytes=8.0 * x.numel())

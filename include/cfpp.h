@@ -36,6 +36,9 @@ int cfpp_copy_peer_async(void* dst, int dst_device, const void* src, int src_dev
 /* ---- index-only layers (bit exact) ------------------------------------------------------------------ */
 /* Squeeze.forward, layers/squeeze.py:10-11: y[b,(c p1 p2),h,w] = x[b,c,h*p1+i,w*p2+j]; (H,W) are INPUT dims. */
 int cfpp_squeeze_fwd(const float* x, float* y, int B, int C, int H, int W, int p1, int p2, void* stream);
+/* the same over the first C channels of every sample of a wider tensor (batch stride x_bstride floats): SplitPrior's z = x[:, :C]
+ * (splitprior.py:13) feeding the next block's Squeeze without a copy of its own; 2x2, W % 8 == 0 only (CFPP_ERR_UNSUPPORTED otherwise) */
+int cfpp_squeeze_strided_fwd(const float* x, int64_t x_bstride, float* y, int B, int C, int H, int W, int p1, int p2, void* stream);
 /* Squeeze.reverse, layers/squeeze.py:13-14; (H,W) are the dims of the un-squeezed OUTPUT. */
 int cfpp_squeeze_inv(const float* y, float* x, int B, int C, int H, int W, int p1, int p2, void* stream);
 /* PermuteAxes((0,2,1,3)).forward, layers/permute_axes.py:13-14: y[b,h,c,w] = x[b,c,h,w]. */
