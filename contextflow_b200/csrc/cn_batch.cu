@@ -46,13 +46,20 @@ __device__ __forceinline__ void cn_layer(const float4* __restrict__ src, float* 
     const float* wp = wt + n;
     const float4* ap = src + s0;
     int krem = K;
-    for (int k4 = 0; k4 < K4; ++k4, wp += N4, ap += CN_SPB, krem -= 4) {
-      float w[4];
-      if (krem >= 4) { w[0] = __ldg(wp); w[1] = __ldg(wp + N); w[2] = __ldg(wp + 2 * N); w[3] = __ldg(wp + 3 * N); }
+    // the weight column streams from L1 / L2: the four values of step k4 + 1 are requested before the FMAs of step k4 (ncu r2e: 5.7 warps
+    // per issue were waiting on these loads when they were consumed right after being issued)
+    auto load_w = [&](const float* p, int rem, float (&w)[4]) {
+      if (rem >= 4) { w[0] = __ldg(p); w[1] = __ldg(p + N); w[2] = __ldg(p + 2 * N); w[3] = __ldg(p + 3 * N); }
       else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) w[q] = q < krem ? __ldg(wp + (int64_t)q * N) : 0.f;
+        for (int q = 0; q < 4; ++q) w[q] = q < rem ? __ldg(p + (int64_t)q * N) : 0.f;
       }
+    };
+    float wn[4];
+    load_w(wp, krem, wn);
+    for (int k4 = 0; k4 < K4; ++k4, wp += N4, ap += CN_SPB, krem -= 4) {
+      float w[4] = {wn[0], wn[1], wn[2], wn[3]};
+      if (k4 + 1 < K4) load_w(wp + N4, krem - 4, wn);
 #pragma unroll
       for (int s = 0; s < SPG; ++s) {
         const float4 c = ap[s];
