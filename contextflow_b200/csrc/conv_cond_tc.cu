@@ -294,6 +294,11 @@ __device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, int c
   }
 }
 
+// stage-2 geometries known at compile time (see stage2_fixed in the kernel); all in descriptor units of 16 bytes
+struct GeoL1 { static constexpr int P = 1, T2 = 2, KS = 2, ROW_U1 = 4, YS_U = 20 * 4, REGION_U = 368 * 64 / 16, TILE_U = 10 * 64, STAGE_U = 2 * 32 * 64 / 16, DCOLS = 64; };
+struct GeoL2 { static constexpr int P = 1, T2 = 1, KS = 4, ROW_U1 = 8, YS_U = 20 * 8, REGION_U = 208 * 128 / 16, TILE_U = 10 * 128, STAGE_U = 2 * 64 * 128 / 16, DCOLS = 128; };
+struct GeoL3 { static constexpr int P = 2, T2 = 2, KS = 4, ROW_U1 = 8, YS_U = 6 * 8, REGION_U = 256 * 128 / 16, TILE_U = 8 * 128, STAGE_U = 2 * 128 * 128 / 16, DCOLS = 256; };
+
 // PIPE (software-pipelined tiles, one CTA per SM).  A tile's stages are a dependent chain  x0 -> MMA 1 -> epilogue 1 -> MMA 2 -> epilogue 2 ->
 // MMA 3 -> epilogue 3: run back to back, the epilogue warps idle through every MMA stage and the tensor pipe idles through every epilogue
 // (ncu r1: tensor pipe 21 %, issue slots 47 % with two such CTAs per SM).  With PIPE the epilogue warps interleave two tiles,
@@ -526,10 +531,60 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
           }
         }
       };
+      // Stage 2 of a geometry known at compile time (the BASELINE levels): every descriptor is `base + constant`, so the whole stage is one
+      // straight-line block of tcgen05.mma with uniform-register adds in between -- no loop counters, no vector-register descriptor
+      // arithmetic, no R2UR per chunk.  (Measured: the generic issue paths spend ~270 cycles of dependent scalar work per chunk transition,
+      // against ~45 cycles of tensor-pipe time per instruction at N <= 64: tools/umma_probe4.cu.)  The ring protocol is the generic one:
+      // the chunk in slot `st` has been waited for by the previous chunk's issue.
+      auto stage2_fixed = [&](auto geo, auto res, int it) {
+        using G = decltype(geo);
+        constexpr int P_ = G::P, T2_ = G::T2;
+        constexpr bool RES = decltype(res)::value;               // resident weights: the chunk's slot is its index, a constant too
+        const uint64_t ah = ahi_seg0 + ((PIPE && (it & 1)) ? set_u : 0u), al = alo_seg0 + ((PIPE && (it & 1)) ? set_u : 0u);
+        if (RES && !wskip) {                                     // first tile of a resident plan: the W2 chunks are still landing
+          for (int c = 1; c <= 9 * P_; ++c) mbar_wait(bar(BAR_FULL) + 8u * c, 0);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int pn = 0; pn < P_; ++pn) {
+              constexpr int KS_ = G::KS;                         // k-steps per chunk (every panel is full at these shapes)
+              const uint32_t off = (uint32_t)(ky * G::YS_U + kx * G::ROW_U1 + pn * G::REGION_U);
+              const uint64_t bd = RES ? bdesc0 + (uint64_t)((1 + (ky * 3 + kx) * P_ + pn) * G::STAGE_U) : bdesc0 + st * (uint32_t)G::STAGE_U;
+#pragma unroll
+              for (int tt = 0; tt < T2_; ++tt)
+#pragma unroll
+                for (int ks = 0; ks < KS_; ++ks) {
+                  const uint32_t dd = acc_base + tt * G::DCOLS;
+                  mma_k<F16>(dd, ah + (uint64_t)(off + tt * G::TILE_U + 2 * ks), bd + 2 * ks, id2N2, (ky | kx | pn | ks) ? 1u : 0u);
+                  mma_k<F16>(dd + G::DCOLS / 2, al + (uint64_t)(off + tt * G::TILE_U + 2 * ks), bd + 2 * ks, idN2, 1u);
+                }
+              if (!RES) {
+                wait_next(true);
+                tc_commit(bar(BAR_EMPTY) + 8u * st);
+                if (++st == (uint32_t)nst) { st = 0; rphase ^= 1; }
+              }
+            }
+        if (RES) {                                               // the only barrier traffic of a resident stage: the first tile waits for W3's first chunk
+          st = (uint32_t)(9 * P_);                               // last W2 chunk: wait_next looks at the slot after it
+          wait_next(true);
+          st = (uint32_t)(1 + 9 * P_);
+        }
+      };
       using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>; using I4 = std::integral_constant<int, 4>;
       const int s2class = (ks_last != ks_full) ? 0 : (T2 == 1 && ks_full == 4) ? 1 : (T2 == 2 && ks_full == 4) ? 2 : (T2 == 2 && ks_full == 2) ? 3
                           : (T2 == 4 && ks_full == 2) ? 4 : (T2 == 4 && ks_full == 4) ? 5 : 0;
 
+      // compile-time geometries (descriptor units of 16 bytes): the three conv-coupling levels of BASELINE configs[1] at the plans make_plan picks
+      //   L1: Ch 32, 16x16, segments (S 1, NSEG 2, GS 10), 64-byte rows;  L2: Ch 64, 8x8, segments (S 2, GS 10), 128-byte rows;
+      //   L3: Ch 128, 4x4, plain layout (WP 6), two channel panels, 128-byte rows
+      const int s2fixed = (!F16 || KH != 3 || KW != 3 || ks_last != ks_full) ? 0
+          : (SEG && rb == 64 && P == 1 && T2 == 2 && ks_full == 2 && ys_u == GeoL1::YS_U && region_u == GeoL1::REGION_U && tile_u2 == GeoL1::TILE_U && stage_u == GeoL1::STAGE_U && tile_cols2 == GeoL1::DCOLS) ? 1
+          : (SEG && rb == 128 && P == 1 && T2 == 1 && ks_full == 4 && ys_u == GeoL2::YS_U && region_u == GeoL2::REGION_U && stage_u == GeoL2::STAGE_U && tile_cols2 == GeoL2::DCOLS) ? 2
+          : (!SEG && rb == 128 && P == 2 && T2 == 2 && ks_full == 4 && ys_u == GeoL3::YS_U && region_u == GeoL3::REGION_U && tile_u2 == GeoL3::TILE_U && stage_u == GeoL3::STAGE_U && tile_cols2 == GeoL3::DCOLS) ? 3 : 0;
       const int cW3 = nchunks_tile - P;                          // first W3 chunk
       auto use_tile = [&](int it) {                              // operand set of tile `it`
         const uint32_t o = (PIPE && (it & 1)) ? set_u : 0u;
@@ -555,7 +610,10 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
         tick(10);
         uint32_t first_acc = 0;
         uint32_t row_u = 0;                                      // ky * YS rows, in descriptor units
-        if (s2class == 1) stage2_ct(I1{}, I4{});
+        if (s2fixed == 1) { if (resident) stage2_fixed(GeoL1{}, std::true_type{}, it); else stage2_fixed(GeoL1{}, std::false_type{}, it); }
+        else if (s2fixed == 2) stage2_fixed(GeoL2{}, std::false_type{}, it);
+        else if (s2fixed == 3) stage2_fixed(GeoL3{}, std::false_type{}, it);
+        else if (s2class == 1) stage2_ct(I1{}, I4{});
         else if (s2class == 2) stage2_ct(I2{}, I4{});
         else if (s2class == 3) stage2_ct(I2{}, I2{});
         else if (s2class == 4) stage2_ct(std::integral_constant<int, 4>{}, I2{});
