@@ -295,9 +295,12 @@ __device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, int c
 }
 
 // stage-2 geometries known at compile time (see stage2_fixed in the kernel); all in descriptor units of 16 bytes
-struct GeoL1 { static constexpr int P = 1, T2 = 2, KS = 2, ROW_U1 = 4, YS_U = 20 * 4, REGION_U = 368 * 64 / 16, TILE_U = 10 * 64, STAGE_U = 2 * 32 * 64 / 16, DCOLS = 64; };
-struct GeoL2 { static constexpr int P = 1, T2 = 1, KS = 4, ROW_U1 = 8, YS_U = 20 * 8, REGION_U = 208 * 128 / 16, TILE_U = 10 * 128, STAGE_U = 2 * 64 * 128 / 16, DCOLS = 128; };
-struct GeoL3 { static constexpr int P = 2, T2 = 2, KS = 4, ROW_U1 = 8, YS_U = 6 * 8, REGION_U = 256 * 128 / 16, TILE_U = 8 * 128, STAGE_U = 2 * 128 * 128 / 16, DCOLS = 256; };
+struct GeoL1 { static constexpr int P = 1, T2 = 2, KS = 2, ROW_U1 = 4, YS_U = 20 * 4, REGION_U = 368 * 64 / 16, TILE_U = 10 * 64, STAGE_U = 2 * 32 * 64 / 16, DCOLS = 64,
+                                    T1 = 3, KS1 = 1, LIN_U = 8 * 64, DCOLS3 = 32; };
+struct GeoL2 { static constexpr int P = 1, T2 = 1, KS = 4, ROW_U1 = 8, YS_U = 20 * 8, REGION_U = 208 * 128 / 16, TILE_U = 10 * 128, STAGE_U = 2 * 64 * 128 / 16, DCOLS = 128,
+                                    T1 = 2, KS1 = 1, LIN_U = 8 * 128, DCOLS3 = 64; };
+struct GeoL3 { static constexpr int P = 2, T2 = 2, KS = 4, ROW_U1 = 8, YS_U = 6 * 8, REGION_U = 256 * 128 / 16, TILE_U = 8 * 128, STAGE_U = 2 * 128 * 128 / 16, DCOLS = 256,
+                                    T1 = 2, KS1 = 2, LIN_U = 8 * 128, DCOLS3 = 128; };
 
 // PIPE (software-pipelined tiles, one CTA per SM).  A tile's stages are a dependent chain  x0 -> MMA 1 -> epilogue 1 -> MMA 2 -> epilogue 2 ->
 // MMA 3 -> epilogue 3: run back to back, the epilogue warps idle through every MMA stage and the tensor pipe idles through every epilogue
@@ -574,6 +577,49 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
           st = (uint32_t)(1 + 9 * P_);
         }
       };
+      // stages 1 and 3 of the same geometries (1x1 convolutions over plain 128-row tiles)
+      auto stage1_fixed = [&](auto geo, auto res, int it) {
+        using G = decltype(geo);
+        constexpr bool RES = decltype(res)::value;
+        const uint64_t ah = ahi_lin0 + ((PIPE && (it & 1)) ? set_u : 0u), al = alo_lin0 + ((PIPE && (it & 1)) ? set_u : 0u);
+        const uint64_t bd = RES ? bdesc0 : bdesc0 + st * (uint32_t)G::STAGE_U;
+#pragma unroll
+        for (int tt = 0; tt < G::T1; ++tt)
+#pragma unroll
+          for (int ks = 0; ks < G::KS1; ++ks) {
+            const uint32_t dd = acc_base + tt * G::DCOLS;
+            mma_k<F16>(dd, ah + (uint64_t)(tt * G::LIN_U + 2 * ks), bd + 2 * ks, id2N2, ks ? 1u : 0u);
+            mma_k<F16>(dd + G::DCOLS / 2, al + (uint64_t)(tt * G::LIN_U + 2 * ks), bd + 2 * ks, idN2, 1u);
+          }
+        if (!RES) {
+          wait_next(true);
+          tc_commit(bar(BAR_EMPTY) + 8u * st);
+          if (++st == (uint32_t)nst) { st = 0; rphase ^= 1; }
+        } else st = 1;                                           // (stage2_fixed waits for the W2 chunks itself on the first tile)
+      };
+      auto stage3_fixed = [&](auto geo, auto res, int it, bool last_tile) {
+        using G = decltype(geo);
+        constexpr bool RES = decltype(res)::value;
+        const uint64_t ah = ahi_lin0 + ((PIPE && (it & 1)) ? set_u : 0u), al = alo_lin0 + ((PIPE && (it & 1)) ? set_u : 0u);
+#pragma unroll
+        for (int pn = 0; pn < G::P; ++pn) {
+          const uint64_t bd = RES ? bdesc0 + (uint64_t)((1 + 9 * G::P + pn) * G::STAGE_U) : bdesc0 + st * (uint32_t)G::STAGE_U;
+#pragma unroll
+          for (int tt = 0; tt < G::T2; ++tt)
+#pragma unroll
+            for (int ks = 0; ks < G::KS; ++ks) {
+              const uint32_t dd = acc_base + tt * G::DCOLS3;
+              mma_k<F16>(dd, ah + (uint64_t)(pn * G::REGION_U + tt * G::LIN_U + 2 * ks), bd + 2 * ks, id2N3, (pn | ks) ? 1u : 0u);
+              mma_k<F16>(dd + G::DCOLS3 / 2, al + (uint64_t)(pn * G::REGION_U + tt * G::LIN_U + 2 * ks), bd + 2 * ks, idN3, 1u);
+            }
+          if (!RES) {
+            wait_next(!(last_tile && pn == G::P - 1));
+            tc_commit(bar(BAR_EMPTY) + 8u * st);
+            if (++st == (uint32_t)nst) { st = 0; rphase ^= 1; }
+          }
+        }
+        if (RES) st = 0;                                         // resident: the ring holds exactly one tile's chunks
+      };
       using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>; using I4 = std::integral_constant<int, 4>;
       const int s2class = (ks_last != ks_full) ? 0 : (T2 == 1 && ks_full == 4) ? 1 : (T2 == 2 && ks_full == 4) ? 2 : (T2 == 2 && ks_full == 2) ? 3
                           : (T2 == 4 && ks_full == 2) ? 4 : (T2 == 4 && ks_full == 4) ? 5 : 0;
@@ -582,9 +628,9 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
       //   L1: Ch 32, 16x16, segments (S 1, NSEG 2, GS 10), 64-byte rows;  L2: Ch 64, 8x8, segments (S 2, GS 10), 128-byte rows;
       //   L3: Ch 128, 4x4, plain layout (WP 6), two channel panels, 128-byte rows
       const int s2fixed = (!F16 || KH != 3 || KW != 3 || ks_last != ks_full) ? 0
-          : (SEG && rb == 64 && P == 1 && T2 == 2 && ks_full == 2 && ys_u == GeoL1::YS_U && region_u == GeoL1::REGION_U && tile_u2 == GeoL1::TILE_U && stage_u == GeoL1::STAGE_U && tile_cols2 == GeoL1::DCOLS) ? 1
-          : (SEG && rb == 128 && P == 1 && T2 == 1 && ks_full == 4 && ys_u == GeoL2::YS_U && region_u == GeoL2::REGION_U && stage_u == GeoL2::STAGE_U && tile_cols2 == GeoL2::DCOLS) ? 2
-          : (!SEG && rb == 128 && P == 2 && T2 == 2 && ks_full == 4 && ys_u == GeoL3::YS_U && region_u == GeoL3::REGION_U && tile_u2 == GeoL3::TILE_U && stage_u == GeoL3::STAGE_U && tile_cols2 == GeoL3::DCOLS) ? 3 : 0;
+          : (SEG && rb == 64 && P == 1 && T2 == 2 && ks_full == 2 && ys_u == GeoL1::YS_U && region_u == GeoL1::REGION_U && tile_u2 == GeoL1::TILE_U && stage_u == GeoL1::STAGE_U && tile_cols2 == GeoL1::DCOLS && T1 == GeoL1::T1 && KS1 == GeoL1::KS1 && tile_cols3 == GeoL1::DCOLS3) ? 1
+          : (SEG && rb == 128 && P == 1 && T2 == 1 && ks_full == 4 && ys_u == GeoL2::YS_U && region_u == GeoL2::REGION_U && stage_u == GeoL2::STAGE_U && tile_cols2 == GeoL2::DCOLS && T1 == GeoL2::T1 && KS1 == GeoL2::KS1 && tile_cols3 == GeoL2::DCOLS3) ? 2
+          : (!SEG && rb == 128 && P == 2 && T2 == 2 && ks_full == 4 && ys_u == GeoL3::YS_U && region_u == GeoL3::REGION_U && tile_u2 == GeoL3::TILE_U && stage_u == GeoL3::STAGE_U && tile_cols2 == GeoL3::DCOLS && T1 == GeoL3::T1 && KS1 == GeoL3::KS1 && tile_cols3 == GeoL3::DCOLS3) ? 3 : 0;
       const int cW3 = nchunks_tile - P;                          // first W3 chunk
       auto use_tile = [&](int it) {                              // operand set of tile `it`
         const uint32_t o = (PIPE && (it & 1)) ? set_u : 0u;
@@ -597,7 +643,10 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
         mbar_wait(bar(BAR_AREADY), it & 1);
         tc_fence_after();
         tick(10);
-        issue_chunk(ahi_lin, alo_lin, lin_u, tile_cols2, T1, KS1, id2N2, idN2, 0, true);
+        if (s2fixed == 1) { if (resident) stage1_fixed(GeoL1{}, std::true_type{}, it); else stage1_fixed(GeoL1{}, std::false_type{}, it); }
+        else if (s2fixed == 2) stage1_fixed(GeoL2{}, std::false_type{}, it);
+        else if (s2fixed == 3) stage1_fixed(GeoL3{}, std::false_type{}, it);
+        else issue_chunk(ahi_lin, alo_lin, lin_u, tile_cols2, T1, KS1, id2N2, idN2, 0, true);
         tc_commit(bar(BAR_ACC1));
         tick(9);
       };
@@ -641,6 +690,10 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
         tc_fence_after();
         tick(10);
         uint32_t pan_u = 0;
+        if (s2fixed == 1) { if (resident) stage3_fixed(GeoL1{}, std::true_type{}, it, last_tile); else stage3_fixed(GeoL1{}, std::false_type{}, it, last_tile); }
+        else if (s2fixed == 2) stage3_fixed(GeoL2{}, std::false_type{}, it, last_tile);
+        else if (s2fixed == 3) stage3_fixed(GeoL3{}, std::false_type{}, it, last_tile);
+        else
         for (int pn = 0; pn < P; ++pn, pan_u += region_u)
           issue_chunk(ahi_lin + pan_u, alo_lin + pan_u, lin_u, tile_cols3, T2, pn == P - 1 ? ks_last : ks_full, id2N3, idN3, pn > 0,
                       !(last_tile && pn == P - 1));
@@ -711,7 +764,7 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
         }
       }
       if (a.z != nullptr && a.add != nullptr) {                // fused coupling: b3 + CN(c) of this tile's samples (read by epilogue 3, ordered by the barrier chain)
-        float* sadd = reinterpret_cast<float*>(base + p.off_add);
+        float* sadd = reinterpret_cast<float*>(base + p.off_add) + ((PIPE && (it & 1)) ? p.S * p.N3 : 0);
         for (int i = tid; i < nS * p.N3; i += kEpiThreads) {
           const int s_ = i / p.N3, c_ = i - s_ * p.N3;
           sadd[i] = c_ < p.Cout ? sb3[c_] + __ldg(a.add + (size_t)(b0 + s_) * p.Cout + c_) : 0.f;
@@ -824,7 +877,7 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
           tmem_ld_wait();
           if (valid) {
             float* zd = a.z + (bb * p.Cout + k0) * HW + pix;
-            const float* ob = a.add ? reinterpret_cast<const float*>(base + p.off_add) + s * p.N3 : sb3;   // output bias: b3 (+ CN(c) of the sample)
+            const float* ob = a.add ? reinterpret_cast<const float*>(base + p.off_add) + ((PIPE && (it & 1)) ? p.S * p.N3 : 0) + s * p.N3 : sb3;   // output bias: b3 (+ CN(c) of the sample)
             float lsum = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -1000,7 +1053,7 @@ static bool make_plan_occ(Plan& p, double& waste_out, int occ, int pipe, int B, 
       const int xbytes = (S * Cin * HW * 4 + 127) / 128 * 128;
       const int tab_bytes = (q.R + q.T2 * 128) * 4;
       const int ls_bytes = epi_warps(occ) / 4 * q.T2 * 128 * 4;          // per (epilogue group, accumulator row) log-scale partials of the fused coupling
-      const int add_bytes = S * q.N3 * 4;
+      const int add_bytes = (pipe ? 2 : 1) * S * q.N3 * 4;                 // PIPE: one per tile parity (stepX of tile i+1 runs before epilogue 3 of tile i)
       const int fixed = q.off_ring + xbytes + bias_bytes + tab_bytes + ls_bytes + add_bytes + bar_bytes + 256;
       int nst = (kSmemMax - fixed) / q.stage_bytes;
       if (nst < 2) break;
@@ -1034,14 +1087,15 @@ static bool make_plan_occ(Plan& p, double& waste_out, int occ, int pipe, int B, 
 }
 
 // CFPP_TC_OCC = 1 / 2 forces the residency; default: two CTAs per SM when such a plan exists and wastes at most 30 % more MMA rows.
-// CFPP_TC_PIPE = 1 turns the software-pipelined form on (one CTA per SM) whenever the shape has such a plan (fp16 kind)
+// CFPP_TC_PIPE = 0 turns the software-pipelined form off; default: used (one CTA per SM) whenever the shape has such a plan (fp16 kind)
+// -- since the straight-line issue paths it is ahead of two resident CTAs at the 16x16 and 8x8 levels (0.217 / 0.144 ms against 0.240 / 0.147)
 // and it wastes at most 30 % more MMA rows than the best unpipelined plan.
 static bool make_plan(Plan& p, int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, long long x_bstride, int sms) {
   const int force = env_int("CFPP_TC_OCC", 0);
   Plan p1, p2, pp; double w1 = 0, w2 = 0, wp = 0;
   const bool ok1 = force != 2 && make_plan_occ(p1, w1, 1, 0, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, sms);
   const bool ok2 = force != 1 && make_plan_occ(p2, w2, 2, 0, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, sms);
-  const bool okp = force != 2 && tc_kind() == 1 && env_int("CFPP_TC_PIPE", 0) && make_plan_occ(pp, wp, 1, 1, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, sms);
+  const bool okp = force != 2 && tc_kind() == 1 && env_int("CFPP_TC_PIPE", 1) && make_plan_occ(pp, wp, 1, 1, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, sms);
   if (okp) {
     const double wbest = ok1 && ok2 ? (w1 < w2 ? w1 : w2) : ok1 ? w1 : ok2 ? w2 : wp;
     if (wp <= 1.3 * wbest) { p = pp; return true; }

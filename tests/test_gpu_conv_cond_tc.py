@@ -141,3 +141,36 @@ def test_tc_fused_coupling_matches_fp64(B, C, H, W, ctx):
     from tests.helpers import L_ATOL, L_RTOL, Z_ATOL, Z_RTOL, assert_close
     assert_close(z.cpu().numpy(), want_z.numpy(), Z_RTOL, Z_ATOL * max(1.0, float(want_z.abs().max())), 'fused coupling z')
     assert_close(ldj.cpu().numpy(), want_l.numpy(), L_RTOL, L_ATOL, 'fused coupling ldj')
+
+
+@pytest.mark.parametrize('env', [{'CFPP_TC_PIPE': '0'}, {'CFPP_TC_PIPE': '1'}, {'CFPP_TC_PIPE': '0', 'CFPP_TC_OCC': '1'}])
+@pytest.mark.parametrize('B,C,H,W', [(700, 16, 16, 16), (1300, 32, 8, 8), (2200, 64, 4, 4)])
+def test_tc_fused_coupling_every_plan_form_with_several_tiles_per_cta(B, C, H, W, env, monkeypatch):
+    """Every CTA walks several tiles (ntiles > 2 x 148), so the software-pipelined form (tile i+1's operand set and per-sample
+    bias staged before tile i's last epilogue) and the two-resident-CTA form are each compared with fp64 (coupling.py:39-66)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cin, ch = C // 2, 2 * C
+    tag = f'tcp{B}.{C}.{H}.{W}'
+    w1, b1, w2, b2, w3, b3 = _weights(tag, cin, ch, C, 3, 3)
+    x = synth.uniform(tag + 'x', (B, C, H, W)) * 2.0 - 1.0
+    add = synth.uniform(tag + 'a', (B, C)) - 0.5
+    lp = synth.uniform(tag + 'l', (B,))
+    pack = ops.conv_cond_tc_pack(w1.to(dev), w2.to(dev), w3.to(dev), cin)
+    out = ops.conv_cond_tc_coupling(x.to(dev), pack, b1.to(dev), b2.to(dev), b3.to(dev), ch, 3, 3, add=add.to(dev), logp_c=lp.to(dev), logp_scale=float(H * W))
+    assert out is not None
+    z, ldj = out
+    h = _ref64(x[:, :cin], w1, b1, w2, b2, w3, b3) + add.double()[:, :, None, None]
+    t, r = h[:, :cin], h[:, cin:]
+    ls = 2 * torch.tanh(r / 2)
+    want_z = torch.cat([x[:, :cin].double(), x[:, cin:].double() * torch.exp(ls) + t], 1)
+    want_l = ls.sum((1, 2, 3)) + lp.double() * H * W
+    assert torch.equal(z[:, :cin].cpu(), x[:, :cin])
+    from tests.helpers import L_ATOL, L_RTOL, Z_ATOL, Z_RTOL, assert_close
+    assert_close(z.cpu().numpy(), want_z.numpy(), Z_RTOL, Z_ATOL * max(1.0, float(want_z.abs().max())), 'fused coupling z')
+    assert_close(ldj.cpu().numpy(), want_l.numpy(), L_RTOL, L_ATOL, 'fused coupling ldj')
+    # the unfused conditioner under the same plan form
+    hh = ops.conv_cond_tc(x[:, :cin].contiguous().to(dev), cin, pack, b1.to(dev), b2.to(dev), b3.to(dev), ch, H, W, 3, 3, C)
+    if hh is not None:
+        want_h = _ref64(x[:, :cin], w1, b1, w2, b2, w3, b3)
+        assert_close(hh.cpu().numpy(), want_h.numpy(), Z_RTOL, Z_ATOL * max(1.0, float(want_h.abs().max())), 'conditioner h')
