@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libcfpp.so')
+LIB_PATH = os.environ.get('CFPP_LIB') or os.path.join(_HERE, 'libcfpp.so')   # CFPP_LIB: an experimental build of the same sources (tools/ A/B runs)
 
 MAX_CTX = 8
 ENC_MAXC = 64

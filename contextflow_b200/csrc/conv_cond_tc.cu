@@ -61,7 +61,10 @@ struct Plan {
 // OCC = CTAs resident per SM.  OCC 1: one CTA owns the SM (12 epilogue warps, 512 TMEM columns, ~226 KB).  OCC 2: two CTAs with half
 // the shared memory and TMEM columns each (8 epilogue warps): a tile's stages are serial inside a CTA (MMA -> epilogue -> MMA ...),
 // so a second resident CTA lets the tensor pipe work on its tile while this one's epilogue warps transform accumulators.
-__host__ __device__ constexpr int epi_warps(int occ) { return occ == 1 ? 12 : 8; }   // multiple of 4: a warp reaches TMEM lanes 32*(warp%4) .. +31 only
+#ifndef CFPP_TC_EPI1
+#define CFPP_TC_EPI1 16   // epilogue warps of the one-CTA-per-SM kernels
+#endif
+__host__ __device__ constexpr int epi_warps(int occ) { return occ == 1 ? CFPP_TC_EPI1 : 8; }   // multiple of 4: a warp reaches TMEM lanes 32*(warp%4) .. +31 only
 __host__ __device__ constexpr int cta_threads(int occ) { return (epi_warps(occ) + 2) * 32; }
 constexpr int kMaxStages = 12;                 // ring slots; when every weight chunk of a tile fits (<= 12 chunks) the weights stay resident
 
