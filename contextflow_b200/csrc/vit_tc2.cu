@@ -13,6 +13,7 @@
 //     GEMMs and the next LayerNorm) and published with a named barrier of the compute threads.
 // LayerNorm / bias rows of the current layer are staged in shared memory once per layer.
 #include "vit_tc_helpers.cuh"
+#include <cstdlib>
 
 namespace cfpp {
 namespace vt2 {
@@ -348,6 +349,431 @@ static int stages_for(int T, int P, int xrows) {
   return (int)(n > kMaxStages ? kMaxStages : n);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// Four threads per token row (the layout of vit_tc4 in vit_tc.cu, for T <= 192 and up to 64 tokens per sample).  The kernel above keeps a
+// whole row in ONE thread -- 4 compute warps per SM, one per scheduler, nothing to switch to while a TMEM load or the MMA round trip is
+// outstanding (cfg3: 0.02-0.03 of the tensor peak, 85 % of the step).  Here 16 compute warps share the tile: warp w serves TMEM lane quadrant
+// w % 4 and column group g = w / 4, i.e. columns 16 g .. +15 of EVERY 64-wide chunk; the residual stream shrinks to P x 16 registers per
+// thread (no row buffer in shared memory), row-wide sums cross the four column groups through shared memory under a per-quadrant named
+// barrier, q rows are staged in shared memory, k / v rows in operand panels 1-2 (free between the q,k,v GEMM and the next LayerNorm), the
+// attention scores in operand panel 0 (free until the attention output is written there; one CTA-wide barrier separates the two uses).
+// Weight stream, MMA issue order and the fp16 hi / scaled-lo arithmetic are those of the kernel above: the two are interchangeable.
+constexpr int kCG = 4, kCW = kW / kCG;
+constexpr int kThreads5 = (4 * kCG + 2) * 32;
+constexpr int kQStride = 68;
+
+__device__ __forceinline__ uint64_t pack2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ uint64_t splat2(float a) { return pack2(a, a); }
+
+__device__ __forceinline__ void compute_sync5() { asm volatile("bar.sync 1, 512;" ::: "memory"); }                 // the 512 compute threads
+__device__ __forceinline__ void quad_sync5(int quad) { asm volatile("bar.sync %0, 128;" ::"r"(2 + quad) : "memory"); }   // the four warps of a lane quadrant
+
+// sum of `v` over the four column-group threads of row r; `red` = this call's [kCG][kRows] table (callers alternate two tables)
+__device__ __forceinline__ float row_sum5(float v, float* red, int r, int g, int quad) {
+  red[g * kRows + r] = v;
+  quad_sync5(quad);
+  return (red[r] + red[kRows + r]) + (red[2 * kRows + r] + red[3 * kRows + r]);
+}
+// (hi, lo') fp16 pairs of two values in packed arithmetic
+__device__ __forceinline__ void f16_split2p(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const float ha = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), hb = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+  float la, lb;
+  unpack2(fmul2(fsub2(pack2(a, b), pack2(ha, hb)), splat2(kLoScale)), la, lb);
+  hi = pack_f16x2_sat(ha, hb);
+  lo = pack_f16x2_sat(la, lb);
+}
+// the thread's 16 channels of operand row `row` of one panel (two 16-byte pieces of the hi / lo images)
+__device__ __forceinline__ void store_operand16(uint8_t* a_hi, uint8_t* a_lo, int row, int g, const float (&v)[kCW]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f16_split2p(v[8 * c + 2 * q], v[8 * c + 2 * q + 1], h[q], l[q]);
+    const uint32_t off = (uint32_t)row * 128u + (uint32_t)((((2 * g + c) ^ row) & 7) << 4);
+    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+// the thread's 16 columns of its accumulator row of one output chunk: main block + 2^-11 * cross block
+__device__ __forceinline__ void load_acc16(uint32_t taddr, int g, float (&o)[kCW]) {
+  float v[16], u[16];
+  tmem_ld16(taddr + kCW * g, v);
+  tmem_ld16(taddr + kW + kCW * g, u);
+  tmem_ld_wait();
+  const uint64_t k2 = splat2(kLoInv);
+#pragma unroll
+  for (int i = 0; i < kCW; i += 2) unpack2(ffma2(pack2(u[i], u[i + 1]), k2, pack2(v[i], v[i + 1])), o[i], o[i + 1]);
+}
+// GELU (erf form) of a pair: erf_as with the polynomial in packed arithmetic
+__device__ __forceinline__ void gelu2(float u0, float u1, float& o0, float& o1) {
+  const uint64_t u = pack2(u0, u1);
+  float t0, t1;
+  unpack2(fmul2(u, splat2(0.70710678118654752440f)), t0, t1);
+  const float a0 = fabsf(t0), a1 = fabsf(t1);
+  const uint64_t ax = pack2(a0, a1);
+  float d0, d1;
+  unpack2(ffma2(splat2(0.3275911f), ax, splat2(1.0f)), d0, d1);
+  const uint64_t t = pack2(__fdividef(1.0f, d0), __fdividef(1.0f, d1));
+  uint64_t p = ffma2(t, splat2(1.061405429f), splat2(-1.453152027f));
+  p = ffma2(t, p, splat2(1.421413741f));
+  p = ffma2(t, p, splat2(-0.284496736f));
+  p = ffma2(t, p, splat2(0.254829592f));
+  p = fmul2(t, p);
+  float e0, e1;
+  unpack2(fmul2(ax, ax), e0, e1);
+  float r0, r1;
+  unpack2(fsub2(splat2(1.0f), fmul2(p, pack2(__expf(-e0), __expf(-e1)))), r0, r1);
+  r0 = copysignf(r0, t0); r1 = copysignf(r1, t1);
+  const uint64_t hu = fmul2(u, splat2(0.5f));
+  unpack2(ffma2(hu, pack2(r0, r1), hu), o0, o1);
+}
+
+enum { G_LN0W = 0, G_LN0B, G_PEB, G_LN1W, G_LN1B, G_LNFW, G_LNFB, G_ROWS };
+
+template <int P>
+__global__ void __launch_bounds__(kThreads5, 1) vit_tc5_kernel(const Args a) {
+  extern __shared__ __align__(1024) uint8_t vt5_smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(vt5_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  constexpr int PW = P * kW;
+  uint8_t* ops = base;                                        // kPanels x [hi 128 rows x 128 B][lo]
+  uint8_t* ring = ops + kPanels * kPanelBytes;                // nstages x kChunkBytes
+  const int kStages = a.nstages;
+  float* Qs = reinterpret_cast<float*>(ring + kStages * kChunkBytes);      // [128][kQStride]
+  float* red2 = Qs + kRows * kQStride;                        // [2][kCG][128] row-reduction partials
+  float* lprm = red2 + 2 * kCG * kRows;                       // [6][PW]: lna_w lna_b lnf_w lnf_b b1 b2 of the current layer, zero padded
+  float* gprm = lprm + 6 * PW;                                // [G_ROWS][PW]: ln0 w/b (patch_dim wide), pe_b, ln1 w/b, final norm w/b
+  int* foff_in = reinterpret_cast<int*>(gprm + G_ROWS * PW);  // [PW] feature part of the patchify offset; -1 beyond patch_dim
+  int* foff_out = foff_in + PW;                               // [PW] the same for the output h; -1 beyond T
+  const uint32_t bars = smem_u32(foff_out + PW);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(foff_out + PW) + 2 * BAR_COUNT;
+  float* Sc = reinterpret_cast<float*>(ops);                  // [128][64] attention scores, aliases operand panel 0; column j of row r sits at j ^ (r & 31)
+  float* Ks = reinterpret_cast<float*>(ops + 1 * kPanelBytes);             // [128][64] fp32, aliases operand panel 1
+  float* Vs = reinterpret_cast<float*>(ops + 2 * kPanelBytes);             // aliases operand panel 2
+  auto bar = [&](int i) { return bars + 8u * i; };
+  const cfpp_vit_desc& d = a.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = d.T, ntok = d.n_tok, depth = d.depth, PD = a.PD;
+  constexpr int kMmaWarp = 4 * kCG, kProdWarp = 4 * kCG + 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(bar(BAR_FULL + i), 1); mbar_init(bar(BAR_EMPTY + i), 1); }
+    mbar_init(bar(BAR_AREADY), kRows * kCG); mbar_init(bar(BAR_ACC), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int idx = tid; idx < G_ROWS * PW; idx += kThreads5) {
+    const int row = idx / PW, i = idx - row * PW;
+    const float* src = row == G_LN0W ? d.ln0_w : row == G_LN0B ? d.ln0_b : row == G_PEB ? d.pe_b : row == G_LN1W ? d.ln1_w : row == G_LN1B ? d.ln1_b
+                     : row == G_LNFW ? d.lnf_w : d.lnf_b;
+    const int n = row <= G_LN0B ? d.patch_dim : T;
+    gprm[idx] = i < n ? __ldg(src + i) : 0.f;
+  }
+  {   // 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' and its inverse: offset = token part + feature part; the feature parts as tables
+    const int HW_ = d.H * d.W, Cout_ = T / (d.p1 * d.p2);
+    for (int f = tid; f < PW; f += kThreads5) {
+      int oi = -1, oo = -1;
+      if (f < d.patch_dim) { const int c = f % d.Cin, pp = f / d.Cin, ii = pp / d.p2, j = pp - ii * d.p2; oi = c * HW_ + ii * d.W + j; }
+      if (f < T) { const int c = f % Cout_, pp = f / Cout_, ii = pp / d.p2, j = pp - ii * d.p2; oo = c * HW_ + ii * d.W + j; }
+      foff_in[f] = oi; foff_out[f] = oo;
+    }
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int chunks_per_tile = P * PD + depth * (3 * P + P + 2 * P * P);
+  const int my_tiles = (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == kProdWarp) {
+    if (elect_one()) {
+      uint32_t st = 0, ph = 0;
+      for (int it = 0; it < my_tiles; ++it)
+        for (int c = 0; c < chunks_per_tile; ++c) {
+          mbar_wait(bar(BAR_EMPTY + st), ph ^ 1);
+          mbar_expect_tx(bar(BAR_FULL + st), kChunkBytes);
+          bulk_g2s(smem_u32(ring + (size_t)st * kChunkBytes), a.wpack + (size_t)c * kChunkBytes, kChunkBytes, bar(BAR_FULL + st));
+          if (++st == (uint32_t)kStages) { st = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == kMmaWarp) {
+    if (elect_one()) {
+      const uint32_t id128 = make_idesc(2 * kW), id64 = make_idesc(kW);
+      const uint64_t a0 = make_desc(smem_u32(ops)), b0 = make_desc(smem_u32(ring));
+      uint32_t st = 0, ph = 0, na = 0;
+      auto gemm = [&](int NC, int PK) {                          // NC output chunks x PK operand panels
+        mbar_wait(bar(BAR_AREADY), na & 1); ++na;
+        tc_fence_after();
+        for (int n = 0; n < NC; ++n)
+          for (int p = 0; p < PK; ++p) {
+            mbar_wait(bar(BAR_FULL + st), ph);
+            tc_fence_after();
+            const uint64_t bd = b0 + (uint64_t)(st * (kChunkBytes >> 4));
+            const uint64_t ah = a0 + (uint64_t)(p * (kPanelBytes >> 4)), al = ah + (uint64_t)((kRows * 128) >> 4);
+            const uint32_t dd = tmem + n * 2 * kW;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              mma_f16(dd, ah + 2 * ks, bd + 2 * ks, id128, (p | ks) ? 1u : 0u);
+              mma_f16(dd + kW, al + 2 * ks, bd + 2 * ks, id64, 1u);
+            }
+            tc_commit(bar(BAR_EMPTY + st));
+            if (++st == (uint32_t)kStages) { st = 0; ph ^= 1; }
+          }
+        tc_commit(bar(BAR_ACC));
+      };
+      for (int it = 0; it < my_tiles; ++it) {
+        gemm(P, PD);
+        for (int l = 0; l < depth; ++l) { gemm(3, P); gemm(P, 1); gemm(P, P); gemm(P, P); }
+      }
+    }
+  } else {
+    // ===================== compute threads: (row, column group) =====================
+    const int quad = warp & 3, g = warp >> 2;
+    const int r = quad * 32 + lane, c0 = kCW * g;
+    const int HW = d.H * d.W, tw = d.W / d.p2, Cout = T / (d.p1 * d.p2);
+    const int64_t lstride = 4 * (int64_t)T + (int64_t)T * 192 + 64 * (int64_t)a.NPT + 2 * (int64_t)T * a.NPT + 2 * (int64_t)a.NPT;
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
+    uint32_t nacc = 0;
+    int flip = 0;
+    auto a_ready = [&]() { fence_async_smem(); mbar_arrive(bar(BAR_AREADY)); };
+    auto acc_wait = [&]() { mbar_wait(bar(BAR_ACC), nacc & 1); ++nacc; tc_fence_after(); };
+    auto op_hi = [&](int p) { return ops + p * kPanelBytes; };
+    auto op_lo = [&](int p) { return ops + p * kPanelBytes + kRows * 128; };
+    // LayerNorm statistics over the first n entries of the row (entries beyond n are zero: they add (PW - n) mean^2 to the centred sum)
+    auto ln_stats5 = [&](const float (&x)[P][kCW], int n, float& mean, float& rstd) {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < P; ++c)
+#pragma unroll
+        for (int i = 0; i < kCW; i += 2) { s0 += x[c][i]; s1 += x[c][i + 1]; }
+      mean = row_sum5(s0 + s1, red2 + (flip & 1) * kCG * kRows, r, g, quad) / (float)n; ++flip;
+      float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < P; ++c)
+#pragma unroll
+        for (int i = 0; i < kCW; i += 2) { const float d0 = x[c][i] - mean, d1 = x[c][i + 1] - mean; v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); }
+      const float ss = row_sum5(v0 + v1, red2 + (flip & 1) * kCG * kRows, r, g, quad); ++flip;
+      const float var = fmaxf(ss - (float)(PW - n) * mean * mean, 0.f) / (float)n;
+      rstd = rsqrtf(var + 1e-5f);
+    };
+    // one chunk of the normalised row: out = (x - mean) rstd w + b (w, b rows zero beyond the live width: so is out)
+    auto ln_chunk = [&](const float (&x)[kCW], float (&out)[kCW], float mean, float rstd, const float* w, const float* b) {
+      const uint64_t m2 = splat2(mean), r2 = splat2(rstd);
+#pragma unroll
+      for (int i = 0; i < kCW; i += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w + i), b4 = *reinterpret_cast<const float4*>(b + i);
+        unpack2(ffma2(fmul2(fsub2(pack2(x[i], x[i + 1]), m2), r2), pack2(w4.x, w4.y), pack2(b4.x, b4.y)), out[i], out[i + 1]);
+        unpack2(ffma2(fmul2(fsub2(pack2(x[i + 2], x[i + 3]), m2), r2), pack2(w4.z, w4.w), pack2(b4.z, b4.w)), out[i + 2], out[i + 3]);
+      }
+    };
+    // LayerNorm(n) of the row -> operand panels 0 .. np-1
+    auto ln_to_operands = [&](const float (&x)[P][kCW], int n, int np, const float* w, const float* b) {
+      float mean, rstd;
+      ln_stats5(x, n, mean, rstd);
+#pragma unroll
+      for (int c = 0; c < P; ++c)
+        if (c < np) {
+          float y[kCW];
+          ln_chunk(x[c], y, mean, rstd, w + kW * c + c0, b + kW * c + c0);
+          store_operand16(op_hi(c), op_lo(c), r, g, y);
+        }
+    };
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b0 = tile * a.S;
+      const int s = r / ntok, tok = r - s * ntok;
+      const bool live = r < a.S * ntok && b0 + s < a.B;
+      const int th = tok / tw, tww = tok - th * tw;
+      const int tokoff = th * d.p1 * d.W + tww * d.p2;
+      float x[P][kCW];                                           // invariant: entries beyond the live width are zero
+      // ---- patchify, LayerNorm(patch_dim) -> operands, Linear, + bias, LayerNorm(T), + positional embedding ----
+      {
+        const float* xs = a.x + (int64_t)(b0 + s) * a.x_bstride + tokoff;
+#pragma unroll
+        for (int c = 0; c < P; ++c)
+#pragma unroll
+          for (int i = 0; i < kCW; ++i) { const int o = foff_in[kW * c + c0 + i]; x[c][i] = (live && o >= 0) ? __ldg(xs + o) : 0.f; }
+      }
+      ln_to_operands(x, d.patch_dim, PD, gprm + G_LN0W * PW, gprm + G_LN0B * PW);
+      a_ready();
+      acc_wait();
+#pragma unroll
+      for (int c = 0; c < P; ++c) {
+        load_acc16(trow + c * 2 * kW, g, x[c]);
+        const float* pb = gprm + G_PEB * PW + kW * c + c0;
+#pragma unroll
+        for (int i = 0; i < kCW; ++i) x[c][i] += pb[i];
+      }
+      tc_fence_before();
+      {
+        float mean, rstd;
+        ln_stats5(x, T, mean, rstd);
+#pragma unroll
+        for (int c = 0; c < P; ++c) {
+          ln_chunk(x[c], x[c], mean, rstd, gprm + G_LN1W * PW + kW * c + c0, gprm + G_LN1B * PW + kW * c + c0);
+#pragma unroll
+          for (int i = 0; i < kCW; ++i) { const int col = kW * c + c0 + i; if (col < T) x[c][i] += __ldg(d.pos + tok * T + col); }
+        }
+      }
+
+      for (int l = 0; l < depth; ++l) {
+        // ---- this layer's LayerNorm / bias rows -> shared memory ----
+        compute_sync5();                                             // everyone is done with the previous layer's rows
+        {
+          const float* Lp = d.layers + l * lstride;
+          const float* lnf = Lp + 2 * T + (int64_t)T * 192 + 64 * (int64_t)a.NPT;
+          const float* b1 = lnf + 2 * T + (int64_t)T * a.NPT;
+          const float* b2 = b1 + a.NPT + (int64_t)T * a.NPT;
+          for (int idx = g * kRows + r; idx < 6 * PW; idx += kRows * kCG) {
+            const int k = idx / PW, i = idx - k * PW;
+            const float* src = k == 0 ? Lp : k == 1 ? Lp + T : k == 2 ? lnf : k == 3 ? lnf + T : k == 4 ? b1 : b2;
+            lprm[idx] = i < T ? __ldg(src + i) : 0.f;
+          }
+        }
+        compute_sync5();
+        // ---- attention: x += Wo softmax(q k^T / 8) v ----
+        ln_to_operands(x, T, P, lprm, lprm + PW);
+        a_ready();
+        acc_wait();
+        {
+          float t16[kCW];
+          load_acc16(trow + 2 * kW, g, t16);                        // k: 16-byte piece q of row r is stored at position q ^ (r % 16) (see the kernel above)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(Ks + r * kW + 4 * ((4 * g + q) ^ (r & 15))) = make_float4(t16[4 * q], t16[4 * q + 1], t16[4 * q + 2], t16[4 * q + 3]);
+          load_acc16(trow + 4 * kW, g, t16);                        // v
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(Vs + r * kW + 4 * ((4 * g + q) ^ (r & 15))) = make_float4(t16[4 * q], t16[4 * q + 1], t16[4 * q + 2], t16[4 * q + 3]);
+          load_acc16(trow, g, t16);                                 // q
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(Qs + r * kQStride + c0 + 4 * q) = make_float4(t16[4 * q], t16[4 * q + 1], t16[4 * q + 2], t16[4 * q + 3]);
+        }
+        tc_fence_before();
+        compute_sync5();                                            // keys / values of the sample may be rows of other quadrants
+        const int r0 = r - tok;
+        if (live)
+          for (int j = g; j < ntok; j += kCG) {                     // full-width scores of the keys this column group owns
+            const int rj = r0 + j, sw = rj & 15;
+            const float* qr = Qs + r * kQStride;
+            const float* kr = Ks + rj * kW;
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const float4 q4 = *reinterpret_cast<const float4*>(qr + 4 * q), k4 = *reinterpret_cast<const float4*>(kr + 4 * (q ^ sw));
+              d0 = fmaf(q4.x, k4.x, d0); d1 = fmaf(q4.y, k4.y, d1); d2 = fmaf(q4.z, k4.z, d2); d3 = fmaf(q4.w, k4.w, d3);
+            }
+            Sc[r * kW + (j ^ (r & 31))] = ((d0 + d1) + (d2 + d3)) * 0.125f;   // dim_head ** -0.5
+          }
+        quad_sync5(quad);                                           // the scores of a row are written and read by its own four threads
+        float o[kCW];
+#pragma unroll
+        for (int i = 0; i < kCW; ++i) o[i] = 0.f;
+        if (live) {
+          const float* sr = Sc + r * kW;
+          const int sx = r & 31;
+          float mx = -INFINITY;
+          for (int j = 0; j < ntok; ++j) mx = fmaxf(mx, sr[j ^ sx]);
+          float den = 0.f;
+          for (int j = 0; j < ntok; ++j) {
+            const float pj = __expf(sr[j ^ sx] - mx);
+            den += pj;
+            const int rj = r0 + j, sw = rj & 15;
+            const float* vr = Vs + rj * kW;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 v4 = *reinterpret_cast<const float4*>(vr + 4 * ((4 * g + q) ^ sw));
+              o[4 * q] = fmaf(pj, v4.x, o[4 * q]); o[4 * q + 1] = fmaf(pj, v4.y, o[4 * q + 1]);
+              o[4 * q + 2] = fmaf(pj, v4.z, o[4 * q + 2]); o[4 * q + 3] = fmaf(pj, v4.w, o[4 * q + 3]);
+            }
+          }
+          const float inv = 1.0f / den;
+#pragma unroll
+          for (int i = 0; i < kCW; ++i) o[i] *= inv;
+        }
+        compute_sync5();                                            // every score has been read: panel 0 takes the attention output
+        store_operand16(op_hi(0), op_lo(0), r, g, o);
+        a_ready();
+        acc_wait();                                                  // (all compute threads have arrived: nobody still reads k / v)
+#pragma unroll
+        for (int c = 0; c < P; ++c) {
+          float y[kCW];
+          load_acc16(trow + c * 2 * kW, g, y);
+#pragma unroll
+          for (int i = 0; i < kCW; i += 2) unpack2(fadd2(pack2(x[c][i], x[c][i + 1]), pack2(y[i], y[i + 1])), x[c][i], x[c][i + 1]);
+        }
+        tc_fence_before();
+        // ---- MLP: x += W2 gelu(W1 LN(x) + b1) + b2 ----
+        ln_to_operands(x, T, P, lprm + 2 * PW, lprm + 3 * PW);
+        a_ready();
+        acc_wait();
+#pragma unroll
+        for (int c = 0; c < P; ++c) {
+          float y[kCW];
+          load_acc16(trow + c * 2 * kW, g, y);
+          const float* pb1 = lprm + 4 * PW + kW * c + c0;
+#pragma unroll
+          for (int i = 0; i < kCW; i += 2) gelu2(y[i] + pb1[i], y[i + 1] + pb1[i + 1], y[i], y[i + 1]);
+          store_operand16(op_hi(c), op_lo(c), r, g, y);              // hidden chunk c = operand panel c of the second MLP layer
+        }
+        tc_fence_before();
+        a_ready();
+        acc_wait();
+#pragma unroll
+        for (int c = 0; c < P; ++c) {
+          float y[kCW];
+          load_acc16(trow + c * 2 * kW, g, y);
+          const float* pb2 = lprm + 5 * PW + kW * c + c0;
+#pragma unroll
+          for (int i = 0; i < kCW; i += 2)
+            unpack2(fadd2(pack2(x[c][i], x[c][i + 1]), fadd2(pack2(y[i], y[i + 1]), pack2(pb2[i], pb2[i + 1]))), x[c][i], x[c][i + 1]);
+        }
+        tc_fence_before();
+      }
+      // ---- final LayerNorm, un-patchify 'b (h w) (p1 p2 c) -> b c (h p1) (w p2)' ----
+      {
+        float mean, rstd;
+        ln_stats5(x, T, mean, rstd);
+        float* hs = a.h + (int64_t)(b0 + s) * Cout * HW + tokoff;
+#pragma unroll
+        for (int c = 0; c < P; ++c) {
+          float y[kCW];
+          ln_chunk(x[c], y, mean, rstd, gprm + G_LNFW * PW + kW * c + c0, gprm + G_LNFB * PW + kW * c + c0);
+          if (live) {
+#pragma unroll
+            for (int i = 0; i < kCW; ++i) { const int o = foff_out[kW * c + c0 + i]; if (o >= 0) hs[o] = y[i]; }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+static size_t fixed_bytes5(int P) {
+  const size_t PW = (size_t)P * kW;
+  return 1024 + (size_t)kPanels * kPanelBytes + (size_t)kRows * kQStride * 4 + (size_t)2 * kCG * kRows * 4 + (6 + G_ROWS) * PW * 4 + 2 * PW * 4 + BAR_COUNT * 8 + 64;
+}
+static int stages_for5(int P) {
+  const long long left = 227LL * 1024 - (long long)fixed_bytes5(P);
+  long long n = left / kChunkBytes;
+  return (int)(n > kMaxStages ? kMaxStages : n);
+}
+// the four-threads-per-row kernel covers up to 64 tokens per sample (score table in operand panel 0); CFPP_VIT_TC2_V1=1 keeps the kernel above (A/B timing)
+static bool use_tc5(int n_tok) {
+  const char* e = getenv("CFPP_VIT_TC2_V1");                   // read per call: the tests compare the two kernels in one process
+  return !(e && *e == '1') && n_tok <= 64;
+}
+
 }  // namespace vt2
 }  // namespace cfpp
 using namespace cfpp;
@@ -373,6 +799,17 @@ extern "C" int cfpp_vit_tc2_fwd(const float* x, int64_t x_bstride, float* h, con
   vt2::Args a{x, x_bstride, h, d, (const uint8_t*)wpack, B, vt2::kRows / d.n_tok, 0, (d.T + 15) / 16 * 16, (d.T + 63) / 64, (d.patch_dim + 63) / 64, vt2::xs_of(d.T), 0, 0};
   a.ntiles = (B + a.S - 1) / a.S;
   a.xrows = a.S * d.n_tok;
+  if (vt2::use_tc5(d.n_tok)) {
+    a.nstages = vt2::stages_for5(a.P);
+    const size_t smem5 = vt2::fixed_bytes5(a.P) + (size_t)a.nstages * vt2::kChunkBytes;
+    const int grid5 = a.ntiles < num_sms() ? a.ntiles : num_sms();
+#define CFPP_VT5(P_) do { static DeviceHighWater attr5; \
+    if (attr5.raise((long long)smem5)) cudaFuncSetAttribute(vt2::vit_tc5_kernel<P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5); \
+    vt2::vit_tc5_kernel<P_><<<grid5, vt2::kThreads5, smem5, (cudaStream_t)stream>>>(a); } while (0)
+    if (a.P == 1) CFPP_VT5(1); else if (a.P == 2) CFPP_VT5(2); else CFPP_VT5(3);
+#undef CFPP_VT5
+    return check_launch("vit_cond_tc_fwd");
+  }
   a.nstages = vt2::stages_for(d.T, a.P, a.xrows);
   const size_t smem = vt2::fixed_bytes(d.T, a.P, a.xrows) + (size_t)a.nstages * vt2::kChunkBytes;
   static DeviceHighWater attr;                                  // per device: one process may drive several GPUs
