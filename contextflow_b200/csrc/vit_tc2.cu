@@ -439,7 +439,7 @@ enum { G_LN0W = 0, G_LN0B, G_PEB, G_LN1W, G_LN1B, G_LNFW, G_LNFB, G_ROWS };
 template <int P>
 __global__ void __launch_bounds__(kThreads5, 1) vit_tc5_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t vt5_smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(vt5_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* base = vt5_smem_raw + ((1024u - (smem_u32(vt5_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the shared array keeps the address space (LDS / STS, not generic LD / ST)
   constexpr int PW = P * kW;
   uint8_t* ops = base;                                        // kPanels x [hi 128 rows x 128 B][lo]
   uint8_t* ring = ops + kPanels * kPanelBytes;                // nstages x kChunkBytes
