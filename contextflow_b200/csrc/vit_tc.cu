@@ -141,7 +141,7 @@ enum { BAR_FULL = 0, BAR_EMPTY = kStages, BAR_AREADY = 2 * kStages, BAR_ACC, BAR
 
 __global__ void __launch_bounds__(kThreads, 1) vit_tc_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t vt_smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(vt_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* base = vt_smem_raw + ((1024u - (smem_u32(vt_smem_raw) & 1023u)) & 1023u);   // (pointer arithmetic on the shared array keeps the address space)
   uint8_t* a_hi = base;                                       // 128 rows x 128 B
   uint8_t* a_lo = base + kRows * 128;
   uint8_t* ring = base + 2 * kRows * 128;                     // kStages x kChunkBytes

@@ -74,7 +74,7 @@ __device__ __forceinline__ void ln_stats(const float* xrow, int n, float& mean, 
 
 __global__ void __launch_bounds__(kThreads, 1) vit_tc2_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t vt2_smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(vt2_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* base = vt2_smem_raw + ((1024u - (smem_u32(vt2_smem_raw) & 1023u)) & 1023u);   // (pointer arithmetic on the shared array keeps the address space)
   uint8_t* ops = base;                                        // kPanels x [hi 128 rows x 128 B][lo]
   uint8_t* ring = ops + kPanels * kPanelBytes;                // nstages x kChunkBytes
   const int kStages = a.nstages;
@@ -659,19 +659,38 @@ __global__ void __launch_bounds__(kThreads5, 1) vit_tc5_kernel(const Args a) {
         tc_fence_before();
         compute_sync5();                                            // keys / values of the sample may be rows of other quadrants
         const int r0 = r - tok;
-        if (live)
-          for (int j = g; j < ntok; j += kCG) {                     // full-width scores of the keys this column group owns
-            const int rj = r0 + j, sw = rj & 15;
-            const float* qr = Qs + r * kQStride;
-            const float* kr = Ks + rj * kW;
-            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        if (live) {
+          // full-width scores of the keys this column group owns (j = g, g + 4, ...), five keys per pass: a 16-byte piece of the q row is
+          // loaded once per pass instead of once per key (19 instead of 32 shared loads per key: the loop is bound by shared-memory bandwidth)
+          constexpr int NK = 5;
+          const float* qr = Qs + r * kQStride;
+          for (int jb = g; jb < ntok; jb += kCG * NK) {
+            float acc[NK][4];
+            const float* kr[NK]; int sw[NK];
+#pragma unroll
+            for (int u = 0; u < NK; ++u) {
+              const int j = min(jb + kCG * u, ntok - 1);             // (keys beyond the last one recompute it; not stored)
+              const int rj = r0 + j;
+              kr[u] = Ks + rj * kW; sw[u] = rj & 15;
+              acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
+            }
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-              const float4 q4 = *reinterpret_cast<const float4*>(qr + 4 * q), k4 = *reinterpret_cast<const float4*>(kr + 4 * (q ^ sw));
-              d0 = fmaf(q4.x, k4.x, d0); d1 = fmaf(q4.y, k4.y, d1); d2 = fmaf(q4.z, k4.z, d2); d3 = fmaf(q4.w, k4.w, d3);
+              const float4 q4 = *reinterpret_cast<const float4*>(qr + 4 * q);
+#pragma unroll
+              for (int u = 0; u < NK; ++u) {
+                const float4 k4 = *reinterpret_cast<const float4*>(kr[u] + 4 * (q ^ sw[u]));
+                acc[u][0] = fmaf(q4.x, k4.x, acc[u][0]); acc[u][1] = fmaf(q4.y, k4.y, acc[u][1]);
+                acc[u][2] = fmaf(q4.z, k4.z, acc[u][2]); acc[u][3] = fmaf(q4.w, k4.w, acc[u][3]);
+              }
             }
-            Sc[r * kW + (j ^ (r & 31))] = ((d0 + d1) + (d2 + d3)) * 0.125f;   // dim_head ** -0.5
+#pragma unroll
+            for (int u = 0; u < NK; ++u) {
+              const int j = jb + kCG * u;
+              if (j < ntok) Sc[r * kW + (j ^ (r & 31))] = ((acc[u][0] + acc[u][1]) + (acc[u][2] + acc[u][3])) * 0.125f;   // dim_head ** -0.5
+            }
           }
+        }
         quad_sync5(quad);                                           // the scores of a row are written and read by its own four threads
         float o[kCW];
 #pragma unroll
