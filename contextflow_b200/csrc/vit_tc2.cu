@@ -434,9 +434,52 @@ __device__ __forceinline__ void gelu2(float u0, float u1, float& o0, float& o1) 
   unpack2(ffma2(hu, pack2(r0, r1), hu), o0, o1);
 }
 
+// maximum of `v` over the four column-group threads of row r (same table protocol as row_sum5)
+__device__ __forceinline__ float row_max5(float v, float* red, int r, int g, int quad) {
+  red[g * kRows + r] = v;
+  quad_sync5(quad);
+  return fmaxf(fmaxf(red[r], red[kRows + r]), fmaxf(red[2 * kRows + r], red[3 * kRows + r]));
+}
+// v^T as the B operand of O = P V (N = 64 value channels, K = 128 keys): key panel kp = r / 64 is a 16 KB block laid out like a weight chunk,
+// [hi image: 64 channel rows x 128 B (64 keys)][lo image]; the thread writes its 16 channels of key r (one fp16 per row, SWIZZLE_128B)
+__device__ __forceinline__ void store_vt16(uint8_t* vt, int r, int g, const float (&v)[kCW]) {
+  const int rk = r & 63;
+  uint8_t* hi = vt + (r >> 6) * kChunkBytes;
+  uint8_t* lo = hi + kW * 128;
+#pragma unroll
+  for (int i = 0; i < kCW; i += 2) {
+    uint32_t h2, l2;
+    f16_split2p(v[i], v[i + 1], h2, l2);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = kCW * g + i + e;
+      const uint32_t off = (uint32_t)c * 128u + (uint32_t)((((rk >> 3) ^ c) & 7) << 4) + (uint32_t)((rk & 7) << 1);
+      *reinterpret_cast<unsigned short*>(hi + off) = (unsigned short)(e ? (h2 >> 16) : (h2 & 0xFFFFu));
+      *reinterpret_cast<unsigned short*>(lo + off) = (unsigned short)(e ? (l2 >> 16) : (l2 & 0xFFFFu));
+    }
+  }
+}
+// the thread's 32 key columns 32 g .. +31 of probability row `row` as A-operand pieces: key panel g / 2, 16-byte pieces 4 (g % 2) .. +3
+__device__ __forceinline__ void store_p32(uint8_t* ops, int row, int g, const float (&pv)[32]) {
+  uint8_t* a_hi = ops + (g >> 1) * kPanelBytes;
+  uint8_t* a_lo = a_hi + kRows * 128;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f16_split2p(pv[8 * c + 2 * q], pv[8 * c + 2 * q + 1], h[q], l[q]);
+    const uint32_t off = (uint32_t)row * 128u + (uint32_t)((((4 * (g & 1) + c) ^ row) & 7) << 4);
+    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
 enum { G_LN0W = 0, G_LN0B, G_PEB, G_LN1W, G_LN1B, G_LNFW, G_LNFB, G_ROWS };
 
-template <int P>
+// TCA: attention on the tensor cores as well -- S = q k^T over the whole tile (128 x 128, only a sample's own block is used), softmax in
+// registers (32 key columns per thread), O = P v with v^T staged as a B operand; the FP32 form (TCA = false) stages q / k / v / scores in
+// shared memory and is bound by shared-memory bandwidth at 36-38 tokens per sample
+template <int P, bool TCA>
 __global__ void __launch_bounds__(kThreads5, 1) vit_tc5_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t vt5_smem_raw[];
   uint8_t* base = vt5_smem_raw + ((1024u - (smem_u32(vt5_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the shared array keeps the address space (LDS / STS, not generic LD / ST)
@@ -444,8 +487,8 @@ __global__ void __launch_bounds__(kThreads5, 1) vit_tc5_kernel(const Args a) {
   uint8_t* ops = base;                                        // kPanels x [hi 128 rows x 128 B][lo]
   uint8_t* ring = ops + kPanels * kPanelBytes;                // nstages x kChunkBytes
   const int kStages = a.nstages;
-  float* Qs = reinterpret_cast<float*>(ring + kStages * kChunkBytes);      // [128][kQStride]
-  float* red2 = Qs + kRows * kQStride;                        // [2][kCG][128] row-reduction partials
+  float* Qs = reinterpret_cast<float*>(ring + kStages * kChunkBytes);      // [128][kQStride] (FP32 attention only)
+  float* red2 = Qs + (TCA ? 0 : kRows * kQStride);            // [2][kCG][128] row-reduction partials
   float* lprm = red2 + 2 * kCG * kRows;                       // [6][PW]: lna_w lna_b lnf_w lnf_b b1 b2 of the current layer, zero padded
   float* gprm = lprm + 6 * PW;                                // [G_ROWS][PW]: ln0 w/b (patch_dim wide), pe_b, ln1 w/b, final norm w/b
   int* foff_in = reinterpret_cast<int*>(gprm + G_ROWS * PW);  // [PW] feature part of the patchify offset; -1 beyond patch_dim
@@ -532,7 +575,36 @@ __global__ void __launch_bounds__(kThreads5, 1) vit_tc5_kernel(const Args a) {
       };
       for (int it = 0; it < my_tiles; ++it) {
         gemm(P, PD);
-        for (int l = 0; l < depth; ++l) { gemm(3, P); gemm(P, 1); gemm(P, P); gemm(P, P); }
+        for (int l = 0; l < depth; ++l) {
+          gemm(3, P);
+          if (TCA) {
+            const uint64_t ah = a0, al = a0 + (uint64_t)((kRows * 128) >> 4), bk = a0 + (uint64_t)(kPanelBytes >> 4);
+            // S = q k^T: A = q rows (panel 0), B = k rows (panel 1: 128 hi rows | 128 lo rows); main block columns 0-127, cross block 128-255
+            mbar_wait(bar(BAR_AREADY), na & 1); ++na;
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              mma_f16(tmem, ah + 2 * ks, bk + 2 * ks, make_idesc(4 * kW), ks ? 1u : 0u);
+              mma_f16(tmem + 2 * kW, al + 2 * ks, bk + 2 * ks, id128, 1u);
+            }
+            tc_commit(bar(BAR_ACC));
+            // O = P v: A = probability rows (key panels 0-1 = operand panels 0-1), B = v^T (panel 2: one chunk-shaped block per key panel); columns 384-511
+            mbar_wait(bar(BAR_AREADY), na & 1); ++na;
+            tc_fence_after();
+#pragma unroll
+            for (int kp = 0; kp < 2; ++kp) {
+              const uint64_t ph_ = a0 + (uint64_t)(kp * (kPanelBytes >> 4)), pl_ = ph_ + (uint64_t)((kRows * 128) >> 4);
+              const uint64_t bv = a0 + (uint64_t)(2 * (kPanelBytes >> 4) + kp * (kChunkBytes >> 4));
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                mma_f16(tmem + 6 * kW, ph_ + 2 * ks, bv + 2 * ks, id128, (kp | ks) ? 1u : 0u);
+                mma_f16(tmem + 7 * kW, pl_ + 2 * ks, bv + 2 * ks, id64, 1u);
+              }
+            }
+            tc_commit(bar(BAR_ACC));
+          }
+          gemm(P, 1); gemm(P, P); gemm(P, P);
+        }
       }
     }
   } else {
@@ -644,80 +716,125 @@ __global__ void __launch_bounds__(kThreads5, 1) vit_tc5_kernel(const Args a) {
         ln_to_operands(x, T, P, lprm, lprm + PW);
         a_ready();
         acc_wait();
+        float o[kCW];
+        if (TCA) {
+          const int r0 = r - tok;
+          {
+            float t16[kCW];
+            load_acc16(trow + 2 * kW, g, t16);                      // k -> B-operand rows (panel 1)
+            store_operand16(op_hi(1), op_lo(1), r, g, t16);
+            load_acc16(trow + 4 * kW, g, t16);                      // v -> v^T (panel 2)
+            store_vt16(ops + 2 * kPanelBytes, r, g, t16);
+            load_acc16(trow, g, t16);                               // q -> A-operand rows (panel 0)
+            store_operand16(op_hi(0), op_lo(0), r, g, t16);
+          }
+          tc_fence_before();
+          a_ready();
+          acc_wait();                                               // S = q k^T
+          float pv[32];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float v[16], u[16];
+            tmem_ld16(trow + 32 * g + 16 * h, v);
+            tmem_ld16(trow + 2 * kW + 32 * g + 16 * h, u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pv[16 * h + i] = fmaf(u[i], kLoInv, v[i]) * 0.125f;   // dim_head ** -0.5
+          }
+          tc_fence_before();
+          const int jlo = r0 - 32 * g, jhi = jlo + ntok;            // this thread's key columns i with jlo <= i < jhi belong to the row's sample
+          float mx = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { if (!(live && i >= jlo && i < jhi)) pv[i] = -INFINITY; mx = fmaxf(mx, pv[i]); }
+          mx = row_max5(mx, red2 + (flip & 1) * kCG * kRows, r, g, quad); ++flip;
+          if (!live) mx = 0.f;
+          float den = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { pv[i] = __expf(pv[i] - mx); den += pv[i]; }
+          den = row_sum5(den, red2 + (flip & 1) * kCG * kRows, r, g, quad); ++flip;
+          const float inv = live ? 1.0f / den : 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pv[i] *= inv;
+          store_p32(ops, r, g, pv);
+          a_ready();
+          acc_wait();                                               // O = P v
+          load_acc16(trow + 6 * kW, g, o);
+          tc_fence_before();
+        } else {
         {
-          float t16[kCW];
-          load_acc16(trow + 2 * kW, g, t16);                        // k: 16-byte piece q of row r is stored at position q ^ (r % 16) (see the kernel above)
+            float t16[kCW];
+            load_acc16(trow + 2 * kW, g, t16);                        // k: 16-byte piece q of row r is stored at position q ^ (r % 16) (see the kernel above)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(Ks + r * kW + 4 * ((4 * g + q) ^ (r & 15))) = make_float4(t16[4 * q], t16[4 * q + 1], t16[4 * q + 2], t16[4 * q + 3]);
-          load_acc16(trow + 4 * kW, g, t16);                        // v
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(Ks + r * kW + 4 * ((4 * g + q) ^ (r & 15))) = make_float4(t16[4 * q], t16[4 * q + 1], t16[4 * q + 2], t16[4 * q + 3]);
+            load_acc16(trow + 4 * kW, g, t16);                        // v
 #pragma unroll
-          for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(Vs + r * kW + 4 * ((4 * g + q) ^ (r & 15))) = make_float4(t16[4 * q], t16[4 * q + 1], t16[4 * q + 2], t16[4 * q + 3]);
-          load_acc16(trow, g, t16);                                 // q
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(Vs + r * kW + 4 * ((4 * g + q) ^ (r & 15))) = make_float4(t16[4 * q], t16[4 * q + 1], t16[4 * q + 2], t16[4 * q + 3]);
+            load_acc16(trow, g, t16);                                 // q
 #pragma unroll
-          for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(Qs + r * kQStride + c0 + 4 * q) = make_float4(t16[4 * q], t16[4 * q + 1], t16[4 * q + 2], t16[4 * q + 3]);
-        }
-        tc_fence_before();
-        compute_sync5();                                            // keys / values of the sample may be rows of other quadrants
-        const int r0 = r - tok;
-        if (live) {
-          // full-width scores of the keys this column group owns (j = g, g + 4, ...), five keys per pass: a 16-byte piece of the q row is
-          // loaded once per pass instead of once per key (19 instead of 32 shared loads per key: the loop is bound by shared-memory bandwidth)
-          constexpr int NK = 5;
-          const float* qr = Qs + r * kQStride;
-          for (int jb = g; jb < ntok; jb += kCG * NK) {
-            float acc[NK][4];
-            const float* kr[NK]; int sw[NK];
-#pragma unroll
-            for (int u = 0; u < NK; ++u) {
-              const int j = min(jb + kCG * u, ntok - 1);             // (keys beyond the last one recompute it; not stored)
-              const int rj = r0 + j;
-              kr[u] = Ks + rj * kW; sw[u] = rj & 15;
-              acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              const float4 q4 = *reinterpret_cast<const float4*>(qr + 4 * q);
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(Qs + r * kQStride + c0 + 4 * q) = make_float4(t16[4 * q], t16[4 * q + 1], t16[4 * q + 2], t16[4 * q + 3]);
+          }
+          tc_fence_before();
+          compute_sync5();                                            // keys / values of the sample may be rows of other quadrants
+          const int r0 = r - tok;
+          if (live) {
+            // full-width scores of the keys this column group owns (j = g, g + 4, ...), five keys per pass: a 16-byte piece of the q row is
+            // loaded once per pass instead of once per key (19 instead of 32 shared loads per key: the loop is bound by shared-memory bandwidth)
+            constexpr int NK = 5;
+            const float* qr = Qs + r * kQStride;
+            for (int jb = g; jb < ntok; jb += kCG * NK) {
+              float acc[NK][4];
+              const float* kr[NK]; int sw[NK];
 #pragma unroll
               for (int u = 0; u < NK; ++u) {
-                const float4 k4 = *reinterpret_cast<const float4*>(kr[u] + 4 * (q ^ sw[u]));
-                acc[u][0] = fmaf(q4.x, k4.x, acc[u][0]); acc[u][1] = fmaf(q4.y, k4.y, acc[u][1]);
-                acc[u][2] = fmaf(q4.z, k4.z, acc[u][2]); acc[u][3] = fmaf(q4.w, k4.w, acc[u][3]);
+                const int j = min(jb + kCG * u, ntok - 1);             // (keys beyond the last one recompute it; not stored)
+                const int rj = r0 + j;
+                kr[u] = Ks + rj * kW; sw[u] = rj & 15;
+                acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
+              }
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const float4 q4 = *reinterpret_cast<const float4*>(qr + 4 * q);
+#pragma unroll
+                for (int u = 0; u < NK; ++u) {
+                  const float4 k4 = *reinterpret_cast<const float4*>(kr[u] + 4 * (q ^ sw[u]));
+                  acc[u][0] = fmaf(q4.x, k4.x, acc[u][0]); acc[u][1] = fmaf(q4.y, k4.y, acc[u][1]);
+                  acc[u][2] = fmaf(q4.z, k4.z, acc[u][2]); acc[u][3] = fmaf(q4.w, k4.w, acc[u][3]);
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < NK; ++u) {
+                const int j = jb + kCG * u;
+                if (j < ntok) Sc[r * kW + (j ^ (r & 31))] = ((acc[u][0] + acc[u][1]) + (acc[u][2] + acc[u][3])) * 0.125f;   // dim_head ** -0.5
               }
             }
-#pragma unroll
-            for (int u = 0; u < NK; ++u) {
-              const int j = jb + kCG * u;
-              if (j < ntok) Sc[r * kW + (j ^ (r & 31))] = ((acc[u][0] + acc[u][1]) + (acc[u][2] + acc[u][3])) * 0.125f;   // dim_head ** -0.5
-            }
           }
-        }
-        quad_sync5(quad);                                           // the scores of a row are written and read by its own four threads
-        float o[kCW];
+          quad_sync5(quad);                                           // the scores of a row are written and read by its own four threads
 #pragma unroll
-        for (int i = 0; i < kCW; ++i) o[i] = 0.f;
-        if (live) {
-          const float* sr = Sc + r * kW;
-          const int sx = r & 31;
-          float mx = -INFINITY;
-          for (int j = 0; j < ntok; ++j) mx = fmaxf(mx, sr[j ^ sx]);
-          float den = 0.f;
-          for (int j = 0; j < ntok; ++j) {
-            const float pj = __expf(sr[j ^ sx] - mx);
-            den += pj;
-            const int rj = r0 + j, sw = rj & 15;
-            const float* vr = Vs + rj * kW;
+          for (int i = 0; i < kCW; ++i) o[i] = 0.f;
+          if (live) {
+            const float* sr = Sc + r * kW;
+            const int sx = r & 31;
+            float mx = -INFINITY;
+            for (int j = 0; j < ntok; ++j) mx = fmaxf(mx, sr[j ^ sx]);
+            float den = 0.f;
+            for (int j = 0; j < ntok; ++j) {
+              const float pj = __expf(sr[j ^ sx] - mx);
+              den += pj;
+              const int rj = r0 + j, sw = rj & 15;
+              const float* vr = Vs + rj * kW;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 v4 = *reinterpret_cast<const float4*>(vr + 4 * ((4 * g + q) ^ sw));
-              o[4 * q] = fmaf(pj, v4.x, o[4 * q]); o[4 * q + 1] = fmaf(pj, v4.y, o[4 * q + 1]);
-              o[4 * q + 2] = fmaf(pj, v4.z, o[4 * q + 2]); o[4 * q + 3] = fmaf(pj, v4.w, o[4 * q + 3]);
+              for (int q = 0; q < 4; ++q) {
+                const float4 v4 = *reinterpret_cast<const float4*>(vr + 4 * ((4 * g + q) ^ sw));
+                o[4 * q] = fmaf(pj, v4.x, o[4 * q]); o[4 * q + 1] = fmaf(pj, v4.y, o[4 * q + 1]);
+                o[4 * q + 2] = fmaf(pj, v4.z, o[4 * q + 2]); o[4 * q + 3] = fmaf(pj, v4.w, o[4 * q + 3]);
+              }
             }
-          }
-          const float inv = 1.0f / den;
+            const float inv = 1.0f / den;
 #pragma unroll
-          for (int i = 0; i < kCW; ++i) o[i] *= inv;
+            for (int i = 0; i < kCW; ++i) o[i] *= inv;
+          }
+          compute_sync5();                                            // every score has been read: panel 0 takes the attention output
         }
-        compute_sync5();                                            // every score has been read: panel 0 takes the attention output
         store_operand16(op_hi(0), op_lo(0), r, g, o);
         a_ready();
         acc_wait();                                                  // (all compute threads have arrived: nobody still reads k / v)
@@ -778,19 +895,24 @@ __global__ void __launch_bounds__(kThreads5, 1) vit_tc5_kernel(const Args a) {
   if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
-static size_t fixed_bytes5(int P) {
+static size_t fixed_bytes5(int P, bool tca) {
   const size_t PW = (size_t)P * kW;
-  return 1024 + (size_t)kPanels * kPanelBytes + (size_t)kRows * kQStride * 4 + (size_t)2 * kCG * kRows * 4 + (6 + G_ROWS) * PW * 4 + 2 * PW * 4 + BAR_COUNT * 8 + 64;
+  return 1024 + (size_t)kPanels * kPanelBytes + (tca ? 0 : (size_t)kRows * kQStride * 4) + (size_t)2 * kCG * kRows * 4 + (6 + G_ROWS) * PW * 4 + 2 * PW * 4 + BAR_COUNT * 8 + 64;
 }
-static int stages_for5(int P) {
-  const long long left = 227LL * 1024 - (long long)fixed_bytes5(P);
+static int stages_for5(int P, bool tca) {
+  const long long left = 227LL * 1024 - (long long)fixed_bytes5(P, tca);
   long long n = left / kChunkBytes;
   return (int)(n > kMaxStages ? kMaxStages : n);
 }
-// the four-threads-per-row kernel covers up to 64 tokens per sample (score table in operand panel 0); CFPP_VIT_TC2_V1=1 keeps the kernel above (A/B timing)
-static bool use_tc5(int n_tok) {
-  const char* e = getenv("CFPP_VIT_TC2_V1");                   // read per call: the tests compare the two kernels in one process
-  return !(e && *e == '1') && n_tok <= 64;
+// 0: the one-thread-per-row kernel above (CFPP_VIT_TC2_V1=1, A/B timing); 1: four threads per row, FP32 attention (CFPP_VIT_ATTN=fma; up to 64
+// tokens per sample: score table in operand panel 0); 2: four threads per row, attention on the tensor cores (default).  Read per call: the
+// tests compare the kernels in one process.
+static int tc5_mode(int n_tok) {
+  const char* e = getenv("CFPP_VIT_TC2_V1");
+  if (e && *e == '1') return 0;
+  const char* at = getenv("CFPP_VIT_ATTN");
+  if (at && at[0] == 'f') return n_tok <= 64 ? 1 : 0;
+  return 2;
 }
 
 }  // namespace vt2
@@ -818,14 +940,16 @@ extern "C" int cfpp_vit_tc2_fwd(const float* x, int64_t x_bstride, float* h, con
   vt2::Args a{x, x_bstride, h, d, (const uint8_t*)wpack, B, vt2::kRows / d.n_tok, 0, (d.T + 15) / 16 * 16, (d.T + 63) / 64, (d.patch_dim + 63) / 64, vt2::xs_of(d.T), 0, 0};
   a.ntiles = (B + a.S - 1) / a.S;
   a.xrows = a.S * d.n_tok;
-  if (vt2::use_tc5(d.n_tok)) {
-    a.nstages = vt2::stages_for5(a.P);
-    const size_t smem5 = vt2::fixed_bytes5(a.P) + (size_t)a.nstages * vt2::kChunkBytes;
+  if (const int mode5 = vt2::tc5_mode(d.n_tok)) {
+    const bool tca = mode5 == 2;
+    a.nstages = vt2::stages_for5(a.P, tca);
+    const size_t smem5 = vt2::fixed_bytes5(a.P, tca) + (size_t)a.nstages * vt2::kChunkBytes;
     const int grid5 = a.ntiles < num_sms() ? a.ntiles : num_sms();
-#define CFPP_VT5(P_) do { static DeviceHighWater attr5; \
-    if (attr5.raise((long long)smem5)) cudaFuncSetAttribute(vt2::vit_tc5_kernel<P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5); \
-    vt2::vit_tc5_kernel<P_><<<grid5, vt2::kThreads5, smem5, (cudaStream_t)stream>>>(a); } while (0)
-    if (a.P == 1) CFPP_VT5(1); else if (a.P == 2) CFPP_VT5(2); else CFPP_VT5(3);
+#define CFPP_VT5(P_, T_) do { static DeviceHighWater attr5; \
+    if (attr5.raise((long long)smem5)) cudaFuncSetAttribute(vt2::vit_tc5_kernel<P_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5); \
+    vt2::vit_tc5_kernel<P_, T_><<<grid5, vt2::kThreads5, smem5, (cudaStream_t)stream>>>(a); } while (0)
+    if (tca) { if (a.P == 1) CFPP_VT5(1, true); else if (a.P == 2) CFPP_VT5(2, true); else CFPP_VT5(3, true); }
+    else { if (a.P == 1) CFPP_VT5(1, false); else if (a.P == 2) CFPP_VT5(2, false); else CFPP_VT5(3, false); }
 #undef CFPP_VT5
     return check_launch("vit_cond_tc_fwd");
   }

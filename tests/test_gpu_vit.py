@@ -48,7 +48,8 @@ def _ref64(m, img):
 # (H, W, p1, p2, T, depth, Cin): the six cfg3 (ATM) conditioners, the SMD one, two small ATM ones, and shapes that exercise two operand
 # panels with a token count that does not divide the tile
 GEOMS = [(18, 1, 2, 1, 152, 6, 38), (36, 1, 2, 1, 152, 6, 38), (72, 1, 2, 1, 152, 6, 38), (76, 1, 2, 1, 36, 6, 9), (76, 1, 2, 1, 72, 6, 18),
-         (76, 1, 2, 1, 144, 6, 36), (8, 1, 2, 1, 76, 6, 19), (12, 1, 2, 1, 16, 6, 4), (10, 2, 2, 2, 128, 2, 16), (14, 6, 2, 2, 64, 1, 8)]
+         (76, 1, 2, 1, 144, 6, 36), (8, 1, 2, 1, 76, 6, 19), (12, 1, 2, 1, 16, 6, 4), (10, 2, 2, 2, 128, 2, 16), (14, 6, 2, 2, 64, 1, 8),
+         (100, 1, 1, 1, 64, 2, 8), (128, 1, 2, 1, 96, 1, 6)]
 
 
 @pytest.mark.parametrize('geom', GEOMS)
@@ -61,15 +62,21 @@ def test_vit_general_kernels_match_fp64(geom, B, monkeypatch):
     want = _ref64(m, x)
     scale = max(1.0, float(want.abs().max()))
     outs = {}
-    for v1 in ('1', '0'):
-        monkeypatch.setenv('CFPP_VIT_TC2_V1', v1)
+    # one thread per token row / four threads per row with FP32 attention (falls back to the former beyond 64 tokens) / four threads per row
+    # with the attention on the tensor cores (default)
+    for mode, env in (('row', {'CFPP_VIT_TC2_V1': '1'}), ('fma', {'CFPP_VIT_ATTN': 'fma'}), ('tc', {})):
+        monkeypatch.delenv('CFPP_VIT_TC2_V1', raising=False)
+        monkeypatch.delenv('CFPP_VIT_ATTN', raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         with torch.no_grad():
-            outs[v1] = m(x)
+            outs[mode] = m(x)
         torch.cuda.synchronize()
-        err = (outs[v1].double() - want).abs().max().item()
-        assert err <= 2e-5 * scale + 1e-4 * 0, f'V1={v1} {geom} B={B}: max abs err {err:.3e} (scale {scale:.3f})'
-    # the two kernels differ only in the order of the LayerNorm / softmax reductions
-    assert (outs['1'] - outs['0']).abs().max().item() <= 2e-5 * scale
+        err = (outs[mode].double() - want).abs().max().item()
+        assert err <= 2e-5 * scale, f'{mode} {geom} B={B}: max abs err {err:.3e} (scale {scale:.3f})'
+    # the kernels differ only in the order of the LayerNorm / softmax reductions and in where the attention products are formed
+    assert (outs['row'] - outs['tc']).abs().max().item() <= 2e-5 * scale
+    assert (outs['fma'] - outs['tc']).abs().max().item() <= 2e-5 * scale
 
 
 def test_vit_strided_half_view(monkeypatch):
