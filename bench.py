@@ -37,6 +37,7 @@ def parse():
                     help='log_prob (default): the headline forward log-density path; train / reverse: the SURVEY §8(f) rows, measured by '
                          'tools/bench_training.py / tools/bench_inverse.py (their own JSON lines)')
     ap.add_argument('--secondary', default='cfg4', choices=sorted(WORKLOADS) + [''], help='second workload measured in the same run ("" = none)')
+    ap.add_argument('--tertiary', default='cfg3', choices=sorted(WORKLOADS) + [''], help='third workload measured in the same run: BASELINE configs[2], the ATM trans specialist ("" = none)')
     ap.add_argument('--no-parity', action='store_true', help='skip the oracle parity check of the timed batch (profiling runs)')
     ap.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying the captured CUDA graph')
     return ap.parse_args()
@@ -476,6 +477,10 @@ def main():
         # BASELINE configs[4] names two shapes for the throughput sweep (CIFAR-shape conv AND SMAP-shape trans): the second one rides
         # along in the same line so that it is seen at every N the driver runs
         sec = measure(a, a.secondary, DEFAULT_BATCH[a.secondary], rank, world, dev, with_e2e=False, parity=not a.no_parity)
+    ter = None
+    if a.tertiary and a.secondary and a.tertiary not in (workload, a.secondary):
+        # BASELINE configs[2] (ATM trans specialist, eye + argmax): the general ViT conditioner's shape, seen at every N as well
+        ter = measure(a, a.tertiary, DEFAULT_BATCH[a.tertiary], rank, world, dev, with_e2e=False, parity=not a.no_parity)
     if saved_stdout is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
@@ -491,6 +496,10 @@ def main():
             line['secondary'] = {'metric': METRIC, 'value': sec['value'], 'unit': UNIT, 'ms_per_step': sec['ms_per_step'], 'config': sec['config'],
                                  'gpu_launches': sec['gpu_launches'], 'roofline': sec['roofline'], 'roofline_coupling': sec['roofline_coupling'],
                                  'roofline_hbm_path': sec['roofline_hbm_path'], 'kernels': sec['kernels'], 'parity_at_bench_batch': sec['parity_at_bench_batch']}
+        if ter is not None:
+            line['tertiary'] = {'metric': METRIC, 'value': ter['value'], 'unit': UNIT, 'ms_per_step': ter['ms_per_step'], 'config': ter['config'],
+                                'gpu_launches': ter['gpu_launches'], 'roofline': ter['roofline'], 'kernels': ter['kernels'],
+                                'parity_at_bench_batch': ter['parity_at_bench_batch']}
         if world == 1 and not a.no_cpu_baseline:
             # bounded sample of the same workload on the host cores: ~10-20 s of CPU work (probe one step, then as many as fit)
             probe, dt1 = reference_run(workload, REF_BATCH[workload], 1, 1)

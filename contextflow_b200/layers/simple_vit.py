@@ -1,6 +1,7 @@
 """SimpleViT conditioner (reference layers/simple_vit.py:18-127): parameter container with the reference's module tree /
 state_dict names; forward is the fused CUDA kernel (cfpp_vit_cond_fwd)."""
 import ctypes
+import os
 
 import torch
 from torch import nn
@@ -108,7 +109,7 @@ class SimpleViT(nn.Module):
         g = self.geom
         lib = _cabi.lib()
         T, pd = g['T'], g['patch_dim']
-        small = bool(lib.cfpp_vit_tc_supported(T, pd, g['n_tok'], 0))
+        small = bool(lib.cfpp_vit_tc_supported(T, pd, g['n_tok'], 0)) and os.environ.get('CFPP_VIT_GENERAL', '0') != '1'   # (=1: A/B the general kernel on the small shapes)
         if not small and not lib.cfpp_vit_tc2_supported(T, pd, g['n_tok'], 0):
             return None
 
