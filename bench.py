@@ -182,7 +182,7 @@ def reference_run(workload, batch, steps, warmup, device='cpu', tf32=None, seed=
 
 
 HBM_KERNELS_EXCLUDED = ('conv_cond_fwd', 'conv_cond_tc_fwd', 'conv_cond_tc_coupling_fwd', 'vit_cond_fwd', 'vit_tc_fwd', 'vit_tc2_fwd', 'gmm_logprob',
-                        'gmm_logprob_ctxtab', 'gmm_tile_logprob', 'ctx_encode_batch', 'ctx_encode', 'cn_batch', 'ctx_tables', 'linear_fwd', 'ldj_sum', 'slogdet')
+                        'gmm_logprob_ctxtab', 'gmm_logprob_ctxtab_cached', 'gmm_tile_logprob', 'ctx_encode_batch', 'ctx_encode', 'cn_batch', 'ctx_tables', 'linear_fwd', 'ldj_sum', 'slogdet')
 TENSOR_KERNELS = ('conv_cond_tc_fwd', 'conv_cond_tc_coupling_fwd', 'vit_tc_fwd', 'vit_tc2_fwd', 'conv1x1_tc_fwd')
 PAIR_KERNELS = TENSOR_KERNELS                                    # fp16 hi/lo pairs: 3 tensor products issued per algorithmic product
 

@@ -95,6 +95,8 @@ _SIGNATURES = {
     'cfpp_gmm_logprob': (i32, [vp, i64, vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, vp]),
     'cfpp_gmm_logprob_ctxtab': (i32, [vp, i64, vp, vp, vp, vp, i32, C.POINTER(i32), C.POINTER(vp), i32, vp, f32, vp, vp, i64,
                                       i32, i32, i32, i32, i32, vp]),
+    'cfpp_gmm_logprob_ctxtab_cached': (i32, [vp, i64, vp, vp, vp, vp, i32, C.POINTER(i32), C.POINTER(vp), i32, vp, f32, vp, vp, i64,
+                                             i32, i32, i32, i32, i32, i32, vp]),
     'cfpp_gmm_ctxtab_workspace_bytes': (i64, [i32, i32, i32, i32, i32, i32, C.POINTER(i32)]),
     'cfpp_gmm_workspace_floats': (i64, [i32, i32, i32, i32]),
     'cfpp_gmm_tile_table_bytes': (i64, [i32, i32, i32, i32, i32]),

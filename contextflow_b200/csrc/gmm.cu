@@ -292,10 +292,26 @@ extern "C" int64_t cfpp_gmm_ctxtab_workspace_bytes(int B, int M, int K, int D, i
   return gmm_tab_plan(B, M, K, D, HW, n_ctx, cards, &NB, &Vs, &S, &bytes) ? bytes : -1;
 }
 
+extern "C" int cfpp_gmm_logprob_ctxtab_cached(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* wG,
+                                              const int64_t* ctx, int n_ctx, const int* cards, const float* const* tables, int width,
+                                              const float* logp_c, float logp_scale, float* out, void* workspace, int64_t workspace_bytes,
+                                              int tables_ready, int B, int M, int K, int D, int HW, void* stream);
+
 extern "C" int cfpp_gmm_logprob_ctxtab(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* wG,
                                        const int64_t* ctx, int n_ctx, const int* cards, const float* const* tables, int width,
                                        const float* logp_c, float logp_scale, float* out, void* workspace, int64_t workspace_bytes,
                                        int B, int M, int K, int D, int HW, void* stream) {
+  return cfpp_gmm_logprob_ctxtab_cached(x, x_bstride, mG, sG, wG, ctx, n_ctx, cards, tables, width, logp_c, logp_scale, out, workspace, workspace_bytes,
+                                        0, B, M, K, D, HW, stream);
+}
+
+// tables_ready != 0: the per-scale-context (1 / (2 sigma^2), log-normaliser) tables at the head of `workspace` were filled by an earlier call with
+// the SAME parameters, batch size and workspace -- they depend on the parameters only, so a caller that keeps the workspace per parameter
+// version skips their recomputation (M*K x contexts CTAs of softplus / log per forward: a third of this op's time at B = 256)
+extern "C" int cfpp_gmm_logprob_ctxtab_cached(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* wG,
+                                              const int64_t* ctx, int n_ctx, const int* cards, const float* const* tables, int width,
+                                              const float* logp_c, float logp_scale, float* out, void* workspace, int64_t workspace_bytes,
+                                              int tables_ready, int B, int M, int K, int D, int HW, void* stream) {
   int NB, Vs, S; int64_t need;
   if (!gmm_tab_plan(B, M, K, D, HW, n_ctx, cards, &NB, &Vs, &S, &need)) {
     set_error("gmm_ctxtab: unsupported context structure (n_ctx=%d) or tile size", n_ctx);
@@ -318,9 +334,12 @@ extern "C" int cfpp_gmm_logprob_ctxtab(const float* x, int64_t x_bstride, const 
   const float* mtab = tables[0];
   const float* stab = n_ctx == 2 ? tables[1] : tables[0];
   const int moff = 0, soff = n_ctx == 2 ? 0 : MK * D;
-  gmm_prepare_tab_kernel<<<dim3(MK, Vs), 256, 0, st>>>(sG, wG, stab, width, soff, w.A, w.LB, MK, K, D, HW);
-  int rc = check_launch("gmm_prepare_tab");
-  if (rc) return rc;
+  int rc = CFPP_OK;
+  if (!tables_ready) {
+    gmm_prepare_tab_kernel<<<dim3(MK, Vs), 256, 0, st>>>(sG, wG, stab, width, soff, w.A, w.LB, MK, K, D, HW);
+    rc = check_launch("gmm_prepare_tab");
+    if (rc) return rc;
+  }
   gmm_bucket_kernel<<<1, 1024, 3 * NB * sizeof(int), st>>>(ctx, n_ctx, n_ctx == 2 ? cards[1] : 1, B, NB, S, w.perm, w.tile_key, w.n_tiles);
   rc = check_launch("gmm_bucket");
   if (rc) return rc;

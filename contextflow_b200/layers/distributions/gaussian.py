@@ -93,7 +93,8 @@ class GaussianMixtureDistribution(nn.Module):
                                                lambda: ops.gmm_tile_table(self.mG, self.sG, self.wG, tables[sf], soff))
                         if tab is not None:
                             return ops.gmm_tile_logprob(input, tab, self.M, self.K, context, cards, tables[0], 0)
-                out = ops.gmm_logprob_ctxtab(input, self.mG, self.sG, self.wG, context, cards, tables)
+                keep = self._tables.get('ctxtab_ws', [self.mG, self.sG, self.wG, *tables], dict)    # workspaces by batch size, per parameter version
+                out = ops.gmm_logprob_ctxtab(input, self.mG, self.sG, self.wG, context, cards, tables, keep=keep)
                 if out is not None:
                     return out
             c, logp_c = self._plan.run(self.context_net, context)       # c: 'b (p m k d)'

@@ -571,8 +571,9 @@ def gmm_logprob(x, mG, sG, wG, ctx_off=None, logp_c=None, logp_scale=0.0):
     return out
 
 
-def gmm_logprob_ctxtab(x, mG, sG, wG, ctx, cards, tables, logp_scale=0.0):
-    """GMM log-prob with embedding-lookup context offsets (bucketed per-context tables); None if the structure is unsupported."""
+def gmm_logprob_ctxtab(x, mG, sG, wG, ctx, cards, tables, logp_scale=0.0, keep=None):
+    """GMM log-prob with embedding-lookup context offsets (bucketed per-context tables); None if the structure is unsupported.
+    keep: a dict the caller holds per parameter version -- the workspace then lives in it and its parameter-only tables are computed once."""
     _need_cuda(x, mG, ctx)
     M, K, D = mG.shape[0], mG.shape[1], mG.shape[2]
     xv, bstride = _half_view(x)
@@ -582,12 +583,22 @@ def gmm_logprob_ctxtab(x, mG, sG, wG, ctx, cards, tables, logp_scale=0.0):
     if need < 0:
         return None
     out = torch.empty((B, M), device=x.device, dtype=torch.float32)
-    ws = torch.empty(need, device=x.device, dtype=torch.uint8)
+    ready = 0
+    if keep is not None:
+        ent = keep.get((B, x.device))
+        if ent is None or ent.numel() != need:
+            ent = keep[(B, x.device)] = torch.empty(need, device=x.device, dtype=torch.uint8)
+        else:
+            ready = 1
+        ws = ent
+    else:
+        ws = torch.empty(need, device=x.device, dtype=torch.uint8)
     tabs = [_f32(t) for t in tables]
     tarr = (vp * n)(*[vp(t.data_ptr()) for t in tabs])
     _set_work(bytes=4.0 * B * D * HW + 4.0 * B * M, flops=3.0 * B * M * K * D * HW)
-    _call('gmm_logprob_ctxtab', (_p(xv), bstride, _p(_f32(mG)), _p(_f32(sG)), _p(_f32(wG)), _p(ctx.contiguous()), n, carr, tarr,
-                                 tabs[0].shape[1], None, float(logp_scale), _p(out), _p(ws), need, B, M, K, D, HW, _stream()))
+    _call('gmm_logprob_ctxtab_cached', (_p(xv), bstride, _p(_f32(mG)), _p(_f32(sG)), _p(_f32(wG)), _p(ctx.contiguous()), n, carr, tarr,
+                                        tabs[0].shape[1], None, float(logp_scale), _p(out), _p(ws), need, ready, B, M, K, D, HW, _stream()),
+          'gmm_logprob_ctxtab')
     return out
 
 

@@ -220,6 +220,12 @@ int cfpp_gmm_logprob_ctxtab(const float* x, int64_t x_bstride, const float* mG, 
                             const int64_t* ctx, int n_ctx, const int* cards, const float* const* tables, int width,
                             const float* logp_c, float logp_scale, float* out, void* workspace, int64_t workspace_bytes,
                             int B, int M, int K, int D, int HW, void* stream);
+/* The same call for a caller that keeps `workspace` alive per parameter version: tables_ready != 0 says the parameter-only tables at its head
+ * (1 / (2 sigma^2) and the log-normalisers per scale context) were filled by an earlier call with the same parameters, B and workspace. */
+int cfpp_gmm_logprob_ctxtab_cached(const float* x, int64_t x_bstride, const float* mG, const float* sG, const float* wG,
+                                   const int64_t* ctx, int n_ctx, const int* cards, const float* const* tables, int width,
+                                   const float* logp_c, float logp_scale, float* out, void* workspace, int64_t workspace_bytes,
+                                   int tables_ready, int B, int M, int K, int D, int HW, void* stream);
 /* bytes of scratch for cfpp_gmm_logprob_ctxtab, or -1 when that context structure is unsupported */
 int64_t cfpp_gmm_ctxtab_workspace_bytes(int B, int M, int K, int D, int HW, int n_ctx, const int* cards);
 
