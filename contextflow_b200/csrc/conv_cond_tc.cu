@@ -1081,7 +1081,8 @@ static bool make_plan_occ(Plan& p, double& waste_out, int occ, int pipe, int B, 
       const double waste = (double)(q.T2 * 128) / (double)(S * HW);
       const int waves = (q.ntiles + sms - 1) / sms;
       const double imbalance = (double)(waves * sms) / (double)q.ntiles;
-      const double cost = waste * (q.ntiles >= sms ? imbalance : 1.0) * (1.0 + 0.02 / S);
+      // (a grid that leaves SMs idle pays for them too: at B = 256 the 4x4 level ran 37 two-M-tile CTAs on 148 SMs; 86 one-M-tile CTAs take half the time)
+      const double cost = waste * imbalance * (1.0 + 0.02 / S);
       if (cost < best_cost - 1e-9) { best_cost = cost; best = q; found = true; waste_out = waste; }
     }
   }
