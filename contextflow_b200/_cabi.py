@@ -78,6 +78,7 @@ _SIGNATURES = {
     'cfpp_conv_cond_tc_pack': (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     'cfpp_conv_cond_tc_supported': (i32, [i32, i32, i32, i32, i32, i32, i32, i32, i64]),
     'cfpp_conv_cond_tc_fwd': (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    'cfpp_conv_cond_tc_train_fwd': (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'cfpp_conv_cond_tc_coupling_supported': (i32, [i32, i32, i32, i32, i32, i32, i32]),
     'cfpp_conv_cond_tc_coupling_fwd': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'cfpp_conv_cond_tc_kind': (i32, []),

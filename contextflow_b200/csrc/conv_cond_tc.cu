@@ -192,6 +192,8 @@ struct Args {
   const float* x; float* h; const uint8_t* wpack; const float* b1; const float* b2; const float* b3; const float* bias1_b;
   // fused affine coupling (coupling.py:50-66), z != NULL: h is not written; x must be the full (B, 2 Cin, H, W) tensor
   float* z; float* ldj; const float* add; const float* logp_c; float logp_scale;
+  // training forward (profile-variant kernels only): the post-ReLU activations of stages 1 / 2 as fp32 (B, Ch, H, W) for the backward pass, or NULL
+  float* h1_out; float* h2_out;
   long long wrepl_stride; int nrepl;   // experiment: weight stream replicas (CTA uses replica blockIdx % nrepl)
   int dbg;           // debug (profile kernels only): bit 0 = epilogue warps skip their TMEM loads / operand stores, bit 1 = skip the x0 transform
   long long* prof;   // optional (debug): 12 phase-cycle counters of CTA 0's epilogue thread 0, see cfpp_conv_cond_tc_set_profile
@@ -240,9 +242,9 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) { 
 // One epilogue item: 32 accumulator columns [c0, c0+32) (16 when only 16 remain) of one row, two column blocks of N each ->
 // + bias -> ReLU -> (v, lo) -> operand row `row`.  All four TMEM loads are in flight before the single wait.  All 32 lanes
 // must call (tcgen05.ld is warp-collective); `write` only guards the stores.
-template <bool F16>
+template <bool F16, bool EMIT = false>
 __device__ __forceinline__ void store_split16(const float (&v)[16], const float (&u)[16], const float* __restrict__ bias, uint8_t* ph, uint8_t* pl,
-                                              int row, int col, int rb) {
+                                              int row, int col, int rb, float* gdst = nullptr, int gstride = 0) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     if (F16) {
@@ -256,6 +258,7 @@ __device__ __forceinline__ void store_split16(const float (&v)[16], const float 
         float r0, r1;
         unpack2(ffma2(pack2(u[i], u[i + 1]), kinv, fadd2(pack2(v[i], v[i + 1]), pack2(b.x, b.y))), r0, r1);
         r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f);
+        if (EMIT && gdst) { gdst[(size_t)i * gstride] = r0; gdst[(size_t)(i + 1) * gstride] = r1; }      // fp32 activation for the backward pass
         const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
         float l0, l1;
         unpack2(fmul2(fsub2(pack2(r0, r1), pack2(h0, h1)), ksc), l0, l1);
@@ -274,13 +277,17 @@ __device__ __forceinline__ void store_split16(const float (&v)[16], const float 
         o[4 * q + 0] = fmaxf(v[i + 0] + u[i + 0] + b.x, 0.f); o[4 * q + 1] = fmaxf(v[i + 1] + u[i + 1] + b.y, 0.f);
         o[4 * q + 2] = fmaxf(v[i + 2] + u[i + 2] + b.z, 0.f); o[4 * q + 3] = fmaxf(v[i + 3] + u[i + 3] + b.w, 0.f);
       }
+      if (EMIT && gdst) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) gdst[(size_t)(8 * g + q) * gstride] = o[q];
+      }
       store_group8<F16, true>(ph, pl, row, col + 8 * g, o, rb);
     }
   }
 }
-template <bool F16, bool WIDE>
+template <bool F16, bool WIDE, bool EMIT = false>
 __device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, int c0, const float* __restrict__ bias, uint8_t* a_hi, uint8_t* a_lo,
-                                                    int region_bytes, int row, bool write, int rb) {
+                                                    int region_bytes, int row, bool write, int rb, float* gdst = nullptr, int gstride = 0) {
   const int cps = F16 ? (rb == 64 ? 5 : 6) : 5;               // log2(channels per operand row)
   float v0[16], u0[16], v1[16], u1[16];
   const bool two = WIDE && c0 + 16 < N;                       // warp-uniform; narrow items (16 columns) halve the live registers
@@ -292,8 +299,8 @@ __device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, int N, int c
     const int pn = c0 >> cps, cc = c0 & ((1 << cps) - 1);
     uint8_t* ph = a_hi + pn * region_bytes;
     uint8_t* pl = a_lo + pn * region_bytes;
-    store_split16<F16>(v0, u0, bias + c0, ph, pl, row, cc, rb);
-    if (two) store_split16<F16>(v1, u1, bias + c0 + 16, ph, pl, row, cc + 16, rb);
+    store_split16<F16, EMIT>(v0, u0, bias + c0, ph, pl, row, cc, rb, gdst, gstride);
+    if (two) store_split16<F16, EMIT>(v1, u1, bias + c0 + 16, ph, pl, row, cc + 16, rb, gdst ? gdst + (size_t)16 * gstride : nullptr, gstride);
   }
 }
 
@@ -795,11 +802,17 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
         while (ci >= nc2) { ci -= nc2; ++t; }                  // item -> (M-tile t, column item ci) without a division
         const int c0 = ci * kIW;
         const int r = t * 128 + row_in_tile;
+        float* g1 = nullptr;                                     // training forward: this stored row's source pixel (halo rows rewrite their mirror pixel's value)
+        if (PROF && a.h1_out != nullptr && r < p.R) {
+          const uint32_t w = tab_in[r];
+          const int s = w >> 24;
+          if (s < nS) g1 = a.h1_out + ((size_t)(b0 + s) * p.Ch + c0) * HW + ((w >> 12) & 0xFFF) * p.W + (w & 0xFFF);
+        }
         if (a.bias1_b == nullptr)                                // two call sites: the shared-memory bias keeps LDS addressing
-          epilogue_to_operand<F16, kWide>(tmem + col1 + lane_base + t * 2 * p.N2, p.N2, c0, sb1, a_hi, a_lo, p.region_bytes, r, r < p.R, rb);
+          epilogue_to_operand<F16, kWide, PROF>(tmem + col1 + lane_base + t * 2 * p.N2, p.N2, c0, sb1, a_hi, a_lo, p.region_bytes, r, r < p.R, rb, g1, HW);
         else
-          epilogue_to_operand<F16, kWide>(tmem + col1 + lane_base + t * 2 * p.N2, p.N2, c0,
-                                          a.bias1_b + (size_t)min(b0 + (r < p.R ? (int)(tab_in[r] >> 24) : 0), p.B - 1) * p.Ch, a_hi, a_lo, p.region_bytes, r, r < p.R, rb);
+          epilogue_to_operand<F16, kWide, PROF>(tmem + col1 + lane_base + t * 2 * p.N2, p.N2, c0,
+                                                a.bias1_b + (size_t)min(b0 + (r < p.R ? (int)(tab_in[r] >> 24) : 0), p.B - 1) * p.Ch, a_hi, a_lo, p.region_bytes, r, r < p.R, rb, g1, HW);
       }
       fence_async_smem();
       tc_fence_before();
@@ -822,7 +835,13 @@ __global__ void __launch_bounds__(cta_threads(OCC), OCC) conv_cond_tc_kernel(con
         while (ci >= nc2) { ci -= nc2; ++t; }
         const int c0 = ci * kIW;
         const int m = t * 128 + row_in_tile;
-        epilogue_to_operand<F16, kWide>(tmem + col2 + lane_base + t * 2 * p.N2, p.N2, c0, sb2, a_hi, a_lo, p.region_bytes, m, (tab_out[m] >> 31) != 0, rb);
+        float* g2 = nullptr;
+        if (PROF && a.h2_out != nullptr) {
+          const uint32_t w = tab_out[m];
+          const int s = (w >> 24) & 0x7F;
+          if ((w >> 31) != 0 && s < nS) g2 = a.h2_out + ((size_t)(b0 + s) * p.Ch + c0) * HW + ((w >> 12) & 0xFFF) * p.W + (w & 0xFFF);
+        }
+        epilogue_to_operand<F16, kWide, PROF>(tmem + col2 + lane_base + t * 2 * p.N2, p.N2, c0, sb2, a_hi, a_lo, p.region_bytes, m, (tab_out[m] >> 31) != 0, rb, g2, HW);
       }
       fence_async_smem();
       tc_fence_before();
@@ -1142,7 +1161,7 @@ extern "C" int cfpp_conv_cond_tc_supported(int B, int Cin, int Ch, int Cout, int
 
 static int conv_cond_tc_launch(const float* x, int64_t x_bstride, float* h, const void* wpack, const float* b1, const float* bias1_b,
                                const float* b2, const float* b3, float* z, float* ldj, const float* add, const float* logp_c, float logp_scale,
-                               int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, void* stream) {
+                               int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, void* stream, float* h1_out = nullptr, float* h2_out = nullptr) {
   if (B <= 0) return CFPP_OK;
   tc::Plan p;
   if (!tc::make_plan(p, B, Cin, Ch, Cout, H, W, KH, KW, x_bstride, num_sms())) {
@@ -1153,7 +1172,7 @@ static int conv_cond_tc_launch(const float* x, int64_t x_bstride, float* h, cons
   tc::g_last_plan = p;
   const int P_ = p.P;
   const long long pack_bytes = (long long)(1 + KH * KW * P_ + P_) * (2 * Ch * p.rb);
-  tc::Args a{x, h, (const uint8_t*)wpack, b1, b2, b3, bias1_b, z, ldj, add, logp_c, logp_scale, pack_bytes, tc::env_int("CFPP_TC_REPL", 1), tc::env_int("CFPP_TC_DBG", 0), tc::g_prof};
+  tc::Args a{x, h, (const uint8_t*)wpack, b1, b2, b3, bias1_b, z, ldj, add, logp_c, logp_scale, h1_out, h2_out, pack_bytes, tc::env_int("CFPP_TC_REPL", 1), tc::env_int("CFPP_TC_DBG", 0), tc::g_prof};
   const int slots = num_sms() * p.occ;
   const int grid = p.ntiles < slots ? p.ntiles : slots;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1177,8 +1196,9 @@ static int conv_cond_tc_launch(const float* x, int64_t x_bstride, float* h, cons
       cudaFuncSetAttribute(kernels[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
   }
-  const int ki = p.pipe ? 16 + (p.seg ? 2 : 0) + (a.prof != nullptr ? 1 : 0)
-                        : (p.occ == 2 ? 8 : 0) | (p.seg ? 4 : 0) | (a.prof != nullptr ? 2 : 0) | (p.kind ? 1 : 0);
+  const bool aux = a.prof != nullptr || h1_out != nullptr || h2_out != nullptr;   // the profile-variant kernels also carry the training outputs
+  const int ki = p.pipe ? 16 + (p.seg ? 2 : 0) + (aux ? 1 : 0)
+                        : (p.occ == 2 ? 8 : 0) | (p.seg ? 4 : 0) | (aux ? 2 : 0) | (p.kind ? 1 : 0);
   kernels[ki]<<<grid, tc::cta_threads(p.occ), p.smem_bytes, st>>>(p, a);
   return check_launch("conv_cond_tc_fwd");
 }
@@ -1187,6 +1207,15 @@ extern "C" int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h
                                      const float* b1, const float* bias1_b, const float* b2, const float* b3,
                                      int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, void* stream) {
   return conv_cond_tc_launch(x, x_bstride, h, wpack, b1, bias1_b, b2, b3, nullptr, nullptr, nullptr, nullptr, 0.f, B, Cin, Ch, Cout, H, W, KH, KW, stream);
+}
+
+/* Training forward of the conditioner: h as above plus the post-ReLU activations a1 = relu(W1 x0 + b1), a2 = relu(W2 * a1 + b2) as fp32
+ * (B, Ch, H, W), which the backward pass needs (ReLU masks, weight gradients). */
+extern "C" int cfpp_conv_cond_tc_train_fwd(const float* x, int64_t x_bstride, float* h, float* a1, float* a2, const void* wpack,
+                                           const float* b1, const float* bias1_b, const float* b2, const float* b3,
+                                           int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, void* stream) {
+  CFPP_REQUIRE(h && a1 && a2, "conv_cond_tc_train: null output");
+  return conv_cond_tc_launch(x, x_bstride, h, wpack, b1, bias1_b, b2, b3, nullptr, nullptr, nullptr, nullptr, 0.f, B, Cin, Ch, Cout, H, W, KH, KW, stream, a1, a2);
 }
 
 extern "C" int cfpp_conv_cond_tc_coupling_supported(int B, int C, int Ch, int H, int W, int KH, int KW) {

@@ -493,6 +493,23 @@ def conv_cond_tc(x, cin, wpack, b1, b2, b3, ch, H, W, KH, KW, cout, bias1_b=None
     return h
 
 
+def conv_cond_tc_train(x, cin, wpack, b1, b2, b3, ch, H, W, KH, KW, cout, bias1_b=None):
+    """Training forward of the tensor-core conditioner: (h, a1, a2) with the post-ReLU activations the backward pass reads, or None
+    (nothing launched) when this shape has no plan."""
+    _need_cuda(x, wpack)
+    xv, bstride = _half_view(x)
+    B = x.shape[0]
+    if x.dtype != torch.float32 or not lib().cfpp_conv_cond_tc_supported(B, cin, ch, cout, H, W, KH, KW, bstride) or xv.data_ptr() % 16:
+        return None
+    h = torch.empty((B, cout, H, W), device=x.device, dtype=torch.float32)
+    a1 = torch.empty((B, ch, H, W), device=x.device, dtype=torch.float32)
+    a2 = torch.empty((B, ch, H, W), device=x.device, dtype=torch.float32)
+    _set_work(bytes=4.0 * B * H * W * (cin + cout + 2 * ch), flops=2.0 * B * H * W * (cin * ch + ch * ch * KH * KW + ch * cout), shape=f'Ch{ch}x{H}x{W}')
+    _call('conv_cond_tc_train_fwd', (_p(xv), bstride, _p(h), _p(a1), _p(a2), _p(wpack), _p(b1), _p(None if bias1_b is None else _f32(bias1_b)), _p(b2), _p(b3),
+                                     B, cin, ch, cout, H, W, KH, KW, _stream()))
+    return h, a1, a2
+
+
 def conv_cond_tc_coupling(x, wpack, b1, b2, b3, ch, KH, KW, add=None, logp_c=None, logp_scale=0.0, bias1_b=None):
     """Conditioner + affine coupling in one kernel: (z, ldj), or None (nothing launched) when the shape has no fused plan."""
     _need_cuda(x, wpack)

@@ -100,6 +100,27 @@ class ActNormFn(Function):
         return dx, dt, dlogs
 
 
+def _conditioner_fwd(x, Ch, w1, b1, w2, b2, w3, b3):
+    """(a1, a2, h) of the 3-conv conditioner on x[:, :Ch] (coupling.py:26-29).  float32 shapes with a tensor-core plan run the inference
+    conditioner kernel with its post-ReLU activations written out for the backward pass (cfpp_conv_cond_tc_train_fwd: fp16 hi / scaled-lo
+    pairs, fp32 faithful); everything else -- and CFPP_TRAIN_TC=0 -- runs three FP32 convolution launches."""
+    import os
+    if (x.dtype == torch.float32 and w2.dim() == 4 and os.environ.get('CFPP_TRAIN_TC', '1') != '0'
+            and w1.dtype == torch.float32 and w1.shape[1] == Ch and w1.numel() == w1.shape[0] * Ch):
+        ch, cout, KH, KW = w2.shape[0], w3.shape[0], w2.shape[2], w2.shape[3]
+        pack = ops.conv_cond_tc_pack(w1.detach(), w2.detach(), w3.detach(), Ch)
+        if pack is not None:
+            out = ops.conv_cond_tc_train(x, Ch, pack, b1.detach().float().contiguous(), b2.detach().float().contiguous(), b3.detach().float().contiguous(),
+                                         ch, x.shape[2], x.shape[3], KH, KW, cout)
+            if out is not None:
+                h, a1, a2 = out
+                return a1, a2, h
+    a1 = ops.conv2d_fwd(x, Ch, w1.detach(), b1.detach(), relu=True)
+    a2 = ops.conv2d_fwd(a1, a1.shape[1], w2.detach(), b2.detach(), relu=True)
+    h = ops.conv2d_fwd(a2, a2.shape[1], w3.detach(), b3.detach(), relu=False)
+    return a1, a2, h
+
+
 class CouplingConvFn(Function):
     """Coupling with the 3-conv conditioner (coupling.py:26-29,39-66), context-free.  Training forward = three conv launches with the
     post-ReLU activations saved + the coupling kernel; backward = coupling_bwd, then the conditioner's weight / data gradients, the
@@ -108,9 +129,7 @@ class CouplingConvFn(Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, w3, b3):
         Ch = x.shape[1] // 2
-        a1 = ops.conv2d_fwd(x, Ch, w1.detach(), b1.detach(), relu=True)
-        a2 = ops.conv2d_fwd(a1, a1.shape[1], w2.detach(), b2.detach(), relu=True)
-        h = ops.conv2d_fwd(a2, a2.shape[1], w3.detach(), b3.detach(), relu=False)
+        a1, a2, h = _conditioner_fwd(x, Ch, w1, b1, w2, b2, w3, b3)
         z, ldj = ops.coupling(x, h)
         ctx.save_for_backward(x, a1, a2, h, w1, w2, w3)
         return z, ldj
@@ -440,9 +459,7 @@ class CouplingCtxConvFn(Function):
     def forward(ctx, x, add, logp_c, w1, b1, w2, b2, w3, b3):
         Ch = x.shape[1] // 2
         HW = x.shape[2] * x.shape[3]
-        a1 = ops.conv2d_fwd(x, Ch, w1.detach(), b1.detach(), relu=True)
-        a2 = ops.conv2d_fwd(a1, a1.shape[1], w2.detach(), b2.detach(), relu=True)
-        h = ops.conv2d_fwd(a2, a2.shape[1], w3.detach(), b3.detach(), relu=False)
+        a1, a2, h = _conditioner_fwd(x, Ch, w1, b1, w2, b2, w3, b3)
         z, ldj = ops.coupling(x, h, add=add, logp_c=logp_c, logp_scale=float(HW))
         ctx.save_for_backward(x, add, a1, a2, h, w1, w2, w3)
         return z, ldj

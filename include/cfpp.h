@@ -139,6 +139,11 @@ int cfpp_conv_cond_tc_supported(int B, int Cin, int Ch, int Cout, int H, int W, 
 int cfpp_conv_cond_tc_fwd(const float* x, int64_t x_bstride, float* h, const void* wpack,
                           const float* b1, const float* bias1_b, const float* b2, const float* b3,
                           int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, void* stream);
+/* Training forward of the conditioner (coupling.py:26-29 under autograd): h as cfpp_conv_cond_tc_fwd plus the post-ReLU activations
+ * a1 = relu(W1 x0 + b1), a2 = relu(W2 * a1 + b2) as fp32 (B, Ch, H, W), which the backward pass reads (ReLU masks, weight gradients). */
+int cfpp_conv_cond_tc_train_fwd(const float* x, int64_t x_bstride, float* h, float* a1, float* a2, const void* wpack,
+                                const float* b1, const float* bias1_b, const float* b2, const float* b3,
+                                int B, int Cin, int Ch, int Cout, int H, int W, int KH, int KW, void* stream);
 /* The conditioner and the affine coupling transform it feeds (coupling.py:39-66) in ONE kernel: the conditioner output h never reaches
  * HBM.  x, z (B, C, H, W) contiguous; x0 = x[:, :C/2] is the conditioner input, h = NN(x0) (+ add[b, :] per channel: CN(c), additive
  * contextflow conditioning, coupling.py:45; NULL: none; bias1_b as in cfpp_conv_cond_tc_fwd for the concatenated form);

@@ -174,3 +174,30 @@ def test_tc_fused_coupling_every_plan_form_with_several_tiles_per_cta(B, C, H, W
     if hh is not None:
         want_h = _ref64(x[:, :cin], w1, b1, w2, b2, w3, b3)
         assert_close(hh.cpu().numpy(), want_h.numpy(), Z_RTOL, Z_ATOL * max(1.0, float(want_h.abs().max())), 'conditioner h')
+
+
+@pytest.mark.parametrize('B,C,H,W', [(5, 16, 16, 16), (9, 32, 8, 8), (10, 64, 4, 4), (301, 32, 8, 8), (700, 16, 16, 16), (2200, 64, 4, 4)])
+def test_tc_training_forward_writes_the_activations_the_backward_reads(B, C, H, W):
+    """cfpp_conv_cond_tc_train_fwd: h plus a1 = relu(W1 x0 + b1), a2 = relu(W2 * a1 + b2) (coupling.py:26-29), each against fp64 and
+    against the three-launch FP32 convolution route the training step used before."""
+    cin, ch = C // 2, 2 * C
+    tag = f'tct{B}.{C}.{H}.{W}'
+    w1, b1, w2, b2, w3, b3 = _weights(tag, cin, ch, C, 3, 3)
+    x = (synth.uniform(tag + 'x', (B, C, H, W)) * 2.0 - 1.0).to(dev)
+    pack = ops.conv_cond_tc_pack(w1.to(dev), w2.to(dev), w3.to(dev), cin)
+    out = ops.conv_cond_tc_train(x, cin, pack, b1.to(dev), b2.to(dev), b3.to(dev), ch, H, W, 3, 3, C)
+    assert out is not None, 'shape should have a plan'
+    h, a1, a2 = out
+    x0 = x[:, :cin].double().cpu()
+    r1 = F.relu(F.conv2d(x0, w1[:, :cin].double()[:, :, None, None], b1.double()))
+    r2 = F.relu(F.conv2d(F.pad(r1, (1, 1, 1, 1), mode='reflect'), w2.double(), b2.double()))
+    r3 = F.conv2d(r2, w3.double()[:, :, None, None], b3.double())
+    from tests.helpers import Z_ATOL, Z_RTOL, assert_close
+    for got, want, what in ((a1, r1, 'a1'), (a2, r2, 'a2'), (h, r3, 'h')):
+        assert_close(got.cpu().numpy(), want.numpy(), Z_RTOL, Z_ATOL * max(1.0, float(want.abs().max())), f'training forward {what}')
+    # every element of a1 / a2 is written (halo rows rewrite their mirror pixel), none left from the allocation
+    assert torch.isfinite(a1).all() and torch.isfinite(a2).all()
+    f1 = ops.conv2d_fwd(x, cin, w1.to(dev)[:, :cin, None, None].contiguous(), b1.to(dev), relu=True)
+    f2 = ops.conv2d_fwd(f1, ch, w2.to(dev), b2.to(dev), relu=True)
+    assert (a1 - f1).abs().max().item() <= 2e-5 * max(1.0, float(f1.abs().max()))
+    assert (a2 - f2).abs().max().item() <= 2e-5 * max(1.0, float(f2.abs().max()))
