@@ -5,6 +5,8 @@
 // First version: FP32 CUDA cores, one CTA per sample with the sample resident in shared memory; every reduction over the batch is
 // two-stage with a fixed order (no atomics): gradients are bit-identical run to run.
 #include <math.h>
+#include <stdlib.h>
+#include <stdint.h>
 #include "common.cuh"
 
 namespace cfpp {
@@ -247,6 +249,181 @@ __global__ void __launch_bounds__(256) conv2d_bwd_data_kernel(const float* __res
     for (int a = 0; a < ny; ++a)
       for (int c = 0; c < nx; ++c) v += spad[ci * Sp + uy[a] * Wp + ux[c]];
     if (act && !(act[b * act_bstride + (int64_t)ci * HW + q] > 0.f)) v = 0.f;
+    float* o = din + b * din_bstride + (int64_t)ci * HW + q;
+    *o = accumulate ? *o + v : v;
+  }
+}
+
+// H = W = 1 with a 1x1 kernel: the FC / CouplingFC layers of the context-encoder flows (`x.view(-1, D, 1, 1)`, coupling.py:83-91 of the
+// reference) at widths of 10-40 channels.  One CTA per sample would leave 256 threads with a few hundred MACs and a grid of B CTAs per
+// launch (36 encoders x 14 such launches per training step); here a CTA takes kRowsPerCta samples as rows of a small matrix product:
+//   FWD : out[b, o] = [relu](bias[o] + sum_i W[o, i] [relu_in](in[b, i]))          (o = co, i = ci)
+//   !FWD: out[b, o] (+)= [act[b, o] > 0] sum_i W[i, o] in[b, i]                    (o = ci, i = co: the gradient w.r.t. the input)
+// the weight matrix sits in shared memory as [i][o] (threads of a warp = consecutive o: conflict-free), the sample rows as [s][i].
+// Summation order per output = i ascending, as in the per-sample kernels (bit-identical results).
+constexpr int kRowsPerCta = 64;
+template <bool FWD>
+__global__ void __launch_bounds__(256) conv_rows_kernel(const float* __restrict__ in, int64_t in_bstride, const float* __restrict__ W,
+                                                        const float* __restrict__ bias, const float* __restrict__ act, int64_t act_bstride,
+                                                        float* __restrict__ out, int64_t out_bstride, int accumulate,
+                                                        int B, int NI, int NO, int relu) {
+  extern __shared__ float smr[];
+  const int NOp = NO | 1, NIp = NI | 1;
+  float* Ms = smr;                                             // [NI][NOp]
+  float* Xs = smr + (size_t)NI * NOp;                          // [kRowsPerCta][NIp]
+  const int64_t b0 = (int64_t)blockIdx.x * kRowsPerCta;
+  const int nS = (int)min((int64_t)kRowsPerCta, (int64_t)B - b0);
+  for (int idx = threadIdx.x; idx < NI * NO; idx += 256) {
+    const int o = FWD ? idx / NI : idx % NO, i = FWD ? idx - o * NI : idx / NO;      // W is (Cout, Cin): FWD (o, i), else (i, o); idx runs along W
+    Ms[i * NOp + o] = __ldg(W + idx);
+  }
+  const bool relu_in = FWD && (relu & 2) != 0;
+  for (int idx = threadIdx.x; idx < nS * NI; idx += 256) {
+    const int sI = idx / NI, i = idx - sI * NI;
+    const float v = __ldg(in + (b0 + sI) * in_bstride + i);
+    Xs[sI * NIp + i] = relu_in ? fmaxf(v, 0.f) : v;
+  }
+  __syncthreads();
+  for (int item = threadIdx.x; item < nS * NO; item += 256) {
+    const int sI = item / NO, o = item - sI * NO;
+    const float* xr = Xs + sI * NIp;
+    const float* mr = Ms + o;
+    float acc = (FWD && bias) ? __ldg(bias + o) : 0.f;
+    for (int i = 0; i < NI; ++i) acc = fmaf(mr[i * NOp], xr[i], acc);
+    const int64_t b = b0 + sI;
+    if (FWD) {
+      out[b * out_bstride + o] = (relu & 1) ? fmaxf(acc, 0.f) : acc;
+    } else {
+      if (act && !(act[b * act_bstride + o] > 0.f)) acc = 0.f;
+      float* op = out + b * out_bstride + o;
+      *op = accumulate ? *op + acc : acc;
+    }
+  }
+}
+
+// Register-tiled 3x3 form of the kernel above (the conditioner's middle convolution: 94 % of its backward-data flops).  Same two phases
+// and the same summation order per output (co outer, taps inner: results are bit-identical to the generic tile), but a thread owns TP
+// CONSECUTIVE padded positions of one row x 4 input channels.  Per output channel co: 3 rows x (TP + 2) staged gradients arrive by
+// 128/64-bit shared loads (rows of WzP columns, a multiple of 4, so every group starts 16-byte aligned) and the 4 x 9 weights
+// W[co, ci0..ci0+3, :, :] are 36 contiguous floats = nine 128-bit warp-uniform loads; together they feed 36 TP FMAs (TP = 4: 144 FMAs per 15
+// loads, against 16 per 8 in the generic tile).  TP = 6 covers a whole padded row of a 4-wide image with one group.
+template <int TP, bool PF>
+__global__ void __launch_bounds__(256, 2) conv2d_bwd_data3_kernel(const float* __restrict__ dout, const float* __restrict__ W,
+                                                                  const float* __restrict__ act, int64_t act_bstride,
+                                                                  float* __restrict__ din, int64_t din_bstride, int accumulate,
+                                                                  int Cin, int Cout, int H, int Wd, int NG, int WzP) {
+  constexpr int NV = TP + 2;                                   // staged gradients per row that TP positions x 3 column taps read
+  extern __shared__ __align__(16) float sm3[];
+  const int HW = H * Wd, Hp = H + 2, Wp = Wd + 2, Hz = H + 4;
+  const int SzC = Hz * WzP, Sp = odd_stride(Hp * Wp);
+  float* sz = sm3;                                             // [Cout][Hz][WzP]: dout at (y + 2, x + 2), zeros elsewhere
+  float* spad = sm3 + (size_t)Cout * SzC + 4;                  // [Cin][Sp]; the 4 floats between are zero: with TP = 4 rows are stored WITHOUT
+                                                               // padding (WzP = 4 NG: the groups of a warp read consecutive 16-byte chunks, no bank
+                                                               // conflicts) and the last group's two extra columns wrap into the next row's zero halo
+  const int64_t b = blockIdx.x;
+  const int tid = threadIdx.x;
+  {   // stage dout: LPR lanes per staged row (a power of two >= WzP when WzP <= 32), four rows in flight per thread
+    const int LPR = WzP <= 8 ? 8 : WzP <= 16 ? 16 : 32, RPW = 32 / LPR;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int lr = lane / LPR, lc = lane - lr * LPR;
+    const int rows = Cout * Hz, rstep = 8 * RPW;
+    const float* src0 = dout + b * (int64_t)Cout * HW;
+    if (tid < 4) sz[(size_t)Cout * SzC + tid] = 0.f;
+    for (int col = lc; col < WzP; col += LPR) {
+      const int x = col - 2;
+      const bool xin = x >= 0 && x < Wd;
+      for (int row0 = warp * RPW + lr; row0 < rows; row0 += 4 * rstep) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int row = row0 + u * rstep;
+          const int c = row / Hz, y = row - c * Hz - 2;
+          v[u] = (row < rows && xin && y >= 0 && y < H) ? __ldg(src0 + ((int64_t)c * H + y) * Wd + x) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int row = row0 + u * rstep;
+          if (row < rows) sz[(size_t)row * WzP + col] = v[u];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int npg = Hp * NG, nitems = npg * (Cin >> 2);
+  for (int item = tid; item < nitems; item += 256) {
+    const int cg = item / npg, pgi = item - cg * npg;
+    const int uy = pgi / NG, ux0 = (pgi - uy * NG) * TP, ci0 = cg * 4;
+    const float* gp = sz + uy * WzP + ux0;                     // tap row kh reads staged row uy + 2 - kh, tap column kw reads column ux + 2 - kw
+    const float4* wq = reinterpret_cast<const float4*>(W + (int64_t)ci0 * 9);
+    const int wstep = Cin * 9 / 4;                             // float4s between consecutive co (Cin % 4 == 0)
+    float acc[4][TP];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int j = 0; j < TP; ++j) acc[c][j] = 0.f;
+    float4 wn[9];                                              // PF: the weights of the next output channel are requested one iteration ahead
+    if (PF) {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) wn[q] = __ldg(wq + q);
+    }
+#pragma unroll 2
+    for (int co = 0; co < Cout; ++co) {                        // unrolled by two: the (w, wn) register sets swap roles instead of being copied
+      float w[36];
+      if (PF) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) { w[4 * q] = wn[q].x; w[4 * q + 1] = wn[q].y; w[4 * q + 2] = wn[q].z; w[4 * q + 3] = wn[q].w; }
+        wq += co + 1 < Cout ? wstep : 0;                       // the last iteration re-reads its own row (in bounds, unused)
+#pragma unroll
+        for (int q = 0; q < 9; ++q) wn[q] = __ldg(wq + q);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) { const float4 t = __ldg(wq + q); w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w; }
+        wq += wstep;
+      }
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const float* r = gp + (2 - kh) * WzP;
+        float v[NV];
+        {
+          const float4 t = *reinterpret_cast<const float4*>(r);
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        }
+        if (NV == 6) { const float2 t = *reinterpret_cast<const float2*>(r + 4); v[4] = t.x; v[5] = t.y; }
+        else { const float4 t = *reinterpret_cast<const float4*>(r + 4); v[4] = t.x; v[5] = t.y; v[NV - 2] = t.z; v[NV - 1] = t.w; }
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float wv = w[c * 9 + kh * 3 + kw];
+#pragma unroll
+            for (int j = 0; j < TP; ++j) acc[c][j] = fmaf(wv, v[j + 2 - kw], acc[c][j]);
+          }
+      }
+      gp += SzC;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int j = 0; j < TP; ++j)
+        if (ux0 + j < Wp) spad[(ci0 + c) * Sp + uy * Wp + ux0 + j] = acc[c][j];
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int i = tid; i < Cin * HW; i += 256) {                  // fold the reflect halo back, mask, store (the generic kernel's summation order)
+    const int ci = i / HW, q = i - ci * HW;
+    const int qy = q / Wd, qx = q - qy * Wd;
+    const float* sp = spad + ci * Sp;
+    auto rowsum = [&](int uyv, float v) {
+      const float* r = sp + uyv * Wp;
+      v += r[qx + 1];
+      if (qx == 1) v += r[0];
+      if (qx == Wd - 2) v += r[Wd + 1];
+      return v;
+    };
+    float v = rowsum(qy + 1, 0.f);
+    if (qy == 1) v = rowsum(0, v);
+    if (qy == H - 2) v = rowsum(H + 1, v);
+    if (act && !(__ldg(act + b * act_bstride + (int64_t)ci * HW + q) > 0.f)) v = 0.f;
     float* o = din + b * din_bstride + (int64_t)ci * HW + q;
     *o = accumulate ? *o + v : v;
   }
@@ -618,10 +795,11 @@ __global__ void __launch_bounds__(256) gmm_ctx_fwd_kernel(const float* __restric
   __syncthreads();
   const float* cm = c + b * 2 * MK * D; const float* cs = cm + (int64_t)MK * D;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int hw_shift = (HW & (HW - 1)) == 0 ? __ffs(HW) - 1 : -1;     // HW a power of two (every image level): d = e >> shift, no division per element
   for (int mk = w; mk < MK; mk += nw) {
     float acc = 0.f;
     for (int e = l; e < n; e += 32) {
-      const int d = e / HW;
+      const int d = hw_shift >= 0 ? e >> hw_shift : e / HW;
       const float mu = mG[(int64_t)mk * n + e] + cm[mk * D + d];
       const float s = softplus_f(sG[(int64_t)mk * n + e] + cs[mk * D + d]);
       const float df = sx[e] - mu;
@@ -675,11 +853,16 @@ __global__ void __launch_bounds__(256) gmm_ctx_bwd_kernel(const float* __restric
     for (int hw = l; hw < HW; hw += 32) {
       const int e = d * HW + hw;
       const float raw = sG[(int64_t)mk * n + e] + os;
-      const float s = softplus_f(raw);
+      // softplus and its derivative from ONE exponential: t = e^raw, s = log1p(t), sigmoid(raw) = t / (1 + t)  (raw > 20: s = raw, sigmoid = 1
+      // to fp32, F.softplus's threshold); 1 / s once, its powers by multiplication
+      const bool big = raw > 20.f;
+      const float t = expf(big ? 0.f : raw);
+      const float s = big ? raw : log1pf(t);
+      const float sig = big ? 1.f : t / (1.f + t);
       const float df = sx[e] - (mG[(int64_t)mk * n + e] + om);
-      const float is2 = 1.0f / (s * s);
+      const float rs = 1.0f / s, is2 = rs * rs;
       a0 += df * is2;
-      a1 += (df * df * is2 / s - 1.0f / s) * (1.0f / (1.0f + expf(-raw)));
+      a1 += (df * df * is2 - 1.0f) * rs * sig;
       if (part) dxp[w * n + e] -= wt * df * is2;       // this warp's share of dx[e] = sum_mk w (mu - x) / s^2 (one lane per e: no race)
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1);
@@ -794,6 +977,16 @@ inline int grid1d(int64_t n, int per_thread = 1) {
   return (int)(blocks < 1 ? 1 : blocks);
 }
 
+inline bool conv_rows_enabled() {
+  const char* e = getenv("CFPP_CONV_ROWS");                    // 0: keep the per-sample kernels for H = W = 1 (A/B switch; same results bit for bit)
+  return !(e && e[0] == '0');
+}
+
+inline bool bwd_data3_enabled() {
+  const char* e = getenv("CFPP_BWD_DATA3");                    // read per call: the tests flip it to compare the two routes bit for bit
+  return !(e && e[0] == '0');
+}
+
 template <typename Kern>
 inline bool want_smem(Kern k, size_t bytes) {
   if (bytes <= 48 * 1024) return true;
@@ -852,6 +1045,13 @@ extern "C" int cfpp_conv2d_fwd(const float* in, int64_t in_bstride, const float*
                                int B, int Cin, int Cout, int H, int Wd, int KH, int KW, int relu, void* stream) {
   CFPP_REQUIRE(conv_shape_ok(H, Wd, KH, KW), "conv2d: kernel %dx%d on %dx%d", KH, KW, H, Wd);
   if (B <= 0) return CFPP_OK;
+  if (H * Wd == 1 && KH == 1 && KW == 1 && conv_rows_enabled()) {
+    const size_t smr = ((size_t)Cin * (Cout | 1) + (size_t)kRowsPerCta * (Cin | 1)) * sizeof(float);
+    if (want_smem(conv_rows_kernel<true>, smr)) {
+      conv_rows_kernel<true><<<(B + kRowsPerCta - 1) / kRowsPerCta, 256, smr, (cudaStream_t)stream>>>(in, in_bstride, W, bias, nullptr, 0, out, Cout, 0, B, Cin, Cout, relu);
+      return check_launch("conv2d_fwd");
+    }
+  }
   const size_t smem = (size_t)Cin * odd_stride((H + 2 * (KH / 2)) * (Wd + 2 * (KW / 2))) * sizeof(float);
   CFPP_CONV_DISPATCH(KH, KW, {
     CFPP_REQUIRE(want_smem(conv2d_fwd_kernel<kKH, kKW>, smem), "conv2d_fwd: sample of %zu bytes exceeds shared memory", smem);
@@ -864,6 +1064,30 @@ extern "C" int cfpp_conv2d_bwd_data(const float* dout, const float* W, const flo
                                     int accumulate, int B, int Cin, int Cout, int H, int Wd, int KH, int KW, void* stream) {
   CFPP_REQUIRE(conv_shape_ok(H, Wd, KH, KW), "conv2d: kernel %dx%d on %dx%d", KH, KW, H, Wd);
   if (B <= 0) return CFPP_OK;
+  if (H * Wd == 1 && KH == 1 && KW == 1 && conv_rows_enabled()) {
+    const size_t smr = ((size_t)Cout * (Cin | 1) + (size_t)kRowsPerCta * (Cout | 1)) * sizeof(float);
+    if (want_smem(conv_rows_kernel<false>, smr)) {
+      conv_rows_kernel<false><<<(B + kRowsPerCta - 1) / kRowsPerCta, 256, smr, (cudaStream_t)stream>>>(dout, Cout, W, nullptr, act, act_bstride, din, din_bstride, accumulate, B, Cout, Cin, 0);
+      return check_launch("conv2d_bwd_data");
+    }
+  }
+  if (KH == 3 && KW == 3 && Cin % 4 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 && bwd_data3_enabled()) {
+    // register-tiled 3x3 route; CFPP_BWD_DATA3=0 keeps the generic tile (same results bit for bit: an A/B switch for timing)
+    const int TP = Wd + 2 <= 6 ? 6 : 4;
+    const int NG = (Wd + 2 + TP - 1) / TP, WzP = TP == 4 ? 4 * NG : 8;
+    const size_t smem3 = ((size_t)Cout * (H + 4) * WzP + 4 + (size_t)Cin * odd_stride((H + 2) * (Wd + 2))) * sizeof(float);
+    bool ok = false;
+    const char* ev = getenv("CFPP_BWD_DATA3");
+    const bool pf = !(ev && ev[0] == '2');                        // CFPP_BWD_DATA3=2: without the one-iteration-ahead weight loads (A/B)
+#define CFPP_BD3(TP_, PF_) do { auto kern = conv2d_bwd_data3_kernel<TP_, PF_>; \
+      if ((ok = want_smem(kern, smem3))) { \
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   /* two samples resident per SM */ \
+        kern<<<B, 256, smem3, (cudaStream_t)stream>>>(dout, W, act, act_bstride, din, din_bstride, accumulate, Cin, Cout, H, Wd, NG, WzP); } } while (0)
+    if (TP == 6) { if (pf) CFPP_BD3(6, true); else CFPP_BD3(6, false); }
+    else { if (pf) CFPP_BD3(4, true); else CFPP_BD3(4, false); }
+#undef CFPP_BD3
+    if (ok) return check_launch("conv2d_bwd_data");
+  }
   const size_t smem = ((size_t)Cout * odd_stride((H + 2 * (KH - 1)) * (Wd + 2 * (KW - 1))) +
                        (KH * KW == 1 ? 0 : (size_t)Cin * odd_stride((H + 2 * (KH / 2)) * (Wd + 2 * (KW / 2))))) * sizeof(float);
   CFPP_CONV_DISPATCH(KH, KW, {

@@ -2,6 +2,8 @@
 (experiment_ad.py:204-209) through the libcfpp backward kernels, against gradients the unmodified reference produced with torch
 autograd (tests/golden/train_*.npz) and against autograd over the oracle on fresh inputs; one torch.optim.AdamW step (the optimizer
 model.py:289 builds) lands on the reference's updated parameters; op-level checks of every backward kernel."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -179,7 +181,9 @@ def test_actnorm_bwd(B, D, H, W):
 
 
 @pytest.mark.parametrize('B,Cin,Cout,H,W,KH,KW', [(3, 4, 16, 16, 16, 1, 1), (3, 16, 16, 16, 16, 3, 3), (5, 64, 64, 8, 8, 3, 3), (4, 112, 112, 8, 1, 3, 1),
-                                                   (2, 28, 112, 8, 1, 1, 1), (2, 6, 10, 2, 2, 3, 3), (3, 5, 7, 3, 4, 3, 3)])
+                                                   (2, 28, 112, 8, 1, 1, 1), (2, 6, 10, 2, 2, 3, 3), (3, 5, 7, 3, 4, 3, 3),
+                                                   (3, 128, 128, 4, 4, 3, 3), (2, 8, 12, 2, 2, 3, 3), (2, 4, 8, 5, 7, 3, 3), (3, 32, 32, 16, 16, 3, 3),
+                                                   (70, 10, 40, 1, 1, 1, 1), (131, 20, 20, 1, 1, 1, 1), (64, 40, 20, 1, 1, 1, 1)])
 def test_conv2d_family(B, Cin, Cout, H, W, KH, KW):
     x = synth.normal('cvx', (B, Cin + 3, H, W)); w = synth.normal('cvw', (Cout, Cin, KH, KW)) * 0.2; b = synth.normal('cvb', (Cout,)) * 0.1
     dout = synth.normal('cvd', (B, Cout, H, W))
@@ -196,6 +200,21 @@ def test_conv2d_family(B, Cin, Cout, H, W, KH, KW):
     assert_close(db.cpu().numpy(), bd.grad.numpy(), 1e-4, 1e-4 * float(bd.grad.abs().max()), 'db')
     din = ops.conv2d_bwd_data(g, w.cuda())
     assert_close(din.cpu().numpy(), xd.grad.numpy(), 1e-4, 1e-5 * float(xd.grad.abs().max()), 'din')
+    if (KH == 3 and KW == 3 and Cin % 4 == 0) or (H * W == 1 and KH == 1 and KW == 1):
+        # the register-tiled 3x3 route and the rows form of H = W = 1 keep the generic kernels' summation order: bit-identical
+        masked = ops.conv2d_bwd_data(g, w.cuda(), act=xc)          # ReLU mask of the layer below: x > 0 on the first Cin channels
+        got_in = ops.conv2d_fwd(xc, Cin, w.cuda(), b.cuda(), relu=True, relu_in=True)
+        os.environ['CFPP_BWD_DATA3'] = '0'; os.environ['CFPP_CONV_ROWS'] = '0'
+        try:
+            din_generic = ops.conv2d_bwd_data(g, w.cuda())
+            masked_generic = ops.conv2d_bwd_data(g, w.cuda(), act=xc)
+            got_generic = ops.conv2d_fwd(xc, Cin, w.cuda(), b.cuda(), relu=True)
+            got_in_generic = ops.conv2d_fwd(xc, Cin, w.cuda(), b.cuda(), relu=True, relu_in=True)
+        finally:
+            del os.environ['CFPP_BWD_DATA3'], os.environ['CFPP_CONV_ROWS']
+        assert torch.equal(din, din_generic) and torch.equal(masked, masked_generic)
+        assert torch.equal(got, got_generic) and torch.equal(got_in, got_in_generic)
+        assert torch.equal(masked, torch.where(xc[:, :Cin] > 0, din, torch.zeros_like(din)))
     wide = torch.ones(B, Cin + 3, H, W, device='cuda')
     ops.conv2d_bwd_data(g, w.cuda(), out=wide, accumulate=True)
     assert_close(wide[:, :Cin].cpu().numpy(), xd.grad.numpy() + 1.0, 1e-4, 1e-5 * float(xd.grad.abs().max()) + 1e-6, 'din accumulate')
