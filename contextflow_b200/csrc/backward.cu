@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) conv2d_bwd_data_kernel(const float* __res
 //   !FWD: out[b, o] (+)= [act[b, o] > 0] sum_i W[i, o] in[b, i]                    (o = ci, i = co: the gradient w.r.t. the input)
 // the weight matrix sits in shared memory as [i][o] (threads of a warp = consecutive o: conflict-free), the sample rows as [s][i].
 // Summation order per output = i ascending, as in the per-sample kernels (bit-identical results).
-constexpr int kRowsPerCta = 64;
+constexpr int kRowsPerCta = 16;                                // 512 CTAs at B = 8192: the launch is latency-bound, not work-bound
 template <bool FWD>
 __global__ void __launch_bounds__(256) conv_rows_kernel(const float* __restrict__ in, int64_t in_bstride, const float* __restrict__ W,
                                                         const float* __restrict__ bias, const float* __restrict__ act, int64_t act_bstride,
@@ -299,6 +299,53 @@ __global__ void __launch_bounds__(256) conv_rows_kernel(const float* __restrict_
       *op = accumulate ? *op + acc : acc;
     }
   }
+}
+
+// Weight / bias gradient of the same H = W = 1 layers: dW[co, ci] = sum_b dout[b, co] in[b, ci], db[co] = sum_b dout[b, co].  A CTA owns a
+// chunk of samples (tiles of kRowsW rows of `in` and `dout` staged in shared memory), a thread up to 8 entries of dW; the chunks' partial
+// sums go to the workspace and chunk_sum_kernel adds them in a fixed order (deterministic, no atomics) -- the per-sample family's scheme
+// with 64 samples per CTA instead of ~14 spread over 256 mostly idle threads.
+constexpr int kRowsW = 64, kRowsWEntries = 8;
+__global__ void __launch_bounds__(256) conv_rows_bwd_weight_kernel(const float* __restrict__ in, int64_t in_bstride, const float* __restrict__ dout,
+                                                                   float* __restrict__ partW, float* __restrict__ partb,
+                                                                   int B, int Cin, int Cout, int per_chunk) {
+  extern __shared__ float smw[];
+  const int CIp = Cin | 1, COp = Cout | 1, nW = Cin * Cout;
+  float* Xs = smw;                                             // [kRowsW][CIp]
+  float* Gs = smw + (size_t)kRowsW * CIp;                      // [kRowsW][COp]
+  const int tid = threadIdx.x;
+  const int64_t b_lo = (int64_t)blockIdx.x * per_chunk;
+  const int64_t b_hi = min((int64_t)B, b_lo + per_chunk);
+  int xo[kRowsWEntries], go[kRowsWEntries];
+  float acc[kRowsWEntries];
+#pragma unroll
+  for (int k = 0; k < kRowsWEntries; ++k) {
+    const int idx = tid + k * 256, co = idx < nW ? idx / Cin : 0;
+    go[k] = co; xo[k] = idx < nW ? idx - co * Cin : 0; acc[k] = 0.f;
+  }
+  float accb = 0.f;
+  for (int64_t b0 = b_lo; b0 < b_hi; b0 += kRowsW) {
+    const int nS = (int)min((int64_t)kRowsW, b_hi - b0);
+    for (int idx = tid; idx < nS * Cin; idx += 256) { const int sI = idx / Cin, i = idx - sI * Cin; Xs[sI * CIp + i] = __ldg(in + (b0 + sI) * in_bstride + i); }
+    for (int idx = tid; idx < nS * Cout; idx += 256) { const int sI = idx / Cout, o = idx - sI * Cout; Gs[sI * COp + o] = __ldg(dout + (b0 + sI) * Cout + o); }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kRowsWEntries; ++k) {
+      if (tid + k * 256 < nW) {
+        const float* gp = Gs + go[k];
+        const float* xp = Xs + xo[k];
+        float a = acc[k];
+        for (int sI = 0; sI < nS; ++sI) a = fmaf(gp[sI * COp], xp[sI * CIp], a);
+        acc[k] = a;
+      }
+    }
+    if (partb && tid < Cout) for (int sI = 0; sI < nS; ++sI) accb += Gs[sI * COp + tid];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < kRowsWEntries; ++k)
+    if (tid + k * 256 < nW) partW[(int64_t)blockIdx.x * nW + tid + k * 256] = acc[k];
+  if (partb && tid < Cout) partb[(int64_t)blockIdx.x * Cout + tid] = accb;
 }
 
 // Register-tiled 3x3 form of the kernel above (the conditioner's middle convolution: 94 % of its backward-data flops).  Same two phases
@@ -1125,6 +1172,25 @@ extern "C" int cfpp_conv2d_bwd_weight(const float* in, int64_t in_bstride, const
   CFPP_REQUIRE(workspace != nullptr, "conv2d_bwd_weight: workspace required (cfpp_conv2d_bwd_weight_workspace_floats)");
   int NCO, coblocks, chunks, per_chunk;
   bwd_weight_plan(B, Cin, Cout, NCO, coblocks, chunks, per_chunk);
+  if (HW == 1 && KK == 1 && nW <= 256 * kRowsWEntries && Cout <= 256 && conv_rows_enabled()) {
+    int chunks_r = (B + kRowsW - 1) / kRowsW; if (chunks_r > chunks) chunks_r = chunks;          // never more partial slices than the workspace holds
+    const int per_r = (B + chunks_r - 1) / chunks_r;
+    chunks_r = (B + per_r - 1) / per_r;
+    float* pW = workspace; float* pb = workspace + (int64_t)chunks_r * nW;
+    const size_t smw = (size_t)kRowsW * ((Cin | 1) + (Cout | 1)) * sizeof(float);
+    if (want_smem(conv_rows_bwd_weight_kernel, smw)) {
+      conv_rows_bwd_weight_kernel<<<chunks_r, 256, smw, (cudaStream_t)stream>>>(in, in_bstride, dout, pW, db ? pb : nullptr, B, Cin, Cout, per_r);
+      int rc = check_launch("conv2d_bwd_weight");
+      if (rc != CFPP_OK) return rc;
+      chunk_sum_kernel<<<(unsigned)((nW + 31) / 32), 256, 0, (cudaStream_t)stream>>>(pW, dW, nW, chunks_r);
+      if ((rc = check_launch("conv2d_bwd_weight_sum")) != CFPP_OK) return rc;
+      if (db) {
+        chunk_sum_kernel<<<(Cout + 31) / 32, 256, 0, (cudaStream_t)stream>>>(pb, db, Cout, chunks_r);
+        rc = check_launch("conv2d_bwd_bias_sum");
+      }
+      return rc;
+    }
+  }
   float* partW = workspace; float* partb = workspace + (int64_t)chunks * nW;
   const size_t smem = ((size_t)Cin * odd_stride((H + 2 * (KH / 2)) * (Wd + 2 * (KW / 2))) + (size_t)NCO * odd_stride(HW)) * sizeof(float);
   const dim3 grid(chunks, coblocks);
