@@ -363,10 +363,13 @@ def test_graphed_train_step_without_context():
             assert torch.equal(got[k], p.grad), k
 
 
-def test_context_mixture_backward_large_sample_fallback():
+@pytest.mark.parametrize('fast', [False, True])
+def test_context_mixture_backward_large_sample_fallback(fast, monkeypatch):
     """cfpp_gmm_ctx_train_bwd keeps eight partial dx rows in shared memory; a sample too large for that (9 x D*HW floats > 200 KB)
     takes the recompute-sigma path instead of failing.  Both paths against float64 autograd."""
-    for D, H, W in ((6, 8, 8), (40, 16, 12)):                   # 384 elements (partials) / 7680 elements (fallback)
+    if fast:                                                    # CFPP_GMM_FAST=1: ex2 / lg2 / rcp.approx forms (opt-in), same op-level tolerances
+        monkeypatch.setenv('CFPP_GMM_FAST', '1')
+    for D, H, W in ((6, 8, 8), (40, 16, 12), (64, 4, 4)):       # 384 elements (partials) / 7680 elements (fallback) / HW < 32 (lane segments)
         B, M, K = 3, 2, 4
         n = D * H * W
         x = synth.normal('gf:x', (B, D, H, W)); mG = synth.normal('gf:m', (M, K, D, H, W)); sG = synth.normal('gf:s', (M, K, D, H, W))
