@@ -92,6 +92,8 @@ class FlowSequential(nn.Module):
         B = input.shape[0]
         out = input
         terms = []
+        if torch.is_grad_enabled():
+            ops.begin_training_step()                               # per-step caches of the backward pass (context sort of embed_scatter) start empty
         # under autograd every layer evaluates its own encoder (trainable encoders run their module tree: training.encode), in layer order
         groups = self._encoder_groups() if (context is not None and not torch.is_grad_enabled()) else {}
         for i, module in enumerate(self.sequence_modules):
@@ -153,6 +155,8 @@ class FlowSequential(nn.Module):
         return self._log_prob_single(input, context)
 
     def _log_prob_single(self, input, context=None):
+        if torch.is_grad_enabled():
+            ops.begin_training_step()
         g = getattr(self, '_graphed', None)
         if g is not None and input.is_cuda and not torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing():
             from .. import rng

@@ -1110,19 +1110,41 @@ def gmm_ctx_train_bwd(x, mG, sG, c, resp, g, need_dx=True, dx_out=None):
     return dx, dc
 
 
+# One training step scatters into the embedding tables of every context-conditioned layer (39 layers x 2 features in BASELINE cfg2) and each
+# call sorted the SAME context column again: 624 radix-sort launches, 5.3 of 106 ms per step (profiles/r2bb_launches_train_cfg2_summary.txt).
+# The sort of a column is kept for the rest of the step, keyed by the context tensor's storage, version counter and layout; FlowSequential.forward
+# empties the cache whenever a forward pass starts under autograd (begin_training_step), so a CUDA-graph capture pass -- which begins with its own
+# forward -- never reuses tensors sorted outside the capture, and an in-place update of the context (version bump) misses the cache.
+_CTX_SORT = {}
+
+
+def begin_training_step():
+    _CTX_SORT.clear()
+
+
+def _sorted_context(ctx, i, card):
+    key = (ctx.data_ptr(), ctx._version, tuple(ctx.shape), tuple(ctx.stride()), ctx.dtype, ctx.device, i, torch.cuda.is_current_stream_capturing())
+    hit = _CTX_SORT.get(key)
+    if hit is None:
+        col = ctx[:, i].contiguous()
+        srt, perm = torch.sort(col, stable=True)
+        hit = _CTX_SORT[key] = (srt, perm.contiguous(), {})
+    srt, perm, offs = hit
+    if card not in offs:
+        # bucket boundaries without a host synchronisation (torch.bincount sizes its output from the data): capturable in a CUDA graph
+        offs[card] = torch.searchsorted(srt, torch.arange(card + 1, device=ctx.device, dtype=srt.dtype)).contiguous()
+    return perm, offs[card]
+
+
 def embed_scatter(dc, ctx, tables):
     """Gradients of the embedding tables from dc (B, n_ctx * width): per feature a stable sort of the batch by context value (torch,
-    index preparation only) and one deterministic bucket-sum kernel."""
+    index preparation only; once per step and feature) and one deterministic bucket-sum kernel."""
     _need_cuda(dc, ctx); dc = _f32(dc)
     width = tables[0].shape[1]
     out = []
     for i, t in enumerate(tables):
         card = t.shape[0]
-        col = ctx[:, i].contiguous()
-        srt, perm = torch.sort(col, stable=True)
-        perm = perm.contiguous()
-        # bucket boundaries without a host synchronisation (torch.bincount sizes its output from the data): capturable in a CUDA graph
-        offsets = torch.searchsorted(srt, torch.arange(card + 1, device=dc.device, dtype=col.dtype)).contiguous()
+        perm, offsets = _sorted_context(ctx, i, card)
         dt = torch.empty((card, width), device=dc.device, dtype=torch.float32)
         _call('embed_scatter', (_p(dc), dc.shape[1], i * width, _p(perm), _p(offsets), _p(dt), card, width, _stream()))
         out.append(dt)

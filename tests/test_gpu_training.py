@@ -388,6 +388,37 @@ def test_context_mixture_backward_large_sample_fallback(fast, monkeypatch):
         assert_close(dc.cpu().numpy(), cd.grad.numpy(), 1e-3, 1e-4 * float(cd.grad.abs().max()), f'dc n={n}')
 
 
+def test_embed_scatter_sorts_a_context_column_once_per_step():
+    """ops.embed_scatter keeps the stable sort of a context column for the rest of the training step (every context-conditioned layer
+    scatters by the same column): a second call hits the cache, an in-place change of the context (version bump) or the start of the next
+    step (ops.begin_training_step, called by FlowSequential.forward under autograd) does not; results equal an index_add reference."""
+    B, width, cards = 257, 6, (5, 3)
+    ctx = torch.stack([synth.NoiseTape('es:c0').rand((B,)).mul(cards[0]).long().clamp(max=cards[0] - 1),
+                       synth.NoiseTape('es:c1').rand((B,)).mul(cards[1]).long().clamp(max=cards[1] - 1)], 1).cuda()
+    dc = synth.normal('es:dc', (B, 2 * width)).cuda()
+    tables = [torch.zeros(c, width, device='cuda') for c in cards]
+
+    def reference(cx):
+        out = []
+        for i, c in enumerate(cards):
+            out.append(torch.zeros(c, width, dtype=torch.float64, device='cuda').index_add_(0, cx[:, i], dc[:, i * width:(i + 1) * width].double()))
+        return out
+
+    ops.begin_training_step()
+    first = ops.embed_scatter(dc, ctx, tables)
+    assert len(ops._CTX_SORT) == 2
+    again = ops.embed_scatter(dc, ctx, tables)
+    assert len(ops._CTX_SORT) == 2 and all(torch.equal(a, b) for a, b in zip(first, again))
+    for got, want in zip(first, reference(ctx)):
+        assert_close(got.cpu().numpy(), want.cpu().numpy(), 1e-5, 1e-5, 'embed_scatter')
+    ctx[:, 0] = (ctx[:, 0] + 1) % cards[0]                      # in place: same storage, new version -> a fresh sort
+    moved = ops.embed_scatter(dc, ctx, tables)
+    for got, want in zip(moved, reference(ctx)):
+        assert_close(got.cpu().numpy(), want.cpu().numpy(), 1e-5, 1e-5, 'embed_scatter after an in-place context update')
+    ops.begin_training_step()
+    assert len(ops._CTX_SORT) == 0
+
+
 def test_unsupported_layers_raise_under_autograd():
     model = build_cuda_model(CASES['mnist_maf_onehot16']).train()     # --coupling maf specialists: the masked linear context block has no backward kernel
     x, ctx = case_inputs(CASES['mnist_maf_onehot16'])

@@ -12,7 +12,7 @@ dev = 'cuda'
 REPS, WARM = int(os.environ.get('REPS', 10)), int(os.environ.get('WARM', 3))
 ONLY = os.environ.get('ONLY', '')              # e.g. ONLY=k3: the 3x3 shapes only
 VARIANTS = [v for v in os.environ.get('VARIANTS', 'new,nopf,old').split(',') if v]
-ENV = {'new': {}, 'nopf': {'CFPP_BWD_DATA3': '2'}, 'old': {'CFPP_BWD_DATA3': '0', 'CFPP_CONV_ROWS': '0'}}
+ENV = {'new': {}, 'nopf': {'CFPP_BWD_DATA3': '2'}, 'nt256': {'CFPP_BWD_DATA3': '3'}, 'old': {'CFPP_BWD_DATA3': '0', 'CFPP_CONV_ROWS': '0'}}
 
 
 def timeit(fn, n=REPS):
